@@ -1,0 +1,143 @@
+/*
+ * mvster_b200.h - C ABI of libmvster_b200.so: the sm_100a implementation of the
+ * MVSTER per-frame forward hot path (homography warp -> epipolar-Transformer
+ * aggregation -> cost regularisation -> depth head).
+ *
+ * The reference (JeffWang987/MVSTER) is pure Python/PyTorch and has no FFI
+ * layer, so there is no existing binding to mirror; each entry point below
+ * names the reference Python function (file:line under the reference tree)
+ * whose arithmetic it replaces.  The Python-side binding a maintainer adds is
+ * shown in INTEGRATION.md (ctypes; mvster_b200/_lib.py is the working copy).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *    the caller owns all memory; the library never allocates device memory.
+ *  - all tensors are dense fp32.  Feature maps are channels-last:
+ *      feature  [B][H][W][C]          ("NHWC")
+ *      cost     [B][D][H][W][G]       ("NDHWC")
+ *      per-depth maps (hypo, logits, attn, wsum)   [B][D][H][W]
+ *      per-pixel maps (depth, conf, inv_min, inv_max) [B][H][W]
+ *  - every call is asynchronous on `stream` (a cudaStream_t / CUstream), is
+ *    re-entrant, and keeps no state besides a thread-local error string and a
+ *    monotonically increasing launch counter.
+ *  - return value: 0 = launched, negative = error (see mvster_last_error()).
+ */
+#ifndef MVSTER_B200_H_
+#define MVSTER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mvster_stream_t; /* cudaStream_t */
+
+#define MVSTER_OK 0
+#define MVSTER_ERR_ARG (-1)     /* unsupported shape / null pointer */
+#define MVSTER_ERR_CUDA (-2)    /* CUDA launch/runtime error */
+
+#define MVSTER_MAX_VIEWS 16     /* source views per mvster_et_fuse_f32 call */
+
+/* flags of mvster_et_fuse_f32 */
+#define MVSTER_ET_PARTIAL 1     /* write un-normalised acc + wsum (view-sharded run) */
+#define MVSTER_ET_ACCUMULATE 2  /* start from the acc/wsum already in cost/wsum */
+
+int mvster_version(void);                 /* 10000*major + 100*minor + patch */
+const char* mvster_last_error(void);      /* thread-local, never NULL */
+uint64_t mvster_launch_count(void);       /* kernels launched by this library so far (process-wide) */
+
+/* ---- hypotheses -------------------------------------------------------- */
+/* models/mvs4net_utils.py:71-77 init_inverse_range.  depth_values [B][n_dv]
+ * (only column 0 and n_dv-1 are read) -> hypo [B][D][H][W], far -> near. */
+int mvster_hypo_init_inverse_f32(const float* depth_values, int n_dv, float* hypo,
+                                 int B, int D, int H, int W, mvster_stream_t stream);
+
+/* models/mvs4net_utils.py:79-86 schedule_inverse_range.  inv_min/inv_max
+ * [B][H/2][W/2] -> hypo [B][D][H][W] (bilinear x2, align_corners, reciprocal). */
+int mvster_hypo_schedule_inverse_f32(const float* inv_min, const float* inv_max, float* hypo,
+                                     int B, int D, int H, int W, mvster_stream_t stream);
+
+/* ---- relative pose ------------------------------------------------------- */
+/* models/mvs4net_utils.py:1032-1035 (K @ E[:3,:4]) and :24 (src_proj @ inverse(ref_proj)).
+ * proj [B][Nv][2][4][4] (slot 0 extrinsic, slot 1 intrinsic; view 0 = reference)
+ * -> pose [B][V][12] (row-major R, then t) for source views first_view .. first_view+V-1. */
+int mvster_pose_f32(const float* proj, float* pose, int B, int Nv, int first_view, int V,
+                    mvster_stream_t stream);
+
+/* ---- fused homography warp + epipolar-Transformer aggregation ----------- */
+/* models/mvs4net_utils.py:13-59 (homo_warping) fused with :1037-1060 (group
+ * correlation, softmax over D / temp / sqrt(C), running weighted sum over source
+ * views, final division).
+ *   ref       [B][H][W][C]
+ *   src_host  HOST array of V device pointers, each [B][Hs][Ws][C]
+ *   pose      [B][V][12]: row-major 3x3 R then t of  src_proj @ inverse(ref_proj)
+ *             (the matrix of mvs4net_utils.py:24, computed by the caller)
+ *   hypo      [B][D][H][W]
+ *   cost      [B][D][H][W][G]   (normalised cost, or acc when MVSTER_ET_PARTIAL)
+ *   wsum      [B][D][H][W]      (required with PARTIAL / ACCUMULATE, else may be NULL)
+ * Supported: (C,G) in {(64,8),(32,8),(16,4),(8,4)} and any C==G*{1,2,4,8} with
+ * G in {4,8}; D in {4,8}; 1 <= V <= MVSTER_MAX_VIEWS. */
+int mvster_et_fuse_f32(const float* ref, const float* const* src_host, int V, const float* pose,
+                       const float* hypo, float* cost, float* wsum,
+                       int B, int C, int G, int D, int H, int W, int Hs, int Ws,
+                       float attn_temp, int flags, mvster_stream_t stream);
+
+/* cost[b,d,y,x,g] = acc / (1e-8 + wsum[b,d,y,x]) in place: the division of
+ * mvs4net_utils.py:1060 applied after the partials were all-reduced. */
+int mvster_et_normalize_f32(float* cost, const float* wsum, int B, int G, int D, int H, int W,
+                            mvster_stream_t stream);
+
+/* ---- regularisation ------------------------------------------------------ */
+/* Generic channels-last 3-D convolution layer with folded BN:
+ *   y = [relu](conv(x, w) + bias) [+ skip]
+ * x [B][Di][Hi][Wi][Cin], w [kd*kh*kw][Cin][Cout], bias [Cout] (may be NULL),
+ * y/skip [B][Do][Ho][Wo][Cout].  kernel (kd,3,3) with kd in {1,3}; pad = k/2;
+ * stride (sd,s,s).  transposed != 0: ConvTranspose3d(k, stride, padding=k/2,
+ * output_padding=stride-1), i.e. exact x2 up-sampling along strided axes.
+ * Replaces ConvBnReLU3D (mvs4net_utils.py:116-123) and the ConvTranspose3d+BN+ReLU
+ * sequences (:885-898, :926-940). */
+int mvster_conv3d_ndhwc_f32(const float* x, const float* w, const float* bias, const float* skip, float* y,
+                            int B, int Di, int Hi, int Wi, int Cin, int Cout,
+                            int kd, int stride_d, int stride_hw, int transposed, int relu,
+                            mvster_stream_t stream);
+
+/* reg2d U-Net (mvs4net_utils.py:870-912) up to, not including, the 1x1x1 `prob`
+ * layer: cost [B][D][H][W][G] -> feat8 [B][D][H][W][8].  `blob` holds the folded
+ * weights of conv0..conv11 in the layout reported by mvster_reg2d_layer_info;
+ * `workspace` must hold mvster_reg2d_workspace_floats() floats. */
+#define MVSTER_REG2D_LAYERS 10
+size_t mvster_reg2d_blob_floats(int G);
+size_t mvster_reg2d_workspace_floats(int B, int D, int H, int W);
+/* info_host[8] = {Cin, Cout, kd, stride_hw, transposed, w_offset, bias_offset, n_taps} */
+int mvster_reg2d_layer_info(int G, int layer, int64_t* info_host);
+int mvster_reg2d_f32(const float* blob, const float* cost, float* feat8, float* workspace,
+                     int B, int G, int D, int H, int W, mvster_stream_t stream);
+
+/* ---- head ---------------------------------------------------------------- */
+/* mvs4net_utils.py:1066-1088.  Either `logits` [B][D][H][W] is given, or
+ * (feat8 [B][D][H][W][8], prob_w[8], prob_b[1]) and the 1x1x1 `prob` conv of
+ * mvs4net_utils.py:900 is applied on the fly.  Outputs (any may be NULL):
+ *   attn [B][D][H][W] softmax over D;  depth [B][H][W] = hypo[argmax] (first max);
+ *   conf [B][H][W] = max prob (LOW resolution; see mvster_upsample_bilinear_f32);
+ *   inv_min/inv_max = 1/depth +- split_itv*(1/hypo[2]-1/hypo[1]);
+ *   soft_depth = sum_d attn*hypo (models/module.py:935-941, optional extra). */
+int mvster_head_f32(const float* logits, const float* feat8, const float* prob_w, const float* prob_b,
+                    const float* hypo, float* attn, float* depth, float* conf,
+                    float* inv_min, float* inv_max, float* soft_depth,
+                    int B, int D, int H, int W, float split_itv, mvster_stream_t stream);
+
+/* F.interpolate(mode='bilinear', align_corners=True) on [B][H][W] -> [B][H*f][W*f]
+ * (confidence up-sampling of mvs4net_utils.py:1076-1077). */
+int mvster_upsample_bilinear_f32(const float* in, float* out, int B, int H, int W, int factor,
+                                 mvster_stream_t stream);
+
+/* NCHW [B][C][H][W] -> NHWC [B][H][W][C] (feeds reference-layout features to the path). */
+int mvster_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W,
+                            mvster_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSTER_B200_H_ */

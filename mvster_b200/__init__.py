@@ -1,0 +1,7 @@
+"""mvster_b200 - sm_100a (B200) implementation of MVSTER's per-frame forward hot path behind
+the reference's ``models`` API: ``from mvster_b200 import MVS4net, MVS4net_loss, Blend_loss``.
+See DESIGN.md for scope and INTEGRATION.md for the drop-in recipe."""
+from .network import MVS4net  # noqa: F401
+from .losses import MVS4net_loss, Blend_loss  # noqa: F401
+
+__all__ = ["MVS4net", "MVS4net_loss", "Blend_loss"]

@@ -1,0 +1,230 @@
+"""Tensor-level wrappers over the C ABI: validate, take ``data_ptr()``s, launch on torch's
+current stream.  Layout conventions are those of include/mvster_b200.h (channels-last
+features, NDHWC cost volume).  CUDA tensors only - anything else raises."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+ET_PARTIAL = 1
+ET_ACCUMULATE = 2
+MAX_VIEWS = 16
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk(t: Tensor, name: str, shape: Optional[Sequence[int]] = None) -> Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.MvsterLibraryError(f"{name}: a CUDA tensor is required (the hot path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: float32 required, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous, got strides {t.stride()} for shape {tuple(t.shape)}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
+def to_nhwc(x: Tensor) -> Tensor:
+    """[B,C,H,W] (any strides) -> contiguous [B,H,W,C].  Free if x is already channels_last."""
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    if x.is_contiguous() and x.dtype == torch.float32 and x.is_cuda:
+        B, Cc, H, W = x.shape
+        out = torch.empty((B, H, W, Cc), device=x.device, dtype=x.dtype)
+        _lib.check(_lib.load().mvster_nchw_to_nhwc_f32(_ptr(x), _ptr(out), B, Cc, H, W, _stream()), "mvster_nchw_to_nhwc_f32")
+        return out
+    return v.contiguous()
+
+
+def hypo_init_inverse(depth_values: Tensor, D: int, H: int, W: int, out: Optional[Tensor] = None) -> Tensor:
+    dv = _chk(depth_values, "depth_values")
+    B, n = dv.shape
+    out = torch.empty((B, D, H, W), device=dv.device, dtype=torch.float32) if out is None else _chk(out, "hypo", (B, D, H, W))
+    _lib.check(_lib.load().mvster_hypo_init_inverse_f32(_ptr(dv), n, _ptr(out), B, D, H, W, _stream()),
+               "mvster_hypo_init_inverse_f32")
+    return out
+
+
+def hypo_schedule_inverse(inv_min: Tensor, inv_max: Tensor, D: int, H: int, W: int, out: Optional[Tensor] = None) -> Tensor:
+    B = inv_min.shape[0]
+    _chk(inv_min, "inv_min", (B, H // 2, W // 2))
+    _chk(inv_max, "inv_max", (B, H // 2, W // 2))
+    out = torch.empty((B, D, H, W), device=inv_min.device, dtype=torch.float32) if out is None else _chk(out, "hypo", (B, D, H, W))
+    _lib.check(_lib.load().mvster_hypo_schedule_inverse_f32(_ptr(inv_min), _ptr(inv_max), _ptr(out), B, D, H, W, _stream()),
+               "mvster_hypo_schedule_inverse_f32")
+    return out
+
+
+def pose(proj: Tensor, first_view: int = 1, n_views: Optional[int] = None) -> Tensor:
+    """proj [B,Nv,2,4,4] -> [B,V,12] relative poses (R row-major, t) of source views
+    first_view .. first_view+V-1 with respect to view 0."""
+    _chk(proj, "proj")
+    B, Nv = proj.shape[:2]
+    if tuple(proj.shape[2:]) != (2, 4, 4):
+        raise ValueError(f"proj: expected [B,Nv,2,4,4], got {tuple(proj.shape)}")
+    V = Nv - first_view if n_views is None else n_views
+    out = torch.empty((B, V, 12), device=proj.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_pose_f32(_ptr(proj), _ptr(out), B, Nv, first_view, V, _stream()), "mvster_pose_f32")
+    return out
+
+
+def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: int, attn_temp: float,
+            cost: Optional[Tensor] = None, wsum: Optional[Tensor] = None, partial: bool = False,
+            accumulate: bool = False) -> Tensor:
+    """ref [B,H,W,C], srcs V x [B,Hs,Ws,C], pose [B,V,12], hypo [B,D,H,W] -> cost [B,D,H,W,G].
+    With ``partial`` the un-normalised accumulators are written to (cost, wsum)."""
+    B, H, W, Cc = ref.shape
+    _chk(ref, "ref")
+    V = len(srcs)
+    D = hypo.shape[1]
+    _chk(hypo, "hypo", (B, D, H, W))
+    Hs, Ws = srcs[0].shape[1:3]
+    for i, s in enumerate(srcs):
+        _chk(s, f"src[{i}]", (B, Hs, Ws, Cc))
+    if cost is None:
+        cost = torch.empty((B, D, H, W, G), device=ref.device, dtype=torch.float32)
+    _chk(cost, "cost", (B, D, H, W, G))
+    if (partial or accumulate) and wsum is None:
+        wsum = torch.empty((B, D, H, W), device=ref.device, dtype=torch.float32)
+    if wsum is not None:
+        _chk(wsum, "wsum", (B, D, H, W))
+    lib = _lib.load()
+    for v0 in range(0, V, MAX_VIEWS):  # more than MAX_VIEWS views: chain launches through the partials
+        chunk = srcs[v0:v0 + MAX_VIEWS]
+        last = v0 + MAX_VIEWS >= V
+        flags = 0
+        if partial or not last:
+            flags |= ET_PARTIAL
+        if accumulate or v0 > 0:
+            flags |= ET_ACCUMULATE
+        if flags and wsum is None:
+            wsum = torch.empty((B, D, H, W), device=ref.device, dtype=torch.float32)
+        pose_c = _chk(pose[:, v0:v0 + len(chunk)].contiguous(), "pose", (B, len(chunk), 12))
+        arr = (C.c_void_p * len(chunk))(*[s.data_ptr() for s in chunk])
+        _lib.check(lib.mvster_et_fuse_f32(_ptr(ref), arr, len(chunk), _ptr(pose_c), _ptr(hypo), _ptr(cost), _ptr(wsum),
+                                          B, Cc, G, D, H, W, Hs, Ws, float(attn_temp), flags, _stream()),
+                   "mvster_et_fuse_f32")
+    if V > MAX_VIEWS and not partial:
+        et_normalize(cost, wsum)
+    return cost
+
+
+def et_normalize(cost: Tensor, wsum: Tensor) -> Tensor:
+    B, D, H, W, G = cost.shape
+    _chk(cost, "cost")
+    _chk(wsum, "wsum", (B, D, H, W))
+    _lib.check(_lib.load().mvster_et_normalize_f32(_ptr(cost), _ptr(wsum), B, G, D, H, W, _stream()), "mvster_et_normalize_f32")
+    return cost
+
+
+def conv3d_ndhwc(x: Tensor, w: Tensor, bias: Optional[Tensor], kd: int, stride_d: int = 1, stride_hw: int = 1,
+                 transposed: bool = False, relu: bool = True, skip: Optional[Tensor] = None) -> Tensor:
+    """x [B,D,H,W,Cin], w [kd*9,Cin,Cout] -> y [B,Do,Ho,Wo,Cout]."""
+    _chk(x, "x")
+    B, Di, Hi, Wi, Cin = x.shape
+    taps, cin2, Cout = w.shape
+    _chk(w, "w", (kd * 9, Cin, Cout))
+    if transposed:
+        Do, Ho, Wo = Di, 2 * Hi, 2 * Wi
+    else:
+        Do, Ho, Wo = (Di - 1) // stride_d + 1, (Hi - 1) // stride_hw + 1, (Wi - 1) // stride_hw + 1
+    y = torch.empty((B, Do, Ho, Wo, Cout), device=x.device, dtype=torch.float32)
+    if bias is not None:
+        _chk(bias, "bias", (Cout,))
+    if skip is not None:
+        _chk(skip, "skip", tuple(y.shape))
+    _lib.check(_lib.load().mvster_conv3d_ndhwc_f32(_ptr(x), _ptr(w), _ptr(bias), _ptr(skip), _ptr(y), B, Di, Hi, Wi, Cin, Cout,
+                                                   kd, stride_d, stride_hw, int(transposed), int(relu), _stream()),
+               "mvster_conv3d_ndhwc_f32")
+    return y
+
+
+def reg2d_layer_table(G: int) -> List[dict]:
+    lib = _lib.load()
+    n_layers = 10
+    out = []
+    for i in range(n_layers):
+        info = (C.c_int64 * 8)()
+        _lib.check(lib.mvster_reg2d_layer_info(G, i, info), "mvster_reg2d_layer_info")
+        out.append(dict(cin=info[0], cout=info[1], kd=info[2], stride=info[3], transposed=bool(info[4]),
+                        w_off=info[5], b_off=info[6], taps=info[7]))
+    return out
+
+
+def reg2d_blob_floats(G: int) -> int:
+    return int(_lib.load().mvster_reg2d_blob_floats(G))
+
+
+def reg2d_workspace_floats(B: int, D: int, H: int, W: int) -> int:
+    return int(_lib.load().mvster_reg2d_workspace_floats(B, D, H, W))
+
+
+def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """cost [B,D,H,W,G] -> feat8 [B,D,H,W,8] (everything of reg2d except the 1x1x1 prob layer)."""
+    _chk(cost, "cost")
+    _chk(blob, "blob")
+    B, D, H, W, G = cost.shape
+    need = reg2d_workspace_floats(B, D, H, W)
+    if workspace is None:
+        workspace = torch.empty(need, device=cost.device, dtype=torch.float32)
+    if workspace.numel() < need:
+        raise ValueError(f"workspace too small: {workspace.numel()} < {need} floats")
+    if blob.numel() != reg2d_blob_floats(G):
+        raise ValueError(f"blob has {blob.numel()} floats, expected {reg2d_blob_floats(G)} for G={G}")
+    out = torch.empty((B, D, H, W, 8), device=cost.device, dtype=torch.float32) if out is None else _chk(out, "feat8", (B, D, H, W, 8))
+    _lib.check(_lib.load().mvster_reg2d_f32(_ptr(blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W, _stream()),
+               "mvster_reg2d_f32")
+    return out
+
+
+def head(hypo: Tensor, split_itv: float, logits: Optional[Tensor] = None, feat8: Optional[Tensor] = None,
+         prob_w: Optional[Tensor] = None, prob_b: Optional[Tensor] = None, inverse: bool = True,
+         want_soft: bool = False) -> dict:
+    _chk(hypo, "hypo")
+    B, D, H, W = hypo.shape
+    if logits is not None:
+        _chk(logits, "logits", (B, D, H, W))
+    else:
+        _chk(feat8, "feat8", (B, D, H, W, 8))
+        _chk(prob_w, "prob_w", (8,))
+        _chk(prob_b, "prob_b", (1,))
+    dev = hypo.device
+    new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+    out = {"attn_weight": new(B, D, H, W), "depth": new(B, H, W), "conf_low": new(B, H, W)}
+    if inverse:
+        out["inverse_min_depth"] = new(B, H, W)
+        out["inverse_max_depth"] = new(B, H, W)
+    if want_soft:
+        out["soft_depth"] = new(B, H, W)
+    _lib.check(_lib.load().mvster_head_f32(_ptr(logits), _ptr(feat8), _ptr(prob_w), _ptr(prob_b), _ptr(hypo),
+                                           _ptr(out["attn_weight"]), _ptr(out["depth"]), _ptr(out["conf_low"]),
+                                           _ptr(out.get("inverse_min_depth")), _ptr(out.get("inverse_max_depth")),
+                                           _ptr(out.get("soft_depth")), B, D, H, W, float(split_itv), _stream()),
+               "mvster_head_f32")
+    return out
+
+
+def upsample_bilinear(x: Tensor, factor: int) -> Tensor:
+    _chk(x, "x")
+    B, H, W = x.shape
+    if factor == 1:
+        return x.clone()
+    out = torch.empty((B, H * factor, W * factor), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_upsample_bilinear_f32(_ptr(x), _ptr(out), B, H, W, factor, _stream()),
+               "mvster_upsample_bilinear_f32")
+    return out

@@ -1,0 +1,34 @@
+// Shared helpers for libmvster_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/mvster_b200.h"
+
+namespace mvster {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return MVSTER_ERR_CUDA;
+    }
+    count_launch();
+    return MVSTER_OK;
+}
+
+#define MVSTER_REQUIRE(cond, ...)            \
+    do {                                     \
+        if (!(cond)) {                       \
+            ::mvster::set_error(__VA_ARGS__); \
+            return MVSTER_ERR_ARG;           \
+        }                                    \
+    } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace mvster

@@ -1,0 +1,305 @@
+// Channels-last (NDHWC) 3-D convolution layers with folded BatchNorm on the CUDA cores (exact
+// fp32 FMA), and the reg2d U-Net driver built from them.
+//   ConvBnReLU3D                      models/mvs4net_utils.py:116-123
+//   ConvTranspose3d + BN + ReLU       models/mvs4net_utils.py:885-898
+//   reg2d.forward                     models/mvs4net_utils.py:902-912
+// This is the exact-fp32 path (bit-faithful to an fp32 FMA chain; it is what the parity tests
+// pin) and the path for the 4..8-channel full-resolution layers, which are HBM/L1-bandwidth
+// bound (12-24 FLOP/B).  One thread = one output voxel x COUT_T output channels; the layer's
+// weights for that channel slice sit in shared memory ([tap][cin][cout], warp-uniform
+// broadcast reads), activations are read straight from global/L1 with 128-bit loads (each
+// voxel's Cin channels are contiguous).
+#include "common.cuh"
+
+namespace mvster {
+
+struct ConvArgs {
+    const float* x; const float* w; const float* bias; const float* skip; float* y;
+    int B, Di, Hi, Wi, Do, Ho, Wo;
+    int cout, kd, sd, s, relu;
+};
+
+template <int CIN, int COUT_T>
+__global__ void __launch_bounds__(128) conv_fwd_kernel(const ConvArgs a) {
+    extern __shared__ __align__(16) float w_s[];  // [kd*9][CIN][COUT_T]
+    const int cg = blockIdx.y;                    // output-channel slice
+    const int taps = a.kd * 9;
+    for (int i = threadIdx.x; i < taps * CIN * COUT_T; i += blockDim.x) {
+        const int o = i % COUT_T, rest = i / COUT_T;  // rest = tap*CIN + cin
+        w_s[i] = __ldg(a.w + (long long)rest * a.cout + cg * COUT_T + o);
+    }
+    __syncthreads();
+    const long long nvox = (long long)a.B * a.Do * a.Ho * a.Wo;
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvox) return;
+    const int ox = (int)(v % a.Wo), oy = (int)((v / a.Wo) % a.Ho);
+    const int oz = (int)((v / ((long long)a.Wo * a.Ho)) % a.Do), b = (int)(v / ((long long)a.Wo * a.Ho * a.Do));
+
+    float acc[COUT_T];
+#pragma unroll
+    for (int o = 0; o < COUT_T; ++o) acc[o] = a.bias ? __ldg(a.bias + cg * COUT_T + o) : 0.f;
+
+    const int pz = a.kd / 2;
+    for (int kz = 0; kz < a.kd; ++kz) {
+        const int iz = oz * a.sd + kz - pz;
+        if ((unsigned)iz >= (unsigned)a.Di) continue;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * a.s + ky - 1;
+            if ((unsigned)iy >= (unsigned)a.Hi) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * a.s + kx - 1;
+                if ((unsigned)ix >= (unsigned)a.Wi) continue;
+                const float4* px = reinterpret_cast<const float4*>(
+                    a.x + ((((long long)b * a.Di + iz) * a.Hi + iy) * a.Wi + ix) * CIN);
+                const float* wt = w_s + ((kz * 3 + ky) * 3 + kx) * CIN * COUT_T;
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                    const float4 t = __ldg(px + c4);
+                    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float* wr = wt + (c4 * 4 + j) * COUT_T;
+#pragma unroll
+                        for (int o = 0; o < COUT_T; ++o) acc[o] = fmaf(tv[j], wr[o], acc[o]);
+                    }
+                }
+            }
+        }
+    }
+    const long long off = v * a.cout + cg * COUT_T;
+#pragma unroll
+    for (int o = 0; o < COUT_T; ++o) {
+        float r = acc[o];
+        if (a.relu) r = fmaxf(r, 0.f);
+        if (a.skip) r += __ldg(a.skip + off + o);  // skip is added AFTER the ReLU (:907-909)
+        acc[o] = r;
+    }
+    if constexpr (COUT_T % 4 == 0) {
+#pragma unroll
+        for (int o = 0; o < COUT_T; o += 4)
+            *reinterpret_cast<float4*>(a.y + off + o) = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
+    } else {
+#pragma unroll
+        for (int o = 0; o < COUT_T; ++o) a.y[off + o] = acc[o];
+    }
+}
+
+// ConvTranspose3d kernel (1,3,3), stride (1,2,2), padding (0,1,1), output_padding (0,1,1):
+// out[2i-1+ky][2j-1+kx] += in[i][j] * w[ky][kx].  One thread owns the 2x2 output quad whose
+// top-left input is (i,j): exactly the 9 (Cin x Cout) tap products, no parity branches.
+template <int CIN, int COUT_T>
+__global__ void __launch_bounds__(128) deconv_fwd_kernel(const ConvArgs a) {
+    extern __shared__ __align__(16) float w_s[];  // [9][CIN][COUT_T]
+    const int cg = blockIdx.y;
+    for (int i = threadIdx.x; i < 9 * CIN * COUT_T; i += blockDim.x) {
+        const int o = i % COUT_T, rest = i / COUT_T;
+        w_s[i] = __ldg(a.w + (long long)rest * a.cout + cg * COUT_T + o);
+    }
+    __syncthreads();
+    const long long nq = (long long)a.B * a.Di * a.Hi * a.Wi;
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int j = (int)(q % a.Wi), i = (int)((q / a.Wi) % a.Hi);
+    const long long bz = q / ((long long)a.Wi * a.Hi);  // b*Di + z
+    const bool right = j + 1 < a.Wi, down = i + 1 < a.Hi;
+
+    float acc[4][COUT_T];
+#pragma unroll
+    for (int o = 0; o < COUT_T; ++o) {
+        const float bv = a.bias ? __ldg(a.bias + cg * COUT_T + o) : 0.f;
+        acc[0][o] = acc[1][o] = acc[2][o] = acc[3][o] = bv;
+    }
+    const float4* p00 = reinterpret_cast<const float4*>(a.x + ((bz * a.Hi + i) * a.Wi + j) * CIN);
+    const float4* p01 = p00 + CIN / 4;
+    const float4* p10 = p00 + (long long)a.Wi * (CIN / 4);
+    const float4* p11 = p10 + CIN / 4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int c4 = 0; c4 < CIN / 4; ++c4) {
+        const float4 t00 = __ldg(p00 + c4);
+        const float4 t01 = right ? __ldg(p01 + c4) : zero;
+        const float4 t10 = down ? __ldg(p10 + c4) : zero;
+        const float4 t11 = (right && down) ? __ldg(p11 + c4) : zero;
+        const float v00[4] = {t00.x, t00.y, t00.z, t00.w}, v01[4] = {t01.x, t01.y, t01.z, t01.w};
+        const float v10[4] = {t10.x, t10.y, t10.z, t10.w}, v11[4] = {t11.x, t11.y, t11.z, t11.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int c = c4 * 4 + jj;
+            auto W = [&](int ky, int kx) { return w_s + ((ky * 3 + kx) * CIN + c) * COUT_T; };
+#pragma unroll
+            for (int o = 0; o < COUT_T; ++o) {
+                acc[0][o] = fmaf(v00[jj], W(1, 1)[o], acc[0][o]);
+                acc[1][o] = fmaf(v00[jj], W(1, 2)[o], fmaf(v01[jj], W(1, 0)[o], acc[1][o]));
+                acc[2][o] = fmaf(v00[jj], W(2, 1)[o], fmaf(v10[jj], W(0, 1)[o], acc[2][o]));
+                acc[3][o] = fmaf(v00[jj], W(2, 2)[o], fmaf(v01[jj], W(2, 0)[o],
+                            fmaf(v10[jj], W(0, 2)[o], fmaf(v11[jj], W(0, 0)[o], acc[3][o]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int oy = 2 * i + (k >> 1), ox = 2 * j + (k & 1);
+        const long long off = ((bz * a.Ho + oy) * a.Wo + ox) * a.cout + cg * COUT_T;
+#pragma unroll
+        for (int o = 0; o < COUT_T; ++o) {
+            float r = acc[k][o];
+            if (a.relu) r = fmaxf(r, 0.f);
+            if (a.skip) r += __ldg(a.skip + off + o);
+            acc[k][o] = r;
+        }
+        if constexpr (COUT_T % 4 == 0) {
+#pragma unroll
+            for (int o = 0; o < COUT_T; o += 4)
+                *reinterpret_cast<float4*>(a.y + off + o) = make_float4(acc[k][o], acc[k][o + 1], acc[k][o + 2], acc[k][o + 3]);
+        } else {
+#pragma unroll
+            for (int o = 0; o < COUT_T; ++o) a.y[off + o] = acc[k][o];
+        }
+    }
+}
+
+template <int CIN, int COUT_T>
+static int launch_conv(const ConvArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)a.kd * 9 * CIN * COUT_T * sizeof(float);
+    auto k = conv_fwd_kernel<CIN, COUT_T>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long n = (long long)a.B * a.Do * a.Ho * a.Wo;
+    k<<<dim3(ceil_div(n, 128), a.cout / COUT_T), 128, smem, st>>>(a);
+    return check_launch("conv_fwd_kernel");
+}
+
+template <int CIN, int COUT_T>
+static int launch_deconv(const ConvArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)9 * CIN * COUT_T * sizeof(float);
+    auto k = deconv_fwd_kernel<CIN, COUT_T>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long n = (long long)a.B * a.Di * a.Hi * a.Wi;
+    k<<<dim3(ceil_div(n, 128), a.cout / COUT_T), 128, smem, st>>>(a);
+    return check_launch("deconv_fwd_kernel");
+}
+
+template <int CIN>
+static int dispatch_cout(const ConvArgs& a, bool transposed, cudaStream_t st) {
+    if (transposed) {  // 4 accumulator sets per thread: keep the channel slice at 8
+        if (a.cout % 8 == 0) return launch_deconv<CIN, 8>(a, st);
+        set_error("mvster_conv3d_ndhwc_f32: transposed conv needs Cout %% 8 == 0 (got %d)", a.cout);
+        return MVSTER_ERR_ARG;
+    }
+    if (a.cout % 16 == 0) return launch_conv<CIN, 16>(a, st);
+    if (a.cout % 8 == 0) return launch_conv<CIN, 8>(a, st);
+    if (a.cout == 1) return launch_conv<CIN, 1>(a, st);
+    set_error("mvster_conv3d_ndhwc_f32: unsupported Cout=%d (1 or a multiple of 8)", a.cout);
+    return MVSTER_ERR_ARG;
+}
+
+static int run_conv(const float* x, const float* w, const float* bias, const float* skip, float* y,
+                    int B, int Di, int Hi, int Wi, int Cin, int Cout, int kd, int sd, int s, int transposed,
+                    int relu, cudaStream_t st) {
+    MVSTER_REQUIRE(x && w && y, "mvster_conv3d_ndhwc_f32: null pointer");
+    MVSTER_REQUIRE(B > 0 && Di > 0 && Hi > 0 && Wi > 0, "mvster_conv3d_ndhwc_f32: bad shape");
+    MVSTER_REQUIRE(kd == 1 || kd == 3, "mvster_conv3d_ndhwc_f32: kd=%d (1 or 3)", kd);
+    MVSTER_REQUIRE((sd == 1 || sd == 2) && (s == 1 || s == 2), "mvster_conv3d_ndhwc_f32: strides must be 1 or 2");
+    ConvArgs a;
+    a.x = x; a.w = w; a.bias = bias; a.skip = skip; a.y = y;
+    a.B = B; a.Di = Di; a.Hi = Hi; a.Wi = Wi;
+    a.cout = Cout; a.kd = kd; a.sd = sd; a.s = s; a.relu = relu;
+    if (transposed) {
+        MVSTER_REQUIRE(kd == 1 && sd == 1 && s == 2, "mvster_conv3d_ndhwc_f32: transposed supports kernel (1,3,3) stride (1,2,2) only");
+        a.Do = Di; a.Ho = 2 * Hi; a.Wo = 2 * Wi;
+    } else {
+        a.Do = (Di - 1) / sd + 1; a.Ho = (Hi - 1) / s + 1; a.Wo = (Wi - 1) / s + 1;  // pad = k/2, k = 3 (or 1 along D)
+    }
+    switch (Cin) {
+        case 4: return dispatch_cout<4>(a, transposed, st);
+        case 8: return dispatch_cout<8>(a, transposed, st);
+        case 16: return dispatch_cout<16>(a, transposed, st);
+        case 32: return dispatch_cout<32>(a, transposed, st);
+        case 64: return dispatch_cout<64>(a, transposed, st);
+    }
+    set_error("mvster_conv3d_ndhwc_f32: unsupported Cin=%d (4,8,16,32,64)", Cin);
+    return MVSTER_ERR_ARG;
+}
+
+// ---- reg2d layer table ----------------------------------------------------------------------
+struct Layer { int cin, cout, kd, s, transposed; };
+static void reg2d_layers(int G, Layer (&L)[MVSTER_REG2D_LAYERS]) {
+    const Layer t[MVSTER_REG2D_LAYERS] = {
+        {G, 8, 1, 1, 0},    // conv0  (1,3,3)
+        {8, 16, 1, 2, 0},   // conv1  (1,3,3) s2
+        {16, 16, 3, 1, 0},  // conv2  3x3x3
+        {16, 32, 1, 2, 0},  // conv3
+        {32, 32, 3, 1, 0},  // conv4
+        {32, 64, 1, 2, 0},  // conv5
+        {64, 64, 3, 1, 0},  // conv6
+        {64, 32, 1, 2, 1},  // conv7  transposed, + conv4
+        {32, 16, 1, 2, 1},  // conv9  transposed, + conv2
+        {16, 8, 1, 2, 1},   // conv11 transposed, + conv0
+    };
+    for (int i = 0; i < MVSTER_REG2D_LAYERS; ++i) L[i] = t[i];
+}
+
+}  // namespace mvster
+
+using namespace mvster;
+
+extern "C" int mvster_conv3d_ndhwc_f32(const float* x, const float* w, const float* bias, const float* skip, float* y,
+                                       int B, int Di, int Hi, int Wi, int Cin, int Cout,
+                                       int kd, int stride_d, int stride_hw, int transposed, int relu,
+                                       mvster_stream_t stream) {
+    return run_conv(x, w, bias, skip, y, B, Di, Hi, Wi, Cin, Cout, kd, stride_d, stride_hw, transposed, relu,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int mvster_reg2d_layer_info(int G, int layer, int64_t* info) {
+    MVSTER_REQUIRE(info && layer >= 0 && layer < MVSTER_REG2D_LAYERS, "mvster_reg2d_layer_info: bad layer %d", layer);
+    Layer L[MVSTER_REG2D_LAYERS];
+    reg2d_layers(G, L);
+    int64_t off = 0;
+    for (int i = 0; i <= layer; ++i) {
+        const int64_t taps = L[i].kd * 9, nw = taps * L[i].cin * L[i].cout;
+        if (i == layer) {
+            info[0] = L[i].cin; info[1] = L[i].cout; info[2] = L[i].kd; info[3] = L[i].s; info[4] = L[i].transposed;
+            info[5] = off; info[6] = off + nw; info[7] = taps;
+        }
+        off += nw + L[i].cout;
+    }
+    return MVSTER_OK;
+}
+
+extern "C" size_t mvster_reg2d_blob_floats(int G) {
+    int64_t info[8];
+    if (mvster_reg2d_layer_info(G, MVSTER_REG2D_LAYERS - 1, info) != MVSTER_OK) return 0;
+    return (size_t)(info[6] + info[1]);
+}
+
+// activations (floats, N = B*D*H*W): c0 8N | c1 4N | c2 4N | c3 2N | c4 2N | c5 N | c6 N | u7 2N | u9 4N  = 28N
+extern "C" size_t mvster_reg2d_workspace_floats(int B, int D, int H, int W) {
+    return (size_t)28 * B * D * H * W;
+}
+
+extern "C" int mvster_reg2d_f32(const float* blob, const float* cost, float* feat8, float* ws,
+                                int B, int G, int D, int H, int W, mvster_stream_t stream) {
+    MVSTER_REQUIRE(blob && cost && feat8 && ws, "mvster_reg2d_f32: null pointer");
+    MVSTER_REQUIRE(G == 4 || G == 8 || G == 16 || G == 32 || G == 64, "mvster_reg2d_f32: unsupported G=%d", G);
+    MVSTER_REQUIRE(H % 8 == 0 && W % 8 == 0, "mvster_reg2d_f32: H,W must be multiples of 8 (got %dx%d)", H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    Layer L[MVSTER_REG2D_LAYERS];
+    reg2d_layers(G, L);
+    const size_t N = (size_t)B * D * H * W;
+    float* c0 = ws;           float* c1 = c0 + 8 * N;  float* c2 = c1 + 4 * N;  float* c3 = c2 + 4 * N;
+    float* c4 = c3 + 2 * N;   float* c5 = c4 + 2 * N;  float* c6 = c5 + N;      float* u7 = c6 + N;
+    float* u9 = u7 + 2 * N;
+    const float* in[MVSTER_REG2D_LAYERS] = {cost, c0, c1, c2, c3, c4, c5, c6, u7, u9};
+    float* out[MVSTER_REG2D_LAYERS] = {c0, c1, c2, c3, c4, c5, c6, u7, u9, feat8};
+    const float* skip[MVSTER_REG2D_LAYERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c4, c2, c0};
+    const int div[MVSTER_REG2D_LAYERS] = {1, 1, 2, 2, 4, 4, 8, 8, 4, 2};  // input resolution divisor
+    for (int i = 0; i < MVSTER_REG2D_LAYERS; ++i) {
+        int64_t info[8];
+        mvster_reg2d_layer_info(G, i, info);
+        const int rc = run_conv(in[i], blob + info[5], blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i],
+                                L[i].cin, L[i].cout, L[i].kd, 1, L[i].s, L[i].transposed, 1, st);
+        if (rc != MVSTER_OK) return rc;
+    }
+    return MVSTER_OK;
+}

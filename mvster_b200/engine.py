@@ -1,0 +1,110 @@
+"""Inference engine: drives the 4-stage cascade (MVS4Net.py:78-105) through the C ABI.
+
+One engine per CUDA device.  It owns the folded/packed regulariser weights for that device
+and nothing else; feature extraction (FPN4, outside the named hot path) runs through the
+module's own ``feature`` sub-module in channels-last memory format so its outputs are
+already the NHWC tensors the kernels consume.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import capi, packing
+
+Tensor = torch.Tensor
+
+
+class StagePlan:
+    """Static per-stage configuration lifted from the module."""
+
+    def __init__(self, k: int, net):
+        self.k = k
+        self.D = net.stage_splits[k]
+        self.G = net.group_cor_dim[k]
+        self.split_itv = float(net.depth_interals_ratio[k])
+        self.up = 2 ** (net.num_stage - 1 - k)  # confidence up-sampling factor, mvs4net_utils.py:1077 (3 - stage_idx)
+
+
+def check_supported(net) -> None:
+    bad = []
+    if net.reg_net != "reg2d":
+        bad.append("reg_net='reg3d'")
+    if not net.group_cor:
+        bad.append("group_cor=False")
+    if not net.inverse_depth:
+        bad.append("inverse_depth=False")
+    if not net.stagenet.attn_fuse_d:
+        bad.append("attn_fuse_d=False")
+    if net.num_stage != 4:
+        bad.append(f"num_stage={net.num_stage}")
+    if bad:
+        raise NotImplementedError("the CUDA inference path does not cover: " + ", ".join(bad) +
+                                  " (shipped config: reg2d, group_cor, inverse_depth, attn_fuse_d, 4 stages)")
+
+
+class InferenceEngine:
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.weights_version = -1
+        self.stage_weights: List[Dict[str, Tensor]] = []
+        self.plans: List[StagePlan] = []
+
+    # ------------------------------------------------------------------ weights
+    def refresh_weights(self, net) -> None:
+        check_supported(net)
+        sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("reg.")}
+        self.plans = [StagePlan(k, net) for k in range(net.num_stage)]
+        self.stage_weights = []
+        with torch.cuda.device(self.device):
+            for p in self.plans:
+                packed = packing.pack_reg2d(sd, f"reg.{p.k}", capi.reg2d_layer_table(p.G))
+                self.stage_weights.append({k: v.to(self.device) for k, v in packed.items()})
+
+    # ------------------------------------------------------------------ full forward
+    def forward(self, net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor) -> Dict:
+        B = imgs[0].shape[0]
+        nv = len(imgs)
+        with torch.cuda.device(self.device):
+            x = torch.cat(list(imgs), 0).contiguous(memory_format=torch.channels_last)
+            pyramid = net.feature(x)  # {stage: [nv*B, C, h, w]}, channels-last strides
+            feats = []
+            for k in range(net.num_stage):
+                f = capi.to_nhwc(pyramid[f"stage{k + 1}"])  # [nv*B, h, w, C]
+                feats.append([f[v * B:(v + 1) * B] for v in range(nv)])
+            return self.run_cascade(net, feats, proj_matrices, depth_values)
+
+    # ------------------------------------------------------------------ the hot path
+    def run_cascade(self, net, feats: List[List[Tensor]], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
+                    attn_temp: Optional[float] = None) -> Dict:
+        """feats[k][v]: NHWC feature of view v at stage k (view 0 = reference)."""
+        temp = float(net.stagenet.attn_temp if attn_temp is None else attn_temp)
+        outputs: Dict = {}
+        prev = None
+        dv = depth_values.to(device=self.device, dtype=torch.float32).contiguous()
+        for p, wts in zip(self.plans, self.stage_weights):
+            key = f"stage{p.k + 1}"
+            ref, srcs = feats[p.k][0], feats[p.k][1:]
+            B, H, W, C = ref.shape
+            proj = proj_matrices[key].to(device=self.device, dtype=torch.float32).contiguous()
+            if p.k == 0:
+                hypo = capi.hypo_init_inverse(dv, p.D, H, W)
+            else:
+                hypo = capi.hypo_schedule_inverse(prev["inverse_min_depth"], prev["inverse_max_depth"], p.D, H, W)
+            pose = capi.pose(proj)
+            cost = capi.et_fuse(ref, srcs, pose, hypo, p.G, temp)
+            feat8 = capi.reg2d(wts["blob"], cost)
+            h = capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=True)
+            out = {"depth": h["depth"],
+                   "photometric_confidence": capi.upsample_bilinear(h["conf_low"], p.up),
+                   "hypo_depth": hypo,
+                   "attn_weight": h["attn_weight"],
+                   "inverse_min_depth": h["inverse_min_depth"],
+                   "inverse_max_depth": h["inverse_max_depth"]}
+            if net.mono:
+                out["mono_feat"] = ref.permute(0, 3, 1, 2)  # [B,C,H,W] view, as mvs4net_utils.py:1092
+            prev = out
+            outputs[key] = out
+            outputs.update(out)
+        return outputs

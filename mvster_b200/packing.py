@@ -1,0 +1,60 @@
+"""Host-side weight preparation for the C ABI: fold eval-mode BatchNorm into the preceding
+(transposed) convolution and lay the kernels out as ``[tap][Cin][Cout]`` fp32.
+
+conv -> BN(eval):  y = (conv(x, w) - mean) / sqrt(var + eps) * gamma + beta
+                     = conv(x, w * s) + (beta - mean * s),   s = gamma / sqrt(var + eps)
+(mvs4net_utils.py:116-123, :885-898; eps = 1e-5, the nn.BatchNorm3d default).
+"""
+from __future__ import annotations
+
+from typing import Dict, Mapping, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+BN_EPS = 1e-5
+
+
+def bn_scale_shift(sd: Mapping[str, Tensor], p: str) -> Tuple[Tensor, Tensor]:
+    s = sd[p + ".weight"].double() / torch.sqrt(sd[p + ".running_var"].double() + BN_EPS)
+    return s, sd[p + ".bias"].double() - sd[p + ".running_mean"].double() * s
+
+
+def fold_conv3d(w: Tensor, scale: Tensor, shift: Tensor) -> Tuple[Tensor, Tensor]:
+    """Conv3d weight [Cout,Cin,kd,kh,kw] -> ([kd*kh*kw, Cin, Cout], [Cout]) fp32."""
+    wf = w.double() * scale.view(-1, 1, 1, 1, 1)
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    return wf.permute(2, 3, 4, 1, 0).reshape(taps, w.shape[1], w.shape[0]).float().contiguous(), shift.float().contiguous()
+
+
+def fold_deconv3d(w: Tensor, scale: Tensor, shift: Tensor) -> Tuple[Tensor, Tensor]:
+    """ConvTranspose3d weight [Cin,Cout,kd,kh,kw] -> ([kd*kh*kw, Cin, Cout], [Cout]) fp32."""
+    wf = w.double() * scale.view(1, -1, 1, 1, 1)
+    taps = w.shape[2] * w.shape[3] * w.shape[4]
+    return wf.permute(2, 3, 4, 0, 1).reshape(taps, w.shape[0], w.shape[1]).float().contiguous(), shift.float().contiguous()
+
+
+REG2D_ORDER = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11")
+
+
+def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, Tensor]:
+    """Pack one reg2d's state (keys ``{prefix}.conv0.conv.weight`` ...) into the blob layout
+    reported by ``mvster_reg2d_layer_info`` (``layer_table`` = capi.reg2d_layer_table(G)).
+    Returns {'blob': 1-D fp32, 'prob_w': [8], 'prob_b': [1]} on the CPU."""
+    total = layer_table[-1]["b_off"] + layer_table[-1]["cout"]
+    blob = torch.zeros(total, dtype=torch.float32)
+    for name, L in zip(REG2D_ORDER, layer_table):
+        p = f"{prefix}.{name}"
+        if L["transposed"]:
+            s, t = bn_scale_shift(sd, p + ".1")
+            w, b = fold_deconv3d(sd[p + ".0.weight"].detach().cpu(), s.cpu(), t.cpu())
+        else:
+            s, t = bn_scale_shift(sd, p + ".bn")
+            w, b = fold_conv3d(sd[p + ".conv.weight"].detach().cpu(), s.cpu(), t.cpu())
+        if tuple(w.shape) != (L["taps"], L["cin"], L["cout"]):
+            raise ValueError(f"{p}: packed shape {tuple(w.shape)} != layer table {(L['taps'], L['cin'], L['cout'])}")
+        blob[L["w_off"]:L["w_off"] + w.numel()] = w.reshape(-1)
+        blob[L["b_off"]:L["b_off"] + b.numel()] = b
+    return {"blob": blob,
+            "prob_w": sd[prefix + ".prob.weight"].detach().cpu().reshape(-1).float().contiguous(),
+            "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}

@@ -1,0 +1,150 @@
+"""CPU-side tests: module mirror (state_dict, autograd path, losses), weight folding/packing and the
+C-ABI surface (library loads, exports every symbol declared in include/mvster_b200.h).  No GPU compute."""
+import ctypes
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import GOLDEN, GOLDEN_CASES, REPO, SHIPPED, build_model, load_golden, oracle
+
+from mvster_b200 import Blend_loss, MVS4net, MVS4net_loss, _lib, packing
+
+
+def test_header_symbols_exported_and_bound():
+    header = (REPO / "include" / "mvster_b200.h").read_text()
+    declared = set(re.findall(r"\b(mvster_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = _lib.load()  # raises if the .so is missing: the build is part of the contract
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported"
+    assert lib.mvster_version() >= 100
+    assert isinstance(lib.mvster_last_error(), bytes)
+
+
+def test_c_abi_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    rc = lib.mvster_reg2d_layer_info(8, 99, (ctypes.c_int64 * 8)())
+    assert rc == -1 and b"bad layer" in lib.mvster_last_error()
+    info = (ctypes.c_int64 * 8)()
+    assert lib.mvster_reg2d_layer_info(8, 6, info) == 0
+    assert list(info)[:5] == [64, 64, 3, 1, 0] and info[7] == 27
+    # blob = sum over layers of taps*cin*cout + cout
+    tbl = [(8, 8, 9), (8, 16, 9), (16, 16, 27), (16, 32, 9), (32, 32, 27), (32, 64, 9), (64, 64, 27), (64, 32, 9), (32, 16, 9), (16, 8, 9)]
+    assert lib.mvster_reg2d_blob_floats(8) == sum(t * a * b + b for a, b, t in tbl)
+    with pytest.raises(_lib.MvsterLibraryError):
+        _lib.check(-1, "probe")
+
+
+def test_inference_on_cpu_raises_instead_of_falling_back():
+    m = build_model(SHIPPED, 1)
+    z, imgs, proj, dv = load_golden("shipped_b2_v2_64x64")
+    with torch.no_grad(), pytest.raises(_lib.MvsterLibraryError):
+        m(imgs, proj, dv)
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_autograd_path_matches_reference_eval(name):
+    """The differentiable PyTorch formulation (training path), run in eval mode with grad enabled."""
+    z, imgs, proj, dv = load_golden(name)
+    m = build_model(GOLDEN_CASES[name], int(z["meta_seed"]))
+    out = m._forward_autograd(imgs, proj, dv)
+    for s in range(1, 5):
+        st = out[f"stage{s}"]
+        ref_attn = torch.from_numpy(z[f"s{s}_attn_weight"])
+        assert (st["attn_weight"] - ref_attn).abs().max().item() < 5e-6
+        d, rd = st["depth"].detach(), torch.from_numpy(z[f"s{s}_depth"])
+        assert ((d - rd).abs() > 1e-4 * rd.abs()).float().mean().item() < 0.02  # argmax near-ties only
+        assert st["photometric_confidence"].shape == tuple(z[f"s{s}_photometric_confidence"].shape)
+
+
+def test_training_mode_forward_and_backward():
+    z = np.load(GOLDEN / "train_mode.npz")
+    g, imgs, proj, dv = load_golden("shipped_b1_v3_64x128")
+    m = build_model(SHIPPED, int(g["meta_seed"])).train()
+    for mod in m.modules():
+        if isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+            mod.eval()
+    out = m(imgs[:2], proj_sub(proj, 2), dv)
+    for s in range(1, 5):
+        assert (out[f"stage{s}"]["attn_weight"].detach() - torch.from_numpy(z[f"s{s}_attn_weight"])).abs().max() < 5e-6
+        if s > 1:
+            md, rmd = out[f"stage{s}"]["mono_depth"].detach(), torch.from_numpy(z[f"s{s}_mono_depth"])
+            assert (md - rmd).abs().max() < 1e-3 * rmd.abs().max()
+        assert out[f"stage{s}"]["photometric_confidence"].item() == 0.0
+    loss = sum(out[f"stage{s}"]["attn_weight"].pow(2).mean() for s in range(1, 5))
+    loss.backward()
+    assert m.reg[3].conv0.conv.weight.grad is not None and m.feature.conv0[0].conv.weight.grad.abs().sum() > 0
+
+
+def proj_sub(proj, nv):
+    return {k: v[:, :nv].contiguous() for k, v in proj.items()}
+
+
+def test_losses_match_reference():
+    z = np.load(GOLDEN / "losses.npz")
+    g, imgs, proj, dv = load_golden("shipped_b1_v3_64x128")
+    stages = {}
+    for s in range(1, 5):
+        stages[f"stage{s}"] = {k: torch.from_numpy(g[f"s{s}_{k}"]) for k in ("depth", "hypo_depth", "attn_weight")}
+    gt = {f"stage{s}": torch.from_numpy(z[f"gt_stage{s}"]) for s in range(1, 5)}
+    mask = {f"stage{s}": torch.from_numpy(z[f"mask_stage{s}"]) for s in range(1, 5)}
+    for tag, kw in (("disc", dict(inverse_depth=True, ot_iter=3, ot_eps=1, ot_continous=False)),
+                    ("cont", dict(inverse_depth=True, ot_iter=5, ot_eps=0.5, ot_continous=True, stage_lw=[1, 2, 3, 4]))):
+        total, l1, ot, oor = MVS4net_loss(stages, gt, mask, **kw)
+        assert abs(total.item() - float(z[f"{tag}_total"])) <= 1e-5 * abs(float(z[f"{tag}_total"]))
+        assert np.allclose([x.item() for x in ot], z[f"{tag}_ot"], rtol=1e-5)
+        assert np.allclose([x.item() for x in oor], z[f"{tag}_oor"], rtol=1e-6)
+    res = Blend_loss(stages, gt, mask, inverse_depth=True, depth_max=torch.tensor([935.0]), depth_min=torch.tensor([425.0]))
+    assert abs(res[0].item() - float(z["blend_total"])) <= 1e-5 * abs(float(z["blend_total"]))
+    assert np.allclose([res[4].item(), res[5].item(), res[6].item()], z["blend_metrics"], rtol=1e-5)
+
+
+def test_bn_folding_and_packing_against_oracle():
+    """Folded [tap][Cin][Cout] weights reproduce conv+BN(+ReLU) of the oracle for a conv and a transposed layer."""
+    m = build_model(SHIPPED, 3)
+    sd = m.state_dict()
+    x = torch.randn(1, 16, 3, 6, 8)
+    s, t = packing.bn_scale_shift(sd, "reg.0.conv2.bn")
+    w, b = packing.fold_conv3d(sd["reg.0.conv2.conv.weight"], s, t)
+    assert w.shape == (27, 16, 16)
+    w_t = w.reshape(3, 3, 3, 16, 16).permute(4, 3, 0, 1, 2).contiguous()
+    mine = F.relu(F.conv3d(x, w_t, b, 1, 1))
+    assert torch.allclose(mine, oracle._cbr3(x, sd, "reg.0.conv2"), atol=2e-6)
+    x = torch.randn(1, 64, 2, 3, 4)
+    s, t = packing.bn_scale_shift(sd, "reg.0.conv7.1")
+    w, b = packing.fold_deconv3d(sd["reg.0.conv7.0.weight"], s, t)
+    assert w.shape == (9, 64, 32)
+    w_t = w.reshape(1, 3, 3, 64, 32).permute(3, 4, 0, 1, 2).contiguous()
+    mine = F.relu(F.conv_transpose3d(x, w_t, b, (1, 2, 2), (0, 1, 1), (0, 1, 1)))
+    assert torch.allclose(mine, oracle._up3(x, sd, "reg.0.conv7", (1, 2, 2), (0, 1, 1), (0, 1, 1)), atol=2e-6)
+
+
+def test_pack_reg2d_blob_layout():
+    from mvster_b200 import capi
+    m = build_model(SHIPPED, 3)
+    tbl = capi.reg2d_layer_table(4)
+    packed = packing.pack_reg2d(m.state_dict(), "reg.3", tbl)
+    assert packed["blob"].numel() == capi.reg2d_blob_floats(4)
+    assert packed["prob_w"].shape == (8,) and packed["prob_b"].shape == (1,)
+    L = tbl[2]
+    w = packed["blob"][L["w_off"]:L["w_off"] + 27 * 16 * 16].reshape(27, 16, 16)
+    s, t = packing.bn_scale_shift(m.state_dict(), "reg.3.conv2.bn")
+    ref_w, ref_b = packing.fold_conv3d(m.state_dict()["reg.3.conv2.conv.weight"], s, t)
+    assert torch.equal(w, ref_w) and torch.equal(packed["blob"][L["b_off"]:L["b_off"] + 16], ref_b)
+
+
+def test_dropin_models_package_exports_reference_names():
+    import importlib
+    import sys
+    sys.path.insert(0, str(REPO / "dropin"))
+    try:
+        sys.modules.pop("models", None)
+        models = importlib.import_module("models")
+        assert models.MVS4net is MVS4net and models.MVS4net_loss is MVS4net_loss and models.Blend_loss is Blend_loss
+    finally:
+        sys.path.remove(str(REPO / "dropin"))
+        sys.modules.pop("models", None)

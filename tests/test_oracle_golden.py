@@ -1,0 +1,80 @@
+"""The CPU oracle (oracle/mvster_oracle.py) against fixtures produced by the unmodified reference
+(oracle/make_golden.py).  The oracle uses the same ATen primitives in the same order, so agreement
+is expected to be bit-exact; a 1e-6 relative slack is allowed for thread-count-dependent conv blocking."""
+import numpy as np
+import pytest
+import torch
+
+from util import GOLDEN, GOLDEN_CASES, build_model, load_golden, oracle, oracle_cfg
+
+RTOL = 1e-6
+
+
+def _close(a: torch.Tensor, b: np.ndarray, what: str, rtol=RTOL, atol=0.0):
+    b = torch.from_numpy(np.asarray(b))
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    err = (a - b).abs().max().item()
+    lim = atol + rtol * b.abs().max().item()
+    assert err <= lim, f"{what}: max abs err {err:.3e} > {lim:.3e}"
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_cascade_matches_reference(name):
+    kwargs = GOLDEN_CASES[name]
+    z, imgs, proj, dv = load_golden(name)
+    sd = build_model(kwargs, int(z["meta_seed"])).state_dict()
+    out = oracle.cascade_forward(sd, oracle_cfg(kwargs), imgs, proj, dv)
+    for s in range(1, 5):
+        st = out[f"stage{s}"]
+        # teacher-free comparison is meaningful because the oracle replays the very same ATen calls
+        _close(st["cost"], z[f"s{s}_cost"], f"{name} stage{s} cost", atol=1e-7)
+        _close(st["hypo_depth"], z[f"s{s}_hypo_depth"], f"{name} stage{s} hypo")
+        _close(st["attn_weight"], z[f"s{s}_attn_weight"], f"{name} stage{s} attn", atol=1e-7)
+        _close(st["depth"], z[f"s{s}_depth"], f"{name} stage{s} depth")
+        _close(st["photometric_confidence"], z[f"s{s}_photometric_confidence"], f"{name} stage{s} conf", atol=1e-7)
+        if f"s{s}_inverse_min_depth" in z.files:
+            _close(st["inverse_min_depth"], z[f"s{s}_inverse_min_depth"], f"{name} stage{s} inv_min")
+            _close(st["inverse_max_depth"], z[f"s{s}_inverse_max_depth"], f"{name} stage{s} inv_max")
+
+
+def test_fpn_matches_reference():
+    name = "shipped_b1_v3_64x128"
+    z, imgs, proj, dv = load_golden(name)
+    sd = build_model(GOLDEN_CASES[name], int(z["meta_seed"])).state_dict()
+    with torch.no_grad():
+        f = oracle.fpn4_features(sd, imgs[0])
+    for s in range(1, 5):
+        _close(f[f"stage{s}"], z[f"fpn_view0_stage{s}"], f"fpn stage{s}", atol=1e-6)
+
+
+def test_warp_edge_cases():
+    z = np.load(GOLDEN / "warp_edge.npz")
+    out = oracle.plane_sweep_warp(torch.from_numpy(z["src"]), torch.from_numpy(z["src_proj"]),
+                                  torch.from_numpy(z["ref_proj"]), torch.from_numpy(z["hypo"]))
+    ref = torch.from_numpy(z["warped"])
+    assert torch.isfinite(ref).all()
+    assert (ref == 0).float().mean() > 0.2, "fixture should exercise out-of-bounds taps"
+    _close(out, z["warped"], "warp edge", rtol=0, atol=1e-6)
+
+
+def test_partial_sums_equal_full_aggregate():
+    """View-sharding identity: sum of per-shard partials, normalised once, == serial loop."""
+    name = "shipped_b1_v3_64x128"
+    z, imgs, proj, dv = load_golden(name)
+    sd = build_model(GOLDEN_CASES[name], int(z["meta_seed"])).state_dict()
+    with torch.no_grad():
+        feats = [oracle.fpn4_features(sd, im)["stage2"] for im in imgs]
+        hypo = torch.from_numpy(z["s2_hypo_depth"])
+        cams = proj["stage2"]
+        full = oracle.et_aggregate(feats, cams, hypo, True, 8, 2.0)
+        a1, w1 = oracle.et_aggregate(feats, cams, hypo, True, 8, 2.0, views=[1], partial=True)
+        a2, w2 = oracle.et_aggregate(feats, cams, hypo, True, 8, 2.0, views=[2], partial=True)
+        merged = oracle.et_normalize(a1 + a2, w1 + w2)
+    assert (merged - full).abs().max().item() <= 1e-6 * full.abs().max().item()
+
+
+def test_soft_depth_regression_formula():
+    p = torch.softmax(torch.randn(2, 5, 3, 4), 1)
+    d = torch.linspace(1, 2, 5).view(1, 5).repeat(2, 1)
+    ref = (p * d.view(2, 5, 1, 1)).sum(1)
+    assert torch.allclose(oracle.soft_depth_regression(p, d), ref)

@@ -1,0 +1,58 @@
+"""Shared helpers for the test-suite (the only place besides bench/smoke allowed to touch oracle/)."""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+GOLDEN = REPO / "tests" / "golden"
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+
+from mvster_b200 import MVS4net, synth  # noqa: E402
+from oracle import mvster_oracle as oracle  # noqa: E402
+
+SHIPPED = dict(reg_net="reg2d", group_cor=True, group_cor_dim=[8, 8, 4, 4], inverse_depth=True, mono=True, attn_temp=2)
+
+GOLDEN_CASES = {
+    "shipped_b1_v3_64x128": SHIPPED,
+    "shipped_b2_v2_64x64": SHIPPED,
+    "reg3d_b1_v2_64x64": dict(reg_net="reg3d", group_cor=True, group_cor_dim=[8, 8, 4, 4], inverse_depth=True, attn_temp=2),
+    "plain_b1_v2_64x64": dict(reg_net="reg2d", group_cor=False, inverse_depth=False, attn_fuse_d=False, attn_temp=2),
+}
+
+
+def oracle_cfg(kwargs: dict) -> dict:
+    cfg = dict(oracle.DEFAULT_CFG)
+    cfg.update(reg_net=kwargs.get("reg_net", "reg2d"), group_cor=kwargs.get("group_cor", False),
+               group_cor_dim=kwargs.get("group_cor_dim", [8, 8, 8, 8]), inverse_depth=kwargs.get("inverse_depth", False),
+               attn_temp=float(kwargs.get("attn_temp", 2)), attn_fuse_d=kwargs.get("attn_fuse_d", True),
+               mono=kwargs.get("mono", False))
+    return cfg
+
+
+def build_model(kwargs: dict, seed: int) -> MVS4net:
+    """Our module with the deterministic synthetic weights of mvster_b200.synth (same as the golden script)."""
+    torch.manual_seed(0)
+    m = MVS4net(**kwargs)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(synth.synthetic_state(shapes, seed), strict=True)
+    return m.eval()
+
+
+def load_golden(name: str):
+    z = np.load(GOLDEN / f"{name}.npz")
+    nv = int(z["meta_Nv"])
+    imgs = [torch.from_numpy(z[f"img{v}"]) for v in range(nv)]
+    proj = {f"stage{s}": torch.from_numpy(z[f"proj_stage{s}"]) for s in range(1, 5)}
+    dv = torch.from_numpy(z["depth_values"])
+    return z, imgs, proj, dv
+
+
+def top2_gap(attn: torch.Tensor) -> torch.Tensor:
+    """Difference between the two largest probabilities over D: [B,D,H,W] -> [B,H,W]."""
+    t = attn.topk(2, dim=1).values
+    return t[:, 0] - t[:, 1]
