@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the MVSTER forward hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # our arm
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference algorithm on the host CPU (oracle port)
+    torchrun ... bench.py --gpus N ...                        # N ranks, one per GPU (batch-sharded replicas, weak scaling)
+
+A step = one full ``MVS4net.forward`` (FPN4 features for all views + the 4-stage cascade) on one
+synthetic frame per GPU: 5 views, 512x640, fp32, shipped configuration.  ``value`` times it with
+the images already resident in HBM; ``e2e`` times the same public call starting from pinned host
+images and ending with depth + confidence back in pinned host memory.  One JSON line on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+SHIPPED = dict(reg_net="reg2d", group_cor=True, group_cor_dim=[8, 8, 4, 4], inverse_depth=True, mono=True, attn_temp=2)
+WORKLOAD = dict(views=5, H=512, W=640, batch_per_gpu=1, stages=4)
+C_K, D_K, G_K = (64, 32, 16, 8), (8, 8, 4, 4), (8, 8, 4, 4)
+METRIC, UNIT = "depth-maps/sec fwd, 5-view 512x640 4-stage; warp HBM GB/s vs B200 peak", "depth-maps/s"
+
+
+def et_algorithmic_bytes(k: int, B: int, V: int, H: int, W: int, partial: bool = False) -> int:
+    """every feature element once + hypotheses once + cost volume once (fp32)."""
+    h, w = H >> (3 - k), W >> (3 - k)
+    b = (1 + V) * B * C_K[k] * h * w * 4 + B * D_K[k] * h * w * 4 + B * G_K[k] * D_K[k] * h * w * 4
+    return b + (B * D_K[k] * h * w * 4 if partial else 0)
+
+
+def measured_peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            j = json.loads(p.read_text())
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(device, seed=0):
+    from mvster_b200 import MVS4net, synth
+    torch.manual_seed(0)
+    m = MVS4net(**SHIPPED)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(synth.synthetic_state(shapes, seed), strict=True)
+    return m.eval().to(device)
+
+
+def run_reference(args, rank: int):
+    """The reference algorithm (CPU oracle port, validated against the unmodified reference by
+    tests/test_oracle_golden.py) timed on the host cores with all threads."""
+    if rank != 0:
+        return
+    from mvster_b200 import MVS4net, synth
+    from oracle import mvster_oracle as oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    m = MVS4net(**SHIPPED)
+    sd = synth.synthetic_state({k: tuple(v.shape) for k, v in m.state_dict().items()}, 0)
+    imgs, proj, dv = synth.make_inputs(WORKLOAD["batch_per_gpu"], WORKLOAD["views"], WORKLOAD["H"], WORKLOAD["W"], seed=0)
+    cfg = dict(oracle.DEFAULT_CFG)
+    for _ in range(args.warmup):
+        oracle.cascade_forward(sd, cfg, imgs, proj, dv)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.cascade_forward(sd, cfg, imgs, proj, dv)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = WORKLOAD["batch_per_gpu"] / dt
+    sample = f"{args.steps} full 5-view 512x640 forwards (FPN4 + 4 stages) after {args.warmup} warm-up, torch CPU fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def config_dict(n):
+    return {"workload": "cfg2: DTU-mid 5-view 512x640, 4-stage cascade, fp32, shipped config (reg2d, group_cor 8/8/4/4, "
+                        "D 8/8/4/4, inverse depth); one frame per GPU",
+            "views": 5, "H": 512, "W": 640, "global_batch": n, "parallelism": f"batch-sharded replicas x{n}",
+            "l2": "512 MB buffer written between timed steps (L2 flush)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    ap.add_argument("--profile-range", action="store_true",
+                    help="wrap the resident timed loop in cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from mvster_b200 import _lib, capi, synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True           # as test_mvs4.py:20
+    torch.backends.cudnn.allow_tf32 = False          # fp32 config: keep the feature net in true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    B, NV, H, W = WORKLOAD["batch_per_gpu"], WORKLOAD["views"], WORKLOAD["H"], WORKLOAD["W"]
+    model = build_model(dev)
+    imgs_h, proj_h, dv_h = synth.make_inputs(B, NV, H, W, seed=rank)
+    imgs_p = [t.pin_memory() for t in imgs_h]
+    proj_p = {k: v.pin_memory() for k, v in proj_h.items()}
+    dv_p = dv_h.pin_memory()
+    imgs_d = [t.to(dev) for t in imgs_h]
+    proj_d = {k: v.to(dev) for k, v in proj_h.items()}
+    dv_d = dv_h.to(dev)
+    depth_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    conf_host = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step_resident():
+        with torch.no_grad():
+            return model(imgs_d, proj_d, dv_d)
+
+    def step_e2e():
+        with torch.no_grad():
+            imgs = [t.to(dev, non_blocking=True) for t in imgs_p]
+            proj = {k: v.to(dev, non_blocking=True) for k, v in proj_p.items()}
+            out = model(imgs, proj, dv_p.to(dev, non_blocking=True))
+            depth_host.copy_(out["depth"], non_blocking=True)
+            conf_host.copy_(out["photometric_confidence"], non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps
+        (outside the event pairs).  Returns the summed step time in ms (max over ranks)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s, e in evs:
+            flush.fill_(1.0)
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        total = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        return float(total.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    for _ in range(2):
+        step_e2e()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    if args.profile_range:
+        torch.cuda.profiler.start()
+    ms_total = timed(step_resident, args.steps)
+    if args.profile_range:
+        torch.cuda.profiler.stop()
+    launches = _lib.launch_count() - l0
+    ms_e2e = ms_total if args.skip_e2e else timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step, ms_step_e2e = ms_total / args.steps, ms_e2e / args.steps
+    value = world * B / (ms_step * 1e-3)
+    e2e_value = world * B / (ms_step_e2e * 1e-3)
+
+    # ---- warp (ET) kernel alone: live CUDA-event timing per stage, L2 flushed between launches
+    peak, peak_src = measured_peaks()
+    roof, breakdown = None, None
+    if rank == 0:
+        with torch.no_grad():
+            out = step_resident()
+            x = torch.cat(imgs_d, 0).contiguous(memory_format=torch.channels_last)
+            pyr = model.feature(x)
+            per_stage = []
+            for k in range(4):
+                f = capi.to_nhwc(pyr[f"stage{k + 1}"])
+                feats = [f[v * B:(v + 1) * B] for v in range(NV)]
+                hypo = out[f"stage{k + 1}"]["hypo_depth"]
+                pose = capi.pose(proj_d[f"stage{k + 1}"])
+                cost = torch.empty((B, D_K[k], H >> (3 - k), W >> (3 - k), G_K[k]), device=dev)
+                for _ in range(3):
+                    capi.et_fuse(feats[0], feats[1:], pose, hypo, G_K[k], 2.0, cost=cost)
+                ts = []
+                for _ in range(20):
+                    flush.fill_(1.0)
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    capi.et_fuse(feats[0], feats[1:], pose, hypo, G_K[k], 2.0, cost=cost)
+                    e.record()
+                    torch.cuda.synchronize()
+                    ts.append(s.elapsed_time(e))
+                t = statistics.mean(ts)
+                nbytes = et_algorithmic_bytes(k, B, NV - 1, H, W)
+                per_stage.append({"stage": k + 1, "us": t * 1e3, "bytes": nbytes, "gbs": nbytes / (t * 1e-3) / 1e9})
+        tot_b = sum(p["bytes"] for p in per_stage)
+        tot_t = sum(p["us"] for p in per_stage) * 1e-6
+        dom = per_stage[3]
+        roof = {"kernel": "et_fuse_kernel (stage 4 launch: C=8,G=4,D=4, 4 source views)", "bound": "hbm",
+                "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "peak_source": peak_src,
+                "traffic": None, "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak,
+                                                 "bytes": tot_b, "us": tot_t * 1e6},
+                "per_stage": per_stage}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import mvster_oracle as oracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        cfg = dict(oracle.DEFAULT_CFG)
+        oracle.cascade_forward(sd, cfg, imgs_h, proj_h, dv_h)
+        t0 = time.perf_counter()
+        for _ in range(args.cpu_baseline_steps):
+            oracle.cascade_forward(sd, cfg, imgs_h, proj_h, dv_h)
+        dt = (time.perf_counter() - t0) / args.cpu_baseline_steps
+        cpu_base = {"value": B / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{args.cpu_baseline_steps} full forwards of the same frame after 1 warm-up (oracle port, torch CPU fp32)"}
+
+    if rank == 0:
+        h2d = sum(t.numel() * 4 for t in imgs_p) + sum(v.numel() * 4 for v in proj_p.values()) + dv_p.numel() * 4
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 2 * B * H * W * 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
