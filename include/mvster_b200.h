@@ -43,6 +43,7 @@ typedef void* mvster_stream_t; /* cudaStream_t */
 /* flags of mvster_et_fuse_f32 */
 #define MVSTER_ET_PARTIAL 1     /* write un-normalised acc + wsum (view-sharded run) */
 #define MVSTER_ET_ACCUMULATE 2  /* start from the acc/wsum already in cost/wsum */
+#define MVSTER_ET_GENERIC 4     /* force the generic G-lanes-per-pixel kernel (A/B testing) */
 
 int mvster_version(void);                 /* 10000*major + 100*minor + patch */
 const char* mvster_last_error(void);      /* thread-local, never NULL */

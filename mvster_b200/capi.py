@@ -85,7 +85,7 @@ def pose(proj: Tensor, first_view: int = 1, n_views: Optional[int] = None) -> Te
 
 def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: int, attn_temp: float,
             cost: Optional[Tensor] = None, wsum: Optional[Tensor] = None, partial: bool = False,
-            accumulate: bool = False) -> Tensor:
+            accumulate: bool = False, generic: bool = False) -> Tensor:
     """ref [B,H,W,C], srcs V x [B,Hs,Ws,C], pose [B,V,12], hypo [B,D,H,W] -> cost [B,D,H,W,G].
     With ``partial`` the un-normalised accumulators are written to (cost, wsum)."""
     B, H, W, Cc = ref.shape
@@ -107,12 +107,12 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
     for v0 in range(0, V, MAX_VIEWS):  # more than MAX_VIEWS views: chain launches through the partials
         chunk = srcs[v0:v0 + MAX_VIEWS]
         last = v0 + MAX_VIEWS >= V
-        flags = 0
+        flags = 4 if generic else 0  # MVSTER_ET_GENERIC
         if partial or not last:
             flags |= ET_PARTIAL
         if accumulate or v0 > 0:
             flags |= ET_ACCUMULATE
-        if flags and wsum is None:
+        if (flags & 3) and wsum is None:
             wsum = torch.empty((B, D, H, W), device=ref.device, dtype=torch.float32)
         pose_c = _chk(pose[:, v0:v0 + len(chunk)].contiguous(), "pose", (B, len(chunk), 12))
         arr = (C.c_void_p * len(chunk))(*[s.data_ptr() for s in chunk])

@@ -178,6 +178,10 @@ __global__ void et_normalize_kernel(float* __restrict__ cost, const float* __res
     if (i < n) cost[i] = __fdiv_rn(cost[i], __fadd_rn(1e-8f, __ldg(wsum + i / G)));
 }
 
+}  // namespace mvster
+#include "et_fuse_tiled.cuh"
+namespace mvster {
+
 template <int CPG, int G, int D>
 static int launch_et(const EtArgs& a, cudaStream_t st) {
     const long long threads = (long long)a.B * a.H * a.W * G;
@@ -231,6 +235,8 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     a.sqrt_c = (float)sqrt((double)C);  // math.sqrt(C) -> fp32 scalar
     a.flags = flags;
     cudaStream_t st = (cudaStream_t)stream;
+    int rc = MVSTER_OK;
+    if (!(flags & MVSTER_ET_GENERIC) && try_launch_tiled(a, C, G, D, st, &rc)) return rc;
     return G == 4 ? dispatch_cpg<4>(a, C / G, D, st) : dispatch_cpg<8>(a, C / G, D, st);
 }
 

@@ -1,0 +1,245 @@
+// Tiled, instruction-lean variant of the fused warp + epipolar-Transformer kernel for the shipped
+// (C, G, D) combinations.  Same arithmetic as et_fuse_kernel (et_fuse.cu) with these changes:
+//   * LPP lanes per reference pixel instead of G: the plane-sweep geometry (the dominant
+//     instruction cost at C = 8..16) is evaluated once per pixel (LPP = 1) or twice/4x for the wide
+//     stages, and every lane moves C/LPP contiguous channels per tap with 128-bit loads.
+//   * 32 x 8-pixel CTA tiles (one warp per row): the lower taps of row y are the upper taps of
+//     row y+1, so the vertical bilinear overlap is served by L1 instead of L2.
+//   * packed fp32 math (FFMA2, fma.rn.f32x2 - new on sm_100) for the 4-tap blend and the
+//     group dot products; divisions by a shared denominator use one reciprocal + an FMA residual
+//     correction (<= 1 ulp from IEEE); softmax uses ex2.approx.
+// The kernel is HBM-bandwidth bound by design: per pixel it must move (1+V)*C*4 + D*4 + G*D*4
+// bytes (240 B at stage 4) and now issues ~1.3 k instructions for them (5.5 instr/B is the
+// B200 issue/HBM balance point).
+#pragma once
+
+namespace mvster {
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// a / b given r ~= 1/b: one Newton-style residual correction (exact residual through FMA).
+__device__ __forceinline__ float div_corrected(float a, float b, float r) {
+    const float q = a * r;
+    return fmaf(fmaf(-q, b, a), r, q);
+}
+
+template <int C, int G, int D, int LPP>
+__global__ void __launch_bounds__(256) et_fuse_tiled_kernel(const EtArgs a) {
+    constexpr int CPL = C / LPP;   // channels per lane
+    constexpr int GPL = G / LPP;   // groups per lane
+    constexpr int CPG = C / G;     // channels per group
+    constexpr int PXW = 32 / LPP;  // pixels per warp (tile width)
+    constexpr int NP = CPL / 2;    // packed pairs per lane
+    static_assert(CPL % 4 == 0 && GPL >= 1 && CPG % 2 == 0, "unsupported tiling");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % LPP;
+    int x = blockIdx.x * PXW + lane / LPP;
+    int y = blockIdx.y * 8 + warp;
+    const int b = blockIdx.z;
+    const bool live = x < a.W && y < a.H;
+    x = min(x, a.W - 1);
+    y = min(y, a.H - 1);
+    const int plane = a.H * a.W, pix = y * a.W + x;
+
+    unsigned long long ref[NP];
+    {
+        const float4* p = reinterpret_cast<const float4*>(a.ref + ((long long)b * plane + pix) * C + sub * CPL);
+#pragma unroll
+        for (int i = 0; i < CPL / 4; ++i) {
+            const float4 t = __ldg(p + i);
+            ref[2 * i] = pack2(t.x, t.y);
+            ref[2 * i + 1] = pack2(t.z, t.w);
+        }
+    }
+    float dep[D], ws[D], acc[GPL][D];
+    const float* hp = a.hypo + (long long)b * D * plane + pix;
+#pragma unroll
+    for (int d = 0; d < D; ++d) dep[d] = __ldg(hp + (long long)d * plane);
+    if (a.flags & MVSTER_ET_ACCUMULATE) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const long long o = ((long long)b * D + d) * plane + pix;
+            ws[d] = a.wsum[o];
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) acc[g][d] = a.cost[o * G + sub * GPL + g];
+        }
+    } else {
+        const float seed = (a.flags & MVSTER_ET_PARTIAL) ? 0.f : 1e-8f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            ws[d] = seed;
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) acc[g][d] = 0.f;
+        }
+    }
+
+    // fold the 1/CPG of .mean(2) into the reference features (power of two: exact)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) ref[i] = mul2(ref[i], pack2(1.f / CPG, 1.f / CPG));
+
+    const float fx = (float)x, fy = (float)y;
+    const float max_x = (float)(a.Ws - 1), max_y = (float)(a.Hs - 1);
+    const float inv_temp_log2e = 1.4426950408889634f / a.attn_temp;
+    const int row = a.Ws * C;
+    const int lane_base = b * a.Hs * row + sub * CPL;  // < 2^31 (checked on the host)
+
+    for (int v = 0; v < a.V; ++v) {
+        const float* P = a.pose + ((long long)b * a.V + v) * 12;
+        const float rx = fmaf(__ldg(P + 2), 1.f, fmaf(__ldg(P + 1), fy, __ldg(P + 0) * fx));
+        const float ry = fmaf(__ldg(P + 5), 1.f, fmaf(__ldg(P + 4), fy, __ldg(P + 3) * fx));
+        const float rz = fmaf(__ldg(P + 8), 1.f, fmaf(__ldg(P + 7), fy, __ldg(P + 6) * fx));
+        const float tx = __ldg(P + 9), ty = __ldg(P + 10), tz = __ldg(P + 11);
+        const float* S = a.src[v];  // warp-uniform base; batch/lane offsets live in the 32-bit tap offsets
+
+        float cor[GPL][D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const float X = __fadd_rn(__fmul_rn(rx, dep[d]), tx);
+            const float Y = __fadd_rn(__fmul_rn(ry, dep[d]), ty);
+            float Z = __fadd_rn(__fmul_rn(rz, dep[d]), tz);
+            if (Z == 0.f) Z = 1e-9f;
+            float rZ;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rZ) : "f"(Z));
+            // Sampling position in source pixels.  The reference normalises to [-1,1] and grid_sample
+            // maps back (mvs4net_utils.py:43-44 + align_corners=True): an identity up to <= 4e-5 px of
+            // fp32 rounding, skipped here.
+            const float ix = div_corrected(X, Z, rZ), iy = div_corrected(Y, Z, rZ);
+            int o_nw, o_ne, o_sw, o_se;
+            float w_nw, w_ne, w_sw, w_se;
+            const bool interior = ix >= 0.f && ix < max_x && iy >= 0.f && iy < max_y;  // false for NaN
+            if (__all_sync(0xffffffffu, interior)) {  // warp-uniform fast path: all 4 taps of every lane in bounds
+                const float x0f = floorf(ix), y0f = floorf(iy);
+                const float wx = ix - x0f, wy = iy - y0f, ex = 1.f - wx, ey = 1.f - wy;
+                o_nw = lane_base + (int)y0f * row + (int)x0f * C;
+                o_ne = o_nw + C; o_sw = o_nw + row; o_se = o_sw + C;
+                w_nw = ey * ex; w_ne = ey * wx; w_sw = wy * ex; w_se = wy * wx;
+            } else {  // zeros padding per tap: clamp the address, zero the weight
+                const float cx = fminf(fmaxf(ix, -2.f), max_x + 2.f), cy = fminf(fmaxf(iy, -2.f), max_y + 2.f);
+                const float x0f = floorf(cx), y0f = floorf(cy);
+                const float wx = cx - x0f, wy = cy - y0f;
+                const int x0 = (int)x0f, y0 = (int)y0f;
+                const float ex = (unsigned)x0 < (unsigned)a.Ws ? 1.f - wx : 0.f, fxw = (unsigned)(x0 + 1) < (unsigned)a.Ws ? wx : 0.f;
+                const float ey = (unsigned)y0 < (unsigned)a.Hs ? 1.f - wy : 0.f, fyw = (unsigned)(y0 + 1) < (unsigned)a.Hs ? wy : 0.f;
+                const int xa = min(max(x0, 0), a.Ws - 1) * C, xb = min(max(x0 + 1, 0), a.Ws - 1) * C;
+                const int ya = lane_base + min(max(y0, 0), a.Hs - 1) * row, yb = lane_base + min(max(y0 + 1, 0), a.Hs - 1) * row;
+                o_nw = ya + xa; o_ne = ya + xb; o_sw = yb + xa; o_se = yb + xb;
+                w_nw = ey * ex; w_ne = ey * fxw; w_sw = fyw * ex; w_se = fyw * fxw;
+            }
+            const float4* p_nw = reinterpret_cast<const float4*>(S + o_nw);
+            const float4* p_ne = reinterpret_cast<const float4*>(S + o_ne);
+            const float4* p_sw = reinterpret_cast<const float4*>(S + o_sw);
+            const float4* p_se = reinterpret_cast<const float4*>(S + o_se);
+            const unsigned long long k_nw = pack2(w_nw, w_nw), k_ne = pack2(w_ne, w_ne);
+            const unsigned long long k_sw = pack2(w_sw, w_sw), k_se = pack2(w_se, w_se);
+            float gsum[GPL];
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) gsum[g] = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPL / 4; ++i) {
+                const float4 t_nw = __ldg(p_nw + i), t_ne = __ldg(p_ne + i);
+                const float4 t_sw = __ldg(p_sw + i), t_se = __ldg(p_se + i);
+                unsigned long long w0 = mul2(pack2(t_nw.x, t_nw.y), k_nw);
+                unsigned long long w1 = mul2(pack2(t_nw.z, t_nw.w), k_nw);
+                w0 = fma2(pack2(t_ne.x, t_ne.y), k_ne, w0); w1 = fma2(pack2(t_ne.z, t_ne.w), k_ne, w1);
+                w0 = fma2(pack2(t_sw.x, t_sw.y), k_sw, w0); w1 = fma2(pack2(t_sw.z, t_sw.w), k_sw, w1);
+                w0 = fma2(pack2(t_se.x, t_se.y), k_se, w0); w1 = fma2(pack2(t_se.z, t_se.w), k_se, w1);
+                // channels 4i..4i+3 of this lane belong to group (4i)/CPG (CPG is 2, 4 or 8)
+                if constexpr (CPG == 2) {
+                    const float2 q0 = unpack2(mul2(ref[2 * i], w0)), q1 = unpack2(mul2(ref[2 * i + 1], w1));
+                    gsum[2 * i] = q0.x + q0.y;
+                    gsum[2 * i + 1] = q1.x + q1.y;
+                } else {
+                    const float2 q = unpack2(fma2(ref[2 * i + 1], w1, mul2(ref[2 * i], w0)));
+                    gsum[(4 * i) / CPG] += q.x + q.y;
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) cor[g][d] = gsum[g];
+        }
+
+        // softmax over D of (sum over all G groups) / temp, then / sqrt(C)   (mvs4net_utils.py:1053)
+        float lg[D], m = -INFINITY;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            float s = cor[0][d];
+#pragma unroll
+            for (int g = 1; g < GPL; ++g) s += cor[g][d];
+#pragma unroll
+            for (int o = 1; o < LPP; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            lg[d] = s * inv_temp_log2e;
+            m = fmaxf(m, lg[d]);
+        }
+        float se = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { lg[d] = exp2f(lg[d] - m); se += lg[d]; }
+        float rs;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(se * a.sqrt_c));
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const float w = lg[d] * rs;
+            ws[d] += w;
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) acc[g][d] = fmaf(w, cor[g][d], acc[g][d]);
+        }
+    }
+
+    if (!live) return;
+    const bool partial = a.flags & MVSTER_ET_PARTIAL;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const long long o = ((long long)b * D + d) * plane + pix;
+        const float r = partial ? 1.f : __frcp_rn(ws[d]);
+        float out[GPL];
+#pragma unroll
+        for (int g = 0; g < GPL; ++g) out[g] = partial ? acc[g][d] : acc[g][d] * r;
+        float* dst = a.cost + o * G + sub * GPL;
+        if constexpr (GPL % 4 == 0) {
+#pragma unroll
+            for (int g = 0; g < GPL; g += 4) *reinterpret_cast<float4*>(dst + g) = make_float4(out[g], out[g + 1], out[g + 2], out[g + 3]);
+        } else if constexpr (GPL == 2) {
+            *reinterpret_cast<float2*>(dst) = make_float2(out[0], out[1]);
+        } else {
+#pragma unroll
+            for (int g = 0; g < GPL; ++g) dst[g] = out[g];
+        }
+        if (partial && sub == 0) a.wsum[o] = ws[d];
+    }
+}
+
+template <int C, int G, int D, int LPP>
+static int launch_et_tiled(const EtArgs& a, cudaStream_t st) {
+    dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 8), a.B);
+    et_fuse_tiled_kernel<C, G, D, LPP><<<grid, 256, 0, st>>>(a);
+    return check_launch("et_fuse_tiled_kernel");
+}
+
+// Returns 1 if a tiled specialisation exists for (C,G,D) and was launched into *rc.
+static bool try_launch_tiled(const EtArgs& a, int C, int G, int D, cudaStream_t st, int* rc) {
+    if ((long long)a.B * a.Hs * a.Ws * C >= (1ll << 31) || a.B > 65535) return false;  // 32-bit tap offsets
+    if (C == 8 && G == 4 && D == 4) { *rc = launch_et_tiled<8, 4, 4, 1>(a, st); return true; }
+    if (C == 16 && G == 4 && D == 4) { *rc = launch_et_tiled<16, 4, 4, 1>(a, st); return true; }
+    if (C == 32 && G == 8 && D == 8) { *rc = launch_et_tiled<32, 8, 8, 2>(a, st); return true; }
+    if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled<64, 8, 8, 4>(a, st); return true; }
+    return false;
+}
+
+}  // namespace mvster

@@ -63,22 +63,38 @@ class InferenceEngine:
                 self.stage_weights.append({k: v.to(self.device) for k, v in packed.items()})
 
     # ------------------------------------------------------------------ full forward
-    def forward(self, net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor) -> Dict:
+    def forward(self, net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
+                shard=None) -> Dict:
+        """``shard`` (sharding.ViewShard) restricts this rank to the reference view plus its own
+        slice of the source views: features are extracted only for those."""
         B = imgs[0].shape[0]
-        nv = len(imgs)
+        own = list(range(len(imgs))) if shard is None else [0] + shard.views
         with torch.cuda.device(self.device):
-            x = torch.cat(list(imgs), 0).contiguous(memory_format=torch.channels_last)
-            pyramid = net.feature(x)  # {stage: [nv*B, C, h, w]}, channels-last strides
+            x = torch.cat([imgs[v] for v in own], 0).contiguous(memory_format=torch.channels_last)
+            pyramid = net.feature(x)  # {stage: [len(own)*B, C, h, w]}, channels-last strides
             feats = []
             for k in range(net.num_stage):
-                f = capi.to_nhwc(pyramid[f"stage{k + 1}"])  # [nv*B, h, w, C]
-                feats.append([f[v * B:(v + 1) * B] for v in range(nv)])
-            return self.run_cascade(net, feats, proj_matrices, depth_values)
+                f = capi.to_nhwc(pyramid[f"stage{k + 1}"])  # [len(own)*B, h, w, C]
+                feats.append([f[i * B:(i + 1) * B] for i in range(len(own))])
+            return self.run_cascade(net, feats, proj_matrices, depth_values, shard=shard)
 
     # ------------------------------------------------------------------ the hot path
+    def _aggregate(self, p: StagePlan, ref: Tensor, srcs: List[Tensor], proj: Tensor, hypo: Tensor, temp: float, shard) -> Tensor:
+        if shard is None:
+            return capi.et_fuse(ref, srcs, capi.pose(proj), hypo, p.G, temp)
+        from . import sharding
+        B, H, W, _ = ref.shape
+
+        def partial(acc, wsum):
+            pose = capi.pose(proj, first_view=shard.first_view, n_views=shard.count)
+            capi.et_fuse(ref, srcs, pose, hypo, p.G, temp, cost=acc, wsum=wsum, partial=True)
+
+        return sharding.sharded_aggregate(partial, capi.et_normalize, (B, p.D, H, W, p.G), shard, self.device)
+
     def run_cascade(self, net, feats: List[List[Tensor]], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
-                    attn_temp: Optional[float] = None) -> Dict:
-        """feats[k][v]: NHWC feature of view v at stage k (view 0 = reference)."""
+                    attn_temp: Optional[float] = None, shard=None) -> Dict:
+        """feats[k][i]: NHWC features at stage k; i = 0 is the reference view, i >= 1 the source
+        views (all of them, or with ``shard`` this rank's ``shard.views`` in order)."""
         temp = float(net.stagenet.attn_temp if attn_temp is None else attn_temp)
         outputs: Dict = {}
         prev = None
@@ -92,8 +108,7 @@ class InferenceEngine:
                 hypo = capi.hypo_init_inverse(dv, p.D, H, W)
             else:
                 hypo = capi.hypo_schedule_inverse(prev["inverse_min_depth"], prev["inverse_max_depth"], p.D, H, W)
-            pose = capi.pose(proj)
-            cost = capi.et_fuse(ref, srcs, pose, hypo, p.G, temp)
+            cost = self._aggregate(p, ref, srcs, proj, hypo, temp, shard)
             feat8 = capi.reg2d(wts["blob"], cost)
             h = capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=True)
             out = {"depth": h["depth"],

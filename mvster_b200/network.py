@@ -245,6 +245,12 @@ class MVS4net(nn.Module):
         # replicas share this dict by reference, each thread touching only its own device's entry).
         self._engines = {}
         self._weights_version = 0
+        self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)
+
+    def set_view_shard(self, shard) -> None:
+        """View-parallel inference: this process aggregates only ``shard.views`` and all-reduces the
+        per-stage partials with the other ranks of ``shard.group`` (mvster_b200/sharding.py)."""
+        self._view_shard = shard
 
     # -- weight-change tracking: packed weights are rebuilt when parameters may have moved
     def train(self, mode: bool = True):
@@ -281,7 +287,7 @@ class MVS4net(nn.Module):
             if eng.weights_version != self._weights_version:
                 eng.refresh_weights(self)
                 eng.weights_version = self._weights_version
-            return eng.forward(self, imgs, proj_matrices, depth_values)
+            return eng.forward(self, imgs, proj_matrices, depth_values, shard=self._view_shard)
         return self._forward_autograd(imgs, proj_matrices, depth_values, filename)
 
     def _forward_autograd(self, imgs, proj_matrices, depth_values, filename=None):

@@ -151,13 +151,16 @@ def relative_pose(src_full: Tensor, ref_full: Tensor):
 def plane_sweep_warp(src_fea: Tensor, src_full: Tensor, ref_full: Tensor, hypo: Tensor) -> Tensor:
     """mvs4net_utils.py:13-59.  src_fea [B,C,Hs,Ws], hypo [B,D,Hr,Wr] ->
     [B,C,D,Hr,Wr]; bilinear, zero padding per tap, align_corners=True; z==0 is
-    replaced by 1e-9; the grid is always fp32."""
+    replaced by 1e-9; the reference's pixel grid is hard-coded fp32 (:28-29).  Feeding fp64
+    tensors runs the whole chain in fp64 (the reference cannot) - used only as the
+    higher-precision "truth" that brackets fp32 rounding noise in the GPU parity tests."""
     B, C, Hs, Ws = src_fea.shape
     _, D, Hr, Wr = hypo.shape
     R, t = relative_pose(src_full, ref_full)
-    yy, xx = torch.meshgrid(torch.arange(0, Hr, dtype=torch.float32),
-                            torch.arange(0, Wr, dtype=torch.float32), indexing="ij")
-    pix = torch.stack((xx.reshape(-1), yy.reshape(-1), torch.ones(Hr * Wr)))  # [3,HW]
+    gdt = torch.float64 if src_fea.dtype == torch.float64 else torch.float32
+    yy, xx = torch.meshgrid(torch.arange(0, Hr, dtype=gdt),
+                            torch.arange(0, Wr, dtype=gdt), indexing="ij")
+    pix = torch.stack((xx.reshape(-1), yy.reshape(-1), torch.ones(Hr * Wr, dtype=gdt)))  # [3,HW]
     ray = torch.matmul(R, pix.unsqueeze(0).repeat(B, 1, 1))                   # [B,3,HW]
     pts = ray.unsqueeze(2).repeat(1, 1, D, 1) * hypo.reshape(B, 1, D, -1) + t.reshape(B, 3, 1, 1)
     z = pts[:, 2:3]
