@@ -104,6 +104,16 @@ int mvster_conv3d_ndhwc_f32(const float* x, const float* w, const float* bias, c
                             int kd, int stride_d, int stride_hw, int transposed, int relu,
                             mvster_stream_t stream);
 
+/* The same layer on the tcgen05 tensor cores (TMA-fed implicit GEMM, accumulators in TMEM) for
+ * stride-1 (kd,3,3) convolutions with Cin, Cout in {16,32,64} (reg2d conv2/conv4/conv6 = 69% of its FLOPs).
+ * w_packed: [hi | lo] halves, each [kd*9][Cin/KC][Cout][KC] fp32 with KC = min(Cin,32)
+ * (K-major weight slabs; lo half only when npass == 3), see mvster_b200/packing.py:pack_tc_weights.
+ * npass = 3: error-compensated 3xTF32 (fp32-faithful, ~2^-21 relative); npass = 1: plain TF32. */
+int mvster_conv3d_tc_supported(int Cin, int Cout, int kd, int stride_hw, int transposed);
+int mvster_conv3d_tc_f32(const float* x, const float* w_packed, const float* bias, const float* skip, float* y,
+                         int B, int D, int H, int W, int Cin, int Cout, int kd, int relu, int npass,
+                         mvster_stream_t stream);
+
 /* reg2d U-Net (mvs4net_utils.py:870-912) up to, not including, the 1x1x1 `prob`
  * layer: cost [B][D][H][W][G] -> feat8 [B][D][H][W][8].  `blob` holds the folded
  * weights of conv0..conv11 in the layout reported by mvster_reg2d_layer_info;

@@ -26,6 +26,8 @@ SIGNATURES = {
     "mvster_et_fuse_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "mvster_et_normalize_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "mvster_conv3d_ndhwc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_conv3d_tc_supported": (_i, [_i, _i, _i, _i, _i]),
+    "mvster_conv3d_tc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_reg2d_blob_floats": (C.c_size_t, [_i]),
     "mvster_reg2d_workspace_floats": (C.c_size_t, [_i, _i, _i, _i]),
     "mvster_reg2d_layer_info": (_i, [_i, _i, C.POINTER(C.c_int64)]),

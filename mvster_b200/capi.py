@@ -154,6 +154,25 @@ def conv3d_ndhwc(x: Tensor, w: Tensor, bias: Optional[Tensor], kd: int, stride_d
     return y
 
 
+def conv3d_tc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, relu: bool = True,
+              skip: Optional[Tensor] = None, npass: int = 3) -> Tensor:
+    """tcgen05 implicit-GEMM conv: x [B,D,H,W,Cin], w_packed from packing.pack_tc_weights -> [B,D,H,W,cout]."""
+    _chk(x, "x")
+    _chk(w_packed, "w_packed")
+    B, D, H, W, Cin = x.shape
+    y = torch.empty((B, D, H, W, cout), device=x.device, dtype=torch.float32)
+    if bias is not None:
+        _chk(bias, "bias", (cout,))
+    if skip is not None:
+        _chk(skip, "skip", tuple(y.shape))
+    want = kd * 9 * Cin * cout * (2 if npass == 3 else 1)
+    if w_packed.numel() != want:
+        raise ValueError(f"w_packed has {w_packed.numel()} floats, expected {want}")
+    _lib.check(_lib.load().mvster_conv3d_tc_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
+                                                kd, int(relu), npass, _stream()), "mvster_conv3d_tc_f32")
+    return y
+
+
 def reg2d_layer_table(G: int) -> List[dict]:
     lib = _lib.load()
     n_layers = 10

@@ -34,6 +34,25 @@ def fold_deconv3d(w: Tensor, scale: Tensor, shift: Tensor) -> Tuple[Tensor, Tens
     return wf.permute(2, 3, 4, 0, 1).reshape(taps, w.shape[0], w.shape[1]).float().contiguous(), shift.float().contiguous()
 
 
+TF32_MASK = -8192  # 0xFFFFE000 as int32: keep sign, exponent and the top 10 mantissa bits
+
+
+def pack_tc_weights(w: Tensor, npass: int = 3) -> Tensor:
+    """[taps][Cin][Cout] fp32 -> the K-major slabs the tcgen05 conv kernel streams by TMA:
+    [hi | lo] x [taps][Cin/KC][Cout][KC], KC = min(Cin, 32).  hi = w truncated to TF32, lo = TF32(w - hi)
+    (exact split: hi + lo reproduces w to 2^-21 relative); npass == 1 keeps w unsplit."""
+    taps, cin, cout = w.shape
+    kc = 32 if cin >= 32 else 16
+    if cin % kc:
+        raise ValueError(f"Cin={cin} is not a multiple of {kc}")
+    slabs = w.float().reshape(taps, cin // kc, kc, cout).permute(0, 1, 3, 2).contiguous()
+    if npass == 1:
+        return slabs.reshape(-1)
+    hi = (slabs.view(torch.int32) & TF32_MASK).view(torch.float32)
+    lo = ((slabs - hi).view(torch.int32) & TF32_MASK).view(torch.float32)
+    return torch.cat([hi.reshape(-1), lo.reshape(-1)])
+
+
 REG2D_ORDER = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11")
 
 

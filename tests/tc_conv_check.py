@@ -1,0 +1,55 @@
+"""Stand-alone check of the tcgen05 convolution against the exact-fp32 CUDA-core convolution.
+Run one case per process (tests/test_gpu_tc_conv.py does that with a timeout) so that a device-side
+trap or a barrier deadlock in the tensor-core kernel cannot take the rest of the suite down.
+
+    python tests/tc_conv_check.py CIN COUT KD B D H W NPASS [skip] [norelu]
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from mvster_b200 import capi, packing  # noqa: E402
+
+
+def main():
+    cin, cout, kd, B, D, H, W, npass = map(int, sys.argv[1:9])
+    use_skip, relu = "skip" in sys.argv, "norelu" not in sys.argv
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(cin * 1000 + cout * 10 + kd + H)
+    x = torch.from_numpy(rng.randn(B, D, H, W, cin).astype(np.float32)).to(dev)
+    w = torch.from_numpy((rng.randn(kd * 9, cin, cout) / np.sqrt(kd * 9 * cin)).astype(np.float32)).to(dev)
+    bias = torch.from_numpy(rng.randn(cout).astype(np.float32) * 0.1).to(dev)
+    skip = torch.from_numpy(rng.randn(B, D, H, W, cout).astype(np.float32)).to(dev) if use_skip else None
+    want = capi.conv3d_ndhwc(x, w, bias, kd, 1, 1, False, relu, skip=skip)
+    got = capi.conv3d_tc(x, packing.pack_tc_weights(w.cpu(), npass).to(dev), bias, cout, kd, relu, skip=skip, npass=npass)
+    torch.cuda.synchronize()
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item()
+    # timing: 20 back-to-back launches (activations stay in L2; this is a kernel-quality number, not a bench line)
+    wp = packing.pack_tc_weights(w.cpu(), npass).to(dev)
+    for _ in range(3):
+        capi.conv3d_tc(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(20):
+        capi.conv3d_tc(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
+    e.record()
+    torch.cuda.synchronize()
+    t_tc = s.elapsed_time(e) / 20
+    s.record()
+    for _ in range(20):
+        capi.conv3d_ndhwc(x, w, bias, kd, 1, 1, False, relu, skip=skip)
+    e.record()
+    torch.cuda.synchronize()
+    t_simt = s.elapsed_time(e) / 20
+    flops = 2.0 * B * D * H * W * kd * 9 * cin * cout
+    print(json.dumps({"case": sys.argv[1:], "abs_err": err, "scale": scale, "rel": err / scale, "finite": bool(torch.isfinite(got).all()),
+                      "us_tc": t_tc * 1e3, "us_simt": t_simt * 1e3, "tflops_tc": flops / (t_tc * 1e-3) / 1e12}))
+
+
+if __name__ == "__main__":
+    main()
