@@ -3,7 +3,7 @@
 //   * LPP lanes per reference pixel instead of G: the plane-sweep geometry (the dominant
 //     instruction cost at C = 8..16) is evaluated once per pixel (LPP = 1) or twice/4x for the wide
 //     stages, and every lane moves C/LPP contiguous channels per tap with 128-bit loads.
-//   * 32 x 8-pixel CTA tiles (one warp per row): the lower taps of row y are the upper taps of
+//   * (32/LPP) x 4-pixel CTA tiles (one warp per row): the lower taps of row y are the upper taps of
 //     row y+1, so the vertical bilinear overlap is served by L1 instead of L2.
 //   * packed fp32 math (FFMA2, fma.rn.f32x2 - new on sm_100) for the 4-tap blend and the
 //     group dot products; divisions by a shared denominator use one reciprocal + an FMA residual
@@ -36,6 +36,16 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
     return d;
 }
 
+struct Pix8 { unsigned long long p[4]; };  // 8 fp32 channels as 4 packed pairs
+// One 256-bit read-only load (LDG.E.256, new on sm_100): a lane fetches its whole 8-channel tap, a
+// warp request is 1 KB of full 128-byte lines for the L1 data pipe (two 128-bit loads cost twice
+// the wavefronts because each quarter-warp then straddles two lines).
+__device__ __forceinline__ Pix8 ldg256(const float* p) {
+    Pix8 r;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.p[0]), "=l"(r.p[1]), "=l"(r.p[2]), "=l"(r.p[3]) : "l"(p));
+    return r;
+}
+
 // a / b given r ~= 1/b: one Newton-style residual correction (exact residual through FMA).
 __device__ __forceinline__ float div_corrected(float a, float b, float r) {
     const float q = a * r;
@@ -43,17 +53,17 @@ __device__ __forceinline__ float div_corrected(float a, float b, float r) {
 }
 
 template <int C, int G, int D, int LPP>
-__global__ void __launch_bounds__(256) et_fuse_tiled_kernel(const EtArgs a) {
+__global__ void __launch_bounds__(128, 4) et_fuse_tiled_kernel(const EtArgs a) {
     constexpr int CPL = C / LPP;   // channels per lane
     constexpr int GPL = G / LPP;   // groups per lane
     constexpr int CPG = C / G;     // channels per group
     constexpr int PXW = 32 / LPP;  // pixels per warp (tile width)
     constexpr int NP = CPL / 2;    // packed pairs per lane
-    static_assert(CPL % 4 == 0 && GPL >= 1 && CPG % 2 == 0, "unsupported tiling");
+    static_assert(CPL == 8 && GPL >= 1 && CPG % 2 == 0 && CPG <= 8, "a lane owns exactly 8 channels (one 256-bit load per tap)");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % LPP;
     int x = blockIdx.x * PXW + lane / LPP;
-    int y = blockIdx.y * 8 + warp;
+    int y = blockIdx.y * 4 + warp;
     const int b = blockIdx.z;
     const bool live = x < a.W && y < a.H;
     x = min(x, a.W - 1);
@@ -62,13 +72,9 @@ __global__ void __launch_bounds__(256) et_fuse_tiled_kernel(const EtArgs a) {
 
     unsigned long long ref[NP];
     {
-        const float4* p = reinterpret_cast<const float4*>(a.ref + ((long long)b * plane + pix) * C + sub * CPL);
+        const Pix8 t = ldg256(a.ref + ((long long)b * plane + pix) * C + sub * CPL);
 #pragma unroll
-        for (int i = 0; i < CPL / 4; ++i) {
-            const float4 t = __ldg(p + i);
-            ref[2 * i] = pack2(t.x, t.y);
-            ref[2 * i + 1] = pack2(t.z, t.w);
-        }
+        for (int i = 0; i < NP; ++i) ref[i] = t.p[i];
     }
     float dep[D], ws[D], acc[GPL][D];
     const float* hp = a.hypo + (long long)b * D * plane + pix;
@@ -144,33 +150,33 @@ __global__ void __launch_bounds__(256) et_fuse_tiled_kernel(const EtArgs a) {
                 o_nw = ya + xa; o_ne = ya + xb; o_sw = yb + xa; o_se = yb + xb;
                 w_nw = ey * ex; w_ne = ey * fxw; w_sw = fyw * ex; w_se = fyw * fxw;
             }
-            const float4* p_nw = reinterpret_cast<const float4*>(S + o_nw);
-            const float4* p_ne = reinterpret_cast<const float4*>(S + o_ne);
-            const float4* p_sw = reinterpret_cast<const float4*>(S + o_sw);
-            const float4* p_se = reinterpret_cast<const float4*>(S + o_se);
+            const Pix8 t_nw = ldg256(S + o_nw), t_ne = ldg256(S + o_ne), t_sw = ldg256(S + o_sw), t_se = ldg256(S + o_se);
             const unsigned long long k_nw = pack2(w_nw, w_nw), k_ne = pack2(w_ne, w_ne);
             const unsigned long long k_sw = pack2(w_sw, w_sw), k_se = pack2(w_se, w_se);
+            unsigned long long prod[NP];  // ref * bilinear(warped) per channel pair
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                unsigned long long wv = mul2(t_nw.p[i], k_nw);
+                wv = fma2(t_ne.p[i], k_ne, wv);
+                wv = fma2(t_sw.p[i], k_sw, wv);
+                wv = fma2(t_se.p[i], k_se, wv);
+                prod[i] = wv;
+            }
             float gsum[GPL];
+            if constexpr (CPG == 2) {         // 4 groups of one pair
 #pragma unroll
-            for (int g = 0; g < GPL; ++g) gsum[g] = 0.f;
+                for (int i = 0; i < 4; ++i) { const float2 q = unpack2(mul2(ref[i], prod[i])); gsum[i] = q.x + q.y; }
+            } else if constexpr (CPG == 4) {  // 2 groups of two pairs
 #pragma unroll
-            for (int i = 0; i < CPL / 4; ++i) {
-                const float4 t_nw = __ldg(p_nw + i), t_ne = __ldg(p_ne + i);
-                const float4 t_sw = __ldg(p_sw + i), t_se = __ldg(p_se + i);
-                unsigned long long w0 = mul2(pack2(t_nw.x, t_nw.y), k_nw);
-                unsigned long long w1 = mul2(pack2(t_nw.z, t_nw.w), k_nw);
-                w0 = fma2(pack2(t_ne.x, t_ne.y), k_ne, w0); w1 = fma2(pack2(t_ne.z, t_ne.w), k_ne, w1);
-                w0 = fma2(pack2(t_sw.x, t_sw.y), k_sw, w0); w1 = fma2(pack2(t_sw.z, t_sw.w), k_sw, w1);
-                w0 = fma2(pack2(t_se.x, t_se.y), k_se, w0); w1 = fma2(pack2(t_se.z, t_se.w), k_se, w1);
-                // channels 4i..4i+3 of this lane belong to group (4i)/CPG (CPG is 2, 4 or 8)
-                if constexpr (CPG == 2) {
-                    const float2 q0 = unpack2(mul2(ref[2 * i], w0)), q1 = unpack2(mul2(ref[2 * i + 1], w1));
-                    gsum[2 * i] = q0.x + q0.y;
-                    gsum[2 * i + 1] = q1.x + q1.y;
-                } else {
-                    const float2 q = unpack2(fma2(ref[2 * i + 1], w1, mul2(ref[2 * i], w0)));
-                    gsum[(4 * i) / CPG] += q.x + q.y;
+                for (int g = 0; g < 2; ++g) {
+                    const float2 q = unpack2(fma2(ref[2 * g + 1], prod[2 * g + 1], mul2(ref[2 * g], prod[2 * g])));
+                    gsum[g] = q.x + q.y;
                 }
+            } else {                          // one group of four pairs
+                unsigned long long q2 = mul2(ref[0], prod[0]);
+                q2 = fma2(ref[1], prod[1], q2); q2 = fma2(ref[2], prod[2], q2); q2 = fma2(ref[3], prod[3], q2);
+                const float2 q = unpack2(q2);
+                gsum[0] = q.x + q.y;
             }
 #pragma unroll
             for (int g = 0; g < GPL; ++g) cor[g][d] = gsum[g];
@@ -227,8 +233,8 @@ __global__ void __launch_bounds__(256) et_fuse_tiled_kernel(const EtArgs a) {
 
 template <int C, int G, int D, int LPP>
 static int launch_et_tiled(const EtArgs& a, cudaStream_t st) {
-    dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 8), a.B);
-    et_fuse_tiled_kernel<C, G, D, LPP><<<grid, 256, 0, st>>>(a);
+    dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 4), a.B);
+    et_fuse_tiled_kernel<C, G, D, LPP><<<grid, 128, 0, st>>>(a);
     return check_launch("et_fuse_tiled_kernel");
 }
 
@@ -236,9 +242,9 @@ static int launch_et_tiled(const EtArgs& a, cudaStream_t st) {
 static bool try_launch_tiled(const EtArgs& a, int C, int G, int D, cudaStream_t st, int* rc) {
     if ((long long)a.B * a.Hs * a.Ws * C >= (1ll << 31) || a.B > 65535) return false;  // 32-bit tap offsets
     if (C == 8 && G == 4 && D == 4) { *rc = launch_et_tiled<8, 4, 4, 1>(a, st); return true; }
-    if (C == 16 && G == 4 && D == 4) { *rc = launch_et_tiled<16, 4, 4, 1>(a, st); return true; }
-    if (C == 32 && G == 8 && D == 8) { *rc = launch_et_tiled<32, 8, 8, 2>(a, st); return true; }
-    if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled<64, 8, 8, 4>(a, st); return true; }
+    if (C == 16 && G == 4 && D == 4) { *rc = launch_et_tiled<16, 4, 4, 2>(a, st); return true; }
+    if (C == 32 && G == 8 && D == 8) { *rc = launch_et_tiled<32, 8, 8, 4>(a, st); return true; }
+    if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled<64, 8, 8, 8>(a, st); return true; }
     return false;
 }
 
