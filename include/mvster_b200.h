@@ -126,6 +126,13 @@ int mvster_reg2d_layer_info(int G, int layer, int64_t* info_host);
 int mvster_reg2d_f32(const float* blob, const float* cost, float* feat8, float* workspace,
                      int B, int G, int D, int H, int W, mvster_stream_t stream);
 
+/* Same network with conv2/conv4/conv6 on the tensor cores (mvster_conv3d_tc_f32).  tc_blob =
+ * pack_tc_weights(conv2) | pack_tc_weights(conv4) | pack_tc_weights(conv6), each in the npass = 3
+ * [hi|lo] layout (mvster_reg2d_tc_blob_floats() floats); biases are read from `blob`. */
+size_t mvster_reg2d_tc_blob_floats(void);
+int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* cost, float* feat8, float* workspace,
+                        int B, int G, int D, int H, int W, int npass, mvster_stream_t stream);
+
 /* ---- head ---------------------------------------------------------------- */
 /* mvs4net_utils.py:1066-1088.  Either `logits` [B][D][H][W] is given, or
  * (feat8 [B][D][H][W][8], prob_w[8], prob_b[1]) and the 1x1x1 `prob` conv of

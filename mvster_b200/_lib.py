@@ -32,6 +32,8 @@ SIGNATURES = {
     "mvster_reg2d_workspace_floats": (C.c_size_t, [_i, _i, _i, _i]),
     "mvster_reg2d_layer_info": (_i, [_i, _i, C.POINTER(C.c_int64)]),
     "mvster_reg2d_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mvster_reg2d_tc_blob_floats": (C.c_size_t, []),
+    "mvster_reg2d_tc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "mvster_upsample_bilinear_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mvster_nchw_to_nhwc_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -193,8 +193,10 @@ def reg2d_workspace_floats(B: int, D: int, H: int, W: int) -> int:
     return int(_lib.load().mvster_reg2d_workspace_floats(B, D, H, W))
 
 
-def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
-    """cost [B,D,H,W,G] -> feat8 [B,D,H,W,8] (everything of reg2d except the 1x1x1 prob layer)."""
+def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: Optional[Tensor] = None,
+          tc_blob: Optional[Tensor] = None, npass: int = 3) -> Tensor:
+    """cost [B,D,H,W,G] -> feat8 [B,D,H,W,8] (everything of reg2d except the 1x1x1 prob layer).
+    With ``tc_blob`` the three 3x3x3 layers run on the tensor cores (npass 3 = 3xTF32, 1 = TF32)."""
     _chk(cost, "cost")
     _chk(blob, "blob")
     B, D, H, W, G = cost.shape
@@ -206,6 +208,11 @@ def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: O
     if blob.numel() != reg2d_blob_floats(G):
         raise ValueError(f"blob has {blob.numel()} floats, expected {reg2d_blob_floats(G)} for G={G}")
     out = torch.empty((B, D, H, W, 8), device=cost.device, dtype=torch.float32) if out is None else _chk(out, "feat8", (B, D, H, W, 8))
+    if tc_blob is not None:
+        _chk(tc_blob, "tc_blob", (int(_lib.load().mvster_reg2d_tc_blob_floats()),))
+        _lib.check(_lib.load().mvster_reg2d_tc_f32(_ptr(blob), _ptr(tc_blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W,
+                                                   npass, _stream()), "mvster_reg2d_tc_f32")
+        return out
     _lib.check(_lib.load().mvster_reg2d_f32(_ptr(blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W, _stream()),
                "mvster_reg2d_f32")
     return out

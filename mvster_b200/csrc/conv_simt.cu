@@ -278,8 +278,25 @@ extern "C" size_t mvster_reg2d_workspace_floats(int B, int D, int H, int W) {
     return (size_t)28 * B * D * H * W;
 }
 
+static int reg2d_run(const float* blob, const float* tc_blob, int npass, const float* cost, float* feat8, float* ws,
+                     int B, int G, int D, int H, int W, mvster_stream_t stream);
+
 extern "C" int mvster_reg2d_f32(const float* blob, const float* cost, float* feat8, float* ws,
                                 int B, int G, int D, int H, int W, mvster_stream_t stream) {
+    return reg2d_run(blob, nullptr, 0, cost, feat8, ws, B, G, D, H, W, stream);
+}
+
+extern "C" size_t mvster_reg2d_tc_blob_floats(void) { return (size_t)2 * 27 * (16 * 16 + 32 * 32 + 64 * 64); }
+
+extern "C" int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* cost, float* feat8, float* ws,
+                                   int B, int G, int D, int H, int W, int npass, mvster_stream_t stream) {
+    MVSTER_REQUIRE(tc_blob, "mvster_reg2d_tc_f32: tc_blob is null");
+    MVSTER_REQUIRE(npass == 1 || npass == 3, "mvster_reg2d_tc_f32: npass must be 1 or 3");
+    return reg2d_run(blob, tc_blob, npass, cost, feat8, ws, B, G, D, H, W, stream);
+}
+
+static int reg2d_run(const float* blob, const float* tc_blob, int npass, const float* cost, float* feat8, float* ws,
+                     int B, int G, int D, int H, int W, mvster_stream_t stream) {
     MVSTER_REQUIRE(blob && cost && feat8 && ws, "mvster_reg2d_f32: null pointer");
     MVSTER_REQUIRE(G == 4 || G == 8 || G == 16 || G == 32 || G == 64, "mvster_reg2d_f32: unsupported G=%d", G);
     MVSTER_REQUIRE(H % 8 == 0 && W % 8 == 0, "mvster_reg2d_f32: H,W must be multiples of 8 (got %dx%d)", H, W);
@@ -297,8 +314,17 @@ extern "C" int mvster_reg2d_f32(const float* blob, const float* cost, float* fea
     for (int i = 0; i < MVSTER_REG2D_LAYERS; ++i) {
         int64_t info[8];
         mvster_reg2d_layer_info(G, i, info);
-        const int rc = run_conv(in[i], blob + info[5], blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i],
-                                L[i].cin, L[i].cout, L[i].kd, 1, L[i].s, L[i].transposed, 1, st);
+        int rc;
+        if (tc_blob && L[i].kd == 3) {
+            // conv2 / conv4 / conv6 (3x3x3, 69 % of the FLOPs) on the tcgen05 tensor cores; their [hi|lo]
+            // K-major slabs sit back to back in tc_blob (2*27*Cin*Cout floats each).
+            const size_t off = i == 2 ? 0 : (i == 4 ? (size_t)2 * 27 * 16 * 16 : (size_t)2 * 27 * (16 * 16 + 32 * 32));
+            rc = mvster_conv3d_tc_f32(in[i], tc_blob + off, blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i],
+                                      L[i].cin, L[i].cout, 3, 1, npass, stream);
+        } else {
+            rc = run_conv(in[i], blob + info[5], blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i],
+                          L[i].cin, L[i].cout, L[i].kd, 1, L[i].s, L[i].transposed, 1, st);
+        }
         if (rc != MVSTER_OK) return rc;
     }
     return MVSTER_OK;

@@ -109,7 +109,11 @@ class InferenceEngine:
             else:
                 hypo = capi.hypo_schedule_inverse(prev["inverse_min_depth"], prev["inverse_max_depth"], p.D, H, W)
             cost = self._aggregate(p, ref, srcs, proj, hypo, temp, shard)
-            feat8 = capi.reg2d(wts["blob"], cost)
+            prec = getattr(net, "reg_precision", "fp32")
+            if prec == "fp32":      # exact fp32 FMA on the CUDA cores for every layer
+                feat8 = capi.reg2d(wts["blob"], cost)
+            else:                   # 3x3x3 layers on tcgen05: "3xtf32" (fp32-faithful) or "tf32"
+                feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc_blob"], npass=3 if prec == "3xtf32" else 1)
             h = capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=True)
             out = {"depth": h["depth"],
                    "photometric_confidence": capi.upsample_bilinear(h["conf_low"], p.up),

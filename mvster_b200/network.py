@@ -12,6 +12,7 @@ Dispatch in ``forward``:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -245,6 +246,9 @@ class MVS4net(nn.Module):
         # replicas share this dict by reference, each thread touching only its own device's entry).
         self._engines = {}
         self._weights_version = 0
+        # arithmetic of the 3x3x3 regulariser layers on the CUDA inference path: "fp32" (CUDA cores, exact),
+        # "3xtf32" (tcgen05, error-compensated, fp32-faithful) or "tf32" (tcgen05, single pass)
+        self.reg_precision = os.environ.get("MVSTER_REG_PRECISION", "fp32")
         self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)
 
     def set_view_shard(self, shard) -> None:

@@ -74,6 +74,11 @@ def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, 
             raise ValueError(f"{p}: packed shape {tuple(w.shape)} != layer table {(L['taps'], L['cin'], L['cout'])}")
         blob[L["w_off"]:L["w_off"] + w.numel()] = w.reshape(-1)
         blob[L["b_off"]:L["b_off"] + b.numel()] = b
-    return {"blob": blob,
+    tc = []
+    for name, L in zip(REG2D_ORDER, layer_table):
+        if L["kd"] == 3:  # conv2 / conv4 / conv6: K-major [hi|lo] slabs for the tcgen05 path
+            w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
+            tc.append(pack_tc_weights(w, 3))
+    return {"blob": blob, "tc_blob": torch.cat(tc),
             "prob_w": sd[prefix + ".prob.weight"].detach().cpu().reshape(-1).float().contiguous(),
             "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}

@@ -12,10 +12,44 @@ import numpy as np
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
 from mvster_b200 import capi, packing  # noqa: E402
 
 
+def reg2d_main():
+    """python tests/tc_conv_check.py reg2d G B D H W NPASS: whole reg2d U-Net, tensor-core 3x3x3 layers vs all-CUDA-core."""
+    from util import SHIPPED, build_model
+    G, B, D, H, W, npass = map(int, sys.argv[2:8])
+    dev = torch.device("cuda", 0)
+    sd = build_model(SHIPPED, 5).state_dict()
+    packed = packing.pack_reg2d(sd, "reg.0" if G == 8 else "reg.3", capi.reg2d_layer_table(G))
+    rng = np.random.RandomState(G + H)
+    cost = torch.from_numpy((rng.randn(B, D, H, W, G) * 0.05).astype(np.float32)).to(dev)
+    blob, tcb = packed["blob"].to(dev), packed["tc_blob"].to(dev)
+    want = capi.reg2d(blob, cost)
+    got = capi.reg2d(blob, cost, tc_blob=tcb, npass=npass)
+    torch.cuda.synchronize()
+    err, scale = (got - want).abs().max().item(), want.abs().max().item()
+    ws = torch.empty(capi.reg2d_workspace_floats(B, D, H, W), device=dev)
+    out = torch.empty_like(want)
+    times = {}
+    for tag, kw in (("simt", {}), ("tc", dict(tc_blob=tcb, npass=npass))):
+        for _ in range(3):
+            capi.reg2d(blob, cost, workspace=ws, out=out, **kw)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            capi.reg2d(blob, cost, workspace=ws, out=out, **kw)
+        e.record()
+        torch.cuda.synchronize()
+        times[tag] = s.elapsed_time(e) / 10 * 1e3
+    print(json.dumps({"case": sys.argv[1:], "abs_err": err, "scale": scale, "rel": err / scale,
+                      "finite": bool(torch.isfinite(got).all()), "us_tc": times["tc"], "us_simt": times["simt"]}))
+
+
 def main():
+    if sys.argv[1] == "reg2d":
+        return reg2d_main()
     cin, cout, kd, B, D, H, W, npass = map(int, sys.argv[1:9])
     use_skip, relu = "skip" in sys.argv, "norelu" not in sys.argv
     dev = torch.device("cuda", 0)
