@@ -44,6 +44,8 @@ typedef void* mvster_stream_t; /* cudaStream_t */
 #define MVSTER_ET_PARTIAL 1     /* write un-normalised acc + wsum (view-sharded run) */
 #define MVSTER_ET_ACCUMULATE 2  /* start from the acc/wsum already in cost/wsum */
 #define MVSTER_ET_GENERIC 4     /* force the generic G-lanes-per-pixel kernel (A/B testing) */
+#define MVSTER_ET_NO_FUSE_D 8   /* attn_fuse_d=False: per-view scalar weight max_d softmax(sum_c cost) (mvs4net_utils.py:1049-1051) */
+#define MVSTER_ET_SQDIFF 16     /* group_cor=False: cost[c] = (ref[c]-warped[c])^2, C cost channels (:1042); pass G == C */
 
 int mvster_version(void);                 /* 10000*major + 100*minor + patch */
 const char* mvster_last_error(void);      /* thread-local, never NULL */
@@ -59,6 +61,14 @@ int mvster_hypo_init_inverse_f32(const float* depth_values, int n_dv, float* hyp
  * [B][H/2][W/2] -> hypo [B][D][H][W] (bilinear x2, align_corners, reciprocal). */
 int mvster_hypo_schedule_inverse_f32(const float* inv_min, const float* inv_max, float* hypo,
                                      int B, int D, int H, int W, mvster_stream_t stream);
+
+/* Linear-depth twins (inverse_depth=False): models/mvs4net_utils.py:61-69 init_range and :88-99
+ * schedule_range.  `depth` [B][H/2][W/2] is the previous stage's depth; the per-sample interval is
+ * ratio * (depth_values[:, -1] - depth_values[:, 0]) / n_dv  (MVS4Net.py:61-63, :97). */
+int mvster_hypo_init_linear_f32(const float* depth_values, int n_dv, float* hypo,
+                                int B, int D, int H, int W, mvster_stream_t stream);
+int mvster_hypo_schedule_linear_f32(const float* depth, const float* depth_values, int n_dv, float ratio, float* hypo,
+                                    int B, int D, int H, int W, mvster_stream_t stream);
 
 /* ---- relative pose ------------------------------------------------------- */
 /* models/mvs4net_utils.py:1032-1035 (K @ E[:3,:4]) and :24 (src_proj @ inverse(ref_proj)).
@@ -114,6 +124,14 @@ int mvster_conv3d_tc_f32(const float* x, const float* w_packed, const float* bia
                          int B, int D, int H, int W, int Cin, int Cout, int kd, int relu, int npass,
                          mvster_stream_t stream);
 
+/* Generation 2 of the tensor-core layer: each 16x8-pixel tile (+halo) is staged once per depth plane and
+ * the in-plane taps are addressed through the UMMA descriptor (no per-tap reload).  Cout may also be 8
+ * (padded to N = 16).  w_packed: [hi | lo] x [kd*9][Cin/16][max(Cout,16)][16], packing.pack_tc2_weights. */
+int mvster_conv3d_tc2_supported(int Cin, int Cout, int kd, int stride_hw, int transposed);
+int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bias, const float* skip, float* y,
+                          int B, int D, int H, int W, int Cin, int Cout, int kd, int relu, int npass,
+                          mvster_stream_t stream);
+
 /* reg2d U-Net (mvs4net_utils.py:870-912) up to, not including, the 1x1x1 `prob`
  * layer: cost [B][D][H][W][G] -> feat8 [B][D][H][W][8].  `blob` holds the folded
  * weights of conv0..conv11 in the layout reported by mvster_reg2d_layer_info;
@@ -126,12 +144,25 @@ int mvster_reg2d_layer_info(int G, int layer, int64_t* info_host);
 int mvster_reg2d_f32(const float* blob, const float* cost, float* feat8, float* workspace,
                      int B, int G, int D, int H, int W, mvster_stream_t stream);
 
-/* Same network with conv2/conv4/conv6 on the tensor cores (mvster_conv3d_tc_f32).  tc_blob =
- * pack_tc_weights(conv2) | pack_tc_weights(conv4) | pack_tc_weights(conv6), each in the npass = 3
- * [hi|lo] layout (mvster_reg2d_tc_blob_floats() floats); biases are read from `blob`. */
+/* Same network with conv2/conv4/conv6 on the tensor cores.  kernel_gen = 1: mvster_conv3d_tc_f32, tc_blob =
+ * pack_tc_weights(conv2) | (conv4) | (conv6); kernel_gen = 2: mvster_conv3d_tc2_f32, tc_blob = pack_tc2_weights(...)
+ * of the same layers.  Both in the npass = 3 [hi|lo] layout (mvster_reg2d_tc_blob_floats() floats); biases are
+ * read from `blob`. */
 size_t mvster_reg2d_tc_blob_floats(void);
 int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* cost, float* feat8, float* workspace,
-                        int B, int G, int D, int H, int W, int npass, mvster_stream_t stream);
+                        int B, int G, int D, int H, int W, int npass, int kernel_gen, mvster_stream_t stream);
+
+/* reg3d U-Net (mvs4net_utils.py:914-965; optional `--reg_mode reg3d`): 3x3x3 kernels, stride 2 along D too,
+ * down_size in {1,2,3} (MVS4Net.py:48), prob = 3x3x3 conv 8->1 without bias.  cost [B][D][H][W][G] ->
+ * logits [B][D][H][W].  Blob layout: the existing layers in network order (mvster_reg3d_layer_info:
+ * info_host[8] = {Cin, Cout, stride, transposed, w_offset, bias_offset or -1, 27, layer id}); weights
+ * [27][Cin][Cout] with BN folded.  CUDA-core fp32 kernels. */
+int mvster_reg3d_num_layers(int down_size);
+int mvster_reg3d_layer_info(int G, int down_size, int layer, int64_t* info_host);
+size_t mvster_reg3d_blob_floats(int G, int down_size);
+size_t mvster_reg3d_workspace_floats(int B, int D, int H, int W);
+int mvster_reg3d_f32(const float* blob, const float* cost, float* logits, float* workspace,
+                     int B, int G, int D, int H, int W, int down_size, mvster_stream_t stream);
 
 /* ---- head ---------------------------------------------------------------- */
 /* mvs4net_utils.py:1066-1088.  Either `logits` [B][D][H][W] is given, or

@@ -22,6 +22,13 @@ SIGNATURES = {
     "mvster_launch_count": (C.c_uint64, []),
     "mvster_hypo_init_inverse_f32": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
     "mvster_hypo_schedule_inverse_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "mvster_hypo_init_linear_f32": (_i, [_p, _i, _p, _i, _i, _i, _i, _p]),
+    "mvster_hypo_schedule_linear_f32": (_i, [_p, _p, _i, _f, _p, _i, _i, _i, _i, _p]),
+    "mvster_reg3d_num_layers": (_i, [_i]),
+    "mvster_reg3d_layer_info": (_i, [_i, _i, _i, C.POINTER(C.c_int64)]),
+    "mvster_reg3d_blob_floats": (C.c_size_t, [_i, _i]),
+    "mvster_reg3d_workspace_floats": (C.c_size_t, [_i, _i, _i, _i]),
+    "mvster_reg3d_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_pose_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mvster_et_fuse_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "mvster_et_normalize_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
@@ -33,7 +40,9 @@ SIGNATURES = {
     "mvster_reg2d_layer_info": (_i, [_i, _i, C.POINTER(C.c_int64)]),
     "mvster_reg2d_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mvster_reg2d_tc_blob_floats": (C.c_size_t, []),
-    "mvster_reg2d_tc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_reg2d_tc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_conv3d_tc2_supported": (_i, [_i, _i, _i, _i, _i]),
+    "mvster_conv3d_tc2_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "mvster_upsample_bilinear_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mvster_nchw_to_nhwc_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -85,9 +85,11 @@ def pose(proj: Tensor, first_view: int = 1, n_views: Optional[int] = None) -> Te
 
 def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: int, attn_temp: float,
             cost: Optional[Tensor] = None, wsum: Optional[Tensor] = None, partial: bool = False,
-            accumulate: bool = False, generic: bool = False) -> Tensor:
+            accumulate: bool = False, generic: bool = False, group_cor: bool = True, fuse_d: bool = True) -> Tensor:
     """ref [B,H,W,C], srcs V x [B,Hs,Ws,C], pose [B,V,12], hypo [B,D,H,W] -> cost [B,D,H,W,G].
-    With ``partial`` the un-normalised accumulators are written to (cost, wsum)."""
+    With ``partial`` the un-normalised accumulators are written to (cost, wsum).  ``group_cor=False``:
+    per-channel squared difference, the cost volume then has C channels (pass G == C);
+    ``fuse_d=False``: the reference's attn_fuse_d=False weighting."""
     B, H, W, Cc = ref.shape
     _chk(ref, "ref")
     V = len(srcs)
@@ -108,6 +110,10 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
         chunk = srcs[v0:v0 + MAX_VIEWS]
         last = v0 + MAX_VIEWS >= V
         flags = 4 if generic else 0  # MVSTER_ET_GENERIC
+        if not fuse_d:
+            flags |= 8                # MVSTER_ET_NO_FUSE_D
+        if not group_cor:
+            flags |= 16               # MVSTER_ET_SQDIFF
         if partial or not last:
             flags |= ET_PARTIAL
         if accumulate or v0 > 0:
@@ -173,6 +179,69 @@ def conv3d_tc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd
     return y
 
 
+def conv3d_tc2(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, relu: bool = True,
+               skip: Optional[Tensor] = None, npass: int = 3) -> Tensor:
+    """Generation-2 tcgen05 conv (tile staged once per plane): w_packed from packing.pack_tc2_weights."""
+    _chk(x, "x")
+    _chk(w_packed, "w_packed")
+    B, D, H, W, Cin = x.shape
+    y = torch.empty((B, D, H, W, cout), device=x.device, dtype=torch.float32)
+    if bias is not None:
+        _chk(bias, "bias", (cout,))
+    if skip is not None:
+        _chk(skip, "skip", tuple(y.shape))
+    want = kd * 9 * Cin * max(cout, 16) * (2 if npass == 3 else 1)
+    if w_packed.numel() != want:
+        raise ValueError(f"w_packed has {w_packed.numel()} floats, expected {want}")
+    _lib.check(_lib.load().mvster_conv3d_tc2_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
+                                                 kd, int(relu), npass, _stream()), "mvster_conv3d_tc2_f32")
+    return y
+
+
+def hypo_init_linear(depth_values: Tensor, D: int, H: int, W: int) -> Tensor:
+    dv = _chk(depth_values, "depth_values")
+    B, n = dv.shape
+    out = torch.empty((B, D, H, W), device=dv.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_hypo_init_linear_f32(_ptr(dv), n, _ptr(out), B, D, H, W, _stream()), "mvster_hypo_init_linear_f32")
+    return out
+
+
+def hypo_schedule_linear(depth: Tensor, depth_values: Tensor, ratio: float, D: int, H: int, W: int) -> Tensor:
+    """depth [B,H/2,W/2] of the previous stage -> [B,D,H,W] (mvs4net_utils.py:88-99)."""
+    B = depth.shape[0]
+    _chk(depth, "depth", (B, H // 2, W // 2))
+    dv = _chk(depth_values, "depth_values")
+    out = torch.empty((B, D, H, W), device=depth.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_hypo_schedule_linear_f32(_ptr(depth), _ptr(dv), dv.shape[1], float(ratio), _ptr(out), B, D, H, W, _stream()),
+               "mvster_hypo_schedule_linear_f32")
+    return out
+
+
+def reg3d_layer_table(G: int, down_size: int) -> List[dict]:
+    lib = _lib.load()
+    out = []
+    for i in range(int(lib.mvster_reg3d_num_layers(down_size))):
+        info = (C.c_int64 * 8)()
+        _lib.check(lib.mvster_reg3d_layer_info(G, down_size, i, info), "mvster_reg3d_layer_info")
+        name = "prob" if info[7] == 100 else f"conv{info[7]}"
+        out.append(dict(name=name, cin=info[0], cout=info[1], stride=info[2], transposed=bool(info[3]), w_off=info[4], b_off=info[5], taps=info[6]))
+    return out
+
+
+def reg3d(blob: Tensor, cost: Tensor, down_size: int) -> Tensor:
+    """cost [B,D,H,W,G] -> logits [B,D,H,W] (the whole reg3d U-Net including its 3x3x3 prob layer)."""
+    _chk(cost, "cost")
+    _chk(blob, "blob")
+    B, D, H, W, G = cost.shape
+    lib = _lib.load()
+    if blob.numel() != int(lib.mvster_reg3d_blob_floats(G, down_size)):
+        raise ValueError(f"blob has {blob.numel()} floats, expected {int(lib.mvster_reg3d_blob_floats(G, down_size))}")
+    ws = torch.empty(int(lib.mvster_reg3d_workspace_floats(B, D, H, W)), device=cost.device, dtype=torch.float32)
+    out = torch.empty((B, D, H, W), device=cost.device, dtype=torch.float32)
+    _lib.check(lib.mvster_reg3d_f32(_ptr(blob), _ptr(cost), _ptr(out), _ptr(ws), B, G, D, H, W, down_size, _stream()), "mvster_reg3d_f32")
+    return out
+
+
 def reg2d_layer_table(G: int) -> List[dict]:
     lib = _lib.load()
     n_layers = 10
@@ -194,9 +263,10 @@ def reg2d_workspace_floats(B: int, D: int, H: int, W: int) -> int:
 
 
 def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: Optional[Tensor] = None,
-          tc_blob: Optional[Tensor] = None, npass: int = 3) -> Tensor:
+          tc_blob: Optional[Tensor] = None, npass: int = 3, kernel_gen: int = 1) -> Tensor:
     """cost [B,D,H,W,G] -> feat8 [B,D,H,W,8] (everything of reg2d except the 1x1x1 prob layer).
-    With ``tc_blob`` the three 3x3x3 layers run on the tensor cores (npass 3 = 3xTF32, 1 = TF32)."""
+    With ``tc_blob`` the three 3x3x3 layers run on the tensor cores (npass 3 = 3xTF32, 1 = TF32;
+    kernel_gen 1 = per-tap TMA kernel with packing.pack_tc_weights slabs, 2 = staged-tile kernel with pack_tc2_weights slabs)."""
     _chk(cost, "cost")
     _chk(blob, "blob")
     B, D, H, W, G = cost.shape
@@ -211,7 +281,7 @@ def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: O
     if tc_blob is not None:
         _chk(tc_blob, "tc_blob", (int(_lib.load().mvster_reg2d_tc_blob_floats()),))
         _lib.check(_lib.load().mvster_reg2d_tc_f32(_ptr(blob), _ptr(tc_blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W,
-                                                   npass, _stream()), "mvster_reg2d_tc_f32")
+                                                   npass, kernel_gen, _stream()), "mvster_reg2d_tc_f32")
         return out
     _lib.check(_lib.load().mvster_reg2d_f32(_ptr(blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W, _stream()),
                "mvster_reg2d_f32")

@@ -278,24 +278,24 @@ extern "C" size_t mvster_reg2d_workspace_floats(int B, int D, int H, int W) {
     return (size_t)28 * B * D * H * W;
 }
 
-static int reg2d_run(const float* blob, const float* tc_blob, int npass, const float* cost, float* feat8, float* ws,
+static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen, const float* cost, float* feat8, float* ws,
                      int B, int G, int D, int H, int W, mvster_stream_t stream);
 
 extern "C" int mvster_reg2d_f32(const float* blob, const float* cost, float* feat8, float* ws,
                                 int B, int G, int D, int H, int W, mvster_stream_t stream) {
-    return reg2d_run(blob, nullptr, 0, cost, feat8, ws, B, G, D, H, W, stream);
+    return reg2d_run(blob, nullptr, 0, 0, cost, feat8, ws, B, G, D, H, W, stream);
 }
 
 extern "C" size_t mvster_reg2d_tc_blob_floats(void) { return (size_t)2 * 27 * (16 * 16 + 32 * 32 + 64 * 64); }
 
 extern "C" int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* cost, float* feat8, float* ws,
-                                   int B, int G, int D, int H, int W, int npass, mvster_stream_t stream) {
+                                   int B, int G, int D, int H, int W, int npass, int kernel_gen, mvster_stream_t stream) {
     MVSTER_REQUIRE(tc_blob, "mvster_reg2d_tc_f32: tc_blob is null");
     MVSTER_REQUIRE(npass == 1 || npass == 3, "mvster_reg2d_tc_f32: npass must be 1 or 3");
-    return reg2d_run(blob, tc_blob, npass, cost, feat8, ws, B, G, D, H, W, stream);
+    return reg2d_run(blob, tc_blob, npass, kernel_gen, cost, feat8, ws, B, G, D, H, W, stream);
 }
 
-static int reg2d_run(const float* blob, const float* tc_blob, int npass, const float* cost, float* feat8, float* ws,
+static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen, const float* cost, float* feat8, float* ws,
                      int B, int G, int D, int H, int W, mvster_stream_t stream) {
     MVSTER_REQUIRE(blob && cost && feat8 && ws, "mvster_reg2d_f32: null pointer");
     MVSTER_REQUIRE(G == 4 || G == 8 || G == 16 || G == 32 || G == 64, "mvster_reg2d_f32: unsupported G=%d", G);
@@ -319,13 +319,205 @@ static int reg2d_run(const float* blob, const float* tc_blob, int npass, const f
             // conv2 / conv4 / conv6 (3x3x3, 69 % of the FLOPs) on the tcgen05 tensor cores; their [hi|lo]
             // K-major slabs sit back to back in tc_blob (2*27*Cin*Cout floats each).
             const size_t off = i == 2 ? 0 : (i == 4 ? (size_t)2 * 27 * 16 * 16 : (size_t)2 * 27 * (16 * 16 + 32 * 32));
-            rc = mvster_conv3d_tc_f32(in[i], tc_blob + off, blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i],
-                                      L[i].cin, L[i].cout, 3, 1, npass, stream);
+            rc = (gen == 2 ? mvster_conv3d_tc2_f32 : mvster_conv3d_tc_f32)(in[i], tc_blob + off, blob + info[6], skip[i], out[i], B, D,
+                                                                            H / div[i], W / div[i], L[i].cin, L[i].cout, 3, 1, npass, stream);
         } else {
             rc = run_conv(in[i], blob + info[5], blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i],
                           L[i].cin, L[i].cout, L[i].kd, 1, L[i].s, L[i].transposed, 1, st);
         }
         if (rc != MVSTER_OK) return rc;
     }
+    return MVSTER_OK;
+}
+
+// ================================================================================================
+// reg3d (mvs4net_utils.py:914-965): full 3-D U-Net - 3x3x3 kernels, stride 2 along D as well,
+// depth `down_size` in {1,2,3} (MVS4Net.py:48: 3,3,2,2 per stage), prob = 3x3x3 conv 8 -> 1 without bias.
+// ================================================================================================
+namespace mvster {
+
+// ConvTranspose3d(3, stride=2, padding=1, output_padding=1): out[o] += in[i] * w[k] with o = 2i - 1 + k.
+// Gather form: one thread per output voxel x COUT_T channels; only taps with matching parity contribute
+// (27/8 on average).  reg3d is an optional path of the reference, so simplicity wins over speed here.
+template <int CIN, int COUT_T>
+__global__ void __launch_bounds__(128) deconv3d_gather_kernel(const ConvArgs a) {
+    extern __shared__ __align__(16) float w_s[];  // [27][CIN][COUT_T]
+    const int cg = blockIdx.y;
+    for (int i = threadIdx.x; i < 27 * CIN * COUT_T; i += blockDim.x) {
+        const int o = i % COUT_T, rest = i / COUT_T;
+        w_s[i] = __ldg(a.w + (long long)rest * a.cout + cg * COUT_T + o);
+    }
+    __syncthreads();
+    const long long nvox = (long long)a.B * a.Do * a.Ho * a.Wo;
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= nvox) return;
+    const int ox = (int)(v % a.Wo), oy = (int)((v / a.Wo) % a.Ho);
+    const int oz = (int)((v / ((long long)a.Wo * a.Ho)) % a.Do), b = (int)(v / ((long long)a.Wo * a.Ho * a.Do));
+    float acc[COUT_T];
+#pragma unroll
+    for (int o = 0; o < COUT_T; ++o) acc[o] = a.bias ? __ldg(a.bias + cg * COUT_T + o) : 0.f;
+    for (int kz = 0; kz < 3; ++kz) {
+        const int tz = oz + 1 - kz;
+        if (tz < 0 || (tz & 1) || (tz >> 1) >= a.Di) continue;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ty = oy + 1 - ky;
+            if (ty < 0 || (ty & 1) || (ty >> 1) >= a.Hi) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tx = ox + 1 - kx;
+                if (tx < 0 || (tx & 1) || (tx >> 1) >= a.Wi) continue;
+                const float4* px = reinterpret_cast<const float4*>(
+                    a.x + ((((long long)b * a.Di + (tz >> 1)) * a.Hi + (ty >> 1)) * a.Wi + (tx >> 1)) * CIN);
+                const float* wt = w_s + ((kz * 3 + ky) * 3 + kx) * CIN * COUT_T;
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                    const float4 t = __ldg(px + c4);
+                    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float* wr = wt + (c4 * 4 + j) * COUT_T;
+#pragma unroll
+                        for (int o = 0; o < COUT_T; ++o) acc[o] = fmaf(tv[j], wr[o], acc[o]);
+                    }
+                }
+            }
+        }
+    }
+    const long long off = v * a.cout + cg * COUT_T;
+#pragma unroll
+    for (int o = 0; o < COUT_T; ++o) {
+        float r = acc[o];
+        if (a.relu) r = fmaxf(r, 0.f);
+        if (a.skip) r += __ldg(a.skip + off + o);
+        a.y[off + o] = r;
+    }
+}
+
+template <int CIN>
+static int launch_deconv3d(const ConvArgs& a, cudaStream_t st) {
+    constexpr int CT = 8;
+    const size_t smem = (size_t)27 * CIN * CT * sizeof(float);
+    auto k = deconv3d_gather_kernel<CIN, CT>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long n = (long long)a.B * a.Do * a.Ho * a.Wo;
+    k<<<dim3(ceil_div(n, 128), a.cout / CT), 128, smem, st>>>(a);
+    return check_launch("deconv3d_gather_kernel");
+}
+
+static int run_deconv3d(const float* x, const float* w, const float* bias, const float* skip, float* y,
+                        int B, int Di, int Hi, int Wi, int Cin, int Cout, cudaStream_t st) {
+    MVSTER_REQUIRE(Cout % 8 == 0, "reg3d transposed conv needs Cout %% 8 == 0 (got %d)", Cout);
+    ConvArgs a;
+    a.x = x; a.w = w; a.bias = bias; a.skip = skip; a.y = y;
+    a.B = B; a.Di = Di; a.Hi = Hi; a.Wi = Wi; a.Do = 2 * Di; a.Ho = 2 * Hi; a.Wo = 2 * Wi;
+    a.cout = Cout; a.kd = 3; a.sd = 2; a.s = 2; a.relu = 1;
+    switch (Cin) {
+        case 16: return launch_deconv3d<16>(a, st);
+        case 32: return launch_deconv3d<32>(a, st);
+        case 64: return launch_deconv3d<64>(a, st);
+    }
+    set_error("reg3d transposed conv: unsupported Cin=%d", Cin);
+    return MVSTER_ERR_ARG;
+}
+
+// layer order in the reg3d blob: only the layers that exist for `down_size`, in this order
+struct Layer3 { const char* name; int cin, cout, stride, transposed, level_in; };
+static int reg3d_layers(int G, int down, Layer3 (&L)[12]) {
+    int n = 0;
+    L[n++] = {"conv0", G, 8, 1, 0, 0};
+    L[n++] = {"conv1", 8, 16, 2, 0, 0};
+    L[n++] = {"conv2", 16, 16, 1, 0, 1};
+    if (down >= 2) { L[n++] = {"conv3", 16, 32, 2, 0, 1}; L[n++] = {"conv4", 32, 32, 1, 0, 2}; }
+    if (down >= 3) { L[n++] = {"conv5", 32, 64, 2, 0, 2}; L[n++] = {"conv6", 64, 64, 1, 0, 3}; L[n++] = {"conv7", 64, 32, 2, 1, 3}; }
+    if (down >= 2) L[n++] = {"conv9", 32, 16, 2, 1, 2};
+    L[n++] = {"conv11", 16, 8, 2, 1, 1};
+    L[n++] = {"prob", 8, 1, 1, 0, 0};
+    return n;
+}
+
+}  // namespace mvster
+
+extern "C" int mvster_reg3d_num_layers(int down_size) {
+    mvster::Layer3 L[12];
+    return (down_size >= 1 && down_size <= 3) ? mvster::reg3d_layers(8, down_size, L) : 0;
+}
+
+/* info[8] = {Cin, Cout, stride, transposed, w_offset, bias_offset (== -1 for prob: no bias), n_taps (27), name id
+ * (0,1,2,3,4,5,6,7,9,11 for conv*, 100 for prob)} */
+extern "C" int mvster_reg3d_layer_info(int G, int down_size, int layer, int64_t* info) {
+    mvster::Layer3 L[12];
+    MVSTER_REQUIRE(info && down_size >= 1 && down_size <= 3, "mvster_reg3d_layer_info: bad arguments");
+    const int n = mvster::reg3d_layers(G, down_size, L);
+    MVSTER_REQUIRE(layer >= 0 && layer < n, "mvster_reg3d_layer_info: bad layer %d", layer);
+    int64_t off = 0;
+    for (int i = 0; i <= layer; ++i) {
+        const int64_t nw = 27ll * L[i].cin * L[i].cout;
+        const bool has_bias = i != n - 1;
+        if (i == layer) {
+            info[0] = L[i].cin; info[1] = L[i].cout; info[2] = L[i].stride; info[3] = L[i].transposed;
+            info[4] = off; info[5] = has_bias ? off + nw : -1; info[6] = 27;
+            info[7] = i == n - 1 ? 100 : atoi(L[i].name + 4);
+        }
+        off += nw + (has_bias ? L[i].cout : 0);
+    }
+    return MVSTER_OK;
+}
+
+extern "C" size_t mvster_reg3d_blob_floats(int G, int down_size) {
+    int64_t info[8];
+    const int n = mvster_reg3d_num_layers(down_size);
+    if (n == 0 || mvster_reg3d_layer_info(G, down_size, n - 1, info) != MVSTER_OK) return 0;
+    return (size_t)(info[4] + 27 * info[0] * info[1]);
+}
+
+extern "C" size_t mvster_reg3d_workspace_floats(int B, int D, int H, int W) { return (size_t)26 * B * D * H * W; }
+
+extern "C" int mvster_reg3d_f32(const float* blob, const float* cost, float* logits, float* ws,
+                                int B, int G, int D, int H, int W, int down_size, mvster_stream_t stream) {
+    using namespace mvster;
+    MVSTER_REQUIRE(blob && cost && logits && ws, "mvster_reg3d_f32: null pointer");
+    MVSTER_REQUIRE(down_size >= 1 && down_size <= 3, "mvster_reg3d_f32: down_size=%d (1..3)", down_size);
+    const int m = 1 << down_size;
+    MVSTER_REQUIRE(D % m == 0 && H % m == 0 && W % m == 0, "mvster_reg3d_f32: D,H,W must be multiples of %d", m);
+    MVSTER_REQUIRE(G == 4 || G == 8 || G == 16 || G == 32 || G == 64, "mvster_reg3d_f32: unsupported G=%d", G);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)B * D * H * W;
+    // activations: c0 8N | c1 2N | c2 2N | c3 .5N | c4 .5N | c5 .125N | c6 .125N | u7 .5N | u9 2N | u11 8N  (< 26N)
+    float* c0 = ws;            float* c1 = c0 + 8 * N;       float* c2 = c1 + 2 * N;      float* c3 = c2 + 2 * N;
+    float* c4 = c3 + N / 2;    float* c5 = c4 + N / 2;       float* c6 = c5 + N / 8;      float* u7 = c6 + N / 8;
+    float* u9 = u7 + N / 2;    float* u11 = u9 + 2 * N;
+    Layer3 L[12];
+    const int n = reg3d_layers(G, down_size, L);
+    auto W_ = [&](int i, int64_t (&info)[8]) { mvster_reg3d_layer_info(G, down_size, i, info); };
+    int rc = MVSTER_OK, li = 0;
+    int64_t info[8];
+    auto conv = [&](const float* x, float* y, int lvl, int cin, int cout, int stride, int relu) {
+        W_(li++, info);
+        const int d = D >> lvl, h = H >> lvl, w = W >> lvl;
+        return run_conv(x, blob + info[4], info[5] >= 0 ? blob + info[5] : nullptr, nullptr, y, B, d, h, w, cin, cout, 3, stride, stride, 0, relu, st);
+    };
+    auto up = [&](const float* x, const float* skip, float* y, int lvl, int cin, int cout) {
+        W_(li++, info);
+        return run_deconv3d(x, blob + info[4], blob + info[5], skip, y, B, D >> lvl, H >> lvl, W >> lvl, cin, cout, st);
+    };
+    if ((rc = conv(cost, c0, 0, G, 8, 1, 1))) return rc;
+    if ((rc = conv(c0, c1, 0, 8, 16, 2, 1))) return rc;
+    if ((rc = conv(c1, c2, 1, 16, 16, 1, 1))) return rc;
+    const float* x = c2;
+    if (down_size >= 2) {
+        if ((rc = conv(c2, c3, 1, 16, 32, 2, 1))) return rc;
+        if ((rc = conv(c3, c4, 2, 32, 32, 1, 1))) return rc;
+        x = c4;
+        if (down_size >= 3) {
+            if ((rc = conv(c4, c5, 2, 32, 64, 2, 1))) return rc;
+            if ((rc = conv(c5, c6, 3, 64, 64, 1, 1))) return rc;
+            if ((rc = up(c6, c4, u7, 3, 64, 32))) return rc;   // x = conv4 + conv7(x)
+            x = u7;
+        }
+        if ((rc = up(x, c2, u9, 2, 32, 16))) return rc;        // x = conv2 + conv9(x)
+        x = u9;
+    }
+    if ((rc = up(x, c0, u11, 1, 16, 8))) return rc;            // x = conv0 + conv11(x)
+    if ((rc = conv(u11, logits, 0, 8, 1, 1, 0))) return rc;    // prob: 3x3x3, no bias, no ReLU
+    (void)n;
     return MVSTER_OK;
 }

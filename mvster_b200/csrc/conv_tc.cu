@@ -42,13 +42,19 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
+    unsigned long long t0 = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 28)) __trap();  // a protocol bug must fail loudly, never hang the GPU
+        if (!done && (spin & 63u) == 63u) {  // watchdog: a protocol bug must fail loudly within ~2 s, never hang the GPU
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,

@@ -58,9 +58,14 @@ __device__ __forceinline__ float group_sum(float s) {
     return s;
 }
 
-template <int CPG, int G, int D>
+// GROUP = true : cost[g] = mean over the lane's CPG channels of ref*warped (group correlation, :1037-1040)
+// GROUP = false: cost[c] = (ref[c] - warped[c])^2 per channel (:1042); the G lanes of a pixel then
+//                own CPG output channels each and the cost volume has C = G*CPG channels.
+template <int CPG, int G, int D, bool GROUP>
 __global__ void __launch_bounds__(256) et_fuse_kernel(const EtArgs a) {
     constexpr int C = CPG * G;
+    constexpr int NOUT = GROUP ? 1 : CPG;   // cost channels per lane
+    constexpr int CO = GROUP ? G : C;       // cost channels per voxel
     const int g = threadIdx.x % G;
     const long long npix = (long long)a.B * a.H * a.W;
     long long pix = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / G;
@@ -75,21 +80,27 @@ __global__ void __launch_bounds__(256) et_fuse_kernel(const EtArgs a) {
     float ref[CPG];
     load_vec<CPG>(a.ref + pix * C + g * CPG, ref);
 
-    float dep[D], acc[D], ws[D];
+    float dep[D], acc[NOUT][D], ws[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) dep[d] = __ldg(a.hypo + ((long long)b * D + d) * plane + pix_in_b);
     if (a.flags & MVSTER_ET_ACCUMULATE) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const long long o = ((long long)b * D + d) * plane + pix_in_b;
-            acc[d] = a.cost[o * G + g];
+#pragma unroll
+            for (int n = 0; n < NOUT; ++n) acc[n][d] = a.cost[o * CO + g * NOUT + n];
             ws[d] = a.wsum[o];
         }
     } else {
         const float seed = (a.flags & MVSTER_ET_PARTIAL) ? 0.f : 1e-8f;  // mvs4net_utils.py:1022
 #pragma unroll
-        for (int d = 0; d < D; ++d) { acc[d] = 0.f; ws[d] = seed; }
+        for (int d = 0; d < D; ++d) {
+            ws[d] = seed;
+#pragma unroll
+            for (int n = 0; n < NOUT; ++n) acc[n][d] = 0.f;
+        }
     }
+    const bool fuse_d = !(a.flags & MVSTER_ET_NO_FUSE_D);
 
     const float fx = (float)x, fy = (float)y;
     const float half_w = 0.5f * (float)(a.Ws - 1);  // (Ws-1)/2, exact in fp32
@@ -105,7 +116,7 @@ __global__ void __launch_bounds__(256) et_fuse_kernel(const EtArgs a) {
         const float tx = __ldg(P + 9), ty = __ldg(P + 10), tz = __ldg(P + 11);
         const float* S = a.src[v] + (long long)b * a.Hs * a.Ws * C + g * CPG;
 
-        float cor[D];
+        float cor[NOUT][D], tot[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             // separately rounded mul / add / div, as the reference's tensor ops (:34-45)
@@ -140,26 +151,38 @@ __global__ void __launch_bounds__(256) et_fuse_kernel(const EtArgs a) {
 #pragma unroll
             for (int c = 0; c < CPG; ++c) {
                 const float warped = t_nw[c] * w_nw + t_ne[c] * w_ne + t_sw[c] * w_sw + t_se[c] * w_se;
-                dot += ref[c] * warped;
+                if constexpr (GROUP) {
+                    dot += ref[c] * warped;
+                } else {
+                    const float df = __fsub_rn(ref[c], warped);
+                    cor[c][d] = __fmul_rn(df, df);  // :1042
+                    dot += cor[c][d];
+                }
             }
-            cor[d] = dot * (1.f / CPG);  // .mean(2), :1040
+            if constexpr (GROUP) { cor[0][d] = dot * (1.f / CPG); tot[d] = cor[0][d]; }  // .mean(2), :1040
+            else tot[d] = dot;
         }
 
-        // attention over the D hypotheses of this pixel (:1053)
+        // attention over the D hypotheses of this pixel: softmax_d(sum over all cost channels [/ temp]) (:1049-1053)
         float lg[D], m = -INFINITY;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            lg[d] = __fdiv_rn(group_sum<G>(cor[d]), a.attn_temp);
+            const float s = group_sum<G>(tot[d]);
+            lg[d] = fuse_d ? __fdiv_rn(s, a.attn_temp) : s;
             m = fmaxf(m, lg[d]);
         }
         float se = 0.f;
 #pragma unroll
         for (int d = 0; d < D; ++d) { lg[d] = expf(lg[d] - m); se += lg[d]; }
+        float wmax = 0.f;  // attn_fuse_d=False: one scalar weight per pixel and view = max_d softmax (:1049)
+#pragma unroll
+        for (int d = 0; d < D; ++d) wmax = fmaxf(wmax, __fdiv_rn(lg[d], se));
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const float w = __fdiv_rn(__fdiv_rn(lg[d], se), a.sqrt_c);
-            ws[d] = __fadd_rn(ws[d], w);                         // :1054
-            acc[d] = __fadd_rn(acc[d], __fmul_rn(w, cor[d]));    // :1055
+            const float w = fuse_d ? __fdiv_rn(__fdiv_rn(lg[d], se), a.sqrt_c) : wmax;
+            ws[d] = __fadd_rn(ws[d], w);                                  // :1050 / :1054
+#pragma unroll
+            for (int n = 0; n < NOUT; ++n) acc[n][d] = __fadd_rn(acc[n][d], __fmul_rn(w, cor[n][d]));  // :1051 / :1055
         }
     }
 
@@ -168,7 +191,8 @@ __global__ void __launch_bounds__(256) et_fuse_kernel(const EtArgs a) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const long long o = ((long long)b * D + d) * plane + pix_in_b;
-        a.cost[o * G + g] = partial ? acc[d] : __fdiv_rn(acc[d], ws[d]);  // :1060
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) a.cost[o * CO + g * NOUT + n] = partial ? acc[n][d] : __fdiv_rn(acc[n][d], ws[d]);  // :1058-1060
         if (partial && g == 0) a.wsum[o] = ws[d];
     }
 }
@@ -185,7 +209,8 @@ namespace mvster {
 template <int CPG, int G, int D>
 static int launch_et(const EtArgs& a, cudaStream_t st) {
     const long long threads = (long long)a.B * a.H * a.W * G;
-    et_fuse_kernel<CPG, G, D><<<ceil_div(threads, 256), 256, 0, st>>>(a);
+    if (a.flags & MVSTER_ET_SQDIFF) et_fuse_kernel<CPG, G, D, false><<<ceil_div(threads, 256), 256, 0, st>>>(a);
+    else et_fuse_kernel<CPG, G, D, true><<<ceil_div(threads, 256), 256, 0, st>>>(a);
     return check_launch("et_fuse_kernel");
 }
 
@@ -220,6 +245,11 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     MVSTER_REQUIRE(ref && src_host && pose && hypo && cost, "mvster_et_fuse_f32: null pointer");
     MVSTER_REQUIRE(V >= 1 && V <= MVSTER_MAX_VIEWS, "mvster_et_fuse_f32: V=%d outside 1..%d", V, MVSTER_MAX_VIEWS);
     MVSTER_REQUIRE(B > 0 && H > 0 && W > 0 && Hs > 0 && Ws > 0, "mvster_et_fuse_f32: bad shape");
+    if (flags & MVSTER_ET_SQDIFF) {  // per-channel cost: the cost volume has C channels; pick the lane count here
+        MVSTER_REQUIRE(G == C, "mvster_et_fuse_f32: with MVSTER_ET_SQDIFF the cost volume has C channels (pass G == C)");
+        MVSTER_REQUIRE(C == 8 || C == 16 || C == 32 || C == 64, "mvster_et_fuse_f32: SQDIFF supports C in {8,16,32,64}, got %d", C);
+        G = C >= 32 ? 8 : 4;
+    }
     MVSTER_REQUIRE(G == 4 || G == 8, "mvster_et_fuse_f32: unsupported G=%d (4 or 8)", G);
     MVSTER_REQUIRE(C % G == 0, "mvster_et_fuse_f32: C=%d not divisible by G=%d", C, G);
     MVSTER_REQUIRE(!(flags & (MVSTER_ET_PARTIAL | MVSTER_ET_ACCUMULATE)) || wsum,
@@ -236,7 +266,8 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     a.flags = flags;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = MVSTER_OK;
-    if (!(flags & MVSTER_ET_GENERIC) && try_launch_tiled(a, C, G, D, st, &rc)) return rc;
+    const bool plain = !(flags & (MVSTER_ET_GENERIC | MVSTER_ET_SQDIFF | MVSTER_ET_NO_FUSE_D));
+    if (plain && try_launch_tiled(a, C, G, D, st, &rc)) return rc;
     return G == 4 ? dispatch_cpg<4>(a, C / G, D, st) : dispatch_cpg<8>(a, C / G, D, st);
 }
 

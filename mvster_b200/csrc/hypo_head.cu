@@ -289,3 +289,77 @@ extern "C" int mvster_pose_f32(const float* proj, float* pose, int B, int Nv, in
     mvster::pose_kernel<<<mvster::ceil_div((long long)B * V, 64), 64, 0, (cudaStream_t)stream>>>(proj, pose, B, Nv, first_view, V);
     return mvster::check_launch("pose_kernel");
 }
+
+// ---- linear-depth hypotheses (inverse_depth=False) --------------------------------------------
+//   init_range      models/mvs4net_utils.py:61-69    d_k = d_min + k * (d_max - d_min)/(D-1)
+//   schedule_range  models/mvs4net_utils.py:88-99    per coarse pixel [depth -+ D/2*itv] in D samples,
+//                   trilinear (align_corners) x2 up-sampling; itv = ratio_k * (d_max - d_min)/n_dv  (MVS4Net.py:61-63,97)
+namespace mvster {
+
+__global__ void hypo_init_linear_kernel(const float* __restrict__ dv, int n_dv, float* __restrict__ hypo,
+                                        int B, int D, long long plane) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)B * D * plane) return;
+    const int d = (int)((i / plane) % D), b = (int)(i / (plane * D));
+    const float lo = __ldg(dv + (long long)b * n_dv), hi = __ldg(dv + (long long)b * n_dv + n_dv - 1);
+    const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(D - 1));
+    hypo[i] = __fadd_rn(lo, __fmul_rn((float)d, step));
+}
+
+template <int D>
+__global__ void hypo_schedule_linear_kernel(const float* __restrict__ depth, const float* __restrict__ dv, int n_dv, float ratio,
+                                            float* __restrict__ hypo, int B, int H, int W) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long plane = (long long)H * W;
+    if (i >= (long long)B * plane) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / plane);
+    const int Hc = H / 2, Wc = W / 2;
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    ac_index(y, Hc, H, y0, y1, ly0, ly1);
+    ac_index(x, Wc, W, x0, x1, lx0, lx1);
+    // depth_interval = (d_max - d_min) / n_dv (MVS4Net.py:63), times depth_interals_ratio[k]
+    const float itv = __fmul_rn(ratio, __fdiv_rn(__fsub_rn(__ldg(dv + (long long)b * n_dv + n_dv - 1), __ldg(dv + (long long)b * n_dv)), (float)n_dv));
+    const float half_span = __fmul_rn((float)D * 0.5f, itv);
+    const float* p = depth + (long long)b * Hc * Wc;
+    const float c[4] = {__ldg(p + (long long)y0 * Wc + x0), __ldg(p + (long long)y0 * Wc + x1),
+                        __ldg(p + (long long)y1 * Wc + x0), __ldg(p + (long long)y1 * Wc + x1)};
+    float lo[4], st[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        lo[k] = __fsub_rn(c[k], half_span);
+        st[k] = __fdiv_rn(__fsub_rn(__fadd_rn(c[k], half_span), lo[k]), (float)(D - 1));
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float s[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] = __fadd_rn(lo[k], __fmul_rn((float)d, st[k]));
+        const float top = __fadd_rn(__fmul_rn(lx0, s[0]), __fmul_rn(lx1, s[1]));
+        const float bot = __fadd_rn(__fmul_rn(lx0, s[2]), __fmul_rn(lx1, s[3]));
+        hypo[((long long)b * D + d) * plane + (long long)y * W + x] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+    }
+}
+
+}  // namespace mvster
+
+extern "C" int mvster_hypo_init_linear_f32(const float* depth_values, int n_dv, float* hypo,
+                                           int B, int D, int H, int W, mvster_stream_t stream) {
+    MVSTER_REQUIRE(depth_values && hypo, "mvster_hypo_init_linear_f32: null pointer");
+    MVSTER_REQUIRE(n_dv >= 1 && B > 0 && D >= 2 && H > 0 && W > 0, "mvster_hypo_init_linear_f32: bad shape");
+    const long long plane = (long long)H * W, n = (long long)B * D * plane;
+    mvster::hypo_init_linear_kernel<<<mvster::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(depth_values, n_dv, hypo, B, D, plane);
+    return mvster::check_launch("hypo_init_linear_kernel");
+}
+
+extern "C" int mvster_hypo_schedule_linear_f32(const float* depth, const float* depth_values, int n_dv, float ratio, float* hypo,
+                                               int B, int D, int H, int W, mvster_stream_t stream) {
+    MVSTER_REQUIRE(depth && depth_values && hypo, "mvster_hypo_schedule_linear_f32: null pointer");
+    MVSTER_REQUIRE(B > 0 && n_dv >= 1 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mvster_hypo_schedule_linear_f32: H,W must be even");
+    const long long n = (long long)B * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (D == 4) mvster::hypo_schedule_linear_kernel<4><<<mvster::ceil_div(n, 256), 256, 0, st>>>(depth, depth_values, n_dv, ratio, hypo, B, H, W);
+    else if (D == 8) mvster::hypo_schedule_linear_kernel<8><<<mvster::ceil_div(n, 256), 256, 0, st>>>(depth, depth_values, n_dv, ratio, hypo, B, H, W);
+    else MVSTER_REQUIRE(false, "mvster_hypo_schedule_linear_f32: unsupported D=%d (4 or 8)", D);
+    return mvster::check_launch("hypo_schedule_linear_kernel");
+}

@@ -4,16 +4,20 @@ One engine per CUDA device.  It owns the folded/packed regulariser weights for t
 and nothing else; feature extraction (FPN4, outside the named hot path) runs through the
 module's own ``feature`` sub-module in channels-last memory format so its outputs are
 already the NHWC tensors the kernels consume.
+
+Configuration coverage: reg2d and reg3d; group correlation and per-channel squared difference
+(``group_cor=False``); ``attn_fuse_d`` on/off; inverse and linear depth sampling.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
 from . import capi, packing
 
 Tensor = torch.Tensor
+REG3D_DOWN = (3, 3, 2, 2)  # MVS4Net.py:48
 
 
 class StagePlan:
@@ -22,26 +26,25 @@ class StagePlan:
     def __init__(self, k: int, net):
         self.k = k
         self.D = net.stage_splits[k]
-        self.G = net.group_cor_dim[k]
+        self.C = net.feature.out_channels[k]
+        self.group_cor = bool(net.group_cor)
+        self.G = net.group_cor_dim[k] if self.group_cor else self.C  # channels of the cost volume
         self.split_itv = float(net.depth_interals_ratio[k])
-        self.up = 2 ** (net.num_stage - 1 - k)  # confidence up-sampling factor, mvs4net_utils.py:1077 (3 - stage_idx)
+        self.up = 2 ** (3 - k)  # confidence up-sampling factor, mvs4net_utils.py:1077
+        self.down = REG3D_DOWN[k] if net.reg_net == "reg3d" else 0
 
 
 def check_supported(net) -> None:
     bad = []
-    if net.reg_net != "reg2d":
-        bad.append("reg_net='reg3d'")
-    if not net.group_cor:
-        bad.append("group_cor=False")
-    if not net.inverse_depth:
-        bad.append("inverse_depth=False")
-    if not net.stagenet.attn_fuse_d:
-        bad.append("attn_fuse_d=False")
     if net.num_stage != 4:
         bad.append(f"num_stage={net.num_stage}")
+    for k in range(min(net.num_stage, 4)):
+        if net.stage_splits[k] not in (4, 8):
+            bad.append(f"stage_splits[{k}]={net.stage_splits[k]} (4 or 8)")
+        if net.group_cor and net.group_cor_dim[k] not in (4, 8):
+            bad.append(f"group_cor_dim[{k}]={net.group_cor_dim[k]} (4 or 8)")
     if bad:
-        raise NotImplementedError("the CUDA inference path does not cover: " + ", ".join(bad) +
-                                  " (shipped config: reg2d, group_cor, inverse_depth, attn_fuse_d, 4 stages)")
+        raise NotImplementedError("the CUDA inference path does not cover: " + ", ".join(bad))
 
 
 class InferenceEngine:
@@ -59,7 +62,10 @@ class InferenceEngine:
         self.stage_weights = []
         with torch.cuda.device(self.device):
             for p in self.plans:
-                packed = packing.pack_reg2d(sd, f"reg.{p.k}", capi.reg2d_layer_table(p.G))
+                if net.reg_net == "reg2d":
+                    packed = packing.pack_reg2d(sd, f"reg.{p.k}", capi.reg2d_layer_table(p.G))
+                else:
+                    packed = {"blob": packing.pack_reg3d(sd, f"reg.{p.k}", capi.reg3d_layer_table(p.G, p.down))}
                 self.stage_weights.append({k: v.to(self.device) for k, v in packed.items()})
 
     # ------------------------------------------------------------------ full forward
@@ -79,23 +85,41 @@ class InferenceEngine:
             return self.run_cascade(net, feats, proj_matrices, depth_values, shard=shard)
 
     # ------------------------------------------------------------------ the hot path
-    def _aggregate(self, p: StagePlan, ref: Tensor, srcs: List[Tensor], proj: Tensor, hypo: Tensor, temp: float, shard) -> Tensor:
+    def _aggregate(self, p: StagePlan, ref: Tensor, srcs: List[Tensor], proj: Tensor, hypo: Tensor, temp: float,
+                   fuse_d: bool, shard) -> Tensor:
+        kw = dict(group_cor=p.group_cor, fuse_d=fuse_d)
         if shard is None:
-            return capi.et_fuse(ref, srcs, capi.pose(proj), hypo, p.G, temp)
+            return capi.et_fuse(ref, srcs, capi.pose(proj), hypo, p.G, temp, **kw)
         from . import sharding
         B, H, W, _ = ref.shape
 
         def partial(acc, wsum):
             pose = capi.pose(proj, first_view=shard.first_view, n_views=shard.count)
-            capi.et_fuse(ref, srcs, pose, hypo, p.G, temp, cost=acc, wsum=wsum, partial=True)
+            capi.et_fuse(ref, srcs, pose, hypo, p.G, temp, cost=acc, wsum=wsum, partial=True, **kw)
 
         return sharding.sharded_aggregate(partial, capi.et_normalize, (B, p.D, H, W, p.G), shard, self.device)
+
+    def _regularise(self, net, p: StagePlan, wts: Dict[str, Tensor], cost: Tensor, hypo: Tensor) -> Dict[str, Tensor]:
+        inverse = bool(net.inverse_depth)
+        if net.reg_net == "reg3d":
+            logits = capi.reg3d(wts["blob"], cost, p.down)
+            return capi.head(hypo, p.split_itv, logits=logits, inverse=inverse)
+        prec = getattr(net, "reg_precision", "fp32")
+        if prec == "fp32":      # exact fp32 FMA on the CUDA cores for every layer
+            feat8 = capi.reg2d(wts["blob"], cost)
+        else:                   # 3x3x3 layers on tcgen05: "3xtf32" (fp32-faithful) or "tf32"
+            gen = int(getattr(net, "tc_kernel_gen", 1))
+            feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc2_blob" if gen == 2 else "tc_blob"],
+                               npass=3 if prec == "3xtf32" else 1, kernel_gen=gen)
+        return capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=inverse)
 
     def run_cascade(self, net, feats: List[List[Tensor]], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
                     attn_temp: Optional[float] = None, shard=None) -> Dict:
         """feats[k][i]: NHWC features at stage k; i = 0 is the reference view, i >= 1 the source
         views (all of them, or with ``shard`` this rank's ``shard.views`` in order)."""
         temp = float(net.stagenet.attn_temp if attn_temp is None else attn_temp)
+        fuse_d = bool(net.stagenet.attn_fuse_d)
+        inverse = bool(net.inverse_depth)
         outputs: Dict = {}
         prev = None
         dv = depth_values.to(device=self.device, dtype=torch.float32).contiguous()
@@ -105,22 +129,20 @@ class InferenceEngine:
             B, H, W, C = ref.shape
             proj = proj_matrices[key].to(device=self.device, dtype=torch.float32).contiguous()
             if p.k == 0:
-                hypo = capi.hypo_init_inverse(dv, p.D, H, W)
-            else:
+                hypo = capi.hypo_init_inverse(dv, p.D, H, W) if inverse else capi.hypo_init_linear(dv, p.D, H, W)
+            elif inverse:
                 hypo = capi.hypo_schedule_inverse(prev["inverse_min_depth"], prev["inverse_max_depth"], p.D, H, W)
-            cost = self._aggregate(p, ref, srcs, proj, hypo, temp, shard)
-            prec = getattr(net, "reg_precision", "fp32")
-            if prec == "fp32":      # exact fp32 FMA on the CUDA cores for every layer
-                feat8 = capi.reg2d(wts["blob"], cost)
-            else:                   # 3x3x3 layers on tcgen05: "3xtf32" (fp32-faithful) or "tf32"
-                feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc_blob"], npass=3 if prec == "3xtf32" else 1)
-            h = capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=True)
+            else:
+                hypo = capi.hypo_schedule_linear(prev["depth"], dv, p.split_itv, p.D, H, W)
+            cost = self._aggregate(p, ref, srcs, proj, hypo, temp, fuse_d, shard)
+            h = self._regularise(net, p, wts, cost, hypo)
             out = {"depth": h["depth"],
                    "photometric_confidence": capi.upsample_bilinear(h["conf_low"], p.up),
                    "hypo_depth": hypo,
-                   "attn_weight": h["attn_weight"],
-                   "inverse_min_depth": h["inverse_min_depth"],
-                   "inverse_max_depth": h["inverse_max_depth"]}
+                   "attn_weight": h["attn_weight"]}
+            if inverse:
+                out["inverse_min_depth"] = h["inverse_min_depth"]
+                out["inverse_max_depth"] = h["inverse_max_depth"]
             if net.mono:
                 out["mono_feat"] = ref.permute(0, 3, 1, 2)  # [B,C,H,W] view, as mvs4net_utils.py:1092
             prev = out

@@ -249,6 +249,7 @@ class MVS4net(nn.Module):
         # arithmetic of the 3x3x3 regulariser layers on the CUDA inference path: "fp32" (CUDA cores, exact),
         # "3xtf32" (tcgen05, error-compensated, fp32-faithful) or "tf32" (tcgen05, single pass)
         self.reg_precision = os.environ.get("MVSTER_REG_PRECISION", "fp32")
+        self.tc_kernel_gen = int(os.environ.get("MVSTER_TC_GEN", "1"))  # 1 = per-tap TMA kernel, 2 = staged-tile kernel
         self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)
 
     def set_view_shard(self, shard) -> None:

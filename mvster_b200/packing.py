@@ -53,6 +53,48 @@ def pack_tc_weights(w: Tensor, npass: int = 3) -> Tensor:
     return torch.cat([hi.reshape(-1), lo.reshape(-1)])
 
 
+def pack_tc2_weights(w: Tensor, npass: int = 3) -> Tensor:
+    """[taps][Cin][Cout] fp32 -> slabs for the staged-tile tcgen05 kernel (conv_tc2.cu):
+    [hi | lo] x [taps][Cin/16][N][16] with N = max(Cout, 16) (zero rows pad Cout = 8 to the minimum UMMA N)."""
+    taps, cin, cout = w.shape
+    if cin % 16:
+        raise ValueError(f"Cin={cin} is not a multiple of 16")
+    n = max(cout, 16)
+    wp = torch.zeros((taps, cin, n), dtype=torch.float32)
+    wp[:, :, :cout] = w.float()
+    slabs = wp.reshape(taps, cin // 16, 16, n).permute(0, 1, 3, 2).contiguous()
+    if npass == 1:
+        return slabs.reshape(-1)
+    hi = (slabs.view(torch.int32) & TF32_MASK).view(torch.float32)
+    lo = ((slabs - hi).view(torch.int32) & TF32_MASK).view(torch.float32)
+    return torch.cat([hi.reshape(-1), lo.reshape(-1)])
+
+
+def pack_reg3d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Tensor:
+    """reg3d state (``{prefix}.conv0.conv.weight`` ... ``{prefix}.prob.weight``) -> blob in the layout of
+    mvster_reg3d_layer_info (``layer_table`` = capi.reg3d_layer_table(G, down_size)); BN folded, prob has no bias."""
+    last = layer_table[-1]
+    blob = torch.zeros(last["w_off"] + 27 * last["cin"] * last["cout"], dtype=torch.float32)
+    for L in layer_table:
+        p = f"{prefix}.{L['name']}"
+        if L["name"] == "prob":
+            w = sd[p + ".weight"].detach().cpu().double()
+            w = w.permute(2, 3, 4, 1, 0).reshape(27, L["cin"], 1).float().contiguous()
+            b = None
+        elif L["transposed"]:
+            s, t = bn_scale_shift(sd, p + ".1")
+            w, b = fold_deconv3d(sd[p + ".0.weight"].detach().cpu(), s.cpu(), t.cpu())
+        else:
+            s, t = bn_scale_shift(sd, p + ".bn")
+            w, b = fold_conv3d(sd[p + ".conv.weight"].detach().cpu(), s.cpu(), t.cpu())
+        if tuple(w.shape) != (27, L["cin"], L["cout"]):
+            raise ValueError(f"{p}: packed shape {tuple(w.shape)} != {(27, L['cin'], L['cout'])}")
+        blob[L["w_off"]:L["w_off"] + w.numel()] = w.reshape(-1)
+        if b is not None:
+            blob[L["b_off"]:L["b_off"] + b.numel()] = b
+    return blob
+
+
 REG2D_ORDER = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11")
 
 
@@ -74,11 +116,12 @@ def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, 
             raise ValueError(f"{p}: packed shape {tuple(w.shape)} != layer table {(L['taps'], L['cin'], L['cout'])}")
         blob[L["w_off"]:L["w_off"] + w.numel()] = w.reshape(-1)
         blob[L["b_off"]:L["b_off"] + b.numel()] = b
-    tc = []
+    tc, tc2 = [], []
     for name, L in zip(REG2D_ORDER, layer_table):
-        if L["kd"] == 3:  # conv2 / conv4 / conv6: K-major [hi|lo] slabs for the tcgen05 path
+        if L["kd"] == 3:  # conv2 / conv4 / conv6: K-major [hi|lo] slabs for the tcgen05 paths
             w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
             tc.append(pack_tc_weights(w, 3))
-    return {"blob": blob, "tc_blob": torch.cat(tc),
+            tc2.append(pack_tc2_weights(w, 3))
+    return {"blob": blob, "tc_blob": torch.cat(tc), "tc2_blob": torch.cat(tc2),
             "prob_w": sd[prefix + ".prob.weight"].detach().cpu().reshape(-1).float().contiguous(),
             "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}

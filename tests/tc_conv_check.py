@@ -1,8 +1,9 @@
-"""Stand-alone check of the tcgen05 convolution against the exact-fp32 CUDA-core convolution.
+"""Stand-alone check of the tcgen05 convolutions against the exact-fp32 CUDA-core convolution.
 Run one case per process (tests/test_gpu_tc_conv.py does that with a timeout) so that a device-side
-trap or a barrier deadlock in the tensor-core kernel cannot take the rest of the suite down.
+trap or a barrier deadlock in a tensor-core kernel cannot take the rest of the suite down.
 
-    python tests/tc_conv_check.py CIN COUT KD B D H W NPASS [skip] [norelu]
+    python tests/tc_conv_check.py {v1|v2} CIN COUT KD B D H W NPASS [skip] [norelu]
+    python tests/tc_conv_check.py {reg2d|reg2dv2} G B D H W NPASS
 """
 import json
 import sys
@@ -16,8 +17,20 @@ sys.path.insert(0, str(Path(__file__).resolve().parent))
 from mvster_b200 import capi, packing  # noqa: E402
 
 
-def reg2d_main():
-    """python tests/tc_conv_check.py reg2d G B D H W NPASS: whole reg2d U-Net, tensor-core 3x3x3 layers vs all-CUDA-core."""
+def timeit(fn, n):
+    for _ in range(3):
+        fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / n * 1e3  # us
+
+
+def reg2d_main(gen):
+    """whole reg2d U-Net, tensor-core 3x3x3 layers vs all-CUDA-core."""
     from util import SHIPPED, build_model
     G, B, D, H, W, npass = map(int, sys.argv[2:8])
     dev = torch.device("cuda", 0)
@@ -25,32 +38,25 @@ def reg2d_main():
     packed = packing.pack_reg2d(sd, "reg.0" if G == 8 else "reg.3", capi.reg2d_layer_table(G))
     rng = np.random.RandomState(G + H)
     cost = torch.from_numpy((rng.randn(B, D, H, W, G) * 0.05).astype(np.float32)).to(dev)
-    blob, tcb = packed["blob"].to(dev), packed["tc_blob"].to(dev)
+    blob, tcb = packed["blob"].to(dev), packed["tc2_blob" if gen == 2 else "tc_blob"].to(dev)
     want = capi.reg2d(blob, cost)
-    got = capi.reg2d(blob, cost, tc_blob=tcb, npass=npass)
+    got = capi.reg2d(blob, cost, tc_blob=tcb, npass=npass, kernel_gen=gen)
     torch.cuda.synchronize()
     err, scale = (got - want).abs().max().item(), want.abs().max().item()
     ws = torch.empty(capi.reg2d_workspace_floats(B, D, H, W), device=dev)
     out = torch.empty_like(want)
-    times = {}
-    for tag, kw in (("simt", {}), ("tc", dict(tc_blob=tcb, npass=npass))):
-        for _ in range(3):
-            capi.reg2d(blob, cost, workspace=ws, out=out, **kw)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(10):
-            capi.reg2d(blob, cost, workspace=ws, out=out, **kw)
-        e.record()
-        torch.cuda.synchronize()
-        times[tag] = s.elapsed_time(e) / 10 * 1e3
+    t_simt = timeit(lambda: capi.reg2d(blob, cost, workspace=ws, out=out), 10)
+    t_tc = timeit(lambda: capi.reg2d(blob, cost, workspace=ws, out=out, tc_blob=tcb, npass=npass, kernel_gen=gen), 10)
     print(json.dumps({"case": sys.argv[1:], "abs_err": err, "scale": scale, "rel": err / scale,
-                      "finite": bool(torch.isfinite(got).all()), "us_tc": times["tc"], "us_simt": times["simt"]}))
+                      "finite": bool(torch.isfinite(got).all()), "us_tc": t_tc, "us_simt": t_simt}))
 
 
 def main():
-    if sys.argv[1] == "reg2d":
-        return reg2d_main()
-    cin, cout, kd, B, D, H, W, npass = map(int, sys.argv[1:9])
+    mode = sys.argv[1]
+    if mode.startswith("reg2d"):
+        return reg2d_main(2 if mode.endswith("v2") else 1)
+    gen = 2 if mode == "v2" else 1
+    cin, cout, kd, B, D, H, W, npass = map(int, sys.argv[2:10])
     use_skip, relu = "skip" in sys.argv, "norelu" not in sys.argv
     dev = torch.device("cuda", 0)
     rng = np.random.RandomState(cin * 1000 + cout * 10 + kd + H)
@@ -59,30 +65,21 @@ def main():
     bias = torch.from_numpy(rng.randn(cout).astype(np.float32) * 0.1).to(dev)
     skip = torch.from_numpy(rng.randn(B, D, H, W, cout).astype(np.float32)).to(dev) if use_skip else None
     want = capi.conv3d_ndhwc(x, w, bias, kd, 1, 1, False, relu, skip=skip)
-    got = capi.conv3d_tc(x, packing.pack_tc_weights(w.cpu(), npass).to(dev), bias, cout, kd, relu, skip=skip, npass=npass)
+    if gen == 2:
+        wp = packing.pack_tc2_weights(w.cpu(), npass).to(dev)
+        run = lambda: capi.conv3d_tc2(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
+    else:
+        wp = packing.pack_tc_weights(w.cpu(), npass).to(dev)
+        run = lambda: capi.conv3d_tc(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
+    got = run()
     torch.cuda.synchronize()
-    err = (got - want).abs().max().item()
-    scale = want.abs().max().item()
-    # timing: 20 back-to-back launches (activations stay in L2; this is a kernel-quality number, not a bench line)
-    wp = packing.pack_tc_weights(w.cpu(), npass).to(dev)
-    for _ in range(3):
-        capi.conv3d_tc(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(20):
-        capi.conv3d_tc(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
-    e.record()
-    torch.cuda.synchronize()
-    t_tc = s.elapsed_time(e) / 20
-    s.record()
-    for _ in range(20):
-        capi.conv3d_ndhwc(x, w, bias, kd, 1, 1, False, relu, skip=skip)
-    e.record()
-    torch.cuda.synchronize()
-    t_simt = s.elapsed_time(e) / 20
+    err, scale = (got - want).abs().max().item(), want.abs().max().item()
+    # timing: back-to-back launches (activations stay in L2: a kernel-quality number, not a bench line)
+    t_tc = timeit(run, 20)
+    t_simt = timeit(lambda: capi.conv3d_ndhwc(x, w, bias, kd, 1, 1, False, relu, skip=skip), 20)
     flops = 2.0 * B * D * H * W * kd * 9 * cin * cout
     print(json.dumps({"case": sys.argv[1:], "abs_err": err, "scale": scale, "rel": err / scale, "finite": bool(torch.isfinite(got).all()),
-                      "us_tc": t_tc * 1e3, "us_simt": t_simt * 1e3, "tflops_tc": flops / (t_tc * 1e-3) / 1e12}))
+                      "us_tc": t_tc, "us_simt": t_simt, "tflops_tc": flops / (t_tc * 1e-6) / 1e12}))
 
 
 if __name__ == "__main__":

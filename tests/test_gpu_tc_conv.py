@@ -1,4 +1,7 @@
-"""tcgen05 (tensor-core) convolution vs the exact-fp32 CUDA-core convolution, one subprocess per case."""
+"""tcgen05 (tensor-core) convolutions vs the exact-fp32 CUDA-core convolution, one subprocess per case.
+
+Tolerances (max abs error / max |output|): 3xTF32 3e-5 - the per-product error of the hi/lo split is 2^-21,
+the tensor core accumulates K = 27*Cin products in fp32 with truncation; measured 3e-6 .. 1.6e-5.  Plain TF32 5e-3."""
 import json
 import subprocess
 import sys
@@ -9,24 +12,33 @@ from util import REPO
 
 pytestmark = pytest.mark.gpu
 
-CASES = [  # cin cout kd B D H W npass [flags]
-    "32 32 3 1 4 16 32 3",
-    "16 16 3 1 8 24 40 3 skip",      # 64-byte swizzle path, ragged right/bottom tiles
-    "64 64 3 1 8 8 10 3",            # two K chunks per tap, image smaller than one tile
-    "32 32 1 2 4 16 16 3 norelu",    # (1,3,3) kernel, batch 2
-    "32 64 3 1 4 32 48 1",           # plain TF32
-    "16 16 3 1 4 256 320 3",         # 2560 tiles: 4 accumulators per CTA in TMEM
-    "64 64 3 1 4 64 80 3 skip",      # reg2d conv6 at cfg2 stage 4
-    "reg2d 8 1 8 64 80 3",           # whole reg2d U-Net, stage-1 shape of cfg2, 3xTF32
-    "reg2d 4 1 4 512 640 3",         # stage-4 shape of cfg2 (1.31 M voxels)
-    "reg2d 4 1 4 128 160 1",         # plain TF32
+CASES = [  # generation cin cout kd B D H W npass [flags]
+    "v1 32 32 3 1 4 16 32 3",
+    "v1 16 16 3 1 8 24 40 3 skip",      # 64-byte swizzle path, ragged right/bottom tiles
+    "v1 64 64 3 1 8 8 10 3",            # two K chunks per tap, image smaller than one tile
+    "v1 32 32 1 2 4 16 16 3 norelu",    # (1,3,3) kernel, batch 2
+    "v1 32 64 3 1 4 32 48 1",           # plain TF32
+    "v1 64 64 3 1 4 64 80 3 skip",      # reg2d conv6 at cfg2 stage 4
+    "v2 32 32 3 1 4 16 32 3",
+    "v2 16 16 3 1 8 24 40 3 skip",      # ragged right/bottom tiles (16x8 tiles on 24x40)
+    "v2 64 64 3 1 8 8 10 3",            # four 16-channel chunks, image smaller than one tile, depth padding
+    "v2 32 32 1 2 4 16 16 3 norelu",    # (1,3,3) kernel, batch 2
+    "v2 32 64 3 1 4 32 48 1",           # plain TF32
+    "v2 64 8 1 2 1 32 40 3 norelu",     # 2-D 3x3 conv 64 -> 8 (N padded to 16): the FPN out4 shape class
+    "v2 16 16 3 1 4 256 320 3",         # reg2d conv2 at cfg2 stage 4: 2560 tiles, 4 accumulators per CTA
+    "v2 32 32 3 1 4 128 160 3 skip",    # conv4
+    "v2 64 64 3 1 4 64 80 3 skip",      # conv6
+    "reg2d 8 1 8 64 80 3",              # whole reg2d U-Net, stage-1 shape of cfg2, 3xTF32, generation 1
+    "reg2dv2 8 1 8 64 80 3",            # ... generation 2
+    "reg2dv2 4 1 4 512 640 3",          # stage-4 shape of cfg2 (1.31 M voxels)
+    "reg2dv2 4 1 4 128 160 1",          # plain TF32
 ]
 
 
 @pytest.mark.parametrize("case", CASES)
 def test_tc_conv_matches_exact_conv(case):
     p = subprocess.run([sys.executable, str(REPO / "tests" / "tc_conv_check.py"), *case.split()], capture_output=True, text=True,
-                       timeout=180)
+                       timeout=90)
     assert p.returncode == 0, f"subprocess failed:\n{p.stdout[-2000:]}\n{p.stderr[-3000:]}"
     res = json.loads(p.stdout.strip().splitlines()[-1])
     out = REPO / "gpurun_out"
@@ -34,6 +46,7 @@ def test_tc_conv_matches_exact_conv(case):
     with open(out / "tc_conv_report.jsonl", "a") as f:
         f.write(json.dumps(res) + "\n")
     assert res["finite"]
-    npass = int(case.split()[-1]) if case.startswith("reg2d") else int(case.split()[7])
-    tol = (2e-5 if case.startswith("reg2d") else 3e-6) if npass == 3 else 5e-3
+    f = case.split()
+    npass = int(f[6]) if f[0].startswith("reg2d") else int(f[8])
+    tol = (1e-4 if f[0].startswith("reg2d") else 3e-5) if npass == 3 else 5e-3
     assert res["rel"] < tol, res

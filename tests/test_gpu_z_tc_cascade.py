@@ -1,0 +1,51 @@
+"""Cascade-level parity with the 3x3x3 regulariser layers on the tcgen05 tensor cores (runs last: an
+illegal-instruction trap in a tensor-core kernel would poison the CUDA context of this process)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import SHIPPED, build_model, oracle, oracle_cfg, top2_gap
+from test_gpu_parity import DEV, nhwc, record
+
+from mvster_b200 import capi, packing, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("gen,npass", [(1, 3), (2, 3), (2, 1)])
+def test_teacher_forced_stages_tensor_core_regulariser(gen, npass):
+    B, nv, H, W = 1, 5, 128, 192
+    imgs, proj, dv = synth.make_inputs(B, nv, H, W, seed=21)
+    sd = build_model(SHIPPED, 7).state_dict()
+    cfg = oracle_cfg(SHIPPED)
+    with torch.no_grad():
+        feats = [oracle.fpn4_features(sd, im) for im in imgs]
+        ref_out = oracle.cascade_forward(sd, cfg, imgs, proj, dv, features=feats)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    failures = []
+    for k in range(4):
+        key = f"stage{k + 1}"
+        G = cfg["group_cor_dim"][k]
+        hypo = ref_out[key]["hypo_depth"]
+        cost = ref_out[key]["cost"].permute(0, 2, 3, 4, 1).contiguous().to(DEV)  # the ORACLE's cost volume: isolates the regulariser
+        with torch.no_grad():
+            truth_attn = F.softmax(oracle.reg2d_logits(sd64, f"reg.{k}", ref_out[key]["cost"].double()), 1)
+        packed = packing.pack_reg2d(sd, f"reg.{k}", capi.reg2d_layer_table(G))
+        feat8 = capi.reg2d(packed["blob"].to(DEV), cost, tc_blob=packed["tc2_blob" if gen == 2 else "tc_blob"].to(DEV),
+                           npass=npass, kernel_gen=gen)
+        h = capi.head(hypo.to(DEV), cfg["depth_interals_ratio"][k], feat8=feat8, prob_w=packed["prob_w"].to(DEV), prob_b=packed["prob_b"].to(DEV))
+        floor_attn = (ref_out[key]["attn_weight"].double() - truth_attn).abs().max().item()
+        aerr_truth = (h["attn_weight"].cpu().double() - truth_attn).abs().max().item()
+        stable = top2_gap(ref_out[key]["attn_weight"]) > 1e-3
+        d, rd = h["depth"].cpu(), ref_out[key]["depth"]
+        bad = (((d - rd).abs() > 1e-4 * rd) & stable).float().mean().item()
+        record(f"tc_regulariser_gen{gen}_npass{npass}_{key}", attn_vs_fp64=aerr_truth, oracle_attn_vs_fp64=floor_attn, depth_bad_stable=bad)
+        if npass == 3:
+            if not aerr_truth <= 8 * floor_attn + 2e-5:
+                failures.append(f"{key}: attn vs fp64 {aerr_truth:.2e} (oracle floor {floor_attn:.2e})")
+            if bad != 0.0:
+                failures.append(f"{key}: {bad:.3%} tie-free pixels disagree on depth")
+        else:  # plain TF32: reduced-precision configuration, probabilities within 2e-3
+            if aerr_truth > 2e-3:
+                failures.append(f"{key}: TF32 attn error {aerr_truth:.2e}")
+    assert not failures, "; ".join(failures)
