@@ -164,6 +164,19 @@ size_t mvster_reg3d_workspace_floats(int B, int D, int H, int W);
 int mvster_reg3d_f32(const float* blob, const float* cost, float* logits, float* workspace,
                      int B, int G, int D, int H, int W, int down_size, mvster_stream_t stream);
 
+/* ---- feature pyramid (FPN4, mvs4net_utils.py:419-502; outside the named hot path, it feeds it) ------- */
+/* NHWC 2-D convolution, k in {1,3,5}, stride 1/2, pad k/2, optional bias (folded BN) and ReLU, CUDA cores.
+ * x [N][H][W][Cin], w [k*k][Cin][Cout] -> y [N][Ho][Wo][Cout].  Conv2d blocks of mvs4net_utils.py:224-251. */
+int mvster_conv2d_nhwc_f32(const float* x, const float* w, const float* bias, float* y,
+                           int N, int H, int W, int Cin, int Cout, int k, int stride, int relu, mvster_stream_t stream);
+/* First layer: 3-channel NCHW image [N][3][H][W] -> NHWC [N][H][W][8]; 3x3, bias, ReLU (conv0.0, :424). w [9][3][8]. */
+int mvster_conv_first_f32(const float* img_nchw, const float* w, const float* bias, float* y,
+                          int N, int H, int W, mvster_stream_t stream);
+/* Top-down merge (:479-486): out = bilinear_x2(top, align_corners=True) + conv1x1(lateral) + bias.
+ * top [N][H/2][W/2][64], lateral [N][H][W][Clat], w [Clat][64], out [N][H][W][64]. */
+int mvster_fpn_merge_f32(const float* top, const float* lateral, const float* w, const float* bias, float* out,
+                         int N, int H, int W, int Clat, mvster_stream_t stream);
+
 /* ---- head ---------------------------------------------------------------- */
 /* mvs4net_utils.py:1066-1088.  Either `logits` [B][D][H][W] is given, or
  * (feat8 [B][D][H][W][8], prob_w[8], prob_b[1]) and the 1x1x1 `prob` conv of

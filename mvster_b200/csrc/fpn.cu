@@ -1,0 +1,219 @@
+// Feature-pyramid (FPN4, models/mvs4net_utils.py:419-502) building blocks on channels-last tensors.
+// FPN4 is outside the named hot path (SURVEY.md 8f "next" #1) but it feeds it and, through cuDNN fp32,
+// was 75 % of the step time; these kernels let the whole forward run inside libmvster_b200:
+//   conv_first_kernel   3x3 conv on the 3-channel NCHW image -> NHWC 8 channels (+ folded BN, ReLU)   (:424, conv0.0)
+//   conv2d_kernel       k x k (k = 1, 3, 5), stride 1 / 2, CUDA-core fp32, folded BN / bias / ReLU      (:425-445, :452-459)
+//   fpn_merge_kernel    top-down merge: bilinear x2 (align_corners) of the coarser map + 1x1 lateral conv (:479-486)
+// The 3x3 stride-1 layers with Cin >= 16 (73 % of FPN4's FLOPs) run on the tcgen05 kernel of conv_tc2.cu.
+#include "common.cuh"
+
+namespace mvster {
+
+struct Conv2dArgs {
+    const float* x; const float* w; const float* bias; float* y;
+    int N, Hi, Wi, Ho, Wo, cout, k, s, relu;
+};
+
+template <int CIN, int COUT_T>
+__global__ void __launch_bounds__(128) conv2d_kernel(const Conv2dArgs a) {
+    extern __shared__ __align__(16) float w_s[];  // [k*k][CIN][COUT_T]
+    const int cg = blockIdx.y, taps = a.k * a.k, pad = a.k / 2;
+    for (int i = threadIdx.x; i < taps * CIN * COUT_T; i += blockDim.x) {
+        const int o = i % COUT_T, rest = i / COUT_T;
+        w_s[i] = __ldg(a.w + (long long)rest * a.cout + cg * COUT_T + o);
+    }
+    __syncthreads();
+    const long long n = (long long)a.N * a.Ho * a.Wo;
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int ox = (int)(v % a.Wo), oy = (int)((v / a.Wo) % a.Ho), b = (int)(v / ((long long)a.Wo * a.Ho));
+    float acc[COUT_T];
+#pragma unroll
+    for (int o = 0; o < COUT_T; ++o) acc[o] = a.bias ? __ldg(a.bias + cg * COUT_T + o) : 0.f;
+    for (int ky = 0; ky < a.k; ++ky) {
+        const int iy = oy * a.s + ky - pad;
+        if ((unsigned)iy >= (unsigned)a.Hi) continue;
+        for (int kx = 0; kx < a.k; ++kx) {
+            const int ix = ox * a.s + kx - pad;
+            if ((unsigned)ix >= (unsigned)a.Wi) continue;
+            const float4* px = reinterpret_cast<const float4*>(a.x + (((long long)b * a.Hi + iy) * a.Wi + ix) * CIN);
+            const float* wt = w_s + (ky * a.k + kx) * CIN * COUT_T;
+#pragma unroll
+            for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                const float4 t = __ldg(px + c4);
+                const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float* wr = wt + (c4 * 4 + j) * COUT_T;
+#pragma unroll
+                    for (int o = 0; o < COUT_T; ++o) acc[o] = fmaf(tv[j], wr[o], acc[o]);
+                }
+            }
+        }
+    }
+    const long long off = v * a.cout + cg * COUT_T;
+#pragma unroll
+    for (int o = 0; o < COUT_T; o += 4) {
+        float4 r = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
+        if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+        *reinterpret_cast<float4*>(a.y + off + o) = r;
+    }
+}
+
+template <int CIN, int COUT_T>
+static int launch_conv2d(const Conv2dArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)a.k * a.k * CIN * COUT_T * sizeof(float);
+    auto k = conv2d_kernel<CIN, COUT_T>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long n = (long long)a.N * a.Ho * a.Wo;
+    k<<<dim3(ceil_div(n, 128), a.cout / COUT_T), 128, smem, st>>>(a);
+    return check_launch("conv2d_kernel");
+}
+
+template <int CIN>
+static int dispatch_conv2d(const Conv2dArgs& a, cudaStream_t st) {
+    if (a.cout % 16 == 0) return launch_conv2d<CIN, 16>(a, st);
+    if (a.cout % 8 == 0) return launch_conv2d<CIN, 8>(a, st);
+    set_error("mvster_conv2d_nhwc_f32: Cout=%d must be a multiple of 8", a.cout);
+    return MVSTER_ERR_ARG;
+}
+
+// 3-channel NCHW image -> 8-channel NHWC feature: 3x3, stride 1, pad 1, bias (folded BN), ReLU.
+// w: [9][3][8].  One thread per output pixel; the image is read plane-wise (coalesced along x).
+__global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int N, int H, int W) {
+    __shared__ float w_s[9 * 3 * 8 + 8];
+    for (int i = threadIdx.x; i < 216; i += blockDim.x) w_s[i] = __ldg(w + i);
+    if (threadIdx.x < 8) w_s[216 + threadIdx.x] = __ldg(bias + threadIdx.x);
+    __syncthreads();
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= (long long)N * H * W) return;
+    const int x = (int)(v % W), yy = (int)((v / W) % H), b = (int)(v / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = w_s[216 + o];
+    const float* base = img + (long long)b * 3 * H * W;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = yy + ky - 1;
+        if ((unsigned)iy >= (unsigned)H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = x + kx - 1;
+            if ((unsigned)ix >= (unsigned)W) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float t = __ldg(base + ((long long)c * H + iy) * W + ix);
+                const float* wr = w_s + ((ky * 3 + kx) * 3 + c) * 8;
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = fmaf(t, wr[o], acc[o]);
+            }
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(y + v * 8);
+    dst[0] = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+    dst[1] = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+}
+
+// out[n,y,x,:] = bilinear_x2(top)[n,y,x,:] + W_lat . lat[n,y,x,:] + bias     (F.interpolate(scale_factor=2,
+// align_corners=True) + 1x1 lateral conv, mvs4net_utils.py:479-486).  top [N][H/2][W/2][64], lat [N][H][W][CL],
+// w [CL][64].  One thread = one pixel x 16 output channels.
+template <int CL>
+__global__ void __launch_bounds__(128) fpn_merge_kernel(const float* __restrict__ top, const float* __restrict__ lat,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        float* __restrict__ out, int N, int H, int W) {
+    __shared__ __align__(16) float w_s[CL * 64 + 64];
+    for (int i = threadIdx.x; i < CL * 64; i += blockDim.x) w_s[i] = __ldg(w + i);
+    if (threadIdx.x < 64) w_s[CL * 64 + threadIdx.x] = __ldg(bias + threadIdx.x);
+    __syncthreads();
+    const int cg = blockIdx.y;  // 16-channel slice of the 64 output channels
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= (long long)N * H * W) return;
+    const int x = (int)(v % W), y = (int)((v / W) % H), b = (int)(v / ((long long)W * H));
+    const int Hc = H / 2, Wc = W / 2;
+    const float sy = Hc > 1 ? __fdiv_rn((float)(Hc - 1), (float)(H - 1)) : 0.f, sx = Wc > 1 ? __fdiv_rn((float)(Wc - 1), (float)(W - 1)) : 0.f;
+    const float fy = __fmul_rn(sy, (float)y), fx = __fmul_rn(sx, (float)x);
+    const int y0 = min((int)floorf(fy), Hc - 1), x0 = min((int)floorf(fx), Wc - 1);
+    const int y1 = y0 + (y0 < Hc - 1), x1 = x0 + (x0 < Wc - 1);
+    const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+    const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* tb = top + (long long)b * Hc * Wc * 64 + cg * 16;
+    const float4* p00 = reinterpret_cast<const float4*>(tb + ((long long)y0 * Wc + x0) * 64);
+    const float4* p01 = reinterpret_cast<const float4*>(tb + ((long long)y0 * Wc + x1) * 64);
+    const float4* p10 = reinterpret_cast<const float4*>(tb + ((long long)y1 * Wc + x0) * 64);
+    const float4* p11 = reinterpret_cast<const float4*>(tb + ((long long)y1 * Wc + x1) * 64);
+    float acc[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 a00 = __ldg(p00 + q), a01 = __ldg(p01 + q), a10 = __ldg(p10 + q), a11 = __ldg(p11 + q);
+        // ATen order: ly0*(lx0*v00 + lx1*v01) + ly1*(lx0*v10 + lx1*v11)
+        acc[4 * q + 0] = ly0 * (lx0 * a00.x + lx1 * a01.x) + ly1 * (lx0 * a10.x + lx1 * a11.x);
+        acc[4 * q + 1] = ly0 * (lx0 * a00.y + lx1 * a01.y) + ly1 * (lx0 * a10.y + lx1 * a11.y);
+        acc[4 * q + 2] = ly0 * (lx0 * a00.z + lx1 * a01.z) + ly1 * (lx0 * a10.z + lx1 * a11.z);
+        acc[4 * q + 3] = ly0 * (lx0 * a00.w + lx1 * a01.w) + ly1 * (lx0 * a10.w + lx1 * a11.w);
+    }
+    float latv[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) latv[o] = w_s[CL * 64 + cg * 16 + o];
+    const float4* pl = reinterpret_cast<const float4*>(lat + v * CL);
+#pragma unroll
+    for (int c4 = 0; c4 < CL / 4; ++c4) {
+        const float4 t = __ldg(pl + c4);
+        const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* wr = w_s + (c4 * 4 + j) * 64 + cg * 16;
+#pragma unroll
+            for (int o = 0; o < 16; ++o) latv[o] = fmaf(tv[j], wr[o], latv[o]);
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(out + v * 64 + cg * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        dst[q] = make_float4(acc[4 * q] + latv[4 * q], acc[4 * q + 1] + latv[4 * q + 1], acc[4 * q + 2] + latv[4 * q + 2], acc[4 * q + 3] + latv[4 * q + 3]);
+}
+
+}  // namespace mvster
+
+using namespace mvster;
+
+extern "C" int mvster_conv2d_nhwc_f32(const float* x, const float* w, const float* bias, float* y,
+                                      int N, int H, int W, int Cin, int Cout, int k, int stride, int relu, mvster_stream_t stream) {
+    MVSTER_REQUIRE(x && w && y, "mvster_conv2d_nhwc_f32: null pointer");
+    MVSTER_REQUIRE(N > 0 && H > 0 && W > 0, "mvster_conv2d_nhwc_f32: bad shape");
+    MVSTER_REQUIRE(k == 1 || k == 3 || k == 5, "mvster_conv2d_nhwc_f32: kernel size %d (1, 3 or 5)", k);
+    MVSTER_REQUIRE(stride == 1 || stride == 2, "mvster_conv2d_nhwc_f32: stride %d (1 or 2)", stride);
+    Conv2dArgs a{x, w, bias, y, N, H, W, (H - 1) / stride + 1, (W - 1) / stride + 1, Cout, k, stride, relu};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (Cin) {
+        case 8: return dispatch_conv2d<8>(a, st);
+        case 16: return dispatch_conv2d<16>(a, st);
+        case 32: return dispatch_conv2d<32>(a, st);
+        case 64: return dispatch_conv2d<64>(a, st);
+    }
+    set_error("mvster_conv2d_nhwc_f32: unsupported Cin=%d (8,16,32,64)", Cin);
+    return MVSTER_ERR_ARG;
+}
+
+extern "C" int mvster_conv_first_f32(const float* img_nchw, const float* w, const float* bias, float* y,
+                                     int N, int H, int W, mvster_stream_t stream) {
+    MVSTER_REQUIRE(img_nchw && w && bias && y, "mvster_conv_first_f32: null pointer");
+    MVSTER_REQUIRE(N > 0 && H > 0 && W > 0, "mvster_conv_first_f32: bad shape");
+    const long long n = (long long)N * H * W;
+    conv_first_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(img_nchw, w, bias, y, N, H, W);
+    return check_launch("conv_first_kernel");
+}
+
+extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, const float* w, const float* bias, float* out,
+                                    int N, int H, int W, int Clat, mvster_stream_t stream) {
+    MVSTER_REQUIRE(top && lateral && w && bias && out, "mvster_fpn_merge_f32: null pointer");
+    MVSTER_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mvster_fpn_merge_f32: H,W must be even");
+    const long long n = (long long)N * H * W;
+    dim3 grid(ceil_div(n, 128), 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Clat == 8) fpn_merge_kernel<8><<<grid, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+    else if (Clat == 16) fpn_merge_kernel<16><<<grid, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+    else if (Clat == 32) fpn_merge_kernel<32><<<grid, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+    else MVSTER_REQUIRE(false, "mvster_fpn_merge_f32: unsupported lateral channels %d (8,16,32)", Clat);
+    return check_launch("fpn_merge_kernel");
+}

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from . import capi, packing
+from . import capi, fpn_engine, packing
 
 Tensor = torch.Tensor
 REG3D_DOWN = (3, 3, 2, 2)  # MVS4Net.py:48
@@ -60,6 +60,8 @@ class InferenceEngine:
         sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("reg.")}
         self.plans = [StagePlan(k, net) for k in range(net.num_stage)]
         self.stage_weights = []
+        fpn_sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("feature.")}
+        self.fpn_weights = {k: v.to(self.device) for k, v in fpn_engine.pack_fpn(fpn_sd).items()}
         with torch.cuda.device(self.device):
             for p in self.plans:
                 if net.reg_net == "reg2d":
@@ -76,12 +78,17 @@ class InferenceEngine:
         B = imgs[0].shape[0]
         own = list(range(len(imgs))) if shard is None else [0] + shard.views
         with torch.cuda.device(self.device):
-            x = torch.cat([imgs[v] for v in own], 0).contiguous(memory_format=torch.channels_last)
-            pyramid = net.feature(x)  # {stage: [len(own)*B, C, h, w]}, channels-last strides
-            feats = []
-            for k in range(net.num_stage):
-                f = capi.to_nhwc(pyramid[f"stage{k + 1}"])  # [len(own)*B, h, w, C]
-                feats.append([f[i * B:(i + 1) * B] for i in range(len(own))])
+            if getattr(net, "fpn_backend", "torch") == "native":
+                # FPN4 inside libmvster_b200 (fpn_engine.py): NCHW images in, NHWC features out
+                x = torch.cat([imgs[v] for v in own], 0).to(dtype=torch.float32).contiguous()
+                npass = {"fp32": 0, "3xtf32": 3, "tf32": 1}[getattr(net, "fpn_precision", "fp32")]
+                pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass)
+                nhwc = [pyramid[f"stage{k + 1}"] for k in range(net.num_stage)]
+            else:
+                x = torch.cat([imgs[v] for v in own], 0).contiguous(memory_format=torch.channels_last)
+                pyramid = net.feature(x)  # {stage: [len(own)*B, C, h, w]}, channels-last strides
+                nhwc = [capi.to_nhwc(pyramid[f"stage{k + 1}"]) for k in range(net.num_stage)]
+            feats = [[f[i * B:(i + 1) * B] for i in range(len(own))] for f in nhwc]
             return self.run_cascade(net, feats, proj_matrices, depth_values, shard=shard)
 
     # ------------------------------------------------------------------ the hot path

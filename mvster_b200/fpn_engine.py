@@ -1,0 +1,111 @@
+"""FPN4 (mvs4net_utils.py:419-502) on libmvster_b200: all views of a frame in one batch, channels-last,
+BN folded, the 3x3 stride-1 layers with Cin >= 16 (73 % of the FLOPs) optionally on the tcgen05 kernel.
+
+FPN4 is outside the named hot path but feeds it (SURVEY.md 8f "next" #1); through cuDNN fp32 it was
+75 % of the step.  Layout: every intermediate is NHWC fp32, so the four outputs are directly the
+feature tensors the warp kernel consumes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Mapping, Optional
+
+import torch
+
+from . import _lib, capi, packing
+
+Tensor = torch.Tensor
+
+
+def _fold2d(sd: Mapping[str, Tensor], p: str):
+    """Conv2d(no bias) + BN(eval) -> ([k*k][Cin][Cout], [Cout])."""
+    w = sd[p + ".conv.weight"].detach().cpu().double()
+    s, t = packing.bn_scale_shift({k: v.detach().cpu() for k, v in sd.items() if k.startswith(p + ".bn")}, p + ".bn")
+    wf = w * s.view(-1, 1, 1, 1)
+    k = w.shape[2]
+    return wf.permute(2, 3, 1, 0).reshape(k * k, w.shape[1], w.shape[0]).float().contiguous(), t.float().contiguous()
+
+
+def _plain2d(w: Tensor):
+    w = w.detach().cpu()
+    k = w.shape[2]
+    return w.permute(2, 3, 1, 0).reshape(k * k, w.shape[1], w.shape[0]).float().contiguous()
+
+
+def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Tensor]:
+    """All FPN4 weights in kernel layouts (CPU tensors): '<layer>.w' [taps][Cin][Cout], '<layer>.b' [Cout],
+    '<layer>.tc' K-major [hi|lo] slabs for the 3x3 stride-1 layers with Cin >= 16."""
+    out: Dict[str, Tensor] = {}
+    p = prefix
+    for name in ("conv0.0", "conv0.1", "conv1.0", "conv1.1", "conv1.2", "conv2.0", "conv2.1", "conv2.2", "conv3.0", "conv3.1", "conv3.2"):
+        w, b = _fold2d(sd, f"{p}.{name}")
+        out[name + ".w"], out[name + ".b"] = w, b
+        if w.shape[0] == 9 and w.shape[1] >= 16:
+            out[name + ".tc"] = packing.pack_tc2_weights(w, 3)
+    for i in (1, 2, 3):
+        w = sd[f"{p}.inner{i}.weight"].detach().cpu()
+        out[f"inner{i}.w"] = w.reshape(w.shape[0], w.shape[1]).t().float().contiguous()  # [Clat][64]
+        out[f"inner{i}.b"] = sd[f"{p}.inner{i}.bias"].detach().cpu().float().contiguous()
+    for i in (1, 2, 3, 4):
+        w = _plain2d(sd[f"{p}.out{i}.weight"])
+        out[f"out{i}.w"] = w
+        if w.shape[0] == 9:
+            out[f"out{i}.tc"] = packing.pack_tc2_weights(w, 3)
+    return out
+
+
+def _conv2d(x: Tensor, w: Tensor, b: Optional[Tensor], k: int, stride: int, relu: bool) -> Tensor:
+    N, H, W, Cin = x.shape
+    cout = w.shape[2]
+    y = torch.empty((N, (H - 1) // stride + 1, (W - 1) // stride + 1, cout), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_conv2d_nhwc_f32(capi._ptr(x), capi._ptr(w), capi._ptr(b), capi._ptr(y), N, H, W, Cin, cout, k, stride,
+                                                  int(relu), capi._stream()), "mvster_conv2d_nhwc_f32")
+    return y
+
+
+def _conv3x3(x: Tensor, wts: Dict[str, Tensor], name: str, relu: bool, npass: int) -> Tensor:
+    """3x3 stride-1 layer: tensor cores (npass 3 = 3xTF32, 1 = TF32) or CUDA cores (npass 0)."""
+    w, b = wts[name + ".w"], wts.get(name + ".b")
+    if npass and (name + ".tc") in wts:
+        N, H, W, Cin = x.shape
+        tc = wts[name + ".tc"]
+        half = tc.numel() // 2
+        y = capi.conv3d_tc2(x.view(N, 1, H, W, Cin), tc if npass == 3 else tc[:half].contiguous(), b, w.shape[2], 1, relu, npass=npass)
+        return y.view(N, H, W, w.shape[2])
+    return _conv2d(x, w, b, 3, 1, relu)
+
+
+def _merge(top: Tensor, lat: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    N, H, W, CL = lat.shape
+    out = torch.empty((N, H, W, 64), device=lat.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_fpn_merge_f32(capi._ptr(top), capi._ptr(lat), capi._ptr(w), capi._ptr(b), capi._ptr(out), N, H, W, CL,
+                                                capi._stream()), "mvster_fpn_merge_f32")
+    return out
+
+
+def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0) -> Dict[str, Tensor]:
+    """imgs [N,3,H,W] contiguous NCHW fp32 on the GPU -> {'stage1'..'stage4': [N,h,w,C] NHWC}."""
+    capi._chk(imgs, "imgs")
+    N, three, H, W = imgs.shape
+    if three != 3 or H % 8 or W % 8:
+        raise ValueError(f"imgs must be [N,3,H,W] with H,W multiples of 8, got {tuple(imgs.shape)}")
+    c0 = torch.empty((N, H, W, 8), device=imgs.device, dtype=torch.float32)
+    _lib.check(_lib.load().mvster_conv_first_f32(capi._ptr(imgs), capi._ptr(wts["conv0.0.w"]), capi._ptr(wts["conv0.0.b"]), capi._ptr(c0),
+                                                 N, H, W, capi._stream()), "mvster_conv_first_f32")
+    c0 = _conv2d(c0, wts["conv0.1.w"], wts["conv0.1.b"], 3, 1, True)
+    levels = [c0]
+    x = c0
+    for L in (1, 2, 3):
+        x = _conv2d(x, wts[f"conv{L}.0.w"], wts[f"conv{L}.0.b"], 5, 2, True)
+        x = _conv3x3(x, wts, f"conv{L}.1", True, npass)
+        x = _conv3x3(x, wts, f"conv{L}.2", True, npass)
+        levels.append(x)
+    c0, c1, c2, c3 = levels
+    out = {"stage1": _conv2d(c3, wts["out1.w"], None, 1, 1, False)}
+    top = _merge(c3, c2, wts["inner1.w"], wts["inner1.b"])
+    out["stage2"] = _conv3x3(top, wts, "out2", False, npass)
+    top = _merge(top, c1, wts["inner2.w"], wts["inner2.b"])
+    out["stage3"] = _conv3x3(top, wts, "out3", False, npass)
+    top = _merge(top, c0, wts["inner3.w"], wts["inner3.b"])
+    out["stage4"] = _conv3x3(top, wts, "out4", False, npass)
+    return out

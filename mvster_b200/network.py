@@ -250,6 +250,10 @@ class MVS4net(nn.Module):
         # "3xtf32" (tcgen05, error-compensated, fp32-faithful) or "tf32" (tcgen05, single pass)
         self.reg_precision = os.environ.get("MVSTER_REG_PRECISION", "fp32")
         self.tc_kernel_gen = int(os.environ.get("MVSTER_TC_GEN", "1"))  # 1 = per-tap TMA kernel, 2 = staged-tile kernel
+        # feature pyramid at inference: "torch" (the module's own convs through cuDNN, channels-last) or "native"
+        # (libmvster_b200 kernels, fpn_engine.py) with fpn_precision "fp32" | "3xtf32" | "tf32" for its 3x3 layers
+        self.fpn_backend = os.environ.get("MVSTER_FPN", "torch")
+        self.fpn_precision = os.environ.get("MVSTER_FPN_PRECISION", "fp32")
         self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)
 
     def set_view_shard(self, shard) -> None:
