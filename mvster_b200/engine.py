@@ -53,10 +53,12 @@ class InferenceEngine:
         self.weights_version = -1
         self.stage_weights: List[Dict[str, Tensor]] = []
         self.plans: List[StagePlan] = []
+        self._graphs: Dict = {}
 
     # ------------------------------------------------------------------ weights
     def refresh_weights(self, net) -> None:
         check_supported(net)
+        self._graphs.clear()  # captured graphs reference the previous packed weights
         sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("reg.")}
         self.plans = [StagePlan(k, net) for k in range(net.num_stage)]
         self.stage_weights = []
@@ -90,6 +92,42 @@ class InferenceEngine:
                 nhwc = [capi.to_nhwc(pyramid[f"stage{k + 1}"]) for k in range(net.num_stage)]
             feats = [[f[i * B:(i + 1) * B] for i in range(len(own))] for f in nhwc]
             return self.run_cascade(net, feats, proj_matrices, depth_values, shard=shard)
+
+    # ------------------------------------------------------------------ CUDA-graph replay (opt-in)
+    def forward_graphed(self, net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor) -> Dict:
+        """Capture the whole forward (feature pyramid + 4-stage cascade, ~60-200 launches) into one CUDA graph
+        per input signature and replay it: removes the per-launch host overhead and the inter-kernel gaps.
+        Inputs are copied into static buffers; the returned tensors are the graph's static outputs and stay
+        valid until the next call with the same signature (``test_mvs4.py`` converts to numpy right away)."""
+        key = (tuple(tuple(t.shape) for t in imgs), tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
+               tuple(depth_values.shape), self.weights_version, getattr(net, "reg_precision", "fp32"),
+               getattr(net, "tc_kernel_gen", 1), getattr(net, "fpn_backend", "torch"), getattr(net, "fpn_precision", "fp32"))
+        entry = self._graphs.get(key)
+        if entry is None:
+            with torch.cuda.device(self.device):
+                s_imgs = [t.detach().to(self.device, torch.float32).clone() for t in imgs]
+                s_proj = {k: v.detach().to(self.device, torch.float32).clone() for k, v in proj_matrices.items()}
+                s_dv = depth_values.detach().to(self.device, torch.float32).clone()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):  # warm-up outside capture: cuDNN autotune, lazy module loads, func attributes
+                    for _ in range(2):
+                        self.forward(net, s_imgs, s_proj, s_dv)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self.forward(net, s_imgs, s_proj, s_dv)
+            entry = self._graphs[key] = (graph, s_imgs, s_proj, s_dv, out)
+            if len(self._graphs) > 4:  # keep the cache small: each graph pins its own workspace
+                self._graphs.pop(next(iter(self._graphs)))
+        graph, s_imgs, s_proj, s_dv, out = entry
+        for dst, src in zip(s_imgs, imgs):
+            dst.copy_(src, non_blocking=True)
+        for k, dst in s_proj.items():
+            dst.copy_(proj_matrices[k], non_blocking=True)
+        s_dv.copy_(depth_values, non_blocking=True)
+        graph.replay()
+        return out
 
     # ------------------------------------------------------------------ the hot path
     def _aggregate(self, p: StagePlan, ref: Tensor, srcs: List[Tensor], proj: Tensor, hypo: Tensor, temp: float,

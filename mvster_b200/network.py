@@ -254,6 +254,8 @@ class MVS4net(nn.Module):
         # (libmvster_b200 kernels, fpn_engine.py) with fpn_precision "fp32" | "3xtf32" | "tf32" for its 3x3 layers
         self.fpn_backend = os.environ.get("MVSTER_FPN", "torch")
         self.fpn_precision = os.environ.get("MVSTER_FPN_PRECISION", "fp32")
+        # replay the whole inference forward as one CUDA graph (outputs are then static buffers, valid until the next call)
+        self.use_cuda_graph = os.environ.get("MVSTER_CUDA_GRAPH", "0") == "1"
         self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)
 
     def set_view_shard(self, shard) -> None:
@@ -296,6 +298,8 @@ class MVS4net(nn.Module):
             if eng.weights_version != self._weights_version:
                 eng.refresh_weights(self)
                 eng.weights_version = self._weights_version
+            if self.use_cuda_graph and self._view_shard is None:
+                return eng.forward_graphed(self, imgs, proj_matrices, depth_values)
             return eng.forward(self, imgs, proj_matrices, depth_values, shard=self._view_shard)
         return self._forward_autograd(imgs, proj_matrices, depth_values, filename)
 

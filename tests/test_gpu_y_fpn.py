@@ -31,6 +31,26 @@ def test_native_fpn_matches_oracle(npass, tol, N, H, W):
         assert err < tol, f"stage{s}: {err:.2e}"
 
 
+@pytest.mark.parametrize("backend", ["torch", "native"])
+def test_cuda_graph_replay_matches_eager(backend):
+    """forward_graphed (one CUDA graph per input signature) must reproduce the eager launch sequence bit for bit,
+    also when replayed on new input values."""
+    m = build_model(SHIPPED, 2).to(DEV)
+    m.fpn_backend = backend
+    torch.backends.cudnn.allow_tf32 = False
+    outs = {}
+    for graph in (False, True):
+        m.use_cuda_graph = graph
+        for seed in (5, 6, 5):
+            imgs, proj, dv = synth.make_inputs(1, 3, 64, 128, seed=seed)
+            with torch.no_grad():
+                o = m([t.to(DEV) for t in imgs], {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV))
+            outs[(graph, seed)] = {k: o[k].clone() for k in ("depth", "attn_weight", "photometric_confidence")}
+    for seed in (5, 6):
+        for k in ("depth", "attn_weight", "photometric_confidence"):
+            assert torch.equal(outs[(True, seed)][k], outs[(False, seed)][k]), (seed, k)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
 def test_forward_with_native_fpn_against_reference_golden(precision):
     name = "shipped_b1_v3_64x128"
