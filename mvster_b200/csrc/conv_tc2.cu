@@ -26,7 +26,7 @@ constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2;
 constexpr int QBYTES = HH_ * HW_ * 16;       // bytes TMA writes per channel quad of the halo tile (2880)
 constexpr int QPLANE = 2944;                 // quad-plane pitch in shared memory: 2880 rounded up to 128 B (TMA destination alignment)
 constexpr int A_HI = 4 * QPLANE;             // 16 channels of one tile (11776 B incl. padding)
-constexpr int TMAX = 4, SA = 2, SB = 4;
+constexpr int SA = 2;
 constexpr int THREADS = 192;
 
 struct Args {
@@ -37,12 +37,16 @@ struct Args {
 
 template <int NC, int NPASS>
 struct Cfg {
+    // tiles accumulated side by side in TMEM, and depth of the per-tap weight ring (> 9 = more than one full
+    // stage of taps in flight: the weight stream never waits for the MMAs of the current stage)
+    static constexpr int TMAX = NC == 64 ? 2 : 4;
+    static constexpr int SB = NC == 64 ? 12 : 10;
     static constexpr int A_TILE = A_HI * (NPASS == 3 ? 2 : 1);
     static constexpr int A_STAGE = TMAX * A_TILE;
     static constexpr int B_HALF = NC * 64;                    // [NC][16] fp32
     static constexpr int B_STAGE = B_HALF * (NPASS == 3 ? 2 : 1);
     static constexpr int SMEM = 1024 + SA * A_STAGE + SB * B_STAGE + 256;
-    static constexpr int TCOLS = TMAX * NC;                   // 64 / 128 / 256
+    static constexpr int TCOLS = TMAX * NC;                   // 64 / 128 / 128
 };
 
 template <int NC, int NPASS>
@@ -52,13 +56,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t a_base = base, b_base = base + SA * C::A_STAGE, bar_base = b_base + SB * C::B_STAGE;
+    const uint32_t a_base = base, b_base = base + SA * C::A_STAGE, bar_base = b_base + C::SB * C::B_STAGE;
     auto A_FULL = [&](int s) { return bar_base + 8u * s; };
     auto A_READY = [&](int s) { return bar_base + 8u * (SA + s); };
     auto A_EMPTY = [&](int s) { return bar_base + 8u * (2 * SA + s); };
     auto B_FULL = [&](int s) { return bar_base + 8u * (3 * SA + s); };
-    auto B_EMPTY = [&](int s) { return bar_base + 8u * (3 * SA + SB + s); };
-    const uint32_t ACC_FULL = bar_base + 8u * (3 * SA + 2 * SB);
+    auto B_EMPTY = [&](int s) { return bar_base + 8u * (3 * SA + C::SB + s); };
+    const uint32_t ACC_FULL = bar_base + 8u * (3 * SA + 2 * C::SB);
     const uint32_t tmem_slot = ACC_FULL + 8u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,7 +74,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < SA; ++s) { mbar_init(A_FULL(s), 1); mbar_init(A_READY(s), 128); mbar_init(A_EMPTY(s), 1); }
-        for (int s = 0; s < SB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+        for (int s = 0; s < C::SB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
         mbar_init(ACC_FULL, 1);
         fence_barrier_init();
     }
@@ -106,8 +110,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                             tma_load_4d(dst + cq * QPLANE, &x_map, A_FULL(s), kc * 16 + cq * 4, x0 - 1, y0 - 1, plane + kz - pz);
                     }
                     for (int tap = 0; tap < 9; ++tap, ++sb_it) {
-                        const int sb = sb_it % SB;
-                        mbar_wait(B_EMPTY(sb), ((sb_it / SB) & 1) ^ 1);
+                        const int sb = sb_it % C::SB;
+                        mbar_wait(B_EMPTY(sb), ((sb_it / C::SB) & 1) ^ 1);
                         mbar_expect_tx(B_FULL(sb), C::B_STAGE);
                         const int wrow = ((kz * 9 + tap) * kch + kc) * NC;
                         tma_load_2d(b_base + sb * C::B_STAGE, &w_map, B_FULL(sb), 0, wrow);
@@ -128,23 +132,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                 const int s = sa_it % SA;
                 mbar_wait(NPASS == 3 ? A_READY(s) : A_FULL(s), (sa_it / SA) & 1);
                 for (int tap = 0; tap < 9; ++tap, ++sb_it) {
-                    const int sb = sb_it % SB;
-                    mbar_wait(B_FULL(sb), (sb_it / SB) & 1);
+                    const int sb = sb_it % C::SB;
+                    mbar_wait(B_FULL(sb), (sb_it / C::SB) & 1);
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t tap_off = (uint32_t)(((tap / 3) * HW_ + tap % 3) * 16);
-                        const uint32_t b_hi = b_base + sb * C::B_STAGE, b_lo = b_hi + C::B_HALF;
+                        // Descriptors differ only in their 16-byte-granular start-address field (low 14 bits, no carry
+                        // out: shared memory < 256 KB), so every operand is the stage descriptor plus a small constant:
+                        // the single issuing thread spends ~2 integer adds per MMA instead of rebuilding descriptors.
+                        const uint64_t a0 = smem_desc(a_base + s * C::A_STAGE, QPLANE, HW_ * 16, 0) +
+                                            (uint64_t)(((tap / 3) * HW_ + tap % 3));  // (ky*10 + kx) * 16 B
+                        const uint64_t b0 = smem_desc(b_base + sb * C::B_STAGE, 16, 512, 4);
+                        const uint32_t first = (fresh && tap == 0) ? 0u : 1u;
                         for (int t = 0; t < T; ++t) {
-                            const uint32_t a_hi = a_base + s * C::A_STAGE + t * C::A_TILE + tap_off, a_lo = a_hi + A_HI;
+                            const uint64_t at = a0 + (uint64_t)(t * (C::A_TILE >> 4));
                             const uint32_t d = tmem_base + (uint32_t)(t * NC);
-#pragma unroll
-                            for (int pass = 0; pass < NPASS; ++pass) {
-                                const uint32_t aa = (pass == 1) ? a_lo : a_hi, bb = (pass == 2) ? b_lo : b_hi;
-#pragma unroll
-                                for (int k = 0; k < 2; ++k) {
-                                    umma_tf32(d, smem_desc(aa + k * 2 * QPLANE, QPLANE, HW_ * 16, 0), smem_desc(bb + k * 32, 16, 512, 4), IDESC,
-                                              (fresh && tap == 0 && pass == 0 && k == 0) ? 0u : 1u);
-                                }
+                            umma_tf32(d, at, b0, IDESC, first);                                   // A_hi * W_hi, channels 0-7
+                            umma_tf32(d, at + (2 * QPLANE >> 4), b0 + 2, IDESC, 1u);              //              channels 8-15
+                            if (NPASS == 3) {
+                                umma_tf32(d, at + (A_HI >> 4), b0, IDESC, 1u);                    // A_lo * W_hi
+                                umma_tf32(d, at + ((A_HI + 2 * QPLANE) >> 4), b0 + 2, IDESC, 1u);
+                                umma_tf32(d, at, b0 + (C::B_HALF >> 4), IDESC, 1u);               // A_hi * W_lo
+                                umma_tf32(d, at + (2 * QPLANE >> 4), b0 + (C::B_HALF >> 4) + 2, IDESC, 1u);
                             }
                         }
                         umma_commit(B_EMPTY(sb));
@@ -306,7 +314,9 @@ extern "C" int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, cons
     a.tiles_x = ceil_div(W, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
+    const int tmax = NC == 64 ? 2 : 4;  // Cfg<NC, *>::TMAX
     a.T = total_tiles >= 4 * 296 ? 4 : (total_tiles >= 2 * 296 ? 2 : 1);
+    a.T = a.T > tmax ? tmax : a.T;
     a.T = a.T > a.tiles_per_plane ? a.tiles_per_plane : a.T;
     a.groups_per_plane = ceil_div(a.tiles_per_plane, a.T);
     const int grid = a.groups_per_plane * B * D;

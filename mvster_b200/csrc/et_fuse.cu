@@ -18,6 +18,7 @@
 // softmax is a log2(G)-step warp shuffle.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace mvster {
 

@@ -52,8 +52,8 @@ __device__ __forceinline__ float div_corrected(float a, float b, float r) {
     return fmaf(fmaf(-q, b, a), r, q);
 }
 
-template <int C, int G, int D, int LPP>
-__global__ void __launch_bounds__(128, 4) et_fuse_tiled_kernel(const EtArgs a) {
+template <int C, int G, int D, int LPP, int MB>
+__global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) {
     constexpr int CPL = C / LPP;   // channels per lane
     constexpr int GPL = G / LPP;   // groups per lane
     constexpr int CPG = C / G;     // channels per group
@@ -231,20 +231,35 @@ __global__ void __launch_bounds__(128, 4) et_fuse_tiled_kernel(const EtArgs a) {
     }
 }
 
-template <int C, int G, int D, int LPP>
+template <int C, int G, int D, int LPP, int MB>
 static int launch_et_tiled(const EtArgs& a, cudaStream_t st) {
     dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 4), a.B);
-    et_fuse_tiled_kernel<C, G, D, LPP><<<grid, 128, 0, st>>>(a);
+    et_fuse_tiled_kernel<C, G, D, LPP, MB><<<grid, 128, 0, st>>>(a);
     return check_launch("et_fuse_tiled_kernel");
+}
+
+// Resident CTAs per SM the D = 4 kernels are compiled for (register cap 65536 / (128 * MB)): 4 -> 128 regs,
+// 5 -> 96 (12 B spilled), 6 -> 80 (68 B spilled).  MVSTER_ET_MB overrides the default for A/B measurements.
+static int et_min_blocks() {
+    const char* e = getenv("MVSTER_ET_MB");
+    const int v = e ? atoi(e) : 4;
+    return (v == 5 || v == 6) ? v : 4;
 }
 
 // Returns 1 if a tiled specialisation exists for (C,G,D) and was launched into *rc.
 static bool try_launch_tiled(const EtArgs& a, int C, int G, int D, cudaStream_t st, int* rc) {
     if ((long long)a.B * a.Hs * a.Ws * C >= (1ll << 31) || a.B > 65535) return false;  // 32-bit tap offsets
-    if (C == 8 && G == 4 && D == 4) { *rc = launch_et_tiled<8, 4, 4, 1>(a, st); return true; }
-    if (C == 16 && G == 4 && D == 4) { *rc = launch_et_tiled<16, 4, 4, 2>(a, st); return true; }
-    if (C == 32 && G == 8 && D == 8) { *rc = launch_et_tiled<32, 8, 8, 4>(a, st); return true; }
-    if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled<64, 8, 8, 8>(a, st); return true; }
+    const int mb = et_min_blocks();
+    if (C == 8 && G == 4 && D == 4) {
+        *rc = mb == 6 ? launch_et_tiled<8, 4, 4, 1, 6>(a, st) : mb == 5 ? launch_et_tiled<8, 4, 4, 1, 5>(a, st) : launch_et_tiled<8, 4, 4, 1, 4>(a, st);
+        return true;
+    }
+    if (C == 16 && G == 4 && D == 4) {
+        *rc = mb == 6 ? launch_et_tiled<16, 4, 4, 2, 6>(a, st) : mb == 5 ? launch_et_tiled<16, 4, 4, 2, 5>(a, st) : launch_et_tiled<16, 4, 4, 2, 4>(a, st);
+        return true;
+    }
+    if (C == 32 && G == 8 && D == 8) { *rc = launch_et_tiled<32, 8, 8, 4, 4>(a, st); return true; }
+    if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled<64, 8, 8, 8, 4>(a, st); return true; }
     return false;
 }
 
