@@ -147,10 +147,12 @@ def run_reference(args, rank: int):
     }))
 
 
-def config_dict(n):
+def config_dict(n, view_parallel=1):
+    par = f"batch-sharded replicas x{n}" if view_parallel == 1 else \
+        f"{n // view_parallel} frame replica(s) x {view_parallel}-way source-view sharding (1 NCCL all-reduce per stage)"
     return {"workload": "cfg2: DTU-mid 5-view 512x640, 4-stage cascade, fp32, shipped config (reg2d, group_cor 8/8/4/4, "
-                        "D 8/8/4/4, inverse depth); one frame per GPU",
-            "views": 5, "H": 512, "W": 640, "global_batch": n, "parallelism": f"batch-sharded replicas x{n}",
+                        "D 8/8/4/4, inverse depth); one frame per GPU (per view group with --view-parallel)",
+            "views": 5, "H": 512, "W": 640, "global_batch": n // view_parallel, "parallelism": par,
             "l2": "512 MB buffer written between timed steps (L2 flush)"}
 
 
@@ -159,12 +161,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_eager"],
+                    help="reference = the reference algorithm on the host CPU (oracle port); torch_eager = the same "
+                         "PyTorch-op formulation the reference executes (mvster_b200/torch_path.py, eval, no_grad) as eager "
+                         "CUDA kernels through cuDNN/ATen - the 'stock library kernels' bar of SURVEY.md 2b (informational)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap the resident timed loop in cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
+    ap.add_argument("--view-parallel", type=int, default=1,
+                    help="P ranks cooperate on one frame by sharding its source views (one all-reduce per stage); "
+                         "world/P frames run as replicas.  Default 1 = pure batch sharding (weak scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -188,7 +196,16 @@ def main():
 
     B, NV, H, W = WORKLOAD["batch_per_gpu"], WORKLOAD["views"], WORKLOAD["H"], WORKLOAD["W"]
     model = build_model(dev)
-    imgs_h, proj_h, dv_h = synth.make_inputs(B, NV, H, W, seed=rank)
+    # the benchmark replays the forward as one CUDA graph (config.engine.cuda_graph); MVSTER_CUDA_GRAPH=0 runs it eagerly
+    model.use_cuda_graph = os.environ.get("MVSTER_CUDA_GRAPH", "1") == "1"
+    P = max(1, args.view_parallel)
+    if world % P:
+        raise SystemExit(f"--view-parallel {P} does not divide the world size {world}")
+    if P > 1:  # ranks r*P .. r*P+P-1 share one frame: each aggregates its slice of the source views,
+        from mvster_b200 import sharding  # one NCCL all-reduce of [acc|wsum] per stage merges them
+        model.set_view_shard(sharding.make_view_shard(NV - 1, P))
+    frames = world // P
+    imgs_h, proj_h, dv_h = synth.make_inputs(B, NV, H, W, seed=rank // P)
     imgs_p = [t.pin_memory() for t in imgs_h]
     proj_p = {k: v.pin_memory() for k, v in proj_h.items()}
     dv_p = dv_h.pin_memory()
@@ -202,6 +219,29 @@ def main():
     def step_resident():
         with torch.no_grad():
             return model(imgs_d, proj_d, dv_d)
+
+    if args.impl == "torch_eager":  # eager ATen/cuDNN execution of the reference's op sequence on this GPU
+        torch.backends.cudnn.allow_tf32 = True   # PyTorch defaults, as the reference would run
+        for _ in range(max(args.warmup, 5)):
+            with torch.no_grad():
+                model._forward_autograd(imgs_d, proj_d, dv_d)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(args.steps):
+            flush.fill_(1.0)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            with torch.no_grad():
+                model._forward_autograd(imgs_d, proj_d, dv_d)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e in evs) / args.steps
+        if rank == 0:
+            print(json.dumps({"impl": "torch_eager_cuda", "metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+                              "steps": args.steps, "ms_per_step": ms, "dtype": "f32 (cuDNN TF32 allowed, PyTorch default)",
+                              "note": "PyTorch-op formulation of the reference forward, eager on this GPU; informational"}))
+        return
 
     def step_e2e():
         with torch.no_grad():
@@ -257,8 +297,8 @@ def main():
     ms_e2e = ms_total if args.skip_e2e else timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_step, ms_step_e2e = ms_total / args.steps, ms_e2e / args.steps
-    value = world * B / (ms_step * 1e-3)
-    e2e_value = world * B / (ms_step_e2e * 1e-3)
+    value = frames * B / (ms_step * 1e-3)
+    e2e_value = frames * B / (ms_step_e2e * 1e-3)
 
     # ---- warp (ET) kernel alone: live CUDA-event timing per stage, L2 flushed between launches
     peak, peak_src = measured_peaks()
@@ -317,8 +357,9 @@ def main():
         h2d = sum(t.numel() * 4 for t in imgs_p) + sum(v.numel() * 4 for v in proj_p.values()) + dv_p.numel() * 4
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": dict(config_dict(world), engine={
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if P == 1 else f"weak over {frames} frame(s), strong x{P} over source views",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(config_dict(world, P), engine={
                 "fpn_backend": model.fpn_backend, "fpn_precision": model.fpn_precision, "reg_precision": model.reg_precision,
                 "tc_kernel_gen": model.tc_kernel_gen, "cuda_graph": bool(model.use_cuda_graph)}),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": h2d,

@@ -31,4 +31,8 @@ inline int check_launch(const char* what) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// conv_simt_px2.cu: two-output-pixels-per-thread CUDA-core convolution; -100 = shape not covered (use the 1-pixel kernel)
+int conv_px2(const float* x, const float* w, const float* bias, const float* skip, float* y,
+             int B, int Di, int Hi, int Wi, int Cin, int Cout, int kd, int k, int sd, int s, int relu, cudaStream_t st);
+
 }  // namespace mvster

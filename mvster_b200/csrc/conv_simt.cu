@@ -209,6 +209,8 @@ static int run_conv(const float* x, const float* w, const float* bias, const flo
         a.Do = Di; a.Ho = 2 * Hi; a.Wo = 2 * Wi;
     } else {
         a.Do = (Di - 1) / sd + 1; a.Ho = (Hi - 1) / s + 1; a.Wo = (Wi - 1) / s + 1;  // pad = k/2, k = 3 (or 1 along D)
+        const int rc = conv_px2(x, w, bias, skip, y, B, Di, Hi, Wi, Cin, Cout, kd, 3, sd, s, relu, st);
+        if (rc != -100) return rc;  // two-pixels-per-thread kernel covered the layer
     }
     switch (Cin) {
         case 4: return dispatch_cout<4>(a, transposed, st);

@@ -1,0 +1,127 @@
+// CUDA-core channels-last convolution, two output pixels per thread.
+// Same arithmetic as conv_fwd_kernel (conv_simt.cu) / conv2d_kernel (fpn.cu) - one fp32 FMA chain per output -
+// but every broadcast weight read from shared memory now feeds two pixels, halving the shared-memory wavefronts
+// per FMA (the single-pixel kernels were bound by the LSU data pipe, not by the FMA pipe).  Generic in the
+// kernel extent: (kd, k, k) with kd in {1,3}, k in {1,3,5}; strides 1/2; used for the strided layers of the
+// regulariser (mvs4net_utils.py:876-880) and the 5x5 stride-2 / small-channel layers of FPN4 (:424-445).
+#include "common.cuh"
+#include <stdlib.h>
+
+namespace mvster {
+
+struct ConvPxArgs {
+    const float* x; const float* w; const float* bias; const float* skip; float* y;
+    int B, Di, Hi, Wi, Do, Ho, Wo, cout, kd, k, sd, s, relu;
+};
+
+template <int CIN, int COUT_T>
+__global__ void __launch_bounds__(128) conv_px2_kernel(const ConvPxArgs a) {
+    extern __shared__ __align__(16) float w_s[];  // [kd*k*k][CIN][COUT_T]
+    const int cg = blockIdx.y, taps = a.kd * a.k * a.k, pad = a.k / 2, pz = a.kd / 2;
+    for (int i = threadIdx.x; i < taps * CIN * COUT_T; i += blockDim.x) {
+        const int o = i % COUT_T, rest = i / COUT_T;
+        w_s[i] = __ldg(a.w + (long long)rest * a.cout + cg * COUT_T + o);
+    }
+    __syncthreads();
+    const int wo2 = a.Wo / 2;
+    const long long n = (long long)a.B * a.Do * a.Ho * wo2;
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int ox = 2 * (int)(v % wo2), oy = (int)((v / wo2) % a.Ho);
+    const int oz = (int)((v / ((long long)wo2 * a.Ho)) % a.Do), b = (int)(v / ((long long)wo2 * a.Ho * a.Do));
+    float acc0[COUT_T], acc1[COUT_T];
+#pragma unroll
+    for (int o = 0; o < COUT_T; ++o) acc0[o] = acc1[o] = a.bias ? __ldg(a.bias + cg * COUT_T + o) : 0.f;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kz = 0; kz < a.kd; ++kz) {
+        const int iz = oz * a.sd + kz - pz;
+        if ((unsigned)iz >= (unsigned)a.Di) continue;
+        for (int ky = 0; ky < a.k; ++ky) {
+            const int iy = oy * a.s + ky - pad;
+            if ((unsigned)iy >= (unsigned)a.Hi) continue;
+            const float* rowp = a.x + (((long long)b * a.Di + iz) * a.Hi + iy) * (long long)a.Wi * CIN;
+            for (int kx = 0; kx < a.k; ++kx) {
+                const int ix0 = ox * a.s + kx - pad, ix1 = ix0 + a.s;
+                const bool v0 = (unsigned)ix0 < (unsigned)a.Wi, v1 = (unsigned)ix1 < (unsigned)a.Wi;
+                if (!v0 && !v1) continue;
+                const float4* p0 = reinterpret_cast<const float4*>(rowp + (long long)ix0 * CIN);
+                const float4* p1 = reinterpret_cast<const float4*>(rowp + (long long)ix1 * CIN);
+                const float* wt = w_s + ((kz * a.k + ky) * a.k + kx) * CIN * COUT_T;
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                    const float4 t0 = v0 ? __ldg(p0 + c4) : zero, t1 = v1 ? __ldg(p1 + c4) : zero;
+                    const float a0[4] = {t0.x, t0.y, t0.z, t0.w}, a1[4] = {t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float* wr = wt + (c4 * 4 + j) * COUT_T;
+#pragma unroll
+                        for (int o = 0; o < COUT_T; ++o) {
+                            const float wv = wr[o];
+                            acc0[o] = fmaf(a0[j], wv, acc0[o]);
+                            acc1[o] = fmaf(a1[j], wv, acc1[o]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const long long vox = ((((long long)b * a.Do + oz) * a.Ho + oy) * a.Wo + ox);
+    const long long off = vox * a.cout + cg * COUT_T;
+#pragma unroll
+    for (int o = 0; o < COUT_T; o += 4) {
+        float4 r0 = make_float4(acc0[o], acc0[o + 1], acc0[o + 2], acc0[o + 3]);
+        float4 r1 = make_float4(acc1[o], acc1[o + 1], acc1[o + 2], acc1[o + 3]);
+        if (a.relu) {
+            r0.x = fmaxf(r0.x, 0.f); r0.y = fmaxf(r0.y, 0.f); r0.z = fmaxf(r0.z, 0.f); r0.w = fmaxf(r0.w, 0.f);
+            r1.x = fmaxf(r1.x, 0.f); r1.y = fmaxf(r1.y, 0.f); r1.z = fmaxf(r1.z, 0.f); r1.w = fmaxf(r1.w, 0.f);
+        }
+        if (a.skip) {  // added AFTER the ReLU (mvs4net_utils.py:907-909)
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.skip + off + o));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.skip + off + a.cout + o));
+            r0.x += s0.x; r0.y += s0.y; r0.z += s0.z; r0.w += s0.w;
+            r1.x += s1.x; r1.y += s1.y; r1.z += s1.z; r1.w += s1.w;
+        }
+        *reinterpret_cast<float4*>(a.y + off + o) = r0;
+        *reinterpret_cast<float4*>(a.y + off + a.cout + o) = r1;
+    }
+}
+
+template <int CIN, int COUT_T>
+static int launch_px2(const ConvPxArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)a.kd * a.k * a.k * CIN * COUT_T * sizeof(float);
+    auto k = conv_px2_kernel<CIN, COUT_T>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long n = (long long)a.B * a.Do * a.Ho * (a.Wo / 2);
+    k<<<dim3(ceil_div(n, 128), a.cout / COUT_T), 128, smem, st>>>(a);
+    return check_launch("conv_px2_kernel");
+}
+
+template <int CIN>
+static int dispatch_px2(const ConvPxArgs& a, cudaStream_t st) {
+    if (a.cout % 16 == 0) return launch_px2<CIN, 16>(a, st);
+    return launch_px2<CIN, 8>(a, st);
+}
+
+// Returns MVSTER_ERR_UNSUPPORTED_SHAPE (-100) when the two-pixel kernel does not cover the layer (the caller then
+// uses its one-pixel kernel), otherwise the launch status.
+int conv_px2(const float* x, const float* w, const float* bias, const float* skip, float* y,
+             int B, int Di, int Hi, int Wi, int Cin, int Cout, int kd, int k, int sd, int s, int relu, cudaStream_t st) {
+    ConvPxArgs a;
+    a.x = x; a.w = w; a.bias = bias; a.skip = skip; a.y = y;
+    a.B = B; a.Di = Di; a.Hi = Hi; a.Wi = Wi;
+    a.Do = (Di - 1) / sd + 1; a.Ho = (Hi - 1) / s + 1; a.Wo = (Wi - 1) / s + 1;
+    a.cout = Cout; a.kd = kd; a.k = k; a.sd = sd; a.s = s; a.relu = relu;
+    const char* sw = getenv("MVSTER_CONV_PX2");  // "0" forces the one-pixel kernels (A/B measurements)
+    if (sw && sw[0] == '0') return -100;
+    if (a.Wo % 2 || Cout % 8 || (size_t)kd * k * k * Cin * (Cout % 16 == 0 ? 16 : 8) * 4 > 200 * 1024) return -100;
+    switch (Cin) {
+        case 4: return dispatch_px2<4>(a, st);
+        case 8: return dispatch_px2<8>(a, st);
+        case 16: return dispatch_px2<16>(a, st);
+        case 32: return dispatch_px2<32>(a, st);
+        case 64: return dispatch_px2<64>(a, st);
+    }
+    return -100;
+}
+
+}  // namespace mvster

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
 
 // out[n,y,x,:] = bilinear_x2(top)[n,y,x,:] + W_lat . lat[n,y,x,:] + bias     (F.interpolate(scale_factor=2,
 // align_corners=True) + 1x1 lateral conv, mvs4net_utils.py:479-486).  top [N][H/2][W/2][64], lat [N][H][W][CL],
-// w [CL][64].  One thread = one pixel x 16 output channels.
+// w [CL][64].  One thread = one pixel x 4 output channels (16 lanes per pixel).
 template <int CL>
 __global__ void __launch_bounds__(128) fpn_merge_kernel(const float* __restrict__ top, const float* __restrict__ lat,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
@@ -126,8 +126,11 @@ __global__ void __launch_bounds__(128) fpn_merge_kernel(const float* __restrict_
     for (int i = threadIdx.x; i < CL * 64; i += blockDim.x) w_s[i] = __ldg(w + i);
     if (threadIdx.x < 64) w_s[CL * 64 + threadIdx.x] = __ldg(bias + threadIdx.x);
     __syncthreads();
-    const int cg = blockIdx.y;  // 16-channel slice of the 64 output channels
-    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // 16 consecutive lanes own one pixel, lane q its channels 4q..4q+3: every load of `top` and every store of `out`
+    // is a fully coalesced 256-byte run per pixel (the 64-channel full-resolution map is the largest tensor of FPN4).
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long v = t >> 4;
+    const int q = (int)(t & 15);
     if (v >= (long long)N * H * W) return;
     const int x = (int)(v % W), y = (int)((v / W) % H), b = (int)(v / ((long long)W * H));
     const int Hc = H / 2, Wc = W / 2;
@@ -137,40 +140,31 @@ __global__ void __launch_bounds__(128) fpn_merge_kernel(const float* __restrict_
     const int y1 = y0 + (y0 < Hc - 1), x1 = x0 + (x0 < Wc - 1);
     const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
     const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-    const float* tb = top + (long long)b * Hc * Wc * 64 + cg * 16;
-    const float4* p00 = reinterpret_cast<const float4*>(tb + ((long long)y0 * Wc + x0) * 64);
-    const float4* p01 = reinterpret_cast<const float4*>(tb + ((long long)y0 * Wc + x1) * 64);
-    const float4* p10 = reinterpret_cast<const float4*>(tb + ((long long)y1 * Wc + x0) * 64);
-    const float4* p11 = reinterpret_cast<const float4*>(tb + ((long long)y1 * Wc + x1) * 64);
-    float acc[16];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 a00 = __ldg(p00 + q), a01 = __ldg(p01 + q), a10 = __ldg(p10 + q), a11 = __ldg(p11 + q);
-        // ATen order: ly0*(lx0*v00 + lx1*v01) + ly1*(lx0*v10 + lx1*v11)
-        acc[4 * q + 0] = ly0 * (lx0 * a00.x + lx1 * a01.x) + ly1 * (lx0 * a10.x + lx1 * a11.x);
-        acc[4 * q + 1] = ly0 * (lx0 * a00.y + lx1 * a01.y) + ly1 * (lx0 * a10.y + lx1 * a11.y);
-        acc[4 * q + 2] = ly0 * (lx0 * a00.z + lx1 * a01.z) + ly1 * (lx0 * a10.z + lx1 * a11.z);
-        acc[4 * q + 3] = ly0 * (lx0 * a00.w + lx1 * a01.w) + ly1 * (lx0 * a10.w + lx1 * a11.w);
-    }
-    float latv[16];
-#pragma unroll
-    for (int o = 0; o < 16; ++o) latv[o] = w_s[CL * 64 + cg * 16 + o];
+    const float* tb = top + (long long)b * Hc * Wc * 64 + q * 4;
+    const float4 a00 = __ldg(reinterpret_cast<const float4*>(tb + ((long long)y0 * Wc + x0) * 64));
+    const float4 a01 = __ldg(reinterpret_cast<const float4*>(tb + ((long long)y0 * Wc + x1) * 64));
+    const float4 a10 = __ldg(reinterpret_cast<const float4*>(tb + ((long long)y1 * Wc + x0) * 64));
+    const float4 a11 = __ldg(reinterpret_cast<const float4*>(tb + ((long long)y1 * Wc + x1) * 64));
+    // ATen order: ly0*(lx0*v00 + lx1*v01) + ly1*(lx0*v10 + lx1*v11)
+    float4 up;
+    up.x = ly0 * (lx0 * a00.x + lx1 * a01.x) + ly1 * (lx0 * a10.x + lx1 * a11.x);
+    up.y = ly0 * (lx0 * a00.y + lx1 * a01.y) + ly1 * (lx0 * a10.y + lx1 * a11.y);
+    up.z = ly0 * (lx0 * a00.z + lx1 * a01.z) + ly1 * (lx0 * a10.z + lx1 * a11.z);
+    up.w = ly0 * (lx0 * a00.w + lx1 * a01.w) + ly1 * (lx0 * a10.w + lx1 * a11.w);
+    float4 lv = *reinterpret_cast<const float4*>(w_s + CL * 64 + q * 4);  // lateral 1x1 conv: bias + sum_c lat[c] * w[c][4q..4q+3]
     const float4* pl = reinterpret_cast<const float4*>(lat + v * CL);
 #pragma unroll
     for (int c4 = 0; c4 < CL / 4; ++c4) {
-        const float4 t = __ldg(pl + c4);
-        const float tv[4] = {t.x, t.y, t.z, t.w};
+        const float4 tt = __ldg(pl + c4);
+        const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float* wr = w_s + (c4 * 4 + j) * 64 + cg * 16;
-#pragma unroll
-            for (int o = 0; o < 16; ++o) latv[o] = fmaf(tv[j], wr[o], latv[o]);
+            const float4 wr = *reinterpret_cast<const float4*>(w_s + (c4 * 4 + j) * 64 + q * 4);
+            lv.x = fmaf(tv[j], wr.x, lv.x); lv.y = fmaf(tv[j], wr.y, lv.y);
+            lv.z = fmaf(tv[j], wr.z, lv.z); lv.w = fmaf(tv[j], wr.w, lv.w);
         }
     }
-    float4* dst = reinterpret_cast<float4*>(out + v * 64 + cg * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        dst[q] = make_float4(acc[4 * q] + latv[4 * q], acc[4 * q + 1] + latv[4 * q + 1], acc[4 * q + 2] + latv[4 * q + 2], acc[4 * q + 3] + latv[4 * q + 3]);
+    *reinterpret_cast<float4*>(out + v * 64 + q * 4) = make_float4(up.x + lv.x, up.y + lv.y, up.z + lv.z, up.w + lv.w);
 }
 
 }  // namespace mvster
@@ -185,6 +179,8 @@ extern "C" int mvster_conv2d_nhwc_f32(const float* x, const float* w, const floa
     MVSTER_REQUIRE(stride == 1 || stride == 2, "mvster_conv2d_nhwc_f32: stride %d (1 or 2)", stride);
     Conv2dArgs a{x, w, bias, y, N, H, W, (H - 1) / stride + 1, (W - 1) / stride + 1, Cout, k, stride, relu};
     cudaStream_t st = (cudaStream_t)stream;
+    const int rc = conv_px2(x, w, bias, nullptr, y, N, 1, H, W, Cin, Cout, 1, k, 1, stride, relu, st);
+    if (rc != -100) return rc;  // two-pixels-per-thread kernel covered the layer
     switch (Cin) {
         case 8: return dispatch_conv2d<8>(a, st);
         case 16: return dispatch_conv2d<16>(a, st);
@@ -208,8 +204,8 @@ extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, cons
                                     int N, int H, int W, int Clat, mvster_stream_t stream) {
     MVSTER_REQUIRE(top && lateral && w && bias && out, "mvster_fpn_merge_f32: null pointer");
     MVSTER_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mvster_fpn_merge_f32: H,W must be even");
-    const long long n = (long long)N * H * W;
-    dim3 grid(ceil_div(n, 128), 4);
+    const long long n = (long long)N * H * W * 16;  // 16 lanes per pixel
+    dim3 grid(ceil_div(n, 128));
     cudaStream_t st = (cudaStream_t)stream;
     if (Clat == 8) fpn_merge_kernel<8><<<grid, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
     else if (Clat == 16) fpn_merge_kernel<16><<<grid, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);

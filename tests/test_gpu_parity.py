@@ -279,9 +279,13 @@ def test_layout_helper():
 
 
 # ----------------------------------------------------------------------------- cascade
-def _run_ours(kwargs, seed, imgs, proj, dv):
+def _run_ours(kwargs, seed, imgs, proj, dv, strict_fp32=False):
+    """strict_fp32: every convolution as an exact fp32 FMA chain (CUDA-core regulariser, cuDNN fp32 feature net);
+    default: the engine's defaults (3xTF32 tensor-core 3x3 layers, native feature pyramid)."""
     torch.backends.cudnn.allow_tf32 = False
     m = build_model(kwargs, seed).to(DEV)
+    if strict_fp32:
+        m.reg_precision, m.fpn_backend = "fp32", "torch"
     with torch.no_grad():
         out = m([t.to(DEV) for t in imgs], {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV))
     torch.cuda.synchronize()
@@ -339,11 +343,12 @@ def test_teacher_forced_stages_match_oracle():
     assert not failures, "; ".join(failures)
 
 
+@pytest.mark.parametrize("strict_fp32", [True, False], ids=["strict_fp32", "default_3xtf32"])
 @pytest.mark.parametrize("name", ["shipped_b1_v3_64x128", "shipped_b2_v2_64x64"])
-def test_module_forward_against_reference_golden(name):
+def test_module_forward_against_reference_golden(name, strict_fp32):
     """End to end through MVS4net.forward on the GPU vs outputs of the unmodified reference (fixtures)."""
     z, imgs, proj, dv = load_golden(name)
-    m, out = _run_ours(GOLDEN_CASES[name], int(z["meta_seed"]), imgs, proj, dv)
+    m, out = _run_ours(GOLDEN_CASES[name], int(z["meta_seed"]), imgs, proj, dv, strict_fp32=strict_fp32)
     drift_free = torch.ones_like(torch.from_numpy(z["s1_depth"]), dtype=torch.bool)
     for s in range(1, 5):
         st = out[f"stage{s}"]
@@ -355,10 +360,11 @@ def test_module_forward_against_reference_golden(name):
         agree = (st["depth"].cpu() - ref_depth).abs() <= 1e-4 * ref_depth
         stable = top2_gap(ref_attn) > 1e-3
         bad = ((~agree) & stable & drift_free).float().sum().item() / max(1.0, (stable & drift_free).float().sum().item())
-        record(f"e2e_golden_{name}_s{s}", bad_frac=bad, considered=float((stable & drift_free).float().mean()), agree_all=float(agree.float().mean()))
+        record(f"e2e_golden_{name}_{'strict' if strict_fp32 else 'default'}_s{s}", bad_frac=bad,
+               considered=float((stable & drift_free).float().mean()), agree_all=float(agree.float().mean()))
         assert bad < 5e-3, f"stage {s}: {bad:.3%} of tie-free, drift-free pixels differ by > 1e-4 relative"
-        if s == 1:
-            assert (st["attn_weight"].cpu() - ref_attn).abs().max().item() < 5e-5
+        if s == 1:  # identical hypotheses on both sides at stage 1: probabilities are directly comparable
+            assert (st["attn_weight"].cpu() - ref_attn).abs().max().item() < (5e-5 if strict_fp32 else 5e-4)
         drift_free = drift_free & agree
     assert out["depth"].data_ptr() == out["stage4"]["depth"].data_ptr()  # top-level keys alias the last stage
     assert out["stage2"]["mono_feat"].shape == (imgs[0].shape[0], 32, imgs[0].shape[2] // 4, imgs[0].shape[3] // 4)

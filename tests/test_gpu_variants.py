@@ -131,5 +131,5 @@ def test_variant_module_forward_against_reference_golden(name):
         record(f"e2e_golden_{name}_s{s}", bad_frac=bad, considered=float((stable & ok).float().mean()), agree_all=float(agree.float().mean()))
         assert bad < 5e-3, f"stage {s}: {bad:.3%} of tie-free, drift-free pixels differ"
         if s == 1:
-            assert (st["attn_weight"].cpu() - ref_attn).abs().max().item() < 1e-4
+            assert (st["attn_weight"].cpu() - ref_attn).abs().max().item() < 5e-4  # default engine: 3xTF32 feature pyramid
         ok = ok & agree
