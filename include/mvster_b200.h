@@ -177,6 +177,16 @@ int mvster_conv_first_f32(const float* img_nchw, const float* w, const float* bi
 int mvster_fpn_merge_f32(const float* top, const float* lateral, const float* w, const float* bias, float* out,
                          int N, int H, int W, int Clat, mvster_stream_t stream);
 
+/* Point-wise (1x1) convolution as a tensor-core GEMM [pixels x Cin] x [Cin x Cout] (conv_tc2.cu, centre tap only).
+ * Cin in {16,32,64}; Cout in {8,16,32,64} or 68..80 (N padded to 80).  w_packed = pack_tc2_weights([1][Cin][Cout]). */
+int mvster_pointwise_tc2_f32(const float* x, const float* w_packed, const float* bias, float* y,
+                             int N, int H, int W, int Cin, int Cout, int relu, int npass, mvster_stream_t stream);
+/* Last pyramid level fused (mvs4net_utils.py:485-486, stage4 = out4(up2(top2) + inner3(c0))) without forming the
+ * 64-channel full-resolution map: U [N][H/2][W/2][u_channels >= 72] = per-tap 1x1 conv of top2 (channels tap*8+o),
+ * c0 [N][H][W][8], w_comp [9][8][8] = W4[tap] Wi3, b_tap [9][8] = W4[tap] bi3  ->  out [N][H][W][8]. */
+int mvster_fpn_out4_gather_f32(const float* U, int u_channels, const float* c0, const float* w_comp, const float* b_tap,
+                               float* out, int N, int H, int W, mvster_stream_t stream);
+
 /* ---- head ---------------------------------------------------------------- */
 /* mvs4net_utils.py:1066-1088.  Either `logits` [B][D][H][W] is given, or
  * (feat8 [B][D][H][W][8], prob_w[8], prob_b[1]) and the 1x1x1 `prob` conv of

@@ -46,6 +46,8 @@ SIGNATURES = {
     "mvster_conv2d_nhwc_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_conv_first_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "mvster_fpn_merge_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "mvster_pointwise_tc2_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_fpn_out4_gather_f32": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p]),
     "mvster_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "mvster_upsample_bilinear_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mvster_nchw_to_nhwc_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),

@@ -31,7 +31,7 @@ constexpr int THREADS = 192;
 
 struct Args {
     const float* bias; const float* skip; float* y;
-    int B, D, H, W, cin, cout, kd, relu;
+    int B, D, H, W, cin, cout, kd, ntap, relu;  // ntap = in-plane taps: 9 (3x3) or 1 (1x1, the centre tap)
     int tiles_x, tiles_per_plane, groups_per_plane, T;
 };
 
@@ -39,14 +39,14 @@ template <int NC, int NPASS>
 struct Cfg {
     // tiles accumulated side by side in TMEM, and depth of the per-tap weight ring (> 9 = more than one full
     // stage of taps in flight: the weight stream never waits for the MMAs of the current stage)
-    static constexpr int TMAX = NC == 64 ? 2 : 4;
-    static constexpr int SB = NC == 64 ? 12 : 10;
+    static constexpr int TMAX = NC >= 64 ? 2 : 4;
+    static constexpr int SB = NC == 80 ? 8 : (NC == 64 ? 12 : 10);
     static constexpr int A_TILE = A_HI * (NPASS == 3 ? 2 : 1);
     static constexpr int A_STAGE = TMAX * A_TILE;
     static constexpr int B_HALF = NC * 64;                    // [NC][16] fp32
     static constexpr int B_STAGE = B_HALF * (NPASS == 3 ? 2 : 1);
     static constexpr int SMEM = 1024 + SA * A_STAGE + SB * B_STAGE + 256;
-    static constexpr int TCOLS = TMAX * NC;                   // 64 / 128 / 128
+    static constexpr int TCOLS = TMAX * NC <= 64 ? 64 : (TMAX * NC <= 128 ? 128 : 256);  // power of two >= TMAX*NC
 };
 
 template <int NC, int NPASS>
@@ -109,13 +109,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         for (int cq = 0; cq < 4; ++cq)  // one 4-channel box per quad plane: [18][10][4 floats]
                             tma_load_4d(dst + cq * QPLANE, &x_map, A_FULL(s), kc * 16 + cq * 4, x0 - 1, y0 - 1, plane + kz - pz);
                     }
-                    for (int tap = 0; tap < 9; ++tap, ++sb_it) {
+                    for (int tap = 0; tap < a.ntap; ++tap, ++sb_it) {
                         const int sb = sb_it % C::SB;
                         mbar_wait(B_EMPTY(sb), ((sb_it / C::SB) & 1) ^ 1);
                         mbar_expect_tx(B_FULL(sb), C::B_STAGE);
-                        const int wrow = ((kz * 9 + tap) * kch + kc) * NC;
+                        const int wrow = ((kz * a.ntap + tap) * kch + kc) * NC;
                         tma_load_2d(b_base + sb * C::B_STAGE, &w_map, B_FULL(sb), 0, wrow);
-                        if (NPASS == 3) tma_load_2d(b_base + sb * C::B_STAGE + C::B_HALF, &w_map, B_FULL(sb), 0, a.kd * 9 * kch * NC + wrow);
+                        if (NPASS == 3) tma_load_2d(b_base + sb * C::B_STAGE + C::B_HALF, &w_map, B_FULL(sb), 0, a.kd * a.ntap * kch * NC + wrow);
                     }
                 }
             }
@@ -131,7 +131,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
             for (int kc = 0; kc < kch; ++kc, ++sa_it) {
                 const int s = sa_it % SA;
                 mbar_wait(NPASS == 3 ? A_READY(s) : A_FULL(s), (sa_it / SA) & 1);
-                for (int tap = 0; tap < 9; ++tap, ++sb_it) {
+                for (int tap = 0; tap < a.ntap; ++tap, ++sb_it) {
                     const int sb = sb_it % C::SB;
                     mbar_wait(B_FULL(sb), (sb_it / C::SB) & 1);
                     tc_fence_after();
@@ -140,7 +140,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         // out: shared memory < 256 KB), so every operand is the stage descriptor plus a small constant:
                         // the single issuing thread spends ~2 integer adds per MMA instead of rebuilding descriptors.
                         const uint64_t a0 = smem_desc(a_base + s * C::A_STAGE, QPLANE, HW_ * 16, 0) +
-                                            (uint64_t)(((tap / 3) * HW_ + tap % 3));  // (ky*10 + kx) * 16 B
+                                            (uint64_t)(a.ntap == 1 ? HW_ + 1 : (tap / 3) * HW_ + tap % 3);  // (ky*10 + kx) * 16 B
                         const uint64_t b0 = smem_desc(b_base + sb * C::B_STAGE, 16, 512, 4);
                         const uint32_t first = (fresh && tap == 0) ? 0u : 1u;
                         for (int t = 0; t < T; ++t) {
@@ -278,17 +278,34 @@ extern "C" int mvster_conv3d_tc2_supported(int Cin, int Cout, int kd, int stride
     return cin_ok && cout_ok && (kd == 1 || kd == 3) && stride_hw == 1 && !transposed;
 }
 
+static int run_tc2(const float* x, const float* w_packed, const float* bias, const float* skip, float* y,
+                   int B, int D, int H, int W, int Cin, int Cout, int kd, int ntap, int relu, int npass, mvster_stream_t stream);
+
 extern "C" int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bias, const float* skip, float* y,
                                      int B, int D, int H, int W, int Cin, int Cout, int kd, int relu, int npass,
                                      mvster_stream_t stream) {
+    MVSTER_REQUIRE(mvster_conv3d_tc2_supported(Cin, Cout, kd, 1, 0), "mvster_conv3d_tc2_f32: unsupported layer Cin=%d Cout=%d kd=%d", Cin, Cout, kd);
+    return run_tc2(x, w_packed, bias, skip, y, B, D, H, W, Cin, Cout, kd, 9, relu, npass, stream);
+}
+
+/* Point-wise (1x1) convolution = plain GEMM [pixels x Cin] x [Cin x Cout] on the same kernel (centre tap only).
+ * Cout in {8,16,32,64} or 65..80 (padded to N = 80).  w_packed: packing.pack_tc2_weights of a [1][Cin][Cout] tensor. */
+extern "C" int mvster_pointwise_tc2_f32(const float* x, const float* w_packed, const float* bias, float* y,
+                                        int N, int H, int W, int Cin, int Cout, int relu, int npass, mvster_stream_t stream) {
+    MVSTER_REQUIRE((Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || (Cout > 64 && Cout <= 80 && Cout % 4 == 0)),
+                   "mvster_pointwise_tc2_f32: unsupported Cin=%d Cout=%d", Cin, Cout);
+    return run_tc2(x, w_packed, bias, nullptr, y, N, 1, H, W, Cin, Cout, 1, 1, relu, npass, stream);
+}
+
+static int run_tc2(const float* x, const float* w_packed, const float* bias, const float* skip, float* y,
+                   int B, int D, int H, int W, int Cin, int Cout, int kd, int ntap, int relu, int npass, mvster_stream_t stream) {
     using namespace mvster::tc2;
     MVSTER_REQUIRE(x && w_packed && y, "mvster_conv3d_tc2_f32: null pointer");
-    MVSTER_REQUIRE(mvster_conv3d_tc2_supported(Cin, Cout, kd, 1, 0), "mvster_conv3d_tc2_f32: unsupported layer Cin=%d Cout=%d kd=%d", Cin, Cout, kd);
     MVSTER_REQUIRE(npass == 1 || npass == 3, "mvster_conv3d_tc2_f32: npass must be 1 (tf32) or 3 (3xtf32)");
     MVSTER_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "mvster_conv3d_tc2_f32: bad shape");
     EncodeTiledFn enc = encode_fn();
     MVSTER_REQUIRE(enc, "mvster_conv3d_tc2_f32: cuTensorMapEncodeTiled is unavailable in this driver");
-    const int NC = Cout < 16 ? 16 : Cout, kch = Cin / 16, taps = kd * 9;
+    const int NC = Cout < 16 ? 16 : (Cout > 64 ? 80 : Cout), kch = Cin / 16, taps = kd * ntap;
 
     CUtensorMap xm, wm;
     {   // activations [B*D][H][W][C]; a box is one channel QUAD (16 B) of an 18 x 10 pixel halo patch
@@ -310,11 +327,11 @@ extern "C" int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, cons
     }
     Args a;
     a.bias = bias; a.skip = skip; a.y = y;
-    a.B = B; a.D = D; a.H = H; a.W = W; a.cin = Cin; a.cout = Cout; a.kd = kd; a.relu = relu;
+    a.B = B; a.D = D; a.H = H; a.W = W; a.cin = Cin; a.cout = Cout; a.kd = kd; a.ntap = ntap; a.relu = relu;
     a.tiles_x = ceil_div(W, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
-    const int tmax = NC == 64 ? 2 : 4;  // Cfg<NC, *>::TMAX
+    const int tmax = NC >= 64 ? 2 : 4;  // Cfg<NC, *>::TMAX
     a.T = total_tiles >= 4 * 296 ? 4 : (total_tiles >= 2 * 296 ? 2 : 1);
     a.T = a.T > tmax ? tmax : a.T;
     a.T = a.T > a.tiles_per_plane ? a.tiles_per_plane : a.T;
@@ -323,5 +340,6 @@ extern "C" int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, cons
     cudaStream_t st = (cudaStream_t)stream;
     if (NC == 16) return npass == 3 ? launch<16, 3>(xm, wm, a, grid, st) : launch<16, 1>(xm, wm, a, grid, st);
     if (NC == 32) return npass == 3 ? launch<32, 3>(xm, wm, a, grid, st) : launch<32, 1>(xm, wm, a, grid, st);
+    if (NC == 80) return npass == 3 ? launch<80, 3>(xm, wm, a, grid, st) : launch<80, 1>(xm, wm, a, grid, st);
     return npass == 3 ? launch<64, 3>(xm, wm, a, grid, st) : launch<64, 1>(xm, wm, a, grid, st);
 }

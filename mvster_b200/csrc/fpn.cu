@@ -213,3 +213,93 @@ extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, cons
     else MVSTER_REQUIRE(false, "mvster_fpn_merge_f32: unsupported lateral channels %d (8,16,32)", Clat);
     return check_launch("fpn_merge_kernel");
 }
+
+// ---- last pyramid level without materialising the 64-channel full-resolution map ------------------------------
+// Reference (mvs4net_utils.py:485-486):  top3 = up2(top2) + inner3(c0);  stage4 = out4(top3)  with out4 a 3x3 conv
+// 64 -> 8 without bias.  The conv's channel mixing commutes with the (per-channel, linear) bilinear up-sampling:
+//     out4(top3)(p) = sum_{tap, p+tap inside} [ up2(W4[tap] . top2)(p+tap) + (W4[tap] Wi3) . c0(p+tap) + W4[tap] . bi3 ]
+// so the 64-channel map at FULL resolution (420 MB for 5 views at 512x640, written and re-read) is never formed:
+// U = [W4[tap] . top2]_tap is a 1x1 conv 64 -> 72 at HALF resolution (a GEMM, tensor cores), and this kernel gathers
+// 9 bilinear samples of 8 channels plus a 3x3 conv on the 8-channel c0 with composite weights.  4608 MAC per output
+// pixel become 1152 + 288 + 576; same result up to fp32 summation order.
+namespace mvster {
+
+__global__ void __launch_bounds__(128) fpn_out4_gather_kernel(const float* __restrict__ U, int UC, const float* __restrict__ c0,
+                                                              const float* __restrict__ wc, const float* __restrict__ bt,
+                                                              float* __restrict__ out, int N, int H, int W) {
+    __shared__ __align__(16) float wc_s[9 * 8 * 8 + 9 * 8];
+    for (int i = threadIdx.x; i < 576; i += blockDim.x) wc_s[i] = __ldg(wc + i);
+    if (threadIdx.x < 72) wc_s[576 + threadIdx.x] = __ldg(bt + threadIdx.x);
+    __syncthreads();
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= (long long)N * H * W) return;
+    const int x = (int)(v % W), y = (int)((v / W) % H), b = (int)(v / ((long long)W * H));
+    const int Hc = H / 2, Wc = W / 2;
+    const float sy = Hc > 1 ? __fdiv_rn((float)(Hc - 1), (float)(H - 1)) : 0.f, sx = Wc > 1 ? __fdiv_rn((float)(Wc - 1), (float)(W - 1)) : 0.f;
+    // align_corners=True source rows / columns of the three fine rows y-1..y+1 and columns x-1..x+1
+    int ry0[3], ry1[3], rx0[3], rx1[3];
+    float wy1[3], wx1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int yy = min(max(y + k - 1, 0), H - 1), xx = min(max(x + k - 1, 0), W - 1);
+        const float fy = __fmul_rn(sy, (float)yy), fx = __fmul_rn(sx, (float)xx);
+        ry0[k] = min((int)floorf(fy), Hc - 1); rx0[k] = min((int)floorf(fx), Wc - 1);
+        ry1[k] = ry0[k] + (ry0[k] < Hc - 1); rx1[k] = rx0[k] + (rx0[k] < Wc - 1);
+        wy1[k] = fminf(fmaxf(fy - (float)ry0[k], 0.f), 1.f); wx1[k] = fminf(fmaxf(fx - (float)rx0[k], 0.f), 1.f);
+    }
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+    const float* Ub = U + (long long)b * Hc * Wc * UC;
+    const float* cb = c0 + (long long)b * H * W * 8;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        if ((unsigned)(y + ky - 1) >= (unsigned)H) continue;  // zero padding of the 3x3 conv
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            if ((unsigned)(x + kx - 1) >= (unsigned)W) continue;
+            const int tap = ky * 3 + kx;
+            // (a) lateral path: composite 3x3 conv on c0 (+ the lateral bias seen through this tap)
+            const float4* pc = reinterpret_cast<const float4*>(cb + ((long long)(y + ky - 1) * W + (x + kx - 1)) * 8);
+            const float4 c_lo = __ldg(pc), c_hi = __ldg(pc + 1);
+            const float cv[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+            const float* wt = wc_s + tap * 64;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[o] += wc_s[576 + tap * 8 + o];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = fmaf(cv[c], wt[c * 8 + o], acc[o]);
+            // (b) top-down path: bilinear sample of U_tap (8 channels at half resolution) at the fine position p + tap
+            const float ly1 = wy1[ky], ly0 = 1.f - ly1, lx1 = wx1[kx], lx0 = 1.f - lx1;
+            const float* u00 = Ub + ((long long)ry0[ky] * Wc + rx0[kx]) * UC + tap * 8;
+            const float* u01 = Ub + ((long long)ry0[ky] * Wc + rx1[kx]) * UC + tap * 8;
+            const float* u10 = Ub + ((long long)ry1[ky] * Wc + rx0[kx]) * UC + tap * 8;
+            const float* u11 = Ub + ((long long)ry1[ky] * Wc + rx1[kx]) * UC + tap * 8;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 a00 = __ldg(reinterpret_cast<const float4*>(u00) + h), a01 = __ldg(reinterpret_cast<const float4*>(u01) + h);
+                const float4 a10 = __ldg(reinterpret_cast<const float4*>(u10) + h), a11 = __ldg(reinterpret_cast<const float4*>(u11) + h);
+                acc[4 * h + 0] += ly0 * (lx0 * a00.x + lx1 * a01.x) + ly1 * (lx0 * a10.x + lx1 * a11.x);
+                acc[4 * h + 1] += ly0 * (lx0 * a00.y + lx1 * a01.y) + ly1 * (lx0 * a10.y + lx1 * a11.y);
+                acc[4 * h + 2] += ly0 * (lx0 * a00.z + lx1 * a01.z) + ly1 * (lx0 * a10.z + lx1 * a11.z);
+                acc[4 * h + 3] += ly0 * (lx0 * a00.w + lx1 * a01.w) + ly1 * (lx0 * a10.w + lx1 * a11.w);
+            }
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(out + v * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+}  // namespace mvster
+
+extern "C" int mvster_fpn_out4_gather_f32(const float* U, int u_channels, const float* c0, const float* w_comp, const float* b_tap,
+                                          float* out, int N, int H, int W, mvster_stream_t stream) {
+    MVSTER_REQUIRE(U && c0 && w_comp && b_tap && out, "mvster_fpn_out4_gather_f32: null pointer");
+    MVSTER_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mvster_fpn_out4_gather_f32: H,W must be even");
+    MVSTER_REQUIRE(u_channels >= 72 && u_channels % 4 == 0, "mvster_fpn_out4_gather_f32: U needs >= 72 channels (9 taps x 8)");
+    const long long n = (long long)N * H * W;
+    mvster::fpn_out4_gather_kernel<<<mvster::ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(U, u_channels, c0, w_comp, b_tap, out, N, H, W);
+    return mvster::check_launch("fpn_out4_gather_kernel");
+}

@@ -51,6 +51,15 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
         out[f"out{i}.w"] = w
         if w.shape[0] == 9:
             out[f"out{i}.tc"] = packing.pack_tc2_weights(w, 3)
+    # fused last level (fpn.cu: fpn_out4_gather_kernel): out4(up2(top2) + inner3(c0)) with the 3x3 conv's channel
+    # mixing moved in front of the up-sampling - composite weights, all built in fp64
+    w4 = out["out4.w"].double()                       # [9][64][8]  (tap, top channel m, out channel o)
+    wi3, bi3 = out["inner3.w"].double(), out["inner3.b"].double()  # [8][64], [64]
+    out["out4.wc"] = torch.einsum("cm,tmo->tco", wi3, w4).float().contiguous()   # [9][8][8]
+    out["out4.bt"] = torch.einsum("m,tmo->to", bi3, w4).float().contiguous()     # [9][8]
+    u_w = w4.permute(1, 0, 2).reshape(1, 64, 72).float().contiguous()            # U channel = tap*8 + o
+    out["out4.u_w"] = u_w
+    out["out4.u_tc"] = packing.pack_tc2_weights(u_w, 3)
     return out
 
 
@@ -83,8 +92,10 @@ def _merge(top: Tensor, lat: Tensor, w: Tensor, b: Tensor) -> Tensor:
     return out
 
 
-def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0) -> Dict[str, Tensor]:
-    """imgs [N,3,H,W] contiguous NCHW fp32 on the GPU -> {'stage1'..'stage4': [N,h,w,C] NHWC}."""
+def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bool = True) -> Dict[str, Tensor]:
+    """imgs [N,3,H,W] contiguous NCHW fp32 on the GPU -> {'stage1'..'stage4': [N,h,w,C] NHWC}.
+    npass: 0 = every layer on the CUDA cores (exact fp32), 3 / 1 = 3x3 stride-1 layers with Cin >= 16 on tcgen05
+    (3xTF32 / TF32).  fused_last: algebraically fused last level (never forms the 64-channel full-res map)."""
     capi._chk(imgs, "imgs")
     N, three, H, W = imgs.shape
     if three != 3 or H % 8 or W % 8:
@@ -106,6 +117,26 @@ def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0) -> Dict[str, T
     out["stage2"] = _conv3x3(top, wts, "out2", False, npass)
     top = _merge(top, c1, wts["inner2.w"], wts["inner2.b"])
     out["stage3"] = _conv3x3(top, wts, "out3", False, npass)
-    top = _merge(top, c0, wts["inner3.w"], wts["inner3.b"])
-    out["stage4"] = _conv3x3(top, wts, "out4", False, npass)
+    if fused_last:
+        out["stage4"] = _fused_last_level(wts, top, c0, npass)
+    else:  # literal form: materialise the 64-channel full-resolution map, then the 3x3 conv
+        top = _merge(top, c0, wts["inner3.w"], wts["inner3.b"])
+        out["stage4"] = _conv3x3(top, wts, "out4", False, npass)
+    return out
+
+
+def _fused_last_level(wts: Dict[str, Tensor], top2: Tensor, c0: Tensor, npass: int) -> Tensor:
+    """stage4 = out4(up2(top2) + inner3(c0)) = sum_tap [ up2(W4[tap].top2) + (W4[tap] Wi3).c0 + W4[tap].bi3 ](p + tap)."""
+    N, h, w, _ = top2.shape
+    lib = _lib.load()
+    if npass:
+        tc = wts["out4.u_tc"]
+        U = torch.empty((N, h, w, 72), device=top2.device, dtype=torch.float32)
+        _lib.check(lib.mvster_pointwise_tc2_f32(capi._ptr(top2), capi._ptr(tc if npass == 3 else tc[:tc.numel() // 2].contiguous()), None,
+                                                capi._ptr(U), N, h, w, 64, 72, 0, npass, capi._stream()), "mvster_pointwise_tc2_f32")
+    else:
+        U = _conv2d(top2, wts["out4.u_w"], None, 1, 1, False)
+    out = torch.empty((N, 2 * h, 2 * w, 8), device=top2.device, dtype=torch.float32)
+    _lib.check(lib.mvster_fpn_out4_gather_f32(capi._ptr(U), 72, capi._ptr(c0), capi._ptr(wts["out4.wc"]), capi._ptr(wts["out4.bt"]),
+                                              capi._ptr(out), N, 2 * h, 2 * w, capi._stream()), "mvster_fpn_out4_gather_f32")
     return out

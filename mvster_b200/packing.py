@@ -59,7 +59,7 @@ def pack_tc2_weights(w: Tensor, npass: int = 3) -> Tensor:
     taps, cin, cout = w.shape
     if cin % 16:
         raise ValueError(f"Cin={cin} is not a multiple of 16")
-    n = max(cout, 16)
+    n = 16 if cout < 16 else (80 if cout > 64 else cout)  # the UMMA N the kernel instantiates (16 / 32 / 64 / 80)
     wp = torch.zeros((taps, cin, n), dtype=torch.float32)
     wp[:, :, :cout] = w.float()
     slabs = wp.reshape(taps, cin // 16, 16, n).permute(0, 1, 3, 2).contiguous()

@@ -12,22 +12,23 @@ from mvster_b200 import fpn_engine, synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("fused_last", [True, False], ids=["fused_last_level", "literal_last_level"])
 @pytest.mark.parametrize("npass,tol", [(0, 2e-5), (3, 1e-4), (1, 2e-2)])
 @pytest.mark.parametrize("N,H,W", [(2, 64, 128), (3, 128, 192)])
-def test_native_fpn_matches_oracle(npass, tol, N, H, W):
+def test_native_fpn_matches_oracle(npass, tol, N, H, W, fused_last):
     sd = build_model(SHIPPED, 4).state_dict()
     imgs, _, _ = synth.make_inputs(1, N, H, W, seed=8)
     x = torch.cat(imgs, 0)
     with torch.no_grad():
         want = oracle.fpn4_features(sd, x)
     wts = {k: v.to(DEV) for k, v in fpn_engine.pack_fpn(sd).items()}
-    got = fpn_engine.run_fpn(wts, x.to(DEV), npass)
+    got = fpn_engine.run_fpn(wts, x.to(DEV), npass, fused_last=fused_last)
     for s in range(1, 5):
         g = got[f"stage{s}"].permute(0, 3, 1, 2).cpu()
         w = want[f"stage{s}"]
         assert g.shape == w.shape
         err = (g - w).abs().max().item() / w.abs().max().item()
-        record(f"fpn_npass{npass}_{N}x{H}x{W}_stage{s}", rel_to_max=err)
+        record(f"fpn_npass{npass}_{'fused' if fused_last else 'literal'}_{N}x{H}x{W}_stage{s}", rel_to_max=err)
         assert err < tol, f"stage{s}: {err:.2e}"
 
 
