@@ -332,9 +332,11 @@ def main():
         tot_b = sum(p["bytes"] for p in per_stage)
         tot_t = sum(p["us"] for p in per_stage) * 1e-6
         dom = per_stage[3]
-        roof = {"kernel": "et_fuse_kernel (stage 4 launch: C=8,G=4,D=4, 4 source views)", "bound": "hbm",
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+        # (profiles/r01_et_fuse_tiled_v3_ncu.md: 55.0 MB + 3.18 MB; the 21 MB cost volume mostly stays in the 126 MB L2)
+        roof = {"kernel": "et_fuse_tiled_kernel<8,4,4,1> (stage 4 launch: C=8, G=4, D=4, 4 source views, 327680 pixels)", "bound": "hbm",
                 "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "peak_source": peak_src,
-                "traffic": None, "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak,
+                "algorithmic_bytes": dom["bytes"], "traffic": 58.18e6 if (B, NV, H, W) == (1, 5, 512, 640) else None, "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak,
                                                  "bytes": tot_b, "us": tot_t * 1e6},
                 "per_stage": per_stage}
 

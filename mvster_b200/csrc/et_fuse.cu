@@ -205,6 +205,7 @@ __global__ void et_normalize_kernel(float* __restrict__ cost, const float* __res
 
 }  // namespace mvster
 #include "et_fuse_tiled.cuh"
+#include "et_fuse_dlane.cuh"
 namespace mvster {
 
 template <int CPG, int G, int D>
@@ -268,7 +269,8 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     cudaStream_t st = (cudaStream_t)stream;
     int rc = MVSTER_OK;
     const bool plain = !(flags & (MVSTER_ET_GENERIC | MVSTER_ET_SQDIFF | MVSTER_ET_NO_FUSE_D));
-    if (plain && try_launch_tiled(a, C, G, D, st, &rc)) return rc;
+    if (plain && try_launch_dlane(a, C, G, D, st, &rc)) return rc;   // D = 4 stages: hypotheses across lanes
+    if (plain && try_launch_tiled(a, C, G, D, st, &rc)) return rc;   // D = 8 stages: hypotheses unrolled per lane
     return G == 4 ? dispatch_cpg<4>(a, C / G, D, st) : dispatch_cpg<8>(a, C / G, D, st);
 }
 
