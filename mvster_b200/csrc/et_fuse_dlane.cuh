@@ -156,11 +156,14 @@ static int launch_et_dlane(const EtArgs& a, cudaStream_t st) {
     return check_launch("et_fuse_dlane_kernel");
 }
 
-// D = 4 stages of the shipped configuration.  MVSTER_ET_DLANE=0 falls back to et_fuse_tiled_kernel (A/B measurements).
+// MEASURED (B200, cfg2, profiles/r01_et_fuse_dlane_ncu.md): global-load sectors drop 2.5x (18.3 M -> 7.3 M at stage 4) as
+// intended, but a 256-bit warp load is executed as 8 four-lane passes and lanes of different passes do not share a
+// wavefront, so the request count (x2.3) keeps the LSU data pipe just as busy (66 %): 31.8 / 57.4 us vs 29.3 / 55.3 us for
+// et_fuse_tiled_kernel at stages 3 / 4.  Kept as an opt-in experiment: MVSTER_ET_DLANE=1 selects it for the D = 4 stages.
 static bool try_launch_dlane(const EtArgs& a, int C, int G, int D, cudaStream_t st, int* rc) {
     if (D != 4 || (long long)a.B * a.Hs * a.Ws * C >= (1ll << 31) || a.B > 65535) return false;
     const char* e = getenv("MVSTER_ET_DLANE");
-    if (e && e[0] == '0') return false;
+    if (!e || e[0] != '1') return false;
     if (C == 8 && G == 4) { *rc = launch_et_dlane<8, 4, 1>(a, st); return true; }
     if (C == 16 && G == 4) { *rc = launch_et_dlane<16, 4, 2>(a, st); return true; }
     return false;

@@ -18,7 +18,7 @@ for r in data:
     a[0] += 1
     a[1] += v
     tot += v
-mine = sum(t for k, (n, t) in agg.items() if k.startswith("mvster::"))
+mine = sum(t for k, (n, t) in agg.items() if k.startswith(("mvster::", "tc::", "tc2::", "tc3::")))
 print(f"{len(data)} launches, {tot:.0f} us of GPU time in one step (serialised, cold-cache: compare shares); "
       f"libmvster_b200 kernels: {mine:.0f} us ({100 * mine / tot:.1f} %)\n")
 print("| us | share | launches | kernel |\n|---:|---:|---:|---|")
