@@ -293,7 +293,7 @@ def main():
     ms_total = timed(step_resident, args.steps)
     if args.profile_range:
         torch.cuda.profiler.stop()
-    launches = launches_per_step * args.steps if model.use_cuda_graph else _lib.launch_count() - l0
+    launches = launches_per_step * args.steps if (model.use_cuda_graph and P == 1) else _lib.launch_count() - l0
     ms_e2e = ms_total if args.skip_e2e else timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_step, ms_step_e2e = ms_total / args.steps, ms_e2e / args.steps
@@ -303,9 +303,9 @@ def main():
     # ---- warp (ET) kernel alone: live CUDA-event timing per stage, L2 flushed between launches
     peak, peak_src = measured_peaks()
     roof, breakdown = None, None
+    out = step_resident()  # every rank: under --view-parallel the forward holds a collective
     if rank == 0:
         with torch.no_grad():
-            out = step_resident()
             x = torch.cat(imgs_d, 0).contiguous(memory_format=torch.channels_last)
             pyr = model.feature(x)
             per_stage = []
@@ -334,7 +334,7 @@ def main():
         dom = per_stage[3]
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
         # (profiles/r01_et_fuse_tiled_v3_ncu.md: 55.0 MB + 3.18 MB; the 21 MB cost volume mostly stays in the 126 MB L2)
-        roof = {"kernel": "et_fuse_tiled_kernel<8,4,4,1> (stage 4 launch: C=8, G=4, D=4, 4 source views, 327680 pixels)", "bound": "hbm",
+        roof = {"kernel": "et_fuse_tiled_kernel<C=8,G=4,D=4,LPP=1> (stage 4 launch: C=8, G=4, D=4, 4 source views, 327680 pixels)", "bound": "hbm",
                 "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "peak_source": peak_src,
                 "algorithmic_bytes": dom["bytes"], "traffic": 58.18e6 if (B, NV, H, W) == (1, 5, 512, 640) else None, "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak,
                                                  "bytes": tot_b, "us": tot_t * 1e6},
@@ -363,7 +363,7 @@ def main():
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(config_dict(world, P), engine={
                 "fpn_backend": model.fpn_backend, "fpn_precision": model.fpn_precision, "reg_precision": model.reg_precision,
-                "tc_kernel_gen": model.tc_kernel_gen, "cuda_graph": bool(model.use_cuda_graph)}),
+                "tc_kernel_gen": model.tc_kernel_gen, "cuda_graph": bool(model.use_cuda_graph) and P == 1}),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 2 * B * H * W * 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,

@@ -132,6 +132,21 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
                           int B, int D, int H, int W, int Cin, int Cout, int kd, int relu, int npass,
                           mvster_stream_t stream);
 
+/* Generation 3 of the tensor-core layer (conv_tc3.cu): persistent kernel, error-compensated BF16 (three bf16 terms per
+ * fp32 operand, six products in three MMAs per 16 channels: fp32-faithful, dropped terms <= 2^-24 relative), staged halo
+ * tiles addressed through a per-layer stage/tap plan.  Replaces ConvBnReLU3D / ConvBnReLU (mvs4net_utils.py:116-123,
+ * :100-113 after BN folding) for:  stride 1, k in {1,3}, kd in {1,3};  stride (1,2,2), k in {3,5}, kd = 1 (pad = k/2).
+ * Cin in {4,8,16,32,64}, Cout in {8,16,32,64}.  x [B][D][H][W][Cin] -> y [B][D][Ho][Wo][Cout], Ho = (H-1)/stride + 1.
+ * w_packed: one 96*max(Cout,16)-byte slab per (stage, tap) in the order mvster_conv_tc3_plan reports (slabs[i] =
+ * {kz, ky, kx, first input channel}); slab = [2 K-halves][w1 | w2 | w3 rows of max(Cout,16)][8 bf16] over 16 input
+ * channels (zero padded) - packing.pack_tc3_weights.  x and w_packed 16-byte aligned. */
+int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw);
+int mvster_conv_tc3_plan(int Cin, int kd, int k, int stride_hw, int* slabs, int max_slabs);
+size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int stride_hw);
+int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
+                        int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
+                        mvster_stream_t stream);
+
 /* reg2d U-Net (mvs4net_utils.py:870-912) up to, not including, the 1x1x1 `prob`
  * layer: cost [B][D][H][W][G] -> feat8 [B][D][H][W][8].  `blob` holds the folded
  * weights of conv0..conv11 in the layout reported by mvster_reg2d_layer_info;
@@ -151,6 +166,14 @@ int mvster_reg2d_f32(const float* blob, const float* cost, float* feat8, float* 
 size_t mvster_reg2d_tc_blob_floats(void);
 int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* cost, float* feat8, float* workspace,
                         int B, int G, int D, int H, int W, int npass, int kernel_gen, mvster_stream_t stream);
+
+/* Same network with conv0..conv6 (every forward convolution, stride 1 and stride (1,2,2)) on the generation-3 tensor-core
+ * kernel (mvster_conv_tc3_f32, 3 x bf16, fp32-faithful); the three transposed layers stay on the CUDA cores.  tc3_blob =
+ * packing.pack_tc3_weights of conv0..conv6 back to back (mvster_reg2d_tc3_blob_bytes(G) bytes, 16-byte aligned); biases
+ * and the transposed layers' weights are read from `blob`. */
+size_t mvster_reg2d_tc3_blob_bytes(int G);
+int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* workspace,
+                         int B, int G, int D, int H, int W, mvster_stream_t stream);
 
 /* reg3d U-Net (mvs4net_utils.py:914-965; optional `--reg_mode reg3d`): 3x3x3 kernels, stride 2 along D too,
  * down_size in {1,2,3} (MVS4Net.py:48), prob = 3x3x3 conv 8->1 without bias.  cost [B][D][H][W][G] ->

@@ -198,6 +198,40 @@ def conv3d_tc2(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, k
     return y
 
 
+def conv_tc3_plan(cin: int, kd: int, k: int, stride: int) -> List[tuple]:
+    """(kz, ky, kx, first input channel) of every weight slab of a generation-3 layer, in the order the kernel streams them.
+    Pure host logic of the library (no GPU needed)."""
+    lib = _lib.load()
+    n = lib.mvster_conv_tc3_plan(cin, kd, k, stride, None, 0)
+    if n < 0:
+        raise ValueError(f"conv_tc3: unsupported layer Cin={cin} kd={kd} k={k} stride={stride}")
+    buf = (C.c_int * (4 * n))()
+    lib.mvster_conv_tc3_plan(cin, kd, k, stride, buf, n)
+    return [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
+
+
+def conv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, k: int, stride: int = 1, relu: bool = True,
+             skip: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """Generation-3 tcgen05 conv (persistent, 3 x bf16): x [B,D,H,W,Cin] -> [B,D,Ho,Wo,cout]; w_packed from
+    packing.pack_tc3_weights (a float32-typed byte blob)."""
+    _chk(x, "x")
+    _chk(w_packed, "w_packed")
+    B, D, H, W, Cin = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    y = torch.empty((B, D, Ho, Wo, cout), device=x.device, dtype=torch.float32) if out is None else _chk(out, "out", (B, D, Ho, Wo, cout))
+    if bias is not None:
+        _chk(bias, "bias", (cout,))
+    if skip is not None:
+        _chk(skip, "skip", tuple(y.shape))
+    lib = _lib.load()
+    want = lib.mvster_conv_tc3_packed_bytes(Cin, cout, kd, k, stride)
+    if want == 0 or w_packed.numel() * 4 != want:
+        raise ValueError(f"conv_tc3: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
+    _lib.check(lib.mvster_conv_tc3_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
+                                       kd, k, stride, int(relu), _stream()), "mvster_conv_tc3_f32")
+    return y
+
+
 def hypo_init_linear(depth_values: Tensor, D: int, H: int, W: int) -> Tensor:
     dv = _chk(depth_values, "depth_values")
     B, n = dv.shape
@@ -278,6 +312,11 @@ def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: O
     if blob.numel() != reg2d_blob_floats(G):
         raise ValueError(f"blob has {blob.numel()} floats, expected {reg2d_blob_floats(G)} for G={G}")
     out = torch.empty((B, D, H, W, 8), device=cost.device, dtype=torch.float32) if out is None else _chk(out, "feat8", (B, D, H, W, 8))
+    if tc_blob is not None and kernel_gen == 3:  # conv0..conv6 on the persistent 3 x bf16 kernel (packing.pack_reg2d 'tc3_blob')
+        _chk(tc_blob, "tc3_blob", (int(_lib.load().mvster_reg2d_tc3_blob_bytes(G)) // 4,))
+        _lib.check(_lib.load().mvster_reg2d_tc3_f32(_ptr(blob), _ptr(tc_blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W,
+                                                    _stream()), "mvster_reg2d_tc3_f32")
+        return out
     if tc_blob is not None:
         _chk(tc_blob, "tc_blob", (int(_lib.load().mvster_reg2d_tc_blob_floats()),))
         _lib.check(_lib.load().mvster_reg2d_tc_f32(_ptr(blob), _ptr(tc_blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W,

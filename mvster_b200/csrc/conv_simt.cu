@@ -297,6 +297,25 @@ extern "C" int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, cons
     return reg2d_run(blob, tc_blob, npass, kernel_gen, cost, feat8, ws, B, G, D, H, W, stream);
 }
 
+// byte offset of layer i's slab stream inside the generation-3 blob (layers 0..6, the non-transposed ones, back to back)
+static size_t tc3_layer_offset(const Layer (&L)[MVSTER_REG2D_LAYERS], int layer) {
+    size_t off = 0;
+    for (int i = 0; i < layer && i < 7; ++i) off += mvster_conv_tc3_packed_bytes(L[i].cin, L[i].cout, L[i].kd, 3, L[i].s);
+    return off;
+}
+
+extern "C" size_t mvster_reg2d_tc3_blob_bytes(int G) {
+    Layer L[MVSTER_REG2D_LAYERS];
+    reg2d_layers(G, L);
+    return tc3_layer_offset(L, 7);
+}
+
+extern "C" int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* ws,
+                                    int B, int G, int D, int H, int W, mvster_stream_t stream) {
+    MVSTER_REQUIRE(tc3_blob, "mvster_reg2d_tc3_f32: tc3_blob is null");
+    return reg2d_run(blob, (const float*)tc3_blob, 3, 3, cost, feat8, ws, B, G, D, H, W, stream);
+}
+
 static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen, const float* cost, float* feat8, float* ws,
                      int B, int G, int D, int H, int W, mvster_stream_t stream) {
     MVSTER_REQUIRE(blob && cost && feat8 && ws, "mvster_reg2d_f32: null pointer");
@@ -317,7 +336,11 @@ static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen
         int64_t info[8];
         mvster_reg2d_layer_info(G, i, info);
         int rc;
-        if (tc_blob && L[i].kd == 3) {
+        if (tc_blob && gen == 3 && !L[i].transposed) {
+            // every forward convolution (stride 1 and stride (1,2,2)) on the persistent 3 x bf16 tcgen05 kernel
+            rc = mvster_conv_tc3_f32(in[i], (const uint8_t*)tc_blob + tc3_layer_offset(L, i), blob + info[6], skip[i], out[i], B, D,
+                                     H / div[i], W / div[i], L[i].cin, L[i].cout, L[i].kd, 3, L[i].s, 1, stream);
+        } else if (tc_blob && gen != 3 && L[i].kd == 3) {
             // conv2 / conv4 / conv6 (3x3x3, 69 % of the FLOPs) on the tcgen05 tensor cores; their [hi|lo]
             // K-major slabs sit back to back in tc_blob (2*27*Cin*Cout floats each).
             const size_t off = i == 2 ? 0 : (i == 4 ? (size_t)2 * 27 * 16 * 16 : (size_t)2 * 27 * (16 * 16 + 32 * 32));

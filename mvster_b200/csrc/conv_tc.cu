@@ -31,6 +31,13 @@ namespace mvster {
 // ------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp; see tc_ptx.cuh for why single-thread tcgen05/TMA issue is guarded by this
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -160,7 +167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0, bi = 0;
             for (int tap = 0; tap < taps; ++tap) {
                 const int kz = tap / 9 - a.kd / 2, ky = (tap % 9) / 3 - 1, kx = tap % 3 - 1;
@@ -195,7 +202,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                     const int s = it % Cfg::SA;
                     mbar_wait(NPASS == 3 ? A_READY(s) : A_FULL(s), (it / Cfg::SA) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t a_hi = a_base + s * Cfg::A_STAGE, a_lo = a_hi + Cfg::A_BYTES;
                         const uint32_t d = tmem_base + (uint32_t)(t * NC);
                         const bool first = (tap == 0 && kc == 0);
@@ -215,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant_
                 }
             }
         }
-        if (lane == 0) umma_commit(ACC_FULL);
+        if (elect_one()) umma_commit(ACC_FULL);
         __syncwarp();
     } else {
         // ------------------------------------------------------------------ A splitter (3xTF32 only)

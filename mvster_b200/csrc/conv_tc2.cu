@@ -92,7 +92,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int sa_it = 0, sb_it = 0;
             for (int kz = 0; kz < a.kd; ++kz) {
                 const int zz = z + kz - pz;
@@ -135,7 +135,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     const int sb = sb_it % C::SB;
                     mbar_wait(B_FULL(sb), (sb_it / C::SB) & 1);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         // Descriptors differ only in their 16-byte-granular start-address field (low 14 bits, no carry
                         // out: shared memory < 256 KB), so every operand is the stage descriptor plus a small constant:
                         // the single issuing thread spends ~2 integer adds per MMA instead of rebuilding descriptors.
@@ -159,12 +159,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     }
                     __syncwarp();
                 }
-                if (lane == 0) umma_commit(A_EMPTY(s));
+                if (elect_one()) umma_commit(A_EMPTY(s));
                 __syncwarp();
                 fresh = false;
             }
         }
-        if (lane == 0) umma_commit(ACC_FULL);
+        if (elect_one()) umma_commit(ACC_FULL);
         __syncwarp();
     } else {
         const int tid = threadIdx.x - 64;  // 0..127

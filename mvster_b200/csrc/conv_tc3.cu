@@ -1,0 +1,436 @@
+// Implicit-GEMM convolution on tcgen05, generation 3: persistent, fully pipelined, error-compensated BF16.
+//
+// What changed against conv_tc2.cu, and the measurement behind each change (tools/mma_microbench.cu on B200: one
+// M128 x K8 kind::tf32 MMA costs 39 / 40 / 48 / 64 / 128 cycles at N = 16 / 32 / 64 / 128 / 256 - below N = 64 the
+// instruction is bound by the 4 KB A-operand fetch from shared memory, not by the multipliers, whatever the layout):
+//   * Arithmetic: the fp32 operands are split into three bf16 terms (a = a1 + a2 + a3 exactly to 24 bits, same for w) and
+//     the six significant products a1w1, a1w2, a1w3, a2w1, a2w2, a3w1 (dropped terms <= 2^-24 relative) are computed by
+//     THREE kind::f16 MMAs per 16 channels: a1 x [w1|w2|w3] (N = 3*NC), a2 x [w1|w2] (N = 2*NC), a3 x [w1] (N = NC) - the
+//     weight splits sit side by side along N, which is free while the MMA is A-fetch bound.  3xTF32 needed six MMAs (K = 8)
+//     for the same 16 channels.  The three column blocks of the accumulator are summed in the epilogue.
+//   * Persistent CTAs (one per SM) walk groups of T tiles; two accumulator sets in TMEM (2 x 192 columns) let the epilogue
+//     of group g overlap the MMAs of group g+1; TMA staging, operand conversion, MMA issue and epilogue are separate warps
+//     connected by mbarrier rings, so no stage waits for a prologue.
+//   * A small per-layer plan (stages x taps) generalises the addressing: a stage is one TMA-staged halo tile (18 x 10 pixels
+//     x <= 16 channels of one input plane, optionally of one stride-2 parity class via the tensor map's element strides), a
+//     tap is a 16-byte-granular shift of the A descriptor inside it.  Stride-1 3x3(x3) and 1x1, and stride-2 3x3 / 5x5
+//     convolutions (4 parity classes, no wasted taps) run on the same kernel.
+//   * tcgen05 / TMA issue is guarded by elect.sync (see tc_ptx.cuh: a lane test makes the compiler serialise every issue).
+//
+// warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = fp32 -> 3 x bf16 converters, warps 10-13 = epilogue.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace mvster {
+namespace tc3 {
+using namespace ptx;
+
+constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2, HPIX = HW_ * HH_;
+constexpr int QBYTES = HPIX * 16;            // bytes per channel quad of a halo tile (2880)
+constexpr int F_BYTES = 4 * QBYTES;          // fp32 staging of one tile-stage: [180 pixels][<= 16 channels], ONE TMA box
+constexpr int PLANE = QBYTES;                // bf16 operand plane = [180 pixels][8 channels]; 2880 = 64 (mod 128): the two
+                                             // octet planes a converter half-warp writes fall into disjoint banks
+constexpr int A_SPLIT = 2 * PLANE;           // one bf16 term of one tile-stage: 2 channel octets
+constexpr int A_BYTES = 3 * A_SPLIT;         // a1 | a2 | a3
+constexpr int NCONV = 256;                 // converter threads (8 warps: one warp per SM sub-partition was latency-bound)
+constexpr int THREADS = 64 + NCONV + 128;
+constexpr int MAX_STAGES = 16, MAX_TAPS = 9;
+constexpr int NF = 4, NB = 10;
+
+struct Stage {
+    short c0, nq, ox, oy, dz, ntap, slab0, pad;
+};
+struct Plan {
+    Stage st[MAX_STAGES];
+    unsigned char a_off[MAX_STAGES][MAX_TAPS + 3];  // (halo row * 10 + halo column) of each tap = descriptor shift in 16-byte units
+};
+struct Args {
+    const uint8_t* w;
+    const float* bias; const float* skip; float* y;
+    int D, Ho, Wo, cout, relu, sx, nstage, T, tiles_x, tiles_per_plane, groups_per_plane, total_groups, zero_a;
+};
+
+template <int NC>
+struct Cfg {
+    static constexpr int TMAX = 64 / NC;                    // tiles accumulated side by side: 3*NC*TMAX = 192 TMEM columns per set
+    static constexpr int NA = NC == 64 ? 6 : 8;             // bf16 operand ring (tile-stages)
+    static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 bf16]
+    static constexpr int SMEM = 1024 + NF * F_BYTES + NA * A_BYTES + NB * B_BYTES + 512;
+};
+
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// two fp32 -> three packed bf16 pairs with v == t1 + t2 + t3 to 24 bits (the subtractions are exact in fp32)
+__device__ __forceinline__ void split3(float x, float y, uint32_t& t1, uint32_t& t2, uint32_t& t3) {
+    t1 = bf16x2_rn(x, y);
+    float rx = x - __uint_as_float(t1 << 16), ry = y - __uint_as_float(t1 & 0xFFFF0000u);
+    t2 = bf16x2_rn(rx, ry);
+    rx -= __uint_as_float(t2 << 16);
+    ry -= __uint_as_float(t2 & 0xFFFF0000u);
+    t3 = bf16x2_rn(rx, ry);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ Plan plan, const Args a) {
+    using C = Cfg<NC>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t f_base = base, a_base = f_base + NF * F_BYTES, b_base = a_base + C::NA * A_BYTES, bar_base = b_base + NB * C::B_BYTES;
+    auto F_FULL = [&](uint32_t s) { return bar_base + 8u * s; };
+    auto F_EMPTY = [&](uint32_t s) { return bar_base + 8u * (NF + s); };
+    auto A_FULL = [&](uint32_t s) { return bar_base + 8u * (2 * NF + s); };
+    auto A_EMPTY = [&](uint32_t s) { return bar_base + 8u * (2 * NF + C::NA + s); };
+    auto B_FULL = [&](uint32_t s) { return bar_base + 8u * (2 * NF + 2 * C::NA + s); };
+    auto B_EMPTY = [&](uint32_t s) { return bar_base + 8u * (2 * NF + 2 * C::NA + NB + s); };
+    auto ACC_FULL = [&](uint32_t s) { return bar_base + 8u * (2 * NF + 2 * C::NA + 2 * NB + s); };
+    auto ACC_EMPTY = [&](uint32_t s) { return bar_base + 8u * (2 * NF + 2 * C::NA + 2 * NB + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * NF + 2 * C::NA + 2 * NB + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NF; ++s) { mbar_init(F_FULL(s), 1); mbar_init(F_EMPTY(s), NCONV); }
+        for (int s = 0; s < C::NA; ++s) { mbar_init(A_FULL(s), NCONV); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(ACC_FULL(s), 1); mbar_init(ACC_EMPTY(s), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (a.zero_a) {  // Cin < 16: the converters never write the upper channel planes, the MMAs read them as zeros
+        uint4* p = reinterpret_cast<uint4*>(smem_raw + (a_base - raw));
+        for (int i = threadIdx.x; i < C::NA * A_BYTES / 16; i += THREADS) p[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    // every role walks the same sequence: groups g (T tiles of one output plane) x stages x tiles / taps
+#define MVSTER_TC3_GROUP_HEAD                                                                         \
+    const int plane = g / a.groups_per_plane, tile0 = (g % a.groups_per_plane) * a.T, z = plane % a.D; \
+    const int Tg = min(a.T, a.tiles_per_plane - tile0);
+#define MVSTER_TC3_STAGE_SKIP(s) ((unsigned)(z + plan.st[s].dz) >= (unsigned)a.D)
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            uint32_t fu = 0, bu = 0;
+            for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
+                MVSTER_TC3_GROUP_HEAD
+                for (int s = 0; s < a.nstage; ++s) {
+                    if (MVSTER_TC3_STAGE_SKIP(s)) continue;  // depth padding: the plane contributes nothing
+                    const Stage st = plan.st[s];
+                    for (int t = 0; t < Tg; ++t, ++fu) {
+                        const uint32_t fs = fu % NF;
+                        mbar_wait(F_EMPTY(fs), ((fu / NF) & 1) ^ 1);
+                        mbar_expect_tx(F_FULL(fs), st.nq * QBYTES);
+                        const int ti = tile0 + t, y0 = (ti / a.tiles_x) * TH, x0 = (ti % a.tiles_x) * TW;
+                        // one box = [18][10] pixels x min(Cin,16) channels (64-byte rows: a 16-byte-row box per channel quad
+                        // costs the TMA engine 4x the requests); the converters re-lay it out for the MMA anyway
+                        tma_load_4d(f_base + fs * F_BYTES, &x_map, F_FULL(fs), st.c0, a.sx * x0 + st.ox, a.sx * y0 + st.oy, plane + st.dz);
+                    }
+                    for (int tap = 0; tap < st.ntap; ++tap, ++bu) {
+                        const uint32_t sb = bu % NB;
+                        mbar_wait(B_EMPTY(sb), ((bu / NB) & 1) ^ 1);
+                        mbar_expect_tx(B_FULL(sb), C::B_BYTES);
+                        bulk_load(b_base + sb * C::B_BYTES, a.w + (size_t)(st.slab0 + tap) * C::B_BYTES, C::B_BYTES, B_FULL(sb));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t ID3 = idesc_bf16_m128(3 * NC), ID2 = idesc_bf16_m128(2 * NC), ID1 = idesc_bf16_m128(NC);
+        uint32_t u = 0, bu = 0, gc = 0;
+        for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x, ++gc) {
+            MVSTER_TC3_GROUP_HEAD
+            const uint32_t set = gc & 1;
+            mbar_wait(ACC_EMPTY(set), ((gc >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
+            tc_fence_after();
+            bool fresh = true;
+            for (int s = 0; s < a.nstage; ++s) {
+                if (MVSTER_TC3_STAGE_SKIP(s)) continue;
+                const int ntap = plan.st[s].ntap;
+                for (int t = 0; t < Tg; ++t) mbar_wait(A_FULL((u + t) % C::NA), ((u + t) / C::NA) & 1);
+                for (int tap = 0; tap < ntap; ++tap, ++bu) {
+                    const uint32_t sb = bu % NB;
+                    mbar_wait(B_FULL(sb), (bu / NB) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t b0 = smem_desc(b_base + sb * C::B_BYTES, 3 * NC * 16, 128, 0);
+                        const uint64_t shift = plan.a_off[s][tap];
+                        const uint32_t first = (fresh && tap == 0) ? 0u : 1u;
+                        for (int t = 0; t < Tg; ++t) {
+                            const uint64_t a1 = smem_desc(a_base + ((u + t) % C::NA) * A_BYTES, PLANE, HW_ * 16, 0) + shift;
+                            const uint32_t d = tmem_base + set * 256u + (uint32_t)(t * 3 * NC);
+                            umma_bf16(d, a1, b0, ID3, first);                           // a1 x [w1|w2|w3]
+                            umma_bf16(d, a1 + (A_SPLIT >> 4), b0, ID2, 1u);             // a2 x [w1|w2]
+                            umma_bf16(d, a1 + (2 * A_SPLIT >> 4), b0, ID1, 1u);         // a3 x [w1]
+                        }
+                        umma_commit(B_EMPTY(sb));
+                    }
+                    __syncwarp();
+                }
+                if (elect_one())
+                    for (int t = 0; t < Tg; ++t) umma_commit(A_EMPTY((u + t) % C::NA));
+                __syncwarp();
+                u += Tg;
+                fresh = false;
+            }
+            if (elect_one()) umma_commit(ACC_FULL(set));
+            __syncwarp();
+        }
+    } else if (warp < 2 + NCONV / 32) {
+        // ------------------------------------------------------------------ converters: fp32 halo tile -> a1 | a2 | a3 (bf16)
+        const int tid = threadIdx.x - 64;
+        uint32_t u = 0;
+        for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
+            MVSTER_TC3_GROUP_HEAD
+            for (int s = 0; s < a.nstage; ++s) {
+                if (MVSTER_TC3_STAGE_SKIP(s)) continue;
+                const int nq = plan.st[s].nq, items = HPIX * nq, qsh = nq >> 1;  // nq in {1,2,4}: pixel = item >> qsh
+                for (int t = 0; t < Tg; ++t, ++u) {
+                    const uint32_t fs = u % NF, as = u % C::NA;
+                    mbar_wait(F_FULL(fs), (u / NF) & 1);
+                    mbar_wait(A_EMPTY(as), ((u / C::NA) & 1) ^ 1);
+                    const uint8_t* F = smem_raw + (f_base + fs * F_BYTES - raw);
+                    uint8_t* A = smem_raw + (a_base + as * A_BYTES - raw);
+                    // item = one channel quad of one halo pixel = 16 contiguous bytes of F; <= 3 items per thread, all loads first
+                    constexpr int IT = (HPIX * 4 + NCONV - 1) / NCONV;
+                    float4 v[IT];
+#pragma unroll
+                    for (int k = 0; k < IT; ++k) {
+                        const int i = tid + k * NCONV;
+                        if (i < items) v[k] = *reinterpret_cast<const float4*>(F + i * 16);
+                    }
+#pragma unroll
+                    for (int k = 0; k < IT; ++k) {
+                        const int i = tid + k * NCONV;
+                        if (i < items) {
+                            const int p = i >> qsh, q = i & (nq - 1);
+                            uint2 t1, t2, t3;
+                            split3(v[k].x, v[k].y, t1.x, t2.x, t3.x);
+                            split3(v[k].z, v[k].w, t1.y, t2.y, t3.y);
+                            uint8_t* dst = A + (q >> 1) * PLANE + p * 16 + (q & 1) * 8;
+                            *reinterpret_cast<uint2*>(dst) = t1;
+                            *reinterpret_cast<uint2*>(dst + A_SPLIT) = t2;
+                            *reinterpret_cast<uint2*>(dst + 2 * A_SPLIT) = t3;
+                        }
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(A_FULL(as));
+                    mbar_arrive(F_EMPTY(fs));
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int q = warp & 3, r = q * 32 + lane;  // TMEM lane quarter, accumulator row = pixel in the tile
+        uint32_t gc = 0;
+        for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x, ++gc) {
+            MVSTER_TC3_GROUP_HEAD
+            (void)z;
+            const uint32_t set = gc & 1;
+            mbar_wait(ACC_FULL(set), (gc >> 1) & 1);
+            tc_fence_after();
+            for (int t = 0; t < Tg; ++t) {
+                const int ti = tile0 + t, yy = (ti / a.tiles_x) * TH + r / TW, xx = (ti % a.tiles_x) * TW + r % TW;
+                const bool ok = yy < a.Ho && xx < a.Wo;
+                const long long off = (((long long)plane * a.Ho + yy) * a.Wo + xx) * a.cout;
+                const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)(t * 3 * NC);
+#pragma unroll
+                for (int c0 = 0; c0 < NC; c0 += 16) {
+                    uint32_t v1[16], v2[16], v3[16];
+                    tmem_ld16(col + c0, v1);
+                    tmem_ld16(col + NC + c0, v2);
+                    tmem_ld16(col + 2 * NC + c0, v3);
+                    tmem_ld_wait();
+                    if (ok && c0 < a.cout) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            if (c0 + j >= a.cout) break;
+                            float o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                o[e] = (__uint_as_float(v3[j + e]) + __uint_as_float(v2[j + e])) + __uint_as_float(v1[j + e]);
+                                if (a.bias) o[e] += __ldg(a.bias + c0 + j + e);
+                                if (a.relu) o[e] = fmaxf(o[e], 0.f);
+                            }
+                            if (a.skip) {
+                                const float4 sk = __ldg(reinterpret_cast<const float4*>(a.skip + off + c0 + j));
+                                o[0] += sk.x; o[1] += sk.y; o[2] += sk.z; o[3] += sk.w;
+                            }
+                            *reinterpret_cast<float4*>(a.y + off + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(ACC_EMPTY(set));
+        }
+    }
+#undef MVSTER_TC3_GROUP_HEAD
+#undef MVSTER_TC3_STAGE_SKIP
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static bool supported(int Cin, int Cout, int kd, int k, int s) {
+    const bool cin_ok = Cin == 4 || Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64;
+    const bool cout_ok = Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64;
+    const bool shape_ok = (s == 1 && (k == 1 || k == 3) && (kd == 1 || kd == 3)) || (s == 2 && (k == 3 || k == 5) && kd == 1);
+    return cin_ok && cout_ok && shape_ok && kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16) <= MAX_STAGES;
+}
+
+// Stage/tap enumeration shared by the launcher and by the host-side weight packer (mvster_conv_tc3_plan).
+// Stride 2: input row 2y + ky - pad = 2 (y + m) + py with parity class py in {0,1}; class (py, px) is staged as its own halo
+// tile (TMA element strides 2, origin 2*y0 - 2 + py) and tap ky lands on halo row m + 1.
+static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[4]) {
+    int ns = 0, nslab = 0;
+    const int kch = (Cin + 15) / 16, pz = kd / 2, pad = k / 2, npar = s == 2 ? 2 : 1;
+    for (int kz = 0; kz < kd; ++kz)
+        for (int py = 0; py < npar; ++py)
+            for (int px = 0; px < npar; ++px)
+                for (int kc = 0; kc < kch; ++kc, ++ns) {
+                    Stage S;
+                    S.c0 = (short)(kc * 16);
+                    S.nq = (short)((Cin - kc * 16) / 4 < 4 ? (Cin - kc * 16) / 4 : 4);
+                    S.dz = (short)(kz - pz);
+                    S.ox = (short)(s == 2 ? -2 + px : -1);
+                    S.oy = (short)(s == 2 ? -2 + py : -1);
+                    S.slab0 = (short)nslab;
+                    S.pad = 0;
+                    int nt = 0;
+                    for (int ky = 0; ky < k; ++ky)
+                        for (int kx = 0; kx < k; ++kx) {
+                            int hy, hx;
+                            if (s == 1) {
+                                hy = ky - pad + 1; hx = kx - pad + 1;
+                            } else {
+                                const int oy = ky - pad, ox = kx - pad, cy = ((oy % 2) + 2) % 2, cx = ((ox % 2) + 2) % 2;
+                                if (cy != py || cx != px) continue;
+                                hy = (oy - cy) / 2 + 1; hx = (ox - cx) / 2 + 1;
+                            }
+                            if (plan) plan->a_off[ns][nt] = (unsigned char)(hy * HW_ + hx);
+                            if (slabs) { slabs[nslab][0] = kz; slabs[nslab][1] = ky; slabs[nslab][2] = kx; slabs[nslab][3] = kc * 16; }
+                            ++nt; ++nslab;
+                        }
+                    S.ntap = (short)nt;
+                    if (plan) plan->st[ns] = S;
+                }
+    return nslab;
+}
+
+template <int NC>
+static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st) {
+    using C = Cfg<NC>;
+    int T = C::TMAX;
+    while (T > 1 && total_tiles < (long long)T * 2 * sms) T >>= 1;  // keep every SM busy before widening the groups
+    if (T > a.tiles_per_plane) T = a.tiles_per_plane;
+    a.T = T;
+    a.groups_per_plane = ceil_div(a.tiles_per_plane, T);
+    a.total_groups = (int)(total_tiles / a.tiles_per_plane) * a.groups_per_plane;
+    auto k = conv_tc3_kernel<NC>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
+        set_error("conv_tc3_kernel: cannot reserve %d bytes of shared memory", C::SMEM);
+        cudaGetLastError();
+        return MVSTER_ERR_CUDA;
+    }
+    const int grid = a.total_groups < sms ? a.total_groups : sms;
+    k<<<grid, THREADS, C::SMEM, st>>>(xm, plan, a);
+    return check_launch("conv_tc3_kernel");
+}
+
+}  // namespace tc3
+}  // namespace mvster
+
+using namespace mvster;
+
+extern "C" int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw) {
+    return tc3::supported(Cin, Cout, kd, k, stride_hw);
+}
+
+extern "C" int mvster_conv_tc3_plan(int Cin, int kd, int k, int stride_hw, int* slabs, int max_slabs) {
+    if (!tc3::supported(Cin, 16, kd, k, stride_hw)) return -1;
+    const int n = tc3::build_plan(Cin, kd, k, stride_hw, nullptr, nullptr);
+    if (slabs) {
+        if (n > max_slabs) return -1;
+        tc3::build_plan(Cin, kd, k, stride_hw, nullptr, reinterpret_cast<int(*)[4]>(slabs));
+    }
+    return n;
+}
+
+extern "C" size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int stride_hw) {
+    if (!tc3::supported(Cin, Cout, kd, k, stride_hw)) return 0;
+    const int NC = Cout < 16 ? 16 : Cout;
+    return (size_t)tc3::build_plan(Cin, kd, k, stride_hw, nullptr, nullptr) * 96 * NC;
+}
+
+extern "C" int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
+                                   int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
+                                   mvster_stream_t stream) {
+    using namespace mvster::tc3;
+    MVSTER_REQUIRE(x && w_packed && y, "mvster_conv_tc3_f32: null pointer");
+    MVSTER_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "mvster_conv_tc3_f32: bad shape");
+    MVSTER_REQUIRE(supported(Cin, Cout, kd, k, stride_hw), "mvster_conv_tc3_f32: unsupported layer Cin=%d Cout=%d kd=%d k=%d stride=%d",
+                   Cin, Cout, kd, k, stride_hw);
+    MVSTER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)x & 15) == 0, "mvster_conv_tc3_f32: x and w_packed must be 16-byte aligned");
+    EncodeTiledFn enc = encode_fn();
+    MVSTER_REQUIRE(enc, "mvster_conv_tc3_f32: cuTensorMapEncodeTiled is unavailable in this driver");
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int s = stride_hw;
+    CUtensorMap xm;
+    {   // activations [B*D][H][W][C]; a box is <= 16 channels of an 18 x 10 pixel halo patch, every s-th pixel
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * D};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
+        cuuint32_t box[4] = {(cuuint32_t)(Cin < 16 ? Cin : 16), (cuuint32_t)(HW_ * s), (cuuint32_t)(HH_ * s), 1}, es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVSTER_REQUIRE(r == CUDA_SUCCESS, "mvster_conv_tc3_f32: activation tensor map rejected (CUresult %d)", (int)r);
+    }
+    Plan plan;
+    memset(&plan, 0, sizeof(plan));
+    build_plan(Cin, kd, k, s, &plan, nullptr);
+    Args a;
+    a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
+    a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = relu; a.sx = s;
+    a.nstage = kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16);
+    a.tiles_x = ceil_div(a.Wo, TW);
+    a.tiles_per_plane = a.tiles_x * ceil_div(a.Ho, TH);
+    a.zero_a = Cin < 16;
+    const long long total_tiles = (long long)a.tiles_per_plane * B * D;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NC = Cout < 16 ? 16 : Cout;
+    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st);
+    return launch<64>(xm, plan, a, total_tiles, sms, st);
+}

@@ -83,8 +83,9 @@ class InferenceEngine:
             if getattr(net, "fpn_backend", "torch") == "native":
                 # FPN4 inside libmvster_b200 (fpn_engine.py): NCHW images in, NHWC features out
                 x = torch.cat([imgs[v] for v in own], 0).to(dtype=torch.float32).contiguous()
-                npass = {"fp32": 0, "3xtf32": 3, "tf32": 1}[getattr(net, "fpn_precision", "fp32")]
-                pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass)
+                prec = getattr(net, "fpn_precision", "fp32")
+                npass = {"fp32": 0, "3xtf32": 3, "tf32": 1, "3xbf16": 3}[prec]
+                pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=3 if prec == "3xbf16" else 2)
                 nhwc = [pyramid[f"stage{k + 1}"] for k in range(net.num_stage)]
             else:
                 x = torch.cat([imgs[v] for v in own], 0).contiguous(memory_format=torch.channels_last)
@@ -152,6 +153,8 @@ class InferenceEngine:
         prec = getattr(net, "reg_precision", "fp32")
         if prec == "fp32":      # exact fp32 FMA on the CUDA cores for every layer
             feat8 = capi.reg2d(wts["blob"], cost)
+        elif prec == "3xbf16":  # conv0..conv6 on the persistent tcgen05 kernel, three bf16 terms per operand (fp32-faithful)
+            feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc3_blob"], kernel_gen=3)
         else:                   # 3x3x3 layers on tcgen05: "3xtf32" (fp32-faithful) or "tf32"
             gen = int(getattr(net, "tc_kernel_gen", 1))
             feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc2_blob" if gen == 2 else "tc_blob"],

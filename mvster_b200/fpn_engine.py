@@ -42,6 +42,8 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
         out[name + ".w"], out[name + ".b"] = w, b
         if w.shape[0] == 9 and w.shape[1] >= 16:
             out[name + ".tc"] = packing.pack_tc2_weights(w, 3)
+        if w.shape[1] >= 8:  # generation-3 kernel: every layer after the 3-channel stem, stride-2 5x5 layers included
+            out[name + ".tc3"] = packing.pack_tc3_weights(w, 1, 5 if w.shape[0] == 25 else 3, 2 if name.endswith(".0") else 1)
     for i in (1, 2, 3):
         w = sd[f"{p}.inner{i}.weight"].detach().cpu()
         out[f"inner{i}.w"] = w.reshape(w.shape[0], w.shape[1]).t().float().contiguous()  # [Clat][64]
@@ -51,6 +53,8 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
         out[f"out{i}.w"] = w
         if w.shape[0] == 9:
             out[f"out{i}.tc"] = packing.pack_tc2_weights(w, 3)
+        if w.shape[2] >= 8 and i < 4:
+            out[f"out{i}.tc3"] = packing.pack_tc3_weights(w, 1, 3 if w.shape[0] == 9 else 1, 1)
     # fused last level (fpn.cu: fpn_out4_gather_kernel): out4(up2(top2) + inner3(c0)) with the 3x3 conv's channel
     # mixing moved in front of the up-sampling - composite weights, all built in fp64
     w4 = out["out4.w"].double()                       # [9][64][8]  (tap, top channel m, out channel o)
@@ -72,8 +76,18 @@ def _conv2d(x: Tensor, w: Tensor, b: Optional[Tensor], k: int, stride: int, relu
     return y
 
 
-def _conv3x3(x: Tensor, wts: Dict[str, Tensor], name: str, relu: bool, npass: int) -> Tensor:
-    """3x3 stride-1 layer: tensor cores (npass 3 = 3xTF32, 1 = TF32) or CUDA cores (npass 0)."""
+def _conv_tc3(x: Tensor, wts: Dict[str, Tensor], name: str, k: int, stride: int, relu: bool) -> Tensor:
+    """any FPN conv after the stem on the persistent 3 x bf16 tcgen05 kernel (conv_tc3.cu)."""
+    N, H, W, Cin = x.shape
+    cout = wts[name + ".w"].shape[2]
+    y = capi.conv_tc3(x.view(N, 1, H, W, Cin), wts[name + ".tc3"], wts.get(name + ".b"), cout, 1, k, stride, relu)
+    return y.view(N, y.shape[2], y.shape[3], cout)
+
+
+def _conv3x3(x: Tensor, wts: Dict[str, Tensor], name: str, relu: bool, npass: int, gen: int = 2) -> Tensor:
+    """3x3 stride-1 layer: tensor cores (gen 3: 3 x bf16; gen 2: npass 3 = 3xTF32, 1 = TF32) or CUDA cores (npass 0)."""
+    if npass and gen == 3 and (name + ".tc3") in wts:
+        return _conv_tc3(x, wts, name, 3, 1, relu)
     w, b = wts[name + ".w"], wts.get(name + ".b")
     if npass and (name + ".tc") in wts:
         N, H, W, Cin = x.shape
@@ -92,10 +106,12 @@ def _merge(top: Tensor, lat: Tensor, w: Tensor, b: Tensor) -> Tensor:
     return out
 
 
-def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bool = True) -> Dict[str, Tensor]:
+def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bool = True, gen: int = 2) -> Dict[str, Tensor]:
     """imgs [N,3,H,W] contiguous NCHW fp32 on the GPU -> {'stage1'..'stage4': [N,h,w,C] NHWC}.
     npass: 0 = every layer on the CUDA cores (exact fp32), 3 / 1 = 3x3 stride-1 layers with Cin >= 16 on tcgen05
-    (3xTF32 / TF32).  fused_last: algebraically fused last level (never forms the 64-channel full-res map)."""
+    (3xTF32 / TF32); gen = 3 (with npass = 3): every conv after the 3-channel stem, the stride-2 5x5 layers and the 1x1 out1
+    included, on the persistent 3 x bf16 kernel.  fused_last: algebraically fused last level (never forms the 64-channel
+    full-res map)."""
     capi._chk(imgs, "imgs")
     N, three, H, W = imgs.shape
     if three != 3 or H % 8 or W % 8:
@@ -103,25 +119,26 @@ def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bo
     c0 = torch.empty((N, H, W, 8), device=imgs.device, dtype=torch.float32)
     _lib.check(_lib.load().mvster_conv_first_f32(capi._ptr(imgs), capi._ptr(wts["conv0.0.w"]), capi._ptr(wts["conv0.0.b"]), capi._ptr(c0),
                                                  N, H, W, capi._stream()), "mvster_conv_first_f32")
-    c0 = _conv2d(c0, wts["conv0.1.w"], wts["conv0.1.b"], 3, 1, True)
+    g3 = bool(npass) and gen == 3
+    c0 = _conv_tc3(c0, wts, "conv0.1", 3, 1, True) if g3 else _conv2d(c0, wts["conv0.1.w"], wts["conv0.1.b"], 3, 1, True)
     levels = [c0]
     x = c0
     for L in (1, 2, 3):
-        x = _conv2d(x, wts[f"conv{L}.0.w"], wts[f"conv{L}.0.b"], 5, 2, True)
-        x = _conv3x3(x, wts, f"conv{L}.1", True, npass)
-        x = _conv3x3(x, wts, f"conv{L}.2", True, npass)
+        x = _conv_tc3(x, wts, f"conv{L}.0", 5, 2, True) if g3 else _conv2d(x, wts[f"conv{L}.0.w"], wts[f"conv{L}.0.b"], 5, 2, True)
+        x = _conv3x3(x, wts, f"conv{L}.1", True, npass, gen)
+        x = _conv3x3(x, wts, f"conv{L}.2", True, npass, gen)
         levels.append(x)
     c0, c1, c2, c3 = levels
-    out = {"stage1": _conv2d(c3, wts["out1.w"], None, 1, 1, False)}
+    out = {"stage1": _conv_tc3(c3, wts, "out1", 1, 1, False) if g3 else _conv2d(c3, wts["out1.w"], None, 1, 1, False)}
     top = _merge(c3, c2, wts["inner1.w"], wts["inner1.b"])
-    out["stage2"] = _conv3x3(top, wts, "out2", False, npass)
+    out["stage2"] = _conv3x3(top, wts, "out2", False, npass, gen)
     top = _merge(top, c1, wts["inner2.w"], wts["inner2.b"])
-    out["stage3"] = _conv3x3(top, wts, "out3", False, npass)
+    out["stage3"] = _conv3x3(top, wts, "out3", False, npass, gen)
     if fused_last:
         out["stage4"] = _fused_last_level(wts, top, c0, npass)
     else:  # literal form: materialise the 64-channel full-resolution map, then the 3x3 conv
         top = _merge(top, c0, wts["inner3.w"], wts["inner3.b"])
-        out["stage4"] = _conv3x3(top, wts, "out4", False, npass)
+        out["stage4"] = _conv3x3(top, wts, "out4", False, npass, gen)
     return out
 
 

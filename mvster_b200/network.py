@@ -246,16 +246,18 @@ class MVS4net(nn.Module):
         # replicas share this dict by reference, each thread touching only its own device's entry).
         self._engines = {}
         self._weights_version = 0
-        # arithmetic of the 3x3x3 regulariser layers on the CUDA inference path: "fp32" (CUDA cores, exact),
-        # "3xtf32" (tcgen05, error-compensated, fp32-faithful) or "tf32" (tcgen05, single pass)
-        # Default "3xtf32": validated on B200 (tests/test_gpu_tc_conv.py, test_gpu_z_tc_cascade.py) - per layer <= 1.6e-5 of
-        # max, depth identical to the fp32 oracle on every tie-free pixel.
-        self.reg_precision = os.environ.get("MVSTER_REG_PRECISION", "3xtf32")
-        self.tc_kernel_gen = int(os.environ.get("MVSTER_TC_GEN", "2"))  # 1 = per-tap TMA kernel, 2 = staged-tile kernel
-        # feature pyramid at inference: "native" (libmvster_b200 kernels, fpn_engine.py; fpn_precision "fp32" | "3xtf32" |
-        # "tf32" for its 3x3 layers) or "torch" (the module's own convs through cuDNN, channels-last)
+        # arithmetic of the regulariser convolutions on the CUDA inference path:
+        #   "fp32"   every layer on the CUDA cores (exact fp32 FMA)
+        #   "3xbf16" conv0..conv6 on the persistent tcgen05 kernel (conv_tc3.cu): three bf16 terms per operand, fp32-faithful
+        #            (per layer <= 5e-6 of max against an fp64 convolution, tests/test_gpu_tc_conv.py) - the default
+        #   "3xtf32" the 3x3x3 layers on the generation-1/2 kernels, error-compensated TF32 (<= 1.6e-5 of max)
+        #   "tf32"   ... single TF32 pass (reduced precision, opt-in)
+        self.reg_precision = os.environ.get("MVSTER_REG_PRECISION", "3xbf16")
+        self.tc_kernel_gen = int(os.environ.get("MVSTER_TC_GEN", "2"))  # TF32 modes: 1 = per-tap TMA kernel, 2 = staged-tile kernel
+        # feature pyramid at inference: "native" (libmvster_b200 kernels, fpn_engine.py; fpn_precision as above, "3xbf16" puts
+        # every layer after the 3-channel stem on the tensor cores) or "torch" (the module's own convs through cuDNN, channels-last)
         self.fpn_backend = os.environ.get("MVSTER_FPN", "native")
-        self.fpn_precision = os.environ.get("MVSTER_FPN_PRECISION", "3xtf32")
+        self.fpn_precision = os.environ.get("MVSTER_FPN_PRECISION", "3xbf16")
         # replay the whole inference forward as one CUDA graph (outputs are then static buffers, valid until the next call)
         self.use_cuda_graph = os.environ.get("MVSTER_CUDA_GRAPH", "0") == "1"
         self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)

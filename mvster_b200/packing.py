@@ -70,6 +70,37 @@ def pack_tc2_weights(w: Tensor, npass: int = 3) -> Tensor:
     return torch.cat([hi.reshape(-1), lo.reshape(-1)])
 
 
+def bf16_split3(w: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """fp32 -> three bf16 terms with w == t1 + t2 + t3 to 24 bits (round-to-nearest at every step, exact residuals)."""
+    t1 = w.to(torch.bfloat16)
+    r = w - t1.float()
+    t2 = r.to(torch.bfloat16)
+    t3 = (r - t2.float()).to(torch.bfloat16)
+    return t1, t2, t3
+
+
+def pack_tc3_weights(w: Tensor, kd: int, k: int, stride: int = 1) -> Tensor:
+    """[kd*k*k][Cin][Cout] fp32 -> the slab stream of the generation-3 tcgen05 kernel (conv_tc3.cu): one slab per
+    (stage, tap) in the order of ``capi.conv_tc3_plan``; slab = [2 K-halves][w1 | w2 | w3, N rows each][8 bf16] over 16
+    input channels (zero padded), N = max(Cout, 16).  Returned as a float32-typed byte blob."""
+    from . import capi  # host-side plan enumeration lives in the library so that packer and kernel cannot diverge
+    taps, cin, cout = w.shape
+    if taps != kd * k * k:
+        raise ValueError(f"weight has {taps} taps, expected kd*k*k = {kd * k * k}")
+    n = max(cout, 16)
+    plan = capi.conv_tc3_plan(cin, kd, k, stride)
+    out = torch.zeros((len(plan), 2, 3 * n, 8), dtype=torch.bfloat16)
+    w = w.detach().float().cpu()
+    for i, (kz, ky, kx, c0) in enumerate(plan):
+        cs = min(16, cin - c0)
+        wt = torch.zeros((16, n), dtype=torch.float32)
+        wt[:cs, :cout] = w[(kz * k + ky) * k + kx, c0:c0 + cs, :]
+        for j, t in enumerate(bf16_split3(wt)):
+            for h in range(2):
+                out[i, h, j * n:(j + 1) * n, :] = t[h * 8:(h + 1) * 8, :].T
+    return out.reshape(-1).view(torch.float32)
+
+
 def pack_reg3d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Tensor:
     """reg3d state (``{prefix}.conv0.conv.weight`` ... ``{prefix}.prob.weight``) -> blob in the layout of
     mvster_reg3d_layer_info (``layer_table`` = capi.reg3d_layer_table(G, down_size)); BN folded, prob has no bias."""
@@ -122,6 +153,11 @@ def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, 
             w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
             tc.append(pack_tc_weights(w, 3))
             tc2.append(pack_tc2_weights(w, 3))
-    return {"blob": blob, "tc_blob": torch.cat(tc), "tc2_blob": torch.cat(tc2),
+    tc3 = []
+    for name, L in zip(REG2D_ORDER, layer_table):
+        if not L["transposed"]:  # conv0..conv6: slab streams of the generation-3 kernel, back to back
+            w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
+            tc3.append(pack_tc3_weights(w, L["kd"], 3, L["stride"]))
+    return {"blob": blob, "tc_blob": torch.cat(tc), "tc2_blob": torch.cat(tc2), "tc3_blob": torch.cat(tc3),
             "prob_w": sd[prefix + ".prob.weight"].detach().cpu().reshape(-1).float().contiguous(),
             "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}

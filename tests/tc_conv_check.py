@@ -51,8 +51,40 @@ def reg2d_main(gen):
                       "finite": bool(torch.isfinite(got).all()), "us_tc": t_tc, "us_simt": t_simt}))
 
 
+def v3_main():
+    """generation 3 (persistent, 3 x bf16): v3 CIN COUT KD K STRIDE B D H W [skip] [norelu]; truth = fp64 torch conv."""
+    import torch.nn.functional as F
+    cin, cout, kd, k, stride, B, D, H, W = map(int, sys.argv[2:11])
+    use_skip, relu = "skip" in sys.argv, "norelu" not in sys.argv
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(cin * 1000 + cout * 10 + kd + H + k + stride)
+    x = torch.from_numpy(rng.randn(B, D, H, W, cin).astype(np.float32)).to(dev)
+    w = torch.from_numpy((rng.randn(kd * k * k, cin, cout) / np.sqrt(kd * k * k * cin)).astype(np.float32))
+    bias = torch.from_numpy(rng.randn(cout).astype(np.float32) * 0.1).to(dev)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    skip = torch.from_numpy(rng.randn(B, D, Ho, Wo, cout).astype(np.float32)).to(dev) if use_skip else None
+    w5 = w.to(dev).double().reshape(kd, k, k, cin, cout).permute(4, 3, 0, 1, 2)
+    want = F.conv3d(x.double().permute(0, 4, 1, 2, 3), w5, bias.double(), stride=(1, stride, stride), padding=(kd // 2, k // 2, k // 2))
+    want = want.permute(0, 2, 3, 4, 1)
+    if relu:
+        want = want.clamp_min(0)
+    if skip is not None:
+        want = want + skip.double()
+    wp = packing.pack_tc3_weights(w, kd, k, stride).to(dev)
+    run = lambda: capi.conv_tc3(x, wp, bias, cout, kd, k, stride, relu, skip=skip)
+    got = run()
+    torch.cuda.synchronize()
+    err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()
+    t_tc = timeit(run, 20)
+    flops = 2.0 * B * D * Ho * Wo * kd * k * k * cin * cout
+    print(json.dumps({"case": sys.argv[1:], "abs_err": err, "scale": scale, "rel": err / scale, "finite": bool(torch.isfinite(got).all()),
+                      "us_tc": t_tc, "tflops_tc": flops / (t_tc * 1e-6) / 1e12}))
+
+
 def main():
     mode = sys.argv[1]
+    if mode == "v3":
+        return v3_main()
     if mode.startswith("reg2d"):
         return reg2d_main(2 if mode.endswith("v2") else 1)
     gen = 2 if mode == "v2" else 1

@@ -281,7 +281,7 @@ def test_layout_helper():
 # ----------------------------------------------------------------------------- cascade
 def _run_ours(kwargs, seed, imgs, proj, dv, strict_fp32=False):
     """strict_fp32: every convolution as an exact fp32 FMA chain (CUDA-core regulariser, cuDNN fp32 feature net);
-    default: the engine's defaults (3xTF32 tensor-core 3x3 layers, native feature pyramid)."""
+    default: the engine's defaults (3 x bf16 tensor-core convolutions, native feature pyramid)."""
     torch.backends.cudnn.allow_tf32 = False
     m = build_model(kwargs, seed).to(DEV)
     if strict_fp32:
@@ -343,7 +343,7 @@ def test_teacher_forced_stages_match_oracle():
     assert not failures, "; ".join(failures)
 
 
-@pytest.mark.parametrize("strict_fp32", [True, False], ids=["strict_fp32", "default_3xtf32"])
+@pytest.mark.parametrize("strict_fp32", [True, False], ids=["strict_fp32", "default"])
 @pytest.mark.parametrize("name", ["shipped_b1_v3_64x128", "shipped_b2_v2_64x64"])
 def test_module_forward_against_reference_golden(name, strict_fp32):
     """End to end through MVS4net.forward on the GPU vs outputs of the unmodified reference (fixtures)."""

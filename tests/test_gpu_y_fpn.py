@@ -13,22 +13,22 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("fused_last", [True, False], ids=["fused_last_level", "literal_last_level"])
-@pytest.mark.parametrize("npass,tol", [(0, 2e-5), (3, 1e-4), (1, 2e-2)])
+@pytest.mark.parametrize("npass,gen,tol", [(0, 2, 2e-5), (3, 2, 1e-4), (1, 2, 2e-2), (3, 3, 2e-5)])
 @pytest.mark.parametrize("N,H,W", [(2, 64, 128), (3, 128, 192)])
-def test_native_fpn_matches_oracle(npass, tol, N, H, W, fused_last):
+def test_native_fpn_matches_oracle(npass, gen, tol, N, H, W, fused_last):
     sd = build_model(SHIPPED, 4).state_dict()
     imgs, _, _ = synth.make_inputs(1, N, H, W, seed=8)
     x = torch.cat(imgs, 0)
     with torch.no_grad():
         want = oracle.fpn4_features(sd, x)
     wts = {k: v.to(DEV) for k, v in fpn_engine.pack_fpn(sd).items()}
-    got = fpn_engine.run_fpn(wts, x.to(DEV), npass, fused_last=fused_last)
+    got = fpn_engine.run_fpn(wts, x.to(DEV), npass, fused_last=fused_last, gen=gen)
     for s in range(1, 5):
         g = got[f"stage{s}"].permute(0, 3, 1, 2).cpu()
         w = want[f"stage{s}"]
         assert g.shape == w.shape
         err = (g - w).abs().max().item() / w.abs().max().item()
-        record(f"fpn_npass{npass}_{'fused' if fused_last else 'literal'}_{N}x{H}x{W}_stage{s}", rel_to_max=err)
+        record(f"fpn_npass{npass}_gen{gen}_{'fused' if fused_last else 'literal'}_{N}x{H}x{W}_stage{s}", rel_to_max=err)
         assert err < tol, f"stage{s}: {err:.2e}"
 
 
@@ -52,14 +52,13 @@ def test_cuda_graph_replay_matches_eager(backend):
             assert torch.equal(outs[(True, seed)][k], outs[(False, seed)][k]), (seed, k)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "3xtf32"])
+@pytest.mark.parametrize("precision", ["fp32", "3xtf32", "3xbf16"])
 def test_forward_with_native_fpn_against_reference_golden(precision):
     name = "shipped_b1_v3_64x128"
     z, imgs, proj, dv = load_golden(name)
     m = build_model(GOLDEN_CASES[name], int(z["meta_seed"])).to(DEV)
     m.fpn_backend, m.fpn_precision = "native", precision
-    if precision != "fp32":
-        m.reg_precision, m.tc_kernel_gen = precision, 2
+    m.reg_precision, m.tc_kernel_gen = precision, 2
     with torch.no_grad():
         out = m([t.to(DEV) for t in imgs], {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV))
     ok = torch.ones_like(torch.from_numpy(z["s1_depth"]), dtype=torch.bool)
