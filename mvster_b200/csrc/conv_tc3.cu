@@ -17,7 +17,8 @@
 //     convolutions (4 parity classes, no wasted taps) run on the same kernel.
 //   * tcgen05 / TMA issue is guarded by elect.sync (see tc_ptx.cuh: a lane test makes the compiler serialise every issue).
 //
-// warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-9 = fp32 -> 3 x bf16 converters, warps 10-13 = epilogue.
+// warp 0 = activation producer (TMA), warp 1 = TMEM owner + MMA issuer, warp 2 = weight producer, warps 3-10 = fp32 -> 3 x bf16
+// converters, warps 11-14 = epilogue.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -33,7 +34,7 @@ constexpr int PLANE = QBYTES;                // bf16 operand plane = [180 pixels
 constexpr int A_SPLIT = 2 * PLANE;           // one bf16 term of one tile-stage: 2 channel octets
 constexpr int A_BYTES = 3 * A_SPLIT;         // a1 | a2 | a3
 constexpr int NCONV = 256;                 // converter threads (8 warps: one warp per SM sub-partition was latency-bound)
-constexpr int THREADS = 64 + NCONV + 128;
+constexpr int THREADS = 96 + NCONV + 128;
 constexpr int MAX_STAGES = 16, MAX_TAPS = 9;
 constexpr int NF = 4, NB = 10;
 
@@ -118,9 +119,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
 #define MVSTER_TC3_STAGE_SKIP(s) ((unsigned)(z + plan.st[s].dz) >= (unsigned)a.D)
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ activation producer (TMA halo tiles)
+        // Its own warp: sharing one issue thread with the weight stream (a ring of ~1 stage of taps) tied the activation
+        // prefetch distance to the MMA progress and left the converters waiting for data half of the time.
         if (elect_one()) {
-            uint32_t fu = 0, bu = 0;
+            uint32_t fu = 0;
             for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
                 MVSTER_TC3_GROUP_HEAD
                 for (int s = 0; s < a.nstage; ++s) {
@@ -131,64 +134,89 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         mbar_wait(F_EMPTY(fs), ((fu / NF) & 1) ^ 1);
                         mbar_expect_tx(F_FULL(fs), st.nq * QBYTES);
                         const int ti = tile0 + t, y0 = (ti / a.tiles_x) * TH, x0 = (ti % a.tiles_x) * TW;
-                        // one box = [18][10] pixels x min(Cin,16) channels (64-byte rows: a 16-byte-row box per channel quad
-                        // costs the TMA engine 4x the requests); the converters re-lay it out for the MMA anyway
+                        // one box = [18][10] pixels x min(Cin,16) channels (64-byte rows); the converters re-lay it out for the MMA
                         tma_load_4d(f_base + fs * F_BYTES, &x_map, F_FULL(fs), st.c0, a.sx * x0 + st.ox, a.sx * y0 + st.oy, plane + st.dz);
                     }
-                    for (int tap = 0; tap < st.ntap; ++tap, ++bu) {
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ------------------------------------------------------------------ weight producer (one bulk copy per (stage, tap))
+        if (elect_one()) {
+            uint32_t bu = 0;
+            for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
+                MVSTER_TC3_GROUP_HEAD
+                (void)tile0; (void)Tg;
+                for (int s = 0; s < a.nstage; ++s) {
+                    if (MVSTER_TC3_STAGE_SKIP(s)) continue;
+                    const int ntap = plan.st[s].ntap, slab0 = plan.st[s].slab0;
+                    for (int tap = 0; tap < ntap; ++tap, ++bu) {
                         const uint32_t sb = bu % NB;
                         mbar_wait(B_EMPTY(sb), ((bu / NB) & 1) ^ 1);
                         mbar_expect_tx(B_FULL(sb), C::B_BYTES);
-                        bulk_load(b_base + sb * C::B_BYTES, a.w + (size_t)(st.slab0 + tap) * C::B_BYTES, C::B_BYTES, B_FULL(sb));
+                        bulk_load(b_base + sb * C::B_BYTES, a.w + (size_t)(slab0 + tap) * C::B_BYTES, C::B_BYTES, B_FULL(sb));
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        constexpr uint32_t ID3 = idesc_bf16_m128(3 * NC), ID2 = idesc_bf16_m128(2 * NC), ID1 = idesc_bf16_m128(NC);
-        uint32_t u = 0, bu = 0, gc = 0;
-        for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x, ++gc) {
-            MVSTER_TC3_GROUP_HEAD
-            const uint32_t set = gc & 1;
-            mbar_wait(ACC_EMPTY(set), ((gc >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
-            tc_fence_after();
-            bool fresh = true;
-            for (int s = 0; s < a.nstage; ++s) {
-                if (MVSTER_TC3_STAGE_SKIP(s)) continue;
-                const int ntap = plan.st[s].ntap;
-                for (int t = 0; t < Tg; ++t) mbar_wait(A_FULL((u + t) % C::NA), ((u + t) / C::NA) & 1);
-                for (int tap = 0; tap < ntap; ++tap, ++bu) {
-                    const uint32_t sb = bu % NB;
-                    mbar_wait(B_FULL(sb), (bu / NB) & 1);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t b0 = smem_desc(b_base + sb * C::B_BYTES, 3 * NC * 16, 128, 0);
-                        const uint64_t shift = plan.a_off[s][tap];
-                        const uint32_t first = (fresh && tap == 0) ? 0u : 1u;
-                        for (int t = 0; t < Tg; ++t) {
-                            const uint64_t a1 = smem_desc(a_base + ((u + t) % C::NA) * A_BYTES, PLANE, HW_ * 16, 0) + shift;
-                            const uint32_t d = tmem_base + set * 256u + (uint32_t)(t * 3 * NC);
-                            umma_bf16(d, a1, b0, ID3, first);                           // a1 x [w1|w2|w3]
-                            umma_bf16(d, a1 + (A_SPLIT >> 4), b0, ID2, 1u);             // a2 x [w1|w2]
-                            umma_bf16(d, a1 + (2 * A_SPLIT >> 4), b0, ID1, 1u);         // a3 x [w1]
+        // ONE thread runs the whole role (waits included) and keeps the per-tap scalar work to a few adds: with a per-tap
+        // elect / descriptor rebuild / warp sync the issue thread needed ~1000 cycles per tap whatever the MMA sizes and the
+        // tensor pipe idled a third of the time (ncu source page, profiles/r01_conv_tc3_ncu.md).
+        if (elect_one()) {
+            constexpr uint32_t ID3 = idesc_bf16_m128(3 * NC), ID2 = idesc_bf16_m128(2 * NC), ID1 = idesc_bf16_m128(NC);
+            // descriptor = (hi << 32) | lo; lo = start address >> 4 | LBO >> 4 << 16 (taps / splits / slots only move the address)
+            constexpr uint64_t A_HI = (uint64_t)((HW_ * 16) >> 4) | (1ull << 14), B_HI = (uint64_t)(128 >> 4) | (1ull << 14);
+            constexpr uint32_t A_LBO = (uint32_t)(PLANE >> 4) << 16, B_LBO = (uint32_t)((3 * NC * 16) >> 4) << 16;
+            uint32_t a_slot = 0, a_par = 0, b_slot = 0, b_par = 0, gc = 0;
+            for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x, ++gc) {
+                MVSTER_TC3_GROUP_HEAD
+                const uint32_t set = gc & 1;
+                mbar_wait(ACC_EMPTY(set), ((gc >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + set * 256u;
+                uint32_t accumulate = 0;
+                for (int s = 0; s < a.nstage; ++s) {
+                    if (MVSTER_TC3_STAGE_SKIP(s)) continue;
+                    const int ntap = plan.st[s].ntap;
+                    uint32_t alo[C::TMAX], aslot[C::TMAX];
+#pragma unroll
+                    for (int t = 0; t < C::TMAX; ++t)
+                        if (t < Tg) {
+                            mbar_wait(A_FULL(a_slot), a_par);
+                            aslot[t] = a_slot;
+                            alo[t] = (((a_base + a_slot * A_BYTES) & 0x3FFFFu) >> 4) | A_LBO;
+                            if (++a_slot == C::NA) { a_slot = 0; a_par ^= 1; }
                         }
-                        umma_commit(B_EMPTY(sb));
+                    tc_fence_after();
+                    for (int tap = 0; tap < ntap; ++tap) {
+                        mbar_wait(B_FULL(b_slot), b_par);
+                        tc_fence_after();
+                        const uint64_t bd = (B_HI << 32) | ((((b_base + b_slot * C::B_BYTES) & 0x3FFFFu) >> 4) | B_LBO);
+                        const uint32_t shift = plan.a_off[s][tap];
+#pragma unroll
+                        for (int t = 0; t < C::TMAX; ++t)
+                            if (t < Tg) {
+                                const uint32_t lo = alo[t] + shift, d = d0 + (uint32_t)(t * 3 * NC);
+                                umma_bf16(d, (A_HI << 32) | lo, bd, ID3, accumulate);                           // a1 x [w1|w2|w3]
+                                umma_bf16(d, (A_HI << 32) | (lo + (A_SPLIT >> 4)), bd, ID2, 1u);                // a2 x [w1|w2]
+                                umma_bf16(d, (A_HI << 32) | (lo + (2 * A_SPLIT >> 4)), bd, ID1, 1u);            // a3 x [w1]
+                            }
+                        umma_commit(B_EMPTY(b_slot));
+                        if (++b_slot == NB) { b_slot = 0; b_par ^= 1; }
+                        accumulate = 1;
                     }
-                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < C::TMAX; ++t)
+                        if (t < Tg) umma_commit(A_EMPTY(aslot[t]));
                 }
-                if (elect_one())
-                    for (int t = 0; t < Tg; ++t) umma_commit(A_EMPTY((u + t) % C::NA));
-                __syncwarp();
-                u += Tg;
-                fresh = false;
+                umma_commit(ACC_FULL(set));
             }
-            if (elect_one()) umma_commit(ACC_FULL(set));
-            __syncwarp();
         }
-    } else if (warp < 2 + NCONV / 32) {
+    } else if (warp < 3 + NCONV / 32) {
         // ------------------------------------------------------------------ converters: fp32 halo tile -> a1 | a2 | a3 (bf16)
-        const int tid = threadIdx.x - 64;
+        const int tid = threadIdx.x - 96;
         uint32_t u = 0;
         for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
             MVSTER_TC3_GROUP_HEAD
