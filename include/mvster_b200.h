@@ -147,6 +147,17 @@ int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias,
                         int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
                         mvster_stream_t stream);
 
+/* Transposed convolution on the same kernel: kernel (1,3,3), stride (1,2,2), padding 1, output padding 1 (Deconv3d after BN
+ * folding, mvs4net_utils.py:126-145, :893-897) computed as a 2x2 stride-1 convolution on the input grid whose N columns are the
+ * output parity classes [class (py,px)][Cout], scattered depth-to-space by the epilogue.  x [B][D][H][W][Cin] ->
+ * y [B][D][2H][2W][Cout] (+ skip, same shape).  rows = -1: all four classes in one launch (needs 4*Cout <= 64); rows = 0 / 1:
+ * only output rows of that parity (2*Cout <= 64), two launches cover the layer.  Cin in {16,32,64}, Cout in {8,16,32}.
+ * w_packed: packing.pack_tc3_deconv_weights(w [9][Cin][Cout], rows), mvster_deconv_tc3_packed_bytes bytes. */
+int mvster_deconv_tc3_supported(int Cin, int Cout, int rows);
+size_t mvster_deconv_tc3_packed_bytes(int Cin, int Cout, int rows);
+int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
+                          int B, int D, int H, int W, int Cin, int Cout, int rows, int relu, mvster_stream_t stream);
+
 /* reg2d U-Net (mvs4net_utils.py:870-912) up to, not including, the 1x1x1 `prob`
  * layer: cost [B][D][H][W][G] -> feat8 [B][D][H][W][8].  `blob` holds the folded
  * weights of conv0..conv11 in the layout reported by mvster_reg2d_layer_info;
@@ -167,10 +178,11 @@ size_t mvster_reg2d_tc_blob_floats(void);
 int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* cost, float* feat8, float* workspace,
                         int B, int G, int D, int H, int W, int npass, int kernel_gen, mvster_stream_t stream);
 
-/* Same network with conv0..conv6 (every forward convolution, stride 1 and stride (1,2,2)) on the generation-3 tensor-core
- * kernel (mvster_conv_tc3_f32, 3 x bf16, fp32-faithful); the three transposed layers stay on the CUDA cores.  tc3_blob =
- * packing.pack_tc3_weights of conv0..conv6 back to back (mvster_reg2d_tc3_blob_bytes(G) bytes, 16-byte aligned); biases
- * and the transposed layers' weights are read from `blob`. */
+/* Same network with conv1..conv6 (stride 1 and stride (1,2,2)) on the generation-3 tensor-core kernel
+ * (mvster_conv_tc3_f32, 3 x bf16, fp32-faithful); conv0 (G -> 8 channels: K and N would be mostly padding) and the three
+ * transposed layers stay on the CUDA cores.  tc3_blob = packing.pack_tc3_weights of conv0..conv6 back to back
+ * (mvster_reg2d_tc3_blob_bytes(G) bytes, 16-byte aligned; conv0's slabs are present but unused); biases and the CUDA-core
+ * layers' weights are read from `blob`. */
 size_t mvster_reg2d_tc3_blob_bytes(int G);
 int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* workspace,
                          int B, int G, int D, int H, int W, mvster_stream_t stream);

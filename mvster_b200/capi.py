@@ -276,6 +276,27 @@ def reg3d(blob: Tensor, cost: Tensor, down_size: int) -> Tensor:
     return out
 
 
+def deconv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, rows: int = -1, relu: bool = True,
+               skip: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """Transposed conv (1,3,3) / stride (1,2,2) on the generation-3 tcgen05 kernel: x [B,D,H,W,Cin] -> [B,D,2H,2W,cout].
+    rows = -1 writes every output pixel; rows = 0 / 1 only the output rows of that parity (pass ``out`` to the second call)."""
+    _chk(x, "x")
+    _chk(w_packed, "w_packed")
+    B, D, H, W, Cin = x.shape
+    y = torch.empty((B, D, 2 * H, 2 * W, cout), device=x.device, dtype=torch.float32) if out is None else _chk(out, "out", (B, D, 2 * H, 2 * W, cout))
+    if bias is not None:
+        _chk(bias, "bias", (cout,))
+    if skip is not None:
+        _chk(skip, "skip", tuple(y.shape))
+    lib = _lib.load()
+    want = lib.mvster_deconv_tc3_packed_bytes(Cin, cout, rows)
+    if want == 0 or w_packed.numel() * 4 != want:
+        raise ValueError(f"deconv_tc3: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
+    _lib.check(lib.mvster_deconv_tc3_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout, rows,
+                                         int(relu), _stream()), "mvster_deconv_tc3_f32")
+    return y
+
+
 def reg2d_layer_table(G: int) -> List[dict]:
     lib = _lib.load()
     n_layers = 10

@@ -297,17 +297,24 @@ extern "C" int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, cons
     return reg2d_run(blob, tc_blob, npass, kernel_gen, cost, feat8, ws, B, G, D, H, W, stream);
 }
 
-// byte offset of layer i's slab stream inside the generation-3 blob (layers 0..6, the non-transposed ones, back to back)
+// Generation-3 blob: slab streams of conv0..conv6 back to back, then the transposed layers conv7 (output rows of parity 0,
+// then parity 1: 4*32 columns do not fit one launch), conv9, conv11 (all four parity classes in one launch).
+static int tc3_deconv_rows(const Layer& l) { return 4 * l.cout <= 64 ? -1 : 0; }  // -1: one launch, 0: two launches (rows 0, 1)
+static size_t tc3_layer_bytes(const Layer& l) {
+    if (!l.transposed) return mvster_conv_tc3_packed_bytes(l.cin, l.cout, l.kd, 3, l.s);
+    if (tc3_deconv_rows(l) < 0) return mvster_deconv_tc3_packed_bytes(l.cin, l.cout, -1);
+    return mvster_deconv_tc3_packed_bytes(l.cin, l.cout, 0) + mvster_deconv_tc3_packed_bytes(l.cin, l.cout, 1);
+}
 static size_t tc3_layer_offset(const Layer (&L)[MVSTER_REG2D_LAYERS], int layer) {
     size_t off = 0;
-    for (int i = 0; i < layer && i < 7; ++i) off += mvster_conv_tc3_packed_bytes(L[i].cin, L[i].cout, L[i].kd, 3, L[i].s);
+    for (int i = 0; i < layer; ++i) off += tc3_layer_bytes(L[i]);
     return off;
 }
 
 extern "C" size_t mvster_reg2d_tc3_blob_bytes(int G) {
     Layer L[MVSTER_REG2D_LAYERS];
     reg2d_layers(G, L);
-    return tc3_layer_offset(L, 7);
+    return tc3_layer_offset(L, MVSTER_REG2D_LAYERS);
 }
 
 extern "C" int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* ws,
@@ -336,10 +343,21 @@ static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen
         int64_t info[8];
         mvster_reg2d_layer_info(G, i, info);
         int rc;
-        if (tc_blob && gen == 3 && !L[i].transposed) {
-            // every forward convolution (stride 1 and stride (1,2,2)) on the persistent 3 x bf16 tcgen05 kernel
+        if (tc_blob && gen == 3 && !L[i].transposed && i > 0) {
+            // conv1..conv6 (stride 1 and stride (1,2,2)) on the persistent 3 x bf16 tcgen05 kernel.  conv0 (G -> 8 channels at
+            // full resolution) stays on the CUDA cores: with K and N mostly padding the tensor-core tile costs as much as a
+            // 16 -> 16 layer (measured 101 us vs 42 us at cfg2 stage 4).
             rc = mvster_conv_tc3_f32(in[i], (const uint8_t*)tc_blob + tc3_layer_offset(L, i), blob + info[6], skip[i], out[i], B, D,
                                      H / div[i], W / div[i], L[i].cin, L[i].cout, L[i].kd, 3, L[i].s, 1, stream);
+        } else if (tc_blob && gen == 3 && L[i].transposed) {
+            // conv7 / conv9 / conv11: 2x2 convolution on the input grid + depth-to-space epilogue (mvster_deconv_tc3_f32)
+            const uint8_t* wl = (const uint8_t*)tc_blob + tc3_layer_offset(L, i);
+            const int rows = tc3_deconv_rows(L[i]);
+            rc = mvster_deconv_tc3_f32(in[i], wl, blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i], L[i].cin, L[i].cout,
+                                       rows, 1, stream);
+            if (rc == MVSTER_OK && rows == 0)
+                rc = mvster_deconv_tc3_f32(in[i], wl + mvster_deconv_tc3_packed_bytes(L[i].cin, L[i].cout, 0), blob + info[6], skip[i],
+                                           out[i], B, D, H / div[i], W / div[i], L[i].cin, L[i].cout, 1, 1, stream);
         } else if (tc_blob && gen != 3 && L[i].kd == 3) {
             // conv2 / conv4 / conv6 (3x3x3, 69 % of the FLOPs) on the tcgen05 tensor cores; their [hi|lo]
             // K-major slabs sit back to back in tc_blob (2*27*Cin*Cout floats each).

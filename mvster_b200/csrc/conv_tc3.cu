@@ -49,6 +49,7 @@ struct Args {
     const uint8_t* w;
     const float* bias; const float* skip; float* y;
     int D, Ho, Wo, cout, relu, sx, nstage, T, tiles_x, tiles_per_plane, groups_per_plane, total_groups, zero_a;
+    int ncls, py0;  // transposed conv: ncls output parity classes of Cout channels side by side along N (1 = plain conv)
 };
 
 template <int NC>
@@ -272,29 +273,52 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                 const bool ok = yy < a.Ho && xx < a.Wo;
                 const long long off = (((long long)plane * a.Ho + yy) * a.Wo + xx) * a.cout;
                 const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)(t * 3 * NC);
+                const int ncol = a.ncls * a.cout;
+                // plain conv: column = output channel.  Transposed conv (depth-to-space): column = class * Cout + channel,
+                // class (py, px) of input pixel (yy, xx) is output pixel (2 yy + py, 2 xx + px)
+                auto out_offset = [&](int c, int& ch) -> long long {
+                    if (a.ncls == 1) { ch = c; return off + c; }
+                    const int cls = c / a.cout;
+                    ch = c - cls * a.cout;
+                    return (((long long)plane * (2 * a.Ho) + 2 * yy + a.py0 + (cls >> 1)) * (2 * a.Wo) + 2 * xx + (cls & 1)) * a.cout + ch;
+                };
+                constexpr int RC = NC < 32 ? NC : 32;  // columns per round: their skip values are fetched up front, all in flight
 #pragma unroll
-                for (int c0 = 0; c0 < NC; c0 += 16) {
-                    uint32_t v1[16], v2[16], v3[16];
-                    tmem_ld16(col + c0, v1);
-                    tmem_ld16(col + NC + c0, v2);
-                    tmem_ld16(col + 2 * NC + c0, v3);
-                    tmem_ld_wait();
-                    if (ok && c0 < a.cout) {
+                for (int cb = 0; cb < NC; cb += RC) {
+                    float4 sk[RC / 4];
+                    if (a.skip && ok) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            if (c0 + j >= a.cout) break;
-                            float o[4];
+                        for (int jg = 0; jg < RC / 4; ++jg) {
+                            int ch;
+                            if (cb + 4 * jg < ncol) sk[jg] = __ldg(reinterpret_cast<const float4*>(a.skip + out_offset(cb + 4 * jg, ch)));
+                        }
+                    }
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                o[e] = (__uint_as_float(v3[j + e]) + __uint_as_float(v2[j + e])) + __uint_as_float(v1[j + e]);
-                                if (a.bias) o[e] += __ldg(a.bias + c0 + j + e);
-                                if (a.relu) o[e] = fmaxf(o[e], 0.f);
+                    for (int c0 = cb; c0 < cb + RC; c0 += 16) {
+                        uint32_t v1[16], v2[16], v3[16];
+                        tmem_ld16(col + c0, v1);
+                        tmem_ld16(col + NC + c0, v2);
+                        tmem_ld16(col + 2 * NC + c0, v3);
+                        tmem_ld_wait();
+                        if (ok && c0 < ncol) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                if (c0 + j >= ncol) break;
+                                int ch;
+                                const long long o_off = out_offset(c0 + j, ch);
+                                float o[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    o[e] = (__uint_as_float(v3[j + e]) + __uint_as_float(v2[j + e])) + __uint_as_float(v1[j + e]);
+                                    if (a.bias) o[e] += __ldg(a.bias + ch + e);
+                                    if (a.relu) o[e] = fmaxf(o[e], 0.f);
+                                }
+                                if (a.skip) {
+                                    const float4 s4 = sk[(c0 - cb + j) / 4];
+                                    o[0] += s4.x; o[1] += s4.y; o[2] += s4.z; o[3] += s4.w;
+                                }
+                                *reinterpret_cast<float4*>(a.y + o_off) = make_float4(o[0], o[1], o[2], o[3]);
                             }
-                            if (a.skip) {
-                                const float4 sk = __ldg(reinterpret_cast<const float4*>(a.skip + off + c0 + j));
-                                o[0] += sk.x; o[1] += sk.y; o[2] += sk.z; o[3] += sk.w;
-                            }
-                            *reinterpret_cast<float4*>(a.y + off + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
                         }
                     }
                 }
@@ -455,9 +479,81 @@ extern "C" int mvster_conv_tc3_f32(const float* x, const void* w_packed, const f
     a.tiles_x = ceil_div(a.Wo, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(a.Ho, TH);
     a.zero_a = Cin < 16;
+    a.ncls = 1; a.py0 = 0;
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
     cudaStream_t st = (cudaStream_t)stream;
     const int NC = Cout < 16 ? 16 : Cout;
+    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st);
+    return launch<64>(xm, plan, a, total_tiles, sms, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Transposed convolution, kernel (1,3,3), stride (1,2,2), padding 1, output padding 1 (Deconv3d of reg2d, mvs4net_utils.py:
+// 893-897): out[2i - 1 + k] += in[i] w[k].  Output pixel (2y + py, 2x + px) depends on input rows y + dy with
+//     py = 0: (dy = 0, ky = 1)            py = 1: (dy = 0, ky = 2), (dy = 1, ky = 0)        (columns alike)
+// so the layer is a 2 x 2 stride-1 convolution on the INPUT grid (taps (dy,dx) in {0,1}^2 = halo offsets 1..2) producing the
+// output parity classes side by side along N - [class (py,px)][Cout] columns, zero weights where a tap does not feed a class -
+// followed by a depth-to-space scatter in the epilogue.  rows = -1: all four classes in one launch (4*Cout <= 64 columns);
+// rows = 0 / 1: only the output rows of parity py (2*Cout columns; two launches cover the layer when 4*Cout > 64).
+// Slab order: [16-channel chunk][tap (dy,dx) row-major over the taps the launch needs]; rows = 0 needs only dy = 0.
+static int deconv_ncls(int rows) { return rows < 0 ? 4 : 2; }
+static int deconv_ntap(int rows) { return rows == 0 ? 2 : 4; }
+
+extern "C" int mvster_deconv_tc3_supported(int Cin, int Cout, int rows) {
+    const int n = deconv_ncls(rows) * Cout;
+    return (Cin == 16 || Cin == 32 || Cin == 64) && (Cout == 8 || Cout == 16 || Cout == 32) && rows >= -1 && rows <= 1 &&
+           (n == 16 || n == 32 || n == 64);
+}
+
+extern "C" size_t mvster_deconv_tc3_packed_bytes(int Cin, int Cout, int rows) {
+    if (!mvster_deconv_tc3_supported(Cin, Cout, rows)) return 0;
+    return (size_t)(Cin / 16) * deconv_ntap(rows) * 96 * deconv_ncls(rows) * Cout;
+}
+
+extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
+                                     int B, int D, int H, int W, int Cin, int Cout, int rows, int relu, mvster_stream_t stream) {
+    using namespace mvster::tc3;
+    MVSTER_REQUIRE(x && w_packed && y, "mvster_deconv_tc3_f32: null pointer");
+    MVSTER_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "mvster_deconv_tc3_f32: bad shape");
+    MVSTER_REQUIRE(mvster_deconv_tc3_supported(Cin, Cout, rows), "mvster_deconv_tc3_f32: unsupported layer Cin=%d Cout=%d rows=%d", Cin, Cout, rows);
+    MVSTER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)x & 15) == 0, "mvster_deconv_tc3_f32: x and w_packed must be 16-byte aligned");
+    EncodeTiledFn enc = encode_fn();
+    MVSTER_REQUIRE(enc, "mvster_deconv_tc3_f32: cuTensorMapEncodeTiled is unavailable in this driver");
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    CUtensorMap xm;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * D};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
+        cuuint32_t box[4] = {16, HW_, HH_, 1}, es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVSTER_REQUIRE(r == CUDA_SUCCESS, "mvster_deconv_tc3_f32: activation tensor map rejected (CUresult %d)", (int)r);
+    }
+    Plan plan;
+    memset(&plan, 0, sizeof(plan));
+    const int kch = Cin / 16, ntap = deconv_ntap(rows);
+    for (int kc = 0; kc < kch; ++kc) {
+        Stage S;
+        S.c0 = (short)(kc * 16); S.nq = 4; S.ox = -1; S.oy = -1; S.dz = 0; S.ntap = (short)ntap; S.slab0 = (short)(kc * ntap); S.pad = 0;
+        plan.st[kc] = S;
+        for (int t = 0; t < ntap; ++t) plan.a_off[kc][t] = (unsigned char)((t / 2 + 1) * HW_ + (t % 2 + 1));  // halo (1 + dy, 1 + dx)
+    }
+    Args a;
+    a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
+    a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = relu; a.sx = 1; a.nstage = kch;
+    a.tiles_x = ceil_div(W, TW);
+    a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
+    a.zero_a = 0;
+    a.ncls = deconv_ncls(rows); a.py0 = rows == 1 ? 1 : 0;
+    const long long total_tiles = (long long)a.tiles_per_plane * B * D;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NC = a.ncls * Cout;
     if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st);
     if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st);
     return launch<64>(xm, plan, a, total_tiles, sms, st);

@@ -101,6 +101,41 @@ def pack_tc3_weights(w: Tensor, kd: int, k: int, stride: int = 1) -> Tensor:
     return out.reshape(-1).view(torch.float32)
 
 
+def _tc3_slabs(mats) -> Tensor:
+    """list of [16][n] fp32 matrices (16 input channels x n accumulator columns) -> generation-3 slab stream."""
+    n = mats[0].shape[1]
+    out = torch.zeros((len(mats), 2, 3 * n, 8), dtype=torch.bfloat16)
+    for i, wt in enumerate(mats):
+        for j, t in enumerate(bf16_split3(wt)):
+            for h in range(2):
+                out[i, h, j * n:(j + 1) * n, :] = t[h * 8:(h + 1) * 8, :].T
+    return out.reshape(-1).view(torch.float32)
+
+
+def pack_tc3_deconv_weights(w: Tensor, rows: int = -1) -> Tensor:
+    """Transposed conv (1,3,3)/stride (1,2,2)/pad 1 weights [9][Cin][Cout] -> slab stream of mvster_deconv_tc3_f32: per
+    16-channel chunk, one slab per input tap (dy,dx) in {0,1}^2 (rows = 0: dy = 0 only) whose columns are the output parity
+    classes [class][Cout]; class (py,px) reads kernel element ky(py,dy), kx(px,dx) with k(0,0) = 1, k(1,0) = 2, k(1,1) = 0 and
+    nothing for (0,1) (out[2i - 1 + k] += in[i] w[k])."""
+    taps, cin, cout = w.shape
+    if taps != 9 or cin % 16:
+        raise ValueError(f"expected [9][Cin % 16 == 0][Cout], got {tuple(w.shape)}")
+    w = w.detach().float().cpu()
+    kidx = {(0, 0): 1, (1, 0): 2, (1, 1): 0}  # (output parity, input offset) -> kernel index
+    classes = [(py, px) for py in ((0, 1) if rows < 0 else (rows,)) for px in (0, 1)]
+    mats = []
+    for c0 in range(0, cin, 16):
+        for dy in ((0,) if rows == 0 else (0, 1)):
+            for dx in (0, 1):
+                m = torch.zeros((16, len(classes) * cout), dtype=torch.float32)
+                for ci, (py, px) in enumerate(classes):
+                    ky, kx = kidx.get((py, dy)), kidx.get((px, dx))
+                    if ky is not None and kx is not None:
+                        m[:, ci * cout:(ci + 1) * cout] = w[ky * 3 + kx, c0:c0 + 16, :]
+                mats.append(m)
+    return _tc3_slabs(mats)
+
+
 def pack_reg3d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Tensor:
     """reg3d state (``{prefix}.conv0.conv.weight`` ... ``{prefix}.prob.weight``) -> blob in the layout of
     mvster_reg3d_layer_info (``layer_table`` = capi.reg3d_layer_table(G, down_size)); BN folded, prob has no bias."""
@@ -155,9 +190,14 @@ def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, 
             tc2.append(pack_tc2_weights(w, 3))
     tc3 = []
     for name, L in zip(REG2D_ORDER, layer_table):
-        if not L["transposed"]:  # conv0..conv6: slab streams of the generation-3 kernel, back to back
-            w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
+        # slab streams of the generation-3 kernel in layer order (layout: conv_simt.cu tc3_layer_bytes)
+        w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
+        if not L["transposed"]:
             tc3.append(pack_tc3_weights(w, L["kd"], 3, L["stride"]))
+        elif 4 * L["cout"] <= 64:   # all four output parity classes in one launch
+            tc3.append(pack_tc3_deconv_weights(w, -1))
+        else:                       # conv7 (64 -> 32): output rows of parity 0, then parity 1
+            tc3 += [pack_tc3_deconv_weights(w, 0), pack_tc3_deconv_weights(w, 1)]
     return {"blob": blob, "tc_blob": torch.cat(tc), "tc2_blob": torch.cat(tc2), "tc3_blob": torch.cat(tc3),
             "prob_w": sd[prefix + ".prob.weight"].detach().cpu().reshape(-1).float().contiguous(),
             "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}

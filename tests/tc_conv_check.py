@@ -81,10 +81,47 @@ def v3_main():
                       "us_tc": t_tc, "tflops_tc": flops / (t_tc * 1e-6) / 1e12}))
 
 
+def d3_main():
+    """generation-3 transposed conv (1,3,3)/stride (1,2,2): d3 CIN COUT B D H W [skip]; truth = fp64 conv_transpose3d."""
+    import torch.nn.functional as F
+    cin, cout, B, D, H, W = map(int, sys.argv[2:8])
+    use_skip = "skip" in sys.argv
+    dev = torch.device("cuda", 0)
+    rng = np.random.RandomState(cin * 100 + cout + H)
+    x = torch.from_numpy(rng.randn(B, D, H, W, cin).astype(np.float32)).to(dev)
+    w = torch.from_numpy((rng.randn(9, cin, cout) / np.sqrt(2.25 * cin)).astype(np.float32))
+    bias = torch.from_numpy(rng.randn(cout).astype(np.float32) * 0.1).to(dev)
+    skip = torch.from_numpy(rng.randn(B, D, 2 * H, 2 * W, cout).astype(np.float32)).to(dev) if use_skip else None
+    wt = w.to(dev).double().reshape(1, 3, 3, cin, cout).permute(3, 4, 0, 1, 2)  # [Cin][Cout][1][3][3]
+    want = F.conv_transpose3d(x.double().permute(0, 4, 1, 2, 3), wt, bias.double(), stride=(1, 2, 2), padding=(0, 1, 1), output_padding=(0, 1, 1))
+    want = want.permute(0, 2, 3, 4, 1).clamp_min(0)
+    if skip is not None:
+        want = want + skip.double()
+    if 4 * cout <= 64:
+        wp = packing.pack_tc3_deconv_weights(w, -1).to(dev)
+        run = lambda: capi.deconv_tc3(x, wp, bias, cout, -1, True, skip=skip)
+    else:
+        wp0, wp1 = packing.pack_tc3_deconv_weights(w, 0).to(dev), packing.pack_tc3_deconv_weights(w, 1).to(dev)
+        buf = torch.full((B, D, 2 * H, 2 * W, cout), float("nan"), device=dev)
+
+        def run():
+            capi.deconv_tc3(x, wp0, bias, cout, 0, True, skip=skip, out=buf)
+            return capi.deconv_tc3(x, wp1, bias, cout, 1, True, skip=skip, out=buf)
+    got = run()
+    torch.cuda.synchronize()
+    err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()
+    t_tc = timeit(run, 20)
+    t_simt = timeit(lambda: capi.conv3d_ndhwc(x, w.to(dev), bias, 1, 1, 2, True, True, skip=skip), 20)
+    print(json.dumps({"case": sys.argv[1:], "abs_err": err, "scale": scale, "rel": err / scale, "finite": bool(torch.isfinite(got).all()),
+                      "us_tc": t_tc, "us_simt": t_simt, "tflops_tc": 2.0 * B * D * H * W * 9 * cin * cout / (t_tc * 1e-6) / 1e12}))
+
+
 def main():
     mode = sys.argv[1]
     if mode == "v3":
         return v3_main()
+    if mode == "d3":
+        return d3_main()
     if mode.startswith("reg2d"):
         return reg2d_main(2 if mode.endswith("v2") else 1)
     gen = 2 if mode == "v2" else 1

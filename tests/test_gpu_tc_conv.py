@@ -46,6 +46,13 @@ CASES = [  # generation cin cout kd B D H W npass [flags]
     "v3 16 16 3 3 1 1 4 256 320",       # reg2d conv2 at cfg2 stage 4: 2560 tiles, persistent loop
     "v3 16 16 1 3 1 5 1 512 640",       # FPN out3 (12800 tiles)
     "v3 32 32 3 3 1 1 4 128 160 skip",  # conv4
+    # generation-3 transposed conv (1,3,3)/stride (1,2,2) = 2x2 conv + depth-to-space: d3 cin cout B D H W [skip]
+    "d3 16 8 1 2 24 40 skip",           # conv11 class: four parity classes in one launch (N = 32), ragged tiles
+    "d3 32 16 2 2 16 16",               # conv9 class (N = 64), batch 2
+    "d3 64 32 1 4 8 10 skip",           # conv7 class: two launches (output rows of parity 0, 1), image smaller than a tile
+    "d3 16 8 1 4 256 320 skip",         # conv11 at cfg2 stage 4
+    "d3 32 16 1 4 128 160 skip",        # conv9
+    "d3 64 32 1 4 64 80 skip",          # conv7
     "reg2d 8 1 8 64 80 3",              # whole reg2d U-Net, stage-1 shape of cfg2, 3xTF32, generation 1
     "reg2dv2 8 1 8 64 80 3",            # ... generation 2
     "reg2dv2 4 1 4 512 640 3",          # stage-4 shape of cfg2 (1.31 M voxels)
@@ -65,7 +72,7 @@ def test_tc_conv_matches_exact_conv(case):
         f.write(json.dumps(res) + "\n")
     assert res["finite"]
     f = case.split()
-    if f[0] == "v3":  # measured against an fp64 convolution: fp32-level agreement
+    if f[0] in ("v3", "d3"):  # measured against an fp64 convolution: fp32-level agreement
         assert res["rel"] < 1e-5, res  # measured 3e-7 .. 4.5e-6 (K up to 1728 products, fp32 accumulation in the tensor core)
         return
     npass = int(f[6]) if f[0].startswith("reg2d") else int(f[8])
