@@ -51,6 +51,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peak():
+    """dense bf16 tensor throughput (TFLOP/s): the burst figure of MEASURED_PEAKS.json (kernel timed alone), else the recipe's fallback."""
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+        except Exception:
+            pass
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -340,6 +351,38 @@ def main():
                                                  "bytes": tot_b, "us": tot_t * 1e6},
                 "per_stage": per_stage}
 
+    # ---- the convolution kernel that holds most of the step time (profiles/r01_launches_tc3.md): tensor-pipe view.
+    # One launch of reg2d conv2 at stage 4 (16 -> 16 channels, 3x3x3, D x H/2 x W/2 voxels), timed alone like the ET launches.
+    roof_tc = None
+    if rank == 0 and model.reg_precision == "3xbf16":
+        from mvster_b200 import packing
+        tf_peak = tensor_peak()
+        vox = (B, D_K[3], H // 2, W // 2)
+        xin = torch.randn(*vox, 16, device=dev)
+        wp = packing.pack_tc3_weights(torch.randn(27, 16, 16) / 20.0, 3, 3, 1).to(dev)
+        bias = torch.zeros(16, device=dev)
+        yout = torch.empty(*vox, 16, device=dev)
+        for _ in range(3):
+            capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout)
+        ts = []
+        for _ in range(20):
+            flush.fill_(1.0)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout)
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        t = statistics.mean(ts)
+        flops = 2.0 * vox[0] * vox[1] * vox[2] * vox[3] * 27 * 16 * 16
+        roof_tc = {"kernel": "conv_tc3_kernel<16> (reg2d conv2 at stage 4: 16 -> 16 channels, 3x3x3, %d voxels)" % (vox[0] * vox[1] * vox[2] * vox[3]),
+                   "bound": "tensor", "achieved": flops / (t * 1e-3) / 1e12, "peak": tf_peak[0], "unit": "TFLOP/s",
+                   "frac": flops / (t * 1e-3) / 1e12 / tf_peak[0], "peak_source": tf_peak[1], "us": t * 1e3,
+                   "algorithmic_flops": flops,
+                   "note": "fp32-faithful conv flops; the kernel issues 6 bf16 products per fp32 product (3 MMAs of N = 48/32/16 per tap and "
+                           "16 channels) and is bound by the 4 KB A-operand fetch of each M128 x K16 MMA, not by the multipliers "
+                           "(profiles/r01_conv_tc3_ncu.md)", "traffic": None}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import mvster_oracle as oracle
@@ -366,7 +409,7 @@ def main():
                 "tc_kernel_gen": model.tc_kernel_gen, "cuda_graph": bool(model.use_cuda_graph) and P == 1}),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 2 * B * H * W * 4},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tc, "cpu_baseline": cpu_base,
         }))
     if world > 1:
         dist.destroy_process_group()

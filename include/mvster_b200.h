@@ -135,7 +135,7 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
 /* Generation 3 of the tensor-core layer (conv_tc3.cu): persistent kernel, error-compensated BF16 (three bf16 terms per
  * fp32 operand, six products in three MMAs per 16 channels: fp32-faithful, dropped terms <= 2^-24 relative), staged halo
  * tiles addressed through a per-layer stage/tap plan.  Replaces ConvBnReLU3D / ConvBnReLU (mvs4net_utils.py:116-123,
- * :100-113 after BN folding) for:  stride 1, k in {1,3}, kd in {1,3};  stride (1,2,2), k in {3,5}, kd = 1 (pad = k/2).
+ * :224-251 `Conv2d` after BN folding) for:  stride 1, k in {1,3}, kd in {1,3};  stride (1,2,2), k in {3,5}, kd = 1 (pad = k/2).
  * Cin in {4,8,16,32,64}, Cout in {8,16,32,64}.  x [B][D][H][W][Cin] -> y [B][D][Ho][Wo][Cout], Ho = (H-1)/stride + 1.
  * w_packed: one 96*max(Cout,16)-byte slab per (stage, tap) in the order mvster_conv_tc3_plan reports (slabs[i] =
  * {kz, ky, kx, first input channel}); slab = [2 K-halves][w1 | w2 | w3 rows of max(Cout,16)][8 bf16] over 16 input
@@ -148,7 +148,7 @@ int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias,
                         mvster_stream_t stream);
 
 /* Transposed convolution on the same kernel: kernel (1,3,3), stride (1,2,2), padding 1, output padding 1 (Deconv3d after BN
- * folding, mvs4net_utils.py:126-145, :893-897) computed as a 2x2 stride-1 convolution on the input grid whose N columns are the
+ * folding: the ConvTranspose3d + BN + ReLU sequences of reg2d, mvs4net_utils.py:885-898) computed as a 2x2 stride-1 convolution on the input grid whose N columns are the
  * output parity classes [class (py,px)][Cout], scattered depth-to-space by the epilogue.  x [B][D][H][W][Cin] ->
  * y [B][D][2H][2W][Cout] (+ skip, same shape).  rows = -1: all four classes in one launch (needs 4*Cout <= 64); rows = 0 / 1:
  * only output rows of that parity (2*Cout <= 64), two launches cover the layer.  Cin in {16,32,64}, Cout in {8,16,32}.
