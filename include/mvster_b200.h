@@ -216,8 +216,14 @@ int mvster_fpn_merge_f32(const float* top, const float* lateral, const float* w,
  * Cin in {16,32,64}; Cout in {8,16,32,64} or 68..80 (N padded to 80).  w_packed = pack_tc2_weights([1][Cin][Cout]). */
 int mvster_pointwise_tc2_f32(const float* x, const float* w_packed, const float* bias, float* y,
                              int N, int H, int W, int Cin, int Cout, int relu, int npass, mvster_stream_t stream);
+/* Point-wise convolution on the generation-3 kernel whose output channel blocks go to separate tensors: channels
+ * [j*block, (j+1)*block) -> [N][H][W][block] at y + j*block_stride_floats (no bias / relu).  Cin in {16,32,64}, Cout in
+ * {8,16,32,64}; w_packed = packing.pack_tc3_weights([1][Cin][Cout], 1, 1, 1).  Used to produce the per-tap planes of U below. */
+int mvster_pointwise_tc3_blocks_f32(const float* x, const void* w_packed, float* y, int N, int H, int W, int Cin, int Cout,
+                                    int block, long long block_stride_floats, mvster_stream_t stream);
 /* Last pyramid level fused (mvs4net_utils.py:485-486, stage4 = out4(up2(top2) + inner3(c0))) without forming the
- * 64-channel full-resolution map: U [N][H/2][W/2][u_channels >= 72] = per-tap 1x1 conv of top2 (channels tap*8+o),
+ * 64-channel full-resolution map: U = per-tap 1x1 conv of top2, either interleaved [N][H/2][W/2][u_channels >= 72] (channels
+ * tap*8+o) or, with u_channels == 8, planar [9][N][H/2][W/2][8];
  * c0 [N][H][W][8], w_comp [9][8][8] = W4[tap] Wi3, b_tap [9][8] = W4[tap] bi3  ->  out [N][H][W][8]. */
 int mvster_fpn_out4_gather_f32(const float* U, int u_channels, const float* c0, const float* w_comp, const float* b_tap,
                                float* out, int N, int H, int W, mvster_stream_t stream);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "mvster_conv_tc3_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), _i]),
     "mvster_conv_tc3_packed_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "mvster_conv_tc3_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_pointwise_tc3_blocks_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.c_longlong, _p]),
     "mvster_conv2d_nhwc_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_conv_first_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "mvster_fpn_merge_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

@@ -49,8 +49,22 @@ struct Args {
     const uint8_t* w;
     const float* bias; const float* skip; float* y;
     int D, Ho, Wo, cout, relu, sx, nstage, T, tiles_x, tiles_per_plane, groups_per_plane, total_groups, zero_a;
-    int ncls, py0;  // transposed conv: ncls output parity classes of Cout channels side by side along N (1 = plain conv)
+    // epilogue addressing (see there): ncls column blocks of Cout channels; up = 2 for the depth-to-space scatter of a transposed conv
+    int ncls, py0, up, lg_cout, cls_a, cls_b;
 };
+
+// plain / planar-block / depth-to-space output addressing of a launch; false if an offset would not fit 32 bits
+static bool set_output_mode(Args& a, int ncls, int py0, bool d2s, long long block_stride) {
+    a.ncls = ncls; a.py0 = py0; a.up = d2s ? 2 : 1;
+    a.lg_cout = 0;
+    while ((1 << a.lg_cout) < a.cout) ++a.lg_cout;
+    long long ca = 0, cb = 0;
+    if (d2s) { ca = 2ll * a.Wo * a.cout; cb = a.cout; }
+    else if (ncls > 1) { ca = 2 * block_stride; cb = block_stride; }
+    if ((1 << a.lg_cout) != a.cout || ca * (ncls / 2 + 1) >= (1ll << 31)) return false;
+    a.cls_a = (int)ca; a.cls_b = (int)cb;
+    return true;
+}
 
 template <int NC>
 struct Cfg {
@@ -271,16 +285,19 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
             for (int t = 0; t < Tg; ++t) {
                 const int ti = tile0 + t, yy = (ti / a.tiles_x) * TH + r / TW, xx = (ti % a.tiles_x) * TW + r % TW;
                 const bool ok = yy < a.Ho && xx < a.Wo;
-                const long long off = (((long long)plane * a.Ho + yy) * a.Wo + xx) * a.cout;
                 const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)(t * 3 * NC);
                 const int ncol = a.ncls * a.cout;
-                // plain conv: column = output channel.  Transposed conv (depth-to-space): column = class * Cout + channel,
-                // class (py, px) of input pixel (yy, xx) is output pixel (2 yy + py, 2 xx + px)
-                auto out_offset = [&](int c, int& ch) -> long long {
-                    if (a.ncls == 1) { ch = c; return off + c; }
-                    const int cls = c / a.cout;
-                    ch = c - cls * a.cout;
-                    return (((long long)plane * (2 * a.Ho) + 2 * yy + a.py0 + (cls >> 1)) * (2 * a.Wo) + 2 * xx + (cls & 1)) * a.cout + ch;
+                // Column c = class * Cout + channel (Cout a power of two).  Plain conv: one class.  Transposed conv (depth-to-space,
+                // up = 2): class (py, px) of input pixel (yy, xx) is output pixel (2 yy + py, 2 xx + px): cls_a = one output row,
+                // cls_b = one output pixel.  Planar blocks: class j is its own tensor, cls_b = its distance, cls_a = 2 cls_b.
+                // One 64-bit base per tile and pixel; everything per column is 32-bit.
+                const long long base = (((long long)plane * (a.up * a.Ho) + a.up * yy + a.py0) * (a.up * a.Wo) + a.up * xx) * a.cout;
+                float* const yb = a.y + base;
+                const float* const sb = a.skip + base;
+                auto out_offset = [&](int c, int& ch) -> int {
+                    const int cls = c >> a.lg_cout;
+                    ch = c & (a.cout - 1);
+                    return (cls >> 1) * a.cls_a + (cls & 1) * a.cls_b + ch;
                 };
                 constexpr int RC = NC < 32 ? NC : 32;  // columns per round: their skip values are fetched up front, all in flight
 #pragma unroll
@@ -290,7 +307,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
 #pragma unroll
                         for (int jg = 0; jg < RC / 4; ++jg) {
                             int ch;
-                            if (cb + 4 * jg < ncol) sk[jg] = __ldg(reinterpret_cast<const float4*>(a.skip + out_offset(cb + 4 * jg, ch)));
+                            if (cb + 4 * jg < ncol) sk[jg] = __ldg(reinterpret_cast<const float4*>(sb + out_offset(cb + 4 * jg, ch)));
                         }
                     }
 #pragma unroll
@@ -305,7 +322,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                             for (int j = 0; j < 16; j += 4) {
                                 if (c0 + j >= ncol) break;
                                 int ch;
-                                const long long o_off = out_offset(c0 + j, ch);
+                                const int o_off = out_offset(c0 + j, ch);
                                 float o[4];
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
@@ -317,7 +334,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                                     const float4 s4 = sk[(c0 - cb + j) / 4];
                                     o[0] += s4.x; o[1] += s4.y; o[2] += s4.z; o[3] += s4.w;
                                 }
-                                *reinterpret_cast<float4*>(a.y + o_off) = make_float4(o[0], o[1], o[2], o[3]);
+                                *reinterpret_cast<float4*>(yb + o_off) = make_float4(o[0], o[1], o[2], o[3]);
                             }
                         }
                     }
@@ -442,9 +459,11 @@ extern "C" size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k,
     return (size_t)tc3::build_plan(Cin, kd, k, stride_hw, nullptr, nullptr) * 96 * NC;
 }
 
-extern "C" int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
-                                   int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
-                                   mvster_stream_t stream) {
+// block == 0: y [B][D][Ho][Wo][Cout].  block > 0 (divides Cout): output channels [j*block, (j+1)*block) go to a separate
+// tensor [B][D][Ho][Wo][block] at y + j*block_stride (floats).
+static int conv_tc3_run(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
+                        int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
+                        int block, long long block_stride, mvster_stream_t stream) {
     using namespace mvster::tc3;
     MVSTER_REQUIRE(x && w_packed && y, "mvster_conv_tc3_f32: null pointer");
     MVSTER_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "mvster_conv_tc3_f32: bad shape");
@@ -479,13 +498,29 @@ extern "C" int mvster_conv_tc3_f32(const float* x, const void* w_packed, const f
     a.tiles_x = ceil_div(a.Wo, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(a.Ho, TH);
     a.zero_a = Cin < 16;
-    a.ncls = 1; a.py0 = 0;
+    const bool blocks = block > 0 && block < Cout;
+    if (blocks) a.cout = block;
+    MVSTER_REQUIRE(set_output_mode(a, blocks ? Cout / block : 1, 0, false, block_stride),
+                   "mvster_conv_tc3_f32: output addressing does not fit (Cout block %d must be a power of two, blocks < 2^31 floats apart)", a.cout);
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
     cudaStream_t st = (cudaStream_t)stream;
     const int NC = Cout < 16 ? 16 : Cout;
     if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st);
     if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st);
     return launch<64>(xm, plan, a, total_tiles, sms, st);
+}
+
+extern "C" int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
+                                   int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
+                                   mvster_stream_t stream) {
+    return conv_tc3_run(x, w_packed, bias, skip, y, B, D, H, W, Cin, Cout, kd, k, stride_hw, relu, 0, 0, stream);
+}
+
+extern "C" int mvster_pointwise_tc3_blocks_f32(const float* x, const void* w_packed, float* y, int N, int H, int W, int Cin, int Cout,
+                                               int block, long long block_stride_floats, mvster_stream_t stream) {
+    MVSTER_REQUIRE(block >= 4 && block % 4 == 0 && Cout % block == 0 && (Cout == block || block_stride_floats % 4 == 0),
+                   "mvster_pointwise_tc3_blocks_f32: bad block %d for Cout %d", block, Cout);
+    return conv_tc3_run(x, w_packed, nullptr, nullptr, y, N, 1, H, W, Cin, Cout, 1, 1, 1, 0, block, block_stride_floats, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -550,7 +585,7 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
     a.tiles_x = ceil_div(W, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
     a.zero_a = 0;
-    a.ncls = deconv_ncls(rows); a.py0 = rows == 1 ? 1 : 0;
+    MVSTER_REQUIRE(set_output_mode(a, deconv_ncls(rows), rows == 1 ? 1 : 0, true, 0), "mvster_deconv_tc3_f32: output row pitch does not fit 32 bits");
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
     cudaStream_t st = (cudaStream_t)stream;
     const int NC = a.ncls * Cout;

@@ -224,7 +224,10 @@ extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, cons
 // pixel become 1152 + 288 + 576; same result up to fp32 summation order.
 namespace mvster {
 
-__global__ void __launch_bounds__(128) fpn_out4_gather_kernel(const float* __restrict__ U, int UC, const float* __restrict__ c0,
+// U addressing: pixel pitch UC floats, tap t at + t * tap_stride floats (interleaved [..][72]: UC = 72, tap_stride = 8;
+// planar [9][N][Hc][Wc][8]: UC = 8, tap_stride = N*Hc*Wc*8 - consecutive half-resolution pixels of one tap are then contiguous,
+// so a warp's bilinear samples fall into 4-5 cache lines instead of one line per lane pair)
+__global__ void __launch_bounds__(128) fpn_out4_gather_kernel(const float* __restrict__ U, int UC, long long tap_stride, const float* __restrict__ c0,
                                                               const float* __restrict__ wc, const float* __restrict__ bt,
                                                               float* __restrict__ out, int N, int H, int W) {
     __shared__ __align__(16) float wc_s[9 * 8 * 8 + 9 * 8];
@@ -272,10 +275,11 @@ __global__ void __launch_bounds__(128) fpn_out4_gather_kernel(const float* __res
                 for (int o = 0; o < 8; ++o) acc[o] = fmaf(cv[c], wt[c * 8 + o], acc[o]);
             // (b) top-down path: bilinear sample of U_tap (8 channels at half resolution) at the fine position p + tap
             const float ly1 = wy1[ky], ly0 = 1.f - ly1, lx1 = wx1[kx], lx0 = 1.f - lx1;
-            const float* u00 = Ub + ((long long)ry0[ky] * Wc + rx0[kx]) * UC + tap * 8;
-            const float* u01 = Ub + ((long long)ry0[ky] * Wc + rx1[kx]) * UC + tap * 8;
-            const float* u10 = Ub + ((long long)ry1[ky] * Wc + rx0[kx]) * UC + tap * 8;
-            const float* u11 = Ub + ((long long)ry1[ky] * Wc + rx1[kx]) * UC + tap * 8;
+            const float* ut = Ub + tap * tap_stride;
+            const float* u00 = ut + ((long long)ry0[ky] * Wc + rx0[kx]) * UC;
+            const float* u01 = ut + ((long long)ry0[ky] * Wc + rx1[kx]) * UC;
+            const float* u10 = ut + ((long long)ry1[ky] * Wc + rx0[kx]) * UC;
+            const float* u11 = ut + ((long long)ry1[ky] * Wc + rx1[kx]) * UC;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const float4 a00 = __ldg(reinterpret_cast<const float4*>(u00) + h), a01 = __ldg(reinterpret_cast<const float4*>(u01) + h);
@@ -298,8 +302,10 @@ extern "C" int mvster_fpn_out4_gather_f32(const float* U, int u_channels, const 
                                           float* out, int N, int H, int W, mvster_stream_t stream) {
     MVSTER_REQUIRE(U && c0 && w_comp && b_tap && out, "mvster_fpn_out4_gather_f32: null pointer");
     MVSTER_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mvster_fpn_out4_gather_f32: H,W must be even");
-    MVSTER_REQUIRE(u_channels >= 72 && u_channels % 4 == 0, "mvster_fpn_out4_gather_f32: U needs >= 72 channels (9 taps x 8)");
+    MVSTER_REQUIRE(u_channels == 8 || (u_channels >= 72 && u_channels % 4 == 0),
+                   "mvster_fpn_out4_gather_f32: U is [..][>= 72 channels] (9 taps x 8 interleaved) or, with u_channels = 8, planar [9][N][H/2][W/2][8]");
     const long long n = (long long)N * H * W;
-    mvster::fpn_out4_gather_kernel<<<mvster::ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(U, u_channels, c0, w_comp, b_tap, out, N, H, W);
+    const long long tap_stride = u_channels == 8 ? (long long)N * (H / 2) * (W / 2) * 8 : 8;
+    mvster::fpn_out4_gather_kernel<<<mvster::ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(U, u_channels, tap_stride, c0, w_comp, b_tap, out, N, H, W);
     return mvster::check_launch("fpn_out4_gather_kernel");
 }

@@ -64,6 +64,9 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
     u_w = w4.permute(1, 0, 2).reshape(1, 64, 72).float().contiguous()            # U channel = tap*8 + o
     out["out4.u_w"] = u_w
     out["out4.u_tc"] = packing.pack_tc2_weights(u_w, 3)
+    # generation 3: taps 0..7 as one 64-column GEMM, tap 8 as an 8-column one, each tap's 8 channels written as its own plane
+    out["out4.u_tc3a"] = packing.pack_tc3_weights(u_w[:, :, :64].contiguous(), 1, 1, 1)
+    out["out4.u_tc3b"] = packing.pack_tc3_weights(u_w[:, :, 64:].contiguous(), 1, 1, 1)
     return out
 
 
@@ -137,18 +140,27 @@ def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bo
     top = _merge(top, c1, wts["inner2.w"], wts["inner2.b"])
     out["stage3"] = _conv3x3(top, wts, "out3", False, npass, gen)
     if fused_last:
-        out["stage4"] = _fused_last_level(wts, top, c0, npass)
+        out["stage4"] = _fused_last_level(wts, top, c0, npass, gen)
     else:  # literal form: materialise the 64-channel full-resolution map, then the 3x3 conv
         top = _merge(top, c0, wts["inner3.w"], wts["inner3.b"])
         out["stage4"] = _conv3x3(top, wts, "out4", False, npass, gen)
     return out
 
 
-def _fused_last_level(wts: Dict[str, Tensor], top2: Tensor, c0: Tensor, npass: int) -> Tensor:
+def _fused_last_level(wts: Dict[str, Tensor], top2: Tensor, c0: Tensor, npass: int, gen: int = 2) -> Tensor:
     """stage4 = out4(up2(top2) + inner3(c0)) = sum_tap [ up2(W4[tap].top2) + (W4[tap] Wi3).c0 + W4[tap].bi3 ](p + tap)."""
     N, h, w, _ = top2.shape
     lib = _lib.load()
-    if npass:
+    uc = 72
+    if npass and gen == 3:  # U planar [9][N][h][w][8]: two point-wise GEMMs on the persistent 3 x bf16 kernel
+        plane = N * h * w * 8
+        U = torch.empty((9, N, h, w, 8), device=top2.device, dtype=torch.float32)
+        _lib.check(lib.mvster_pointwise_tc3_blocks_f32(capi._ptr(top2), capi._ptr(wts["out4.u_tc3a"]), capi._ptr(U), N, h, w, 64, 64, 8,
+                                                       plane, capi._stream()), "mvster_pointwise_tc3_blocks_f32")
+        _lib.check(lib.mvster_pointwise_tc3_blocks_f32(capi._ptr(top2), capi._ptr(wts["out4.u_tc3b"]), capi._ptr(U[8]), N, h, w, 64, 8, 8,
+                                                       plane, capi._stream()), "mvster_pointwise_tc3_blocks_f32")
+        uc = 8
+    elif npass:
         tc = wts["out4.u_tc"]
         U = torch.empty((N, h, w, 72), device=top2.device, dtype=torch.float32)
         _lib.check(lib.mvster_pointwise_tc2_f32(capi._ptr(top2), capi._ptr(tc if npass == 3 else tc[:tc.numel() // 2].contiguous()), None,
@@ -156,6 +168,6 @@ def _fused_last_level(wts: Dict[str, Tensor], top2: Tensor, c0: Tensor, npass: i
     else:
         U = _conv2d(top2, wts["out4.u_w"], None, 1, 1, False)
     out = torch.empty((N, 2 * h, 2 * w, 8), device=top2.device, dtype=torch.float32)
-    _lib.check(lib.mvster_fpn_out4_gather_f32(capi._ptr(U), 72, capi._ptr(c0), capi._ptr(wts["out4.wc"]), capi._ptr(wts["out4.bt"]),
+    _lib.check(lib.mvster_fpn_out4_gather_f32(capi._ptr(U), uc, capi._ptr(c0), capi._ptr(wts["out4.wc"]), capi._ptr(wts["out4.bt"]),
                                               capi._ptr(out), N, 2 * h, 2 * w, capi._stream()), "mvster_fpn_out4_gather_f32")
     return out
