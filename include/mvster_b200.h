@@ -137,9 +137,11 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
  * tiles addressed through a per-layer stage/tap plan.  Replaces ConvBnReLU3D / ConvBnReLU (mvs4net_utils.py:116-123,
  * :224-251 `Conv2d` after BN folding) for:  stride 1, k in {1,3}, kd in {1,3};  stride (1,2,2), k in {3,5}, kd = 1 (pad = k/2).
  * Cin in {4,8,16,32,64}, Cout in {8,16,32,64}.  x [B][D][H][W][Cin] -> y [B][D][Ho][Wo][Cout], Ho = (H-1)/stride + 1.
- * w_packed: one 96*max(Cout,16)-byte slab per (stage, tap) in the order mvster_conv_tc3_plan reports (slabs[i] =
- * {kz, ky, kx, first input channel}); slab = [2 K-halves][w1 | w2 | w3 rows of max(Cout,16)][8 bf16] over 16 input
- * channels (zero padded) - packing.pack_tc3_weights.  x and w_packed 16-byte aligned. */
+ * w_packed: one 96*max(Cout,16)-byte slab per MMA slot in the order mvster_conv_tc3_plan reports (slabs[i], 6 ints each =
+ * {kz, ky, kx, first input channel, ky2, kx2}; max_slabs counts slabs); slab = [2 K-halves][w1 | w2 | w3 rows of
+ * max(Cout,16)][8 bf16].  Its 16 K rows are 16 input channels of tap (ky,kx) (zero padded) or, for Cin <= 8, 8 channels of
+ * tap (ky,kx) then 8 channels of tap (ky2,kx2) (two taps per MMA; -1,-1 = none) - packing.pack_tc3_weights.
+ * x and w_packed 16-byte aligned. */
 int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw);
 int mvster_conv_tc3_plan(int Cin, int kd, int k, int stride_hw, int* slabs, int max_slabs);
 size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int stride_hw);

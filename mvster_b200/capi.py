@@ -199,15 +199,16 @@ def conv3d_tc2(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, k
 
 
 def conv_tc3_plan(cin: int, kd: int, k: int, stride: int) -> List[tuple]:
-    """(kz, ky, kx, first input channel) of every weight slab of a generation-3 layer, in the order the kernel streams them.
+    """(kz, ky, kx, first input channel, ky2, kx2) of every weight slab (= MMA slot) of a generation-3 layer, in the order the
+    kernel streams them; (ky2, kx2) is the second tap sharing the MMA of an <= 8-channel layer, else (-1, -1).
     Pure host logic of the library (no GPU needed)."""
     lib = _lib.load()
     n = lib.mvster_conv_tc3_plan(cin, kd, k, stride, None, 0)
     if n < 0:
         raise ValueError(f"conv_tc3: unsupported layer Cin={cin} kd={kd} k={k} stride={stride}")
-    buf = (C.c_int * (4 * n))()
+    buf = (C.c_int * (6 * n))()
     lib.mvster_conv_tc3_plan(cin, kd, k, stride, buf, n)
-    return [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
+    return [tuple(buf[6 * i:6 * i + 6]) for i in range(n)]
 
 
 def conv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, k: int, stride: int = 1, relu: bool = True,

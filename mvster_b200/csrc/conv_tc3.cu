@@ -34,6 +34,7 @@ constexpr int PLANE = QBYTES;                // bf16 operand plane = [180 pixels
 constexpr int A_SPLIT = 2 * PLANE;           // one bf16 term of one tile-stage: 2 channel octets
 constexpr int A_BYTES = 3 * A_SPLIT;         // a1 | a2 | a3
 constexpr int NCONV = 256;                 // converter threads (8 warps: one warp per SM sub-partition was latency-bound)
+constexpr int CTEAM = NCONV / 2;           // ... in two teams that take alternate tile-stages
 constexpr int THREADS = 96 + NCONV + 128;
 constexpr int MAX_STAGES = 16, MAX_TAPS = 9;
 constexpr int NF = 4, NB = 10;
@@ -43,8 +44,13 @@ struct Stage {
 };
 struct Plan {
     Stage st[MAX_STAGES];
-    unsigned char a_off[MAX_STAGES][MAX_TAPS + 3];  // (halo row * 10 + halo column) of each tap = descriptor shift in 16-byte units
+    // Per MMA slot of a stage, the low descriptor word to add to the tile's base: start shift = halo row * 10 + halo column of the
+    // tap (16-byte units, bits 0-13) | LBO (bits 16-29).  LBO = distance between the two 8-channel K halves of the MMA: the next
+    // channel-octet plane for Cin >= 16; for Cin <= 8 the second K half is a SECOND TAP of the same plane (LBO = its shift minus
+    // the first tap's), so a 3x3 conv on 8 channels needs 5 MMA slots instead of 9.
+    uint32_t a_desc[MAX_STAGES][MAX_TAPS];
 };
+__host__ inline uint32_t tap_desc(int off, int lbo) { return (uint32_t)off | ((uint32_t)lbo << 16); }
 struct Args {
     const uint8_t* w;
     const float* bias; const float* skip; float* y;
@@ -68,8 +74,8 @@ static bool set_output_mode(Args& a, int ncls, int py0, bool d2s, long long bloc
 
 template <int NC>
 struct Cfg {
-    static constexpr int TMAX = 64 / NC;                    // tiles accumulated side by side: 3*NC*TMAX = 192 TMEM columns per set
-    static constexpr int NA = NC == 64 ? 6 : 8;             // bf16 operand ring (tile-stages)
+    static constexpr int TMAX = NC > 64 ? 1 : 64 / NC;      // tiles accumulated side by side: 3*NC*TMAX <= 240 TMEM columns per set
+    static constexpr int NA = NC >= 64 ? 6 : 8;             // bf16 operand ring (tile-stages)
     static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 bf16]
     static constexpr int SMEM = 1024 + NF * F_BYTES + NA * A_BYTES + NB * B_BYTES + 512;
 };
@@ -110,8 +116,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NF; ++s) { mbar_init(F_FULL(s), 1); mbar_init(F_EMPTY(s), NCONV); }
-        for (int s = 0; s < C::NA; ++s) { mbar_init(A_FULL(s), NCONV); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < NF; ++s) { mbar_init(F_FULL(s), 1); mbar_init(F_EMPTY(s), CTEAM); }
+        for (int s = 0; s < C::NA; ++s) { mbar_init(A_FULL(s), CTEAM); mbar_init(A_EMPTY(s), 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(ACC_FULL(s), 1); mbar_init(ACC_EMPTY(s), 128); }
         fence_barrier_init();
@@ -183,7 +189,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
             constexpr uint32_t ID3 = idesc_bf16_m128(3 * NC), ID2 = idesc_bf16_m128(2 * NC), ID1 = idesc_bf16_m128(NC);
             // descriptor = (hi << 32) | lo; lo = start address >> 4 | LBO >> 4 << 16 (taps / splits / slots only move the address)
             constexpr uint64_t A_HI = (uint64_t)((HW_ * 16) >> 4) | (1ull << 14), B_HI = (uint64_t)(128 >> 4) | (1ull << 14);
-            constexpr uint32_t A_LBO = (uint32_t)(PLANE >> 4) << 16, B_LBO = (uint32_t)((3 * NC * 16) >> 4) << 16;
+            constexpr uint32_t B_LBO = (uint32_t)((3 * NC * 16) >> 4) << 16;  // the A operand's LBO comes with each tap (plan.a_desc)
             uint32_t a_slot = 0, a_par = 0, b_slot = 0, b_par = 0, gc = 0;
             for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x, ++gc) {
                 MVSTER_TC3_GROUP_HEAD
@@ -201,7 +207,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         if (t < Tg) {
                             mbar_wait(A_FULL(a_slot), a_par);
                             aslot[t] = a_slot;
-                            alo[t] = (((a_base + a_slot * A_BYTES) & 0x3FFFFu) >> 4) | A_LBO;
+                            alo[t] = ((a_base + a_slot * A_BYTES) & 0x3FFFFu) >> 4;
                             if (++a_slot == C::NA) { a_slot = 0; a_par ^= 1; }
                         }
                     tc_fence_after();
@@ -209,7 +215,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         mbar_wait(B_FULL(b_slot), b_par);
                         tc_fence_after();
                         const uint64_t bd = (B_HI << 32) | ((((b_base + b_slot * C::B_BYTES) & 0x3FFFFu) >> 4) | B_LBO);
-                        const uint32_t shift = plan.a_off[s][tap];
+                        const uint32_t shift = plan.a_desc[s][tap];  // start shift (bits 0-13) + LBO (bits 16-29): one add per MMA
 #pragma unroll
                         for (int t = 0; t < C::TMAX; ++t)
                             if (t < Tg) {
@@ -231,7 +237,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
         }
     } else if (warp < 3 + NCONV / 32) {
         // ------------------------------------------------------------------ converters: fp32 halo tile -> a1 | a2 | a3 (bf16)
-        const int tid = threadIdx.x - 96;
+        // Two teams of CTEAM threads take alternate tile-stages, so one team's barrier waits and proxy fence overlap the other
+        // team's conversion (with all 8 warps on one tile-stage the role cost ~1100 cycles per tile-stage whatever the tap count).
+        const int team = (threadIdx.x - 96) / CTEAM, tid = (threadIdx.x - 96) % CTEAM;
         uint32_t u = 0;
         for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
             MVSTER_TC3_GROUP_HEAD
@@ -239,22 +247,23 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                 if (MVSTER_TC3_STAGE_SKIP(s)) continue;
                 const int nq = plan.st[s].nq, items = HPIX * nq, qsh = nq >> 1;  // nq in {1,2,4}: pixel = item >> qsh
                 for (int t = 0; t < Tg; ++t, ++u) {
+                    if ((int)(u & 1) != team) continue;
                     const uint32_t fs = u % NF, as = u % C::NA;
                     mbar_wait(F_FULL(fs), (u / NF) & 1);
                     mbar_wait(A_EMPTY(as), ((u / C::NA) & 1) ^ 1);
                     const uint8_t* F = smem_raw + (f_base + fs * F_BYTES - raw);
                     uint8_t* A = smem_raw + (a_base + as * A_BYTES - raw);
-                    // item = one channel quad of one halo pixel = 16 contiguous bytes of F; <= 3 items per thread, all loads first
-                    constexpr int IT = (HPIX * 4 + NCONV - 1) / NCONV;
+                    // item = one channel quad of one halo pixel = 16 contiguous bytes of F; <= 6 items per thread, all loads first
+                    constexpr int IT = (HPIX * 4 + CTEAM - 1) / CTEAM;
                     float4 v[IT];
 #pragma unroll
                     for (int k = 0; k < IT; ++k) {
-                        const int i = tid + k * NCONV;
+                        const int i = tid + k * CTEAM;
                         if (i < items) v[k] = *reinterpret_cast<const float4*>(F + i * 16);
                     }
 #pragma unroll
                     for (int k = 0; k < IT; ++k) {
-                        const int i = tid + k * NCONV;
+                        const int i = tid + k * CTEAM;
                         if (i < items) {
                             const int p = i >> qsh, q = i & (nq - 1);
                             uint2 t1, t2, t3;
@@ -299,7 +308,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     ch = c & (a.cout - 1);
                     return (cls >> 1) * a.cls_a + (cls & 1) * a.cls_b + ch;
                 };
-                constexpr int RC = NC < 32 ? NC : 32;  // columns per round: their skip values are fetched up front, all in flight
+                constexpr int RC = NC % 32 ? 16 : 32;  // columns per round: their skip values are fetched up front, all in flight
 #pragma unroll
                 for (int cb = 0; cb < NC; cb += RC) {
                     float4 sk[RC / 4];
@@ -370,17 +379,20 @@ static EncodeTiledFn encode_fn() {
 
 static bool supported(int Cin, int Cout, int kd, int k, int s) {
     const bool cin_ok = Cin == 4 || Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64;
-    const bool cout_ok = Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64;
-    const bool shape_ok = (s == 1 && (k == 1 || k == 3) && (kd == 1 || kd == 3)) || (s == 2 && (k == 3 || k == 5) && kd == 1);
+    const bool cout_ok = Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || (Cout == 72 && k == 1 && kd == 1);  // 72: N padded to 80
+    const bool shape_ok =(s == 1 && (k == 1 || k == 3) && (kd == 1 || kd == 3)) || (s == 2 && (k == 3 || k == 5) && kd == 1);
     return cin_ok && cout_ok && shape_ok && kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16) <= MAX_STAGES;
 }
 
 // Stage/tap enumeration shared by the launcher and by the host-side weight packer (mvster_conv_tc3_plan).
 // Stride 2: input row 2y + ky - pad = 2 (y + m) + py with parity class py in {0,1}; class (py, px) is staged as its own halo
 // tile (TMA element strides 2, origin 2*y0 - 2 + py) and tap ky lands on halo row m + 1.
-static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[4]) {
+// slabs[i] = {kz, ky, kx, first input channel, ky2, kx2}: the weights of MMA slot i; (ky2, kx2) = the tap in the second K half
+// when two taps of an <= 8-channel layer share one MMA, else (-1, -1).
+static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[6]) {
     int ns = 0, nslab = 0;
     const int kch = (Cin + 15) / 16, pz = kd / 2, pad = k / 2, npar = s == 2 ? 2 : 1;
+    const bool pair = Cin <= 8;
     for (int kz = 0; kz < kd; ++kz)
         for (int py = 0; py < npar; ++py)
             for (int px = 0; px < npar; ++px)
@@ -393,7 +405,7 @@ static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[4]
                     S.oy = (short)(s == 2 ? -2 + py : -1);
                     S.slab0 = (short)nslab;
                     S.pad = 0;
-                    int nt = 0;
+                    int nt = 0, toff[25], tky[25], tkx[25];  // the stage's taps, halo offsets ascending
                     for (int ky = 0; ky < k; ++ky)
                         for (int kx = 0; kx < k; ++kx) {
                             int hy, hx;
@@ -404,11 +416,24 @@ static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[4]
                                 if (cy != py || cx != px) continue;
                                 hy = (oy - cy) / 2 + 1; hx = (ox - cx) / 2 + 1;
                             }
-                            if (plan) plan->a_off[ns][nt] = (unsigned char)(hy * HW_ + hx);
-                            if (slabs) { slabs[nslab][0] = kz; slabs[nslab][1] = ky; slabs[nslab][2] = kx; slabs[nslab][3] = kc * 16; }
-                            ++nt; ++nslab;
+                            toff[nt] = hy * HW_ + hx; tky[nt] = ky; tkx[nt] = kx;
+                            ++nt;
                         }
-                    S.ntap = (short)nt;
+                    int nslot = 0;
+                    for (int t = 0; t < nt; ++nslot, ++nslab) {
+                        // paired layers with an odd tap count: the FIRST slot is the single one, so that its second K half
+                        // (LBO = 1: the next pixel, against zero weights) still reads converted data and never past the tile
+                        const bool two = pair && !(t == 0 && (nt & 1));
+                        // LBO: next channel-octet plane, or (paired) the second tap relative to the first
+                        const int lbo = pair ? (two ? toff[t + 1] - toff[t] : 1) : (PLANE >> 4);
+                        if (plan) plan->a_desc[ns][nslot] = tap_desc(toff[t], lbo);
+                        if (slabs) {
+                            slabs[nslab][0] = kz; slabs[nslab][1] = tky[t]; slabs[nslab][2] = tkx[t]; slabs[nslab][3] = kc * 16;
+                            slabs[nslab][4] = two ? tky[t + 1] : -1; slabs[nslab][5] = two ? tkx[t + 1] : -1;
+                        }
+                        t += two ? 2 : 1;
+                    }
+                    S.ntap = (short)nslot;
                     if (plan) plan->st[ns] = S;
                 }
     return nslab;
@@ -448,14 +473,14 @@ extern "C" int mvster_conv_tc3_plan(int Cin, int kd, int k, int stride_hw, int* 
     const int n = tc3::build_plan(Cin, kd, k, stride_hw, nullptr, nullptr);
     if (slabs) {
         if (n > max_slabs) return -1;
-        tc3::build_plan(Cin, kd, k, stride_hw, nullptr, reinterpret_cast<int(*)[4]>(slabs));
+        tc3::build_plan(Cin, kd, k, stride_hw, nullptr, reinterpret_cast<int(*)[6]>(slabs));
     }
     return n;
 }
 
 extern "C" size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int stride_hw) {
     if (!tc3::supported(Cin, Cout, kd, k, stride_hw)) return 0;
-    const int NC = Cout < 16 ? 16 : Cout;
+    const int NC = Cout < 16 ? 16 : (Cout > 64 ? 80 : Cout);
     return (size_t)tc3::build_plan(Cin, kd, k, stride_hw, nullptr, nullptr) * 96 * NC;
 }
 
@@ -497,16 +522,18 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     a.nstage = kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16);
     a.tiles_x = ceil_div(a.Wo, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(a.Ho, TH);
-    a.zero_a = Cin < 16;
+    a.zero_a = Cin < 8;  // Cin = 4: each 16-byte row holds 4 real channels, the other 4 must read as zero (Cin = 8 fills the one plane it reads)
     const bool blocks = block > 0 && block < Cout;
     if (blocks) a.cout = block;
     MVSTER_REQUIRE(set_output_mode(a, blocks ? Cout / block : 1, 0, false, block_stride),
                    "mvster_conv_tc3_f32: output addressing does not fit (Cout block %d must be a power of two, blocks < 2^31 floats apart)", a.cout);
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
     cudaStream_t st = (cudaStream_t)stream;
-    const int NC = Cout < 16 ? 16 : Cout;
+    MVSTER_REQUIRE(Cout <= 64 || blocks, "mvster_conv_tc3_f32: Cout = %d only as separate channel blocks", Cout);
+    const int NC = Cout < 16 ? 16 : (Cout > 64 ? 80 : Cout);
     if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st);
     if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 80) return launch<80>(xm, plan, a, total_tiles, sms, st);
     return launch<64>(xm, plan, a, total_tiles, sms, st);
 }
 
@@ -577,7 +604,7 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
         Stage S;
         S.c0 = (short)(kc * 16); S.nq = 4; S.ox = -1; S.oy = -1; S.dz = 0; S.ntap = (short)ntap; S.slab0 = (short)(kc * ntap); S.pad = 0;
         plan.st[kc] = S;
-        for (int t = 0; t < ntap; ++t) plan.a_off[kc][t] = (unsigned char)((t / 2 + 1) * HW_ + (t % 2 + 1));  // halo (1 + dy, 1 + dx)
+        for (int t = 0; t < ntap; ++t) plan.a_desc[kc][t] = tap_desc((t / 2 + 1) * HW_ + (t % 2 + 1), PLANE >> 4);  // halo (1 + dy, 1 + dx)
     }
     Args a;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;

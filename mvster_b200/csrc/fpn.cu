@@ -227,6 +227,19 @@ namespace mvster {
 // U addressing: pixel pitch UC floats, tap t at + t * tap_stride floats (interleaved [..][72]: UC = 72, tap_stride = 8;
 // planar [9][N][Hc][Wc][8]: UC = 8, tap_stride = N*Hc*Wc*8 - consecutive half-resolution pixels of one tap are then contiguous,
 // so a warp's bilinear samples fall into 4-5 cache lines instead of one line per lane pair)
+// eight consecutive floats with ONE 256-bit read-only load (32-byte aligned): half the L1 requests of two 128-bit loads
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ldg_f8(const float* p) {
+    unsigned long long q0, q1, q2, q3;
+    asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(p));
+    F8 r;
+    r.v[0] = __uint_as_float((unsigned)q0); r.v[1] = __uint_as_float((unsigned)(q0 >> 32));
+    r.v[2] = __uint_as_float((unsigned)q1); r.v[3] = __uint_as_float((unsigned)(q1 >> 32));
+    r.v[4] = __uint_as_float((unsigned)q2); r.v[5] = __uint_as_float((unsigned)(q2 >> 32));
+    r.v[6] = __uint_as_float((unsigned)q3); r.v[7] = __uint_as_float((unsigned)(q3 >> 32));
+    return r;
+}
+
 __global__ void __launch_bounds__(128) fpn_out4_gather_kernel(const float* __restrict__ U, int UC, long long tap_stride, const float* __restrict__ c0,
                                                               const float* __restrict__ wc, const float* __restrict__ bt,
                                                               float* __restrict__ out, int N, int H, int W) {
@@ -263,9 +276,8 @@ __global__ void __launch_bounds__(128) fpn_out4_gather_kernel(const float* __res
             if ((unsigned)(x + kx - 1) >= (unsigned)W) continue;
             const int tap = ky * 3 + kx;
             // (a) lateral path: composite 3x3 conv on c0 (+ the lateral bias seen through this tap)
-            const float4* pc = reinterpret_cast<const float4*>(cb + ((long long)(y + ky - 1) * W + (x + kx - 1)) * 8);
-            const float4 c_lo = __ldg(pc), c_hi = __ldg(pc + 1);
-            const float cv[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+            const F8 cpx = ldg_f8(cb + ((long long)(y + ky - 1) * W + (x + kx - 1)) * 8);
+            const float* cv = cpx.v;
             const float* wt = wc_s + tap * 64;
 #pragma unroll
             for (int o = 0; o < 8; ++o) acc[o] += wc_s[576 + tap * 8 + o];
@@ -280,15 +292,10 @@ __global__ void __launch_bounds__(128) fpn_out4_gather_kernel(const float* __res
             const float* u01 = ut + ((long long)ry0[ky] * Wc + rx1[kx]) * UC;
             const float* u10 = ut + ((long long)ry1[ky] * Wc + rx0[kx]) * UC;
             const float* u11 = ut + ((long long)ry1[ky] * Wc + rx1[kx]) * UC;
+            const F8 a00 = ldg_f8(u00), a01 = ldg_f8(u01), a10 = ldg_f8(u10), a11 = ldg_f8(u11);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float4 a00 = __ldg(reinterpret_cast<const float4*>(u00) + h), a01 = __ldg(reinterpret_cast<const float4*>(u01) + h);
-                const float4 a10 = __ldg(reinterpret_cast<const float4*>(u10) + h), a11 = __ldg(reinterpret_cast<const float4*>(u11) + h);
-                acc[4 * h + 0] += ly0 * (lx0 * a00.x + lx1 * a01.x) + ly1 * (lx0 * a10.x + lx1 * a11.x);
-                acc[4 * h + 1] += ly0 * (lx0 * a00.y + lx1 * a01.y) + ly1 * (lx0 * a10.y + lx1 * a11.y);
-                acc[4 * h + 2] += ly0 * (lx0 * a00.z + lx1 * a01.z) + ly1 * (lx0 * a10.z + lx1 * a11.z);
-                acc[4 * h + 3] += ly0 * (lx0 * a00.w + lx1 * a01.w) + ly1 * (lx0 * a10.w + lx1 * a11.w);
-            }
+            for (int o = 0; o < 8; ++o)
+                acc[o] += ly0 * (lx0 * a00.v[o] + lx1 * a01.v[o]) + ly1 * (lx0 * a10.v[o] + lx1 * a11.v[o]);
         }
     }
     float4* dst = reinterpret_cast<float4*>(out + v * 8);

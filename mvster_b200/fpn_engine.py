@@ -8,6 +8,7 @@ feature tensors the warp kernel consumes.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Mapping, Optional
 
 import torch
@@ -64,9 +65,8 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
     u_w = w4.permute(1, 0, 2).reshape(1, 64, 72).float().contiguous()            # U channel = tap*8 + o
     out["out4.u_w"] = u_w
     out["out4.u_tc"] = packing.pack_tc2_weights(u_w, 3)
-    # generation 3: taps 0..7 as one 64-column GEMM, tap 8 as an 8-column one, each tap's 8 channels written as its own plane
-    out["out4.u_tc3a"] = packing.pack_tc3_weights(u_w[:, :, :64].contiguous(), 1, 1, 1)
-    out["out4.u_tc3b"] = packing.pack_tc3_weights(u_w[:, :, 64:].contiguous(), 1, 1, 1)
+    # generation 3: one 64 -> 72 point-wise GEMM (N padded to 80) that writes each tap's 8 channels as its own plane
+    out["out4.u_tc3"] = packing.pack_tc3_weights(u_w, 1, 1, 1)
     return out
 
 
@@ -123,9 +123,12 @@ def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bo
     _lib.check(_lib.load().mvster_conv_first_f32(capi._ptr(imgs), capi._ptr(wts["conv0.0.w"]), capi._ptr(wts["conv0.0.b"]), capi._ptr(c0),
                                                  N, H, W, capi._stream()), "mvster_conv_first_f32")
     g3 = bool(npass) and gen == 3
-    # conv0.1 (8 -> 8 at full resolution) stays on the CUDA cores: on the tensor cores its K and N are mostly padding
-    # (measured 124 us vs 107 us at cfg2)
-    c0 = _conv2d(c0, wts["conv0.1.w"], wts["conv0.1.b"], 3, 1, True)
+    # conv0.1 (8 -> 8 at full resolution): on the tensor cores two taps share each MMA (K = 2 x 8 channels); MVSTER_FPN_C01=simt
+    # keeps it on the CUDA cores (107 us at cfg2; 124 us on the tensor cores before the tap pairing)
+    if g3 and os.environ.get("MVSTER_FPN_C01", "tc") != "simt":
+        c0 = _conv_tc3(c0, wts, "conv0.1", 3, 1, True)
+    else:
+        c0 = _conv2d(c0, wts["conv0.1.w"], wts["conv0.1.b"], 3, 1, True)
     levels = [c0]
     x = c0
     for L in (1, 2, 3):
@@ -152,13 +155,10 @@ def _fused_last_level(wts: Dict[str, Tensor], top2: Tensor, c0: Tensor, npass: i
     N, h, w, _ = top2.shape
     lib = _lib.load()
     uc = 72
-    if npass and gen == 3:  # U planar [9][N][h][w][8]: two point-wise GEMMs on the persistent 3 x bf16 kernel
-        plane = N * h * w * 8
+    if npass and gen == 3:  # U planar [9][N][h][w][8]: one point-wise GEMM on the persistent 3 x bf16 kernel
         U = torch.empty((9, N, h, w, 8), device=top2.device, dtype=torch.float32)
-        _lib.check(lib.mvster_pointwise_tc3_blocks_f32(capi._ptr(top2), capi._ptr(wts["out4.u_tc3a"]), capi._ptr(U), N, h, w, 64, 64, 8,
-                                                       plane, capi._stream()), "mvster_pointwise_tc3_blocks_f32")
-        _lib.check(lib.mvster_pointwise_tc3_blocks_f32(capi._ptr(top2), capi._ptr(wts["out4.u_tc3b"]), capi._ptr(U[8]), N, h, w, 64, 8, 8,
-                                                       plane, capi._stream()), "mvster_pointwise_tc3_blocks_f32")
+        _lib.check(lib.mvster_pointwise_tc3_blocks_f32(capi._ptr(top2), capi._ptr(wts["out4.u_tc3"]), capi._ptr(U), N, h, w, 64, 72, 8,
+                                                       N * h * w * 8, capi._stream()), "mvster_pointwise_tc3_blocks_f32")
         uc = 8
     elif npass:
         tc = wts["out4.u_tc"]

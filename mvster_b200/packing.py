@@ -87,14 +87,19 @@ def pack_tc3_weights(w: Tensor, kd: int, k: int, stride: int = 1) -> Tensor:
     taps, cin, cout = w.shape
     if taps != kd * k * k:
         raise ValueError(f"weight has {taps} taps, expected kd*k*k = {kd * k * k}")
-    n = max(cout, 16)
+    n = 16 if cout < 16 else (80 if cout > 64 else cout)  # the UMMA N the kernel instantiates per weight split
     plan = capi.conv_tc3_plan(cin, kd, k, stride)
     out = torch.zeros((len(plan), 2, 3 * n, 8), dtype=torch.bfloat16)
     w = w.detach().float().cpu()
-    for i, (kz, ky, kx, c0) in enumerate(plan):
-        cs = min(16, cin - c0)
-        wt = torch.zeros((16, n), dtype=torch.float32)
-        wt[:cs, :cout] = w[(kz * k + ky) * k + kx, c0:c0 + cs, :]
+    for i, (kz, ky, kx, c0, ky2, kx2) in enumerate(plan):
+        wt = torch.zeros((16, n), dtype=torch.float32)  # rows = the MMA's K: 16 input channels, or (Cin <= 8) two taps x 8 channels
+        if cin <= 8:
+            wt[:cin, :cout] = w[(kz * k + ky) * k + kx, :, :]
+            if ky2 >= 0:
+                wt[8:8 + cin, :cout] = w[(kz * k + ky2) * k + kx2, :, :]
+        else:
+            cs = min(16, cin - c0)
+            wt[:cs, :cout] = w[(kz * k + ky) * k + kx, c0:c0 + cs, :]
         for j, t in enumerate(bf16_split3(wt)):
             for h in range(2):
                 out[i, h, j * n:(j + 1) * n, :] = t[h * 8:(h + 1) * 8, :].T
