@@ -406,7 +406,8 @@ def main():
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(config_dict(world, P), engine={
                 "fpn_backend": model.fpn_backend, "fpn_precision": model.fpn_precision, "reg_precision": model.reg_precision,
-                "tc_kernel_gen": model.tc_kernel_gen, "cuda_graph": bool(model.use_cuda_graph) and P == 1}),
+                "tc_kernel_gen": model.tc_kernel_gen, "cuda_graph": bool(model.use_cuda_graph) and P == 1,
+                "overlap_stages": bool(getattr(model, "overlap_stages", False)) and P == 1}),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 2 * B * H * W * 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tc, "cpu_baseline": cpu_base,

@@ -142,6 +142,11 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
  * max(Cout,16)][8 bf16].  Its 16 K rows are 16 input channels of tap (ky,kx) (zero padded) or, for Cin <= 8, 8 channels of
  * tap (ky,kx) then 8 channels of tap (ky2,kx2) (two taps per MMA; -1,-1 = none) - packing.pack_tc3_weights.
  * x and w_packed 16-byte aligned. */
+/* The generation-3 kernel is persistent (one CTA per SM for the whole launch): the grid size is how much of the GPU a launch
+ * claims.  mvster_set_sm_budget(n) caps the grid of the mvster_*_tc3_* launches that follow, process-wide (0 = all SMs, the
+ * default) - the one piece of state besides the error string and the launch counter.  Used by the host to run the small
+ * early cascade stages on a second stream next to the feature pyramid's large layers. */
+void mvster_set_sm_budget(int n);
 int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw);
 int mvster_conv_tc3_plan(int Cin, int kd, int k, int stride_hw, int* slabs, int max_slabs);
 size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int stride_hw);

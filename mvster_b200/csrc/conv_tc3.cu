@@ -439,9 +439,15 @@ static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[6]
     return nslab;
 }
 
+// Persistent CTAs keep their SM for the whole launch, so the grid size is also how much of the GPU a launch claims.
+// mvster_set_sm_budget(n) caps the grid of the launches that follow (0 = every SM): the host uses it to run the small
+// early cascade stages on a second stream next to the feature pyramid's large layers (engine.py).
+static int g_sm_budget = 0;
+
 template <int NC>
 static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st) {
     using C = Cfg<NC>;
+    if (g_sm_budget > 0 && g_sm_budget < sms) sms = g_sm_budget;
     int T = C::TMAX;
     while (T > 1 && total_tiles < (long long)T * 2 * sms) T >>= 1;  // keep every SM busy before widening the groups
     if (T > a.tiles_per_plane) T = a.tiles_per_plane;
@@ -463,6 +469,8 @@ static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long to
 }  // namespace mvster
 
 using namespace mvster;
+
+extern "C" void mvster_set_sm_budget(int n) { tc3::g_sm_budget = n > 0 ? n : 0; }
 
 extern "C" int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw) {
     return tc3::supported(Cin, Cout, kd, k, stride_hw);

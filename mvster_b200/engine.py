@@ -10,11 +10,12 @@ Configuration coverage: reg2d and reg3d; group correlation and per-channel squar
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from . import capi, fpn_engine, packing
+from . import _lib, capi, fpn_engine, packing
 
 Tensor = torch.Tensor
 REG3D_DOWN = (3, 3, 2, 2)  # MVS4Net.py:48
@@ -54,6 +55,7 @@ class InferenceEngine:
         self.stage_weights: List[Dict[str, Tensor]] = []
         self.plans: List[StagePlan] = []
         self._graphs: Dict = {}
+        self._side = None  # second stream for the early cascade stages (_forward_overlapped)
 
     # ------------------------------------------------------------------ weights
     def refresh_weights(self, net) -> None:
@@ -85,7 +87,10 @@ class InferenceEngine:
                 x = torch.cat([imgs[v] for v in own], 0).to(dtype=torch.float32).contiguous()
                 prec = getattr(net, "fpn_precision", "fp32")
                 npass = {"fp32": 0, "3xtf32": 3, "tf32": 1, "3xbf16": 3}[prec]
-                pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=3 if prec == "3xbf16" else 2)
+                gen = 3 if prec == "3xbf16" else 2
+                if shard is None and net.num_stage == 4 and getattr(net, "overlap_stages", True):
+                    return self._forward_overlapped(net, x, B, len(own), proj_matrices, depth_values, npass, gen)
+                pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen)
                 nhwc = [pyramid[f"stage{k + 1}"] for k in range(net.num_stage)]
             else:
                 x = torch.cat([imgs[v] for v in own], 0).contiguous(memory_format=torch.channels_last)
@@ -102,7 +107,8 @@ class InferenceEngine:
         valid until the next call with the same signature (``test_mvs4.py`` converts to numpy right away)."""
         key = (tuple(tuple(t.shape) for t in imgs), tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
                tuple(depth_values.shape), self.weights_version, getattr(net, "reg_precision", "fp32"),
-               getattr(net, "tc_kernel_gen", 1), getattr(net, "fpn_backend", "torch"), getattr(net, "fpn_precision", "fp32"))
+               getattr(net, "tc_kernel_gen", 1), getattr(net, "fpn_backend", "torch"), getattr(net, "fpn_precision", "fp32"),
+               getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"))
         entry = self._graphs.get(key)
         if entry is None:
             with torch.cuda.device(self.device):
@@ -161,39 +167,91 @@ class InferenceEngine:
                                npass=3 if prec == "3xtf32" else 1, kernel_gen=gen)
         return capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=inverse)
 
+    def _run_stage(self, net, p: StagePlan, wts: Dict[str, Tensor], feats_k: List[Tensor], proj_matrices: Dict[str, Tensor],
+                   dv: Tensor, prev: Optional[Dict], temp: float, shard=None) -> Dict:
+        """One cascade stage (MVS4Net.py:78-105 loop body + stagenet.forward) on the current stream."""
+        fuse_d = bool(net.stagenet.attn_fuse_d)
+        inverse = bool(net.inverse_depth)
+        ref, srcs = feats_k[0], feats_k[1:]
+        B, H, W, C = ref.shape
+        proj = proj_matrices[f"stage{p.k + 1}"].to(device=self.device, dtype=torch.float32).contiguous()
+        if p.k == 0:
+            hypo = capi.hypo_init_inverse(dv, p.D, H, W) if inverse else capi.hypo_init_linear(dv, p.D, H, W)
+        elif inverse:
+            hypo = capi.hypo_schedule_inverse(prev["inverse_min_depth"], prev["inverse_max_depth"], p.D, H, W)
+        else:
+            hypo = capi.hypo_schedule_linear(prev["depth"], dv, p.split_itv, p.D, H, W)
+        cost = self._aggregate(p, ref, srcs, proj, hypo, temp, fuse_d, shard)
+        h = self._regularise(net, p, wts, cost, hypo)
+        out = {"depth": h["depth"],
+               "photometric_confidence": capi.upsample_bilinear(h["conf_low"], p.up),
+               "hypo_depth": hypo,
+               "attn_weight": h["attn_weight"]}
+        if inverse:
+            out["inverse_min_depth"] = h["inverse_min_depth"]
+            out["inverse_max_depth"] = h["inverse_max_depth"]
+        if net.mono:
+            out["mono_feat"] = ref.permute(0, 3, 1, 2)  # [B,C,H,W] view, as mvs4net_utils.py:1092
+        return out
+
     def run_cascade(self, net, feats: List[List[Tensor]], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
                     attn_temp: Optional[float] = None, shard=None) -> Dict:
         """feats[k][i]: NHWC features at stage k; i = 0 is the reference view, i >= 1 the source
         views (all of them, or with ``shard`` this rank's ``shard.views`` in order)."""
         temp = float(net.stagenet.attn_temp if attn_temp is None else attn_temp)
-        fuse_d = bool(net.stagenet.attn_fuse_d)
-        inverse = bool(net.inverse_depth)
         outputs: Dict = {}
         prev = None
         dv = depth_values.to(device=self.device, dtype=torch.float32).contiguous()
         for p, wts in zip(self.plans, self.stage_weights):
-            key = f"stage{p.k + 1}"
-            ref, srcs = feats[p.k][0], feats[p.k][1:]
-            B, H, W, C = ref.shape
-            proj = proj_matrices[key].to(device=self.device, dtype=torch.float32).contiguous()
-            if p.k == 0:
-                hypo = capi.hypo_init_inverse(dv, p.D, H, W) if inverse else capi.hypo_init_linear(dv, p.D, H, W)
-            elif inverse:
-                hypo = capi.hypo_schedule_inverse(prev["inverse_min_depth"], prev["inverse_max_depth"], p.D, H, W)
-            else:
-                hypo = capi.hypo_schedule_linear(prev["depth"], dv, p.split_itv, p.D, H, W)
-            cost = self._aggregate(p, ref, srcs, proj, hypo, temp, fuse_d, shard)
-            h = self._regularise(net, p, wts, cost, hypo)
-            out = {"depth": h["depth"],
-                   "photometric_confidence": capi.upsample_bilinear(h["conf_low"], p.up),
-                   "hypo_depth": hypo,
-                   "attn_weight": h["attn_weight"]}
-            if inverse:
-                out["inverse_min_depth"] = h["inverse_min_depth"]
-                out["inverse_max_depth"] = h["inverse_max_depth"]
-            if net.mono:
-                out["mono_feat"] = ref.permute(0, 3, 1, 2)  # [B,C,H,W] view, as mvs4net_utils.py:1092
-            prev = out
-            outputs[key] = out
-            outputs.update(out)
+            prev = self._run_stage(net, p, wts, feats[p.k], proj_matrices, dv, prev, temp, shard)
+            outputs[f"stage{p.k + 1}"] = prev
+            outputs.update(prev)
+        return outputs
+
+    # ------------------------------------------------------------------ two-stream forward
+    def _forward_overlapped(self, net, x: Tensor, B: int, n_own: int, proj_matrices: Dict[str, Tensor], depth_values: Tensor,
+                            npass: int, gen: int) -> Dict:
+        """The early cascade stages work on 1/64, 1/16 and 1/4 of the last stage's voxels: ~45 short, latency-bound launches
+        (0.7 ms of 2.1 ms at cfg2) that leave most SMs idle, and stage k only needs pyramid level k.  So they run on a second,
+        high-priority stream next to the pyramid's remaining large layers: level events fork the side stream, the persistent
+        convolution kernels of the two streams split the SMs through mvster_set_sm_budget, and the last stage joins on the main
+        stream.  Works eagerly and under CUDA-graph capture (fork/join through events)."""
+        lib = _lib.load()
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
+            self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        side = self._side
+        # SM split between the persistent convolution launches of the two streams while they overlap: the main stream's leave
+        # `reserve` SMs free, the side stream's claim at most `side_sms` (0 = no limit).  Measured at cfg2: see DESIGN.md 3.5.
+        reserve, side_sms = int(os.environ.get("MVSTER_MAIN_RESERVE", "48")), int(os.environ.get("MVSTER_SIDE_SMS", "0"))
+        events = [torch.cuda.Event() for _ in range(4)]
+
+        def on_level(k, t):
+            events[k].record(main)
+            if k == 0 and reserve > 0:
+                lib.mvster_set_sm_budget(self._sm_count - reserve)
+
+        temp = float(net.stagenet.attn_temp)
+        dv = depth_values.to(device=self.device, dtype=torch.float32).contiguous()
+        outputs: Dict = {}
+        try:
+            pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen, on_level=on_level)
+            feats = [[pyramid[f"stage{k + 1}"][i * B:(i + 1) * B] for i in range(n_own)] for k in range(4)]
+            lib.mvster_set_sm_budget(side_sms)
+            prev = None
+            with torch.cuda.stream(side):
+                for p, wts in zip(self.plans[:3], self.stage_weights[:3]):
+                    side.wait_event(events[p.k])
+                    prev = self._run_stage(net, p, wts, feats[p.k], proj_matrices, dv, prev, temp)
+                    outputs[f"stage{p.k + 1}"] = prev
+                done = torch.cuda.Event()
+                done.record(side)
+            lib.mvster_set_sm_budget(0)
+            main.wait_event(done)
+            prev = self._run_stage(net, self.plans[3], self.stage_weights[3], feats[3], proj_matrices, dv, prev, temp)
+            outputs["stage4"] = prev
+            outputs.update(prev)
+        finally:
+            lib.mvster_set_sm_budget(0)
         return outputs

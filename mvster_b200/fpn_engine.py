@@ -109,12 +109,14 @@ def _merge(top: Tensor, lat: Tensor, w: Tensor, b: Tensor) -> Tensor:
     return out
 
 
-def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bool = True, gen: int = 2) -> Dict[str, Tensor]:
+def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bool = True, gen: int = 2,
+            on_level=None) -> Dict[str, Tensor]:
     """imgs [N,3,H,W] contiguous NCHW fp32 on the GPU -> {'stage1'..'stage4': [N,h,w,C] NHWC}.
     npass: 0 = every layer on the CUDA cores (exact fp32), 3 / 1 = 3x3 stride-1 layers with Cin >= 16 on tcgen05
     (3xTF32 / TF32); gen = 3 (with npass = 3): every conv after the 3-channel stem, the stride-2 5x5 layers and the 1x1 out1
     included, on the persistent 3 x bf16 kernel.  fused_last: algebraically fused last level (never forms the 64-channel
-    full-res map)."""
+    full-res map).  on_level(k, tensor) is called right after the launches producing 'stage{k+1}' are enqueued (coarsest
+    first), so a caller can record an event and start that cascade stage on another stream."""
     capi._chk(imgs, "imgs")
     N, three, H, W = imgs.shape
     if three != 3 or H % 8 or W % 8:
@@ -137,16 +139,21 @@ def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bo
         x = _conv3x3(x, wts, f"conv{L}.2", True, npass, gen)
         levels.append(x)
     c0, c1, c2, c3 = levels
+    notify = on_level if on_level is not None else (lambda k, t: None)
     out = {"stage1": _conv_tc3(c3, wts, "out1", 1, 1, False) if g3 else _conv2d(c3, wts["out1.w"], None, 1, 1, False)}
+    notify(0, out["stage1"])
     top = _merge(c3, c2, wts["inner1.w"], wts["inner1.b"])
     out["stage2"] = _conv3x3(top, wts, "out2", False, npass, gen)
+    notify(1, out["stage2"])
     top = _merge(top, c1, wts["inner2.w"], wts["inner2.b"])
     out["stage3"] = _conv3x3(top, wts, "out3", False, npass, gen)
+    notify(2, out["stage3"])
     if fused_last:
         out["stage4"] = _fused_last_level(wts, top, c0, npass, gen)
     else:  # literal form: materialise the 64-channel full-resolution map, then the 3x3 conv
         top = _merge(top, c0, wts["inner3.w"], wts["inner3.b"])
         out["stage4"] = _conv3x3(top, wts, "out4", False, npass, gen)
+    notify(3, out["stage4"])
     return out
 
 

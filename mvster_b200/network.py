@@ -258,6 +258,8 @@ class MVS4net(nn.Module):
         # every layer after the 3-channel stem on the tensor cores) or "torch" (the module's own convs through cuDNN, channels-last)
         self.fpn_backend = os.environ.get("MVSTER_FPN", "native")
         self.fpn_precision = os.environ.get("MVSTER_FPN_PRECISION", "3xbf16")
+        # run cascade stages 1-3 on a second stream next to the feature pyramid's last levels (engine._forward_overlapped)
+        self.overlap_stages = os.environ.get("MVSTER_OVERLAP", "1") == "1"
         # replay the whole inference forward as one CUDA graph (outputs are then static buffers, valid until the next call)
         self.use_cuda_graph = os.environ.get("MVSTER_CUDA_GRAPH", "0") == "1"
         self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)
