@@ -138,10 +138,10 @@ class InferenceEngine:
 
     # ------------------------------------------------------------------ the hot path
     def _aggregate(self, p: StagePlan, ref: Tensor, srcs: List[Tensor], proj: Tensor, hypo: Tensor, temp: float,
-                   fuse_d: bool, shard) -> Tensor:
+                   fuse_d: bool, shard, pose: Optional[Tensor] = None) -> Tensor:
         kw = dict(group_cor=p.group_cor, fuse_d=fuse_d)
         if shard is None:
-            return capi.et_fuse(ref, srcs, capi.pose(proj), hypo, p.G, temp, **kw)
+            return capi.et_fuse(ref, srcs, capi.pose(proj) if pose is None else pose, hypo, p.G, temp, **kw)
         from . import sharding
         B, H, W, _ = ref.shape
 
@@ -168,8 +168,11 @@ class InferenceEngine:
         return capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=inverse)
 
     def _run_stage(self, net, p: StagePlan, wts: Dict[str, Tensor], feats_k: List[Tensor], proj_matrices: Dict[str, Tensor],
-                   dv: Tensor, prev: Optional[Dict], temp: float, shard=None) -> Dict:
-        """One cascade stage (MVS4Net.py:78-105 loop body + stagenet.forward) on the current stream."""
+                   dv: Tensor, prev: Optional[Dict], temp: float, shard=None, pose: Optional[Tensor] = None,
+                   deferred: Optional[List] = None) -> Dict:
+        """One cascade stage (MVS4Net.py:78-105 loop body + stagenet.forward) on the current stream.  ``pose``: relative poses
+        computed earlier (they only depend on the inputs); ``deferred``: if given, the confidence up-sampling - which no later
+        stage reads - is appended to it as a closure instead of being launched here, to keep it off the stage-to-stage chain."""
         fuse_d = bool(net.stagenet.attn_fuse_d)
         inverse = bool(net.inverse_depth)
         ref, srcs = feats_k[0], feats_k[1:]
@@ -181,12 +184,13 @@ class InferenceEngine:
             hypo = capi.hypo_schedule_inverse(prev["inverse_min_depth"], prev["inverse_max_depth"], p.D, H, W)
         else:
             hypo = capi.hypo_schedule_linear(prev["depth"], dv, p.split_itv, p.D, H, W)
-        cost = self._aggregate(p, ref, srcs, proj, hypo, temp, fuse_d, shard)
+        cost = self._aggregate(p, ref, srcs, proj, hypo, temp, fuse_d, shard, pose)
         h = self._regularise(net, p, wts, cost, hypo)
-        out = {"depth": h["depth"],
-               "photometric_confidence": capi.upsample_bilinear(h["conf_low"], p.up),
-               "hypo_depth": hypo,
-               "attn_weight": h["attn_weight"]}
+        out = {"depth": h["depth"], "hypo_depth": hypo, "attn_weight": h["attn_weight"]}
+        if deferred is None:
+            out["photometric_confidence"] = capi.upsample_bilinear(h["conf_low"], p.up)
+        else:
+            deferred.append(lambda o=out, c=h["conf_low"], f=p.up: o.__setitem__("photometric_confidence", capi.upsample_bilinear(c, f)))
         if inverse:
             out["inverse_min_depth"] = h["inverse_min_depth"]
             out["inverse_max_depth"] = h["inverse_max_depth"]
@@ -235,7 +239,10 @@ class InferenceEngine:
         temp = float(net.stagenet.attn_temp)
         dv = depth_values.to(device=self.device, dtype=torch.float32).contiguous()
         outputs: Dict = {}
+        deferred: List = []
         try:
+            # relative poses depend on the inputs only: computed up front, off the stage-to-stage chain
+            poses = [capi.pose(proj_matrices[f"stage{k + 1}"].to(device=self.device, dtype=torch.float32).contiguous()) for k in range(4)]
             pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen, on_level=on_level)
             feats = [[pyramid[f"stage{k + 1}"][i * B:(i + 1) * B] for i in range(n_own)] for k in range(4)]
             lib.mvster_set_sm_budget(side_sms)
@@ -243,13 +250,15 @@ class InferenceEngine:
             with torch.cuda.stream(side):
                 for p, wts in zip(self.plans[:3], self.stage_weights[:3]):
                     side.wait_event(events[p.k])
-                    prev = self._run_stage(net, p, wts, feats[p.k], proj_matrices, dv, prev, temp)
+                    prev = self._run_stage(net, p, wts, feats[p.k], proj_matrices, dv, prev, temp, pose=poses[p.k], deferred=deferred)
                     outputs[f"stage{p.k + 1}"] = prev
                 done = torch.cuda.Event()
                 done.record(side)
             lib.mvster_set_sm_budget(0)
             main.wait_event(done)
-            prev = self._run_stage(net, self.plans[3], self.stage_weights[3], feats[3], proj_matrices, dv, prev, temp)
+            prev = self._run_stage(net, self.plans[3], self.stage_weights[3], feats[3], proj_matrices, dv, prev, temp, pose=poses[3])
+            for fn in deferred:  # confidence maps of stages 1-3 (outputs only)
+                fn()
             outputs["stage4"] = prev
             outputs.update(prev)
         finally:
