@@ -46,6 +46,8 @@ typedef void* mvster_stream_t; /* cudaStream_t */
 #define MVSTER_ET_GENERIC 4     /* force the generic G-lanes-per-pixel kernel (A/B testing) */
 #define MVSTER_ET_NO_FUSE_D 8   /* attn_fuse_d=False: per-view scalar weight max_d softmax(sum_c cost) (mvs4net_utils.py:1049-1051) */
 #define MVSTER_ET_SQDIFF 16     /* group_cor=False: cost[c] = (ref[c]-warped[c])^2, C cost channels (:1042); pass G == C */
+#define MVSTER_ET_WINDOW 32     /* force the window kernel (correlate, then interpolate) where a specialisation exists */
+#define MVSTER_ET_NO_WINDOW 64  /* never use the window kernel (A/B testing) */
 
 int mvster_version(void);                 /* 10000*major + 100*minor + patch */
 const char* mvster_last_error(void);      /* thread-local, never NULL */
@@ -141,7 +143,12 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
  * {kz, ky, kx, first input channel, ky2, kx2}; max_slabs counts slabs); slab = [2 K-halves][w1 | w2 | w3 rows of
  * max(Cout,16)][8 bf16].  Its 16 K rows are 16 input channels of tap (ky,kx) (zero padded) or, for Cin <= 8, 8 channels of
  * tap (ky,kx) then 8 channels of tap (ky2,kx2) (two taps per MMA; -1,-1 = none) - packing.pack_tc3_weights.
- * x and w_packed 16-byte aligned. */
+ * x and w_packed 16-byte aligned.
+ * Second arithmetic: OR MVSTER_TC3_FP16X2 into the `relu` argument (bit 0 stays the ReLU switch) when w_packed holds two FP16
+ * terms per weight, rows [w1 | w2 | unused] with w1 = fp16(w), w2 = fp16(2^11 (w - w1)) (packing.pack_tc3_weights(split=2)):
+ * the activations are split the same way and the layer costs two MMAs per 16 channels instead of three; same fp32-class
+ * accuracy (22-bit operands) for |x|, |w| < 65504. */
+#define MVSTER_TC3_FP16X2 256
 /* The generation-3 kernel is persistent (one CTA per SM for the whole launch): the grid size is how much of the GPU a launch
  * claims.  mvster_set_sm_budget(n) caps the grid of the mvster_*_tc3_* launches that follow, process-wide (0 = all SMs, the
  * default) - the one piece of state besides the error string and the launch counter.  Used by the host to run the small
@@ -191,6 +198,9 @@ int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* co
  * (mvster_reg2d_tc3_blob_bytes(G) bytes, 16-byte aligned; conv0's slabs are present but unused); biases and the CUDA-core
  * layers' weights are read from `blob`. */
 size_t mvster_reg2d_tc3_blob_bytes(int G);
+int mvster_reg2d_tc3_ex_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* workspace,
+                            int B, int G, int D, int H, int W, int flags /* 0 or MVSTER_TC3_FP16X2 (tc3_blob packed with split=2) */,
+                            mvster_stream_t stream);
 int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* workspace,
                          int B, int G, int D, int H, int W, mvster_stream_t stream);
 
@@ -226,6 +236,9 @@ int mvster_pointwise_tc2_f32(const float* x, const float* w_packed, const float*
 /* Point-wise convolution on the generation-3 kernel whose output channel blocks go to separate tensors: channels
  * [j*block, (j+1)*block) -> [N][H][W][block] at y + j*block_stride_floats (no bias / relu).  Cin in {16,32,64}, Cout in
  * {8,16,32,64}; w_packed = packing.pack_tc3_weights([1][Cin][Cout], 1, 1, 1).  Used to produce the per-tap planes of U below. */
+int mvster_pointwise_tc3_blocks_ex_f32(const float* x, const void* w_packed, float* y, int N, int H, int W, int Cin, int Cout,
+                                       int block, long long block_stride_floats, int flags /* 0 or MVSTER_TC3_FP16X2 */,
+                                       mvster_stream_t stream);
 int mvster_pointwise_tc3_blocks_f32(const float* x, const void* w_packed, float* y, int N, int H, int W, int Cin, int Cout,
                                     int block, long long block_stride_floats, mvster_stream_t stream);
 /* Last pyramid level fused (mvs4net_utils.py:485-486, stage4 = out4(up2(top2) + inner3(c0))) without forming the

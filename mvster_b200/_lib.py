@@ -45,6 +45,7 @@ SIGNATURES = {
     "mvster_conv3d_tc2_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_reg2d_tc3_blob_bytes": (C.c_size_t, [_i]),
     "mvster_reg2d_tc3_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mvster_reg2d_tc3_ex_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_deconv_tc3_supported": (_i, [_i, _i, _i]),
     "mvster_deconv_tc3_packed_bytes": (C.c_size_t, [_i, _i, _i]),
     "mvster_deconv_tc3_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "mvster_conv_tc3_packed_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "mvster_conv_tc3_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_pointwise_tc3_blocks_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.c_longlong, _p]),
+    "mvster_pointwise_tc3_blocks_ex_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.c_longlong, _i, _p]),
     "mvster_conv2d_nhwc_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_conv_first_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "mvster_fpn_merge_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

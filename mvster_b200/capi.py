@@ -85,11 +85,13 @@ def pose(proj: Tensor, first_view: int = 1, n_views: Optional[int] = None) -> Te
 
 def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: int, attn_temp: float,
             cost: Optional[Tensor] = None, wsum: Optional[Tensor] = None, partial: bool = False,
-            accumulate: bool = False, generic: bool = False, group_cor: bool = True, fuse_d: bool = True) -> Tensor:
+            accumulate: bool = False, generic: bool = False, group_cor: bool = True, fuse_d: bool = True,
+            window: Optional[bool] = None) -> Tensor:
     """ref [B,H,W,C], srcs V x [B,Hs,Ws,C], pose [B,V,12], hypo [B,D,H,W] -> cost [B,D,H,W,G].
     With ``partial`` the un-normalised accumulators are written to (cost, wsum).  ``group_cor=False``:
     per-channel squared difference, the cost volume then has C channels (pass G == C);
-    ``fuse_d=False``: the reference's attn_fuse_d=False weighting."""
+    ``fuse_d=False``: the reference's attn_fuse_d=False weighting.  ``window``: True / False force / forbid the
+    window kernel (et_fuse_win.cuh); None leaves the choice to the library."""
     B, H, W, Cc = ref.shape
     _chk(ref, "ref")
     V = len(srcs)
@@ -114,6 +116,8 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
             flags |= 8                # MVSTER_ET_NO_FUSE_D
         if not group_cor:
             flags |= 16               # MVSTER_ET_SQDIFF
+        if window is not None:
+            flags |= 32 if window else 64  # MVSTER_ET_WINDOW / MVSTER_ET_NO_WINDOW
         if partial or not last:
             flags |= ET_PARTIAL
         if accumulate or v0 > 0:
@@ -211,10 +215,13 @@ def conv_tc3_plan(cin: int, kd: int, k: int, stride: int) -> List[tuple]:
     return [tuple(buf[6 * i:6 * i + 6]) for i in range(n)]
 
 
+TC3_FP16X2 = 256  # MVSTER_TC3_FP16X2: the packed weights hold two fp16 terms (packing.pack_tc3_weights(split=2))
+
+
 def conv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, k: int, stride: int = 1, relu: bool = True,
-             skip: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
-    """Generation-3 tcgen05 conv (persistent, 3 x bf16): x [B,D,H,W,Cin] -> [B,D,Ho,Wo,cout]; w_packed from
-    packing.pack_tc3_weights (a float32-typed byte blob)."""
+             skip: Optional[Tensor] = None, out: Optional[Tensor] = None, split: int = 3) -> Tensor:
+    """Generation-3 tcgen05 conv (persistent): x [B,D,H,W,Cin] -> [B,D,Ho,Wo,cout]; w_packed from
+    packing.pack_tc3_weights(split=split) (a float32-typed byte blob); split 3 = three bf16 terms per operand, 2 = two fp16."""
     _chk(x, "x")
     _chk(w_packed, "w_packed")
     B, D, H, W, Cin = x.shape
@@ -229,7 +236,7 @@ def conv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd:
     if want == 0 or w_packed.numel() * 4 != want:
         raise ValueError(f"conv_tc3: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
     _lib.check(lib.mvster_conv_tc3_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
-                                       kd, k, stride, int(relu), _stream()), "mvster_conv_tc3_f32")
+                                       kd, k, stride, int(relu) | (TC3_FP16X2 if split == 2 else 0), _stream()), "mvster_conv_tc3_f32")
     return y
 
 
@@ -278,7 +285,7 @@ def reg3d(blob: Tensor, cost: Tensor, down_size: int) -> Tensor:
 
 
 def deconv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, rows: int = -1, relu: bool = True,
-               skip: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+               skip: Optional[Tensor] = None, out: Optional[Tensor] = None, split: int = 3) -> Tensor:
     """Transposed conv (1,3,3) / stride (1,2,2) on the generation-3 tcgen05 kernel: x [B,D,H,W,Cin] -> [B,D,2H,2W,cout].
     rows = -1 writes every output pixel; rows = 0 / 1 only the output rows of that parity (pass ``out`` to the second call)."""
     _chk(x, "x")
@@ -294,7 +301,7 @@ def deconv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, r
     if want == 0 or w_packed.numel() * 4 != want:
         raise ValueError(f"deconv_tc3: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
     _lib.check(lib.mvster_deconv_tc3_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout, rows,
-                                         int(relu), _stream()), "mvster_deconv_tc3_f32")
+                                         int(relu) | (TC3_FP16X2 if split == 2 else 0), _stream()), "mvster_deconv_tc3_f32")
     return y
 
 
@@ -319,7 +326,7 @@ def reg2d_workspace_floats(B: int, D: int, H: int, W: int) -> int:
 
 
 def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: Optional[Tensor] = None,
-          tc_blob: Optional[Tensor] = None, npass: int = 3, kernel_gen: int = 1) -> Tensor:
+          tc_blob: Optional[Tensor] = None, npass: int = 3, kernel_gen: int = 1, split: int = 3) -> Tensor:
     """cost [B,D,H,W,G] -> feat8 [B,D,H,W,8] (everything of reg2d except the 1x1x1 prob layer).
     With ``tc_blob`` the three 3x3x3 layers run on the tensor cores (npass 3 = 3xTF32, 1 = TF32;
     kernel_gen 1 = per-tap TMA kernel with packing.pack_tc_weights slabs, 2 = staged-tile kernel with pack_tc2_weights slabs)."""
@@ -336,8 +343,8 @@ def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: O
     out = torch.empty((B, D, H, W, 8), device=cost.device, dtype=torch.float32) if out is None else _chk(out, "feat8", (B, D, H, W, 8))
     if tc_blob is not None and kernel_gen == 3:  # conv0..conv6 on the persistent 3 x bf16 kernel (packing.pack_reg2d 'tc3_blob')
         _chk(tc_blob, "tc3_blob", (int(_lib.load().mvster_reg2d_tc3_blob_bytes(G)) // 4,))
-        _lib.check(_lib.load().mvster_reg2d_tc3_f32(_ptr(blob), _ptr(tc_blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W,
-                                                    _stream()), "mvster_reg2d_tc3_f32")
+        _lib.check(_lib.load().mvster_reg2d_tc3_ex_f32(_ptr(blob), _ptr(tc_blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W,
+                                                       TC3_FP16X2 if split == 2 else 0, _stream()), "mvster_reg2d_tc3_f32")
         return out
     if tc_blob is not None:
         _chk(tc_blob, "tc_blob", (int(_lib.load().mvster_reg2d_tc_blob_floats()),))

@@ -317,10 +317,16 @@ extern "C" size_t mvster_reg2d_tc3_blob_bytes(int G) {
     return tc3_layer_offset(L, MVSTER_REG2D_LAYERS);
 }
 
+extern "C" int mvster_reg2d_tc3_ex_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* ws,
+                                       int B, int G, int D, int H, int W, int flags, mvster_stream_t stream) {
+    MVSTER_REQUIRE(tc3_blob, "mvster_reg2d_tc3_f32: tc3_blob is null");
+    // npass carries the arithmetic of the generation-3 layers: 3 = three bf16 terms, 2 = two fp16 terms
+    return reg2d_run(blob, (const float*)tc3_blob, (flags & MVSTER_TC3_FP16X2) ? 2 : 3, 3, cost, feat8, ws, B, G, D, H, W, stream);
+}
+
 extern "C" int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* ws,
                                     int B, int G, int D, int H, int W, mvster_stream_t stream) {
-    MVSTER_REQUIRE(tc3_blob, "mvster_reg2d_tc3_f32: tc3_blob is null");
-    return reg2d_run(blob, (const float*)tc3_blob, 3, 3, cost, feat8, ws, B, G, D, H, W, stream);
+    return mvster_reg2d_tc3_ex_f32(blob, tc3_blob, cost, feat8, ws, B, G, D, H, W, 0, stream);
 }
 
 static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen, const float* cost, float* feat8, float* ws,
@@ -339,6 +345,7 @@ static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen
     float* out[MVSTER_REG2D_LAYERS] = {c0, c1, c2, c3, c4, c5, c6, u7, u9, feat8};
     const float* skip[MVSTER_REG2D_LAYERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c4, c2, c0};
     const int div[MVSTER_REG2D_LAYERS] = {1, 1, 2, 2, 4, 4, 8, 8, 4, 2};  // input resolution divisor
+    const int relu3 = 1 | ((gen == 3 && npass == 2) ? MVSTER_TC3_FP16X2 : 0);  // ReLU + arithmetic of the generation-3 layers
     for (int i = 0; i < MVSTER_REG2D_LAYERS; ++i) {
         int64_t info[8];
         mvster_reg2d_layer_info(G, i, info);
@@ -348,16 +355,16 @@ static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen
             // full resolution) stays on the CUDA cores: with K and N mostly padding the tensor-core tile costs as much as a
             // 16 -> 16 layer (measured 101 us vs 42 us at cfg2 stage 4).
             rc = mvster_conv_tc3_f32(in[i], (const uint8_t*)tc_blob + tc3_layer_offset(L, i), blob + info[6], skip[i], out[i], B, D,
-                                     H / div[i], W / div[i], L[i].cin, L[i].cout, L[i].kd, 3, L[i].s, 1, stream);
+                                     H / div[i], W / div[i], L[i].cin, L[i].cout, L[i].kd, 3, L[i].s, relu3, stream);
         } else if (tc_blob && gen == 3 && L[i].transposed) {
             // conv7 / conv9 / conv11: 2x2 convolution on the input grid + depth-to-space epilogue (mvster_deconv_tc3_f32)
             const uint8_t* wl = (const uint8_t*)tc_blob + tc3_layer_offset(L, i);
             const int rows = tc3_deconv_rows(L[i]);
             rc = mvster_deconv_tc3_f32(in[i], wl, blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i], L[i].cin, L[i].cout,
-                                       rows, 1, stream);
+                                       rows, relu3, stream);
             if (rc == MVSTER_OK && rows == 0)
                 rc = mvster_deconv_tc3_f32(in[i], wl + mvster_deconv_tc3_packed_bytes(L[i].cin, L[i].cout, 0), blob + info[6], skip[i],
-                                           out[i], B, D, H / div[i], W / div[i], L[i].cin, L[i].cout, 1, 1, stream);
+                                           out[i], B, D, H / div[i], W / div[i], L[i].cin, L[i].cout, 1, relu3, stream);
         } else if (tc_blob && gen != 3 && L[i].kd == 3) {
             // conv2 / conv4 / conv6 (3x3x3, 69 % of the FLOPs) on the tcgen05 tensor cores; their [hi|lo]
             // K-major slabs sit back to back in tc_blob (2*27*Cin*Cout floats each).

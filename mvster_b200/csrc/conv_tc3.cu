@@ -17,8 +17,15 @@
 //     convolutions (4 parity classes, no wasted taps) run on the same kernel.
 //   * tcgen05 / TMA issue is guarded by elect.sync (see tc_ptx.cuh: a lane test makes the compiler serialise every issue).
 //
+//   * Second arithmetic (NS = 2, MVSTER_TC3_FP16X2): two FP16 terms per operand, a = a1 + 2^-11 a2 with a1 = fp16(a) and
+//     a2 = fp16(2^11 (a - a1)) (22 significand bits; the scaling keeps the residual out of fp16's subnormal range), same for w.
+//     TWO MMAs per 16 channels: a1 x [w1|w2] (N = 2*NC) and a2 x [w1] accumulated onto the SECOND column block, so block 0
+//     holds a1w1 and block 1 holds a1w2 + a2w1; the epilogue returns block0 + 2^-11 block1 (dropped: 2^-22 a2w2).  Same
+//     fp32-class accuracy with 2/3 of the MMAs, operand conversions and operand bytes; valid for |x| < 65504 (fp16 range; larger
+//     inputs saturate), which is why the 3 x bf16 arithmetic stays available.
+//
 // warp 0 = activation producer (TMA), warp 1 = TMEM owner + MMA issuer, warp 2 = weight producer, warps 3-10 = fp32 -> 3 x bf16
-// converters, warps 11-14 = epilogue.
+// (or 2 x fp16) converters, warps 11-14 = epilogue.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -31,8 +38,7 @@ constexpr int QBYTES = HPIX * 16;            // bytes per channel quad of a halo
 constexpr int F_BYTES = 4 * QBYTES;          // fp32 staging of one tile-stage: [180 pixels][<= 16 channels], ONE TMA box
 constexpr int PLANE = QBYTES;                // bf16 operand plane = [180 pixels][8 channels]; 2880 = 64 (mod 128): the two
                                              // octet planes a converter half-warp writes fall into disjoint banks
-constexpr int A_SPLIT = 2 * PLANE;           // one bf16 term of one tile-stage: 2 channel octets
-constexpr int A_BYTES = 3 * A_SPLIT;         // a1 | a2 | a3
+constexpr int A_SPLIT = 2 * PLANE;           // one 16-bit term of one tile-stage: 2 channel octets
 constexpr int NCONV = 256;                 // converter threads (8 warps: one warp per SM sub-partition was latency-bound)
 constexpr int CTEAM = NCONV / 2;           // ... in two teams that take alternate tile-stages
 constexpr int THREADS = 96 + NCONV + 128;
@@ -72,11 +78,12 @@ static bool set_output_mode(Args& a, int ncls, int py0, bool d2s, long long bloc
     return true;
 }
 
-template <int NC>
+template <int NC, int NS>
 struct Cfg {
     static constexpr int TMAX = NC > 64 ? 1 : 64 / NC;      // tiles accumulated side by side: 3*NC*TMAX <= 240 TMEM columns per set
-    static constexpr int NA = NC >= 64 ? 6 : 8;             // bf16 operand ring (tile-stages)
-    static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 bf16]
+    static constexpr int NA = NC >= 64 ? 6 : 8;             // 16-bit operand ring (tile-stages)
+    static constexpr int A_BYTES = NS * A_SPLIT;            // a1 | a2 | a3   (NS = 2: a1 | a2)
+    static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 x 16 bit]
     static constexpr int SMEM = 1024 + NF * F_BYTES + NA * A_BYTES + NB * B_BYTES + 512;
 };
 
@@ -94,11 +101,20 @@ __device__ __forceinline__ void split3(float x, float y, uint32_t& t1, uint32_t&
     ry -= __uint_as_float(t2 & 0xFFFF0000u);
     t3 = bf16x2_rn(rx, ry);
 }
+// two fp32 -> two packed fp16 pairs with v == t1 + 2^-11 t2 to 22 bits (saturating: |v| >= 65504 is outside this arithmetic)
+__device__ __forceinline__ void split2h(float x, float y, uint32_t& t1, uint32_t& t2) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(t1) : "f"(y), "f"(x));
+    float bx, by;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(bx), "=f"(by) : "r"(t1));
+    const float rx = (x - bx) * 2048.f, ry = (y - by) * 2048.f;  // exact: the residual has <= 13 significant bits
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(t2) : "f"(ry), "f"(rx));
+}
 
-template <int NC>
+template <int NC, int NS>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ Plan plan, const Args a) {
-    using C = Cfg<NC>;
+    using C = Cfg<NC, NS>;
+    constexpr int A_BYTES = C::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -187,6 +203,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
         // tensor pipe idled a third of the time (ncu source page, profiles/r01_conv_tc3_ncu.md).
         if (elect_one()) {
             constexpr uint32_t ID3 = idesc_bf16_m128(3 * NC), ID2 = idesc_bf16_m128(2 * NC), ID1 = idesc_bf16_m128(NC);
+            constexpr uint32_t IH2 = idesc_f16_m128(2 * NC), IH1 = idesc_f16_m128(NC);
             // descriptor = (hi << 32) | lo; lo = start address >> 4 | LBO >> 4 << 16 (taps / splits / slots only move the address)
             constexpr uint64_t A_HI = (uint64_t)((HW_ * 16) >> 4) | (1ull << 14), B_HI = (uint64_t)(128 >> 4) | (1ull << 14);
             constexpr uint32_t B_LBO = (uint32_t)((3 * NC * 16) >> 4) << 16;  // the A operand's LBO comes with each tap (plan.a_desc)
@@ -220,9 +237,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         for (int t = 0; t < C::TMAX; ++t)
                             if (t < Tg) {
                                 const uint32_t lo = alo[t] + shift, d = d0 + (uint32_t)(t * 3 * NC);
-                                umma_bf16(d, (A_HI << 32) | lo, bd, ID3, accumulate);                           // a1 x [w1|w2|w3]
-                                umma_bf16(d, (A_HI << 32) | (lo + (A_SPLIT >> 4)), bd, ID2, 1u);                // a2 x [w1|w2]
-                                umma_bf16(d, (A_HI << 32) | (lo + (2 * A_SPLIT >> 4)), bd, ID1, 1u);            // a3 x [w1]
+                                if constexpr (NS == 3) {
+                                    umma_bf16(d, (A_HI << 32) | lo, bd, ID3, accumulate);                           // a1 x [w1|w2|w3]
+                                    umma_bf16(d, (A_HI << 32) | (lo + (A_SPLIT >> 4)), bd, ID2, 1u);                // a2 x [w1|w2]
+                                    umma_bf16(d, (A_HI << 32) | (lo + (2 * A_SPLIT >> 4)), bd, ID1, 1u);            // a3 x [w1]
+                                } else {  // fp16 terms: block 0 += a1 w1, block 1 += a1 w2 + a2 w1
+                                    umma_bf16(d, (A_HI << 32) | lo, bd, IH2, accumulate);                           // a1 x [w1|w2]
+                                    umma_bf16(d + (uint32_t)NC, (A_HI << 32) | (lo + (A_SPLIT >> 4)), bd, IH1, 1u); // a2 x [w1] -> block 1
+                                }
                             }
                         umma_commit(B_EMPTY(b_slot));
                         if (++b_slot == NB) { b_slot = 0; b_par ^= 1; }
@@ -266,13 +288,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         const int i = tid + k * CTEAM;
                         if (i < items) {
                             const int p = i >> qsh, q = i & (nq - 1);
-                            uint2 t1, t2, t3;
-                            split3(v[k].x, v[k].y, t1.x, t2.x, t3.x);
-                            split3(v[k].z, v[k].w, t1.y, t2.y, t3.y);
                             uint8_t* dst = A + (q >> 1) * PLANE + p * 16 + (q & 1) * 8;
-                            *reinterpret_cast<uint2*>(dst) = t1;
-                            *reinterpret_cast<uint2*>(dst + A_SPLIT) = t2;
-                            *reinterpret_cast<uint2*>(dst + 2 * A_SPLIT) = t3;
+                            if constexpr (NS == 3) {
+                                uint2 t1, t2, t3;
+                                split3(v[k].x, v[k].y, t1.x, t2.x, t3.x);
+                                split3(v[k].z, v[k].w, t1.y, t2.y, t3.y);
+                                *reinterpret_cast<uint2*>(dst) = t1;
+                                *reinterpret_cast<uint2*>(dst + A_SPLIT) = t2;
+                                *reinterpret_cast<uint2*>(dst + 2 * A_SPLIT) = t3;
+                            } else {
+                                uint2 t1, t2;
+                                split2h(v[k].x, v[k].y, t1.x, t2.x);
+                                split2h(v[k].z, v[k].w, t1.y, t2.y);
+                                *reinterpret_cast<uint2*>(dst) = t1;
+                                *reinterpret_cast<uint2*>(dst + A_SPLIT) = t2;
+                            }
                         }
                     }
                     fence_proxy_async();
@@ -324,7 +354,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         uint32_t v1[16], v2[16], v3[16];
                         tmem_ld16(col + c0, v1);
                         tmem_ld16(col + NC + c0, v2);
-                        tmem_ld16(col + 2 * NC + c0, v3);
+                        if constexpr (NS == 3) tmem_ld16(col + 2 * NC + c0, v3);
                         tmem_ld_wait();
                         if (ok && c0 < ncol) {
 #pragma unroll
@@ -335,7 +365,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                                 float o[4];
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
-                                    o[e] = (__uint_as_float(v3[j + e]) + __uint_as_float(v2[j + e])) + __uint_as_float(v1[j + e]);
+                                    if constexpr (NS == 3) o[e] = (__uint_as_float(v3[j + e]) + __uint_as_float(v2[j + e])) + __uint_as_float(v1[j + e]);
+                                    else o[e] = fmaf(__uint_as_float(v2[j + e]), 1.f / 2048.f, __uint_as_float(v1[j + e]));
                                     if (a.bias) o[e] += __ldg(a.bias + ch + e);
                                     if (a.relu) o[e] = fmaxf(o[e], 0.f);
                                 }
@@ -444,9 +475,9 @@ static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[6]
 // early cascade stages on a second stream next to the feature pyramid's large layers (engine.py).
 static int g_sm_budget = 0;
 
-template <int NC>
-static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st) {
-    using C = Cfg<NC>;
+template <int NC, int NS>
+static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st) {
+    using C = Cfg<NC, NS>;
     if (g_sm_budget > 0 && g_sm_budget < sms) sms = g_sm_budget;
     int T = C::TMAX;
     while (T > 1 && total_tiles < (long long)T * 2 * sms) T >>= 1;  // keep every SM busy before widening the groups
@@ -454,7 +485,7 @@ static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long to
     a.T = T;
     a.groups_per_plane = ceil_div(a.tiles_per_plane, T);
     a.total_groups = (int)(total_tiles / a.tiles_per_plane) * a.groups_per_plane;
-    auto k = conv_tc3_kernel<NC>;
+    auto k = conv_tc3_kernel<NC, NS>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
         set_error("conv_tc3_kernel: cannot reserve %d bytes of shared memory", C::SMEM);
         cudaGetLastError();
@@ -463,6 +494,11 @@ static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long to
     const int grid = a.total_groups < sms ? a.total_groups : sms;
     k<<<grid, THREADS, C::SMEM, st>>>(xm, plan, a);
     return check_launch("conv_tc3_kernel");
+}
+
+template <int NC>
+static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st, bool fp16x2) {
+    return fp16x2 ? launch_ns<NC, 2>(xm, plan, a, total_tiles, sms, st) : launch_ns<NC, 3>(xm, plan, a, total_tiles, sms, st);
 }
 
 }  // namespace tc3
@@ -526,7 +562,8 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     build_plan(Cin, kd, k, s, &plan, nullptr);
     Args a;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
-    a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = relu; a.sx = s;
+    const bool fp16x2 = relu & MVSTER_TC3_FP16X2;
+    a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = relu & 1; a.sx = s;
     a.nstage = kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16);
     a.tiles_x = ceil_div(a.Wo, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(a.Ho, TH);
@@ -539,10 +576,10 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     cudaStream_t st = (cudaStream_t)stream;
     MVSTER_REQUIRE(Cout <= 64 || blocks, "mvster_conv_tc3_f32: Cout = %d only as separate channel blocks", Cout);
     const int NC = Cout < 16 ? 16 : (Cout > 64 ? 80 : Cout);
-    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st);
-    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st);
-    if (NC == 80) return launch<80>(xm, plan, a, total_tiles, sms, st);
-    return launch<64>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st, fp16x2);
+    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st, fp16x2);
+    if (NC == 80) return launch<80>(xm, plan, a, total_tiles, sms, st, fp16x2);
+    return launch<64>(xm, plan, a, total_tiles, sms, st, fp16x2);
 }
 
 extern "C" int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
@@ -551,11 +588,17 @@ extern "C" int mvster_conv_tc3_f32(const float* x, const void* w_packed, const f
     return conv_tc3_run(x, w_packed, bias, skip, y, B, D, H, W, Cin, Cout, kd, k, stride_hw, relu, 0, 0, stream);
 }
 
-extern "C" int mvster_pointwise_tc3_blocks_f32(const float* x, const void* w_packed, float* y, int N, int H, int W, int Cin, int Cout,
-                                               int block, long long block_stride_floats, mvster_stream_t stream) {
+extern "C" int mvster_pointwise_tc3_blocks_ex_f32(const float* x, const void* w_packed, float* y, int N, int H, int W, int Cin, int Cout,
+                                                  int block, long long block_stride_floats, int flags, mvster_stream_t stream) {
     MVSTER_REQUIRE(block >= 4 && block % 4 == 0 && Cout % block == 0 && (Cout == block || block_stride_floats % 4 == 0),
                    "mvster_pointwise_tc3_blocks_f32: bad block %d for Cout %d", block, Cout);
-    return conv_tc3_run(x, w_packed, nullptr, nullptr, y, N, 1, H, W, Cin, Cout, 1, 1, 1, 0, block, block_stride_floats, stream);
+    return conv_tc3_run(x, w_packed, nullptr, nullptr, y, N, 1, H, W, Cin, Cout, 1, 1, 1, flags & MVSTER_TC3_FP16X2, block,
+                        block_stride_floats, stream);
+}
+
+extern "C" int mvster_pointwise_tc3_blocks_f32(const float* x, const void* w_packed, float* y, int N, int H, int W, int Cin, int Cout,
+                                               int block, long long block_stride_floats, mvster_stream_t stream) {
+    return mvster_pointwise_tc3_blocks_ex_f32(x, w_packed, y, N, H, W, Cin, Cout, block, block_stride_floats, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -616,7 +659,8 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
     }
     Args a;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
-    a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = relu; a.sx = 1; a.nstage = kch;
+    const bool fp16x2 = relu & MVSTER_TC3_FP16X2;
+    a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = relu & 1; a.sx = 1; a.nstage = kch;
     a.tiles_x = ceil_div(W, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
     a.zero_a = 0;
@@ -624,7 +668,7 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
     cudaStream_t st = (cudaStream_t)stream;
     const int NC = a.ncls * Cout;
-    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st);
-    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st);
-    return launch<64>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st, fp16x2);
+    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st, fp16x2);
+    return launch<64>(xm, plan, a, total_tiles, sms, st, fp16x2);
 }

@@ -32,6 +32,7 @@ struct EtArgs {
     int B, V, H, W, Hs, Ws;
     float attn_temp, sqrt_c;
     int flags;
+    int prefetch;  // window kernels: L2 prefetch of every view's window rows before the view loop
 };
 
 template <int N>
@@ -206,6 +207,7 @@ __global__ void et_normalize_kernel(float* __restrict__ cost, const float* __res
 }  // namespace mvster
 #include "et_fuse_tiled.cuh"
 #include "et_fuse_dlane.cuh"
+#include "et_fuse_win.cuh"
 namespace mvster {
 
 template <int CPG, int G, int D>
@@ -266,9 +268,12 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     a.attn_temp = attn_temp;
     a.sqrt_c = (float)sqrt((double)C);  // math.sqrt(C) -> fp32 scalar
     a.flags = flags;
+    { const char* pf = getenv("MVSTER_ET_PREFETCH"); a.prefetch = pf ? atoi(pf) : 1; }
     cudaStream_t st = (cudaStream_t)stream;
     int rc = MVSTER_OK;
     const bool plain = !(flags & (MVSTER_ET_GENERIC | MVSTER_ET_SQDIFF | MVSTER_ET_NO_FUSE_D));
+    const bool window = (flags & MVSTER_ET_NO_WINDOW) ? false : (flags & MVSTER_ET_WINDOW) ? true : et_window_default();
+    if (plain && window && try_launch_win(a, C, G, D, st, &rc)) return rc;  // stages 2-4: shared 3 x 3 tap window
     if (plain && try_launch_dlane(a, C, G, D, st, &rc)) return rc;   // D = 4 stages: hypotheses across lanes
     if (plain && try_launch_tiled(a, C, G, D, st, &rc)) return rc;   // D = 8 stages: hypotheses unrolled per lane
     return G == 4 ? dispatch_cpg<4>(a, C / G, D, st) : dispatch_cpg<8>(a, C / G, D, st);

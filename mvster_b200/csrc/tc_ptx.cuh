@@ -123,5 +123,10 @@ __host__ __device__ constexpr uint32_t idesc_bf16_m128(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// same with FP16 A and B (format code 0)
+__host__ __device__ constexpr uint32_t idesc_f16_m128(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
 }  // namespace ptx
 }  // namespace mvster

@@ -86,8 +86,8 @@ class InferenceEngine:
                 # FPN4 inside libmvster_b200 (fpn_engine.py): NCHW images in, NHWC features out
                 x = torch.cat([imgs[v] for v in own], 0).to(dtype=torch.float32).contiguous()
                 prec = getattr(net, "fpn_precision", "fp32")
-                npass = {"fp32": 0, "3xtf32": 3, "tf32": 1, "3xbf16": 3}[prec]
-                gen = 3 if prec == "3xbf16" else 2
+                npass = {"fp32": 0, "3xtf32": 3, "tf32": 1, "3xbf16": 3, "2xfp16": 2}[prec]
+                gen = 3 if prec in ("3xbf16", "2xfp16") else 2
                 if shard is None and net.num_stage == 4 and getattr(net, "overlap_stages", True):
                     return self._forward_overlapped(net, x, B, len(own), proj_matrices, depth_values, npass, gen)
                 pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen)
@@ -161,6 +161,8 @@ class InferenceEngine:
             feat8 = capi.reg2d(wts["blob"], cost)
         elif prec == "3xbf16":  # conv0..conv6 on the persistent tcgen05 kernel, three bf16 terms per operand (fp32-faithful)
             feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc3_blob"], kernel_gen=3)
+        elif prec == "2xfp16":  # same kernel, two fp16 terms per operand (22-bit operands, 2/3 of the MMAs; |x| < 65504)
+            feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc3h_blob"], kernel_gen=3, split=2)
         else:                   # 3x3x3 layers on tcgen05: "3xtf32" (fp32-faithful) or "tf32"
             gen = int(getattr(net, "tc_kernel_gen", 1))
             feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc2_blob" if gen == 2 else "tc_blob"],

@@ -44,7 +44,9 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
         if w.shape[0] == 9 and w.shape[1] >= 16:
             out[name + ".tc"] = packing.pack_tc2_weights(w, 3)
         if w.shape[1] >= 8:  # generation-3 kernel: every layer after the 3-channel stem, stride-2 5x5 layers included
-            out[name + ".tc3"] = packing.pack_tc3_weights(w, 1, 5 if w.shape[0] == 25 else 3, 2 if name.endswith(".0") else 1)
+            kk, ss = (5 if w.shape[0] == 25 else 3), (2 if name.endswith(".0") else 1)
+            out[name + ".tc3"] = packing.pack_tc3_weights(w, 1, kk, ss)
+            out[name + ".tc3h"] = packing.pack_tc3_weights(w, 1, kk, ss, split=2)  # two fp16 terms (MVSTER_TC3_FP16X2)
     for i in (1, 2, 3):
         w = sd[f"{p}.inner{i}.weight"].detach().cpu()
         out[f"inner{i}.w"] = w.reshape(w.shape[0], w.shape[1]).t().float().contiguous()  # [Clat][64]
@@ -56,6 +58,7 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
             out[f"out{i}.tc"] = packing.pack_tc2_weights(w, 3)
         if w.shape[2] >= 8 and i < 4:
             out[f"out{i}.tc3"] = packing.pack_tc3_weights(w, 1, 3 if w.shape[0] == 9 else 1, 1)
+            out[f"out{i}.tc3h"] = packing.pack_tc3_weights(w, 1, 3 if w.shape[0] == 9 else 1, 1, split=2)
     # fused last level (fpn.cu: fpn_out4_gather_kernel): out4(up2(top2) + inner3(c0)) with the 3x3 conv's channel
     # mixing moved in front of the up-sampling - composite weights, all built in fp64
     w4 = out["out4.w"].double()                       # [9][64][8]  (tap, top channel m, out channel o)
@@ -67,6 +70,7 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
     out["out4.u_tc"] = packing.pack_tc2_weights(u_w, 3)
     # generation 3: one 64 -> 72 point-wise GEMM (N padded to 80) that writes each tap's 8 channels as its own plane
     out["out4.u_tc3"] = packing.pack_tc3_weights(u_w, 1, 1, 1)
+    out["out4.u_tc3h"] = packing.pack_tc3_weights(u_w, 1, 1, 1, split=2)
     return out
 
 
@@ -79,18 +83,19 @@ def _conv2d(x: Tensor, w: Tensor, b: Optional[Tensor], k: int, stride: int, relu
     return y
 
 
-def _conv_tc3(x: Tensor, wts: Dict[str, Tensor], name: str, k: int, stride: int, relu: bool) -> Tensor:
-    """any FPN conv after the stem on the persistent 3 x bf16 tcgen05 kernel (conv_tc3.cu)."""
+def _conv_tc3(x: Tensor, wts: Dict[str, Tensor], name: str, k: int, stride: int, relu: bool, split: int = 3) -> Tensor:
+    """any FPN conv after the stem on the persistent tcgen05 kernel (conv_tc3.cu); split 3 = 3 x bf16, 2 = 2 x fp16 operands."""
     N, H, W, Cin = x.shape
     cout = wts[name + ".w"].shape[2]
-    y = capi.conv_tc3(x.view(N, 1, H, W, Cin), wts[name + ".tc3"], wts.get(name + ".b"), cout, 1, k, stride, relu)
+    y = capi.conv_tc3(x.view(N, 1, H, W, Cin), wts[name + (".tc3h" if split == 2 else ".tc3")], wts.get(name + ".b"), cout, 1, k, stride,
+                      relu, split=split)
     return y.view(N, y.shape[2], y.shape[3], cout)
 
 
 def _conv3x3(x: Tensor, wts: Dict[str, Tensor], name: str, relu: bool, npass: int, gen: int = 2) -> Tensor:
     """3x3 stride-1 layer: tensor cores (gen 3: 3 x bf16; gen 2: npass 3 = 3xTF32, 1 = TF32) or CUDA cores (npass 0)."""
     if npass and gen == 3 and (name + ".tc3") in wts:
-        return _conv_tc3(x, wts, name, 3, 1, relu)
+        return _conv_tc3(x, wts, name, 3, 1, relu, 2 if npass == 2 else 3)
     w, b = wts[name + ".w"], wts.get(name + ".b")
     if npass and (name + ".tc") in wts:
         N, H, W, Cin = x.shape
@@ -125,22 +130,23 @@ def run_fpn(wts: Dict[str, Tensor], imgs: Tensor, npass: int = 0, fused_last: bo
     _lib.check(_lib.load().mvster_conv_first_f32(capi._ptr(imgs), capi._ptr(wts["conv0.0.w"]), capi._ptr(wts["conv0.0.b"]), capi._ptr(c0),
                                                  N, H, W, capi._stream()), "mvster_conv_first_f32")
     g3 = bool(npass) and gen == 3
+    sp = 2 if npass == 2 else 3  # generation 3 only: npass = 2 selects the two-fp16-term arithmetic
     # conv0.1 (8 -> 8 at full resolution): on the tensor cores two taps share each MMA (K = 2 x 8 channels); MVSTER_FPN_C01=simt
     # keeps it on the CUDA cores (107 us at cfg2; 124 us on the tensor cores before the tap pairing)
     if g3 and os.environ.get("MVSTER_FPN_C01", "tc") != "simt":
-        c0 = _conv_tc3(c0, wts, "conv0.1", 3, 1, True)
+        c0 = _conv_tc3(c0, wts, "conv0.1", 3, 1, True, sp)
     else:
         c0 = _conv2d(c0, wts["conv0.1.w"], wts["conv0.1.b"], 3, 1, True)
     levels = [c0]
     x = c0
     for L in (1, 2, 3):
-        x = _conv_tc3(x, wts, f"conv{L}.0", 5, 2, True) if g3 else _conv2d(x, wts[f"conv{L}.0.w"], wts[f"conv{L}.0.b"], 5, 2, True)
+        x = _conv_tc3(x, wts, f"conv{L}.0", 5, 2, True, sp) if g3 else _conv2d(x, wts[f"conv{L}.0.w"], wts[f"conv{L}.0.b"], 5, 2, True)
         x = _conv3x3(x, wts, f"conv{L}.1", True, npass, gen)
         x = _conv3x3(x, wts, f"conv{L}.2", True, npass, gen)
         levels.append(x)
     c0, c1, c2, c3 = levels
     notify = on_level if on_level is not None else (lambda k, t: None)
-    out = {"stage1": _conv_tc3(c3, wts, "out1", 1, 1, False) if g3 else _conv2d(c3, wts["out1.w"], None, 1, 1, False)}
+    out = {"stage1": _conv_tc3(c3, wts, "out1", 1, 1, False, sp) if g3 else _conv2d(c3, wts["out1.w"], None, 1, 1, False)}
     notify(0, out["stage1"])
     top = _merge(c3, c2, wts["inner1.w"], wts["inner1.b"])
     out["stage2"] = _conv3x3(top, wts, "out2", False, npass, gen)
@@ -164,8 +170,10 @@ def _fused_last_level(wts: Dict[str, Tensor], top2: Tensor, c0: Tensor, npass: i
     uc = 72
     if npass and gen == 3:  # U planar [9][N][h][w][8]: one point-wise GEMM on the persistent 3 x bf16 kernel
         U = torch.empty((9, N, h, w, 8), device=top2.device, dtype=torch.float32)
-        _lib.check(lib.mvster_pointwise_tc3_blocks_f32(capi._ptr(top2), capi._ptr(wts["out4.u_tc3"]), capi._ptr(U), N, h, w, 64, 72, 8,
-                                                       N * h * w * 8, capi._stream()), "mvster_pointwise_tc3_blocks_f32")
+        h16 = npass == 2
+        _lib.check(lib.mvster_pointwise_tc3_blocks_ex_f32(capi._ptr(top2), capi._ptr(wts["out4.u_tc3h" if h16 else "out4.u_tc3"]), capi._ptr(U),
+                                                          N, h, w, 64, 72, 8, N * h * w * 8, capi.TC3_FP16X2 if h16 else 0, capi._stream()),
+                   "mvster_pointwise_tc3_blocks_f32")
         uc = 8
     elif npass:
         tc = wts["out4.u_tc"]

@@ -79,17 +79,36 @@ def bf16_split3(w: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     return t1, t2, t3
 
 
-def pack_tc3_weights(w: Tensor, kd: int, k: int, stride: int = 1) -> Tensor:
+def fp16_split2(w: Tensor) -> Tuple[Tensor, Tensor]:
+    """fp32 -> two fp16 terms with w == t1 + 2^-11 t2 to 22 bits: t1 = fp16(w), t2 = fp16(2^11 (w - t1)) (the scaling keeps the
+    residual out of fp16's subnormal range).  |w| must stay below 65504."""
+    wc = w.clamp(-65504.0, 65504.0)
+    t1 = wc.to(torch.float16)
+    t2 = ((wc - t1.float()) * 2048.0).clamp(-65504.0, 65504.0).to(torch.float16)
+    return t1, t2
+
+
+def _split_terms(wt: Tensor, split: int):
+    """16-bit operand terms of a weight matrix as raw int16 bit patterns: split 3 = three bf16 terms, 2 = two fp16 terms."""
+    if split == 3:
+        return [t.view(torch.int16) for t in bf16_split3(wt)]
+    if split == 2:
+        return [t.view(torch.int16) for t in fp16_split2(wt)]  # third row block of the slab stays zero (unused)
+    raise ValueError(f"split must be 2 (fp16 terms) or 3 (bf16 terms), got {split}")
+
+
+def pack_tc3_weights(w: Tensor, kd: int, k: int, stride: int = 1, split: int = 3) -> Tensor:
     """[kd*k*k][Cin][Cout] fp32 -> the slab stream of the generation-3 tcgen05 kernel (conv_tc3.cu): one slab per
     (stage, tap) in the order of ``capi.conv_tc3_plan``; slab = [2 K-halves][w1 | w2 | w3, N rows each][8 bf16] over 16
-    input channels (zero padded), N = max(Cout, 16).  Returned as a float32-typed byte blob."""
+    input channels (zero padded), N = max(Cout, 16).  ``split`` = 2: two fp16 terms [w1 | w2 | unused] for the
+    MVSTER_TC3_FP16X2 arithmetic (same slab size).  Returned as a float32-typed byte blob."""
     from . import capi  # host-side plan enumeration lives in the library so that packer and kernel cannot diverge
     taps, cin, cout = w.shape
     if taps != kd * k * k:
         raise ValueError(f"weight has {taps} taps, expected kd*k*k = {kd * k * k}")
     n = 16 if cout < 16 else (80 if cout > 64 else cout)  # the UMMA N the kernel instantiates per weight split
     plan = capi.conv_tc3_plan(cin, kd, k, stride)
-    out = torch.zeros((len(plan), 2, 3 * n, 8), dtype=torch.bfloat16)
+    out = torch.zeros((len(plan), 2, 3 * n, 8), dtype=torch.int16)
     w = w.detach().float().cpu()
     for i, (kz, ky, kx, c0, ky2, kx2) in enumerate(plan):
         wt = torch.zeros((16, n), dtype=torch.float32)  # rows = the MMA's K: 16 input channels, or (Cin <= 8) two taps x 8 channels
@@ -100,24 +119,24 @@ def pack_tc3_weights(w: Tensor, kd: int, k: int, stride: int = 1) -> Tensor:
         else:
             cs = min(16, cin - c0)
             wt[:cs, :cout] = w[(kz * k + ky) * k + kx, c0:c0 + cs, :]
-        for j, t in enumerate(bf16_split3(wt)):
+        for j, t in enumerate(_split_terms(wt, split)):
             for h in range(2):
                 out[i, h, j * n:(j + 1) * n, :] = t[h * 8:(h + 1) * 8, :].T
     return out.reshape(-1).view(torch.float32)
 
 
-def _tc3_slabs(mats) -> Tensor:
+def _tc3_slabs(mats, split: int = 3) -> Tensor:
     """list of [16][n] fp32 matrices (16 input channels x n accumulator columns) -> generation-3 slab stream."""
     n = mats[0].shape[1]
-    out = torch.zeros((len(mats), 2, 3 * n, 8), dtype=torch.bfloat16)
+    out = torch.zeros((len(mats), 2, 3 * n, 8), dtype=torch.int16)
     for i, wt in enumerate(mats):
-        for j, t in enumerate(bf16_split3(wt)):
+        for j, t in enumerate(_split_terms(wt, split)):
             for h in range(2):
                 out[i, h, j * n:(j + 1) * n, :] = t[h * 8:(h + 1) * 8, :].T
     return out.reshape(-1).view(torch.float32)
 
 
-def pack_tc3_deconv_weights(w: Tensor, rows: int = -1) -> Tensor:
+def pack_tc3_deconv_weights(w: Tensor, rows: int = -1, split: int = 3) -> Tensor:
     """Transposed conv (1,3,3)/stride (1,2,2)/pad 1 weights [9][Cin][Cout] -> slab stream of mvster_deconv_tc3_f32: per
     16-channel chunk, one slab per input tap (dy,dx) in {0,1}^2 (rows = 0: dy = 0 only) whose columns are the output parity
     classes [class][Cout]; class (py,px) reads kernel element ky(py,dy), kx(px,dx) with k(0,0) = 1, k(1,0) = 2, k(1,1) = 0 and
@@ -138,7 +157,7 @@ def pack_tc3_deconv_weights(w: Tensor, rows: int = -1) -> Tensor:
                     if ky is not None and kx is not None:
                         m[:, ci * cout:(ci + 1) * cout] = w[ky * 3 + kx, c0:c0 + 16, :]
                 mats.append(m)
-    return _tc3_slabs(mats)
+    return _tc3_slabs(mats, split)
 
 
 def pack_reg3d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Tensor:
@@ -193,16 +212,18 @@ def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, 
             w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
             tc.append(pack_tc_weights(w, 3))
             tc2.append(pack_tc2_weights(w, 3))
-    tc3 = []
+    tc3 = {3: [], 2: []}  # three bf16 terms ('tc3_blob') and two fp16 terms ('tc3h_blob', MVSTER_TC3_FP16X2)
     for name, L in zip(REG2D_ORDER, layer_table):
         # slab streams of the generation-3 kernel in layer order (layout: conv_simt.cu tc3_layer_bytes)
         w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
-        if not L["transposed"]:
-            tc3.append(pack_tc3_weights(w, L["kd"], 3, L["stride"]))
-        elif 4 * L["cout"] <= 64:   # all four output parity classes in one launch
-            tc3.append(pack_tc3_deconv_weights(w, -1))
-        else:                       # conv7 (64 -> 32): output rows of parity 0, then parity 1
-            tc3 += [pack_tc3_deconv_weights(w, 0), pack_tc3_deconv_weights(w, 1)]
-    return {"blob": blob, "tc_blob": torch.cat(tc), "tc2_blob": torch.cat(tc2), "tc3_blob": torch.cat(tc3),
+        for split, lst in tc3.items():
+            if not L["transposed"]:
+                lst.append(pack_tc3_weights(w, L["kd"], 3, L["stride"], split))
+            elif 4 * L["cout"] <= 64:   # all four output parity classes in one launch
+                lst.append(pack_tc3_deconv_weights(w, -1, split))
+            else:                       # conv7 (64 -> 32): output rows of parity 0, then parity 1
+                lst += [pack_tc3_deconv_weights(w, 0, split), pack_tc3_deconv_weights(w, 1, split)]
+    return {"blob": blob, "tc_blob": torch.cat(tc), "tc2_blob": torch.cat(tc2), "tc3_blob": torch.cat(tc3[3]),
+            "tc3h_blob": torch.cat(tc3[2]),
             "prob_w": sd[prefix + ".prob.weight"].detach().cpu().reshape(-1).float().contiguous(),
             "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}

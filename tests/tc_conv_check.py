@@ -4,6 +4,8 @@ trap or a barrier deadlock in a tensor-core kernel cannot take the rest of the s
 
     python tests/tc_conv_check.py {v1|v2} CIN COUT KD B D H W NPASS [skip] [norelu]
     python tests/tc_conv_check.py {reg2d|reg2dv2} G B D H W NPASS
+    python tests/tc_conv_check.py v3 CIN COUT KD K STRIDE B D H W [skip] [norelu] [h16]     (h16: two-fp16-term arithmetic)
+    python tests/tc_conv_check.py d3 CIN COUT B D H W [skip] [h16]
 """
 import json
 import sys
@@ -70,8 +72,9 @@ def v3_main():
         want = want.clamp_min(0)
     if skip is not None:
         want = want + skip.double()
-    wp = packing.pack_tc3_weights(w, kd, k, stride).to(dev)
-    run = lambda: capi.conv_tc3(x, wp, bias, cout, kd, k, stride, relu, skip=skip)
+    split = 2 if "h16" in sys.argv else 3  # h16: two fp16 terms per operand (MVSTER_TC3_FP16X2)
+    wp = packing.pack_tc3_weights(w, kd, k, stride, split).to(dev)
+    run = lambda: capi.conv_tc3(x, wp, bias, cout, kd, k, stride, relu, skip=skip, split=split)
     got = run()
     torch.cuda.synchronize()
     err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()
@@ -97,16 +100,17 @@ def d3_main():
     want = want.permute(0, 2, 3, 4, 1).clamp_min(0)
     if skip is not None:
         want = want + skip.double()
+    split = 2 if "h16" in sys.argv else 3
     if 4 * cout <= 64:
-        wp = packing.pack_tc3_deconv_weights(w, -1).to(dev)
-        run = lambda: capi.deconv_tc3(x, wp, bias, cout, -1, True, skip=skip)
+        wp = packing.pack_tc3_deconv_weights(w, -1, split).to(dev)
+        run = lambda: capi.deconv_tc3(x, wp, bias, cout, -1, True, skip=skip, split=split)
     else:
-        wp0, wp1 = packing.pack_tc3_deconv_weights(w, 0).to(dev), packing.pack_tc3_deconv_weights(w, 1).to(dev)
+        wp0, wp1 = packing.pack_tc3_deconv_weights(w, 0, split).to(dev), packing.pack_tc3_deconv_weights(w, 1, split).to(dev)
         buf = torch.full((B, D, 2 * H, 2 * W, cout), float("nan"), device=dev)
 
         def run():
-            capi.deconv_tc3(x, wp0, bias, cout, 0, True, skip=skip, out=buf)
-            return capi.deconv_tc3(x, wp1, bias, cout, 1, True, skip=skip, out=buf)
+            capi.deconv_tc3(x, wp0, bias, cout, 0, True, skip=skip, out=buf, split=split)
+            return capi.deconv_tc3(x, wp1, bias, cout, 1, True, skip=skip, out=buf, split=split)
     got = run()
     torch.cuda.synchronize()
     err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()

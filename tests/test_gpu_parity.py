@@ -11,7 +11,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from util import GOLDEN_CASES, REPO, SHIPPED, build_model, load_golden, oracle, oracle_cfg, top2_gap
+from util import narrow_et_inputs, GOLDEN_CASES, REPO, SHIPPED, build_model, load_golden, oracle, oracle_cfg, top2_gap
 
 from mvster_b200 import _lib, capi, packing, synth
 
@@ -134,6 +134,53 @@ def test_et_fuse_tiled_and_generic_kernels_agree(case):
     gerr = (from_ndhwc(generic) - want).abs().max().item() / want.abs().max().item()
     record(f"et_generic_vs_oracle_{case}", rel_to_max=gerr)
     assert gerr < 2e-4
+
+
+# window kernel (csrc/et_fuse_win.cuh): hypotheses within one or two source cells, as in cascade stages 2-4.
+# Chosen so that 10-65 % of the pixels straddle a cell boundary in x, up to 40 % in y, and 6-40 % do not fit at all
+# (taps outside the image, span > 2 cells): those warps take the kernel's per-hypothesis path.
+WIN_CASES = [  # (B, nv, C, G, D, H, W, step_deg, rel_span)
+    (1, 5, 8, 4, 4, 64, 128, 1.0, 0.3),
+    (2, 3, 16, 4, 4, 64, 80, 2.0, 0.2),
+    (1, 4, 32, 8, 8, 32, 40, 4.0, 0.06),
+    (1, 3, 8, 4, 4, 40, 72, 3.0, 0.12),   # ragged tile width
+    (1, 3, 16, 4, 4, 45, 61, 6.0, 0.05),  # ragged both ways, wide baseline
+]
+
+
+@pytest.mark.parametrize("case", WIN_CASES)
+def test_et_fuse_window_kernel_matches_oracle(case):
+    B, nv, C, G, D, H, W, step, span = case
+    feats, cams, hypo = narrow_et_inputs(B, nv, C, D, H, W, step, span, seed=7)
+    want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0)
+    ref, srcs = nhwc(feats[0]), [nhwc(f) for f in feats[1:]]
+    pose, hy = capi.pose(cams.to(DEV)), hypo.to(DEV)
+    win = from_ndhwc(capi.et_fuse(ref, srcs, pose, hy, G, 2.0, window=True))
+    per_d = from_ndhwc(capi.et_fuse(ref, srcs, pose, hy, G, 2.0, window=False))
+    scale = want.abs().max().item()
+    err, err_pd = (win - want).abs().max().item(), (per_d - want).abs().max().item()
+    record(f"et_window_{case}", rel_to_max=err / scale, per_hypothesis_kernel_rel_to_max=err_pd / scale,
+           window_vs_per_hypothesis=(win - per_d).abs().max().item() / scale)
+    assert err <= 2e-4 * scale, f"window kernel: abs err {err:.3e} vs scale {scale:.3e}"
+    assert err_pd <= 2e-4 * scale
+
+
+def test_et_fuse_window_partial_accumulate():
+    """View-sharded use of the window kernel: partial sums of two view subsets, chained accumulation."""
+    B, nv, C, G, D, H, W, step, span = 1, 5, 16, 4, 4, 48, 64, 2.0, 0.2
+    feats, cams, hypo = narrow_et_inputs(B, nv, C, D, H, W, step, span, seed=9)
+    ref, srcs = nhwc(feats[0]), [nhwc(f) for f in feats[1:]]
+    pose, hy = capi.pose(cams.to(DEV)), hypo.to(DEV)
+    full = capi.et_fuse(ref, srcs, pose, hy, G, 2.0, window=True)
+    c1, w1 = torch.empty_like(full), torch.empty((B, D, H, W), device=DEV)
+    capi.et_fuse(ref, srcs[:2], pose[:, :2].contiguous(), hy, G, 2.0, cost=c1, wsum=w1, partial=True, window=True)
+    capi.et_fuse(ref, srcs[2:], pose[:, 2:].contiguous(), hy, G, 2.0, cost=c1, wsum=w1, partial=True, accumulate=True, window=True)
+    acc_want, w_want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0, partial=True)
+    assert (w1.cpu() - w_want).abs().max().item() < 1e-5
+    capi.et_normalize(c1, w1)
+    rel = (c1 - full).abs().max().item() / full.abs().max().item()
+    record("et_window_partial_chain", rel_to_max=rel)
+    assert rel < 1e-5
 
 
 def test_et_fuse_partial_accumulate_and_normalize():

@@ -53,6 +53,24 @@ CASES = [  # generation cin cout kd B D H W npass [flags]
     "d3 16 8 1 4 256 320 skip",         # conv11 at cfg2 stage 4
     "d3 32 16 1 4 128 160 skip",        # conv9
     "d3 64 32 1 4 64 80 skip",          # conv7
+    # the same kernel with two fp16 terms per operand (MVSTER_TC3_FP16X2): same fp64 yardstick, same tolerance
+    "v3 16 16 3 3 1 1 8 24 40 h16",
+    "v3 32 32 3 3 1 2 4 16 16 norelu h16",
+    "v3 64 64 3 3 1 1 4 64 80 skip h16",
+    "v3 64 8 1 3 1 2 1 32 40 norelu h16",
+    "v3 8 8 1 3 1 1 4 32 48 h16",
+    "v3 4 8 1 3 1 1 4 32 48 h16",
+    "v3 32 64 1 1 1 1 1 64 80 norelu h16",
+    "v3 16 32 1 3 2 1 4 30 44 h16",
+    "v3 8 16 1 5 2 2 1 64 96 h16",
+    "v3 32 64 1 5 2 1 1 64 80 h16",
+    "v3 16 16 3 3 1 1 4 256 320 h16",
+    "v3 16 16 1 3 1 5 1 512 640 h16",
+    "v3 32 32 3 3 1 1 4 128 160 skip h16",
+    "d3 16 8 1 2 24 40 skip h16",
+    "d3 32 16 2 2 16 16 h16",
+    "d3 64 32 1 4 8 10 skip h16",
+    "d3 16 8 1 4 256 320 skip h16",
     "reg2d 8 1 8 64 80 3",              # whole reg2d U-Net, stage-1 shape of cfg2, 3xTF32, generation 1
     "reg2dv2 8 1 8 64 80 3",            # ... generation 2
     "reg2dv2 4 1 4 512 640 3",          # stage-4 shape of cfg2 (1.31 M voxels)

@@ -12,7 +12,7 @@ from mvster_b200 import capi, packing, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("gen,npass", [(1, 3), (2, 3), (2, 1), (3, 3)])
+@pytest.mark.parametrize("gen,npass", [(1, 3), (2, 3), (2, 1), (3, 3), (3, 2)])  # (3, 2) = generation 3 with two fp16 terms
 def test_teacher_forced_stages_tensor_core_regulariser(gen, npass):
     B, nv, H, W = 1, 5, 128, 192
     imgs, proj, dv = synth.make_inputs(B, nv, H, W, seed=21)
@@ -31,8 +31,8 @@ def test_teacher_forced_stages_tensor_core_regulariser(gen, npass):
         with torch.no_grad():
             truth_attn = F.softmax(oracle.reg2d_logits(sd64, f"reg.{k}", ref_out[key]["cost"].double()), 1)
         packed = packing.pack_reg2d(sd, f"reg.{k}", capi.reg2d_layer_table(G))
-        feat8 = capi.reg2d(packed["blob"].to(DEV), cost, tc_blob=packed[{1: "tc_blob", 2: "tc2_blob", 3: "tc3_blob"}[gen]].to(DEV),
-                           npass=npass, kernel_gen=gen)
+        tcb = packed["tc3h_blob" if (gen, npass) == (3, 2) else {1: "tc_blob", 2: "tc2_blob", 3: "tc3_blob"}[gen]].to(DEV)
+        feat8 = capi.reg2d(packed["blob"].to(DEV), cost, tc_blob=tcb, npass=npass, kernel_gen=gen, split=2 if npass == 2 else 3)
         h = capi.head(hypo.to(DEV), cfg["depth_interals_ratio"][k], feat8=feat8, prob_w=packed["prob_w"].to(DEV), prob_b=packed["prob_b"].to(DEV))
         floor_attn = (ref_out[key]["attn_weight"].double() - truth_attn).abs().max().item()
         aerr_truth = (h["attn_weight"].cpu().double() - truth_attn).abs().max().item()
@@ -40,7 +40,7 @@ def test_teacher_forced_stages_tensor_core_regulariser(gen, npass):
         d, rd = h["depth"].cpu(), ref_out[key]["depth"]
         bad = (((d - rd).abs() > 1e-4 * rd) & stable).float().mean().item()
         record(f"tc_regulariser_gen{gen}_npass{npass}_{key}", attn_vs_fp64=aerr_truth, oracle_attn_vs_fp64=floor_attn, depth_bad_stable=bad)
-        if npass == 3:
+        if npass >= 2:
             # 3xTF32: the tensor core's fp32 accumulator truncates on every MMA, so a K = 27*Cin chain carries ~1e-5 of the
             # layer's max (measured, tests/test_gpu_tc_conv.py); through the U-Net that is <= 1e-3 on a probability - the
             # same level as the fp32 pipeline's own sensitivity to fp32 sampling coordinates (teacher_forced_*: 2e-4 .. 1e-3)

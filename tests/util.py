@@ -56,3 +56,16 @@ def top2_gap(attn: torch.Tensor) -> torch.Tensor:
     """Difference between the two largest probabilities over D: [B,D,H,W] -> [B,H,W]."""
     t = attn.topk(2, dim=1).values
     return t[:, 0] - t[:, 1]
+
+
+def narrow_et_inputs(B, nv, C, D, H, W, step_deg, rel_span, seed=0):
+    """Inputs shaped like cascade stages 2-4: every pixel has its own hypothesis centre (425..935) and its D
+    hypotheses cover only ``rel_span`` of it (far -> near), so they sample within one or two source-pixel
+    cells - the regime the window kernel (csrc/et_fuse_win.cuh) is built for.  Returns (features, cams, hypo)."""
+    rng = np.random.RandomState(seed)
+    feats = [torch.from_numpy(rng.randn(B, C, H, W).astype(np.float32)) for _ in range(nv)]
+    cams = synth.stage_projections(synth.arc_cameras(nv, H, W, step_deg), B, num_stage=1)["stage1"]
+    centre = rng.uniform(450.0, 900.0, (B, 1, H, W))
+    lin = np.linspace(0.5, -0.5, D).reshape(1, D, 1, 1)
+    hypo = torch.from_numpy((centre * (1.0 + rel_span * lin)).astype(np.float32))
+    return feats, cams, hypo
