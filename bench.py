@@ -344,44 +344,49 @@ def main():
         tot_t = sum(p["us"] for p in per_stage) * 1e-6
         dom = per_stage[3]
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
-        # (profiles/r01_et_fuse_tiled_v3_ncu.md: 55.0 MB + 3.18 MB; the 21 MB cost volume mostly stays in the 126 MB L2)
-        roof = {"kernel": "et_fuse_tiled_kernel<C=8,G=4,D=4,LPP=1> (stage 4 launch: C=8, G=4, D=4, 4 source views, 327680 pixels)", "bound": "hbm",
+        # (profiles/r01_et_fuse_win_ncu.md: 55.0 MB + 3.67 MB; the 21 MB cost volume mostly stays in the 126 MB L2)
+        win = os.environ.get("MVSTER_ET_WIN", "1") != "0"
+        roof = {"kernel": ("et_fuse_win_kernel<C=8,G=4,D=4,LPP=1>" if win else "et_fuse_tiled_kernel<C=8,G=4,D=4,LPP=1>") +
+                          " (stage 4 launch: C=8, G=4, D=4, 4 source views, 327680 pixels)", "bound": "hbm",
                 "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "peak_source": peak_src,
-                "algorithmic_bytes": dom["bytes"], "traffic": 58.18e6 if (B, NV, H, W) == (1, 5, 512, 640) else None, "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak,
+                "algorithmic_bytes": dom["bytes"], "traffic": (58.67e6 if win else 58.18e6) if (B, NV, H, W) == (1, 5, 512, 640) else None, "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak,
                                                  "bytes": tot_b, "us": tot_t * 1e6},
                 "per_stage": per_stage}
 
     # ---- the convolution kernel that holds most of the step time (profiles/r01_launches_tc3.md): tensor-pipe view.
     # One launch of reg2d conv2 at stage 4 (16 -> 16 channels, 3x3x3, D x H/2 x W/2 voxels), timed alone like the ET launches.
     roof_tc = None
-    if rank == 0 and model.reg_precision == "3xbf16":
+    if rank == 0 and model.reg_precision in ("3xbf16", "2xfp16"):
         from mvster_b200 import packing
         tf_peak = tensor_peak()
+        split = 2 if model.reg_precision == "2xfp16" else 3
         vox = (B, D_K[3], H // 2, W // 2)
         xin = torch.randn(*vox, 16, device=dev)
-        wp = packing.pack_tc3_weights(torch.randn(27, 16, 16) / 20.0, 3, 3, 1).to(dev)
+        wp = packing.pack_tc3_weights(torch.randn(27, 16, 16) / 20.0, 3, 3, 1, split).to(dev)
         bias = torch.zeros(16, device=dev)
         yout = torch.empty(*vox, 16, device=dev)
         for _ in range(3):
-            capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout)
+            capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout, split=split)
         ts = []
         for _ in range(20):
             flush.fill_(1.0)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout)
+            capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout, split=split)
             e.record()
             torch.cuda.synchronize()
             ts.append(s.elapsed_time(e))
         t = statistics.mean(ts)
         flops = 2.0 * vox[0] * vox[1] * vox[2] * vox[3] * 27 * 16 * 16
-        roof_tc = {"kernel": "conv_tc3_kernel<16> (reg2d conv2 at stage 4: 16 -> 16 channels, 3x3x3, %d voxels)" % (vox[0] * vox[1] * vox[2] * vox[3]),
+        roof_tc = {"kernel": "conv_tc3_kernel<16,%d> (reg2d conv2 at stage 4: 16 -> 16 channels, 3x3x3, %d voxels)" % (split, vox[0] * vox[1] * vox[2] * vox[3]),
                    "bound": "tensor", "achieved": flops / (t * 1e-3) / 1e12, "peak": tf_peak[0], "unit": "TFLOP/s",
                    "frac": flops / (t * 1e-3) / 1e12 / tf_peak[0], "peak_source": tf_peak[1], "us": t * 1e3,
                    "algorithmic_flops": flops,
-                   "note": "fp32-faithful conv flops; the kernel issues 6 bf16 products per fp32 product (3 MMAs of N = 48/32/16 per tap and "
-                           "16 channels) and is bound by the 4 KB A-operand fetch of each M128 x K16 MMA, not by the multipliers "
-                           "(profiles/r01_conv_tc3_ncu.md)", "traffic": None}
+                   "note": ("fp32-faithful conv flops; the kernel issues 3 fp16 products per fp32 product (2 MMAs of N = 32/16 per tap and 16 channels)"
+                            if split == 2 else
+                            "fp32-faithful conv flops; the kernel issues 6 bf16 products per fp32 product (3 MMAs of N = 48/32/16 per tap and 16 channels)") +
+                           "; every M128 x K16 MMA is bound by its 4 KB A-operand fetch from shared memory, not by the multipliers, and the"
+                           " layer by the activation ring's latency (profiles/r01_conv_tc3_h16_ncu.md)", "traffic": None}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

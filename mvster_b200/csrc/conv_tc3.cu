@@ -28,6 +28,8 @@
 // (or 2 x fp16) converters, warps 11-14 = epilogue.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace mvster {
 namespace tc3 {
@@ -63,6 +65,12 @@ struct Args {
     int D, Ho, Wo, cout, relu, sx, nstage, T, tiles_x, tiles_per_plane, groups_per_plane, total_groups, zero_a;
     // epilogue addressing (see there): ncls column blocks of Cout channels; up = 2 for the depth-to-space scatter of a transposed conv
     int ncls, py0, up, lg_cout, cls_a, cls_b;
+    // MVSTER_TC3_DEBUG (stage ablation for profiling; results are garbage): 1 = epilogue without global loads/stores,
+    // 2 = converters only hand the slots over, 8 = no activation loads
+    int debug;
+    // resident != 0: the layer's nslab weight slabs fit in shared memory next to the rings - they are loaded once per CTA and
+    // stay; otherwise they stream through a ring of NB slabs per group of tiles (large Cin * taps * Cout)
+    int resident, nslab;
 };
 
 // plain / planar-block / depth-to-space output addressing of a launch; false if an offset would not fit 32 bits
@@ -84,7 +92,8 @@ struct Cfg {
     static constexpr int NA = NC >= 64 ? 6 : 8;             // 16-bit operand ring (tile-stages)
     static constexpr int A_BYTES = NS * A_SPLIT;            // a1 | a2 | a3   (NS = 2: a1 | a2)
     static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 x 16 bit]
-    static constexpr int SMEM = 1024 + NF * F_BYTES + NA * A_BYTES + NB * B_BYTES + 512;
+    static constexpr int SMEM_FIXED = 1024 + NF * F_BYTES + NA * A_BYTES + 512;  // alignment slack, rings, barriers; + weight slabs
+    static constexpr int SMEM_MAX = 232448;                                         // 227 KB opt-in limit per CTA on sm_100
 };
 
 __device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
@@ -110,6 +119,37 @@ __device__ __forceinline__ void split2h(float x, float y, uint32_t& t1, uint32_t
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(t2) : "f"(ry), "f"(rx));
 }
 
+// All MMAs of one tile and one tap in ONE asm block: the three (two) A descriptors differ by a constant, the accumulator
+// blocks by a constant column offset, and every other operand is an immediate - so the issuing thread spends one add and the
+// register -> uniform-register moves of (lo, d) per tile instead of re-materialising every operand per MMA (the issue thread,
+// not the tensor pipe, bounded the N <= 32 layers: ncu source page, profiles/r01_conv_tc3_h16_ncu.md).
+template <int NC, int NS>
+__device__ __forceinline__ void mma_tile(uint32_t lo, uint64_t bd, uint32_t d, uint32_t accumulate) {
+    constexpr uint32_t A_HI32 = (uint32_t)((HW_ * 16) >> 4) | (1u << 14);
+    if constexpr (NS == 3) {
+        asm volatile(
+            "{\n\t.reg .pred pa, pt;\n\t.reg .b32 l2, l3;\n\t.reg .b64 a1, a2, a3;\n\t"
+            "setp.ne.b32 pa, %3, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+            "add.u32 l2, %1, %4;\n\tadd.u32 l3, %1, %5;\n\t"
+            "mov.b64 a1, {%1, %6};\n\tmov.b64 a2, {l2, %6};\n\tmov.b64 a3, {l3, %6};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, %2, %7, pa;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, %2, %8, pt;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, %2, %9, pt;\n\t}"
+            ::"r"(d), "r"(lo), "l"(bd), "r"(accumulate), "n"(A_SPLIT >> 4), "n"(2 * A_SPLIT >> 4), "n"(A_HI32),
+              "n"(idesc_bf16_m128(3 * NC)), "n"(idesc_bf16_m128(2 * NC)), "n"(idesc_bf16_m128(NC)) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred pa, pt;\n\t.reg .b32 l2, d2;\n\t.reg .b64 a1, a2;\n\t"
+            "setp.ne.b32 pa, %3, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+            "add.u32 l2, %1, %4;\n\tadd.u32 d2, %0, %5;\n\t"
+            "mov.b64 a1, {%1, %6};\n\tmov.b64 a2, {l2, %6};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, %2, %7, pa;\n\t"   // a1 x [w1|w2]: block 0 = a1 w1, block 1 = a1 w2
+            "tcgen05.mma.cta_group::1.kind::f16 [d2], a2, %2, %8, pt;\n\t}"  // a2 x [w1] onto block 1
+            ::"r"(d), "r"(lo), "l"(bd), "r"(accumulate), "n"(A_SPLIT >> 4), "n"(NC), "n"(A_HI32),
+              "n"(idesc_f16_m128(2 * NC)), "n"(idesc_f16_m128(NC)) : "memory");
+    }
+}
+
 template <int NC, int NS>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ Plan plan, const Args a) {
@@ -118,7 +158,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t f_base = base, a_base = f_base + NF * F_BYTES, b_base = a_base + C::NA * A_BYTES, bar_base = b_base + NB * C::B_BYTES;
+    const uint32_t f_base = base, a_base = f_base + NF * F_BYTES, bar_base = a_base + C::NA * A_BYTES, b_base = bar_base + 512;
     auto F_FULL = [&](uint32_t s) { return bar_base + 8u * s; };
     auto F_EMPTY = [&](uint32_t s) { return bar_base + 8u * (NF + s); };
     auto A_FULL = [&](uint32_t s) { return bar_base + 8u * (2 * NF + s); };
@@ -169,6 +209,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     for (int t = 0; t < Tg; ++t, ++fu) {
                         const uint32_t fs = fu % NF;
                         mbar_wait(F_EMPTY(fs), ((fu / NF) & 1) ^ 1);
+                        if (a.debug & 8) { mbar_arrive(F_FULL(fs)); continue; }
                         mbar_expect_tx(F_FULL(fs), st.nq * QBYTES);
                         const int ti = tile0 + t, y0 = (ti / a.tiles_x) * TH, x0 = (ti % a.tiles_x) * TW;
                         // one box = [18][10] pixels x min(Cin,16) channels (64-byte rows); the converters re-lay it out for the MMA
@@ -180,18 +221,24 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
     } else if (warp == 2) {
         // ------------------------------------------------------------------ weight producer (one bulk copy per (stage, tap))
         if (elect_one()) {
-            uint32_t bu = 0;
-            for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
-                MVSTER_TC3_GROUP_HEAD
-                (void)tile0; (void)Tg;
-                for (int s = 0; s < a.nstage; ++s) {
-                    if (MVSTER_TC3_STAGE_SKIP(s)) continue;
-                    const int ntap = plan.st[s].ntap, slab0 = plan.st[s].slab0;
-                    for (int tap = 0; tap < ntap; ++tap, ++bu) {
-                        const uint32_t sb = bu % NB;
-                        mbar_wait(B_EMPTY(sb), ((bu / NB) & 1) ^ 1);
-                        mbar_expect_tx(B_FULL(sb), C::B_BYTES);
-                        bulk_load(b_base + sb * C::B_BYTES, a.w + (size_t)(slab0 + tap) * C::B_BYTES, C::B_BYTES, B_FULL(sb));
+            if (a.resident) {  // the whole layer once: B_FULL(0) completes when every slab has landed
+                mbar_expect_tx(B_FULL(0), (uint32_t)a.nslab * C::B_BYTES);
+                for (int i = 0; i < a.nslab; ++i)
+                    bulk_load(b_base + i * C::B_BYTES, a.w + (size_t)i * C::B_BYTES, C::B_BYTES, B_FULL(0));
+            } else {
+                uint32_t bu = 0;
+                for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
+                    MVSTER_TC3_GROUP_HEAD
+                    (void)tile0; (void)Tg;
+                    for (int s = 0; s < a.nstage; ++s) {
+                        if (MVSTER_TC3_STAGE_SKIP(s)) continue;
+                        const int ntap = plan.st[s].ntap, slab0 = plan.st[s].slab0;
+                        for (int tap = 0; tap < ntap; ++tap, ++bu) {
+                            const uint32_t sb = bu % NB;
+                            mbar_wait(B_EMPTY(sb), ((bu / NB) & 1) ^ 1);
+                            mbar_expect_tx(B_FULL(sb), C::B_BYTES);
+                            bulk_load(b_base + sb * C::B_BYTES, a.w + (size_t)(slab0 + tap) * C::B_BYTES, C::B_BYTES, B_FULL(sb));
+                        }
                     }
                 }
             }
@@ -202,12 +249,18 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
         // elect / descriptor rebuild / warp sync the issue thread needed ~1000 cycles per tap whatever the MMA sizes and the
         // tensor pipe idled a third of the time (ncu source page, profiles/r01_conv_tc3_ncu.md).
         if (elect_one()) {
-            constexpr uint32_t ID3 = idesc_bf16_m128(3 * NC), ID2 = idesc_bf16_m128(2 * NC), ID1 = idesc_bf16_m128(NC);
-            constexpr uint32_t IH2 = idesc_f16_m128(2 * NC), IH1 = idesc_f16_m128(NC);
             // descriptor = (hi << 32) | lo; lo = start address >> 4 | LBO >> 4 << 16 (taps / splits / slots only move the address)
-            constexpr uint64_t A_HI = (uint64_t)((HW_ * 16) >> 4) | (1ull << 14), B_HI = (uint64_t)(128 >> 4) | (1ull << 14);
+            constexpr uint64_t B_HI = (uint64_t)(128 >> 4) | (1ull << 14);
             constexpr uint32_t B_LBO = (uint32_t)((3 * NC * 16) >> 4) << 16;  // the A operand's LBO comes with each tap (plan.a_desc)
+            // the role is instantiated twice (weights resident / streamed) so that the tap loop carries no mode test: with one
+            // tile per group (N >= 64) the issue thread's ~40 instructions per tap cost as much as the tap's MMAs
+            auto run_role = [&](auto resident_tag) {
+            constexpr bool RES = decltype(resident_tag)::value;
             uint32_t a_slot = 0, a_par = 0, b_slot = 0, b_par = 0, gc = 0;
+            if constexpr (RES) {
+                mbar_wait(B_FULL(0), 0);
+                tc_fence_after();
+            }
             for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x, ++gc) {
                 MVSTER_TC3_GROUP_HEAD
                 const uint32_t set = gc & 1;
@@ -226,28 +279,32 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                             aslot[t] = a_slot;
                             alo[t] = ((a_base + a_slot * A_BYTES) & 0x3FFFFu) >> 4;
                             if (++a_slot == C::NA) { a_slot = 0; a_par ^= 1; }
+                        } else {
+                            alo[t] = alo[0];
                         }
                     tc_fence_after();
+                    uint32_t b_res = b_base + (uint32_t)plan.st[s].slab0 * C::B_BYTES;  // resident: this stage's first slab
+#pragma unroll 1
                     for (int tap = 0; tap < ntap; ++tap) {
-                        mbar_wait(B_FULL(b_slot), b_par);
-                        tc_fence_after();
-                        const uint64_t bd = (B_HI << 32) | ((((b_base + b_slot * C::B_BYTES) & 0x3FFFFu) >> 4) | B_LBO);
-                        const uint32_t shift = plan.a_desc[s][tap];  // start shift (bits 0-13) + LBO (bits 16-29): one add per MMA
+                        uint32_t b_addr;
+                        if constexpr (RES) {
+                            b_addr = b_res;
+                            b_res += C::B_BYTES;
+                        } else {
+                            mbar_wait(B_FULL(b_slot), b_par);
+                            tc_fence_after();
+                            b_addr = b_base + b_slot * C::B_BYTES;
+                        }
+                        const uint64_t bd = (B_HI << 32) | (((b_addr & 0x3FFFFu) >> 4) | B_LBO);
+                        const uint32_t shift = plan.a_desc[s][tap];  // start shift (bits 0-13) + LBO (bits 16-29): one add per tile
+                        // every tile slot of the group is issued, also past Tg (a ragged last group of a plane): alo[] then repeats
+                        // tile 0's operands and the MMAs land in accumulator columns the epilogue never reads - straight-line code
 #pragma unroll
-                        for (int t = 0; t < C::TMAX; ++t)
-                            if (t < Tg) {
-                                const uint32_t lo = alo[t] + shift, d = d0 + (uint32_t)(t * 3 * NC);
-                                if constexpr (NS == 3) {
-                                    umma_bf16(d, (A_HI << 32) | lo, bd, ID3, accumulate);                           // a1 x [w1|w2|w3]
-                                    umma_bf16(d, (A_HI << 32) | (lo + (A_SPLIT >> 4)), bd, ID2, 1u);                // a2 x [w1|w2]
-                                    umma_bf16(d, (A_HI << 32) | (lo + (2 * A_SPLIT >> 4)), bd, ID1, 1u);            // a3 x [w1]
-                                } else {  // fp16 terms: block 0 += a1 w1, block 1 += a1 w2 + a2 w1
-                                    umma_bf16(d, (A_HI << 32) | lo, bd, IH2, accumulate);                           // a1 x [w1|w2]
-                                    umma_bf16(d + (uint32_t)NC, (A_HI << 32) | (lo + (A_SPLIT >> 4)), bd, IH1, 1u); // a2 x [w1] -> block 1
-                                }
-                            }
-                        umma_commit(B_EMPTY(b_slot));
-                        if (++b_slot == NB) { b_slot = 0; b_par ^= 1; }
+                        for (int t = 0; t < C::TMAX; ++t) mma_tile<NC, NS>(alo[t] + shift, bd, d0 + (uint32_t)(t * 3 * NC), accumulate);
+                        if constexpr (!RES) {
+                            umma_commit(B_EMPTY(b_slot));
+                            if (++b_slot == NB) { b_slot = 0; b_par ^= 1; }
+                        }
                         accumulate = 1;
                     }
 #pragma unroll
@@ -256,6 +313,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                 }
                 umma_commit(ACC_FULL(set));
             }
+            };
+            if (a.resident) run_role(std::true_type{});
+            else run_role(std::false_type{});
         }
     } else if (warp < 3 + NCONV / 32) {
         // ------------------------------------------------------------------ converters: fp32 halo tile -> a1 | a2 | a3 (bf16)
@@ -276,6 +336,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     const uint8_t* F = smem_raw + (f_base + fs * F_BYTES - raw);
                     uint8_t* A = smem_raw + (a_base + as * A_BYTES - raw);
                     // item = one channel quad of one halo pixel = 16 contiguous bytes of F; <= 6 items per thread, all loads first
+                    if (a.debug & 2) {
+                        mbar_arrive(A_FULL(as));
+                        mbar_arrive(F_EMPTY(fs));
+                        continue;
+                    }
                     constexpr int IT = (HPIX * 4 + CTEAM - 1) / CTEAM;
                     float4 v[IT];
 #pragma unroll
@@ -323,7 +388,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
             tc_fence_after();
             for (int t = 0; t < Tg; ++t) {
                 const int ti = tile0 + t, yy = (ti / a.tiles_x) * TH + r / TW, xx = (ti % a.tiles_x) * TW + r % TW;
-                const bool ok = yy < a.Ho && xx < a.Wo;
+                const bool ok = yy < a.Ho && xx < a.Wo && !(a.debug & 1);
                 const uint32_t col = tmem_base + ((uint32_t)(q * 32) << 16) + set * 256u + (uint32_t)(t * 3 * NC);
                 const int ncol = a.ncls * a.cout;
                 // Column c = class * Cout + channel (Cout a power of two).  Plain conv: one class.  Transposed conv (depth-to-space,
@@ -486,13 +551,17 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
     a.groups_per_plane = ceil_div(a.tiles_per_plane, T);
     a.total_groups = (int)(total_tiles / a.tiles_per_plane) * a.groups_per_plane;
     auto k = conv_tc3_kernel<NC, NS>;
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
-        set_error("conv_tc3_kernel: cannot reserve %d bytes of shared memory", C::SMEM);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_MAX) != cudaSuccess) {
+        set_error("conv_tc3_kernel: cannot reserve %d bytes of shared memory", C::SMEM_MAX);
         cudaGetLastError();
         return MVSTER_ERR_CUDA;
     }
+    // weights resident in shared memory when the whole layer fits next to the rings (MVSTER_TC3_STREAM=1 forces the ring)
+    static const bool force_stream = getenv("MVSTER_TC3_STREAM") && atoi(getenv("MVSTER_TC3_STREAM")) != 0;
+    a.resident = !force_stream && a.nslab > 0 && C::SMEM_FIXED + a.nslab * C::B_BYTES <= C::SMEM_MAX;
+    const int smem = C::SMEM_FIXED + (a.resident ? a.nslab : NB) * C::B_BYTES;
     const int grid = a.total_groups < sms ? a.total_groups : sms;
-    k<<<grid, THREADS, C::SMEM, st>>>(xm, plan, a);
+    k<<<grid, THREADS, smem, st>>>(xm, plan, a);
     return check_launch("conv_tc3_kernel");
 }
 
@@ -559,14 +628,16 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     }
     Plan plan;
     memset(&plan, 0, sizeof(plan));
-    build_plan(Cin, kd, k, s, &plan, nullptr);
+    const int nslab = build_plan(Cin, kd, k, s, &plan, nullptr);
     Args a;
+    a.nslab = nslab;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
     const bool fp16x2 = relu & MVSTER_TC3_FP16X2;
     a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = relu & 1; a.sx = s;
     a.nstage = kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16);
     a.tiles_x = ceil_div(a.Wo, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(a.Ho, TH);
+    { const char* dbg = getenv("MVSTER_TC3_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     a.zero_a = Cin < 8;  // Cin = 4: each 16-byte row holds 4 real channels, the other 4 must read as zero (Cin = 8 fills the one plane it reads)
     const bool blocks = block > 0 && block < Cout;
     if (blocks) a.cout = block;
@@ -661,9 +732,11 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
     const bool fp16x2 = relu & MVSTER_TC3_FP16X2;
     a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = relu & 1; a.sx = 1; a.nstage = kch;
+    a.nslab = kch * ntap;
     a.tiles_x = ceil_div(W, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
     a.zero_a = 0;
+    { const char* dbg = getenv("MVSTER_TC3_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
     MVSTER_REQUIRE(set_output_mode(a, deconv_ncls(rows), rows == 1 ? 1 : 0, true, 0), "mvster_deconv_tc3_f32: output row pitch does not fit 32 bits");
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
     cudaStream_t st = (cudaStream_t)stream;

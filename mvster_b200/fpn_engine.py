@@ -97,6 +97,8 @@ def _conv3x3(x: Tensor, wts: Dict[str, Tensor], name: str, relu: bool, npass: in
     if npass and gen == 3 and (name + ".tc3") in wts:
         return _conv_tc3(x, wts, name, 3, 1, relu, 2 if npass == 2 else 3)
     w, b = wts[name + ".w"], wts.get(name + ".b")
+    if npass == 2:
+        npass = 3  # a layer without generation-3 weights (the literal out4): 3xTF32 on the generation-2 kernel
     if npass and (name + ".tc") in wts:
         N, H, W, Cin = x.shape
         tc = wts[name + ".tc"]
