@@ -45,7 +45,7 @@ constexpr int NCONV = 256;                 // converter threads (8 warps: one wa
 constexpr int CTEAM = NCONV / 2;           // ... in two teams that take alternate tile-stages
 constexpr int THREADS = 96 + NCONV + 128;
 constexpr int MAX_STAGES = 16, MAX_TAPS = 9;
-constexpr int NF = 8, NF_MIN = 4, NB = 10;  // NF: most fp32 staging tiles in flight (barrier layout); a launch uses Args::nf of them
+constexpr int NF = 4, NB = 10;
 
 struct Stage {
     short c0, nq, ox, oy, dz, ntap, slab0, pad;
@@ -71,8 +71,6 @@ struct Args {
     // resident != 0: the layer's nslab weight slabs fit in shared memory next to the rings - they are loaded once per CTA and
     // stay; otherwise they stream through a ring of NB slabs per group of tiles (large Cin * taps * Cout)
     int resident, nslab;
-    // fp32 staging ring depth, NF_MIN..NF halo tiles in flight (default NF_MIN; see launch_ns)
-    int nf;
 };
 
 // plain / planar-block / depth-to-space output addressing of a launch; false if an offset would not fit 32 bits
@@ -94,7 +92,7 @@ struct Cfg {
     static constexpr int NA = NC >= 64 ? 6 : 8;             // 16-bit operand ring (tile-stages)
     static constexpr int A_BYTES = NS * A_SPLIT;            // a1 | a2 | a3   (NS = 2: a1 | a2)
     static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 x 16 bit]
-    static constexpr int SMEM_FIXED = 1024 + NA * A_BYTES + 512;  // alignment slack, operand ring, barriers; + staging ring + weight slabs
+    static constexpr int SMEM_FIXED = 1024 + NF * F_BYTES + NA * A_BYTES + 512;  // alignment slack, rings, barriers; + weight slabs
     static constexpr int SMEM_MAX = 232448;                                         // 227 KB opt-in limit per CTA on sm_100
 };
 
@@ -160,8 +158,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t nf = (uint32_t)a.nf;
-    const uint32_t f_base = base, a_base = f_base + nf * F_BYTES, bar_base = a_base + C::NA * A_BYTES, b_base = bar_base + 512;
+    const uint32_t f_base = base, a_base = f_base + NF * F_BYTES, bar_base = a_base + C::NA * A_BYTES, b_base = bar_base + 512;
     auto F_FULL = [&](uint32_t s) { return bar_base + 8u * s; };
     auto F_EMPTY = [&](uint32_t s) { return bar_base + 8u * (NF + s); };
     auto A_FULL = [&](uint32_t s) { return bar_base + 8u * (2 * NF + s); };
@@ -210,8 +207,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     if (MVSTER_TC3_STAGE_SKIP(s)) continue;  // depth padding: the plane contributes nothing
                     const Stage st = plan.st[s];
                     for (int t = 0; t < Tg; ++t, ++fu) {
-                        const uint32_t fs = fu % nf;
-                        mbar_wait(F_EMPTY(fs), ((fu / nf) & 1) ^ 1);
+                        const uint32_t fs = fu % NF;
+                        mbar_wait(F_EMPTY(fs), ((fu / NF) & 1) ^ 1);
                         if (a.debug & 8) { mbar_arrive(F_FULL(fs)); continue; }
                         mbar_expect_tx(F_FULL(fs), st.nq * QBYTES);
                         const int ti = tile0 + t, y0 = (ti / a.tiles_x) * TH, x0 = (ti % a.tiles_x) * TW;
@@ -333,8 +330,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                 const int nq = plan.st[s].nq, items = HPIX * nq, qsh = nq >> 1;  // nq in {1,2,4}: pixel = item >> qsh
                 for (int t = 0; t < Tg; ++t, ++u) {
                     if ((int)(u & 1) != team) continue;
-                    const uint32_t fs = u % nf, as = u % C::NA;
-                    mbar_wait(F_FULL(fs), (u / nf) & 1);
+                    const uint32_t fs = u % NF, as = u % C::NA;
+                    mbar_wait(F_FULL(fs), (u / NF) & 1);
                     mbar_wait(A_EMPTY(as), ((u / C::NA) & 1) ^ 1);
                     const uint8_t* F = smem_raw + (f_base + fs * F_BYTES - raw);
                     uint8_t* A = smem_raw + (a_base + as * A_BYTES - raw);
@@ -561,16 +558,8 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
     }
     // weights resident in shared memory when the whole layer fits next to the rings (MVSTER_TC3_STREAM=1 forces the ring)
     static const bool force_stream = getenv("MVSTER_TC3_STREAM") && atoi(getenv("MVSTER_TC3_STREAM")) != 0;
-    a.resident = !force_stream && a.nslab > 0 && C::SMEM_FIXED + NF_MIN * F_BYTES + a.nslab * C::B_BYTES <= C::SMEM_MAX;
-    const int smem_rest = C::SMEM_FIXED + (a.resident ? a.nslab : NB) * C::B_BYTES;
-    // measured on B200 (cfg2): a deeper ring does NOT pay - 8 slots 1.568 ms/step vs 4 slots 1.539 (16 -> 16 full-resolution layer
-    // 72.7 -> 80.7 us) - so 4 stays the default and MVSTER_TC3_NF (up to 8) only exists for experiments
-    static const int nf_cap = getenv("MVSTER_TC3_NF") ? atoi(getenv("MVSTER_TC3_NF")) : NF_MIN;
-    a.nf = (C::SMEM_MAX - smem_rest) / F_BYTES;
-    if (a.nf > nf_cap) a.nf = nf_cap;
-    if (a.nf > NF) a.nf = NF;
-    if (a.nf < NF_MIN) a.nf = NF_MIN;
-    const int smem = smem_rest + a.nf * F_BYTES;
+    a.resident = !force_stream && a.nslab > 0 && C::SMEM_FIXED + a.nslab * C::B_BYTES <= C::SMEM_MAX;
+    const int smem = C::SMEM_FIXED + (a.resident ? a.nslab : NB) * C::B_BYTES;
     const int grid = a.total_groups < sms ? a.total_groups : sms;
     k<<<grid, THREADS, smem, st>>>(xm, plan, a);
     return check_launch("conv_tc3_kernel");
