@@ -4,4 +4,6 @@ See DESIGN.md for scope and INTEGRATION.md for the drop-in recipe."""
 from .network import MVS4net  # noqa: F401
 from .losses import MVS4net_loss, Blend_loss  # noqa: F401
 
-__all__ = ["MVS4net", "MVS4net_loss", "Blend_loss"]
+from . import formats  # noqa: F401  (PFM / camera-file / pair-list I/O compatible with the reference's datasets package)
+
+__all__ = ["MVS4net", "MVS4net_loss", "Blend_loss", "formats"]

@@ -1,0 +1,127 @@
+"""On-disk formats either side of the forward path (SURVEY.md 8f "next" #4): PFM depth / confidence maps, MVSNet camera
+files, pair lists, and the per-stage projection stack the forward consumes.
+
+Byte-compatible with the reference's readers and writers (``datasets/data_io.py:6-71``, ``datasets/general_eval4.py:25-79,
+155-183``): a file written here is read back identically by the reference and vice versa (tests/test_formats.py pins both
+directions against fixtures written by the unmodified reference).  Pure numpy, no GPU.
+"""
+from __future__ import annotations
+
+import re
+import sys
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+
+def read_pfm(filename: str) -> Tuple[np.ndarray, float]:
+    """``datasets/data_io.py:6-40``.  Returns (image [H,W] or [H,W,3] float32 in the FILE's byte order, top row first; scale).
+    Header: ``PF``/``Pf``, ``width height``, signed scale (negative = little-endian); rows are stored bottom-up."""
+    with open(filename, "rb") as f:
+        header = f.readline().decode("utf-8").rstrip()
+        if header == "PF":
+            color = True
+        elif header == "Pf":
+            color = False
+        else:
+            raise Exception("Not a PFM file.")
+        m = re.match(r"^(\d+)\s(\d+)\s$", f.readline().decode("utf-8"))
+        if not m:
+            raise Exception("Malformed PFM header.")
+        width, height = map(int, m.groups())
+        scale = float(f.readline().rstrip())
+        endian = "<" if scale < 0 else ">"
+        scale = abs(scale)
+        data = np.frombuffer(f.read(), dtype=endian + "f4")
+    shape = (height, width, 3) if color else (height, width)
+    if data.size != int(np.prod(shape)):
+        raise Exception(f"PFM payload holds {data.size} floats, header says {shape}")
+    return np.flipud(data.reshape(shape)), scale
+
+
+def save_pfm(filename: str, image: np.ndarray, scale: float = 1) -> None:
+    """``datasets/data_io.py:43-71``: float32 [H,W], [H,W,1] or [H,W,3]; rows written bottom-up, scale sign = byte order."""
+    if image.dtype.name != "float32":
+        raise Exception("Image dtype must be float32.")
+    if image.ndim == 3 and image.shape[2] == 3:
+        color = True
+    elif image.ndim == 2 or (image.ndim == 3 and image.shape[2] == 1):
+        color = False
+    else:
+        raise Exception("Image must have H x W x 3, H x W x 1 or H x W dimensions.")
+    endian = image.dtype.byteorder
+    if endian == "<" or (endian == "=" and sys.byteorder == "little"):
+        scale = -scale
+    with open(filename, "wb") as f:
+        f.write(b"PF\n" if color else b"Pf\n")
+        f.write(f"{image.shape[1]} {image.shape[0]}\n".encode("utf-8"))
+        f.write(("%f\n" % scale).encode("utf-8"))
+        f.write(np.ascontiguousarray(np.flipud(image)).tobytes())
+
+
+def read_cam_file(filename: str, interval_scale: float = 1.0, ndepths: int = 192):
+    """``datasets/general_eval4.py:59-79``: (intrinsics [3,3] already divided by 4 in its first two rows, extrinsics [4,4],
+    depth_min, depth_interval).  With a third number on the depth line the interval is re-derived from it for ``ndepths``."""
+    with open(filename) as f:
+        lines = [line.rstrip() for line in f.readlines()]
+    extrinsics = np.array(" ".join(lines[1:5]).split(), dtype=np.float32).reshape(4, 4)
+    intrinsics = np.array(" ".join(lines[7:10]).split(), dtype=np.float32).reshape(3, 3)
+    intrinsics[:2, :] /= 4.0
+    tokens = lines[11].split()
+    depth_min, depth_interval = float(tokens[0]), float(tokens[1])
+    if len(tokens) >= 3:
+        depth_max = depth_min + int(float(tokens[2])) * depth_interval
+        depth_interval = (depth_max - depth_min) / ndepths
+    depth_interval *= interval_scale
+    return intrinsics, extrinsics, depth_min, depth_interval
+
+
+def write_cam_file(filename: str, extrinsics: np.ndarray, intrinsics: np.ndarray, depth_min: float, depth_interval: float) -> None:
+    """The MVSNet ``*_cam.txt`` layout ``read_cam_file`` parses (``intrinsics`` at FULL scale: the reader divides by 4)."""
+    with open(filename, "w") as f:
+        f.write("extrinsic\n")
+        for r in np.asarray(extrinsics, dtype=np.float64).reshape(4, 4):
+            f.write(" ".join(repr(float(x)) for x in r) + " \n")
+        f.write("\nintrinsic\n")
+        for r in np.asarray(intrinsics, dtype=np.float64).reshape(3, 3):
+            f.write(" ".join(repr(float(x)) for x in r) + " \n")
+        f.write(f"\n{float(depth_min)!r} {float(depth_interval)!r} \n")
+
+
+def read_pair_file(filename: str, nviews: int) -> List[Tuple[int, List[int]]]:
+    """``datasets/general_eval4.py:36-52``: [(reference view, source views)], views without sources dropped, short lists padded
+    with their first source view up to ``nviews``."""
+    metas = []
+    with open(filename) as f:
+        n = int(f.readline())
+        for _ in range(n):
+            ref = int(f.readline().rstrip())
+            src = [int(x) for x in f.readline().rstrip().split()[1::2]]
+            if src:
+                if len(src) < nviews:
+                    src = src + [src[0]] * (nviews - len(src))
+                metas.append((ref, src))
+    return metas
+
+
+def stage_projections(extrinsics: Sequence[np.ndarray], intrinsics: Sequence[np.ndarray]) -> Dict[str, np.ndarray]:
+    """``datasets/general_eval4.py:155-183``: per view ``[2,4,4]`` (slot 0 extrinsic, slot 1 intrinsic in the top-left 3x3) at
+    the stage-2 (quarter) scale the cam reader delivers; stage 1 halves, stages 3 / 4 double / quadruple intrinsic rows 0-1."""
+    mats = np.zeros((len(extrinsics), 2, 4, 4), np.float32)
+    for v, (e, k) in enumerate(zip(extrinsics, intrinsics)):
+        mats[v, 0, :4, :4] = e
+        mats[v, 1, :3, :3] = k
+    out = {}
+    for name, s in (("stage1", 0.5), ("stage2", 1.0), ("stage3", 2.0), ("stage4", 4.0)):
+        m = mats.copy()
+        if s == 0.5:
+            m[:, 1, :2, :] = mats[:, 1, :2, :] / 2.0
+        elif s != 1.0:
+            m[:, 1, :2, :] = mats[:, 1, :2, :] * s
+        out[name] = m
+    return out
+
+
+def depth_values(depth_min: float, depth_interval: float, ndepths: int = 192) -> np.ndarray:
+    """``datasets/general_eval4.py:164-165``: the evaluation loaders' hypothesis list (the forward reads its first and last entry)."""
+    return np.arange(depth_min, depth_interval * (ndepths - 0.5) + depth_min, depth_interval, dtype=np.float32)

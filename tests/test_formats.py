@@ -1,0 +1,111 @@
+"""mvster_b200/formats.py (PFM, camera files, pair lists, per-stage projections) against fixtures written / parsed by the
+unmodified reference (tests/golden/make_format_fixtures.py: datasets/data_io.py:6-71, datasets/general_eval4.py:25-79,
+155-183), and - when the reference tree is mounted - against the reference's functions directly."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from util import GOLDEN
+from mvster_b200 import formats
+
+FIX = GOLDEN / "formats"
+
+
+@pytest.mark.parametrize("name,scale", [("depth_6x9", 1.0), ("color_4x5", 2.0), ("big_endian_3x4", 1.0)])
+def test_read_pfm_matches_reference_written_files(name, scale):
+    data, s = formats.read_pfm(str(FIX / f"{name}.pfm"))
+    want = np.load(FIX / f"{name}.npy")
+    assert s == scale
+    assert data.shape == want.shape
+    assert np.array_equal(np.asarray(data, np.float32), want)  # bit-exact
+
+
+@pytest.mark.parametrize("name,scale", [("depth_6x9", 1), ("color_4x5", 2)])
+def test_save_pfm_is_byte_identical_to_the_reference_writer(tmp_path, name, scale):
+    img = np.load(FIX / f"{name}.npy")
+    p = tmp_path / "out.pfm"
+    formats.save_pfm(str(p), img, scale=scale)
+    assert p.read_bytes() == (FIX / f"{name}.pfm").read_bytes()
+    back, s = formats.read_pfm(str(p))
+    assert s == float(scale) and np.array_equal(np.asarray(back, np.float32), img)
+
+
+def test_save_pfm_rejects_what_the_reference_rejects(tmp_path):
+    with pytest.raises(Exception, match="float32"):
+        formats.save_pfm(str(tmp_path / "a.pfm"), np.zeros((2, 2), np.float64))
+    with pytest.raises(Exception, match="dimensions"):
+        formats.save_pfm(str(tmp_path / "a.pfm"), np.zeros((2, 2, 2), np.float32))
+    (tmp_path / "bad.pfm").write_bytes(b"P6\n2 2\n-1.0\n")
+    with pytest.raises(Exception, match="Not a PFM"):
+        formats.read_pfm(str(tmp_path / "bad.pfm"))
+    (tmp_path / "bad2.pfm").write_bytes(b"Pf\n2x2\n-1.0\n")
+    with pytest.raises(Exception, match="Malformed"):
+        formats.read_pfm(str(tmp_path / "bad2.pfm"))
+
+
+def test_single_channel_3d_image_is_written_as_greyscale(tmp_path):
+    img = np.arange(6, dtype=np.float32).reshape(2, 3, 1)
+    formats.save_pfm(str(tmp_path / "g.pfm"), img)
+    back, _ = formats.read_pfm(str(tmp_path / "g.pfm"))
+    assert back.shape == (2, 3) and np.array_equal(back, img[:, :, 0])
+
+
+def test_read_cam_file_matches_the_reference_reader():
+    expected = json.loads((FIX / "cam_expected.json").read_text())
+    for key, want in expected.items():
+        name, scale, nd = key.split("|")
+        k, e, dmin, itv = formats.read_cam_file(str(FIX / name), float(scale), int(nd))
+        assert np.array_equal(k, np.array(want["K"], np.float32)), key
+        assert np.array_equal(e, np.array(want["E"], np.float32)), key
+        assert dmin == want["depth_min"] and itv == want["depth_interval"], key
+
+
+def test_cam_file_round_trip(tmp_path):
+    k, e, dmin, itv = formats.read_cam_file(str(FIX / "00000000_cam.txt"))
+    k_full = k.copy()
+    k_full[:2] *= 4.0
+    formats.write_cam_file(str(tmp_path / "c.txt"), e, k_full, dmin, itv)
+    k2, e2, dmin2, itv2 = formats.read_cam_file(str(tmp_path / "c.txt"))
+    assert np.array_equal(k, k2) and np.array_equal(e, e2) and (dmin, itv) == (dmin2, itv2)
+
+
+def test_pair_file_padding_and_dropping():
+    metas = formats.read_pair_file(str(FIX / "pair.txt"), nviews=5)
+    assert metas == [(0, [10, 1, 9, 12, 10]), (2, [0, 1, 0, 0, 0])]  # view 1 has no source views: dropped
+    assert formats.read_pair_file(str(FIX / "pair.txt"), nviews=2)[0] == (0, [10, 1, 9, 12])
+
+
+def test_stage_projections_and_depth_values():
+    cams = [formats.read_cam_file(str(FIX / n)) for n in ("00000000_cam.txt", "00000001_cam.txt")]
+    proj = formats.stage_projections([c[1] for c in cams], [c[0] for c in cams])
+    assert set(proj) == {"stage1", "stage2", "stage3", "stage4"}
+    for name, s in (("stage1", 0.5), ("stage2", 1.0), ("stage3", 2.0), ("stage4", 4.0)):
+        m = proj[name]
+        assert m.shape == (2, 2, 4, 4) and m.dtype == np.float32
+        assert np.array_equal(m[:, 0], np.stack([c[1] for c in cams]))                       # extrinsics untouched
+        assert np.allclose(m[0, 1, :2, :3], cams[0][0][:2] * s, rtol=0, atol=0)               # rows 0-1 scaled (powers of two: exact)
+        assert np.array_equal(m[0, 1, 2, :3], cams[0][0][2]) and not m[:, 1, 3].any() and not m[:, 1, :, 3].any()
+    dv = formats.depth_values(425.0, 2.5 * 1.06, 192)
+    assert dv.dtype == np.float32 and len(dv) == 192 and dv[0] == 425.0
+    assert np.array_equal(dv, np.arange(425.0, 2.5 * 1.06 * 191.5 + 425.0, 2.5 * 1.06, dtype=np.float32))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/datasets"), reason="reference tree not mounted (GPU box)")
+def test_against_the_reference_functions_directly(tmp_path):
+    sys.path.insert(0, "/root/reference")
+    try:
+        from datasets.data_io import read_pfm as ref_read, save_pfm as ref_save
+    finally:
+        sys.path.pop(0)
+    rng = np.random.RandomState(3)
+    for shape in ((5, 7), (3, 4, 3), (8, 2, 1)):
+        img = rng.randn(*shape).astype(np.float32)
+        ref_save(str(tmp_path / "r.pfm"), img, scale=3)
+        formats.save_pfm(str(tmp_path / "o.pfm"), img, scale=3)
+        assert (tmp_path / "r.pfm").read_bytes() == (tmp_path / "o.pfm").read_bytes()
+        a, sa = ref_read(str(tmp_path / "o.pfm"))
+        b, sb = formats.read_pfm(str(tmp_path / "r.pfm"))
+        assert sa == sb == 3.0 and np.array_equal(np.asarray(a), np.asarray(b))

@@ -137,6 +137,37 @@ def test_pack_reg2d_blob_layout():
     assert torch.equal(w, ref_w) and torch.equal(packed["blob"][L["b_off"]:L["b_off"] + 16], ref_b)
 
 
+def test_tc3_weight_slabs_both_arithmetics():
+    """packing.pack_tc3_weights: slab = [2 K-halves][w1 | w2 | w3 rows][8 x 16 bit] per MMA slot, in the plan's order.  The bf16
+    terms (split=3) must sum to the fp32 weight to 24 bits, the fp16 terms (split=2) as w1 + 2^-11 w2 to 22 bits; both blobs
+    have the size the library expects, and the fp16 blob leaves the third row block empty."""
+    from mvster_b200 import _lib, capi
+    torch.manual_seed(5)
+    cin, cout, kd, k = 32, 16, 3, 3
+    w = torch.randn(kd * k * k, cin, cout) / 17.0
+    lib = _lib.load()
+    plan = capi.conv_tc3_plan(cin, kd, k, 1)
+    assert len(plan) == kd * k * k * (cin // 16)
+    for split in (3, 2):
+        blob = packing.pack_tc3_weights(w, kd, k, 1, split)
+        assert blob.numel() * 4 == lib.mvster_conv_tc3_packed_bytes(cin, cout, kd, k, 1)
+        raw = blob.view(torch.int16).reshape(len(plan), 2, 3 * 16, 8)
+        terms = raw.view(torch.bfloat16 if split == 3 else torch.float16).float()
+        for i, (kz, ky, kx, c0, _, _) in enumerate(plan):
+            want = w[(kz * k + ky) * k + kx, c0:c0 + 16, :]                       # [16 channels][Cout]
+            rows = torch.cat([terms[i, 0], terms[i, 1]], dim=1)                    # [3*N rows][16 channels]
+            t1, t2, t3 = rows[0:16].T, rows[16:32].T, rows[32:48].T               # each [16 channels][Cout]
+            if split == 3:
+                got, tol = t1 + t2 + t3, 2.0 ** -23
+            else:
+                got, tol = t1 + t2 / 2048.0, 2.0 ** -21
+                assert not t3.any()
+            # absolute floor 2^-35: below fp16's normal range (|w| < 6.1e-5) the first term is a subnormal, the scaled residual still holds 2^-36
+            assert ((got.double() - want.double()).abs() <= tol * want.abs().double() + 2.0 ** -35).all(), (split, i)
+    t1, t2 = packing.fp16_split2(torch.tensor([1e5, -1e5, 3.0e-6, 0.0]))
+    assert torch.isfinite(t1.float()).all() and torch.isfinite(t2.float()).all()   # out-of-range weights saturate, never inf
+
+
 def test_dropin_models_package_exports_reference_names():
     import importlib
     import sys
