@@ -270,6 +270,19 @@ int mvster_upsample_bilinear_f32(const float* in, float* out, int B, int H, int 
 int mvster_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W,
                             mvster_stream_t stream);
 
+/* ---- geometric-consistency filter (after the forward) ---------------------- */
+/* test_mvs4.py:271-328 (reproject_with_depth + check_geometric_consistency) for one (reference, source) pair, and the
+ * accumulation of filter_depth :362-378.  depth_ref [H][W], depth_src [Hs][Ws] (device, fp32).  mats: HOST array of 60 doubles =
+ * inv(K_ref) 3x3 | (E_src inv(E_ref)) rows 0-2 (3x4) | K_src | inv(K_src) | (E_ref inv(E_src)) rows 0-2 | K_ref, row-major,
+ * computed by the caller the way the reference computes them (float32 numpy).  Outputs (device): depth_reproj [H][W]
+ * (zero where |p_reproj - p| >= dist_thres pixels or |d_reproj - d| / d >= rel_thres); optional x_src, y_src [H][W] (the
+ * float32 source-pixel coordinates), mask [H][W] (uint8); optional accumulators mask_sum (int32, += mask) and depth_sum
+ * (fp32, += depth_reproj).  The source depth is sampled like cv2.remap(INTER_LINEAR): coordinates rounded to 1/32 pixel,
+ * zeros outside the image. */
+int mvster_geo_consistency_f32(const float* depth_ref, const float* depth_src, const double* mats, float* depth_reproj,
+                               float* x_src, float* y_src, unsigned char* mask, int* mask_sum, float* depth_sum,
+                               int H, int W, int Hs, int Ws, float dist_thres, float rel_thres, mvster_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
