@@ -75,15 +75,20 @@ def test_fuse_reference_view_matches_reference(name):
 
 
 def test_identity_pair_and_cuda_tensor_interface():
-    """A view checked against itself reprojects every valid pixel onto itself: mask == (depth > 0), depth unchanged to rounding;
-    CUDA tensors in -> CUDA tensors out."""
+    """A view checked against itself reprojects every pixel with a non-zero depth onto itself (the reference accepts negative
+    depths as well: only d == 0 fails, through 0 / 0): same mask as the CPU oracle, depth unchanged to rounding; CUDA tensors in ->
+    CUDA tensors out."""
     views = fusion_oracle.synthetic_scene(2, 96, 160, seed=3)
     v = views[0]
+    v["depth"][5, 7] = 0.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want_mask, want_d, _, _ = fusion_oracle.check_geometric_consistency(v["depth"].copy(), v["K"], v["E"], v["depth"].copy(), v["K"], v["E"])
     d = torch.from_numpy(v["depth"]).cuda()
     mask, dr, xs, ys = fusion.check_geometric_consistency(d, v["K"], v["E"], d, v["K"], v["E"])
     assert mask.is_cuda and mask.dtype == torch.bool and dr.is_cuda
-    valid = d > 0
-    assert torch.equal(mask, valid)
-    assert ((dr[valid] - d[valid]).abs() <= 1e-5 * d[valid]).all() and not dr[~valid].any()
+    assert np.array_equal(mask.cpu().numpy(), want_mask) and not want_mask[5, 7] and want_mask.mean() > 0.99
+    m = torch.from_numpy(want_mask).cuda()
+    assert ((dr[m] - d[m]).abs() <= 1e-5 * d[m].abs()).all() and not dr[~m].any()
+    assert (dr.cpu().numpy()[want_mask] == want_d[want_mask]).mean() > 0.99
     xx = torch.arange(160, device="cuda", dtype=torch.float32).expand(96, 160)
-    assert ((xs - xx)[valid].abs() < 1e-3).all()
+    assert ((xs - xx)[m].abs() < 1e-3).all()
