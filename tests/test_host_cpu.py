@@ -179,3 +179,26 @@ def test_dropin_models_package_exports_reference_names():
     finally:
         sys.path.remove(str(REPO / "dropin"))
         sys.modules.pop("models", None)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference algorithm on the host cores) runs without a GPU and prints ONE JSON line with
+    the keys the driver reads; under torchrun only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    p = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "depth-maps/s" and j["higher_is_better"] is True and j["value"] > 0
+    assert j["metric"].startswith("depth-maps/sec fwd, 5-view 512") and j["config"]["workload"].startswith("cfg2")
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    quiet = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=60, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert quiet.returncode == 0 and not quiet.stdout.strip()
