@@ -341,289 +341,9 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Software-pipelined variant.  The kernel above waits one full DRAM round trip per source view (ncu: 3.8 long-scoreboard
-// stall cycles per issued instruction with 14 resident warps per SM, DRAM 17 % busy): the taps of view v are requested only
-// after its geometry and consumed right away.  Here the sampling positions of view v+1 are evaluated and its four
-// unconditional window taps requested as soon as the taps of view v have been reduced to their per-group correlations
-// (the tap registers are free again at that point), so the interpolation, softmax and accumulation of view v run under
-// the next view's memory latency.  With prefetch != 0 every lane also issues an L2 prefetch (CCTL.PF2) for the two window
-// rows of every view at the first hypothesis before the loop.
-template <int D>
-__device__ __forceinline__ void win_positions(const float4 q0, const float4 q1, const float4 q2, float fx, float fy,
-                                              const unsigned long long (&dep2)[D / 2], float (&ix)[D], float (&iy)[D]) {
-    const float rx = fmaf(q0.z, 1.f, fmaf(q0.y, fy, q0.x * fx));
-    const float ry = fmaf(q1.y, 1.f, fmaf(q1.x, fy, q0.w * fx));
-    const float nrz = -fmaf(q2.x, 1.f, fmaf(q1.w, fy, q1.z * fx));
-    const float tx = q2.y, ty = q2.z, ntz = -q2.w;
-#pragma unroll
-    for (int k = 0; k < D / 2; ++k) {
-        const float2 dd = unpack2(dep2[k]);
-        const unsigned long long X2 = add2(pack2(__fmul_rn(rx, dd.x), __fmul_rn(rx, dd.y)), pack2(tx, tx));
-        const unsigned long long Y2 = add2(pack2(__fmul_rn(ry, dd.x), __fmul_rn(ry, dd.y)), pack2(ty, ty));
-        float2 zn = unpack2(add2(pack2(__fmul_rn(nrz, dd.x), __fmul_rn(nrz, dd.y)), pack2(ntz, ntz)));  // -Z
-        if (zn.x == 0.f) zn.x = -1e-9f;
-        if (zn.y == 0.f) zn.y = -1e-9f;
-        float r0, r1;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(-zn.x));
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-zn.y));
-        const unsigned long long Zn2 = pack2(zn.x, zn.y), r2 = pack2(r0, r1);
-        const unsigned long long qx = mul2(X2, r2), qy = mul2(Y2, r2);
-        const float2 px = unpack2(fma2(fma2(qx, Zn2, X2), r2, qx));
-        const float2 py = unpack2(fma2(fma2(qy, Zn2, Y2), r2, qy));
-        ix[2 * k] = px.x; ix[2 * k + 1] = px.y;
-        iy[2 * k] = py.x; iy[2 * k + 1] = py.y;
-    }
-}
-
-template <int C, int G, int D, int LPP, int MB>
-__global__ void __launch_bounds__(128, MB) et_fuse_winp_kernel(const EtArgs a) {
-    constexpr int CPL = C / LPP, GPL = G / LPP, CPG = C / G, PXW = 32 / LPP, NJ = GPL / 2;
-    static_assert(CPL == 8 && (GPL == 2 || GPL == 4) && (CPG == 2 || CPG == 4) && D % 2 == 0,
-                  "a lane owns 8 channels = 2 or 4 whole groups");
-    __shared__ float4 pose_s[MVSTER_MAX_VIEWS * 3];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane % LPP;
-    int x = blockIdx.x * PXW + lane / LPP;
-    int y = blockIdx.y * 4 + warp;
-    const int b = blockIdx.z;
-    if (threadIdx.x < a.V * 3)
-        pose_s[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(a.pose + (long long)b * a.V * 12) + threadIdx.x);
-    const bool live = x < a.W && y < a.H;
-    x = min(x, a.W - 1);
-    y = min(y, a.H - 1);
-    const int plane = a.H * a.W, pix = y * a.W + x;
-
-    unsigned long long ref[4];
-    {
-        const Pix8 t = ldg256(a.ref + ((long long)b * plane + pix) * C + sub * CPL);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ref[i] = mul2(t.p[i], pack2(1.f / CPG, 1.f / CPG));  // the 1/CPG of .mean(2): exact
-    }
-    unsigned long long dep2[D / 2];
-    float ws[D];
-    unsigned long long acc2[NJ][D];
-    {
-        const float* hp = a.hypo + (long long)b * D * plane + pix;
-#pragma unroll
-        for (int k = 0; k < D / 2; ++k)
-            dep2[k] = pack2(__ldg(hp + (long long)(2 * k) * plane), __ldg(hp + (long long)(2 * k + 1) * plane));
-    }
-    if (a.flags & MVSTER_ET_ACCUMULATE) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const long long o = ((long long)b * D + d) * plane + pix;
-            ws[d] = a.wsum[o];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const float2 t = *reinterpret_cast<const float2*>(a.cost + o * G + sub * GPL + 2 * j);
-                acc2[j][d] = pack2(t.x, t.y);
-            }
-        }
-    } else {
-        const float seed = (a.flags & MVSTER_ET_PARTIAL) ? 0.f : 1e-8f;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            ws[d] = seed;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc2[j][d] = 0ull;
-        }
-    }
-    __syncthreads();  // pose_s
-
-    const float fx = (float)x, fy = (float)y;
-    const float max_x = (float)(a.Ws - 1), max_y = (float)(a.Hs - 1);
-    const float inv_temp_log2e = 1.4426950408889634f / a.attn_temp;
-    const int row = a.Ws * C;
-    const int lane_base = b * a.Hs * row + sub * CPL;  // < 2^31 (checked on the host)
-
-    if (a.prefetch & 1) {  // every view's window rows towards L2 before the loop
-        const float dfirst = unpack2(dep2[0]).x;
-        for (int v = 0; v < a.V; ++v) win_prefetch<C, 2>(pose_s, v, a.src[v], fx, fy, dfirst, max_x, max_y, lane_base, row);
-    }
-
-    // staged ("next") view: positions, window and the four unconditional taps in flight
-    float ixN[D], iyN[D], bxN, byN, mxN, myN;
-    bool fastN;
-    const float* pN = nullptr;
-    Pix8 tq[4];
-    auto stage_view = [&](int v) {
-        win_positions<D>(pose_s[v * 3], pose_s[v * 3 + 1], pose_s[v * 3 + 2], fx, fy, dep2, ixN, iyN);
-        bxN = floorf(ixN[0]); byN = floorf(iyN[0]); mxN = bxN; myN = byN;
-#pragma unroll
-        for (int d = 1; d < D; ++d) {
-            const float fxd = floorf(ixN[d]), fyd = floorf(iyN[d]);
-            bxN = min_nan(bxN, fxd); mxN = max_nan(mxN, fxd);
-            byN = min_nan(byN, fyd); myN = max_nan(myN, fyd);
-        }
-        const bool fits = bxN >= 0.f && mxN < max_x && byN >= 0.f && myN < max_y && (mxN - bxN) <= 1.f && (myN - byN) <= 1.f;
-        fastN = __all_sync(0xffffffffu, fits);
-        if (fastN) {
-            pN = a.src[v] + (lane_base + (int)byN * row + (int)bxN * C);
-            tq[0] = ldg256(pN); tq[1] = ldg256(pN + C); tq[2] = ldg256(pN + row); tq[3] = ldg256(pN + row + C);
-        }
-    };
-    stage_view(0);
-
-    for (int v = 0; v < a.V; ++v) {
-        // take the staged view over
-        float ixC[D], iyC[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) { ixC[d] = ixN[d]; iyC[d] = iyN[d]; }
-        const float bxf = bxN, byf = byN;
-        const bool fastC = fastN;
-        unsigned long long T0[3][NJ], dx0[3][NJ], dx1[3][NJ];  // first column of the window and the column differences
-        if (fastC) {
-            const bool needx = mxN > bxN, needy = myN > byN;
-            const float* p0 = pN;
-            const float* p1 = p0 + row;
-            unsigned long long T1[3][NJ], T2[3][NJ];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) T2[0][j] = T2[1][j] = T2[2][j] = T0[2][j] = T1[2][j] = 0ull;
-            tap_groups<CPG, NJ>(tq[0], ref, T0[0]);
-            tap_groups<CPG, NJ>(tq[1], ref, T1[0]);
-            tap_groups<CPG, NJ>(tq[2], ref, T0[1]);
-            tap_groups<CPG, NJ>(tq[3], ref, T1[1]);
-            if (needx) {  // the neighbouring lanes requested these lines as their own second column: L1 hits
-                const Pix8 t02 = ldg256(p0 + 2 * C), t12 = ldg256(p1 + 2 * C);
-                tap_groups<CPG, NJ>(t02, ref, T2[0]);
-                tap_groups<CPG, NJ>(t12, ref, T2[1]);
-            }
-            if (needy) {
-                const float* p2 = p1 + row;
-                const Pix8 t20 = ldg256(p2), t21 = ldg256(p2 + C);
-                tap_groups<CPG, NJ>(t20, ref, T0[2]);
-                tap_groups<CPG, NJ>(t21, ref, T1[2]);
-                if (needx) {
-                    const Pix8 t22 = ldg256(p2 + 2 * C);
-                    tap_groups<CPG, NJ>(t22, ref, T2[2]);
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    dx0[r][j] = sub2(T1[r][j], T0[r][j]);
-                    dx1[r][j] = sub2(T2[r][j], T1[r][j]);
-                }
-        }
-        // request the next view's taps now: the rest of this view's arithmetic runs under their latency
-        if (v + 1 < a.V) stage_view(v + 1);
-
-        unsigned long long cor2[NJ][D];
-        if (fastC) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const float ux = ixC[d] - bxf, uy = iyC[d] - byf;  // exact, in [0,2)
-                const float ax = fminf(ux, 1.f), bx = fmaxf(ux - 1.f, 0.f);
-                const float ay = fminf(uy, 1.f), by = fmaxf(uy - 1.f, 0.f);
-                const unsigned long long ax2 = pack2(ax, ax), bx2 = pack2(bx, bx), ay2 = pack2(ay, ay), by2 = pack2(by, by);
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const unsigned long long h0 = fma2(bx2, dx1[0][j], fma2(ax2, dx0[0][j], T0[0][j]));
-                    const unsigned long long h1 = fma2(bx2, dx1[1][j], fma2(ax2, dx0[1][j], T0[1][j]));
-                    const unsigned long long h2 = fma2(bx2, dx1[2][j], fma2(ax2, dx0[2][j], T0[2][j]));
-                    cor2[j][d] = fma2(by2, sub2(h2, h1), fma2(ay2, sub2(h1, h0), h0));
-                }
-            }
-        } else {
-            // per-hypothesis gather with zeros padding per tap (et_fuse_tiled_kernel's arithmetic)
-            const float* S = a.src[v];
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                int o_nw, o_ne, o_sw, o_se;
-                float w_nw, w_ne, w_sw, w_se;
-                const float px = ixC[d], py = iyC[d];
-                const bool interior = px >= 0.f && px < max_x && py >= 0.f && py < max_y;  // false for NaN
-                if (__all_sync(0xffffffffu, interior)) {
-                    const float x0f = floorf(px), y0f = floorf(py);
-                    const float wx = px - x0f, wy = py - y0f, ex = 1.f - wx, ey = 1.f - wy;
-                    o_nw = lane_base + (int)y0f * row + (int)x0f * C;
-                    o_ne = o_nw + C; o_sw = o_nw + row; o_se = o_sw + C;
-                    w_nw = ey * ex; w_ne = ey * wx; w_sw = wy * ex; w_se = wy * wx;
-                } else {
-                    const float cx = fminf(fmaxf(px, -2.f), max_x + 2.f), cy = fminf(fmaxf(py, -2.f), max_y + 2.f);
-                    const float x0f = floorf(cx), y0f = floorf(cy);
-                    const float wx = cx - x0f, wy = cy - y0f;
-                    const int x0 = (int)x0f, y0 = (int)y0f;
-                    const float ex = (unsigned)x0 < (unsigned)a.Ws ? 1.f - wx : 0.f, fxw = (unsigned)(x0 + 1) < (unsigned)a.Ws ? wx : 0.f;
-                    const float ey = (unsigned)y0 < (unsigned)a.Hs ? 1.f - wy : 0.f, fyw = (unsigned)(y0 + 1) < (unsigned)a.Hs ? wy : 0.f;
-                    const int xa = min(max(x0, 0), a.Ws - 1) * C, xb = min(max(x0 + 1, 0), a.Ws - 1) * C;
-                    const int ya = lane_base + min(max(y0, 0), a.Hs - 1) * row, yb = lane_base + min(max(y0 + 1, 0), a.Hs - 1) * row;
-                    o_nw = ya + xa; o_ne = ya + xb; o_sw = yb + xa; o_se = yb + xb;
-                    w_nw = ey * ex; w_ne = ey * fxw; w_sw = fyw * ex; w_se = fyw * fxw;
-                }
-                const Pix8 t_nw = ldg256(S + o_nw), t_ne = ldg256(S + o_ne), t_sw = ldg256(S + o_sw), t_se = ldg256(S + o_se);
-                Pix8 wv;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    unsigned long long s = mul2(t_nw.p[i], pack2(w_nw, w_nw));
-                    s = fma2(t_ne.p[i], pack2(w_ne, w_ne), s);
-                    s = fma2(t_sw.p[i], pack2(w_sw, w_sw), s);
-                    wv.p[i] = fma2(t_se.p[i], pack2(w_se, w_se), s);
-                }
-                unsigned long long g2[NJ];
-                tap_groups<CPG, NJ>(wv, ref, g2);
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) cor2[j][d] = g2[j];
-            }
-        }
-
-        // softmax over D of (sum over all G groups) / temp, then / sqrt(C)   (mvs4net_utils.py:1053)
-        float lg[D], m = -INFINITY;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            unsigned long long t2 = cor2[0][d];
-            if constexpr (NJ == 2) t2 = add2(t2, cor2[1][d]);
-            const float2 t = unpack2(t2);
-            float s = t.x + t.y;
-#pragma unroll
-            for (int o = 1; o < LPP; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            lg[d] = s * inv_temp_log2e;
-            m = fmaxf(m, lg[d]);
-        }
-        float se = 0.f;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lg[d]) : "f"(lg[d] - m));
-            se += lg[d];
-        }
-        float rs;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(se * a.sqrt_c));
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const float w = lg[d] * rs;
-            ws[d] += w;
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) acc2[j][d] = fma2(pack2(w, w), cor2[j][d], acc2[j][d]);
-        }
-    }
-
-    if (!live) return;
-    const bool partial = a.flags & MVSTER_ET_PARTIAL;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        const long long o = ((long long)b * D + d) * plane + pix;
-        const float r = partial ? 1.f : __frcp_rn(ws[d]);
-        float* dst = a.cost + o * G + sub * GPL;
-        if constexpr (NJ == 2) {
-            const float2 u0 = unpack2(acc2[0][d]), u1 = unpack2(acc2[1][d]);
-            *reinterpret_cast<float4*>(dst) = partial ? make_float4(u0.x, u0.y, u1.x, u1.y)
-                                                      : make_float4(u0.x * r, u0.y * r, u1.x * r, u1.y * r);
-        } else {
-            const float2 u0 = unpack2(acc2[0][d]);
-            *reinterpret_cast<float2*>(dst) = partial ? make_float2(u0.x, u0.y) : make_float2(u0.x * r, u0.y * r);
-        }
-        if (partial && sub == 0) a.wsum[o] = ws[d];
-    }
-}
-
-template <int C, int G, int D, int LPP, int MB>
-static int launch_et_winp(const EtArgs& a, cudaStream_t st) {
-    dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 4), a.B);
-    et_fuse_winp_kernel<C, G, D, LPP, MB><<<grid, 128, 0, st>>>(a);
-    return check_launch("et_fuse_winp_kernel");
-}
+// A software-pipelined variant (next view's positions evaluated and its four unconditional taps requested while the current
+// view is interpolated) was measured and dropped: it needs 168-196 registers (8-12 warps per SM) and was slower at every
+// stage (profiles/r01_et_fuse_win_ncu.md: stage 4 50.9 us vs 47.0 us).
 
 template <int C, int G, int D, int LPP, int MB>
 static int launch_et_win(const EtArgs& a, cudaStream_t st) {
@@ -645,21 +365,6 @@ static bool try_launch_win(const EtArgs& a, int C, int G, int D, cudaStream_t st
     if (a.V * 3 > 128 || ((uintptr_t)a.pose & 15)) return false;      // pose staged with 128-bit loads
     const char* e = getenv("MVSTER_ET_WIN_MB");  // resident CTAs per SM the kernel is compiled for (A/B measurements)
     const int mb = e ? atoi(e) : 0;
-    const char* pe = getenv("MVSTER_ET_WIN_PIPE");
-    if (pe ? atoi(pe) != 0 : false) {  // software-pipelined variant
-        if (C == 8 && G == 4 && D == 4) {
-            *rc = mb == 2 ? launch_et_winp<8, 4, 4, 1, 2>(a, st) : mb == 4 ? launch_et_winp<8, 4, 4, 1, 4>(a, st) : launch_et_winp<8, 4, 4, 1, 3>(a, st);
-            return true;
-        }
-        if (C == 16 && G == 4 && D == 4) {
-            *rc = mb == 3 ? launch_et_winp<16, 4, 4, 2, 3>(a, st) : mb == 5 ? launch_et_winp<16, 4, 4, 2, 5>(a, st) : launch_et_winp<16, 4, 4, 2, 4>(a, st);
-            return true;
-        }
-        if (C == 32 && G == 8 && D == 8) {
-            *rc = mb == 2 ? launch_et_winp<32, 8, 8, 4, 2>(a, st) : mb == 4 ? launch_et_winp<32, 8, 8, 4, 4>(a, st) : launch_et_winp<32, 8, 8, 4, 3>(a, st);
-            return true;
-        }
-    }
     if (C == 8 && G == 4 && D == 4) {
         *rc = mb == 3 ? launch_et_win<8, 4, 4, 1, 3>(a, st) : mb == 5 ? launch_et_win<8, 4, 4, 1, 5>(a, st) : launch_et_win<8, 4, 4, 1, 4>(a, st);
         return true;

@@ -28,12 +28,8 @@ VARIANTS = [
     ("win_mb5", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_MB="5")),
     ("win_mb5_pf1", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_MB="5", MVSTER_ET_PREFETCH="1")),
     ("win_mb5_pf3", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_MB="5", MVSTER_ET_PREFETCH="3")),
-    ("pipe", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_PIPE="1")),
-    ("pipe_mb2", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_PIPE="1", MVSTER_ET_WIN_MB="2")),
-    ("pipe_mb4", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_PIPE="1", MVSTER_ET_WIN_MB="4")),
-    ("pipe_pf1", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_PIPE="1", MVSTER_ET_PREFETCH="1")),
 ]
-KEYS = ("MVSTER_ET_WIN", "MVSTER_ET_WIN_MB", "MVSTER_ET_WIN_PIPE", "MVSTER_ET_PREFETCH")
+KEYS = ("MVSTER_ET_WIN", "MVSTER_ET_WIN_MB", "MVSTER_ET_PREFETCH")
 
 
 def main():
