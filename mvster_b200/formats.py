@@ -125,3 +125,59 @@ def stage_projections(extrinsics: Sequence[np.ndarray], intrinsics: Sequence[np.
 def depth_values(depth_min: float, depth_interval: float, ndepths: int = 192) -> np.ndarray:
     """``datasets/general_eval4.py:164-165``: the evaluation loaders' hypothesis list (the forward reads its first and last entry)."""
     return np.arange(depth_min, depth_interval * (ndepths - 0.5) + depth_min, depth_interval, dtype=np.float32)
+
+
+def read_img(filename: str) -> np.ndarray:
+    """``datasets/general_eval4.py:81-86``: 8-bit image -> float32 in [0, 1], [H,W,3]."""
+    from PIL import Image
+    return np.array(Image.open(filename), dtype=np.float32) / 255.0
+
+
+def scale_mvs_input(img: np.ndarray, intrinsics: np.ndarray, max_w: int, max_h: int, base: int = 64):
+    """``datasets/general_eval4.py:92-109``: shrink to fit (max_h, max_w) if necessary, then cut both sides down to multiples of
+    ``base`` by RESIZING (not cropping), scaling the intrinsic rows with it.  ``intrinsics`` is modified in place like the reference."""
+    import cv2
+    h, w = img.shape[:2]
+    if h > max_h or w > max_w:
+        scale = 1.0 * max_h / h
+        if scale * w > max_w:
+            scale = 1.0 * max_w / w
+        new_w, new_h = scale * w // base * base, scale * h // base * base
+    else:
+        new_w, new_h = 1.0 * w // base * base, 1.0 * h // base * base
+    intrinsics[0, :] *= 1.0 * new_w / w
+    intrinsics[1, :] *= 1.0 * new_h / h
+    return cv2.resize(img, (int(new_w), int(new_h))), intrinsics
+
+
+def load_eval_sample(datapath: str, scan: str, ref_view: int, src_views: Sequence[int], nviews: int, interval_scale: float = 1.06,
+                     max_h: int = 1200, max_w: int = 1600, ndepths: int = 192) -> Dict:
+    """One evaluation sample as ``MVSDataset.__getitem__`` builds it (``datasets/general_eval4.py:111-188``, ``fix_res=False``):
+    ``imgs`` list of nviews [3,H,W] float32, ``proj_matrices`` {stage1..4: [nviews,2,4,4]}, ``depth_values`` [ndepths],
+    ``filename`` pattern.  Every view is resized to the (multiple-of-64) size of the reference view."""
+    import os
+    import cv2
+    view_ids = [ref_view] + list(src_views)[:nviews - 1]
+    imgs, ext, intr, dv = [], [], [], None
+    s_h = s_w = 0
+    for i, vid in enumerate(view_ids):
+        name = os.path.join(datapath, "{}/images_post/{:0>8}.jpg".format(scan, vid))
+        if not os.path.exists(name):
+            name = os.path.join(datapath, "{}/images/{:0>8}.jpg".format(scan, vid))
+        img = read_img(name)
+        k, e, depth_min, depth_interval = read_cam_file(os.path.join(datapath, "{}/cams/{:0>8}_cam.txt".format(scan, vid)), interval_scale, ndepths)
+        img, k = scale_mvs_input(img, k, max_w, max_h)
+        if i == 0:
+            s_h, s_w = img.shape[:2]
+        c_h, c_w = img.shape[:2]
+        if c_h != s_h or c_w != s_w:
+            img = cv2.resize(img, (s_w, s_h))
+            k[0, :] *= 1.0 * s_w / c_w
+            k[1, :] *= 1.0 * s_h / c_h
+        imgs.append(img.transpose(2, 0, 1))
+        ext.append(e)
+        intr.append(k)
+        if i == 0:
+            dv = depth_values(depth_min, depth_interval, ndepths)
+    return {"imgs": imgs, "proj_matrices": stage_projections(ext, intr), "depth_values": dv,
+            "filename": scan + "/{}/" + "{:0>8}".format(view_ids[0]) + "{}"}

@@ -109,3 +109,47 @@ def test_against_the_reference_functions_directly(tmp_path):
         a, sa = ref_read(str(tmp_path / "o.pfm"))
         b, sb = formats.read_pfm(str(tmp_path / "r.pfm"))
         assert sa == sb == 3.0 and np.array_equal(np.asarray(a), np.asarray(b))
+
+
+def _write_scan(root, n_views=4, hw=((140, 200), (140, 200), (150, 210), (140, 200))):
+    """A tiny scan directory in the layout the reference's evaluation loader reads (images/, cams/, pair.txt)."""
+    from PIL import Image
+    from mvster_b200 import synth
+    scan = root / "scan1"
+    (scan / "images").mkdir(parents=True)
+    (scan / "cams").mkdir()
+    rng = np.random.RandomState(11)
+    cams = synth.arc_cameras(n_views, 140, 200, 3.0)
+    for v in range(n_views):
+        h, w = hw[v]
+        Image.fromarray((rng.rand(h, w, 3) * 255).astype(np.uint8)).save(scan / "images" / f"{v:0>8}.jpg", quality=95)
+        k = cams[v, 1, :3, :3].astype(np.float64).copy()
+        k[:2] *= 4.0  # cam files hold full-scale intrinsics; the reader divides by 4
+        formats.write_cam_file(str(scan / "cams" / f"{v:0>8}_cam.txt"), cams[v, 0], k, 425.0, 2.5)
+    (scan / "pair.txt").write_text("4\n0\n3 1 9.0 2 8.0 3 7.0\n1\n2 0 9.0 2 5.0\n2\n1 0 3.0\n3\n0\n")
+    return scan
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/datasets"), reason="reference tree not mounted (GPU box)")
+def test_eval_sample_matches_the_reference_dataset(tmp_path):
+    """formats.load_eval_sample vs the reference's MVSDataset.__getitem__ (datasets/general_eval4.py) on a synthetic scan:
+    images, the four projection stacks and the hypothesis list, bit for bit; one view has a different size and is resized."""
+    _write_scan(tmp_path)
+    sys.path.insert(0, "/root/reference")
+    try:
+        from datasets.general_eval4 import MVSDataset
+    finally:
+        sys.path.pop(0)
+    ds = MVSDataset(str(tmp_path), ["scan1"], "test", 4, 1.06, max_h=1200, max_w=1600, fix_res=False)
+    metas = formats.read_pair_file(str(tmp_path / "scan1" / "pair.txt"), 4)
+    assert [(m[1], m[2]) for m in ds.metas] == metas
+    for idx, (ref_view, src_views) in enumerate(metas):
+        want = ds[idx]
+        got = formats.load_eval_sample(str(tmp_path), "scan1", ref_view, src_views, 4, 1.06, 1200, 1600)
+        assert got["filename"] == want["filename"]
+        assert np.array_equal(got["depth_values"], want["depth_values"])
+        assert len(got["imgs"]) == len(want["imgs"]) == 4
+        for a, b in zip(got["imgs"], want["imgs"]):
+            assert a.shape == b.shape == (3, 128, 192) and a.dtype == np.float32 and np.array_equal(a, b)
+        for s in ("stage1", "stage2", "stage3", "stage4"):
+            assert np.array_equal(got["proj_matrices"][s], want["proj_matrices"][s]), s
