@@ -17,23 +17,11 @@
 // hypotheses of the pixel stay in registers; the sum over groups that feeds the
 // softmax is a log2(G)-step warp shuffle.
 #include "common.cuh"
+#include "et_args.cuh"
 #include <math.h>
 #include <stdlib.h>
 
 namespace mvster {
-
-struct EtArgs {
-    const float* ref;
-    const float* src[MVSTER_MAX_VIEWS];
-    const float* pose;  // [B][V][12]
-    const float* hypo;  // [B][D][H][W]
-    float* cost;        // [B][D][H][W][G]
-    float* wsum;        // [B][D][H][W] or nullptr
-    int B, V, H, W, Hs, Ws;
-    float attn_temp, sqrt_c;
-    int flags;
-    int prefetch;  // window kernels: L2 prefetch of every view's window rows before the view loop
-};
 
 template <int N>
 __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[N]) {

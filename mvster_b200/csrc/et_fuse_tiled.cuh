@@ -15,6 +15,18 @@
 
 namespace mvster {
 
+#ifdef MVSTER_CPU_EMU  // tests/emu: the same helpers in portable C++ so that the kernel sources below run on the host
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) { return emu::pack(lo, hi); }
+__device__ __forceinline__ float2 unpack2(unsigned long long v) { return emu::unpack(v); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    const float2 x = emu::unpack(a), y = emu::unpack(b), z = emu::unpack(c);
+    return emu::pack(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y));
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    const float2 x = emu::unpack(a), y = emu::unpack(b);
+    return emu::pack(x.x * y.x, x.y * y.y);
+}
+#else
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -35,6 +47,7 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+#endif
 
 struct Pix8 { unsigned long long p[4]; };  // 8 fp32 channels as 4 packed pairs
 // One 256-bit read-only load (LDG.E.256, new on sm_100): a lane fetches its whole 8-channel tap, a
@@ -42,8 +55,31 @@ struct Pix8 { unsigned long long p[4]; };  // 8 fp32 channels as 4 packed pairs
 // the wavefronts because each quarter-warp then straddles two lines).
 __device__ __forceinline__ Pix8 ldg256(const float* p) {
     Pix8 r;
+#ifdef MVSTER_CPU_EMU
+    for (int i = 0; i < 4; ++i) r.p[i] = emu::pack(p[2 * i], p[2 * i + 1]);
+#else
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(r.p[0]), "=l"(r.p[1]), "=l"(r.p[2]), "=l"(r.p[3]) : "l"(p));
+#endif
     return r;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP
+#ifdef MVSTER_CPU_EMU
+    return 1.f / x;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2 (results below 2^-126 flush to 0)
+#ifdef MVSTER_CPU_EMU
+    return exp2f(x);
+#else
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
 }
 
 // a / b given r ~= 1/b: one Newton-style residual correction (exact residual through FMA).
@@ -51,6 +87,8 @@ __device__ __forceinline__ float div_corrected(float a, float b, float r) {
     const float q = a * r;
     return fmaf(fmaf(-q, b, a), r, q);
 }
+
+#ifndef MVSTER_CPU_EMU  // the emulation build (tests/emu) takes the helpers above and the window kernel only
 
 template <int C, int G, int D, int LPP, int MB>
 __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) {
@@ -262,5 +300,7 @@ static bool try_launch_tiled(const EtArgs& a, int C, int G, int D, cudaStream_t 
     if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled<64, 8, 8, 8, 4>(a, st); return true; }
     return false;
 }
+
+#endif  // MVSTER_CPU_EMU
 
 }  // namespace mvster

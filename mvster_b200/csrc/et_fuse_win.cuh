@@ -24,6 +24,20 @@
 
 namespace mvster {
 
+#ifdef MVSTER_CPU_EMU
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    const float2 x = emu::unpack(a), y = emu::unpack(b);
+    return emu::pack(x.x + y.x, x.y + y.y);
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    const float2 x = emu::unpack(a), y = emu::unpack(b);
+    return emu::pack(x.x - y.x, x.y - y.y);
+}
+__device__ __forceinline__ float min_nan(float a, float b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
+__device__ __forceinline__ void prefetch_l2(const float*) {}
+__device__ __forceinline__ void prefetch_l1(const float*) {}
+#else
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
     unsigned long long d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -44,6 +58,9 @@ __device__ __forceinline__ float max_nan(float a, float b) {
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
     return d;
 }
+__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
 
 // Per-group correlations of one 8-channel tap with the lane's (pre-scaled) reference channels,
 // packed two groups per 64-bit pair.  CPG = 2: 4 groups (2 pairs); CPG = 4: 2 groups (1 pair).
@@ -72,17 +89,16 @@ __device__ __forceinline__ void win_prefetch(const float4* pose_s, int v, const 
     const float X = fmaf(fmaf(q0.z, 1.f, fmaf(q0.y, fy, q0.x * fx)), d0, q2.y);
     const float Y = fmaf(fmaf(q1.y, 1.f, fmaf(q1.x, fy, q0.w * fx)), d0, q2.z);
     const float Z = fmaf(fmaf(q2.x, 1.f, fmaf(q1.w, fy, q1.z * fx)), d0, q2.w);
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(Z));
+    const float r = rcp_approx(Z);
     const float px = X * r, py = Y * r;
     if (px >= 0.f && px < max_x && py >= 0.f && py < max_y) {
         const float* p = src + (lane_base + (int)py * row + (int)px * C);
         if constexpr (LEVEL == 2) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + row));
+            prefetch_l2(p);
+            prefetch_l2(p + row);
         } else {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + row));
+            prefetch_l1(p);
+            prefetch_l1(p + row);
         }
     }
 }
@@ -179,9 +195,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
             float2 zn = unpack2(add2(pack2(__fmul_rn(nrz, dd.x), __fmul_rn(nrz, dd.y)), pack2(ntz, ntz)));  // -Z
             if (zn.x == 0.f) zn.x = -1e-9f;
             if (zn.y == 0.f) zn.y = -1e-9f;
-            float r0, r1;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(-zn.x));
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(-zn.y));
+            const float r0 = rcp_approx(-zn.x), r1 = rcp_approx(-zn.y);
             const unsigned long long Zn2 = pack2(zn.x, zn.y), r2 = pack2(r0, r1);
             const unsigned long long qx = mul2(X2, r2), qy = mul2(Y2, r2);
             const float2 px = unpack2(fma2(fma2(qx, Zn2, X2), r2, qx));
@@ -308,11 +322,10 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
         float se = 0.f;
 #pragma unroll
         for (int d = 0; d < D; ++d) {  // arguments <= 0: the bare MUFU.EX2 (results below 2^-126 flush to 0)
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lg[d]) : "f"(lg[d] - m));
+            lg[d] = ex2_approx(lg[d] - m);
             se += lg[d];
         }
-        float rs;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(se * a.sqrt_c));
+        const float rs = rcp_approx(se * a.sqrt_c);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const float w = lg[d] * rs;
@@ -344,6 +357,8 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
 // A software-pipelined variant (next view's positions evaluated and its four unconditional taps requested while the current
 // view is interpolated) was measured and dropped: it needs 168-196 registers (8-12 warps per SM) and was slower at every
 // stage (profiles/r01_et_fuse_win_ncu.md: stage 4 50.9 us vs 47.0 us).
+
+#ifndef MVSTER_CPU_EMU  // host-side launch code (CUDA runtime)
 
 template <int C, int G, int D, int LPP, int MB>
 static int launch_et_win(const EtArgs& a, cudaStream_t st) {
@@ -379,5 +394,7 @@ static bool try_launch_win(const EtArgs& a, int C, int G, int D, cudaStream_t st
     }
     return false;
 }
+
+#endif  // MVSTER_CPU_EMU
 
 }  // namespace mvster

@@ -1,0 +1,111 @@
+// Host emulation of the CUDA SIMT model for tests (tests/test_emu_kernels.py): the SIMT kernel SOURCES of
+// mvster_b200/csrc are compiled with g++ and run on CPU threads - one OS thread per CUDA thread of a block, blocks one after
+// another - so that kernel logic can be checked against the oracle without a GPU.  Warp collectives (__all_sync,
+// __shfl_xor_sync) and __syncthreads are real barriers between those threads.  Test infrastructure only: nothing in the
+// product path includes this header, and tcgen05 / TMA kernels are out of its reach.
+#pragma once
+#define MVSTER_CPU_EMU 1
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) alignas(n)
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+inline float2 make_float2(float x, float y) { return {x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+
+namespace emu {
+struct Warp {
+    std::barrier<> bar{32};
+    int vote[32];
+    float f[32];
+    explicit Warp(int n) : bar(n) {}
+};
+struct Ctx { Warp* warp; std::barrier<>* block; int lane; };
+inline thread_local Ctx ctx;
+inline unsigned long long pack(float lo, float hi) {
+    uint32_t a, b;
+    std::memcpy(&a, &lo, 4); std::memcpy(&b, &hi, 4);
+    return (unsigned long long)a | ((unsigned long long)b << 32);
+}
+inline float2 unpack(unsigned long long v) {
+    const uint32_t a = (uint32_t)v, b = (uint32_t)(v >> 32);
+    float2 r; std::memcpy(&r.x, &a, 4); std::memcpy(&r.y, &b, 4);
+    return r;
+}
+}  // namespace emu
+
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+
+inline void __syncthreads() { emu::ctx.block->arrive_and_wait(); }
+inline bool __all_sync(unsigned, bool p) {
+    emu::Warp& w = *emu::ctx.warp;
+    w.vote[emu::ctx.lane] = p;
+    w.bar.arrive_and_wait();
+    bool r = true;
+    for (int i = 0; i < 32; ++i) r = r && w.vote[i];
+    w.bar.arrive_and_wait();
+    return r;
+}
+inline float __shfl_xor_sync(unsigned, float v, int o) {
+    emu::Warp& w = *emu::ctx.warp;
+    w.f[emu::ctx.lane] = v;
+    w.bar.arrive_and_wait();
+    const float r = w.f[emu::ctx.lane ^ o];
+    w.bar.arrive_and_wait();
+    return r;
+}
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __frcp_rn(float a) { return 1.f / a; }
+inline int __float2int_rn(float a) { return (int)std::lrintf(a); }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+
+namespace emu {
+// run kernel(args...) over the grid: blocks sequentially, the threads of a block concurrently (block.x must be a multiple of 32)
+template <class F>
+inline void launch(dim3 grid, dim3 block, F body) {
+    const int nthreads = (int)(block.x * block.y * block.z), nwarps = nthreads / 32;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                std::barrier<> block_bar(nthreads);
+                std::vector<std::unique_ptr<Warp>> warps;
+                for (int w = 0; w < nwarps; ++w) warps.emplace_back(new Warp(32));
+                std::vector<std::thread> th;
+                th.reserve(nthreads);
+                for (int t = 0; t < nthreads; ++t)
+                    th.emplace_back([&, t] {
+                        threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+                        blockIdx = {bx, by, bz};
+                        blockDim = block; gridDim = grid;
+                        ctx = {warps[t / 32].get(), &block_bar, t % 32};
+                        body();
+                        block_bar.arrive_and_drop();        // a thread that has left the kernel no longer takes part in barriers
+                        warps[t / 32]->bar.arrive_and_drop();
+                    });
+                for (auto& x : th) x.join();
+            }
+}
+}  // namespace emu
