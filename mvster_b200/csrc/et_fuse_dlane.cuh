@@ -66,8 +66,7 @@ __global__ void __launch_bounds__(128, 6) et_fuse_dlane_kernel(const EtArgs a) {
         const float Y = __fadd_rn(__fmul_rn(ry, dep), __ldg(P + 10));
         float Z = __fadd_rn(__fmul_rn(rz, dep), __ldg(P + 11));
         if (Z == 0.f) Z = 1e-9f;
-        float rZ;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rZ) : "f"(Z));
+        const float rZ = rcp_approx(Z);
         const float ix = div_corrected(X, Z, rZ), iy = div_corrected(Y, Z, rZ);
         int o_nw, o_ne, o_sw, o_se;
         float w_nw, w_ne, w_sw, w_se;
@@ -127,8 +126,7 @@ __global__ void __launch_bounds__(128, 6) et_fuse_dlane_kernel(const EtArgs a) {
         const float e = exp2f(lg - m);
         float se = e + __shfl_xor_sync(0xffffffffu, e, LPP);
         se += __shfl_xor_sync(0xffffffffu, se, 2 * LPP);
-        float rs;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(se * a.sqrt_c));
+        const float rs = rcp_approx(se * a.sqrt_c);
         const float w = e * rs;
         ws += w;
 #pragma unroll

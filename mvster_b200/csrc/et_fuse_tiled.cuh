@@ -88,8 +88,6 @@ __device__ __forceinline__ float div_corrected(float a, float b, float r) {
     return fmaf(fmaf(-q, b, a), r, q);
 }
 
-#ifndef MVSTER_CPU_EMU  // the emulation build (tests/emu) takes the helpers above and the window kernel only
-
 template <int C, int G, int D, int LPP, int MB>
 __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) {
     constexpr int CPL = C / LPP;   // channels per lane
@@ -161,8 +159,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) 
             const float Y = __fadd_rn(__fmul_rn(ry, dep[d]), ty);
             float Z = __fadd_rn(__fmul_rn(rz, dep[d]), tz);
             if (Z == 0.f) Z = 1e-9f;
-            float rZ;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rZ) : "f"(Z));
+            const float rZ = rcp_approx(Z);
             // Sampling position in source pixels.  The reference normalises to [-1,1] and grid_sample
             // maps back (mvs4net_utils.py:43-44 + align_corners=True): an identity up to <= 4e-5 px of
             // fp32 rounding, skipped here.
@@ -235,8 +232,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) 
         float se = 0.f;
 #pragma unroll
         for (int d = 0; d < D; ++d) { lg[d] = exp2f(lg[d] - m); se += lg[d]; }
-        float rs;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(se * a.sqrt_c));
+        const float rs = rcp_approx(se * a.sqrt_c);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const float w = lg[d] * rs;
@@ -300,7 +296,5 @@ static bool try_launch_tiled(const EtArgs& a, int C, int G, int D, cudaStream_t 
     if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled<64, 8, 8, 8, 4>(a, st); return true; }
     return false;
 }
-
-#endif  // MVSTER_CPU_EMU
 
 }  // namespace mvster

@@ -358,8 +358,6 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
 // view is interpolated) was measured and dropped: it needs 168-196 registers (8-12 warps per SM) and was slower at every
 // stage (profiles/r01_et_fuse_win_ncu.md: stage 4 50.9 us vs 47.0 us).
 
-#ifndef MVSTER_CPU_EMU  // host-side launch code (CUDA runtime)
-
 template <int C, int G, int D, int LPP, int MB>
 static int launch_et_win(const EtArgs& a, cudaStream_t st) {
     dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 4), a.B);
@@ -394,7 +392,5 @@ static bool try_launch_win(const EtArgs& a, int C, int G, int D, cudaStream_t st
     }
     return false;
 }
-
-#endif  // MVSTER_CPU_EMU
 
 }  // namespace mvster

@@ -230,13 +230,17 @@ namespace mvster {
 // eight consecutive floats with ONE 256-bit read-only load (32-byte aligned): half the L1 requests of two 128-bit loads
 struct F8 { float v[8]; };
 __device__ __forceinline__ F8 ldg_f8(const float* p) {
+    F8 r;
+#ifdef MVSTER_CPU_EMU  // tests/emu: host build of this source
+    for (int i = 0; i < 8; ++i) r.v[i] = p[i];
+#else
     unsigned long long q0, q1, q2, q3;
     asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q0), "=l"(q1), "=l"(q2), "=l"(q3) : "l"(p));
-    F8 r;
     r.v[0] = __uint_as_float((unsigned)q0); r.v[1] = __uint_as_float((unsigned)(q0 >> 32));
     r.v[2] = __uint_as_float((unsigned)q1); r.v[3] = __uint_as_float((unsigned)(q1 >> 32));
     r.v[4] = __uint_as_float((unsigned)q2); r.v[5] = __uint_as_float((unsigned)(q2 >> 32));
     r.v[6] = __uint_as_float((unsigned)q3); r.v[7] = __uint_as_float((unsigned)(q3 >> 32));
+#endif
     return r;
 }
 

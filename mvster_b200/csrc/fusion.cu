@@ -7,9 +7,7 @@
 // prepared with the reference's own numpy calls (float32 inverses / products, passed as doubles), float32 casts where the
 // reference casts, and cv2.remap(INTER_LINEAR)'s fixed-point sampling for the source-depth lookup: coordinates rounded to
 // 1/32 pixel, float32 weights, zeros outside the image, products and sums rounded separately.
-#ifndef MVSTER_CPU_EMU  // tests/emu compiles the kernel below for the host
 #include "common.cuh"
-#endif
 
 namespace mvster {
 
@@ -92,7 +90,6 @@ __global__ void __launch_bounds__(256) geo_consistency_kernel(const GeoArgs a) {
 
 }  // namespace mvster
 
-#ifndef MVSTER_CPU_EMU
 using namespace mvster;
 
 extern "C" int mvster_geo_consistency_f32(const float* depth_ref, const float* depth_src, const double* mats, float* depth_reproj,
@@ -116,4 +113,3 @@ extern "C" int mvster_geo_consistency_f32(const float* depth_ref, const float* d
     geo_consistency_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("geo_consistency_kernel");
 }
-#endif  // MVSTER_CPU_EMU

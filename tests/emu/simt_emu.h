@@ -21,7 +21,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
@@ -37,7 +37,7 @@ struct Warp {
     float f[32];
     explicit Warp(int n) : bar(n) {}
 };
-struct Ctx { Warp* warp; std::barrier<>* block; int lane; };
+struct Ctx { Warp* warp; std::barrier<>* block; int lane; unsigned char* dyn_smem; };
 inline thread_local Ctx ctx;
 inline unsigned long long pack(float lo, float hi) {
     uint32_t a, b;
@@ -81,12 +81,28 @@ inline float __frcp_rn(float a) { return 1.f / a; }
 inline int __float2int_rn(float a) { return (int)std::lrintf(a); }
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+inline float __expf(float a) { return std::exp(a); }
 
 namespace emu {
 // run kernel(args...) over the grid: blocks sequentially, the threads of a block concurrently (block.x must be a multiple of 32)
 template <class F>
-inline void launch(dim3 grid, dim3 block, F body) {
+inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
     const int nthreads = (int)(block.x * block.y * block.z), nwarps = nthreads / 32;
+    std::vector<unsigned char> smem_store(smem_bytes + 128);
+    unsigned char* smem = smem_store.data() + (128 - (reinterpret_cast<uintptr_t>(smem_store.data()) & 127)) % 128;
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -100,7 +116,7 @@ inline void launch(dim3 grid, dim3 block, F body) {
                         threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
                         blockIdx = {bx, by, bz};
                         blockDim = block; gridDim = grid;
-                        ctx = {warps[t / 32].get(), &block_bar, t % 32};
+                        ctx = {warps[t / 32].get(), &block_bar, t % 32, smem};
                         body();
                         block_bar.arrive_and_drop();        // a thread that has left the kernel no longer takes part in barriers
                         warps[t / 32]->bar.arrive_and_drop();

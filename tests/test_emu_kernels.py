@@ -1,111 +1,237 @@
-"""SIMT kernel SOURCES of libmvster_b200 executed on the CPU (tests/emu/simt_emu.h: one OS thread per CUDA thread, real
-barriers for __syncthreads / warp votes / shuffles) and checked against the oracle - kernel logic coverage that needs no GPU:
-  * et_fuse_win_kernel (csrc/et_fuse_win.cuh) for its three specialisations, window path and per-hypothesis fallback,
-    partial / accumulate modes, ragged tiles;
-  * geo_consistency_kernel (csrc/fusion.cu) against the reference's own outputs.
-The GPU build of the same sources is byte-identical with or without this harness (only #ifdef MVSTER_CPU_EMU blocks were added)."""
+"""The SIMT half of libmvster_b200 executed on the CPU and checked against the oracle - kernel logic coverage without a GPU.
+
+tests/emu/build_emu.py compiles the SOURCE files of mvster_b200/csrc that contain no tensor-core code (warp + ET kernels in
+all variants, CUDA-core convolutions / reg2d / reg3d, head, hypotheses, pose, FPN glue, geometric-consistency filter) with
+g++ against tests/emu/simt_emu.h: one OS thread per CUDA thread of a block, real barriers for __syncthreads / warp votes /
+shuffles, `<<<...>>>` launches rewritten to a host loop over blocks.  The result exports the same C ABI and takes host
+pointers; here `mvster_b200.capi` is pointed at it (test-only monkeypatching: the product has no such path and still raises
+without a GPU), so the very wrappers and kernels the GPU tests exercise run on small inputs.  The GPU object code is
+byte-identical with and without the few `#ifdef MVSTER_CPU_EMU` twins of inline-PTX helpers (SASS hashes compared)."""
 import ctypes as C
-import subprocess
-from pathlib import Path
+import sys
 
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
-from util import GOLDEN, REPO, narrow_et_inputs, oracle
+from util import GOLDEN, REPO, SHIPPED, build_model, narrow_et_inputs, oracle, oracle_cfg
 from oracle import fusion_oracle
 
-EMU = REPO / "tests" / "emu"
+from mvster_b200 import _lib, capi, fpn_engine, packing, synth
+
+sys.path.insert(0, str(REPO / "tests" / "emu"))
+
+
+class _EmuWithHostLogic:
+    """The emulation library for everything it exports; pure host logic of the tensor-core files (layer plans, packed sizes -
+    no kernel launches) is answered by the real library, which loads without a GPU."""
+    HOST_ONLY = {"mvster_conv_tc3_plan", "mvster_conv_tc3_packed_bytes", "mvster_conv_tc3_supported", "mvster_deconv_tc3_packed_bytes",
+                 "mvster_deconv_tc3_supported", "mvster_conv3d_tc_supported", "mvster_conv3d_tc2_supported"}
+
+    def __init__(self, emu, real):
+        self._emu, self._real = emu, real
+
+    def __getattr__(self, name):
+        if name in self.HOST_ONLY:
+            return getattr(self._real, name)
+        return getattr(self._emu, name)
 
 
 @pytest.fixture(scope="module")
-def emu():
-    out = EMU / "_build"
-    out.mkdir(exist_ok=True)
-    lib = out / "libmvster_emu.so"
-    srcs = [EMU / "kernels_emu.cpp", EMU / "simt_emu.h", REPO / "mvster_b200/csrc/et_fuse_win.cuh", REPO / "mvster_b200/csrc/et_fuse_tiled.cuh",
-            REPO / "mvster_b200/csrc/et_args.cuh", REPO / "mvster_b200/csrc/fusion.cu"]
-    if not lib.exists() or lib.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
-        subprocess.check_call(["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-shared", "-fPIC", str(EMU / "kernels_emu.cpp"), "-o", str(lib)])
-    return C.CDLL(str(lib))
+def emu_lib():
+    import build_emu
+    lib = C.CDLL(str(build_emu.build()))
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if name in _EmuWithHostLogic.HOST_ONLY:
+            continue
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype, fn.argtypes = res, args
+    return _EmuWithHostLogic(lib, _lib.load())
 
 
-def fptr(a):
-    return a.ctypes.data_as(C.c_void_p)
+@pytest.fixture()
+def emu(emu_lib, monkeypatch):
+    """capi / fpn_engine on the emulation library, CPU tensors accepted."""
+    def chk(t, name, shape=None):
+        assert isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.is_contiguous() and not t.is_cuda, name
+        assert shape is None or tuple(t.shape) == tuple(shape), (name, tuple(t.shape), tuple(shape))
+        return t
+    monkeypatch.setattr(_lib, "_lib", emu_lib)
+    monkeypatch.setattr(capi, "_chk", chk)
+    monkeypatch.setattr(capi, "_stream", lambda: C.c_void_p(0))
+    return emu_lib
 
 
-def run_win(emu, feats, cams, hypo, G, flags=0, cost=None, wsum=None):
-    """feats [ref, src...] each [B,C,H,W] torch; returns cost [B,G,D,H,W] numpy (and wsum)."""
-    B, Cc, H, W = feats[0].shape
-    D = hypo.shape[1]
-    nhwc = [np.ascontiguousarray(f.permute(0, 2, 3, 1).numpy()) for f in feats]
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def from_ndhwc(t):
+    return t.permute(0, 4, 1, 2, 3).contiguous()
+
+
+# ----------------------------------------------------------------------------- hypotheses, pose
+def test_hypotheses_and_pose_on_cpu(emu):
+    dv = torch.tensor([[425.0, 700.0, 935.0], [300.0, 500.0, 800.0]])
+    got = capi.hypo_init_inverse(dv, 8, 8, 12)
+    assert torch.equal(got, oracle.hypo_init_inverse(dv, 8, 8, 12))                       # bit-exact, as on the GPU
+    rng = np.random.RandomState(0)
+    inv_max = torch.from_numpy(rng.uniform(1 / 900, 1 / 600, (2, 8, 12)).astype(np.float32))
+    inv_min = inv_max + torch.from_numpy(rng.uniform(1e-5, 3e-4, (2, 8, 12)).astype(np.float32))
+    for D in (4, 8):
+        got = capi.hypo_schedule_inverse(inv_min, inv_max, D, 16, 24)
+        want = oracle.hypo_schedule_inverse(inv_min, inv_max, D, 16, 24)
+        assert ((got - want).abs() / want.abs()).max().item() < 5e-7
+    _, proj, _ = synth.make_inputs(2, 4, 64, 64, seed=1, step_deg=5.0)
+    cams = proj["stage3"]
+    got = capi.pose(cams)
     ref_full = oracle.compose_projection(cams[:, 0])
-    pose = np.zeros((B, len(feats) - 1, 12), np.float32)
-    for v in range(1, len(feats)):
+    for v in range(1, 4):
         R, t = oracle.relative_pose(oracle.compose_projection(cams[:, v]), ref_full)
-        pose[:, v - 1, :9] = R.reshape(B, 9).numpy()
-        pose[:, v - 1, 9:] = t.reshape(B, 3).numpy()
-    hy = np.ascontiguousarray(hypo.numpy())
-    if cost is None:
-        cost = np.full((B, D, H, W, G), np.nan, np.float32)
-    if wsum is None:
-        wsum = np.zeros((B, D, H, W), np.float32)
-    srcs = (C.c_void_p * (len(feats) - 1))(*[a.ctypes.data for a in nhwc[1:]])
-    rc = emu.emu_et_fuse_win(fptr(nhwc[0]), srcs, len(feats) - 1, fptr(pose), fptr(hy), fptr(cost), fptr(wsum),
-                             B, Cc, G, D, H, W, H, W, C.c_float(2.0), flags)
-    assert rc == 0
-    return cost, wsum
+        want = torch.cat([R.reshape(2, 9), t.reshape(2, 3)], 1)
+        assert ((got[:, v - 1] - want).abs().max() / want.abs().max()).item() < 2e-6
 
 
-EMU_CASES = [  # (B, nv, C, G, D, H, W, step_deg, rel_span): small grids (every CUDA thread is an OS thread here)
-    (1, 3, 8, 4, 4, 8, 64, 1.0, 0.3),
-    (1, 3, 8, 4, 4, 6, 40, 3.0, 0.12),    # ragged tile, wide baseline: out-of-image taps -> per-hypothesis path
-    (1, 3, 16, 4, 4, 8, 32, 2.0, 0.2),    # two lanes per pixel (shuffles)
-    (2, 2, 32, 8, 8, 4, 16, 4.0, 0.06),   # four lanes per pixel, D = 8, batch 2
+# ----------------------------------------------------------------------------- warp + ET kernels, every variant
+ET_SMALL = [  # (B, nv, C, G, D, H, W, step_deg): wide hypothesis ranges -> per-hypothesis kernels; the window kernel falls back
+    (1, 3, 64, 8, 8, 4, 8, 1.0),
+    (1, 3, 32, 8, 8, 8, 8, 5.0),
+    (1, 2, 16, 4, 4, 8, 16, 2.0),
+    (1, 3, 8, 4, 4, 8, 32, 1.0),
+    (1, 2, 16, 8, 4, 4, 8, 3.0),   # generic kernel only: C/G = 2, G = 8
 ]
 
 
-@pytest.mark.parametrize("case", EMU_CASES)
-def test_window_kernel_source_on_cpu_matches_oracle(emu, case):
-    B, nv, Cc, G, D, H, W, step, span = case
-    feats, cams, hypo = narrow_et_inputs(B, nv, Cc, D, H, W, step, span, seed=13)
-    want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0).numpy()           # [B,G,D,H,W]
-    cost, _ = run_win(emu, feats, cams, hypo, G)
-    got = cost.transpose(0, 4, 1, 2, 3)
-    assert np.isfinite(got).all()
-    scale = np.abs(want).max()
-    assert np.abs(got - want).max() <= 2e-4 * scale
+def et_inputs(B, nv, C, G, D, H, W, step, seed=0):
+    rng = np.random.RandomState(seed)
+    feats = [torch.from_numpy(rng.randn(B, C, H, W).astype(np.float32)) for _ in range(nv)]
+    cams = synth.stage_projections(synth.arc_cameras(nv, H, W, step), B, num_stage=1)["stage1"]
+    hypo = oracle.hypo_init_inverse(torch.tensor([[425.0, 935.0]] * B), D, H, W)
+    hypo = hypo * torch.from_numpy(rng.uniform(0.97, 1.03, (B, D, H, W)).astype(np.float32))
+    return feats, cams, hypo
 
 
-def test_window_kernel_source_partial_and_accumulate_on_cpu(emu):
-    B, nv, Cc, G, D, H, W = 1, 4, 8, 4, 4, 8, 32
-    feats, cams, hypo = narrow_et_inputs(B, nv, Cc, D, H, W, 2.0, 0.2, seed=17)
-    acc_want, w_want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0, partial=True)
-    c1, w1 = run_win(emu, feats[:3], cams[:, :3], hypo, G, flags=1)                                    # views 1-2, partial
-    c1, w1 = run_win(emu, [feats[0], feats[3]], cams[:, [0, 3]], hypo, G, flags=1 | 2, cost=c1, wsum=w1)  # + view 3, accumulate
-    assert np.abs(w1 - w_want.numpy()).max() < 1e-5
-    got = c1.transpose(0, 4, 1, 2, 3)
-    assert np.abs(got - acc_want.numpy()).max() <= 2e-4 * np.abs(acc_want.numpy()).max()
+@pytest.mark.parametrize("case", ET_SMALL)
+def test_et_kernels_on_cpu_match_oracle(emu, case, monkeypatch):
+    B, nv, C_, G, D, H, W, step = case
+    feats, cams, hypo = et_inputs(*case)
+    want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0)
+    scale = want.abs().max().item()
+    ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)
+    variants = [dict(generic=True), dict(window=False), dict(window=True)]
+    for kw in variants:
+        got = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, **kw))
+        assert (got - want).abs().max().item() <= 2e-4 * scale, kw
+    if D == 4 and C_ in (8, 16) and G == 4:  # depth-across-lanes variant (opt-in)
+        monkeypatch.setenv("MVSTER_ET_DLANE", "1")
+        got = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, window=False))
+        assert (got - want).abs().max().item() <= 2e-4 * scale
 
 
+WIN_SMALL = [  # (B, nv, C, G, D, H, W, step_deg, rel_span): hypotheses within one or two source cells -> window path
+    (1, 3, 8, 4, 4, 8, 64, 1.0, 0.3),
+    (1, 3, 8, 4, 4, 6, 40, 3.0, 0.12),
+    (1, 3, 16, 4, 4, 8, 32, 2.0, 0.2),
+    (2, 2, 32, 8, 8, 4, 16, 4.0, 0.06),
+]
+
+
+@pytest.mark.parametrize("case", WIN_SMALL)
+def test_window_kernel_on_cpu_matches_oracle(emu, case):
+    B, nv, C_, G, D, H, W, step, span = case
+    feats, cams, hypo = narrow_et_inputs(B, nv, C_, D, H, W, step, span, seed=13)
+    want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0)
+    got = from_ndhwc(capi.et_fuse(nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams), hypo, G, 2.0, window=True))
+    assert torch.isfinite(got).all() and (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+
+
+def test_et_variants_sqdiff_no_fuse_d_partial_on_cpu(emu):
+    feats, cams, hypo = et_inputs(1, 3, 8, 8, 4, 4, 8, 2.0, seed=2)
+    ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)
+    want = oracle.et_aggregate(feats, cams, hypo, False, 8, 2.0)                           # group_cor=False: (ref - warped)^2 per channel
+    got = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, 8, 2.0, group_cor=False))
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+    feats, cams, hypo = et_inputs(1, 3, 16, 4, 4, 4, 8, 2.0, seed=3)
+    ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)
+    want = oracle.et_aggregate(feats, cams, hypo, True, 4, 2.0, attn_fuse_d=False)
+    got = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, 4, 2.0, fuse_d=False))
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+    full = capi.et_fuse(ref, srcs, pose, hypo, 4, 2.0)
+    c1, w1 = torch.empty_like(full), torch.empty((1, 4, 4, 8))
+    capi.et_fuse(ref, srcs[:1], pose[:, :1].contiguous(), hypo, 4, 2.0, cost=c1, wsum=w1, partial=True)
+    capi.et_fuse(ref, srcs[1:], pose[:, 1:].contiguous(), hypo, 4, 2.0, cost=c1, wsum=w1, partial=True, accumulate=True)
+    capi.et_normalize(c1, w1)
+    assert (c1 - full).abs().max().item() <= 1e-5 * full.abs().max().item()
+
+
+# ----------------------------------------------------------------------------- regulariser + head (exact-fp32 CUDA-core path)
+@pytest.mark.parametrize("k,D,H,W", [(0, 8, 8, 8), (3, 4, 16, 8)])
+def test_reg2d_and_head_on_cpu_match_oracle(emu, k, D, H, W):
+    sd = build_model(SHIPPED, 5).state_dict()
+    G = SHIPPED["group_cor_dim"][k]
+    rng = np.random.RandomState(k)
+    cost = torch.from_numpy((rng.randn(1, G, D, H, W) * 0.1).astype(np.float32))
+    hypo = oracle.hypo_init_inverse(torch.tensor([[425.0, 935.0]]), D, H, W)
+    with torch.no_grad():
+        logits = oracle.reg2d_logits(sd, f"reg.{k}", cost)
+        want = oracle.depth_head(logits, hypo, k, 0.5, True)
+    packed = packing.pack_reg2d(sd, f"reg.{k}", capi.reg2d_layer_table(G))
+    feat8 = capi.reg2d(packed["blob"], cost.permute(0, 2, 3, 4, 1).contiguous())
+    h = capi.head(hypo, 0.5, feat8=feat8, prob_w=packed["prob_w"], prob_b=packed["prob_b"])
+    assert (h["attn_weight"] - want["attn_weight"]).abs().max().item() < 2e-5
+    gap = want["attn_weight"].topk(2, dim=1).values
+    stable = (gap[:, 0] - gap[:, 1]) > 1e-3
+    assert torch.equal(h["depth"][stable], want["depth"][stable])                           # winner-take-all: gathered, so bit-exact
+    assert ((h["inverse_min_depth"] - want["inverse_min_depth"]).abs()[stable] <= 1e-6 * want["inverse_min_depth"].abs()[stable]).all()
+
+
+def test_reg3d_on_cpu_matches_oracle(emu):
+    cfg = dict(reg_net="reg3d", group_cor=True, group_cor_dim=[8, 8, 4, 4], inverse_depth=True, attn_temp=2)
+    sd = build_model(cfg, 6).state_dict()
+    rng = np.random.RandomState(4)
+    cost = torch.from_numpy((rng.randn(1, 4, 4, 8, 8) * 0.1).astype(np.float32))
+    with torch.no_grad():
+        want = oracle.reg3d_logits(sd, "reg.3", cost, 2)
+    blob = packing.pack_reg3d(sd, "reg.3", capi.reg3d_layer_table(4, 2))
+    got = capi.reg3d(blob, cost.permute(0, 2, 3, 4, 1).contiguous(), 2)
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+
+
+# ----------------------------------------------------------------------------- feature pyramid (CUDA-core path)
+@pytest.mark.parametrize("fused_last", [True, False])
+def test_native_fpn_on_cpu_matches_oracle(emu, fused_last):
+    sd = build_model(SHIPPED, 4).state_dict()
+    imgs, _, _ = synth.make_inputs(1, 2, 16, 24, seed=8)
+    x = torch.cat(imgs, 0)
+    with torch.no_grad():
+        want = oracle.fpn4_features(sd, x)
+    got = fpn_engine.run_fpn(fpn_engine.pack_fpn(sd), x, 0, fused_last=fused_last)
+    for s in range(1, 5):
+        g, w = got[f"stage{s}"].permute(0, 3, 1, 2), want[f"stage{s}"]
+        assert g.shape == w.shape and ((g - w).abs().max() / w.abs().max()).item() < 2e-5, s
+
+
+# ----------------------------------------------------------------------------- geometric-consistency filter
 @pytest.mark.parametrize("name", ["plane_4v_48x64", "plane_3v_40x56_wide"])
-def test_geo_consistency_kernel_source_on_cpu_matches_reference(emu, name):
+def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
     from mvster_b200.fusion import _prepare_mats
     z = np.load(GOLDEN / "fusion" / f"{name}.npz")
     nv, H, W, seed = (int(x) for x in z["meta"])
     views = fusion_oracle.synthetic_scene(nv, H, W, seed, float(z["step"]))
     ref = views[0]
     count, dsum = np.zeros((H, W), np.int32), np.zeros((H, W), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     for v in range(1, nv):
         s = views[v]
-        mats = np.ascontiguousarray(_prepare_mats(ref["K"], ref["E"], s["K"], s["E"]))
+        mats = (C.c_double * 60)(*_prepare_mats(ref["K"], ref["E"], s["K"], s["E"]).tolist())
         dr, xs, ys = (np.empty((H, W), np.float32) for _ in range(3))
         mask = np.empty((H, W), np.uint8)
-        rc = emu.emu_geo_consistency(fptr(ref["depth"]), fptr(s["depth"]), mats.ctypes.data_as(C.c_void_p), fptr(dr), fptr(xs), fptr(ys),
-                                     fptr(mask), fptr(count), fptr(dsum), H, W, H, W, C.c_float(1.0), C.c_float(0.01))
+        rc = emu.mvster_geo_consistency_f32(p(ref["depth"]), p(s["depth"]), mats, p(dr), p(xs), p(ys), p(mask), p(count), p(dsum),
+                                            H, W, H, W, 1.0, 0.01, None)
         assert rc == 0
-        assert np.array_equal(mask.astype(bool), z[f"mask{v}"])
-        assert np.array_equal(dr, z[f"depth_reprojected{v}"])
+        assert np.array_equal(mask.astype(bool), z[f"mask{v}"]) and np.array_equal(dr, z[f"depth_reprojected{v}"])
         assert np.array_equal(xs, z[f"x2d_src{v}"], equal_nan=True) and np.array_equal(ys, z[f"y2d_src{v}"], equal_nan=True)
     assert np.array_equal(count, z["geo_mask_sum"])
     assert np.array_equal((dsum + ref["depth"]) / (count + 1), z["depth_est_averaged"])
