@@ -6,6 +6,7 @@
 //   fpn_merge_kernel    top-down merge: bilinear x2 (align_corners) of the coarser map + 1x1 lateral conv (:479-486)
 // The 3x3 stride-1 layers with Cin >= 16 (73 % of FPN4's FLOPs) run on the tcgen05 kernel of conv_tc2.cu.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mvster {
 
@@ -307,6 +308,105 @@ __global__ void __launch_bounds__(128) fpn_out4_gather_kernel(const float* __res
     dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
+// ---- variant 2 (opt-in, MVSTER_FPN_GATHER=2; not timed yet): the same sum from shared memory --------------------------
+// fpn_out4_gather_kernel pushes 45 256-bit loads per output pixel through the load path (9 taps x (4 bilinear samples of U +
+// 1 pixel of c0)) although neighbouring pixels share almost all of them.  Here a CTA owns an 8 x 32 tile of output pixels and
+// first stages what the tile needs - the (8+2) x (32+2) halo of c0 and, for each of the 9 tap planes of U, the <= 7 x 20 patch
+// of half-resolution pixels its bilinear samples can touch - with coalesced 128-bit loads, split into two 4-channel halves so
+// that the per-pixel 128-bit reads of consecutive lanes are conflict-free; the per-pixel arithmetic is the v1 expression, term
+// for term, so both kernels return the same bits (tests/test_emu_kernels.py runs them against each other on the CPU).
+constexpr int G2_TH = 8, G2_TW = 32, G2_RMAX = 7, G2_CMAX = 20, G2_UPX = G2_RMAX * G2_CMAX, G2_CPX = (G2_TH + 2) * (G2_TW + 2);
+constexpr int G2_SMEM_FLOATS = 9 * 2 * G2_UPX * 4 + 2 * G2_CPX * 4 + 576 + 72;
+
+__global__ void __launch_bounds__(256) fpn_out4_gather2_kernel(const float* __restrict__ U, long long tap_stride, const float* __restrict__ c0,
+                                                               const float* __restrict__ wc, const float* __restrict__ bt,
+                                                               float* __restrict__ out, int N, int H, int W) {
+    extern __shared__ __align__(16) float g2_s[];
+    float* const u_s = g2_s;                          // [9][2][G2_UPX][4]
+    float* const c_s = u_s + 9 * 2 * G2_UPX * 4;      // [2][G2_CPX][4]
+    float* const wc_s = c_s + 2 * G2_CPX * 4;         // [9][8][8] then [9][8]
+    const int tid = threadIdx.x, b = blockIdx.z;
+    const int x0 = blockIdx.x * G2_TW, y0 = blockIdx.y * G2_TH;
+    const int Hc = H / 2, Wc = W / 2;
+    const float sy = Hc > 1 ? __fdiv_rn((float)(Hc - 1), (float)(H - 1)) : 0.f, sx = Wc > 1 ? __fdiv_rn((float)(Wc - 1), (float)(W - 1)) : 0.f;
+    for (int i = tid; i < 576; i += 256) wc_s[i] = __ldg(wc + i);
+    if (tid < 72) wc_s[576 + tid] = __ldg(bt + tid);
+    // half-resolution patch covered by the tile's bilinear samples (clamped fine rows y0-1 .. y0+TH, columns x0-1 .. x0+TW)
+    const int fy_lo = max(y0 - 1, 0), fy_hi = min(y0 + G2_TH, H - 1), fx_lo = max(x0 - 1, 0), fx_hi = min(x0 + G2_TW, W - 1);
+    const int r_lo = min((int)floorf(__fmul_rn(sy, (float)fy_lo)), Hc - 1), c_lo = min((int)floorf(__fmul_rn(sx, (float)fx_lo)), Wc - 1);
+    int r_hi = min((int)floorf(__fmul_rn(sy, (float)fy_hi)), Hc - 1), c_hi = min((int)floorf(__fmul_rn(sx, (float)fx_hi)), Wc - 1);
+    r_hi += (r_hi < Hc - 1); c_hi += (c_hi < Wc - 1);
+    const int nr = r_hi - r_lo + 1, nc = c_hi - c_lo + 1;  // <= G2_RMAX, G2_CMAX (scale < 1/2)
+    const float* Ub = U + (long long)b * Hc * Wc * 8;
+    for (int i = tid; i < 9 * nr * nc * 2; i += 256) {
+        const int half = i & 1, px = (i >> 1) % (nr * nc), tap = (i >> 1) / (nr * nc);
+        const int r = px / nc, c = px % nc;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(Ub + tap * tap_stride + ((long long)(r_lo + r) * Wc + (c_lo + c)) * 8 + half * 4));
+        *reinterpret_cast<float4*>(u_s + ((tap * 2 + half) * G2_UPX + r * G2_CMAX + c) * 4) = v;
+    }
+    const float* cb = c0 + (long long)b * H * W * 8;
+    for (int i = tid; i < G2_CPX * 2; i += 256) {
+        const int half = i & 1, px = i >> 1, r = px / (G2_TW + 2), c = px % (G2_TW + 2);
+        const int yy = y0 - 1 + r, xx = x0 - 1 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W)
+            v = __ldg(reinterpret_cast<const float4*>(cb + ((long long)yy * W + xx) * 8 + half * 4));
+        *reinterpret_cast<float4*>(c_s + (half * G2_CPX + px) * 4) = v;
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5, x = x0 + tx, y = y0 + ty;
+    if (x >= W || y >= H) return;
+    int ry0[3], ry1[3], rx0[3], rx1[3];
+    float wy1[3], wx1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int yy = min(max(y + k - 1, 0), H - 1), xx = min(max(x + k - 1, 0), W - 1);
+        const float fy = __fmul_rn(sy, (float)yy), fx = __fmul_rn(sx, (float)xx);
+        ry0[k] = min((int)floorf(fy), Hc - 1); rx0[k] = min((int)floorf(fx), Wc - 1);
+        ry1[k] = ry0[k] + (ry0[k] < Hc - 1); rx1[k] = rx0[k] + (rx0[k] < Wc - 1);
+        wy1[k] = fminf(fmaxf(fy - (float)ry0[k], 0.f), 1.f); wx1[k] = fminf(fmaxf(fx - (float)rx0[k], 0.f), 1.f);
+        ry0[k] -= r_lo; ry1[k] -= r_lo; rx0[k] -= c_lo; rx1[k] -= c_lo;  // patch coordinates
+    }
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        if ((unsigned)(y + ky - 1) >= (unsigned)H) continue;  // zero padding of the 3x3 conv
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            if ((unsigned)(x + kx - 1) >= (unsigned)W) continue;
+            const int tap = ky * 3 + kx;
+            const int cp = (ty + ky) * (G2_TW + 2) + (tx + kx);
+            const float4 cl = *reinterpret_cast<const float4*>(c_s + cp * 4), ch = *reinterpret_cast<const float4*>(c_s + (G2_CPX + cp) * 4);
+            const float cv[8] = {cl.x, cl.y, cl.z, cl.w, ch.x, ch.y, ch.z, ch.w};
+            const float* wt = wc_s + tap * 64;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[o] += wc_s[576 + tap * 8 + o];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = fmaf(cv[c], wt[c * 8 + o], acc[o]);
+            const float ly1 = wy1[ky], ly0 = 1.f - ly1, lx1 = wx1[kx], lx0 = 1.f - lx1;
+            const int p00 = ry0[ky] * G2_CMAX + rx0[kx], p01 = ry0[ky] * G2_CMAX + rx1[kx];
+            const int p10 = ry1[ky] * G2_CMAX + rx0[kx], p11 = ry1[ky] * G2_CMAX + rx1[kx];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const float* up = u_s + (tap * 2 + half) * G2_UPX * 4;
+                const float4 a00 = *reinterpret_cast<const float4*>(up + p00 * 4), a01 = *reinterpret_cast<const float4*>(up + p01 * 4);
+                const float4 a10 = *reinterpret_cast<const float4*>(up + p10 * 4), a11 = *reinterpret_cast<const float4*>(up + p11 * 4);
+                acc[half * 4 + 0] += ly0 * (lx0 * a00.x + lx1 * a01.x) + ly1 * (lx0 * a10.x + lx1 * a11.x);
+                acc[half * 4 + 1] += ly0 * (lx0 * a00.y + lx1 * a01.y) + ly1 * (lx0 * a10.y + lx1 * a11.y);
+                acc[half * 4 + 2] += ly0 * (lx0 * a00.z + lx1 * a01.z) + ly1 * (lx0 * a10.z + lx1 * a11.z);
+                acc[half * 4 + 3] += ly0 * (lx0 * a00.w + lx1 * a01.w) + ly1 * (lx0 * a10.w + lx1 * a11.w);
+            }
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(out + (((long long)b * H + y) * W + x) * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
 }  // namespace mvster
 
 extern "C" int mvster_fpn_out4_gather_f32(const float* U, int u_channels, const float* c0, const float* w_comp, const float* b_tap,
@@ -317,6 +417,14 @@ extern "C" int mvster_fpn_out4_gather_f32(const float* U, int u_channels, const 
                    "mvster_fpn_out4_gather_f32: U is [..][>= 72 channels] (9 taps x 8 interleaved) or, with u_channels = 8, planar [9][N][H/2][W/2][8]");
     const long long n = (long long)N * H * W;
     const long long tap_stride = u_channels == 8 ? (long long)N * (H / 2) * (W / 2) * 8 : 8;
+    const char* variant = getenv("MVSTER_FPN_GATHER");
+    if (variant && atoi(variant) == 2 && u_channels == 8 && N < 65536) {  // shared-memory tiled variant (opt-in until it has been timed)
+        auto k = mvster::fpn_out4_gather2_kernel;
+        const size_t smem = (size_t)mvster::G2_SMEM_FLOATS * sizeof(float);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<dim3(mvster::ceil_div(W, mvster::G2_TW), mvster::ceil_div(H, mvster::G2_TH), N), 256, smem, (cudaStream_t)stream>>>(U, tap_stride, c0, w_comp, b_tap, out, N, H, W);
+        return mvster::check_launch("fpn_out4_gather2_kernel");
+    }
     mvster::fpn_out4_gather_kernel<<<mvster::ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(U, u_channels, tap_stride, c0, w_comp, b_tap, out, N, H, W);
     return mvster::check_launch("fpn_out4_gather_kernel");
 }

@@ -213,6 +213,28 @@ def test_native_fpn_on_cpu_matches_oracle(emu, fused_last):
         assert g.shape == w.shape and ((g - w).abs().max() / w.abs().max()).item() < 2e-5, s
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 16, 24), (1, 24, 80), (1, 10, 34), (1, 2, 2)])
+def test_tiled_gather_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, H, W):
+    """fpn_out4_gather2_kernel (shared-memory tiles, MVSTER_FPN_GATHER=2) against fpn_out4_gather_kernel: same expression per
+    pixel, so the outputs must be identical - multi-tile, ragged and single-pixel-patch shapes."""
+    rng = np.random.RandomState(H * W)
+    U = torch.from_numpy(rng.randn(9, N, H // 2, W // 2, 8).astype(np.float32))
+    c0 = torch.from_numpy(rng.randn(N, H, W, 8).astype(np.float32))
+    wc = torch.from_numpy((rng.randn(9, 8, 8) / 8).astype(np.float32))
+    bt = torch.from_numpy(rng.randn(9, 8).astype(np.float32))
+
+    def run():
+        out = torch.full((N, H, W, 8), float("nan"))
+        rc = emu.mvster_fpn_out4_gather_f32(capi._ptr(U), 8, capi._ptr(c0), capi._ptr(wc), capi._ptr(bt), capi._ptr(out), N, H, W, None)
+        assert rc == 0
+        return out
+    monkeypatch.delenv("MVSTER_FPN_GATHER", raising=False)
+    want = run()
+    monkeypatch.setenv("MVSTER_FPN_GATHER", "2")
+    got = run()
+    assert torch.isfinite(want).all() and torch.equal(got, want)
+
+
 # ----------------------------------------------------------------------------- geometric-consistency filter
 @pytest.mark.parametrize("name", ["plane_4v_48x64", "plane_3v_40x56_wide"])
 def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
