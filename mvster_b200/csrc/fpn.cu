@@ -168,6 +168,75 @@ __global__ void __launch_bounds__(128) fpn_merge_kernel(const float* __restrict_
     *reinterpret_cast<float4*>(out + v * 64 + q * 4) = make_float4(up.x + lv.x, up.y + lv.y, up.z + lv.z, up.w + lv.w);
 }
 
+// Variant 2 of the merge (opt-in, MVSTER_FPN_MERGE=2; not timed yet): the same 16 lanes per pixel, but every lane keeps its
+// 4 output channels for FOUR consecutive pixels of a row, so each weight row is read from shared memory once per 4 pixels and
+// 16 independent loads of `top` are in flight per lane.  Per pixel the arithmetic is the v1 expression term for term (same bits).
+template <int CL>
+__global__ void __launch_bounds__(128) fpn_merge4_kernel(const float* __restrict__ top, const float* __restrict__ lat,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float* __restrict__ out, int N, int H, int W) {
+    __shared__ __align__(16) float w_s[CL * 64 + 64];
+    for (int i = threadIdx.x; i < CL * 64; i += blockDim.x) w_s[i] = __ldg(w + i);
+    if (threadIdx.x < 64) w_s[CL * 64 + threadIdx.x] = __ldg(bias + threadIdx.x);
+    __syncthreads();
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int q = (int)(t & 15);
+    const long long g = t >> 4;
+    const int gpr = (W + 3) / 4;  // pixel groups per row
+    if (g >= (long long)N * H * gpr) return;
+    const int xg = (int)(g % gpr), y = (int)((g / gpr) % H), b = (int)(g / ((long long)gpr * H));
+    const int Hc = H / 2, Wc = W / 2;
+    const float sy = Hc > 1 ? __fdiv_rn((float)(Hc - 1), (float)(H - 1)) : 0.f, sx = Wc > 1 ? __fdiv_rn((float)(Wc - 1), (float)(W - 1)) : 0.f;
+    const float fy = __fmul_rn(sy, (float)y);
+    const int y0 = min((int)floorf(fy), Hc - 1);
+    const int y1 = y0 + (y0 < Hc - 1);
+    const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), ly0 = 1.f - ly1;
+    const float* tb = top + (long long)b * Hc * Wc * 64 + q * 4;
+    float4 up[4], lv[4];
+    const float4 b4 = *reinterpret_cast<const float4*>(w_s + CL * 64 + q * 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = min(xg * 4 + j, W - 1);  // a ragged last group repeats the last pixel (never stored)
+        const float fx = __fmul_rn(sx, (float)x);
+        const int x0 = min((int)floorf(fx), Wc - 1);
+        const int x1 = x0 + (x0 < Wc - 1);
+        const float lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f), lx0 = 1.f - lx1;
+        const float4 a00 = __ldg(reinterpret_cast<const float4*>(tb + ((long long)y0 * Wc + x0) * 64));
+        const float4 a01 = __ldg(reinterpret_cast<const float4*>(tb + ((long long)y0 * Wc + x1) * 64));
+        const float4 a10 = __ldg(reinterpret_cast<const float4*>(tb + ((long long)y1 * Wc + x0) * 64));
+        const float4 a11 = __ldg(reinterpret_cast<const float4*>(tb + ((long long)y1 * Wc + x1) * 64));
+        up[j].x = ly0 * (lx0 * a00.x + lx1 * a01.x) + ly1 * (lx0 * a10.x + lx1 * a11.x);
+        up[j].y = ly0 * (lx0 * a00.y + lx1 * a01.y) + ly1 * (lx0 * a10.y + lx1 * a11.y);
+        up[j].z = ly0 * (lx0 * a00.z + lx1 * a01.z) + ly1 * (lx0 * a10.z + lx1 * a11.z);
+        up[j].w = ly0 * (lx0 * a00.w + lx1 * a01.w) + ly1 * (lx0 * a10.w + lx1 * a11.w);
+        lv[j] = b4;
+    }
+    const long long row = ((long long)b * H + y) * W;
+#pragma unroll
+    for (int c4 = 0; c4 < CL / 4; ++c4) {
+        float tv[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 tt = __ldg(reinterpret_cast<const float4*>(lat + (row + min(xg * 4 + j, W - 1)) * CL) + c4);
+            tv[j][0] = tt.x; tv[j][1] = tt.y; tv[j][2] = tt.z; tv[j][3] = tt.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float4 wr = *reinterpret_cast<const float4*>(w_s + (c4 * 4 + e) * 64 + q * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                lv[j].x = fmaf(tv[j][e], wr.x, lv[j].x); lv[j].y = fmaf(tv[j][e], wr.y, lv[j].y);
+                lv[j].z = fmaf(tv[j][e], wr.z, lv[j].z); lv[j].w = fmaf(tv[j][e], wr.w, lv[j].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (xg * 4 + j < W)
+            *reinterpret_cast<float4*>(out + (row + xg * 4 + j) * 64 + q * 4) =
+                make_float4(up[j].x + lv[j].x, up[j].y + lv[j].y, up[j].z + lv[j].z, up[j].w + lv[j].w);
+}
+
 }  // namespace mvster
 
 using namespace mvster;
@@ -205,9 +274,19 @@ extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, cons
                                     int N, int H, int W, int Clat, mvster_stream_t stream) {
     MVSTER_REQUIRE(top && lateral && w && bias && out, "mvster_fpn_merge_f32: null pointer");
     MVSTER_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mvster_fpn_merge_f32: H,W must be even");
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* variant = getenv("MVSTER_FPN_MERGE");
+    if (variant && atoi(variant) == 2) {  // four pixels per lane (opt-in until it has been timed)
+        const long long n4 = (long long)N * H * ((W + 3) / 4) * 16;
+        dim3 grid4(ceil_div(n4, 128));
+        if (Clat == 8) fpn_merge4_kernel<8><<<grid4, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+        else if (Clat == 16) fpn_merge4_kernel<16><<<grid4, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+        else if (Clat == 32) fpn_merge4_kernel<32><<<grid4, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+        else MVSTER_REQUIRE(false, "mvster_fpn_merge_f32: unsupported lateral channels %d (8,16,32)", Clat);
+        return check_launch("fpn_merge4_kernel");
+    }
     const long long n = (long long)N * H * W * 16;  // 16 lanes per pixel
     dim3 grid(ceil_div(n, 128));
-    cudaStream_t st = (cudaStream_t)stream;
     if (Clat == 8) fpn_merge_kernel<8><<<grid, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
     else if (Clat == 16) fpn_merge_kernel<16><<<grid, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
     else if (Clat == 32) fpn_merge_kernel<32><<<grid, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);

@@ -235,6 +235,21 @@ def test_tiled_gather_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, 
     assert torch.isfinite(want).all() and torch.equal(got, want)
 
 
+@pytest.mark.parametrize("N,H,W,CL", [(2, 8, 12, 32), (1, 6, 10, 16), (1, 4, 30, 8)])
+def test_four_pixel_merge_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, H, W, CL):
+    """fpn_merge4_kernel (MVSTER_FPN_MERGE=2) against fpn_merge_kernel, ragged rows included (W not a multiple of 4)."""
+    rng = np.random.RandomState(H * W + CL)
+    top = torch.from_numpy(rng.randn(N, H // 2, W // 2, 64).astype(np.float32))
+    lat = torch.from_numpy(rng.randn(N, H, W, CL).astype(np.float32))
+    w = torch.from_numpy((rng.randn(CL, 64) / 4).astype(np.float32))
+    bias = torch.from_numpy(rng.randn(64).astype(np.float32))
+    monkeypatch.delenv("MVSTER_FPN_MERGE", raising=False)
+    want = fpn_engine._merge(top, lat, w, bias)
+    monkeypatch.setenv("MVSTER_FPN_MERGE", "2")
+    got = fpn_engine._merge(top, lat, w, bias)
+    assert torch.isfinite(want).all() and torch.equal(got, want)
+
+
 # ----------------------------------------------------------------------------- geometric-consistency filter
 @pytest.mark.parametrize("name", ["plane_4v_48x64", "plane_3v_40x56_wide"])
 def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
