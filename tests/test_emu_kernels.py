@@ -147,6 +147,26 @@ def test_window_kernel_on_cpu_matches_oracle(emu, case):
     assert torch.isfinite(got).all() and (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_et_kernels_agree_on_extreme_geometry_on_cpu(emu, seed):
+    """Wide baselines and hypotheses from very near to very far: most taps fall outside the source images, sampling positions
+    reach thousands of pixels, hypotheses of one pixel straddle several cells - the window kernel must fall back where it has to
+    and every variant must still match the oracle (zeros padding per tap)."""
+    rng = np.random.RandomState(100 + seed)
+    B, nv, C_, G, D, H, W = 1, 3, 8, 4, 4, 8, 32
+    feats = [torch.from_numpy(rng.randn(B, C_, H, W).astype(np.float32)) for _ in range(nv)]
+    cams = synth.stage_projections(synth.arc_cameras(nv, H, W, [25.0, 8.0, 1.0][seed]), B, num_stage=1)["stage1"]
+    base = torch.from_numpy(np.exp(rng.uniform(np.log(5.0), np.log(5e4), (B, 1, H, W))).astype(np.float32))
+    hypo = (base * torch.tensor([1.0, 0.999, 0.5, 0.01]).reshape(1, D, 1, 1)).contiguous()
+    want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0)
+    ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)
+    scale = max(want.abs().max().item(), 1e-3)
+    for kw in (dict(generic=True), dict(window=False), dict(window=True)):
+        got = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, **kw))
+        assert torch.isfinite(got).all(), kw
+        assert (got - want).abs().max().item() <= 5e-4 * scale, (kw, (got - want).abs().max().item(), scale)
+
+
 def test_et_variants_sqdiff_no_fuse_d_partial_on_cpu(emu):
     feats, cams, hypo = et_inputs(1, 3, 8, 8, 4, 4, 8, 2.0, seed=2)
     ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)
