@@ -56,6 +56,21 @@ class InferenceEngine:
         self.plans: List[StagePlan] = []
         self._graphs: Dict = {}
         self._side = None  # second stream for the early cascade stages (_forward_overlapped)
+        self.fp16_safe = {"fpn": True, "reg": True}  # folded weights inside the two-fp16-term range (refresh_weights)
+        self._warned_fp16 = False
+
+    def _precision(self, net, which: str) -> str:
+        """Arithmetic of the convolutions of ``which`` ("fpn" | "reg"): the module's setting, except that "2xfp16" becomes "3xbf16"
+        (same kernel, full fp32 range) for a model whose folded weights do not fit the fp16 terms."""
+        prec = getattr(net, which + "_precision", "fp32")
+        if prec == "2xfp16" and not self.fp16_safe.get(which, True):
+            if not self._warned_fp16:
+                import warnings
+                warnings.warn(f"mvster_b200: folded {which} weights exceed the range of the two-fp16-term arithmetic "
+                              f"(|w| > {packing.FP16_WEIGHT_LIMIT:g} or non-finite); using three bf16 terms instead")
+                self._warned_fp16 = True
+            return "3xbf16"
+        return prec
 
     # ------------------------------------------------------------------ weights
     def refresh_weights(self, net) -> None:
@@ -65,13 +80,16 @@ class InferenceEngine:
         self.plans = [StagePlan(k, net) for k in range(net.num_stage)]
         self.stage_weights = []
         fpn_sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("feature.")}
-        self.fpn_weights = {k: v.to(self.device) for k, v in fpn_engine.pack_fpn(fpn_sd).items()}
+        fpn_packed = fpn_engine.pack_fpn(fpn_sd)
+        self.fp16_safe = {"fpn": packing.fp16_range_ok(v for k, v in fpn_packed.items() if k.endswith(".w")), "reg": True}
+        self.fpn_weights = {k: v.to(self.device) for k, v in fpn_packed.items()}
         with torch.cuda.device(self.device):
             for p in self.plans:
                 if net.reg_net == "reg2d":
                     packed = packing.pack_reg2d(sd, f"reg.{p.k}", capi.reg2d_layer_table(p.G))
                 else:
                     packed = {"blob": packing.pack_reg3d(sd, f"reg.{p.k}", capi.reg3d_layer_table(p.G, p.down))}
+                self.fp16_safe["reg"] = self.fp16_safe["reg"] and packing.fp16_range_ok([packed["blob"]])
                 self.stage_weights.append({k: v.to(self.device) for k, v in packed.items()})
 
     # ------------------------------------------------------------------ full forward
@@ -85,7 +103,7 @@ class InferenceEngine:
             if getattr(net, "fpn_backend", "torch") == "native":
                 # FPN4 inside libmvster_b200 (fpn_engine.py): NCHW images in, NHWC features out
                 x = torch.cat([imgs[v] for v in own], 0).to(dtype=torch.float32).contiguous()
-                prec = getattr(net, "fpn_precision", "fp32")
+                prec = self._precision(net, "fpn")
                 npass = {"fp32": 0, "3xtf32": 3, "tf32": 1, "3xbf16": 3, "2xfp16": 2}[prec]
                 gen = 3 if prec in ("3xbf16", "2xfp16") else 2
                 if shard is None and net.num_stage == 4 and getattr(net, "overlap_stages", True):
@@ -106,8 +124,8 @@ class InferenceEngine:
         Inputs are copied into static buffers; the returned tensors are the graph's static outputs and stay
         valid until the next call with the same signature (``test_mvs4.py`` converts to numpy right away)."""
         key = (tuple(tuple(t.shape) for t in imgs), tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
-               tuple(depth_values.shape), self.weights_version, getattr(net, "reg_precision", "fp32"),
-               getattr(net, "tc_kernel_gen", 1), getattr(net, "fpn_backend", "torch"), getattr(net, "fpn_precision", "fp32"),
+               tuple(depth_values.shape), self.weights_version, self._precision(net, "reg"),
+               getattr(net, "tc_kernel_gen", 1), getattr(net, "fpn_backend", "torch"), self._precision(net, "fpn"),
                getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"))
         entry = self._graphs.get(key)
         if entry is None:
@@ -156,7 +174,7 @@ class InferenceEngine:
         if net.reg_net == "reg3d":
             logits = capi.reg3d(wts["blob"], cost, p.down)
             return capi.head(hypo, p.split_itv, logits=logits, inverse=inverse)
-        prec = getattr(net, "reg_precision", "fp32")
+        prec = self._precision(net, "reg")
         if prec == "fp32":      # exact fp32 FMA on the CUDA cores for every layer
             feat8 = capi.reg2d(wts["blob"], cost)
         elif prec == "3xbf16":  # conv0..conv6 on the persistent tcgen05 kernel, three bf16 terms per operand (fp32-faithful)

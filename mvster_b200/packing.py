@@ -88,6 +88,19 @@ def fp16_split2(w: Tensor) -> Tuple[Tensor, Tensor]:
     return t1, t2
 
 
+FP16_WEIGHT_LIMIT = 3.0e4  # |w| above this leaves no headroom below fp16's 65504: such a model runs with three bf16 terms instead
+
+
+def fp16_range_ok(tensors) -> bool:
+    """True if every (finite) value of the given folded weight tensors stays inside the range the two-fp16-term arithmetic
+    represents faithfully (``MVSTER_TC3_FP16X2``); the engine falls back to three bf16 terms otherwise."""
+    for t in tensors:
+        t = t.detach().float()
+        if t.numel() and (not bool(torch.isfinite(t).all()) or float(t.abs().max()) > FP16_WEIGHT_LIMIT):
+            return False
+    return True
+
+
 def _split_terms(wt: Tensor, split: int):
     """16-bit operand terms of a weight matrix as raw int16 bit patterns: split 3 = three bf16 terms, 2 = two fp16 terms."""
     if split == 3:

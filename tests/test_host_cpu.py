@@ -202,3 +202,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     quiet = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                            capture_output=True, text=True, timeout=60, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert quiet.returncode == 0 and not quiet.stdout.strip()
+
+
+def test_fp16_arithmetic_falls_back_when_weights_leave_its_range():
+    """The default '2xfp16' convolution arithmetic holds values below 65504; a model whose folded weights do not fit runs with
+    three bf16 terms instead (engine._precision), with one warning."""
+    import types
+    import warnings
+    from mvster_b200.engine import InferenceEngine
+    assert packing.fp16_range_ok([torch.randn(3, 3)]) and packing.fp16_range_ok([])
+    assert not packing.fp16_range_ok([torch.tensor([1.0, -4.0e4])]) and not packing.fp16_range_ok([torch.tensor([float("inf")])])
+    eng = InferenceEngine(torch.device("cpu"))
+    net = types.SimpleNamespace(fpn_precision="2xfp16", reg_precision="2xfp16")
+    assert eng._precision(net, "fpn") == "2xfp16" and eng._precision(net, "reg") == "2xfp16"
+    eng.fp16_safe["reg"] = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert eng._precision(net, "reg") == "3xbf16" and eng._precision(net, "reg") == "3xbf16" and eng._precision(net, "fpn") == "2xfp16"
+    assert len(w) == 1
+    net.reg_precision = "fp32"
+    assert eng._precision(net, "reg") == "fp32"
+    sd = build_model(SHIPPED, 0).state_dict()   # the benchmark's synthetic weights are far inside the range
+    from mvster_b200 import fpn_engine
+    fp = fpn_engine.pack_fpn({k: v for k, v in sd.items() if k.startswith("feature.")})
+    assert packing.fp16_range_ok(v for k, v in fp.items() if k.endswith(".w"))
+
