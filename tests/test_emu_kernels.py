@@ -292,3 +292,43 @@ def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
         assert np.array_equal(xs, z[f"x2d_src{v}"], equal_nan=True) and np.array_equal(ys, z[f"y2d_src{v}"], equal_nan=True)
     assert np.array_equal(count, z["geo_mask_sum"])
     assert np.array_equal((dsum + ref["depth"]) / (count + 1), z["depth_est_averaged"])
+
+
+# ----------------------------------------------------------------------------- the whole forward
+def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch):
+    """InferenceEngine.forward - native feature pyramid, four cascade stages, every convolution on the exact-fp32 CUDA-core
+    kernels - executed on the emulation library with CPU tensors, against the outputs of the unmodified reference
+    (tests/golden/shipped_b1_v3_64x128.npz): the same tie-aware, drift-aware criterion as the GPU test, and here every pixel
+    of every stage agrees."""
+    import contextlib
+    from util import GOLDEN_CASES, load_golden, top2_gap
+    from mvster_b200.engine import InferenceEngine
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    name = "shipped_b1_v3_64x128"
+    z, imgs, proj, dv = load_golden(name)
+    m = build_model(GOLDEN_CASES[name], int(z["meta_seed"]))
+    m.reg_precision = m.fpn_precision = "fp32"
+    m.overlap_stages, m.fpn_backend = False, "native"
+    eng = InferenceEngine(torch.device("cpu"))
+    eng.refresh_weights(m)
+    with torch.no_grad():
+        out = eng.forward(m, imgs, proj, dv)
+    drift_free = torch.ones_like(torch.from_numpy(z["s1_depth"]), dtype=torch.bool)
+    for s_ in range(1, 5):
+        st = out[f"stage{s_}"]
+        for key in ("depth", "photometric_confidence", "hypo_depth", "attn_weight", "inverse_min_depth", "inverse_max_depth"):
+            assert tuple(st[key].shape) == tuple(z[f"s{s_}_{key}"].shape), (s_, key)
+        ref_attn, ref_depth = torch.from_numpy(z[f"s{s_}_attn_weight"]), torch.from_numpy(z[f"s{s_}_depth"])
+        if s_ > 1:
+            drift_free = F.interpolate(drift_free.float()[:, None], scale_factor=2, mode="bilinear", align_corners=True)[:, 0] > 0.999
+        agree = (st["depth"] - ref_depth).abs() <= 1e-4 * ref_depth
+        stable = top2_gap(ref_attn) > 1e-3
+        bad = ((~agree) & stable & drift_free).float().sum().item() / max(1.0, (stable & drift_free).float().sum().item())
+        assert bad < 5e-3, f"stage {s_}: {bad:.3%} of tie-free, drift-free pixels differ by > 1e-4 relative"
+        if s_ == 1:
+            assert (st["attn_weight"] - ref_attn).abs().max().item() < 5e-5
+        drift_free = drift_free & agree
+    assert out["depth"].data_ptr() == out["stage4"]["depth"].data_ptr()
+    conf = torch.from_numpy(z["s4_photometric_confidence"])
+    assert (out["photometric_confidence"] - conf).abs()[drift_free].max().item() < 1e-4
+
