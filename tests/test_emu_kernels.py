@@ -23,43 +23,18 @@ from mvster_b200 import _lib, capi, fpn_engine, packing, synth
 sys.path.insert(0, str(REPO / "tests" / "emu"))
 
 
-class _EmuWithHostLogic:
-    """The emulation library for everything it exports; pure host logic of the tensor-core files (layer plans, packed sizes -
-    no kernel launches) is answered by the real library, which loads without a GPU."""
-    HOST_ONLY = {"mvster_conv_tc3_plan", "mvster_conv_tc3_packed_bytes", "mvster_conv_tc3_supported", "mvster_deconv_tc3_packed_bytes",
-                 "mvster_deconv_tc3_supported", "mvster_conv3d_tc_supported", "mvster_conv3d_tc2_supported"}
-
-    def __init__(self, emu, real):
-        self._emu, self._real = emu, real
-
-    def __getattr__(self, name):
-        if name in self.HOST_ONLY:
-            return getattr(self._real, name)
-        return getattr(self._emu, name)
-
-
 @pytest.fixture(scope="module")
 def emu_lib():
-    import build_emu
-    lib = C.CDLL(str(build_emu.build()))
-    for name, (res, args) in _lib.SIGNATURES.items():
-        if name in _EmuWithHostLogic.HOST_ONLY:
-            continue
-        fn = getattr(lib, name, None)
-        if fn is not None:
-            fn.restype, fn.argtypes = res, args
-    return _EmuWithHostLogic(lib, _lib.load())
+    import install
+    return install.load()
 
 
 @pytest.fixture()
 def emu(emu_lib, monkeypatch):
     """capi / fpn_engine on the emulation library, CPU tensors accepted."""
-    def chk(t, name, shape=None):
-        assert isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.is_contiguous() and not t.is_cuda, name
-        assert shape is None or tuple(t.shape) == tuple(shape), (name, tuple(t.shape), tuple(shape))
-        return t
+    import install
     monkeypatch.setattr(_lib, "_lib", emu_lib)
-    monkeypatch.setattr(capi, "_chk", chk)
+    monkeypatch.setattr(capi, "_chk", install.cpu_chk)
     monkeypatch.setattr(capi, "_stream", lambda: C.c_void_p(0))
     return emu_lib
 
