@@ -71,6 +71,7 @@ struct Args {
     // resident != 0: the layer's nslab weight slabs fit in shared memory next to the rings - they are loaded once per CTA and
     // stay; otherwise they stream through a ring of NB slabs per group of tiles (large Cin * taps * Cout)
     int resident, nslab;
+    int cin_merged;  // > 0: x_map is the 3-D map with (channels x pixels) merged; value = channels per pixel
 };
 
 // plain / planar-block / depth-to-space output addressing of a launch; false if an offset would not fit 32 bits
@@ -150,7 +151,10 @@ __device__ __forceinline__ void mma_tile(uint32_t lo, uint64_t bd, uint32_t d, u
     }
 }
 
-template <int NC, int NS>
+// MG (opt-in, MVSTER_TC3_MERGE=1; not timed yet): the activation tensor map has channels and pixels MERGED into one dimension
+// (stride-1 layers whose stage covers all channels, Cin <= 16), so a halo-tile row is one contiguous run for the TMA unit instead
+// of HW_ pixel-sized pieces; the bytes land in shared memory in the same order.
+template <int NC, int NS, bool MG = false>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ Plan plan, const Args a) {
     using C = Cfg<NC, NS>;
@@ -213,7 +217,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         mbar_expect_tx(F_FULL(fs), st.nq * QBYTES);
                         const int ti = tile0 + t, y0 = (ti / a.tiles_x) * TH, x0 = (ti % a.tiles_x) * TW;
                         // one box = [18][10] pixels x min(Cin,16) channels (64-byte rows); the converters re-lay it out for the MMA
-                        tma_load_4d(f_base + fs * F_BYTES, &x_map, F_FULL(fs), st.c0, a.sx * x0 + st.ox, a.sx * y0 + st.oy, plane + st.dz);
+                        if constexpr (MG)
+                            tma_load_3d(f_base + fs * F_BYTES, &x_map, F_FULL(fs), (x0 + st.ox) * a.cin_merged, y0 + st.oy, plane + st.dz);
+                        else
+                            tma_load_4d(f_base + fs * F_BYTES, &x_map, F_FULL(fs), st.c0, a.sx * x0 + st.ox, a.sx * y0 + st.oy, plane + st.dz);
                     }
                 }
             }
@@ -540,7 +547,7 @@ static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[6]
 // early cascade stages on a second stream next to the feature pyramid's large layers (engine.py).
 static int g_sm_budget = 0;
 
-template <int NC, int NS>
+template <int NC, int NS, bool MG = false>
 static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st) {
     using C = Cfg<NC, NS>;
     if (g_sm_budget > 0 && g_sm_budget < sms) sms = g_sm_budget;
@@ -550,7 +557,7 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
     a.T = T;
     a.groups_per_plane = ceil_div(a.tiles_per_plane, T);
     a.total_groups = (int)(total_tiles / a.tiles_per_plane) * a.groups_per_plane;
-    auto k = conv_tc3_kernel<NC, NS>;
+    auto k = conv_tc3_kernel<NC, NS, MG>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_MAX) != cudaSuccess) {
         set_error("conv_tc3_kernel: cannot reserve %d bytes of shared memory", C::SMEM_MAX);
         cudaGetLastError();
@@ -567,6 +574,10 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
 
 template <int NC>
 static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st, bool fp16x2) {
+    if constexpr (NC <= 32) {  // merged-dimension activation map: only small-Cin layers qualify (conv_tc3_run decides)
+        if (a.cin_merged > 0)
+            return fp16x2 ? launch_ns<NC, 2, true>(xm, plan, a, total_tiles, sms, st) : launch_ns<NC, 3, true>(xm, plan, a, total_tiles, sms, st);
+    }
     return fp16x2 ? launch_ns<NC, 2>(xm, plan, a, total_tiles, sms, st) : launch_ns<NC, 3>(xm, plan, a, total_tiles, sms, st);
 }
 
@@ -618,7 +629,16 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     }
     const int s = stride_hw;
     CUtensorMap xm;
-    {   // activations [B*D][H][W][C]; a box is <= 16 channels of an 18 x 10 pixel halo patch, every s-th pixel
+    static const bool want_merge = getenv("MVSTER_TC3_MERGE") && atoi(getenv("MVSTER_TC3_MERGE")) != 0;
+    const bool merged = want_merge && s == 1 && Cin <= 16 && Cout <= 32 && (long long)W * Cin < (1ll << 31);
+    if (merged) {  // [B*D][H][W*C]: a box row = the halo row's HW_ pixels x Cin channels as ONE contiguous run
+        cuuint64_t dims[3] = {(cuuint64_t)W * Cin, (cuuint64_t)H, (cuuint64_t)B * D};
+        cuuint64_t strides[2] = {(cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
+        cuuint32_t box[3] = {(cuuint32_t)(HW_ * Cin), (cuuint32_t)HH_, 1}, es[3] = {1, 1, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MVSTER_REQUIRE(r == CUDA_SUCCESS, "mvster_conv_tc3_f32: merged activation tensor map rejected (CUresult %d)", (int)r);
+    } else {   // activations [B*D][H][W][C]; a box is <= 16 channels of an 18 x 10 pixel halo patch, every s-th pixel
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * D};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
         cuuint32_t box[4] = {(cuuint32_t)(Cin < 16 ? Cin : 16), (cuuint32_t)(HW_ * s), (cuuint32_t)(HH_ * s), 1}, es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
@@ -631,6 +651,7 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     const int nslab = build_plan(Cin, kd, k, s, &plan, nullptr);
     Args a;
     a.nslab = nslab;
+    a.cin_merged = merged ? Cin : 0;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
     const bool fp16x2 = relu & MVSTER_TC3_FP16X2;
     a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = relu & 1; a.sx = s;
@@ -733,6 +754,7 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
     const bool fp16x2 = relu & MVSTER_TC3_FP16X2;
     a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = relu & 1; a.sx = 1; a.nstage = kch;
     a.nslab = kch * ntap;
+    a.cin_merged = 0;
     a.tiles_x = ceil_div(W, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
     a.zero_a = 0;

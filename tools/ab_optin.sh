@@ -1,0 +1,15 @@
+#!/bin/bash
+# A/B of the opt-in kernel variants that were prepared without GPU time (functionally checked on the CPU emulation or by SASS
+# inspection only): correctness on the GPU first, then the bench step with each switch.  Usage (on the B200 box):
+#     bash tools/ab_optin.sh 2>&1 | tee gpurun_out/ab_optin.txt
+set -u
+echo "== correctness with the switches on"
+MVSTER_TC3_MERGE=1 timeout 400 python -m pytest tests/test_gpu_tc_conv.py -m gpu -q -x -k "v3" 2>&1 | tail -2
+MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=2 MVSTER_FPN_MERGE=2 timeout 300 python -m pytest tests/test_gpu_y_fpn.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
+echo "== bench step (ms) per switch"
+for sw in "" "MVSTER_TC3_MERGE=1" "MVSTER_FPN_GATHER=2" "MVSTER_FPN_MERGE=2" "MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=2 MVSTER_FPN_MERGE=2"; do
+  out=$(env $sw timeout 200 python bench.py --no-cpu-baseline 2>/dev/null)
+  echo "$out" | python -c "
+import json,sys
+j=json.loads(sys.stdin.read()); print('%-70s %.4f ms  %.1f maps/s  e2e %.1f' % ('[$sw]', j['ms_per_step'], j['value'], j['e2e']['value']))"
+done
