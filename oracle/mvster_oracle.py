@@ -35,6 +35,34 @@ BN_EPS = 1e-5  # torch.nn.BatchNorm{2,3}d default, used by every BN in the refer
 
 
 # --------------------------------------------------------------------------
+# reduced-precision STORAGE (BASELINE cfg3 "bf16"): the reference has no bf16 path - its pixel grid is hard-coded fp32
+# (mvs4net_utils.py:28-29) and torch.autocast destroys the geometry - so the bf16 configuration is
+# defined as the fp32 reference with bf16 ROUNDING at the points where a bf16 build stores data: the FPN outputs, the cost
+# volume, and every convolution's operands (activations and weights; accumulation, BN, geometry and softmax stay fp32).
+# --------------------------------------------------------------------------
+_STORAGE = None
+
+
+class storage:
+    """``with storage(torch.bfloat16): ...`` - emulate that storage type in every function below (None = exact fp32)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _STORAGE
+        self.prev, _STORAGE = _STORAGE, self.dtype
+
+    def __exit__(self, *exc):
+        global _STORAGE
+        _STORAGE = self.prev
+
+
+def _q(x: Tensor) -> Tensor:
+    return x if _STORAGE is None or not x.is_floating_point() else x.to(_STORAGE).to(x.dtype)
+
+
+# --------------------------------------------------------------------------
 # small building blocks
 # --------------------------------------------------------------------------
 def _bn_eval(x: Tensor, sd: State, p: str) -> Tensor:
@@ -46,20 +74,20 @@ def _bn_eval(x: Tensor, sd: State, p: str) -> Tensor:
 
 def _cbr3(x: Tensor, sd: State, p: str, stride=(1, 1, 1), pad=(1, 1, 1)) -> Tensor:
     """conv3d(no bias) -> BN -> ReLU, mvs4net_utils.py:116-123."""
-    y = F.conv3d(x, sd[p + ".conv.weight"], None, stride, pad)
+    y = F.conv3d(_q(x), _q(sd[p + ".conv.weight"]), None, stride, pad)
     return F.relu(_bn_eval(y, sd, p + ".bn"))
 
 
 def _up3(x: Tensor, sd: State, p: str, stride, pad, out_pad) -> Tensor:
     """ConvTranspose3d(no bias) -> BN -> ReLU packed as nn.Sequential
     (indices .0/.1), mvs4net_utils.py:885-898 and :926-940."""
-    y = F.conv_transpose3d(x, sd[p + ".0.weight"], None, stride, pad, out_pad)
+    y = F.conv_transpose3d(_q(x), _q(sd[p + ".0.weight"]), None, stride, pad, out_pad)
     return F.relu(_bn_eval(y, sd, p + ".1"))
 
 
 def _cbr2(x: Tensor, sd: State, p: str, stride: int, pad: int, relu: bool = True) -> Tensor:
     """2-D conv -> BN -> ReLU block of the feature net, mvs4net_utils.py:224-251."""
-    y = _bn_eval(F.conv2d(x, sd[p + ".conv.weight"], None, stride, pad), sd, p + ".bn")
+    y = _bn_eval(F.conv2d(_q(x), _q(sd[p + ".conv.weight"]), None, stride, pad), sd, p + ".bn")
     return F.relu(y) if relu else y
 
 
@@ -80,15 +108,18 @@ def fpn4_features(sd: State, img: Tensor, p: str = "feature") -> Dict[str, Tenso
     def up(t):
         return F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)
 
+    def w(name):
+        return _q(sd[p + name])
+
     out = {}
     top = c3
-    out["stage1"] = F.conv2d(top, sd[p + ".out1.weight"])
-    top = up(top) + F.conv2d(c2, sd[p + ".inner1.weight"], sd[p + ".inner1.bias"])
-    out["stage2"] = F.conv2d(top, sd[p + ".out2.weight"], None, 1, 1)
-    top = up(top) + F.conv2d(c1, sd[p + ".inner2.weight"], sd[p + ".inner2.bias"])
-    out["stage3"] = F.conv2d(top, sd[p + ".out3.weight"], None, 1, 1)
-    top = up(top) + F.conv2d(c0, sd[p + ".inner3.weight"], sd[p + ".inner3.bias"])
-    out["stage4"] = F.conv2d(top, sd[p + ".out4.weight"], None, 1, 1)
+    out["stage1"] = _q(F.conv2d(_q(top), w(".out1.weight")))
+    top = up(top) + F.conv2d(_q(c2), w(".inner1.weight"), sd[p + ".inner1.bias"])
+    out["stage2"] = _q(F.conv2d(_q(top), w(".out2.weight"), None, 1, 1))
+    top = up(top) + F.conv2d(_q(c1), w(".inner2.weight"), sd[p + ".inner2.bias"])
+    out["stage3"] = _q(F.conv2d(_q(top), w(".out3.weight"), None, 1, 1))
+    top = up(top) + F.conv2d(_q(c0), w(".inner3.weight"), sd[p + ".inner3.bias"])
+    out["stage4"] = _q(F.conv2d(_q(top), w(".out4.weight"), None, 1, 1))
     return out
 
 
@@ -239,7 +270,7 @@ def reg2d_logits(sd: State, p: str, cost: Tensor) -> Tensor:
     x = c4 + _up3(x, sd, p + ".conv7", s2, p2, p2)
     x = c2 + _up3(x, sd, p + ".conv9", s2, p2, p2)
     x = c0 + _up3(x, sd, p + ".conv11", s2, p2, p2)
-    return F.conv3d(x, sd[p + ".prob.weight"], sd[p + ".prob.bias"]).squeeze(1)
+    return F.conv3d(_q(x), _q(sd[p + ".prob.weight"]), sd[p + ".prob.bias"]).squeeze(1)
 
 
 def reg3d_logits(sd: State, p: str, cost: Tensor, down_size: int) -> Tensor:
@@ -256,7 +287,7 @@ def reg3d_logits(sd: State, p: str, cost: Tensor, down_size: int) -> Tensor:
             x = c4 + _up3(x, sd, p + ".conv7", s2, one, one)
         x = c2 + _up3(x, sd, p + ".conv9", s2, one, one)
     x = c0 + _up3(x, sd, p + ".conv11", s2, one, one)
-    return F.conv3d(x, sd[p + ".prob.weight"], None, 1, 1).squeeze(1)
+    return F.conv3d(_q(x), _q(sd[p + ".prob.weight"]), None, 1, 1).squeeze(1)
 
 
 # --------------------------------------------------------------------------
@@ -303,7 +334,7 @@ REG3D_DOWN = [3, 3, 2, 2]  # MVS4Net.py:48
 def stage_forward(sd: State, cfg: dict, k: int, feats: List[Tensor], cams: Tensor, hypo: Tensor) -> Dict[str, Tensor]:
     """stagenet.forward for stage index k (0-based), mvs4net_utils.py:1012-1094 (eval mode)."""
     G = cfg["group_cor_dim"][k]
-    cost = et_aggregate(feats, cams, hypo, cfg["group_cor"], G, cfg["attn_temp"], cfg.get("attn_fuse_d", True))
+    cost = _q(et_aggregate(feats, cams, hypo, cfg["group_cor"], G, cfg["attn_temp"], cfg.get("attn_fuse_d", True)))
     if cfg["reg_net"] == "reg2d":
         logits = reg2d_logits(sd, f"reg.{k}", cost)
     else:
@@ -317,9 +348,10 @@ def stage_forward(sd: State, cfg: dict, k: int, feats: List[Tensor], cams: Tenso
 
 
 def cascade_forward(sd: State, cfg: dict, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor],
-                    depth_values: Tensor, features: Optional[List[Dict[str, Tensor]]] = None) -> Dict:
-    """MVS4net.forward in eval mode, MVS4Net.py:60-111."""
-    with torch.no_grad():
+                    depth_values: Tensor, features: Optional[List[Dict[str, Tensor]]] = None, storage_dtype=None) -> Dict:
+    """MVS4net.forward in eval mode, MVS4Net.py:60-111.  ``storage_dtype=torch.bfloat16`` evaluates the bf16-storage
+    configuration (see ``storage`` above); None is the reference's fp32."""
+    with torch.no_grad(), storage(storage_dtype):
         if features is None:
             features = [fpn4_features(sd, im) for im in imgs]
         outputs: Dict = {}
