@@ -270,7 +270,8 @@ def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
 
 
 # ----------------------------------------------------------------------------- the whole forward
-def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch):
+@pytest.mark.parametrize("name", ["shipped_b1_v3_64x128", "reg3d_b1_v2_64x64", "plain_b1_v2_64x64"])
+def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch, name):
     """InferenceEngine.forward - native feature pyramid, four cascade stages, every convolution on the exact-fp32 CUDA-core
     kernels - executed on the emulation library with CPU tensors, against the outputs of the unmodified reference
     (tests/golden/shipped_b1_v3_64x128.npz): the same tie-aware, drift-aware criterion as the GPU test, and here every pixel
@@ -279,7 +280,6 @@ def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch):
     from util import GOLDEN_CASES, load_golden, top2_gap
     from mvster_b200.engine import InferenceEngine
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
-    name = "shipped_b1_v3_64x128"
     z, imgs, proj, dv = load_golden(name)
     m = build_model(GOLDEN_CASES[name], int(z["meta_seed"]))
     m.reg_precision = m.fpn_precision = "fp32"
@@ -292,11 +292,12 @@ def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch):
     for s_ in range(1, 5):
         st = out[f"stage{s_}"]
         for key in ("depth", "photometric_confidence", "hypo_depth", "attn_weight", "inverse_min_depth", "inverse_max_depth"):
-            assert tuple(st[key].shape) == tuple(z[f"s{s_}_{key}"].shape), (s_, key)
+            if f"s{s_}_{key}" in z.files:  # the inverse-range outputs exist only with inverse_depth
+                assert tuple(st[key].shape) == tuple(z[f"s{s_}_{key}"].shape), (s_, key)
         ref_attn, ref_depth = torch.from_numpy(z[f"s{s_}_attn_weight"]), torch.from_numpy(z[f"s{s_}_depth"])
         if s_ > 1:
             drift_free = F.interpolate(drift_free.float()[:, None], scale_factor=2, mode="bilinear", align_corners=True)[:, 0] > 0.999
-        agree = (st["depth"] - ref_depth).abs() <= 1e-4 * ref_depth
+        agree = (st["depth"] - ref_depth).abs() <= 1e-4 * ref_depth.abs()  # linear sampling can go negative
         stable = top2_gap(ref_attn) > 1e-3
         bad = ((~agree) & stable & drift_free).float().sum().item() / max(1.0, (stable & drift_free).float().sum().item())
         assert bad < 5e-3, f"stage {s_}: {bad:.3%} of tie-free, drift-free pixels differ by > 1e-4 relative"
@@ -305,5 +306,5 @@ def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch):
         drift_free = drift_free & agree
     assert out["depth"].data_ptr() == out["stage4"]["depth"].data_ptr()
     conf = torch.from_numpy(z["s4_photometric_confidence"])
-    assert (out["photometric_confidence"] - conf).abs()[drift_free].max().item() < 1e-4
+    assert (out["photometric_confidence"] - conf).abs()[drift_free].max().item() < 1e-3  # max probability of the last stage, after four stages of fp32 noise
 
