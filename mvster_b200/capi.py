@@ -13,8 +13,14 @@ from . import _lib
 
 Tensor = torch.Tensor
 
+# flags of mvster_et_fuse_f32 (include/mvster_b200.h)
 ET_PARTIAL = 1
 ET_ACCUMULATE = 2
+ET_GENERIC = 4
+ET_NO_FUSE_D = 8
+ET_SQDIFF = 16
+ET_WINDOW = 32
+ET_NO_WINDOW = 64
 MAX_VIEWS = 16
 
 
@@ -111,13 +117,13 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
     for v0 in range(0, V, MAX_VIEWS):  # more than MAX_VIEWS views: chain launches through the partials
         chunk = srcs[v0:v0 + MAX_VIEWS]
         last = v0 + MAX_VIEWS >= V
-        flags = 4 if generic else 0  # MVSTER_ET_GENERIC
+        flags = ET_GENERIC if generic else 0
         if not fuse_d:
-            flags |= 8                # MVSTER_ET_NO_FUSE_D
+            flags |= ET_NO_FUSE_D
         if not group_cor:
-            flags |= 16               # MVSTER_ET_SQDIFF
+            flags |= ET_SQDIFF
         if window is not None:
-            flags |= 32 if window else 64  # MVSTER_ET_WINDOW / MVSTER_ET_NO_WINDOW
+            flags |= ET_WINDOW if window else ET_NO_WINDOW
         if partial or not last:
             flags |= ET_PARTIAL
         if accumulate or v0 > 0:

@@ -227,3 +227,13 @@ def test_fp16_arithmetic_falls_back_when_weights_leave_its_range():
     fp = fpn_engine.pack_fpn({k: v for k, v in sd.items() if k.startswith("feature.")})
     assert packing.fp16_range_ok(v for k, v in fp.items() if k.endswith(".w"))
 
+
+def test_python_flag_constants_match_the_header():
+    import re
+    from mvster_b200 import capi
+    header = (REPO / "include" / "mvster_b200.h").read_text()
+    for name in ("PARTIAL", "ACCUMULATE", "GENERIC", "NO_FUSE_D", "SQDIFF", "WINDOW", "NO_WINDOW"):
+        assert getattr(capi, "ET_" + name) == int(re.search(rf"#define MVSTER_ET_{name} (\d+)", header).group(1)), name
+    assert capi.TC3_FP16X2 == int(re.search(r"#define MVSTER_TC3_FP16X2 (\d+)", header).group(1))
+    assert capi.MAX_VIEWS == int(re.search(r"#define MVSTER_MAX_VIEWS (\d+)", header).group(1))
+
