@@ -181,3 +181,53 @@ def load_eval_sample(datapath: str, scan: str, ref_view: int, src_views: Sequenc
             dv = depth_values(depth_min, depth_interval, ndepths)
     return {"imgs": imgs, "proj_matrices": stage_projections(ext, intr), "depth_values": dv,
             "filename": scan + "/{}/" + "{:0>8}".format(view_ids[0]) + "{}"}
+
+
+def save_ply(filename: str, xyz: np.ndarray, rgb: np.ndarray = None) -> None:
+    """Point cloud as the reference's ``filter_depth`` writes it through ``plyfile`` (``test_mvs4.py:402-414``): one ``vertex``
+    element with float32 ``x y z`` and, with colours, uint8 ``red green blue``; binary, native (little-endian) byte order."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    fields = [("x", "<f4"), ("y", "<f4"), ("z", "<f4")]
+    if rgb is not None:
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+        if len(rgb) != len(xyz):
+            raise ValueError(f"{len(xyz)} points but {len(rgb)} colours")
+        fields += [("red", "u1"), ("green", "u1"), ("blue", "u1")]
+    rec = np.empty(len(xyz), dtype=fields)
+    rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    if rgb is not None:
+        rec["red"], rec["green"], rec["blue"] = rgb[:, 0], rgb[:, 1], rgb[:, 2]
+    names = {"<f4": "float", "u1": "uchar"}
+    header = "ply\nformat binary_little_endian 1.0\nelement vertex %d\n" % len(xyz)
+    header += "".join("property %s %s\n" % (names[t], n) for n, t in fields) + "end_header\n"
+    with open(filename, "wb") as f:
+        f.write(header.encode("ascii"))
+        f.write(rec.tobytes())
+
+
+def read_ply(filename: str):
+    """Reads back what ``save_ply`` (or plyfile, for the same vertex layout) wrote: (xyz [N,3] float32, rgb [N,3] uint8 or None)."""
+    with open(filename, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise Exception("Not a PLY file.")
+        fmt, n, props = None, 0, []
+        while True:
+            line = f.readline().decode("ascii").strip()
+            if line == "end_header":
+                break
+            tok = line.split()
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                if tok[1] != "vertex":
+                    raise Exception("only a single vertex element is supported")
+                n = int(tok[2])
+            elif tok[0] == "property":
+                props.append((tok[2], {"float": "f4", "float32": "f4", "uchar": "u1", "uint8": "u1"}[tok[1]]))
+        if fmt not in ("binary_little_endian", "binary_big_endian"):
+            raise Exception(f"unsupported PLY format {fmt}")
+        order = "<" if fmt == "binary_little_endian" else ">"
+        rec = np.frombuffer(f.read(), dtype=[(nm, order + t if t != "u1" else t) for nm, t in props], count=n)
+    xyz = np.stack([rec["x"], rec["y"], rec["z"]], 1).astype(np.float32)
+    rgb = np.stack([rec["red"], rec["green"], rec["blue"]], 1) if "red" in rec.dtype.names else None
+    return xyz, rgb

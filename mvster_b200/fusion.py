@@ -111,3 +111,29 @@ def fuse_reference_view(ref_depth: Array, ref_intrinsics, ref_extrinsics, confid
     geo = count >= thres_view
     res = {"photo_mask": photo, "geo_mask": geo, "final_mask": photo & geo, "geo_mask_sum": count, "depth_est_averaged": averaged}
     return {k: v.cpu().numpy() for k, v in res.items()} if as_numpy else res
+
+
+def backproject_points(depth: Array, mask: Array, intrinsics, extrinsics, image: Array = None):
+    """World-space points of the pixels selected by ``mask`` (``test_mvs4.py:384-399`` of ``filter_depth``): pixel (x, y) with depth
+    d -> ``inv(K) [x, y, 1] d`` in the camera frame -> ``inv(E)`` to the world.  Arithmetic as in the reference (float64 products
+    with float32 matrix inverses).  Returns (xyz [N,3] float32, rgb [N,3] uint8 or None); works on numpy arrays or tensors of any
+    device and returns the same kind."""
+    as_numpy = not isinstance(depth, Tensor)
+    d = torch.as_tensor(np.asarray(depth)) if as_numpy else depth
+    m = torch.as_tensor(np.asarray(mask)).to(d.device) if not isinstance(mask, Tensor) else mask.to(d.device)
+    H, W = d.shape
+    k_inv = torch.from_numpy(np.linalg.inv(_np32(intrinsics)[:3, :3]).astype(np.float64)).to(d.device)
+    e_inv = torch.from_numpy(np.linalg.inv(_np32(extrinsics)).astype(np.float64)).to(d.device)
+    ys, xs = torch.nonzero(m.bool(), as_tuple=True)          # row-major order = the reference's boolean indexing
+    dv = d[ys, xs].to(torch.float64)
+    pix = torch.stack((xs.to(torch.float64) * dv, ys.to(torch.float64) * dv, dv))      # [3,N]
+    cam = k_inv @ pix
+    world = (e_inv @ torch.cat((cam, torch.ones_like(cam[:1]))))[:3]
+    xyz = world.t().to(torch.float32).contiguous()
+    rgb = None
+    if image is not None:
+        img = torch.as_tensor(np.asarray(image)).to(d.device) if not isinstance(image, Tensor) else image.to(d.device)
+        rgb = (img[ys, xs] * 255).to(torch.uint8)              # (color * 255).astype(np.uint8): truncation
+    if as_numpy:
+        return xyz.cpu().numpy(), (None if rgb is None else rgb.cpu().numpy())
+    return xyz, rgb

@@ -153,3 +153,29 @@ def test_eval_sample_matches_the_reference_dataset(tmp_path):
             assert a.shape == b.shape == (3, 128, 192) and a.dtype == np.float32 and np.array_equal(a, b)
         for s in ("stage1", "stage2", "stage3", "stage4"):
             assert np.array_equal(got["proj_matrices"][s], want["proj_matrices"][s]), s
+
+
+def test_backprojection_and_ply_round_trip(tmp_path):
+    """fusion.backproject_points against the formulas of test_mvs4.py:384-399 written out in numpy, and the PLY writer / reader."""
+    from mvster_b200 import fusion
+    from oracle import fusion_oracle
+    v = fusion_oracle.synthetic_scene(2, 24, 32, seed=2)[1]
+    rng = np.random.RandomState(5)
+    mask = rng.rand(24, 32) > 0.6
+    img = rng.rand(24, 32, 3).astype(np.float32)
+    xyz, rgb = fusion.backproject_points(v["depth"], mask, v["K"], v["E"], img)
+    x, y = np.meshgrid(np.arange(32), np.arange(24))
+    x, y, depth = x[mask], y[mask], v["depth"][mask]
+    xyz_ref = np.matmul(np.linalg.inv(v["K"]), np.vstack((x, y, np.ones_like(x))) * depth)
+    want = np.matmul(np.linalg.inv(v["E"]), np.vstack((xyz_ref, np.ones_like(x))))[:3].transpose((1, 0))
+    assert xyz.dtype == np.float32 and xyz.shape == (int(mask.sum()), 3)
+    assert np.abs(xyz - want.astype(np.float32)).max() <= 1e-4 * np.abs(want).max()
+    assert np.array_equal(rgb, (img[mask] * 255).astype(np.uint8))
+    formats.save_ply(str(tmp_path / "a.ply"), xyz, rgb)
+    head = (tmp_path / "a.ply").read_bytes()[:200].decode("ascii", "ignore")
+    assert head.startswith("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\n" % len(xyz)) and "property uchar blue" in head
+    xyz2, rgb2 = formats.read_ply(str(tmp_path / "a.ply"))
+    assert np.array_equal(xyz2, xyz) and np.array_equal(rgb2, rgb)
+    formats.save_ply(str(tmp_path / "b.ply"), xyz)
+    xyz3, rgb3 = formats.read_ply(str(tmp_path / "b.ply"))
+    assert np.array_equal(xyz3, xyz) and rgb3 is None
