@@ -97,31 +97,38 @@ inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 inline float __expf(float a) { return std::exp(a); }
 
 namespace emu {
-// run kernel(args...) over the grid: blocks sequentially, the threads of a block concurrently (block.x must be a multiple of 32)
+// run kernel(args...) over the grid: blocks sequentially, the threads of a block concurrently (block size a multiple of 32).
+// The OS threads are created once per launch and walk the blocks together; the per-block barrier objects are fresh for every
+// block because a thread that leaves the kernel early drops out of them.
 template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
     const int nthreads = (int)(block.x * block.y * block.z), nwarps = nthreads / 32;
+    const long long nblocks = (long long)grid.x * grid.y * grid.z;
     std::vector<unsigned char> smem_store(smem_bytes + 128);
     unsigned char* smem = smem_store.data() + (128 - (reinterpret_cast<uintptr_t>(smem_store.data()) & 127)) % 128;
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                std::barrier<> block_bar(nthreads);
-                std::vector<std::unique_ptr<Warp>> warps;
-                for (int w = 0; w < nwarps; ++w) warps.emplace_back(new Warp(32));
-                std::vector<std::thread> th;
-                th.reserve(nthreads);
-                for (int t = 0; t < nthreads; ++t)
-                    th.emplace_back([&, t] {
-                        threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
-                        blockIdx = {bx, by, bz};
-                        blockDim = block; gridDim = grid;
-                        ctx = {warps[t / 32].get(), &block_bar, t % 32, smem};
-                        body();
-                        block_bar.arrive_and_drop();        // a thread that has left the kernel no longer takes part in barriers
-                        warps[t / 32]->bar.arrive_and_drop();
-                    });
-                for (auto& x : th) x.join();
+    std::barrier<> start_bar(nthreads), end_bar(nthreads);
+    std::unique_ptr<std::barrier<>> block_bar;
+    std::vector<std::unique_ptr<Warp>> warps(nwarps);
+    auto worker = [&](int t) {
+        for (long long b = 0; b < nblocks; ++b) {
+            if (t == 0) {
+                block_bar.reset(new std::barrier<>(nthreads));
+                for (int w = 0; w < nwarps; ++w) warps[w].reset(new Warp(32));
             }
+            start_bar.arrive_and_wait();
+            threadIdx = {(unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / (block.x * block.y))};
+            blockIdx = {(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y))};
+            blockDim = block; gridDim = grid;
+            ctx = {warps[t / 32].get(), block_bar.get(), t % 32, smem};
+            body();
+            block_bar->arrive_and_drop();          // a thread that has left the kernel no longer takes part in its barriers
+            warps[t / 32]->bar.arrive_and_drop();
+            end_bar.arrive_and_wait();             // nobody still uses this block's barrier objects
+        }
+    };
+    std::vector<std::thread> th;
+    th.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+    for (auto& x : th) x.join();
 }
 }  // namespace emu
