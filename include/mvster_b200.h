@@ -102,6 +102,20 @@ int mvster_et_fuse_f32(const float* ref, const float* const* src_host, int V, co
 int mvster_et_normalize_f32(float* cost, const float* wsum, int B, int G, int D, int H, int W,
                             mvster_stream_t stream);
 
+/* Backward of mvster_et_fuse_f32 (group correlation, attn_fuse_d) for training: what autograd derives through
+ * mvs4net_utils.py:1037-1060 and homo_warping :13-59.  The sampling grid is built under torch.no_grad() (:23) and the
+ * hypotheses are detached (MVS4Net.py:95), so only the features receive gradients.  Inputs: the forward's operands,
+ * its normalised output `cost` [B][D][H][W][G], `wsum` [B][D][H][W] = the sum over views of the weights WITHOUT the 1e-8
+ * seed (what the forward writes with MVSTER_ET_PARTIAL, before mvster_et_normalize_f32), grad_cost [B][D][H][W][G].
+ * Outputs: grad_ref [B][H][W][C] (overwritten); grad_src_host[v] [B][Hs][Ws][C] (HOST array of V device pointers, each
+ * accumulated into with atomics - zero it first - or NULL when that view needs no gradient).  Nothing but cost and wsum
+ * is saved between the passes: taps are gathered again and the per-view softmax is recomputed. */
+int mvster_et_fuse_bwd_f32(const float* ref, const float* const* src_host, int V, const float* pose,
+                           const float* hypo, const float* cost, const float* wsum, const float* grad_cost,
+                           float* grad_ref, float* const* grad_src_host,
+                           int B, int C, int G, int D, int H, int W, int Hs, int Ws,
+                           float attn_temp, mvster_stream_t stream);
+
 /* ---- regularisation ------------------------------------------------------ */
 /* Generic channels-last 3-D convolution layer with folded BN:
  *   y = [relu](conv(x, w) + bias) [+ skip]

@@ -148,6 +148,40 @@ def et_normalize(cost: Tensor, wsum: Tensor) -> Tensor:
     return cost
 
 
+def et_fuse_bwd(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, cost: Tensor, wsum: Tensor,
+                grad_cost: Tensor, attn_temp: float, need_src: Optional[Sequence[bool]] = None):
+    """Gradients of ``et_fuse`` (group correlation, attn_fuse_d) w.r.t. the features: ref [B,H,W,C], srcs V x [B,Hs,Ws,C],
+    pose [B,V,12], hypo [B,D,H,W], cost / grad_cost [B,D,H,W,G], wsum [B,D,H,W] (the partial sums, no 1e-8 seed) ->
+    (grad_ref [B,H,W,C], [grad_src_v [B,Hs,Ws,C] or None]).  ``need_src[v]`` False skips that view's scatter."""
+    B, H, W, Cc = ref.shape
+    _chk(ref, "ref")
+    V = len(srcs)
+    D, G = hypo.shape[1], cost.shape[-1]
+    _chk(hypo, "hypo", (B, D, H, W))
+    _chk(cost, "cost", (B, D, H, W, G))
+    _chk(grad_cost, "grad_cost", (B, D, H, W, G))
+    _chk(wsum, "wsum", (B, D, H, W))
+    Hs, Ws = srcs[0].shape[1:3]
+    for i, s in enumerate(srcs):
+        _chk(s, f"src[{i}]", (B, Hs, Ws, Cc))
+    need = [True] * V if need_src is None else list(need_src)
+    grad_src = [torch.zeros_like(s) if n else None for s, n in zip(srcs, need)]
+    grad_ref = torch.zeros_like(ref)
+    lib = _lib.load()
+    for v0 in range(0, V, MAX_VIEWS):  # the gradient is a sum over views: chunks of MAX_VIEWS add up
+        chunk = srcs[v0:v0 + MAX_VIEWS]
+        pose_c = _chk(pose[:, v0:v0 + len(chunk)].contiguous(), "pose", (B, len(chunk), 12))
+        arr = (C.c_void_p * len(chunk))(*[s.data_ptr() for s in chunk])
+        garr = (C.c_void_p * len(chunk))(*[None if g is None else g.data_ptr() for g in grad_src[v0:v0 + len(chunk)]])
+        part = grad_ref if v0 == 0 else torch.empty_like(ref)
+        _lib.check(lib.mvster_et_fuse_bwd_f32(_ptr(ref), arr, len(chunk), _ptr(pose_c), _ptr(hypo), _ptr(cost), _ptr(wsum),
+                                              _ptr(grad_cost), _ptr(part), garr, B, Cc, G, D, H, W, Hs, Ws,
+                                              float(attn_temp), _stream()), "mvster_et_fuse_bwd_f32")
+        if v0:
+            grad_ref += part
+    return grad_ref, grad_src
+
+
 def conv3d_ndhwc(x: Tensor, w: Tensor, bias: Optional[Tensor], kd: int, stride_d: int = 1, stride_hw: int = 1,
                  transposed: bool = False, relu: bool = True, skip: Optional[Tensor] = None) -> Tensor:
     """x [B,D,H,W,Cin], w [kd*9,Cin,Cout] -> y [B,Do,Ho,Wo,Cout]."""

@@ -7,7 +7,9 @@ proj_matrices, depth_values, filename=None) -> dict`` contract, same output keys
 Dispatch in ``forward``:
   * eval mode under ``torch.no_grad()`` on CUDA tensors  -> the sm_100a library through
     the C ABI (engine.py).  This is the product path; it raises if the library is missing.
-  * training / grad enabled -> differentiable PyTorch ops (torch_path.py), any device.
+  * training / grad enabled -> differentiable PyTorch ops (torch_path.py), any device; with ``MVSTER_TRAIN_ET=1`` (or
+    ``model.stagenet.train_et = True``) the warp + ET aggregation of CUDA features runs on the fused kernel and its
+    hand-written backward (train_ops.py, csrc/et_fuse_bwd.cu) instead of materialising the warped volumes.
   * eval + no_grad on CPU tensors -> error (no CPU fallback by design).
 """
 from __future__ import annotations
@@ -20,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import torch_path as tp
+from . import train_ops
 
 Tensor = torch.Tensor
 
@@ -189,12 +192,17 @@ class stagenet(nn.Module):
         super().__init__()
         self.inverse_depth, self.mono, self.attn_fuse_d = inverse_depth, mono, attn_fuse_d
         self.vis_ETA, self.attn_temp = vis_ETA, attn_temp
+        self.train_et = None  # True / False: aggregate CUDA features through the fused kernels + their backward; None: MVSTER_TRAIN_ET
 
     def forward(self, features, proj_matrices, depth_hypo, regnet, stage_idx, group_cor=False, group_cor_dim=8,
                 split_itv=1, fn=None):
         if self.vis_ETA:
             raise NotImplementedError("vis_ETA debug dumps are not part of this implementation")
-        cost = tp.aggregate(features, proj_matrices, depth_hypo, group_cor, group_cor_dim, self.attn_temp, self.attn_fuse_d)
+        kernels = train_ops.enabled_by_default() if self.train_et is None else self.train_et
+        if kernels and train_ops.usable(features) and group_cor and self.attn_fuse_d:
+            cost = train_ops.aggregate(features, proj_matrices, depth_hypo, group_cor_dim, self.attn_temp)
+        else:
+            cost = tp.aggregate(features, proj_matrices, depth_hypo, group_cor, group_cor_dim, self.attn_temp, self.attn_fuse_d)
         out = tp.head(regnet(cost), depth_hypo, stage_idx, split_itv, self.inverse_depth, self.training)
         if self.mono:
             out["mono_feat"] = features[0]

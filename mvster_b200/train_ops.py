@@ -1,0 +1,67 @@
+"""Training-side use of the fused warp + epipolar-Transformer kernels: an autograd node whose forward is
+``mvster_et_fuse_f32`` and whose backward is ``mvster_et_fuse_bwd_f32`` (csrc/et_fuse_bwd.cu).
+
+The reference differentiates ``stagenet.forward`` (mvs4net_utils.py:1015-1062) through PyTorch ops and therefore keeps, for
+every source view of every stage, the warped volume [B,C,D,H,W], the correlation and the weights alive until the backward
+pass (at 5 views 512x640 about 1.2 GB per stage-4 view).  Here the node saves the channels-last features it was given plus
+the cost volume and the weight sum; the backward kernel gathers the taps again.  Gradients reach the features only: the
+sampling grid is built under ``torch.no_grad()`` (:23) and the hypotheses are detached (MVS4Net.py:95).
+
+There is no CPU implementation: without the CUDA library the calls raise (``_lib.load``).
+"""
+from __future__ import annotations
+
+import os
+from typing import Sequence
+
+import torch
+from torch import Tensor
+
+from . import capi
+
+
+def enabled_by_default() -> bool:
+    """MVSTER_TRAIN_ET=1 routes the training-mode aggregation of CUDA tensors through the kernels (default: PyTorch ops)."""
+    return os.environ.get("MVSTER_TRAIN_ET", "0") == "1"
+
+
+def usable(features: Sequence[Tensor]) -> bool:
+    """The kernels take fp32 CUDA feature maps; anything else stays on the PyTorch formulation."""
+    return all(f.is_cuda and f.dtype == torch.float32 for f in features)
+
+
+class EtFuse(torch.autograd.Function):
+    """cost [B,D,H,W,G] = ET aggregation of channels-last features; see ``capi.et_fuse`` / ``capi.et_fuse_bwd``."""
+
+    @staticmethod
+    def forward(ctx, pose: Tensor, hypo: Tensor, G: int, attn_temp: float, ref: Tensor, *srcs: Tensor) -> Tensor:
+        B, H, W, _ = ref.shape
+        D = hypo.shape[1]
+        wsum = torch.empty((B, D, H, W), device=ref.device, dtype=torch.float32)
+        cost = capi.et_fuse(ref, srcs, pose, hypo, G, attn_temp, wsum=wsum, partial=True)
+        capi.et_normalize(cost, wsum)
+        ctx.save_for_backward(pose, hypo, cost, wsum, ref, *srcs)
+        ctx.attn_temp = attn_temp
+        return cost
+
+    @staticmethod
+    def backward(ctx, grad_cost: Tensor):
+        pose, hypo, cost, wsum, ref, *srcs = ctx.saved_tensors
+        need = ctx.needs_input_grad[4:]
+        if not any(need):
+            return (None,) * (4 + 1 + len(srcs))
+        grad_ref, grad_src = capi.et_fuse_bwd(ref, srcs, pose, hypo, cost, wsum, grad_cost.contiguous(), ctx.attn_temp,
+                                              need_src=need[1:])
+        return (None, None, None, None, grad_ref if need[0] else None, *grad_src)
+
+
+def aggregate(features: Sequence[Tensor], cams: Tensor, hypo: Tensor, G: int, attn_temp: float) -> Tensor:
+    """Differentiable drop-in for ``torch_path.aggregate(..., group_cor=True, attn_fuse_d=True)``: features Nv x [B,C,H,W]
+    (view 0 = reference), cams [B,Nv,2,4,4], hypo [B,D,H,W] -> cost [B,G,D,H,W] (a permuted view of the kernel's
+    channels-last volume)."""
+    with torch.no_grad():
+        pose = capi.pose(cams.contiguous().float())
+        hypo = hypo.detach().contiguous().float()
+    nhwc = [f.permute(0, 2, 3, 1).contiguous() for f in features]
+    cost = EtFuse.apply(pose, hypo, int(G), float(attn_temp), *nhwc)
+    return cost.permute(0, 4, 1, 2, 3)

@@ -5,6 +5,7 @@
 // product path includes this header, and tcgen05 / TMA kernels are out of its reach.
 #pragma once
 #define MVSTER_CPU_EMU 1
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -95,6 +96,7 @@ inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c);
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 inline float __expf(float a) { return std::exp(a); }
+inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 
 namespace emu {
 // run kernel(args...) over the grid: blocks sequentially, the threads of a block concurrently (block size a multiple of 32).
