@@ -13,3 +13,6 @@ for sw in "" "MVSTER_TC3_MERGE=1" "MVSTER_FPN_GATHER=2" "MVSTER_FPN_MERGE=2" "MV
 import json,sys
 j=json.loads(sys.stdin.read()); print('%-70s %.4f ms  %.1f maps/s  e2e %.1f' % ('[$sw]', j['ms_per_step'], j['value'], j['e2e']['value']))"
 done
+echo "== training path: backward of the warp + ET kernel (parity first, then forward/backward time and held memory vs the PyTorch ops)"
+timeout 600 python -m pytest tests/test_gpu_zzz_et_backward.py tests/test_gpu_zz_fusion.py -m gpu -q 2>&1 | tail -3
+timeout 600 python tools/et_bwd_bench.py > gpurun_out/et_bwd_bench.json 2>gpurun_out/et_bwd_bench.err; tail -40 gpurun_out/et_bwd_bench.json
