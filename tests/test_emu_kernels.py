@@ -402,3 +402,19 @@ def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch, na
     conf = torch.from_numpy(z["s4_photometric_confidence"])
     assert (out["photometric_confidence"] - conf).abs()[drift_free].max().item() < 1e-3  # max probability of the last stage, after four stages of fp32 noise
 
+
+
+def test_scan_to_point_cloud_on_cpu(emu, monkeypatch, tmp_path):
+    """The evaluation flow around the forward (tests/flow_util.py): scan directory -> prefetcher -> engine -> PFM -> filter ->
+    PLY, with the kernels on the emulation library."""
+    import contextlib
+    from flow_util import scan_to_point_cloud
+    from mvster_b200.engine import InferenceEngine
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    m = build_model(SHIPPED, seed=2)
+    m.reg_precision = m.fpn_precision = "fp32"
+    m.overlap_stages, m.fpn_backend = False, "native"
+    eng = InferenceEngine(torch.device("cpu"))
+    eng.refresh_weights(m)
+    with torch.no_grad():
+        scan_to_point_cloud(tmp_path, lambda s: eng.forward(m, s["imgs"], s["proj_matrices"], s["depth_values"]), "cpu")
