@@ -236,6 +236,16 @@ def test_training_step_with_kernels_on_cpu_matches_pytorch_ops(emu, monkeypatch)
     assert worst < 5e-2, worst                                      # measured on the CPU emulation: 7.6e-3
 
 
+def test_warp_edge_cases_of_the_reference_through_the_kernels_on_cpu(emu):
+    from util import warp_edge_through_et
+    outs, want = warp_edge_through_et(capi)
+    assert (want == 0).float().mean() > 0.2
+    for got in outs:
+        assert torch.isfinite(got).all()
+        assert (got - want).abs().max().item() <= 2e-6 * want.abs().max().item()
+        assert ((got == 0) == (want == 0)).float().mean() > 0.999             # the zero padding is reproduced tap for tap
+
+
 def test_et_variants_sqdiff_no_fuse_d_partial_on_cpu(emu):
     feats, cams, hypo = et_inputs(1, 3, 8, 8, 4, 4, 8, 2.0, seed=2)
     ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)

@@ -86,3 +86,15 @@ def test_training_step_with_kernels_matches_pytorch_ops():
     worst = max(((grads[True][n] - grads[False][n]).abs().max() / grads[False][n].abs().max()).item()
                 for n in grads[True] if grads[False][n].abs().max().item() > 1e-5 * top)
     assert worst < 5e-2, worst                                      # measured on the CPU emulation: 7.6e-3
+
+
+def test_warp_edge_cases_of_the_reference_through_the_kernels():
+    """Forward kernels on the reference's own homo_warping edge-case fixture (out of bounds on every side, z == 0, source size
+    != reference size); see util.warp_edge_through_et.  The CPU emulation of the same sources agrees to 2e-6 of max."""
+    from util import warp_edge_through_et
+    from mvster_b200 import capi
+    outs, want = warp_edge_through_et(capi, DEV)
+    for got in outs:
+        assert torch.isfinite(got).all()
+        assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+        assert ((got == 0) == (want == 0)).float().mean() > 0.999

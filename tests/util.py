@@ -69,3 +69,27 @@ def narrow_et_inputs(B, nv, C, D, H, W, step_deg, rel_span, seed=0):
     lin = np.linspace(0.5, -0.5, D).reshape(1, D, 1, 1)
     hypo = torch.from_numpy((centre * (1.0 + rel_span * lin)).astype(np.float32))
     return feats, cams, hypo
+
+
+def warp_edge_through_et(capi, device="cpu"):
+    """The reference's own ``homo_warping`` outputs on its edge-case fixture (tests/golden/warp_edge.npz: samples out of bounds on
+    every side, a hypothesis with z exactly 0, source size != reference size) recovered THROUGH the fused warp + ET kernel: with one
+    source view, C = G = 4 (one channel per group), an all-ones reference feature and a huge softmax temperature the cost volume
+    is a / (1e-8 + a) * warped with a = 1/(4 * sqrt(4)), i.e. the warped volume to 8e-8 relative.  D = 3 in the fixture; the last
+    hypothesis is duplicated to reach D = 4.  Returns (got [B,C,3,Hr,Wr], want)."""
+    import numpy as np
+    z = np.load(GOLDEN / "warp_edge.npz")
+    src, hypo = torch.from_numpy(z["src"]), torch.from_numpy(z["hypo"])
+    assert np.array_equal(z["ref_proj"], np.broadcast_to(np.eye(4, dtype=np.float32), z["ref_proj"].shape))
+    P = torch.from_numpy(z["src_proj"])                                  # ref_proj = I  =>  src_proj @ inv(ref_proj) = src_proj
+    pose = torch.cat([P[:, :3, :3].reshape(-1, 9), P[:, :3, 3]], 1)[:, None].contiguous()
+    B, C, Hs, Ws = src.shape
+    _, D, Hr, Wr = hypo.shape
+    hypo4 = torch.cat([hypo, hypo[:, -1:]], 1).contiguous()
+    ref = torch.ones(B, Hr, Wr, C)
+    outs = []
+    for kw in (dict(generic=True), dict(window=False), dict(window=True)):
+        cost = capi.et_fuse(ref.to(device), [src.permute(0, 2, 3, 1).contiguous().to(device)], pose.to(device), hypo4.to(device),
+                            C, 1e6, **kw)                               # [B,4,Hr,Wr,C]
+        outs.append(cost.permute(0, 4, 1, 2, 3)[:, :, :D].cpu())
+    return outs, torch.from_numpy(z["warped"])
