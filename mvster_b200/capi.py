@@ -116,7 +116,6 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
     lib = _lib.load()
     for v0 in range(0, V, MAX_VIEWS):  # more than MAX_VIEWS views: chain launches through the partials
         chunk = srcs[v0:v0 + MAX_VIEWS]
-        last = v0 + MAX_VIEWS >= V
         flags = ET_GENERIC if generic else 0
         if not fuse_d:
             flags |= ET_NO_FUSE_D
@@ -124,7 +123,7 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
             flags |= ET_SQDIFF
         if window is not None:
             flags |= ET_WINDOW if window else ET_NO_WINDOW
-        if partial or not last:
+        if partial or V > MAX_VIEWS:  # a chain stays un-normalised to its end: the division (with the 1e-8 seed) follows once
             flags |= ET_PARTIAL
         if accumulate or v0 > 0:
             flags |= ET_ACCUMULATE

@@ -246,6 +246,26 @@ def test_warp_edge_cases_of_the_reference_through_the_kernels_on_cpu(emu):
         assert ((got == 0) == (want == 0)).float().mean() > 0.999             # the zero padding is reproduced tap for tap
 
 
+def test_more_source_views_than_one_launch_takes_on_cpu(emu):
+    """19 source views > MVSTER_MAX_VIEWS = 16: the forward chains two launches through the partial sums, the backward adds the
+    reference-feature gradients of the two chunks; both against the oracle (fp64 autograd for the gradients)."""
+    from mvster_b200 import train_ops
+    assert capi.MAX_VIEWS == 16
+    feats, cams, hypo = et_inputs(1, 20, 8, 4, 4, 4, 8, 0.3, seed=17)
+    want = oracle.et_aggregate(feats, cams, hypo, True, 4, 2.0)
+    n0 = _lib.launch_count()
+    got = from_ndhwc(capi.et_fuse(nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams), hypo, 4, 2.0))
+    assert _lib.launch_count() - n0 == 4                                  # pose, two chained launches, normalise
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+    gout = torch.from_numpy(np.random.RandomState(1).randn(1, 4, 4, 4, 8).astype(np.float32))
+    f64 = [f.double().requires_grad_(True) for f in feats]
+    gwant = torch.autograd.grad(oracle.et_aggregate(f64, cams.double(), hypo.double(), True, 4, 2.0), f64, gout.double())
+    leaves = [f.clone().requires_grad_(True) for f in feats]
+    ggot = torch.autograd.grad(train_ops.aggregate(leaves, cams, hypo, 4, 2.0), leaves, gout)
+    for v in range(20):
+        assert (ggot[v] - gwant[v].float()).abs().max().item() <= 2e-4 * gwant[v].abs().max().item(), v
+
+
 def test_et_variants_sqdiff_no_fuse_d_partial_on_cpu(emu):
     feats, cams, hypo = et_inputs(1, 3, 8, 8, 4, 4, 8, 2.0, seed=2)
     ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)

@@ -98,3 +98,24 @@ def test_warp_edge_cases_of_the_reference_through_the_kernels():
         assert torch.isfinite(got).all()
         assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
         assert ((got == 0) == (want == 0)).float().mean() > 0.999
+
+
+def test_more_source_views_than_one_launch_takes():
+    """19 source views > MVSTER_MAX_VIEWS: chained forward launches and chunked backward against the oracle."""
+    from mvster_b200 import capi
+    rng = np.random.RandomState(17)
+    B, nv, C, G, D, H, W = 1, 20, 8, 4, 4, 16, 24
+    feats = [torch.from_numpy(rng.randn(B, C, H, W).astype(np.float32)) for _ in range(nv)]
+    cams = synth.stage_projections(synth.arc_cameras(nv, H, W, 0.3), B, num_stage=1)["stage1"]
+    hypo = oracle.hypo_init_inverse(torch.tensor([[425.0, 935.0]] * B), D, H, W)
+    want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0)
+    nhwc = [f.permute(0, 2, 3, 1).contiguous().to(DEV) for f in feats]
+    got = capi.et_fuse(nhwc[0], nhwc[1:], capi.pose(cams.to(DEV)), hypo.to(DEV), G, 2.0).permute(0, 4, 1, 2, 3).cpu()
+    assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+    gout = torch.from_numpy(rng.randn(B, G, D, H, W).astype(np.float32))
+    f64 = [f.double().requires_grad_(True) for f in feats]
+    gwant = torch.autograd.grad(oracle.et_aggregate(f64, cams.double(), hypo.double(), True, G, 2.0), f64, gout.double())
+    leaves = [f.to(DEV).requires_grad_(True) for f in feats]
+    ggot = torch.autograd.grad(train_ops.aggregate(leaves, cams.to(DEV), hypo.to(DEV), G, 2.0), leaves, gout.to(DEV))
+    for v in range(nv):
+        assert (ggot[v].cpu() - gwant[v].float()).abs().max().item() <= 2e-4 * gwant[v].abs().max().item(), v
