@@ -48,6 +48,26 @@ def check_supported(net) -> None:
         raise NotImplementedError("the CUDA inference path does not cover: " + ", ".join(bad))
 
 
+def check_inputs(net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor) -> None:
+    """Shape contract of ``MVS4net.forward`` (MVS4Net.py:60-77), checked before anything is launched; the reference
+    fails on the same inputs with ATen shape errors deep inside the U-Nets."""
+    if len(imgs) < 2:
+        raise ValueError(f"MVS4net.forward needs the reference view and at least one source view, got {len(imgs)} image tensor(s)")
+    shape = tuple(imgs[0].shape)
+    if len(shape) != 4 or shape[1] != 3 or any(tuple(i.shape) != shape for i in imgs):
+        raise ValueError(f"imgs must be Nv tensors of one shape [B,3,H,W], got {[tuple(i.shape) for i in imgs]}")
+    B, _, H, W = shape
+    if H % 64 or W % 64 or H == 0 or W == 0:
+        raise ValueError(f"H and W must be multiples of 64 (four pyramid levels, three stride-2 levels in the regulariser), got {H}x{W}")
+    for k in range(net.num_stage):
+        key = f"stage{k + 1}"
+        if key not in proj_matrices or tuple(proj_matrices[key].shape) != (B, len(imgs), 2, 4, 4):
+            got = tuple(proj_matrices[key].shape) if key in proj_matrices else None
+            raise ValueError(f"proj_matrices['{key}'] must be [B={B}, Nv={len(imgs)}, 2, 4, 4], got {got}")
+    if depth_values.dim() != 2 or depth_values.shape[0] != B or depth_values.shape[1] < 2:
+        raise ValueError(f"depth_values must be [B={B}, >= 2], got {tuple(depth_values.shape)}")
+
+
 class InferenceEngine:
     def __init__(self, device: torch.device):
         self.device = device
@@ -97,6 +117,7 @@ class InferenceEngine:
                 shard=None) -> Dict:
         """``shard`` (sharding.ViewShard) restricts this rank to the reference view plus its own
         slice of the source views: features are extracted only for those."""
+        check_inputs(net, imgs, proj_matrices, depth_values)
         B = imgs[0].shape[0]
         own = list(range(len(imgs))) if shard is None else [0] + shard.views
         with torch.cuda.device(self.device):

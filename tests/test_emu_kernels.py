@@ -266,6 +266,30 @@ def test_more_source_views_than_one_launch_takes_on_cpu(emu):
         assert (ggot[v] - gwant[v].float()).abs().max().item() <= 2e-4 * gwant[v].abs().max().item(), v
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_et_backward_on_extreme_geometry_on_cpu(emu, seed):
+    """The inputs of test_et_kernels_agree_on_extreme_geometry_on_cpu (most taps outside the source images, positions in the
+    thousands of pixels, near and far hypotheses): the backward kernel scatters only into valid taps and matches fp32 autograd
+    through the oracle (same operation order for the sampling positions, hence the same taps)."""
+    from mvster_b200 import train_ops
+    rng = np.random.RandomState(100 + seed)
+    B, nv, C_, G, D, H, W = 1, 3, 8, 4, 4, 8, 32
+    feats = [torch.from_numpy(rng.randn(B, C_, H, W).astype(np.float32)) for _ in range(nv)]
+    cams = synth.stage_projections(synth.arc_cameras(nv, H, W, [25.0, 8.0, 1.0][seed]), B, num_stage=1)["stage1"]
+    base = torch.from_numpy(np.exp(rng.uniform(np.log(5.0), np.log(5e4), (B, 1, H, W))).astype(np.float32))
+    hypo = (base * torch.tensor([1.0, 0.999, 0.5, 0.01]).reshape(1, D, 1, 1)).contiguous()
+    gout = torch.from_numpy(rng.randn(B, G, D, H, W).astype(np.float32))
+    ref_leaves = [f.clone().requires_grad_(True) for f in feats]
+    want = torch.autograd.grad(oracle.et_aggregate(ref_leaves, cams, hypo, True, G, 2.0), ref_leaves, gout)
+    leaves = [f.clone().requires_grad_(True) for f in feats]
+    got = torch.autograd.grad(train_ops.aggregate(leaves, cams, hypo, G, 2.0), leaves, gout)
+    for v in range(nv):
+        assert torch.isfinite(got[v]).all()
+        scale = max(want[v].abs().max().item(), 1e-6)
+        assert (got[v] - want[v]).abs().max().item() <= 1e-3 * scale, (v, (got[v] - want[v]).abs().max().item(), scale)
+        assert ((got[v] == 0) == (want[v] == 0)).float().mean().item() > 0.98     # untouched source pixels stay exactly zero
+
+
 def test_et_variants_sqdiff_no_fuse_d_partial_on_cpu(emu):
     feats, cams, hypo = et_inputs(1, 3, 8, 8, 4, 4, 8, 2.0, seed=2)
     ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)

@@ -237,3 +237,25 @@ def test_python_flag_constants_match_the_header():
     assert capi.TC3_FP16X2 == int(re.search(r"#define MVSTER_TC3_FP16X2 (\d+)", header).group(1))
     assert capi.MAX_VIEWS == int(re.search(r"#define MVSTER_MAX_VIEWS (\d+)", header).group(1))
 
+
+
+def test_engine_input_contract_is_checked_before_any_launch():
+    from mvster_b200 import engine, synth
+    m = build_model(SHIPPED, seed=1)
+    imgs, proj, dv = synth.make_inputs(2, 3, 64, 128, seed=0)
+    engine.check_inputs(m, imgs, proj, dv)                                           # the contract itself passes
+    engine.check_inputs(m, imgs, proj, torch.linspace(425, 935, 192).repeat(2, 1))   # the loaders' 192-entry list too
+    bad = [
+        (imgs[:1], proj, dv, "at least one source view"),
+        ([i[:, :, :60] for i in imgs], proj, dv, "multiples of 64"),
+        ([i[:, :, :, :96] for i in imgs], proj, dv, "multiples of 64"),
+        (imgs[:2] + [imgs[2][:, :, :, :64]], proj, dv, "one shape"),
+        ([i[:, :2] for i in imgs], proj, dv, "one shape"),
+        (imgs, {k: v[:, :2] for k, v in proj.items()}, dv, "proj_matrices['stage1']"),
+        (imgs, {k: v for k, v in proj.items() if k != "stage3"}, dv, "proj_matrices['stage3']"),
+        (imgs, proj, dv[:1], "depth_values"),
+        (imgs, proj, dv[:, :1], "depth_values"),
+    ]
+    for a, b, c, msg in bad:
+        with pytest.raises(ValueError, match=msg.replace("[", r"\[").replace("]", r"\]")):
+            engine.check_inputs(m, a, b, c)
