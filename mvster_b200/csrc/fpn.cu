@@ -116,6 +116,99 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
     dst[1] = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
 }
 
+// conv_first_kernel is instruction-bound (per pixel 216 FMA + 54 LDS.128 of weights + 27 loads ~ 330 instructions for
+// 44 bytes of traffic).  Variant: one thread = four consecutive pixels of a row.  A weight vector read from shared memory
+// serves four pixels, the three image rows arrive as 128-bit loads plus the two edge columns, and the FMAs are packed
+// two output channels per instruction (fma.rn.f32x2): ~135 instructions per pixel.  Same accumulation order per output
+// channel as conv_first_kernel (taps in ky, kx, c order; out-of-image taps contribute fma(0, w, acc) = acc), hence the
+// same bits.  Requires W % 4 == 0.  Opt-in (MVSTER_CONV_FIRST=2) until it has been timed.
+namespace cf4 {
+#ifdef MVSTER_CPU_EMU
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) { return emu::pack(lo, hi); }
+__device__ __forceinline__ float2 unpack2(unsigned long long v) { return emu::unpack(v); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    const float2 x = emu::unpack(a), y = emu::unpack(b), z = emu::unpack(c);
+    return emu::pack(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y));
+}
+#else
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+#endif
+}  // namespace cf4
+
+__global__ void __launch_bounds__(128) conv_first4_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ y, int N, int H, int W) {
+    using namespace cf4;
+    __shared__ __align__(16) float w_s[9 * 3 * 8 + 8];
+    for (int i = threadIdx.x; i < 216; i += blockDim.x) w_s[i] = __ldg(w + i);
+    if (threadIdx.x < 8) w_s[216 + threadIdx.x] = __ldg(bias + threadIdx.x);
+    __syncthreads();
+    const int W4 = W >> 2;
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;      // quad of pixels
+    if (q >= (long long)N * H * W4) return;
+    const int x0 = (int)(q % W4) * 4, yy = (int)((q / W4) % H), b = (int)(q / ((long long)W4 * H));
+    unsigned long long acc[4][4];                                             // [pixel][channel pair]
+    {
+        const float4 b0 = *reinterpret_cast<const float4*>(w_s + 216), b1 = *reinterpret_cast<const float4*>(w_s + 220);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            acc[p][0] = pack2(b0.x, b0.y); acc[p][1] = pack2(b0.z, b0.w);
+            acc[p][2] = pack2(b1.x, b1.y); acc[p][3] = pack2(b1.z, b1.w);
+        }
+    }
+    const float* base = img + (long long)b * 3 * H * W;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = yy + ky - 1;
+        if ((unsigned)iy >= (unsigned)H) continue;
+        float t[3][6];                                                        // [plane][x0-1 .. x0+4]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* row = base + ((long long)c * H + iy) * W + x0;
+            const float4 m = __ldg(reinterpret_cast<const float4*>(row));
+            t[c][0] = x0 > 0 ? __ldg(row - 1) : 0.f;
+            t[c][1] = m.x; t[c][2] = m.y; t[c][3] = m.z; t[c][4] = m.w;
+            t[c][5] = x0 + 4 < W ? __ldg(row + 4) : 0.f;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* wr = w_s + ((ky * 3 + kx) * 3 + c) * 8;
+                const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+                const unsigned long long wp[4] = {pack2(w0.x, w0.y), pack2(w0.z, w0.w), pack2(w1.x, w1.y), pack2(w1.z, w1.w)};
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float v = t[c][p + kx];
+                    const unsigned long long vv = pack2(v, v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[p][j] = fma2(vv, wp[j], acc[p][j]);
+                }
+            }
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(y + (((long long)b * H + yy) * W + x0) * 8);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float2 a0 = unpack2(acc[p][0]), a1 = unpack2(acc[p][1]), a2 = unpack2(acc[p][2]), a3 = unpack2(acc[p][3]);
+        dst[2 * p] = make_float4(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f), fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f));
+        dst[2 * p + 1] = make_float4(fmaxf(a2.x, 0.f), fmaxf(a2.y, 0.f), fmaxf(a3.x, 0.f), fmaxf(a3.y, 0.f));
+    }
+}
+
 // out[n,y,x,:] = bilinear_x2(top)[n,y,x,:] + W_lat . lat[n,y,x,:] + bias     (F.interpolate(scale_factor=2,
 // align_corners=True) + 1x1 lateral conv, mvs4net_utils.py:479-486).  top [N][H/2][W/2][64], lat [N][H][W][CL],
 // w [CL][64].  One thread = one pixel x 4 output channels (16 lanes per pixel).
@@ -266,6 +359,11 @@ extern "C" int mvster_conv_first_f32(const float* img_nchw, const float* w, cons
     MVSTER_REQUIRE(img_nchw && w && bias && y, "mvster_conv_first_f32: null pointer");
     MVSTER_REQUIRE(N > 0 && H > 0 && W > 0, "mvster_conv_first_f32: bad shape");
     const long long n = (long long)N * H * W;
+    const char* variant = getenv("MVSTER_CONV_FIRST");
+    if (variant && atoi(variant) == 2 && W % 4 == 0) {  // four pixels per thread, packed FMAs (opt-in until it has been timed)
+        conv_first4_kernel<<<ceil_div(n / 4, 128), 128, 0, (cudaStream_t)stream>>>(img_nchw, w, bias, y, N, H, W);
+        return check_launch("conv_first4_kernel");
+    }
     conv_first_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(img_nchw, w, bias, y, N, H, W);
     return check_launch("conv_first_kernel");
 }

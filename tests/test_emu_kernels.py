@@ -393,6 +393,31 @@ def test_four_pixel_merge_variant_returns_the_same_bits_on_cpu(emu, monkeypatch,
     assert torch.isfinite(want).all() and torch.equal(got, want)
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 8, 8), (1, 5, 12), (3, 16, 64), (1, 3, 4), (1, 6, 10)])
+def test_four_pixel_stem_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, H, W):
+    """conv_first4_kernel (MVSTER_CONV_FIRST=2: four pixels per thread, packed FMAs) against conv_first_kernel and against
+    F.conv2d; W = 10 is not a multiple of 4 and stays on the one-pixel kernel."""
+    rng = np.random.RandomState(N * 100 + H * W)
+    img = torch.from_numpy(rng.rand(N, 3, H, W).astype(np.float32))
+    wt = torch.from_numpy((rng.randn(8, 3, 3, 3) / 3).astype(np.float32))
+    bias = torch.from_numpy(rng.randn(8).astype(np.float32))
+    packed = wt.permute(2, 3, 1, 0).reshape(9, 3, 8).contiguous()          # [ky*3+kx][cin][cout]
+
+    def run():
+        out = torch.empty(N, H, W, 8)
+        rc = emu.mvster_conv_first_f32(C.c_void_p(img.data_ptr()), C.c_void_p(packed.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                       C.c_void_p(out.data_ptr()), N, H, W, None)
+        assert rc == 0
+        return out
+    monkeypatch.delenv("MVSTER_CONV_FIRST", raising=False)
+    want = run()
+    monkeypatch.setenv("MVSTER_CONV_FIRST", "2")
+    got = run()
+    assert torch.equal(got, want)
+    ref = F.relu(F.conv2d(img, wt, bias, 1, 1)).permute(0, 2, 3, 1)
+    assert (want - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
 # ----------------------------------------------------------------------------- geometric-consistency filter
 @pytest.mark.parametrize("name", ["plane_4v_48x64", "plane_3v_40x56_wide"])
 def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
