@@ -86,6 +86,112 @@ __global__ void __launch_bounds__(128) conv_px2_kernel(const ConvPxArgs a) {
     }
 }
 
+// Specialisation for the regulariser's first layer (conv0: (1,3,3), stride 1, G -> 8 channels at the stage's full resolution,
+// mvs4net_utils.py:875) - the one convolution that stays on the CUDA cores in the tensor-core engine.  conv_px2_kernel is
+// instruction-bound there (~350 instructions per voxel at G = 4 for 48 bytes).  Here one thread owns four consecutive voxels
+// of a row: each weight vector read from shared memory serves four voxels, the FMAs are packed two output channels per
+// instruction (fma.rn.f32x2) with the input value as broadcast operand, the kernel extent is a compile-time 3 x 3.  Same
+// accumulation order per output as conv_px2_kernel (ky, kx, c; out-of-image taps contribute fma(0, w, acc) = acc) - same bits.
+// Opt-in (MVSTER_CONV0_PX4=1) until it has been timed.
+namespace px4 {
+#ifdef MVSTER_CPU_EMU
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) { return emu::pack(lo, hi); }
+__device__ __forceinline__ float2 unpack2(unsigned long long v) { return emu::unpack(v); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    const float2 x = emu::unpack(a), y = emu::unpack(b), z = emu::unpack(c);
+    return emu::pack(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y));
+}
+#else
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+#endif
+}  // namespace px4
+
+template <int CIN>
+__global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ y,
+                                                        long long NP, int H, int W, int relu) {   // NP = B * D planes
+    using namespace px4;
+    __shared__ __align__(16) float w_s[9 * CIN * 8 + 8];
+    for (int i = threadIdx.x; i < 9 * CIN * 8; i += blockDim.x) w_s[i] = __ldg(w + i);
+    if (threadIdx.x < 8) w_s[9 * CIN * 8 + threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;
+    __syncthreads();
+    const unsigned W4 = (unsigned)W >> 2;
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;                 // quads: < 2^31 (checked on the host)
+    if (q >= (unsigned)NP * H * W4) return;
+    const unsigned r = q / W4;                                                // row index over all planes
+    const int x0 = (int)(q - r * W4) * 4, yy = (int)(r % (unsigned)H);
+    const long long pl = r / (unsigned)H;
+    unsigned long long acc[4][4];                                             // [voxel][output-channel pair]
+    {
+        const float4 b0 = *reinterpret_cast<const float4*>(w_s + 9 * CIN * 8), b1 = *reinterpret_cast<const float4*>(w_s + 9 * CIN * 8 + 4);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            acc[p][0] = pack2(b0.x, b0.y); acc[p][1] = pack2(b0.z, b0.w);
+            acc[p][2] = pack2(b1.x, b1.y); acc[p][3] = pack2(b1.z, b1.w);
+        }
+    }
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = yy + ky - 1;
+        if ((unsigned)iy >= (unsigned)H) continue;
+        const float4* row = reinterpret_cast<const float4*>(x + ((pl * H + iy) * W + x0) * CIN);
+        float4 t[6][CIN / 4];                                                 // voxels x0-1 .. x0+4
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const bool ok = (i > 0 || x0 > 0) && (i < 5 || x0 + 4 < W);
+#pragma unroll
+            for (int c4 = 0; c4 < CIN / 4; ++c4) t[i][c4] = ok ? __ldg(row + (i - 1) * (CIN / 4) + c4) : zero;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+            for (int c4 = 0; c4 < CIN / 4; ++c4) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float* wr = w_s + ((ky * 3 + kx) * CIN + c4 * 4 + j) * 8;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+                    const unsigned long long wp[4] = {pack2(w0.x, w0.y), pack2(w0.z, w0.w), pack2(w1.x, w1.y), pack2(w1.z, w1.w)};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float4 tv = t[p + kx][c4];
+                        const float v = j == 0 ? tv.x : j == 1 ? tv.y : j == 2 ? tv.z : tv.w;
+                        const unsigned long long vv = pack2(v, v);
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) acc[p][o] = fma2(vv, wp[o], acc[p][o]);
+                    }
+                }
+            }
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(y + ((pl * H + yy) * W + x0) * 8);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float2 a0 = unpack2(acc[p][0]), a1 = unpack2(acc[p][1]), a2 = unpack2(acc[p][2]), a3 = unpack2(acc[p][3]);
+        float4 r0 = make_float4(a0.x, a0.y, a1.x, a1.y), r1 = make_float4(a2.x, a2.y, a3.x, a3.y);
+        if (relu) {
+            r0.x = fmaxf(r0.x, 0.f); r0.y = fmaxf(r0.y, 0.f); r0.z = fmaxf(r0.z, 0.f); r0.w = fmaxf(r0.w, 0.f);
+            r1.x = fmaxf(r1.x, 0.f); r1.y = fmaxf(r1.y, 0.f); r1.z = fmaxf(r1.z, 0.f); r1.w = fmaxf(r1.w, 0.f);
+        }
+        dst[2 * p] = r0;
+        dst[2 * p + 1] = r1;
+    }
+}
+
 template <int CIN, int COUT_T>
 static int launch_px2(const ConvPxArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)a.kd * a.k * a.k * CIN * COUT_T * sizeof(float);
@@ -113,6 +219,14 @@ int conv_px2(const float* x, const float* w, const float* bias, const float* ski
     a.cout = Cout; a.kd = kd; a.k = k; a.sd = sd; a.s = s; a.relu = relu;
     const char* sw = getenv("MVSTER_CONV_PX2");  // "0" forces the one-pixel kernels (A/B measurements)
     if (sw && sw[0] == '0') return -100;
+    const char* v4 = getenv("MVSTER_CONV0_PX4");
+    if (v4 && v4[0] == '1' && kd == 1 && k == 3 && sd == 1 && s == 1 && Cout == 8 && !skip && Wi % 4 == 0 && (Cin == 4 || Cin == 8) &&
+        (long long)B * Di * Hi * (Wi / 4) < (1ll << 31)) {
+        const long long NP = (long long)B * Di, n = NP * Hi * (Wi / 4);
+        if (Cin == 4) conv0_px4_kernel<4><<<ceil_div(n, 128), 128, 0, st>>>(x, w, bias, y, NP, Hi, Wi, relu);
+        else conv0_px4_kernel<8><<<ceil_div(n, 128), 128, 0, st>>>(x, w, bias, y, NP, Hi, Wi, relu);
+        return check_launch("conv0_px4_kernel");
+    }
     if (a.Wo % 2 || Cout % 8 || (size_t)kd * k * k * Cin * (Cout % 16 == 0 ? 16 : 8) * 4 > 200 * 1024) return -100;
     switch (Cin) {
         case 4: return dispatch_px2<4>(a, st);

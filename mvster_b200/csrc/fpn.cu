@@ -156,10 +156,11 @@ __global__ void __launch_bounds__(128) conv_first4_kernel(const float* __restric
     for (int i = threadIdx.x; i < 216; i += blockDim.x) w_s[i] = __ldg(w + i);
     if (threadIdx.x < 8) w_s[216 + threadIdx.x] = __ldg(bias + threadIdx.x);
     __syncthreads();
-    const int W4 = W >> 2;
-    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;      // quad of pixels
-    if (q >= (long long)N * H * W4) return;
-    const int x0 = (int)(q % W4) * 4, yy = (int)((q / W4) % H), b = (int)(q / ((long long)W4 * H));
+    const unsigned W4 = (unsigned)W >> 2;
+    const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;                  // quad of pixels: < 2^31 (checked on the host)
+    if (q >= (unsigned)N * H * W4) return;
+    const unsigned r = q / W4;
+    const int x0 = (int)(q - r * W4) * 4, yy = (int)(r % (unsigned)H), b = (int)(r / (unsigned)H);
     unsigned long long acc[4][4];                                             // [pixel][channel pair]
     {
         const float4 b0 = *reinterpret_cast<const float4*>(w_s + 216), b1 = *reinterpret_cast<const float4*>(w_s + 220);
@@ -360,7 +361,7 @@ extern "C" int mvster_conv_first_f32(const float* img_nchw, const float* w, cons
     MVSTER_REQUIRE(N > 0 && H > 0 && W > 0, "mvster_conv_first_f32: bad shape");
     const long long n = (long long)N * H * W;
     const char* variant = getenv("MVSTER_CONV_FIRST");
-    if (variant && atoi(variant) == 2 && W % 4 == 0) {  // four pixels per thread, packed FMAs (opt-in until it has been timed)
+    if (variant && atoi(variant) == 2 && W % 4 == 0 && n / 4 < (1ll << 31)) {  // four pixels per thread, packed FMAs (opt-in until it has been timed)
         conv_first4_kernel<<<ceil_div(n / 4, 128), 128, 0, (cudaStream_t)stream>>>(img_nchw, w, bias, y, N, H, W);
         return check_launch("conv_first4_kernel");
     }

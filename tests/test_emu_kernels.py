@@ -418,6 +418,26 @@ def test_four_pixel_stem_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, 
     assert (want - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("B,D,H,W,G,relu", [(1, 4, 8, 16, 4, True), (2, 2, 5, 12, 8, True), (1, 1, 3, 4, 4, False), (1, 4, 16, 64, 8, True),
+                                            (1, 2, 6, 10, 4, True)])
+def test_four_voxel_conv0_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, B, D, H, W, G, relu):
+    """conv0_px4_kernel (MVSTER_CONV0_PX4=1; the regulariser's first layer, (1,3,3) G -> 8) against conv_px2_kernel and against
+    F.conv3d; W = 10 is not a multiple of 4 and stays on the two-voxel kernel."""
+    rng = np.random.RandomState(B * 1000 + H * W + G)
+    x = torch.from_numpy(rng.randn(B, D, H, W, G).astype(np.float32))
+    wt = torch.from_numpy((rng.randn(8, G, 1, 3, 3) / 3).astype(np.float32))
+    bias = torch.from_numpy(rng.randn(8).astype(np.float32))
+    packed = wt[:, :, 0].permute(2, 3, 1, 0).reshape(9, G, 8).contiguous()   # [ky*3+kx][cin][cout]
+    monkeypatch.delenv("MVSTER_CONV0_PX4", raising=False)
+    want = capi.conv3d_ndhwc(x, packed, bias, 1, relu=relu)
+    monkeypatch.setenv("MVSTER_CONV0_PX4", "1")
+    got = capi.conv3d_ndhwc(x, packed, bias, 1, relu=relu)
+    assert torch.equal(got, want)
+    ref = F.conv3d(x.permute(0, 4, 1, 2, 3), wt, bias, 1, (0, 1, 1))
+    ref = (F.relu(ref) if relu else ref).permute(0, 2, 3, 4, 1)
+    assert (want - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
 # ----------------------------------------------------------------------------- geometric-consistency filter
 @pytest.mark.parametrize("name", ["plane_4v_48x64", "plane_3v_40x56_wide"])
 def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
