@@ -273,12 +273,13 @@ __global__ void __launch_bounds__(128) fpn_merge4_kernel(const float* __restrict
     for (int i = threadIdx.x; i < CL * 64; i += blockDim.x) w_s[i] = __ldg(w + i);
     if (threadIdx.x < 64) w_s[CL * 64 + threadIdx.x] = __ldg(bias + threadIdx.x);
     __syncthreads();
-    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;   // < 2^31 (checked on the host): 32-bit index arithmetic
     const int q = (int)(t & 15);
-    const long long g = t >> 4;
-    const int gpr = (W + 3) / 4;  // pixel groups per row
-    if (g >= (long long)N * H * gpr) return;
-    const int xg = (int)(g % gpr), y = (int)((g / gpr) % H), b = (int)(g / ((long long)gpr * H));
+    const unsigned g = t >> 4;
+    const unsigned gpr = (unsigned)(W + 3) / 4;  // pixel groups per row
+    if (g >= (unsigned)N * H * gpr) return;
+    const unsigned rr = g / gpr;
+    const int xg = (int)(g - rr * gpr), y = (int)(rr % (unsigned)H), b = (int)(rr / (unsigned)H);
     const int Hc = H / 2, Wc = W / 2;
     const float sy = Hc > 1 ? __fdiv_rn((float)(Hc - 1), (float)(H - 1)) : 0.f, sx = Wc > 1 ? __fdiv_rn((float)(Wc - 1), (float)(W - 1)) : 0.f;
     const float fy = __fmul_rn(sy, (float)y);
@@ -375,7 +376,7 @@ extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, cons
     MVSTER_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mvster_fpn_merge_f32: H,W must be even");
     cudaStream_t st = (cudaStream_t)stream;
     const char* variant = getenv("MVSTER_FPN_MERGE");
-    if (variant && atoi(variant) == 2) {  // four pixels per lane (opt-in until it has been timed)
+    if (variant && atoi(variant) == 2 && (long long)N * H * ((W + 3) / 4) * 16 < (1ll << 31)) {  // four pixels per lane (opt-in until it has been timed)
         const long long n4 = (long long)N * H * ((W + 3) / 4) * 16;
         dim3 grid4(ceil_div(n4, 128));
         if (Clat == 8) fpn_merge4_kernel<8><<<grid4, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
