@@ -356,7 +356,7 @@ def test_native_fpn_on_cpu_matches_oracle(emu, fused_last):
         assert g.shape == w.shape and ((g - w).abs().max() / w.abs().max()).item() < 2e-5, s
 
 
-@pytest.mark.parametrize("N,H,W", [(2, 16, 24), (1, 24, 80), (1, 10, 34), (1, 2, 2)])
+@pytest.mark.parametrize("N,H,W", [(2, 16, 24), (1, 24, 80), (1, 10, 34), (1, 2, 2), (1, 6, 66)])
 def test_tiled_gather_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, H, W):
     """fpn_out4_gather2_kernel (shared-memory tiles, MVSTER_FPN_GATHER=2) against fpn_out4_gather_kernel: same expression per
     pixel, so the outputs must be identical - multi-tile, ragged and single-pixel-patch shapes."""
@@ -376,6 +376,19 @@ def test_tiled_gather_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, 
     monkeypatch.setenv("MVSTER_FPN_GATHER", "2")
     got = run()
     assert torch.isfinite(want).all() and torch.equal(got, want)
+    # variant 3 (two pixels per thread, packed FMAs, masks instead of branches): the same sum with explicitly fused
+    # multiply-adds, so equal to rounding; and all three against the definition in float64
+    monkeypatch.setenv("MVSTER_FPN_GATHER", "3")
+    got3 = run()
+    scale = want.abs().max().item()
+    assert torch.isfinite(got3).all() and (got3 - want).abs().max().item() <= 2e-6 * scale
+    up = F.interpolate(U.double().permute(1, 0, 4, 2, 3).reshape(N, 72, H // 2, W // 2), scale_factor=2, mode="bilinear",
+                       align_corners=True).reshape(N, 9, 8, H, W)                                   # up2(U_tap) per tap
+    lat = torch.einsum("nyxc,tco->ntoyx", c0.double(), wc.double()) + bt.double().reshape(1, 9, 8, 1, 1)
+    term = F.pad(up + lat, (1, 1, 1, 1))                                                            # zero padding of the 3x3 conv
+    ref = sum(term[:, ky * 3 + kx, :, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)).permute(0, 2, 3, 1)
+    for o in (want, got3):
+        assert (o.double() - ref).abs().max().item() <= 2e-6 * scale
 
 
 @pytest.mark.parametrize("N,H,W,CL", [(2, 8, 12, 32), (1, 6, 10, 16), (1, 4, 30, 8)])
