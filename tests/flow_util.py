@@ -8,15 +8,16 @@ from test_formats import _write_scan
 from mvster_b200 import formats, fusion, prefetch
 
 
-def scan_to_point_cloud(tmp_path, forward, device):
-    _write_scan(tmp_path, hw=((140, 200),) * 4)
+def scan_to_point_cloud(tmp_path, forward, device, hw=(140, 200)):
+    _write_scan(tmp_path, hw=(hw,) * 4)
+    size = (hw[0] // 64 * 64, hw[1] // 64 * 64)               # the loader shrinks both sides to multiples of 64
     pairs = formats.read_pair_file(str(tmp_path / "scan1" / "pair.txt"), 4)
     out_dir = tmp_path / "out"
     depths, confs, cams = {}, {}, {}
     for (ref, _), s in zip(pairs, prefetch.Prefetcher(prefetch.eval_jobs(str(tmp_path), "scan1", pairs, 4), device=device)):
         out = forward(s)
         d, c = out["depth"][0].cpu().numpy(), out["photometric_confidence"][0].cpu().numpy()
-        assert d.shape == c.shape == (128, 192) and np.isfinite(d).all() and (d > 0).all()
+        assert d.shape == c.shape == size and np.isfinite(d).all() and (d > 0).all()
         assert 0.0 <= c.min() and c.max() <= 1.0 + 1e-6
         name = s["filename"][0]
         for kind, arr in (("depth_est", d), ("confidence", c)):
@@ -34,7 +35,7 @@ def scan_to_point_cloud(tmp_path, forward, device):
     views = [(depths[v], cams[v][0], cams[v][1]) for v in srcs]
     res = fusion.fuse_reference_view(depths[ref], cams[ref][0], cams[ref][1], confs[ref], views, conf_thres=0.0, thres_view=1,
                                      device=device)
-    assert res["depth_est_averaged"].shape == (128, 192) and res["final_mask"].dtype == bool
+    assert res["depth_est_averaged"].shape == size and res["final_mask"].dtype == bool
     assert res["geo_mask_sum"].max() <= len(srcs)
     xyz, _ = fusion.backproject_points(res["depth_est_averaged"], res["final_mask"], cams[ref][0], cams[ref][1])
     assert xyz.shape == (int(res["final_mask"].sum()), 3) and np.isfinite(xyz).all()

@@ -529,4 +529,4 @@ def test_scan_to_point_cloud_on_cpu(emu, monkeypatch, tmp_path):
     eng = InferenceEngine(torch.device("cpu"))
     eng.refresh_weights(m)
     with torch.no_grad():
-        scan_to_point_cloud(tmp_path, lambda s: eng.forward(m, s["imgs"], s["proj_matrices"], s["depth_values"]), "cpu")
+        scan_to_point_cloud(tmp_path, lambda s: eng.forward(m, s["imgs"], s["proj_matrices"], s["depth_values"]), "cpu", hw=(70, 136))
