@@ -148,6 +148,29 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 }
 #endif
 }  // namespace cf4
+namespace cf4 {
+#ifdef MVSTER_CPU_EMU
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    const float2 x = emu::unpack(a), y = emu::unpack(b);
+    return emu::pack(x.x * y.x, x.y * y.y);
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    const float2 x = emu::unpack(a), y = emu::unpack(b);
+    return emu::pack(x.x + y.x, x.y + y.y);
+}
+#else
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+#endif
+}  // namespace cf4
 
 __global__ void __launch_bounds__(128) conv_first4_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                           const float* __restrict__ bias, float* __restrict__ y, int N, int H, int W) {
@@ -332,6 +355,101 @@ __global__ void __launch_bounds__(128) fpn_merge4_kernel(const float* __restrict
                 make_float4(up[j].x + lv[j].x, up[j].y + lv[j].y, up[j].z + lv[j].z, up[j].w + lv[j].w);
 }
 
+// Variant 3 of the merge (opt-in, MVSTER_FPN_MERGE=3; not timed yet), built from the SASS counts: with 16 lanes per pixel every
+// lane repeats the pixel's coordinate arithmetic for 4 output channels (v1: ~700 instructions per lane = 11 000 per pixel;
+// variant 2: ~3600 per pixel).  Here FOUR lanes own a group of four consecutive pixels and lane q the 16 channels
+// {16 i + 4 q + k}: the coordinates are computed once per 16 channels, a weight row read from shared memory (four conflict-free
+// 128-bit reads per lane) serves four pixels, and all arithmetic is packed two channels per instruction - ~1100 instructions
+// per pixel, which leaves the kernel to its 45.9 / 157 MB of traffic.  The accumulator starts at up + bias (variants 1/2: up +
+// (bias + sum)); equal to rounding, checked on the CPU emulation against variant 1 and the float64 definition.
+template <int CL>
+__global__ void __launch_bounds__(128) fpn_merge5_kernel(const float* __restrict__ top, const float* __restrict__ lat,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float* __restrict__ out, int N, int H, int W) {
+    using namespace cf4;
+    __shared__ __align__(16) float w_s[CL * 64 + 64];
+    for (int i = threadIdx.x; i < CL * 64; i += blockDim.x) w_s[i] = __ldg(w + i);
+    if (threadIdx.x < 64) w_s[CL * 64 + threadIdx.x] = __ldg(bias + threadIdx.x);
+    __syncthreads();
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;   // < 2^31 (checked on the host)
+    const int q = (int)(t & 3);
+    const unsigned g = t >> 2;
+    const unsigned gpr = (unsigned)(W + 3) / 4;                 // pixel groups per row
+    if (g >= (unsigned)N * H * gpr) return;
+    const unsigned rr = g / gpr;
+    const int xg = (int)(g - rr * gpr), y = (int)(rr % (unsigned)H), b = (int)(rr / (unsigned)H);
+    const int Hc = H / 2, Wc = W / 2;
+    const float sy = Hc > 1 ? __fdiv_rn((float)(Hc - 1), (float)(H - 1)) : 0.f, sx = Wc > 1 ? __fdiv_rn((float)(Wc - 1), (float)(W - 1)) : 0.f;
+    const float fy = __fmul_rn(sy, (float)y);
+    const int y0 = min((int)floorf(fy), Hc - 1);
+    const int y1 = y0 + (y0 < Hc - 1);
+    const float ly1 = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), ly0 = 1.f - ly1;
+    const unsigned long long ly0v = pack2(ly0, ly0), ly1v = pack2(ly1, ly1);
+    const float* tb = top + (long long)b * Hc * Wc * 64 + q * 4;
+    unsigned long long acc[4][8];                               // [pixel][chunk i][pair]: channels 16 i + 4 q + {0,1 | 2,3}
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = min(xg * 4 + j, W - 1);                   // a ragged last group repeats the last pixel (never stored)
+        const float fx = __fmul_rn(sx, (float)x);
+        const int x0 = min((int)floorf(fx), Wc - 1);
+        const int x1 = x0 + (x0 < Wc - 1);
+        const float lx1 = fminf(fmaxf(fx - (float)x0, 0.f), 1.f), lx0 = 1.f - lx1;
+        const unsigned long long lx0v = pack2(lx0, lx0), lx1v = pack2(lx1, lx1);
+        const float* p00 = tb + ((long long)y0 * Wc + x0) * 64;
+        const float* p01 = tb + ((long long)y0 * Wc + x1) * 64;
+        const float* p10 = tb + ((long long)y1 * Wc + x0) * 64;
+        const float* p11 = tb + ((long long)y1 * Wc + x1) * 64;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 a00 = __ldg(reinterpret_cast<const float4*>(p00 + 16 * i)), a01 = __ldg(reinterpret_cast<const float4*>(p01 + 16 * i));
+            const float4 a10 = __ldg(reinterpret_cast<const float4*>(p10 + 16 * i)), a11 = __ldg(reinterpret_cast<const float4*>(p11 + 16 * i));
+            const float4 bb = *reinterpret_cast<const float4*>(w_s + CL * 64 + 16 * i + q * 4);
+            // ATen order: ly0*(lx0*v00 + lx1*v01) + ly1*(lx0*v10 + lx1*v11)
+            const unsigned long long t_lo = fma2(lx1v, pack2(a01.x, a01.y), mul2(lx0v, pack2(a00.x, a00.y)));
+            const unsigned long long b_lo = fma2(lx1v, pack2(a11.x, a11.y), mul2(lx0v, pack2(a10.x, a10.y)));
+            const unsigned long long t_hi = fma2(lx1v, pack2(a01.z, a01.w), mul2(lx0v, pack2(a00.z, a00.w)));
+            const unsigned long long b_hi = fma2(lx1v, pack2(a11.z, a11.w), mul2(lx0v, pack2(a10.z, a10.w)));
+            acc[j][2 * i] = add2(fma2(ly1v, b_lo, mul2(ly0v, t_lo)), pack2(bb.x, bb.y));
+            acc[j][2 * i + 1] = add2(fma2(ly1v, b_hi, mul2(ly0v, t_hi)), pack2(bb.z, bb.w));
+        }
+    }
+    const long long row = ((long long)b * H + y) * W;
+#pragma unroll
+    for (int c4 = 0; c4 < CL / 4; ++c4) {
+        float tv[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 tt = __ldg(reinterpret_cast<const float4*>(lat + (row + min(xg * 4 + j, W - 1)) * CL) + c4);
+            tv[j][0] = tt.x; tv[j][1] = tt.y; tv[j][2] = tt.z; tv[j][3] = tt.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            unsigned long long wp[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 wr = *reinterpret_cast<const float4*>(w_s + (c4 * 4 + e) * 64 + 16 * i + q * 4);
+                wp[2 * i] = pack2(wr.x, wr.y); wp[2 * i + 1] = pack2(wr.z, wr.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned long long vv = pack2(tv[j][e], tv[j][e]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[j][k] = fma2(vv, wp[k], acc[j][k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (xg * 4 + j >= W) break;
+        float* dst = out + (row + xg * 4 + j) * 64 + q * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 lo = unpack2(acc[j][2 * i]), hi = unpack2(acc[j][2 * i + 1]);
+            *reinterpret_cast<float4*>(dst + 16 * i) = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+    }
+}
+
 }  // namespace mvster
 
 using namespace mvster;
@@ -384,6 +502,15 @@ extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, cons
         else if (Clat == 32) fpn_merge4_kernel<32><<<grid4, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
         else MVSTER_REQUIRE(false, "mvster_fpn_merge_f32: unsupported lateral channels %d (8,16,32)", Clat);
         return check_launch("fpn_merge4_kernel");
+    }
+    if (variant && atoi(variant) == 3 && (long long)N * H * ((W + 3) / 4) * 4 < (1ll << 31)) {  // four lanes per four pixels, packed FMAs (opt-in)
+        const long long n5 = (long long)N * H * ((W + 3) / 4) * 4;
+        dim3 grid5(ceil_div(n5, 128));
+        if (Clat == 8) fpn_merge5_kernel<8><<<grid5, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+        else if (Clat == 16) fpn_merge5_kernel<16><<<grid5, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+        else if (Clat == 32) fpn_merge5_kernel<32><<<grid5, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
+        else MVSTER_REQUIRE(false, "mvster_fpn_merge_f32: unsupported lateral channels %d (8,16,32)", Clat);
+        return check_launch("fpn_merge5_kernel");
     }
     const long long n = (long long)N * H * W * 16;  // 16 lanes per pixel
     dim3 grid(ceil_div(n, 128));
@@ -600,29 +727,6 @@ __global__ void __launch_bounds__(256) fpn_out4_gather2_kernel(const float* __re
 //     split-halves layout of variant 2 (conflict-free 128-bit reads by consecutive lanes).
 // Same sum as variants 1/2 with the FMAs written out explicitly (so not bit-identical to what nvcc contracts in variant 1;
 // tests/test_emu_kernels.py bounds the difference and checks against F.conv2d).
-namespace cf4 {
-#ifdef MVSTER_CPU_EMU
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-    const float2 x = emu::unpack(a), y = emu::unpack(b);
-    return emu::pack(x.x * y.x, x.y * y.y);
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-    const float2 x = emu::unpack(a), y = emu::unpack(b);
-    return emu::pack(x.x + y.x, x.y + y.y);
-}
-#else
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-#endif
-}  // namespace cf4
 
 constexpr int G3_SMEM_FLOATS = 9 * 2 * G2_UPX * 4 + 2 * G2_CPX * 4 + 576 + 72;
 

@@ -391,7 +391,7 @@ def test_tiled_gather_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, 
         assert (o.double() - ref).abs().max().item() <= 2e-6 * scale
 
 
-@pytest.mark.parametrize("N,H,W,CL", [(2, 8, 12, 32), (1, 6, 10, 16), (1, 4, 30, 8)])
+@pytest.mark.parametrize("N,H,W,CL", [(2, 8, 12, 32), (1, 6, 10, 16), (1, 4, 30, 8), (1, 2, 2, 16), (2, 4, 66, 32)])
 def test_four_pixel_merge_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, H, W, CL):
     """fpn_merge4_kernel (MVSTER_FPN_MERGE=2) against fpn_merge_kernel, ragged rows included (W not a multiple of 4)."""
     rng = np.random.RandomState(H * W + CL)
@@ -404,6 +404,16 @@ def test_four_pixel_merge_variant_returns_the_same_bits_on_cpu(emu, monkeypatch,
     monkeypatch.setenv("MVSTER_FPN_MERGE", "2")
     got = fpn_engine._merge(top, lat, w, bias)
     assert torch.isfinite(want).all() and torch.equal(got, want)
+    # variant 3 (four lanes per four pixels, packed FMAs, accumulator seeded with up + bias): equal to rounding, and both
+    # against the definition in float64
+    monkeypatch.setenv("MVSTER_FPN_MERGE", "3")
+    got3 = fpn_engine._merge(top, lat, w, bias)
+    scale = want.abs().max().item()
+    assert torch.isfinite(got3).all() and (got3 - want).abs().max().item() <= 2e-6 * scale
+    ref = F.interpolate(top.double().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1) \
+        + lat.double() @ w.double() + bias.double()
+    for o in (want, got3):
+        assert (o.double() - ref).abs().max().item() <= 2e-6 * scale
 
 
 @pytest.mark.parametrize("N,H,W", [(2, 8, 8), (1, 5, 12), (3, 16, 64), (1, 3, 4), (1, 6, 10)])

@@ -6,9 +6,9 @@ set -u
 echo "== correctness with the switches on"
 MVSTER_TC3_MERGE=1 timeout 400 python -m pytest tests/test_gpu_tc_conv.py -m gpu -q -x -k "v3" 2>&1 | tail -2
 MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=2 MVSTER_FPN_MERGE=2 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1 timeout 300 python -m pytest tests/test_gpu_y_fpn.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
-MVSTER_FPN_GATHER=3 timeout 300 python -m pytest tests/test_gpu_y_fpn.py -m gpu -q -x 2>&1 | tail -2
+MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 timeout 300 python -m pytest tests/test_gpu_y_fpn.py -m gpu -q -x 2>&1 | tail -2
 echo "== bench step (ms) per switch"
-for sw in "" "MVSTER_TC3_MERGE=1" "MVSTER_FPN_GATHER=2" "MVSTER_FPN_GATHER=3" "MVSTER_FPN_MERGE=2" "MVSTER_CONV_FIRST=2" "MVSTER_CONV0_PX4=1" "MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=2 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1"; do
+for sw in "" "MVSTER_TC3_MERGE=1" "MVSTER_FPN_GATHER=2" "MVSTER_FPN_GATHER=3" "MVSTER_FPN_MERGE=2" "MVSTER_FPN_MERGE=3" "MVSTER_CONV_FIRST=2" "MVSTER_CONV0_PX4=1" "MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1" "MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1"; do
   out=$(env $sw timeout 200 python bench.py --no-cpu-baseline 2>/dev/null)
   echo "$out" | python -c "
 import json,sys
