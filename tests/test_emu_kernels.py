@@ -486,7 +486,7 @@ def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
 
 
 # ----------------------------------------------------------------------------- the whole forward
-@pytest.mark.parametrize("name", ["shipped_b1_v3_64x128", "reg3d_b1_v2_64x64", "plain_b1_v2_64x64"])
+@pytest.mark.parametrize("name", ["shipped_b1_v3_64x128", "reg3d_b1_v2_64x64", "plain_b1_v2_64x64", "shipped_b1_v3_64x128+variants"])
 def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch, name):
     """InferenceEngine.forward - native feature pyramid, four cascade stages, every convolution on the exact-fp32 CUDA-core
     kernels - executed on the emulation library with CPU tensors, against the outputs of the unmodified reference
@@ -496,6 +496,10 @@ def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch, na
     from util import GOLDEN_CASES, load_golden, top2_gap
     from mvster_b200.engine import InferenceEngine
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    if name.endswith("+variants"):   # the prepared (opt-in) CUDA-core kernel variants switched on
+        name = name[:-len("+variants")]
+        for k, v in (("MVSTER_FPN_GATHER", "3"), ("MVSTER_FPN_MERGE", "3"), ("MVSTER_CONV_FIRST", "2"), ("MVSTER_CONV0_PX4", "1")):
+            monkeypatch.setenv(k, v)
     z, imgs, proj, dv = load_golden(name)
     m = build_model(GOLDEN_CASES[name], int(z["meta_seed"]))
     m.reg_precision = m.fpn_precision = "fp32"
