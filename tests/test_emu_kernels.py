@@ -486,7 +486,7 @@ def test_geo_consistency_kernel_on_cpu_matches_reference(emu, name):
 
 
 # ----------------------------------------------------------------------------- the whole forward
-@pytest.mark.parametrize("name", ["shipped_b1_v3_64x128", "reg3d_b1_v2_64x64", "plain_b1_v2_64x64", "shipped_b1_v3_64x128+variants"])
+@pytest.mark.parametrize("name", ["shipped_b1_v3_64x128", "reg3d_b1_v2_64x64", "plain_b1_v2_64x64", "shipped_b1_v3_64x128+variants", "shipped_b2_v2_64x64"])
 def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch, name):
     """InferenceEngine.forward - native feature pyramid, four cascade stages, every convolution on the exact-fp32 CUDA-core
     kernels - executed on the emulation library with CPU tensors, against the outputs of the unmodified reference
