@@ -1,5 +1,6 @@
 """Builds tests/emu/_build/libmvster_emu.so: the SIMT sources of mvster_b200/csrc, rewritten by transform.py, compiled
 with g++ against simt_emu.h.  The tensor-core (tcgen05 / TMA) entry points are stubs that fail."""
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -16,7 +17,11 @@ FLAGS = ["-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-fPIC", "-w", "-
 
 
 def build(force: bool = False) -> Path:
-    out = HERE / "_build"
+    # MVSTER_EMU_ASAN=1: AddressSanitizer build in its own directory (run pytest with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+    # and ASAN_OPTIONS=detect_leaks=0: tensors then come from the intercepted allocator and every out-of-bounds access of a
+    # kernel is reported)
+    asan = os.environ.get("MVSTER_EMU_ASAN", "0") == "1"
+    out = HERE / ("_build_asan" if asan else "_build")
     src = out / "src"
     lib = out / "libmvster_emu.so"
     deps = [CSRC / f for f in SOURCES + HEADERS] + [HERE / f for f in ("simt_emu.h", "common_emu.h", "transform.py", "build_emu.py", "emu_stubs.cpp")]
@@ -29,7 +34,8 @@ def build(force: bool = False) -> Path:
     for name in SOURCES + ["emu_stubs.cpp"]:
         path = src / name if name != "emu_stubs.cpp" else HERE / name
         obj = out / (Path(name).stem + ".o")
-        procs.append((name, subprocess.Popen(["g++", *FLAGS, "-I", str(src), "-c", str(path), "-o", str(obj)], stdout=subprocess.PIPE,
+        procs.append((name, subprocess.Popen(["g++", *FLAGS, *(["-fsanitize=address", "-g", "-fno-omit-frame-pointer"] if asan else []),
+                                              "-I", str(src), "-c", str(path), "-o", str(obj)], stdout=subprocess.PIPE,
                                              stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     bad = []
@@ -39,7 +45,7 @@ def build(force: bool = False) -> Path:
             bad.append(f"--- {name}\n{log[-6000:]}")
     if bad:
         raise RuntimeError("emulation build failed:\n" + "\n".join(bad))
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", str(lib), *map(str, objs)])
+    subprocess.check_call(["g++", "-shared", "-pthread", *(["-fsanitize=address"] if asan else []), "-o", str(lib), *map(str, objs)])
     return lib
 
 
