@@ -21,7 +21,8 @@ def build(force: bool = False) -> Path:
     # and ASAN_OPTIONS=detect_leaks=0: tensors then come from the intercepted allocator and every out-of-bounds access of a
     # kernel is reported)
     asan = os.environ.get("MVSTER_EMU_ASAN", "0") == "1"
-    out = HERE / ("_build_asan" if asan else "_build")
+    tsan = os.environ.get("MVSTER_EMU_TSAN", "0") == "1"   # ThreadSanitizer: races between the threads of a block (LD_PRELOAD libtsan.so)
+    out = HERE / ("_build_asan" if asan else "_build_tsan" if tsan else "_build")
     src = out / "src"
     lib = out / "libmvster_emu.so"
     deps = [CSRC / f for f in SOURCES + HEADERS] + [HERE / f for f in ("simt_emu.h", "common_emu.h", "transform.py", "build_emu.py", "emu_stubs.cpp")]
@@ -34,7 +35,7 @@ def build(force: bool = False) -> Path:
     for name in SOURCES + ["emu_stubs.cpp"]:
         path = src / name if name != "emu_stubs.cpp" else HERE / name
         obj = out / (Path(name).stem + ".o")
-        procs.append((name, subprocess.Popen(["g++", *FLAGS, *(["-fsanitize=address", "-g", "-fno-omit-frame-pointer"] if asan else []),
+        procs.append((name, subprocess.Popen(["g++", *FLAGS, *(["-fsanitize=address", "-g", "-fno-omit-frame-pointer"] if asan else ["-fsanitize=thread", "-g"] if tsan else []),
                                               "-I", str(src), "-c", str(path), "-o", str(obj)], stdout=subprocess.PIPE,
                                              stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -45,7 +46,7 @@ def build(force: bool = False) -> Path:
             bad.append(f"--- {name}\n{log[-6000:]}")
     if bad:
         raise RuntimeError("emulation build failed:\n" + "\n".join(bad))
-    subprocess.check_call(["g++", "-shared", "-pthread", *(["-fsanitize=address"] if asan else []), "-o", str(lib), *map(str, objs)])
+    subprocess.check_call(["g++", "-shared", "-pthread", *(["-fsanitize=address"] if asan else ["-fsanitize=thread"] if tsan else []), "-o", str(lib), *map(str, objs)])
     return lib
 
 
