@@ -36,6 +36,13 @@ def emu(emu_lib, monkeypatch):
     monkeypatch.setattr(_lib, "_lib", emu_lib)
     monkeypatch.setattr(capi, "_chk", install.cpu_chk)
     monkeypatch.setattr(capi, "_stream", lambda: C.c_void_p(0))
+    # every buffer the wrappers allocate starts as NaN: an output element a kernel does not write cannot pass a comparison
+    real_empty = torch.empty
+
+    def nan_empty(*a, **kw):
+        t = real_empty(*a, **kw)
+        return t.fill_(float("nan")) if t.is_floating_point() else t
+    monkeypatch.setattr(torch, "empty", nan_empty)
     return emu_lib
 
 
