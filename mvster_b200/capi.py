@@ -4,7 +4,6 @@ features, NDHWC cost volume).  CUDA tensors only - anything else raises."""
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import List, Optional, Sequence
 
 import torch

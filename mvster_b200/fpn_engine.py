@@ -7,7 +7,6 @@ feature tensors the warp kernel consumes.
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 from typing import Dict, Mapping, Optional
 

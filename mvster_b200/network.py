@@ -15,7 +15,7 @@ Dispatch in ``forward``:
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional, Sequence
+from typing import Dict
 
 import torch
 import torch.nn as nn

@@ -9,7 +9,7 @@ inference fallback: inference without the CUDA library raises (see network.py).
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Sequence
+from typing import Dict, Sequence
 
 import torch
 import torch.nn.functional as F

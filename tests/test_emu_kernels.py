@@ -15,7 +15,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from util import GOLDEN, REPO, SHIPPED, build_model, narrow_et_inputs, oracle, oracle_cfg
+from util import GOLDEN, REPO, SHIPPED, build_model, narrow_et_inputs, oracle
 from oracle import fusion_oracle
 
 from mvster_b200 import _lib, capi, fpn_engine, packing, synth

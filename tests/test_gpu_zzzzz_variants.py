@@ -2,8 +2,6 @@
 conv0) against the default kernels on the GPU.  They were written after the round's last GPU session and had only run on the
 CPU emulation (tests/test_emu_kernels.py, also under Address- and ThreadSanitizer); this file is the GPU half of that check and
 sorts last.  The library reads its switches at every launch, so the environment is set per call."""
-import ctypes as C
-
 import numpy as np
 import pytest
 import torch
