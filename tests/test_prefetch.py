@@ -79,3 +79,20 @@ def test_transform_and_eval_jobs_on_a_synthetic_scan(tmp_path):
             assert np.array_equal(s["proj_matrices"][k][0].numpy(), want["proj_matrices"][k])
         seen += 1
     assert seen == 3
+
+
+def test_consumer_can_stop_early_without_hanging():
+    started = []
+
+    def jobs():
+        for i in range(1000):
+            def f(i=i):
+                started.append(i)
+                time.sleep(0.005)
+                return {"x": np.zeros(2, np.float32) + i}
+            yield f
+    t0 = time.time()
+    for s in prefetch.Prefetcher(jobs(), device="cpu", depth=2, workers=2):
+        if s["x"][0].item() == 3:
+            break
+    assert time.time() - t0 < 5.0 and len(started) < 40       # pending jobs are cancelled, the pool is shut down
