@@ -39,6 +39,7 @@ BN_EPS = 1e-5  # torch.nn.BatchNorm{2,3}d default, used by every BN in the refer
 # (mvs4net_utils.py:28-29) and torch.autocast destroys the geometry - so the bf16 configuration is
 # defined as the fp32 reference with bf16 ROUNDING at the points where a bf16 build stores data: the FPN outputs, the cost
 # volume, and every convolution's operands (activations and weights; accumulation, BN, geometry and softmax stay fp32).
+# PARITY UNPINNED for this configuration: there is no reference output to pin it to; the fp32 path it is built on is pinned.
 # --------------------------------------------------------------------------
 _STORAGE = None
 
