@@ -1,7 +1,7 @@
 """The default-off CUDA-core kernel variants (fpn.cu: gather 2 / 3, merge 2 / 3, four-pixel stem; conv_simt_px2.cu: four-voxel
 conv0) against the default kernels on the GPU.  They were written after the round's last GPU session and had only run on the
-CPU emulation (tests/test_emu_kernels.py, also under Address- and ThreadSanitizer); this file is the GPU half of that check and
-sorts last.  The library reads its switches at every launch, so the environment is set per call."""
+CPU emulation (tests/test_emu_kernels.py, also under Address- and ThreadSanitizer); this file is the GPU half of that check; it
+sorts after the tests that were green on the B200 and before the two files with more GPU-only surface (backward, prefetcher).  The library reads its switches at every launch, so the environment is set per call."""
 import numpy as np
 import pytest
 import torch
