@@ -4,6 +4,7 @@
 #     bash tools/ab_optin.sh 2>&1 | tee gpurun_out/ab_optin.txt
 set -u
 echo "== correctness with the switches on"
+timeout 400 python -m pytest tests/test_gpu_zzy_variants.py -m gpu -q 2>&1 | tail -3   # every variant against its default kernel
 MVSTER_TC3_MERGE=1 timeout 400 python -m pytest tests/test_gpu_tc_conv.py -m gpu -q -x -k "v3" 2>&1 | tail -2
 MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=2 MVSTER_FPN_MERGE=2 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1 timeout 300 python -m pytest tests/test_gpu_y_fpn.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
 MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 timeout 300 python -m pytest tests/test_gpu_y_fpn.py -m gpu -q -x 2>&1 | tail -2
