@@ -8,6 +8,10 @@ timeout 400 python -m pytest tests/test_gpu_zzy_variants.py -m gpu -q 2>&1 | tai
 MVSTER_TC3_MERGE=1 timeout 400 python -m pytest tests/test_gpu_tc_conv.py -m gpu -q -x -k "v3" 2>&1 | tail -2
 MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=2 MVSTER_FPN_MERGE=2 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1 timeout 300 python -m pytest tests/test_gpu_y_fpn.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
 MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 timeout 300 python -m pytest tests/test_gpu_y_fpn.py -m gpu -q -x 2>&1 | tail -2
+echo "== kernel-level A/B (us per launch, GB/s on the algorithmic bytes, deviation from the default kernel)"
+timeout 600 python tools/glue_ab.py > gpurun_out/glue_ab.json 2>gpurun_out/glue_ab.err; python -c "
+import json
+for r in json.load(open('gpurun_out/glue_ab.json'))['rows']: print('%-42s %-22s %8.2f us %8.1f GB/s  dev %.1e' % (r['kernel'], r['switch'], r['us'], r['GB/s'], r['max_dev_vs_default']))"
 echo "== bench step (ms) per switch"
 for sw in "" "MVSTER_TC3_MERGE=1" "MVSTER_FPN_GATHER=2" "MVSTER_FPN_GATHER=3" "MVSTER_FPN_MERGE=2" "MVSTER_FPN_MERGE=3" "MVSTER_CONV_FIRST=2" "MVSTER_CONV0_PX4=1" "MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1" "MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1"; do
   out=$(env $sw timeout 200 python bench.py --no-cpu-baseline 2>/dev/null)
