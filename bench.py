@@ -167,6 +167,180 @@ def config_dict(n, view_parallel=1):
             "l2": "512 MB buffer written between timed steps (L2 flush)"}
 
 
+def _time_forward(fn, steps, flush, warmup=3):
+    """ms per call of fn: CUDA events on the current stream, L2 flushed before every call."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1.0)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ts = [s.elapsed_time(e) for s, e in evs]
+    return statistics.mean(ts), min(ts)
+
+
+def gpu_eager_baseline(model, imgs_d, proj_d, dv_d, flush, steps=10):
+    """The >= 10x target's denominator (SURVEY.md 8d "GPU baseline"): the reference's forward as PyTorch ops, eager on this GPU
+    through cuDNN/ATen, `cudnn.benchmark=True` as `test_mvs4.py:20`, with TF32 allowed (PyTorch's cuDNN default = how the
+    reference runs) and with strict fp32.  /root/reference does not travel to the GPU box, so the op sequence is this
+    repository's differentiable restatement of it (mvster_b200/torch_path.py + the module's own nn.Conv/BatchNorm layers:
+    same ATen calls per view and stage as mvs4net_utils.py:13-59, 1015-1094), pinned by tests/test_host_cpu.py."""
+    res = {"formulation": "reference op sequence as PyTorch ops (network._forward_autograd, eval, no_grad), eager, cudnn.benchmark=True"}
+    B = imgs_d[0].shape[0]
+    for tf32 in (True, False):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+
+        def fwd():
+            with torch.no_grad():
+                return model._forward_autograd(imgs_d, proj_d, dv_d)
+        ms, best = _time_forward(fwd, steps, flush, warmup=6)
+        res["tf32_on" if tf32 else "tf32_off"] = {"value": B / (ms * 1e-3), "ms_per_step": ms, "min_ms": best, "allow_tf32": tf32}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return res
+
+
+def extra_legs(model, dev, flush, steps=5):
+    """Informational legs on the same line: the reference's own test-time sizes (README.md:77-81, test_mvs4.py:41-42: 832x1152
+    and 1152x1600, 5 views) through the default (CUDA-graph) path, and cfg2 through eager launches (no CUDA graph)."""
+    from mvster_b200 import synth
+    out = {"sizes": []}
+    for (nv, H, W) in ((5, 832, 1152), (5, 1152, 1600)):
+        imgs, proj, dv = synth.make_inputs(1, nv, H, W, seed=0)
+        imgs = [t.to(dev) for t in imgs]
+        proj = {k: v.to(dev) for k, v in proj.items()}
+        dv = dv.to(dev)
+
+        def fwd():
+            with torch.no_grad():
+                return model(imgs, proj, dv)
+        ms, best = _time_forward(fwd, steps, flush)
+        out["sizes"].append({"views": nv, "H": H, "W": W, "ms_per_step": ms, "min_ms": best, "value": 1.0 / (ms * 1e-3),
+                             "cuda_graph": bool(model.use_cuda_graph)})
+        del imgs, proj, dv
+        eng = model._engines.get(dev.index)
+        if eng is not None:
+            eng._graphs.clear()  # each captured graph pins its workspace
+        torch.cuda.empty_cache()
+    return out
+
+
+def et_traffic_record(kernel_key: str):
+    """DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) of the stage-4 warp/ET launch, read from the
+    committed summary of an `ncu --set full` capture (profiles/et_traffic.json, written by tools/ncu_summary.py --traffic);
+    None when no capture of the current kernel is on record - never a literal in this file."""
+    p = REPO / "profiles" / "et_traffic.json"
+    if not p.exists():
+        return None, None
+    import hashlib
+    raw = p.read_bytes()
+    try:
+        rec = json.loads(raw).get(kernel_key)
+    except Exception:
+        return None, None
+    if not rec:
+        return None, None
+    return float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"]), \
+        {"file": "profiles/et_traffic.json", "sha256_16": hashlib.sha256(raw).hexdigest()[:16], "capture": rec.get("capture")}
+
+
+def _timed_ranks(fn, steps, flush, dist, dev, warmup=3):
+    """Summed step time in ms over ``steps`` calls (CUDA events per step, L2 flushed between steps), max over ranks."""
+    for _ in range(warmup):
+        fn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s, e in evs:
+        flush.fill_(1.0)
+        s.record()
+        fn()
+        e.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    total = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], dtype=torch.float64, device=dev)
+    dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    return float(total.item()) / steps
+
+
+def multi_gpu_legs(args, rank, world, dev, flush):
+    """The two multi-GPU configurations BASELINE.json names, measured inside the same `bench.py --gpus N` invocation:
+
+    view_sharded - cfg4: 9 source views at 512x640, sharded over P = min(N, 4) ranks per frame (N/P frames as replicas): every
+      rank extracts features for the reference view + its own source views, the warp/ET kernel writes un-normalised
+      [acc | wsum] partials, ONE NCCL all-reduce per cascade stage merges them (mvs4net_utils.py:1025 is a serial loop over
+      views, :1054-1060 the sum), the regulariser and head run replicated.  Reported next to the same frame unsharded on one
+      GPU (strong scaling over views) and the all-reduce alone per stage.
+    cfg5 - 11 views at 1024x1920, one frame per GPU (batch sharding, no collective)."""
+    import torch.distributed as dist
+    from mvster_b200 import sharding, synth
+    steps = max(5, min(args.steps, 10))
+    P = min(world, 4)
+    frames = world // P
+    NV, H, W = 10, 512, 640
+    model = build_model(dev)
+    model.use_cuda_graph = os.environ.get("MVSTER_CUDA_GRAPH", "1") == "1"
+    imgs, proj, dv = synth.make_inputs(1, NV, H, W, seed=rank // P)
+    imgs = [t.to(dev) for t in imgs]
+    proj = {k: v.to(dev) for k, v in proj.items()}
+    dv = dv.to(dev)
+
+    def fwd():
+        with torch.no_grad():
+            return model(imgs, proj, dv)
+
+    ms_full = _timed_ranks(fwd, steps, flush, dist, dev)     # P = 1: every rank runs the whole 10-view frame alone
+    full = fwd()
+    full_depth, full_attn1 = full["depth"].clone(), full["stage1"]["attn_weight"].clone()
+    shard = sharding.make_view_shard(NV - 1, P)
+    model.set_view_shard(shard)
+    ms_shard = _timed_ranks(fwd, steps, flush, dist, dev)
+    part = fwd()
+    torch.cuda.synchronize()
+    same = torch.tensor([(part["depth"] == full_depth).float().mean().item(),
+                         -(part["stage1"]["attn_weight"] - full_attn1).abs().max().item()], dtype=torch.float64, device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    model.set_view_shard(None)
+    # the collective alone, per stage, on the same process group and payload
+    ar_us, ar_bytes = [], []
+    for k in range(4):
+        n = sharding.allreduce_bytes(1, D_K[k], H >> (3 - k), W >> (3 - k), G_K[k])
+        buf = torch.zeros(n // 4, dtype=torch.float32, device=dev)
+        ms = _timed_ranks(lambda: dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=shard.group), 20, flush, dist, dev)
+        ar_us.append(ms * 1e3)
+        ar_bytes.append(n)
+    view_sharded = {
+        "workload": f"cfg4: 9 source views, 512x640, fp32; {P} view ranks per frame x {frames} frame replica(s)",
+        "view_parallel": P, "frames": frames, "value": frames / (ms_shard * 1e-3), "unit": UNIT, "ms_per_step": ms_shard,
+        "unsharded_ms_per_step": ms_full, "strong_scaling_vs_P1": ms_full / ms_shard,
+        "views_per_rank": [c for _, c in sharding.partition_views(NV - 1, P)],
+        "allreduce_us_per_stage": ar_us, "allreduce_bytes": ar_bytes,
+        "depth_equal_unsharded": float(same[0].item()), "stage1_attn_abs_vs_unsharded": -float(same[1].item()),
+        "cuda_graph": bool(model.use_cuda_graph) and os.environ.get("MVSTER_SHARD_GRAPH", "1") == "1",
+        "collective": "torch.distributed all_reduce(sum) on [acc|wsum], NCCL, one per stage"}
+    del imgs, proj, dv, full, part
+    eng = model._engines.get(dev.index)
+    if eng is not None:
+        eng._graphs.clear()
+    torch.cuda.empty_cache()
+    # cfg5: 11 views, 1024x1920, one frame per GPU
+    imgs, proj, dv = synth.make_inputs(1, 11, 1024, 1920, seed=rank)
+    imgs = [t.to(dev) for t in imgs]
+    proj = {k: v.to(dev) for k, v in proj.items()}
+    dv = dv.to(dev)
+    ms5 = _timed_ranks(fwd, steps, flush, dist, dev)
+    cfg5 = {"workload": f"cfg5: 11 views, 1024x1920 (tanks.py:58-59 crop of 1080x1920), fp32, batch {world} = one frame per GPU, no collective",
+            "value": world / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5}
+    return {"view_sharded": view_sharded, "cfg5": cfg5}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +355,7 @@ def main():
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap the resident timed loop in cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer loop")
+    ap.add_argument("--quick", action="store_true", help="skip the informational legs (GPU-eager baseline, other sizes, multi-GPU view sharding)")
     ap.add_argument("--view-parallel", type=int, default=1,
                     help="P ranks cooperate on one frame by sharding its source views (one all-reduce per stage); "
                          "world/P frames run as replicas.  Default 1 = pure batch sharding (weak scaling)")
@@ -323,11 +498,14 @@ def main():
             fn()
             e.record()
         barrier()
-        total = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], dtype=torch.float64, device=dev)
+        per_step.clear()
+        per_step.extend(s.elapsed_time(e) for s, e in evs)
+        total = torch.tensor([sum(per_step)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(total, op=dist.ReduceOp.MAX)
         return float(total.item())
 
+    per_step = []  # this rank's step times (ms) of the last timed() call
     # kernels of libmvster_b200 per forward, counted on one eager pass (a CUDA-graph replay issues the same kernels
     # without going through the library's launch counter)
     graphed, model.use_cuda_graph = model.use_cuda_graph, False
@@ -346,6 +524,8 @@ def main():
     if args.profile_range:
         torch.cuda.profiler.start()
     ms_total = timed(step_resident, args.steps)
+    step_stats = {"min_ms": min(per_step), "median_ms": statistics.median(per_step),
+                  "p95_ms": sorted(per_step)[min(len(per_step) - 1, int(0.95 * len(per_step)))], "max_ms": max(per_step)}
     if args.profile_range:
         torch.cuda.profiler.stop()
     launches = launches_per_step * args.steps if (model.use_cuda_graph and P == 1) else _lib.launch_count() - l0
@@ -398,14 +578,12 @@ def main():
         tot_b = sum(p["bytes"] for p in per_stage)
         tot_t = sum(p["us"] for p in per_stage) * 1e-6
         dom = per_stage[3]
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
-        # (profiles/r01_et_fuse_win_ncu.md: 55.0 MB + 3.67 MB; the 21 MB cost volume mostly stays in the 126 MB L2)
-        win = os.environ.get("MVSTER_ET_WIN", "1") != "0"
-        roof = {"kernel": ("et_fuse_win_kernel<C=8,G=4,D=4,LPP=1>" if win else "et_fuse_tiled_kernel<C=8,G=4,D=4,LPP=1>") +
-                          " (stage 4 launch: C=8, G=4, D=4, 4 source views, 327680 pixels)", "bound": "hbm",
+        kname = capi.et_last_kernel()  # the stage-4 launch was the last one timed
+        traffic, traffic_src = et_traffic_record(kname) if (B, NV, H, W) == (1, 5, 512, 640) else (None, None)
+        roof = {"kernel": kname + " (stage 4 launch: C=8, G=4, D=4, 4 source views, 327680 pixels)", "bound": "hbm",
                 "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak, "peak_source": peak_src,
-                "algorithmic_bytes": dom["bytes"], "traffic": (58.67e6 if win else 58.18e6) if (B, NV, H, W) == (1, 5, 512, 640) else None, "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak,
-                                                 "bytes": tot_b, "us": tot_t * 1e6},
+                "algorithmic_bytes": dom["bytes"], "traffic": traffic, "traffic_source": traffic_src,
+                "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak, "bytes": tot_b, "us": tot_t * 1e6},
                 "per_stage": per_stage}
 
     # ---- the convolution kernel that holds most of the step time (profiles/r01_launches_tc3.md): tensor-pipe view.
@@ -443,20 +621,36 @@ def main():
                            "; every M128 x K16 MMA is bound by its 4 KB A-operand fetch from shared memory, not by the multipliers, and the"
                            " layer by the activation ring's latency (profiles/r01_conv_tc3_h16_ncu.md)", "traffic": None}
 
-    cpu_base = None
+    cpu_base, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import mvster_oracle as oracle
+        from oracle.compare import cascade_parity
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         cfg = dict(oracle.DEFAULT_CFG)
         small = synth.make_inputs(1, 3, 128, 192, seed=1)
         cores = pick_cpu_threads(lambda: oracle.cascade_forward(sd, cfg, *small))
-        oracle.cascade_forward(sd, cfg, imgs_h, proj_h, dv_h)
+        ref_out = oracle.cascade_forward(sd, cfg, imgs_h, proj_h, dv_h)
         t0 = time.perf_counter()
         for _ in range(args.cpu_baseline_steps):
             oracle.cascade_forward(sd, cfg, imgs_h, proj_h, dv_h)
         dt = (time.perf_counter() - t0) / args.cpu_baseline_steps
         cpu_base = {"value": B / dt, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{args.cpu_baseline_steps} full forwards of the same frame after 1 warm-up (oracle port, torch CPU fp32)"}
+        # the oracle as CHECKER: the frame the timed loop produced (same inputs, same weights) against the oracle's
+        parity = cascade_parity(step_resident(), ref_out)
+
+    eager, extra = None, None
+    if rank == 0 and world == 1 and not args.quick:
+        eager = gpu_eager_baseline(model, imgs_d, proj_d, dv_d, flush)
+        extra = extra_legs(model, dev, flush)
+        graphed, model.use_cuda_graph = model.use_cuda_graph, False  # cfg2 through eager launches (no CUDA graph)
+        ms, best = _time_forward(step_resident, 10, flush)
+        model.use_cuda_graph = graphed
+        extra["no_cuda_graph"] = {"ms_per_step": ms, "min_ms": best, "value": B / (ms * 1e-3)}
+
+    multi = None
+    if world > 1 and not args.quick and P == 1:
+        multi = multi_gpu_legs(args, rank, world, dev, flush)
 
     if rank == 0:
         h2d = sum(t.numel() * 4 for t in imgs_p) + sum(v.numel() * 4 for v in proj_p.values()) + dv_p.numel() * 4
@@ -475,7 +669,12 @@ def main():
                     "serial_value": frames * B / (ms_e2e_serial / args.steps * 1e-3), "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 2 * B * H * W * 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_tensor": roof_tc, "cpu_baseline": cpu_base,
+            "step_stats": step_stats, "parity": parity, "gpu_eager_baseline": eager, "extra": extra,
+            **({} if multi is None else multi),
         }))
+        if parity is not None and not parity["ok"]:
+            sys.stdout.flush()
+            raise SystemExit("bench.py: the benchmarked frame does not match the oracle: " + json.dumps(parity))
     if world > 1:
         dist.destroy_process_group()
 

@@ -101,6 +101,9 @@ int mvster_et_fuse_f32(const float* ref, const float* const* src_host, int V, co
  * mvs4net_utils.py:1060 applied after the partials were all-reduced. */
 int mvster_et_normalize_f32(float* cost, const float* wsum, int B, int G, int D, int H, int W,
                             mvster_stream_t stream);
+/* Name of the kernel the last mvster_et_fuse_f32 call of this thread dispatched to (never NULL; "" before the first call):
+ * what a benchmark prints next to the time it measured, instead of guessing from environment switches. */
+const char* mvster_et_last_kernel(void);
 
 /* Backward of mvster_et_fuse_f32 (group correlation, attn_fuse_d) for training: what autograd derives through
  * mvs4net_utils.py:1037-1060 and homo_warping :13-59.  The sampling grid is built under torch.no_grad() (:23) and the
@@ -164,8 +167,9 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
  * accuracy (22-bit operands) for |x|, |w| < 65504. */
 #define MVSTER_TC3_FP16X2 256
 /* The generation-3 kernel is persistent (one CTA per SM for the whole launch): the grid size is how much of the GPU a launch
- * claims.  mvster_set_sm_budget(n) caps the grid of the mvster_*_tc3_* launches that follow, process-wide (0 = all SMs, the
- * default) - the one piece of state besides the error string and the launch counter.  Used by the host to run the small
+ * claims.  mvster_set_sm_budget(n) caps the grid of the mvster_*_tc3_* launches that follow FROM THE CALLING THREAD (thread-local
+ * like the error string; 0 = all SMs, the default): replicas driven by different host threads (nn.DataParallel) do not see each
+ * other's cap.  The SM count is that of the calling thread's current device.  Used by the host to run the small
  * early cascade stages on a second stream next to the feature pyramid's large layers. */
 void mvster_set_sm_budget(int n);
 int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw);

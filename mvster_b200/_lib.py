@@ -32,6 +32,7 @@ SIGNATURES = {
     "mvster_pose_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mvster_et_fuse_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
     "mvster_et_normalize_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "mvster_et_last_kernel": (C.c_char_p, []),
     "mvster_et_fuse_bwd_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _p, _p, C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
     "mvster_conv3d_ndhwc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_conv3d_tc_supported": (_i, [_i, _i, _i, _i, _i]),

@@ -138,6 +138,11 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
     return cost
 
 
+def et_last_kernel() -> str:
+    """Kernel the last ``et_fuse`` call of this thread was dispatched to (mvster_et_last_kernel)."""
+    return _lib.load().mvster_et_last_kernel().decode()
+
+
 def et_normalize(cost: Tensor, wsum: Tensor) -> Tensor:
     B, D, H, W, G = cost.shape
     _chk(cost, "cost")

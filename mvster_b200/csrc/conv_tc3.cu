@@ -545,7 +545,23 @@ static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[6]
 // Persistent CTAs keep their SM for the whole launch, so the grid size is also how much of the GPU a launch claims.
 // mvster_set_sm_budget(n) caps the grid of the launches that follow (0 = every SM): the host uses it to run the small
 // early cascade stages on a second stream next to the feature pyramid's large layers (engine.py).
-static int g_sm_budget = 0;
+// Thread-local: under nn.DataParallel (test_mvs4.py:196) every replica drives its own device from its own host thread, and a
+// cap set by one replica must not leak into another replica's launches (or into a CUDA-graph capture running beside it).
+static thread_local int g_sm_budget = 0;
+
+// SM count of the CURRENT device (replicas may sit on different devices; cached per device id).
+static int current_sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cache[dev];
+    if (!n) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = n;
+    }
+    return n;
+}
 
 template <int NC, int NS, bool MG = false>
 static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st) {
@@ -621,12 +637,7 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     MVSTER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)x & 15) == 0, "mvster_conv_tc3_f32: x and w_packed must be 16-byte aligned");
     EncodeTiledFn enc = encode_fn();
     MVSTER_REQUIRE(enc, "mvster_conv_tc3_f32: cuTensorMapEncodeTiled is unavailable in this driver");
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = tc3::current_sm_count();
     const int s = stride_hw;
     CUtensorMap xm;
     static const bool want_merge = getenv("MVSTER_TC3_MERGE") && atoi(getenv("MVSTER_TC3_MERGE")) != 0;
@@ -725,12 +736,7 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
     MVSTER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)x & 15) == 0, "mvster_deconv_tc3_f32: x and w_packed must be 16-byte aligned");
     EncodeTiledFn enc = encode_fn();
     MVSTER_REQUIRE(enc, "mvster_deconv_tc3_f32: cuTensorMapEncodeTiled is unavailable in this driver");
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = tc3::current_sm_count();
     CUtensorMap xm;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * D};

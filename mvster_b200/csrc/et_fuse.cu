@@ -23,6 +23,12 @@
 
 namespace mvster {
 
+// name of the kernel the last mvster_et_fuse_f32 call of this thread dispatched to (mvster_et_last_kernel)
+static thread_local char g_et_kernel[112] = "";
+static void note_et_kernel(const char* family, int C, int G, int D, int lpp, int mb) {
+    snprintf(g_et_kernel, sizeof g_et_kernel, "%s<C=%d,G=%d,D=%d,LPP=%d,MB=%d>", family, C, G, D, lpp, mb);
+}
+
 template <int N>
 __device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[N]) {
     if constexpr (N % 4 == 0) {
@@ -203,6 +209,7 @@ static int launch_et(const EtArgs& a, cudaStream_t st) {
     const long long threads = (long long)a.B * a.H * a.W * G;
     if (a.flags & MVSTER_ET_SQDIFF) et_fuse_kernel<CPG, G, D, false><<<ceil_div(threads, 256), 256, 0, st>>>(a);
     else et_fuse_kernel<CPG, G, D, true><<<ceil_div(threads, 256), 256, 0, st>>>(a);
+    note_et_kernel("et_fuse_kernel", CPG * G, G, D, G, 0);
     return check_launch("et_fuse_kernel");
 }
 
@@ -266,6 +273,8 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     if (plain && try_launch_tiled(a, C, G, D, st, &rc)) return rc;   // D = 8 stages: hypotheses unrolled per lane
     return G == 4 ? dispatch_cpg<4>(a, C / G, D, st) : dispatch_cpg<8>(a, C / G, D, st);
 }
+
+extern "C" const char* mvster_et_last_kernel(void) { return g_et_kernel; }
 
 extern "C" int mvster_et_normalize_f32(float* cost, const float* wsum, int B, int G, int D, int H, int W,
                                        mvster_stream_t stream) {

@@ -151,6 +151,7 @@ template <int C, int G, int LPP>
 static int launch_et_dlane(const EtArgs& a, cudaStream_t st) {
     dim3 grid(ceil_div(a.W, 32 / (4 * LPP)), ceil_div(a.H, 4), a.B);
     et_fuse_dlane_kernel<C, G, LPP><<<grid, 128, 0, st>>>(a);
+    note_et_kernel("et_fuse_dlane_kernel", C, G, 4, LPP, 0);
     return check_launch("et_fuse_dlane_kernel");
 }
 

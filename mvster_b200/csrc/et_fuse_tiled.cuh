@@ -269,6 +269,7 @@ template <int C, int G, int D, int LPP, int MB>
 static int launch_et_tiled(const EtArgs& a, cudaStream_t st) {
     dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 4), a.B);
     et_fuse_tiled_kernel<C, G, D, LPP, MB><<<grid, 128, 0, st>>>(a);
+    note_et_kernel("et_fuse_tiled_kernel", C, G, D, LPP, MB);
     return check_launch("et_fuse_tiled_kernel");
 }
 

@@ -44,6 +44,16 @@ def check_supported(net) -> None:
             bad.append(f"stage_splits[{k}]={net.stage_splits[k]} (4 or 8)")
         if net.group_cor and net.group_cor_dim[k] not in (4, 8):
             bad.append(f"group_cor_dim[{k}]={net.group_cor_dim[k]} (4 or 8)")
+    # widths the kernels and the weight packers are built for (the reference itself breaks for reg_channel != 8:
+    # reg2d.prob hard-codes 8 input channels, mvs4net_utils.py:900)
+    if getattr(net.feature, "base_channels", 8) != 8 and getattr(net, "fpn_backend", "native") == "native":
+        bad.append(f"fpn_base_channel={net.feature.base_channels} with the native feature pyramid (8; set fpn_backend='torch')")
+    if list(net.feature.out_channels[:4]) != [64, 32, 16, 8]:
+        bad.append(f"feature.out_channels={list(net.feature.out_channels)} ([64, 32, 16, 8])")
+    reg0 = net.reg[0] if len(net.reg) else None
+    base = getattr(getattr(getattr(reg0, "conv0", None), "conv", None), "out_channels", 8)
+    if base != 8:
+        bad.append(f"reg_channel={base} (8)")
     if bad:
         raise NotImplementedError("the CUDA inference path does not cover: " + ", ".join(bad))
 
@@ -66,6 +76,31 @@ def check_inputs(net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], 
             raise ValueError(f"proj_matrices['{key}'] must be [B={B}, Nv={len(imgs)}, 2, 4, 4], got {got}")
     if depth_values.dim() != 2 or depth_values.shape[0] != B or depth_values.shape[1] < 2:
         raise ValueError(f"depth_values must be [B={B}, >= 2], got {tuple(depth_values.shape)}")
+
+
+def _copy_outputs(out: Dict) -> Dict:
+    """Fresh tensors for every distinct tensor of an output dict (one multi-tensor copy); entries that alias each other in
+    ``out`` (the top-level keys and ``stage4``'s, MVS4Net.py:104-105) alias each other in the result."""
+    memo: Dict[int, Tensor] = {}
+    srcs: List[Tensor] = []
+    dsts: List[Tensor] = []
+
+    def dup(v):
+        if isinstance(v, dict):
+            return {k: dup(x) for k, x in v.items()}
+        if not torch.is_tensor(v):
+            return v
+        got = memo.get(id(v))
+        if got is None:
+            got = memo[id(v)] = torch.empty_like(v)  # preserve_format: the permuted mono_feat view keeps its strides
+            srcs.append(v)
+            dsts.append(got)
+        return got
+
+    res = dup(out)
+    if srcs:
+        torch._foreach_copy_(dsts, srcs)
+    return res
 
 
 class InferenceEngine:
@@ -138,16 +173,22 @@ class InferenceEngine:
             feats = [[f[i * B:(i + 1) * B] for i in range(len(own))] for f in nhwc]
             return self.run_cascade(net, feats, proj_matrices, depth_values, shard=shard)
 
-    # ------------------------------------------------------------------ CUDA-graph replay (opt-in)
-    def forward_graphed(self, net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor) -> Dict:
-        """Capture the whole forward (feature pyramid + 4-stage cascade, ~60-200 launches) into one CUDA graph
-        per input signature and replay it: removes the per-launch host overhead and the inter-kernel gaps.
-        Inputs are copied into static buffers; the returned tensors are the graph's static outputs and stay
-        valid until the next call with the same signature (``test_mvs4.py`` converts to numpy right away)."""
+    # ------------------------------------------------------------------ CUDA-graph replay (the default inference path)
+    def forward_graphed(self, net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
+                        shard=None) -> Dict:
+        """Capture the whole forward (feature pyramid + 4-stage cascade, ~80 launches, plus the per-stage NCCL all-reduce of a
+        view-sharded run) into one CUDA graph per input signature and replay it: removes the per-launch host overhead and the
+        inter-kernel gaps.  Inputs are copied into static buffers.  The graph's outputs are static buffers too; by default the
+        caller gets COPIES (one fused multi-tensor copy after the replay, aliasing between the top-level and the ``stage4``
+        entries preserved), so results stay valid across calls like the reference's; ``net.graph_static_outputs = True`` returns
+        the static buffers themselves (valid until the next call with the same signature - what a serving loop that consumes
+        each frame before requesting the next one wants).  Capture uses the thread-local error mode: nn.DataParallel replicas
+        (test_mvs4.py:196) capture and replay from their own host threads."""
         key = (tuple(tuple(t.shape) for t in imgs), tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
                tuple(depth_values.shape), self.weights_version, self._precision(net, "reg"),
                getattr(net, "tc_kernel_gen", 1), getattr(net, "fpn_backend", "torch"), self._precision(net, "fpn"),
-               getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"))
+               getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"),
+               None if shard is None else (shard.first_view, shard.count, shard.parts, id(shard.group)))
         entry = self._graphs.get(key)
         if entry is None:
             with torch.cuda.device(self.device):
@@ -158,22 +199,25 @@ class InferenceEngine:
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):  # warm-up outside capture: cuDNN autotune, lazy module loads, func attributes
                     for _ in range(2):
-                        self.forward(net, s_imgs, s_proj, s_dv)
+                        self.forward(net, s_imgs, s_proj, s_dv, shard=shard)
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    out = self.forward(net, s_imgs, s_proj, s_dv)
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out = self.forward(net, s_imgs, s_proj, s_dv, shard=shard)
             entry = self._graphs[key] = (graph, s_imgs, s_proj, s_dv, out)
             if len(self._graphs) > 4:  # keep the cache small: each graph pins its own workspace
                 self._graphs.pop(next(iter(self._graphs)))
         graph, s_imgs, s_proj, s_dv, out = entry
-        for dst, src in zip(s_imgs, imgs):
-            dst.copy_(src, non_blocking=True)
-        for k, dst in s_proj.items():
-            dst.copy_(proj_matrices[k], non_blocking=True)
-        s_dv.copy_(depth_values, non_blocking=True)
-        graph.replay()
-        return out
+        with torch.cuda.device(self.device):
+            for dst, src in zip(s_imgs, imgs):
+                dst.copy_(src, non_blocking=True)
+            for k, dst in s_proj.items():
+                dst.copy_(proj_matrices[k], non_blocking=True)
+            s_dv.copy_(depth_values, non_blocking=True)
+            graph.replay()
+            if getattr(net, "graph_static_outputs", False):
+                return out
+            return _copy_outputs(out)
 
     # ------------------------------------------------------------------ the hot path
     def _aggregate(self, p: StagePlan, ref: Tensor, srcs: List[Tensor], proj: Tensor, hypo: Tensor, temp: float,

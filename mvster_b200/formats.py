@@ -32,7 +32,7 @@ def read_pfm(filename: str) -> Tuple[np.ndarray, float]:
         scale = float(f.readline().rstrip())
         endian = "<" if scale < 0 else ">"
         scale = abs(scale)
-        data = np.frombuffer(f.read(), dtype=endian + "f4")
+        data = np.frombuffer(f.read(), dtype=endian + "f4").copy()  # writable, like the reference's np.fromfile
     shape = (height, width, 3) if color else (height, width)
     if data.size != int(np.prod(shape)):
         raise Exception(f"PFM payload holds {data.size} floats, header says {shape}")

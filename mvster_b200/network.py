@@ -199,7 +199,7 @@ class stagenet(nn.Module):
         if self.vis_ETA:
             raise NotImplementedError("vis_ETA debug dumps are not part of this implementation")
         kernels = train_ops.enabled_by_default() if self.train_et is None else self.train_et
-        if kernels and train_ops.usable(features) and group_cor and self.attn_fuse_d:
+        if kernels and group_cor and self.attn_fuse_d and train_ops.usable(features, group_cor_dim, depth_hypo.shape[1]):
             cost = train_ops.aggregate(features, proj_matrices, depth_hypo, group_cor_dim, self.attn_temp)
         else:
             cost = tp.aggregate(features, proj_matrices, depth_hypo, group_cor, group_cor_dim, self.attn_temp, self.attn_fuse_d)
@@ -270,8 +270,11 @@ class MVS4net(nn.Module):
         self.fpn_precision = os.environ.get("MVSTER_FPN_PRECISION", "2xfp16")
         # run cascade stages 1-3 on a second stream next to the feature pyramid's last levels (engine._forward_overlapped)
         self.overlap_stages = os.environ.get("MVSTER_OVERLAP", "1") == "1"
-        # replay the whole inference forward as one CUDA graph (outputs are then static buffers, valid until the next call)
-        self.use_cuda_graph = os.environ.get("MVSTER_CUDA_GRAPH", "0") == "1"
+        # replay the whole inference forward as one CUDA graph per input signature (engine.forward_graphed; MVSTER_CUDA_GRAPH=0 =
+        # eager launches).  Results are returned as copies unless graph_static_outputs is set (then they are the graph's static
+        # buffers, valid until the next call with the same signature).
+        self.use_cuda_graph = os.environ.get("MVSTER_CUDA_GRAPH", "1") == "1"
+        self.graph_static_outputs = os.environ.get("MVSTER_GRAPH_STATIC_OUTPUTS", "0") == "1"
         self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)
 
     def set_view_shard(self, shard) -> None:
@@ -314,8 +317,8 @@ class MVS4net(nn.Module):
             if eng.weights_version != self._weights_version:
                 eng.refresh_weights(self)
                 eng.weights_version = self._weights_version
-            if self.use_cuda_graph and self._view_shard is None:
-                return eng.forward_graphed(self, imgs, proj_matrices, depth_values)
+            if self.use_cuda_graph and (self._view_shard is None or os.environ.get("MVSTER_SHARD_GRAPH", "1") == "1"):
+                return eng.forward_graphed(self, imgs, proj_matrices, depth_values, shard=self._view_shard)
             return eng.forward(self, imgs, proj_matrices, depth_values, shard=self._view_shard)
         return self._forward_autograd(imgs, proj_matrices, depth_values, filename)
 

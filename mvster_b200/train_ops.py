@@ -20,14 +20,29 @@ from torch import Tensor
 from . import capi
 
 
+def _on(device):
+    """Make ``device`` current for the launches inside (they go to its current stream); a no-op for host tensors, which only
+    the test emulation of the kernels passes."""
+    import contextlib
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()
+
+
 def enabled_by_default() -> bool:
     """MVSTER_TRAIN_ET=1 routes the training-mode aggregation of CUDA tensors through the kernels (default: PyTorch ops)."""
     return os.environ.get("MVSTER_TRAIN_ET", "0") == "1"
 
 
-def usable(features: Sequence[Tensor]) -> bool:
-    """The kernels take fp32 CUDA feature maps; anything else stays on the PyTorch formulation."""
-    return all(f.is_cuda and f.dtype == torch.float32 for f in features)
+def usable(features: Sequence[Tensor], G: int = 0, D: int = 0) -> bool:
+    """The kernels take fp32 CUDA feature maps in the shape classes mvster_et_fuse_bwd_f32 is instantiated for
+    (G in {4, 8}, C/G in {1, 2, 4, 8}, D in {4, 8}; pass G / D to have them checked); anything else stays on the PyTorch
+    formulation instead of raising from inside a training step."""
+    if not all(f.is_cuda and f.dtype == torch.float32 for f in features):
+        return False
+    if G:
+        C = features[0].shape[1]
+        if G not in (4, 8) or C % G or C // G not in (1, 2, 4, 8):
+            return False
+    return D in (0, 4, 8)
 
 
 class EtFuse(torch.autograd.Function):
@@ -38,8 +53,9 @@ class EtFuse(torch.autograd.Function):
         B, H, W, _ = ref.shape
         D = hypo.shape[1]
         wsum = torch.empty((B, D, H, W), device=ref.device, dtype=torch.float32)
-        cost = capi.et_fuse(ref, srcs, pose, hypo, G, attn_temp, wsum=wsum, partial=True)
-        capi.et_normalize(cost, wsum)
+        with _on(ref.device):  # launch on the tensors' device and its current stream, whatever is current
+            cost = capi.et_fuse(ref, srcs, pose, hypo, G, attn_temp, wsum=wsum, partial=True)
+            capi.et_normalize(cost, wsum)
         ctx.save_for_backward(pose, hypo, cost, wsum, ref, *srcs)
         ctx.attn_temp = attn_temp
         return cost
@@ -50,8 +66,9 @@ class EtFuse(torch.autograd.Function):
         need = ctx.needs_input_grad[4:]
         if not any(need):
             return (None,) * (4 + 1 + len(srcs))
-        grad_ref, grad_src = capi.et_fuse_bwd(ref, srcs, pose, hypo, cost, wsum, grad_cost.contiguous(), ctx.attn_temp,
-                                              need_src=need[1:])
+        with _on(ref.device):
+            grad_ref, grad_src = capi.et_fuse_bwd(ref, srcs, pose, hypo, cost, wsum, grad_cost.contiguous(), ctx.attn_temp,
+                                                  need_src=need[1:])
         return (None, None, None, None, grad_ref if need[0] else None, *grad_src)
 
 
@@ -59,7 +76,7 @@ def aggregate(features: Sequence[Tensor], cams: Tensor, hypo: Tensor, G: int, at
     """Differentiable drop-in for ``torch_path.aggregate(..., group_cor=True, attn_fuse_d=True)``: features Nv x [B,C,H,W]
     (view 0 = reference), cams [B,Nv,2,4,4], hypo [B,D,H,W] -> cost [B,G,D,H,W] (a permuted view of the kernel's
     channels-last volume)."""
-    with torch.no_grad():
+    with torch.no_grad(), _on(features[0].device):
         pose = capi.pose(cams.contiguous().float())
         hypo = hypo.detach().contiguous().float()
     nhwc = [f.permute(0, 2, 3, 1).contiguous() for f in features]

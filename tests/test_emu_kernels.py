@@ -214,7 +214,7 @@ def test_training_step_with_kernels_on_cpu_matches_pytorch_ops(emu, monkeypatch)
     """MVS4net in train mode (mono decoder, OT + L1 loss): parameter gradients with the aggregation on the fused kernels
     (forward + backward, emulated) against the all-PyTorch formulation."""
     from mvster_b200 import MVS4net_loss, train_ops
-    monkeypatch.setattr(train_ops, "usable", lambda feats: True)
+    monkeypatch.setattr(train_ops, "usable", lambda feats, G=0, D=0: True)
     model = build_model(SHIPPED, seed=3).train()
     for m in model.modules():
         if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):

@@ -1,0 +1,76 @@
+"""Oracle parity AT THE BENCHMARKED SIZES (VERDICT r01 "weak" #1): `MVS4net.forward` on the GPU against
+`oracle.cascade_forward` (the CPU restatement pinned to the unmodified reference) for BASELINE cfg2 (5 views, 512x640) and the
+cfg4 frame (9 source views, 512x640), plus the per-stage teacher-forced cost volume / probabilities at full size.  These are
+the sizes where 32-bit tap offsets, the window kernel's fallback rate, tile counts that do not divide the SM count and the
+resident-weight thresholds of the tensor-core convolutions actually come into play.
+reference: models/MVS4Net.py:60-111, models/mvs4net_utils.py:1012-1094."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import SHIPPED, build_model, oracle, oracle_cfg, top2_gap
+from test_gpu_parity import DEV, from_ndhwc, nhwc, record
+from oracle.compare import cascade_parity
+
+from mvster_b200 import capi, packing, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nv,graph", [(5, False), (5, True), (10, False)], ids=["cfg2_5view", "cfg2_5view_graph", "cfg4_9src"])
+def test_forward_against_oracle_at_bench_size(nv, graph):
+    H, W = 512, 640
+    imgs, proj, dv = synth.make_inputs(1, nv, H, W, seed=0)
+    m = build_model(SHIPPED, 0)
+    ref = oracle.cascade_forward(m.state_dict(), oracle_cfg(SHIPPED), imgs, proj, dv)
+    m = m.to(DEV)
+    m.use_cuda_graph = graph
+    with torch.no_grad():
+        out = m([t.to(DEV) for t in imgs], {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV))
+        if graph:  # second replay of the captured graph must give the same frame
+            out = {k: ({kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} if isinstance(v, dict) else v)
+                   for k, v in out.items()}
+            out2 = m([t.to(DEV) for t in imgs], {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV))
+            assert torch.equal(out2["stage4"]["depth"], out["stage4"]["depth"])
+    torch.cuda.synchronize()
+    rep = cascade_parity(out, ref)
+    record(f"fullsize_nv{nv}_{H}x{W}{'_graph' if graph else ''}", **{k: v for k, v in rep.items() if k != "criterion"})
+    assert rep["ok"], rep
+
+
+@pytest.mark.parametrize("nv", [5, 10], ids=["cfg2_5view", "cfg4_9src"])
+def test_teacher_forced_cost_and_probabilities_at_bench_size(nv):
+    """Per stage, the ORACLE's features and hypotheses go through the warp + ET kernel and the default (tensor-core) regulariser
+    at 512x640: cost volume <= 2e-4 of max against the oracle, winner-take-all depth equal on every tie-free pixel."""
+    H, W = 512, 640
+    imgs, proj, dv = synth.make_inputs(1, nv, H, W, seed=0)
+    sd = build_model(SHIPPED, 0).state_dict()
+    cfg = oracle_cfg(SHIPPED)
+    with torch.no_grad():
+        feats = [oracle.fpn4_features(sd, im) for im in imgs]
+        ref = oracle.cascade_forward(sd, cfg, imgs, proj, dv, features=feats)
+    failures = []
+    for k in range(4):
+        key = f"stage{k + 1}"
+        G = cfg["group_cor_dim"][k]
+        hypo = ref[key]["hypo_depth"].to(DEV)
+        f = [nhwc(ft[key]) for ft in feats]
+        cost = capi.et_fuse(f[0], f[1:], capi.pose(proj[key].to(DEV)), hypo, G, 2.0)
+        want = ref[key]["cost"]
+        cerr = (from_ndhwc(cost) - want).abs().max().item() / want.abs().max().item()
+        packed = packing.pack_reg2d(sd, f"reg.{k}", capi.reg2d_layer_table(G))
+        feat8 = capi.reg2d(packed["blob"].to(DEV), cost, tc_blob=packed["tc3h_blob"].to(DEV), kernel_gen=3, split=2)
+        h = capi.head(hypo, cfg["depth_interals_ratio"][k], feat8=feat8, prob_w=packed["prob_w"].to(DEV), prob_b=packed["prob_b"].to(DEV))
+        aerr = (h["attn_weight"].cpu() - ref[key]["attn_weight"]).abs().max().item()
+        stable = top2_gap(ref[key]["attn_weight"]) > 1e-3
+        d, rd = h["depth"].cpu(), ref[key]["depth"]
+        bad = (((d - rd).abs() > 1e-4 * rd) & stable).float().mean().item()
+        record(f"fullsize_teacher_forced_nv{nv}_{key}", cost_vs_oracle=cerr, attn_vs_oracle=aerr, depth_bad_stable=bad,
+               stable_frac=stable.float().mean().item())
+        if cerr > 2e-4:
+            failures.append(f"{key}: cost volume {cerr:.2e} of max")
+        if aerr > 3e-3:
+            failures.append(f"{key}: probabilities differ by {aerr:.2e}")
+        if bad != 0.0:
+            failures.append(f"{key}: {bad:.4%} of tie-free pixels disagree on depth")
+    assert not failures, "; ".join(failures)

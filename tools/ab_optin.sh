@@ -14,7 +14,7 @@ import json
 for r in json.load(open('gpurun_out/glue_ab.json'))['rows']: print('%-42s %-22s %8.2f us %8.1f GB/s  dev %.1e' % (r['kernel'], r['switch'], r['us'], r['GB/s'], r['max_dev_vs_default']))"
 echo "== bench step (ms) per switch"
 for sw in "" "MVSTER_TC3_MERGE=1" "MVSTER_FPN_GATHER=2" "MVSTER_FPN_GATHER=3" "MVSTER_FPN_MERGE=2" "MVSTER_FPN_MERGE=3" "MVSTER_CONV_FIRST=2" "MVSTER_CONV0_PX4=1" "MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1" "MVSTER_TC3_MERGE=1 MVSTER_FPN_GATHER=3 MVSTER_FPN_MERGE=3 MVSTER_CONV_FIRST=2 MVSTER_CONV0_PX4=1"; do
-  out=$(env $sw timeout 200 python bench.py --no-cpu-baseline 2>/dev/null)
+  out=$(env $sw timeout 200 python bench.py --no-cpu-baseline --quick 2>/dev/null)
   echo "$out" | python -c "
 import json,sys
 j=json.loads(sys.stdin.read()); print('%-70s %.4f ms  %.1f maps/s  e2e %.1f' % ('[$sw]', j['ms_per_step'], j['value'], j['e2e']['value']))"
