@@ -48,6 +48,8 @@ typedef void* mvster_stream_t; /* cudaStream_t */
 #define MVSTER_ET_SQDIFF 16     /* group_cor=False: cost[c] = (ref[c]-warped[c])^2, C cost channels (:1042); pass G == C */
 #define MVSTER_ET_WINDOW 32     /* force the window kernel (correlate, then interpolate) where a specialisation exists */
 #define MVSTER_ET_NO_WINDOW 64  /* never use the window kernel (A/B testing) */
+#define MVSTER_ET_TMA_ON 128    /* force the TMA-staged window kernel (source boxes in shared memory) where a specialisation exists */
+#define MVSTER_ET_TMA_OFF 256   /* never use it: window taps gathered from global memory (A/B testing) */
 
 int mvster_version(void);                 /* 10000*major + 100*minor + patch */
 const char* mvster_last_error(void);      /* thread-local, never NULL */

@@ -20,6 +20,8 @@ ET_NO_FUSE_D = 8
 ET_SQDIFF = 16
 ET_WINDOW = 32
 ET_NO_WINDOW = 64
+ET_TMA_ON = 128
+ET_TMA_OFF = 256
 MAX_VIEWS = 16
 
 
@@ -91,12 +93,13 @@ def pose(proj: Tensor, first_view: int = 1, n_views: Optional[int] = None) -> Te
 def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: int, attn_temp: float,
             cost: Optional[Tensor] = None, wsum: Optional[Tensor] = None, partial: bool = False,
             accumulate: bool = False, generic: bool = False, group_cor: bool = True, fuse_d: bool = True,
-            window: Optional[bool] = None) -> Tensor:
+            window: Optional[bool] = None, tma: Optional[bool] = None) -> Tensor:
     """ref [B,H,W,C], srcs V x [B,Hs,Ws,C], pose [B,V,12], hypo [B,D,H,W] -> cost [B,D,H,W,G].
     With ``partial`` the un-normalised accumulators are written to (cost, wsum).  ``group_cor=False``:
     per-channel squared difference, the cost volume then has C channels (pass G == C);
     ``fuse_d=False``: the reference's attn_fuse_d=False weighting.  ``window``: True / False force / forbid the
-    window kernel (et_fuse_win.cuh); None leaves the choice to the library."""
+    window kernel (et_fuse_win.cuh); ``tma``: True / False force / forbid its TMA-staged form (et_fuse_tma.cuh: source boxes in
+    shared memory); None leaves the choice to the library."""
     B, H, W, Cc = ref.shape
     _chk(ref, "ref")
     V = len(srcs)
@@ -122,6 +125,8 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
             flags |= ET_SQDIFF
         if window is not None:
             flags |= ET_WINDOW if window else ET_NO_WINDOW
+        if tma is not None:
+            flags |= ET_TMA_ON if tma else ET_TMA_OFF
         if partial or V > MAX_VIEWS:  # a chain stays un-normalised to its end: the division (with the 1e-8 seed) follows once
             flags |= ET_PARTIAL
         if accumulate or v0 > 0:

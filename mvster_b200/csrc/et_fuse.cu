@@ -20,6 +20,7 @@
 #include "et_args.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace mvster {
 
@@ -202,6 +203,7 @@ __global__ void et_normalize_kernel(float* __restrict__ cost, const float* __res
 #include "et_fuse_tiled.cuh"
 #include "et_fuse_dlane.cuh"
 #include "et_fuse_win.cuh"
+#include "et_fuse_tma.cuh"
 namespace mvster {
 
 template <int CPG, int G, int D>
@@ -268,7 +270,9 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     int rc = MVSTER_OK;
     const bool plain = !(flags & (MVSTER_ET_GENERIC | MVSTER_ET_SQDIFF | MVSTER_ET_NO_FUSE_D));
     const bool window = (flags & MVSTER_ET_NO_WINDOW) ? false : (flags & MVSTER_ET_WINDOW) ? true : et_window_default();
-    if (plain && window && try_launch_win(a, C, G, D, st, &rc)) return rc;  // stages 2-4: shared 3 x 3 tap window
+    const bool tma = (flags & MVSTER_ET_TMA_OFF) ? false : (flags & MVSTER_ET_TMA_ON) ? true : ettma::et_tma_default();
+    if (plain && window && tma && ettma::try_launch_tma(a, C, G, D, st, &rc)) return rc;  // stages 2-4: TMA-staged source boxes
+    if (plain && window && try_launch_win(a, C, G, D, st, &rc)) return rc;  // same arithmetic, taps gathered from global memory
     if (plain && try_launch_dlane(a, C, G, D, st, &rc)) return rc;   // D = 4 stages: hypotheses across lanes
     if (plain && try_launch_tiled(a, C, G, D, st, &rc)) return rc;   // D = 8 stages: hypotheses unrolled per lane
     return G == 4 ? dispatch_cpg<4>(a, C / G, D, st) : dispatch_cpg<8>(a, C / G, D, st);

@@ -11,6 +11,7 @@ Configuration coverage: reg2d and reg3d; group correlation and per-channel squar
 from __future__ import annotations
 
 import os
+import threading
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -18,6 +19,9 @@ import torch
 from . import _lib, capi, fpn_engine, packing
 
 Tensor = torch.Tensor
+# One CUDA-graph capture at a time per process: replicas driven by different host threads (nn.DataParallel) may replay
+# concurrently, but two captures running side by side trip over each other in the caching allocator.
+_CAPTURE_LOCK = threading.Lock()
 REG3D_DOWN = (3, 3, 2, 2)  # MVS4Net.py:48
 
 
@@ -191,7 +195,7 @@ class InferenceEngine:
                None if shard is None else (shard.first_view, shard.count, shard.parts, id(shard.group)))
         entry = self._graphs.get(key)
         if entry is None:
-            with torch.cuda.device(self.device):
+            with _CAPTURE_LOCK, torch.cuda.device(self.device):
                 s_imgs = [t.detach().to(self.device, torch.float32).clone() for t in imgs]
                 s_proj = {k: v.detach().to(self.device, torch.float32).clone() for k, v in proj_matrices.items()}
                 s_dv = depth_values.detach().to(self.device, torch.float32).clone()

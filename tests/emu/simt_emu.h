@@ -13,6 +13,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -28,6 +29,8 @@
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
+struct alignas(16) int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 inline float2 make_float2(float x, float y) { return {x, y}; }
 inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
@@ -57,6 +60,7 @@ inline thread_local uint3 threadIdx, blockIdx;
 inline thread_local dim3 blockDim, gridDim;
 
 inline void __syncthreads() { emu::ctx.block->arrive_and_wait(); }
+inline void __syncwarp() { emu::ctx.warp->bar.arrive_and_wait(); }
 inline bool __all_sync(unsigned, bool p) {
     emu::Warp& w = *emu::ctx.warp;
     w.vote[emu::ctx.lane] = p;

@@ -125,8 +125,50 @@ def test_window_kernel_on_cpu_matches_oracle(emu, case):
     B, nv, C_, G, D, H, W, step, span = case
     feats, cams, hypo = narrow_et_inputs(B, nv, C_, D, H, W, step, span, seed=13)
     want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0)
-    got = from_ndhwc(capi.et_fuse(nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams), hypo, G, 2.0, window=True))
-    assert torch.isfinite(got).all() and (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
+    for tma in (False, True):  # taps gathered from global memory / from TMA-staged boxes in shared memory
+        got = from_ndhwc(capi.et_fuse(nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams), hypo, G, 2.0, window=True, tma=tma))
+        assert ("tma" in capi.et_last_kernel()) == tma, capi.et_last_kernel()
+        assert torch.isfinite(got).all() and (got - want).abs().max().item() <= 2e-4 * want.abs().max().item(), tma
+
+
+TMA_CASES = [  # (B, nv, C, G, D, H, W, step_deg, rel_span): several tiles per CTA, ragged tiles, batch > 1, more views than box slots
+    (1, 6, 8, 4, 4, 37, 70, 1.0, 0.12),
+    (2, 3, 8, 4, 4, 16, 40, 2.0, 0.3),
+    (1, 5, 16, 4, 4, 17, 48, 1.5, 0.2),
+    (2, 4, 32, 8, 8, 7, 33, 3.0, 0.06),
+]
+
+
+@pytest.mark.parametrize("case", TMA_CASES)
+def test_tma_staged_kernel_on_cpu_matches_oracle(emu, case, monkeypatch):
+    """et_fuse_tma_kernel with the mbarrier / TMA primitives replaced by host twins (same protocol: producer warp, slot ring,
+    swizzled boxes with zero fill): against the oracle, against the global-gather window kernel, in partial + accumulate mode,
+    and with 7-row tiles (two CTAs per SM on the GPU)."""
+    B, nv, C_, G, D, H, W, step, span = case
+    feats, cams, hypo = narrow_et_inputs(B, nv, C_, D, H, W, step, span, seed=17)
+    # a few pixels with hypotheses far outside the narrow band: those warps must take the global-gather path
+    hypo[:, :, 0, :3] *= torch.tensor([1.0, 0.8, 0.6, 0.4] * (D // 4)).reshape(1, D, 1)
+    want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0)
+    scale = want.abs().max().item()
+    ref, srcs, pose = nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams)
+    got = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=True))
+    assert "tma" in capi.et_last_kernel()
+    assert torch.isfinite(got).all() and (got - want).abs().max().item() <= 2e-4 * scale
+    win = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=False))
+    assert (got - win).abs().max().item() <= 2e-5 * scale
+    # view sharding: partial sums of the first views, then accumulate the rest, then normalise
+    k = max(1, (nv - 1) // 2)
+    wsum = torch.empty(B, D, H, W)
+    cost = capi.et_fuse(ref, srcs[:k], pose[:, :k].contiguous(), hypo, G, 2.0, wsum=wsum, partial=True, tma=True)
+    if k < nv - 1:
+        capi.et_fuse(ref, srcs[k:], pose[:, k:].contiguous(), hypo, G, 2.0, cost=cost, wsum=wsum, partial=True, accumulate=True, tma=True)
+    capi.et_normalize(cost, wsum)
+    assert (from_ndhwc(cost) - want).abs().max().item() <= 2e-4 * scale
+    if C_ == 8:
+        monkeypatch.setenv("MVSTER_ET_TMA_TH", "7")
+        got7 = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=True))
+        assert "7x32" in capi.et_last_kernel()
+        assert (got7 - want).abs().max().item() <= 2e-4 * scale
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])

@@ -92,6 +92,7 @@ def test_forward_with_every_variant_on(monkeypatch):
     imgs, proj, dv = synth.make_inputs(1, 3, 128, 192, seed=9)
     imgs, proj, dv = [i.to(DEV) for i in imgs], {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV)
     model = build_model(SHIPPED, seed=5).to(DEV).eval()
+    model.use_cuda_graph = False  # the switches are read at launch time: a replayed graph would keep the default kernels
     with torch.no_grad():
         want = {k: v.clone() for k, v in model(imgs, proj, dv)["stage4"].items() if isinstance(v, torch.Tensor)}
         for k, v in (("MVSTER_FPN_GATHER", "3"), ("MVSTER_FPN_MERGE", "3"), ("MVSTER_CONV_FIRST", "2"), ("MVSTER_CONV0_PX4", "1")):

@@ -21,15 +21,12 @@ from mvster_b200 import capi, synth  # noqa: E402
 
 VARIANTS = [
     ("tiled", dict(MVSTER_ET_WIN="0")),
-    ("win", dict(MVSTER_ET_WIN="1")),
-    ("win_pf1", dict(MVSTER_ET_WIN="1", MVSTER_ET_PREFETCH="1")),
-    ("win_pf2", dict(MVSTER_ET_WIN="1", MVSTER_ET_PREFETCH="2")),
-    ("win_pf3", dict(MVSTER_ET_WIN="1", MVSTER_ET_PREFETCH="3")),
-    ("win_mb5", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_MB="5")),
-    ("win_mb5_pf1", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_MB="5", MVSTER_ET_PREFETCH="1")),
-    ("win_mb5_pf3", dict(MVSTER_ET_WIN="1", MVSTER_ET_WIN_MB="5", MVSTER_ET_PREFETCH="3")),
+    ("tma_15x32", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1")),
+    ("tma_7x32", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7")),
+    ("win", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0")),
+    ("win_mb5", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0", MVSTER_ET_WIN_MB="5")),
 ]
-KEYS = ("MVSTER_ET_WIN", "MVSTER_ET_WIN_MB", "MVSTER_ET_PREFETCH")
+KEYS = ("MVSTER_ET_WIN", "MVSTER_ET_WIN_MB", "MVSTER_ET_PREFETCH", "MVSTER_ET_TMA", "MVSTER_ET_TMA_TH")
 
 
 def main():
@@ -80,7 +77,7 @@ def main():
             row.append({"stage": k + 1, "us": round(t * 1e3, 2), "min_us": round(min(ts) * 1e3, 2),
                         "gbs": round(nbytes / (t * 1e-3) / 1e9, 1), "rel_dev_vs_tiled": dev_max})
         res[name] = row
-        print(name, [r["us"] for r in row], "dev", ["%.1e" % r["rel_dev_vs_tiled"] for r in row], file=sys.stderr)
+        print(name, capi.et_last_kernel(), [r["us"] for r in row], "dev", ["%.1e" % r["rel_dev_vs_tiled"] for r in row], file=sys.stderr)
     print(json.dumps(res))
 
 
