@@ -50,6 +50,13 @@ typedef void* mvster_stream_t; /* cudaStream_t */
 #define MVSTER_ET_NO_WINDOW 64  /* never use the window kernel (A/B testing) */
 #define MVSTER_ET_TMA_ON 128    /* force the TMA-staged window kernel (source boxes in shared memory) where a specialisation exists */
 #define MVSTER_ET_TMA_OFF 256   /* never use it: window taps gathered from global memory (A/B testing) */
+/* ref and src store every aligned block of 8 channels group-interleaved: position p of the block holds channel perm[p] with
+ * perm = {0,2,1,3,4,6,5,7} for C/G = 2 and {0,4,1,5,2,6,3,7} for C/G = 4 (identity for C/G = 8), i.e. a 64-bit pair holds the same
+ * channel index of two neighbouring groups and the group sums need no horizontal adds.  The producer of the features applies
+ * the permutation for free (mvster_b200/fpn_engine.py permutes the output channels of the pyramid's last convolutions when
+ * it packs their weights).  Honoured by the window kernels (TMA-staged or not) for (C, G, D) = (8,4,4), (16,4,4), (32,8,8);
+ * any other kernel rejects it unless C/G = 8.  The cost volume's G channels keep their natural order. */
+#define MVSTER_ET_INTERLEAVED 512
 
 int mvster_version(void);                 /* 10000*major + 100*minor + patch */
 const char* mvster_last_error(void);      /* thread-local, never NULL */

@@ -22,6 +22,7 @@ ET_WINDOW = 32
 ET_NO_WINDOW = 64
 ET_TMA_ON = 128
 ET_TMA_OFF = 256
+ET_INTERLEAVED = 512
 MAX_VIEWS = 16
 
 
@@ -93,13 +94,14 @@ def pose(proj: Tensor, first_view: int = 1, n_views: Optional[int] = None) -> Te
 def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: int, attn_temp: float,
             cost: Optional[Tensor] = None, wsum: Optional[Tensor] = None, partial: bool = False,
             accumulate: bool = False, generic: bool = False, group_cor: bool = True, fuse_d: bool = True,
-            window: Optional[bool] = None, tma: Optional[bool] = None) -> Tensor:
+            window: Optional[bool] = None, tma: Optional[bool] = None, interleaved: bool = False) -> Tensor:
     """ref [B,H,W,C], srcs V x [B,Hs,Ws,C], pose [B,V,12], hypo [B,D,H,W] -> cost [B,D,H,W,G].
     With ``partial`` the un-normalised accumulators are written to (cost, wsum).  ``group_cor=False``:
     per-channel squared difference, the cost volume then has C channels (pass G == C);
     ``fuse_d=False``: the reference's attn_fuse_d=False weighting.  ``window``: True / False force / forbid the
     window kernel (et_fuse_win.cuh); ``tma``: True / False force / forbid its TMA-staged form (et_fuse_tma.cuh: source boxes in
-    shared memory); None leaves the choice to the library."""
+    shared memory); None leaves the choice to the library.  ``interleaved``: ref / srcs store each 8-channel block
+    group-interleaved (MVSTER_ET_INTERLEAVED in include/mvster_b200.h; ``interleave_perm``)."""
     B, H, W, Cc = ref.shape
     _chk(ref, "ref")
     V = len(srcs)
@@ -127,6 +129,8 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
             flags |= ET_WINDOW if window else ET_NO_WINDOW
         if tma is not None:
             flags |= ET_TMA_ON if tma else ET_TMA_OFF
+        if interleaved:
+            flags |= ET_INTERLEAVED
         if partial or V > MAX_VIEWS:  # a chain stays un-normalised to its end: the division (with the 1e-8 seed) follows once
             flags |= ET_PARTIAL
         if accumulate or v0 > 0:
@@ -141,6 +145,15 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
     if V > MAX_VIEWS and not partial:
         et_normalize(cost, wsum)
     return cost
+
+
+def interleave_perm(C: int, G: int) -> List[int]:
+    """Channel stored at each memory position under MVSTER_ET_INTERLEAVED: ``stored[..., p] = natural[..., perm[p]]``."""
+    cpg = C // G
+    block = {2: [0, 2, 1, 3, 4, 6, 5, 7], 4: [0, 4, 1, 5, 2, 6, 3, 7]}.get(cpg)
+    if block is None:
+        return list(range(C))
+    return [8 * (p // 8) + block[p % 8] for p in range(C)]
 
 
 def et_last_kernel() -> str:

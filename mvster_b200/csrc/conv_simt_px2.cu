@@ -219,8 +219,8 @@ int conv_px2(const float* x, const float* w, const float* bias, const float* ski
     a.cout = Cout; a.kd = kd; a.k = k; a.sd = sd; a.s = s; a.relu = relu;
     const char* sw = getenv("MVSTER_CONV_PX2");  // "0" forces the one-pixel kernels (A/B measurements)
     if (sw && sw[0] == '0') return -100;
-    const char* v4 = getenv("MVSTER_CONV0_PX4");
-    if (v4 && v4[0] == '1' && kd == 1 && k == 3 && sd == 1 && s == 1 && Cout == 8 && !skip && Wi % 4 == 0 && (Cin == 4 || Cin == 8) &&
+    const char* v4 = getenv("MVSTER_CONV0_PX4");  // default on (B200: 45.1 -> 38.9 us at stage 4, same bits; profiles/r02_glue_ab.md); "0" = two-pixel kernel
+    if ((!v4 || v4[0] == '1') && kd == 1 && k == 3 && sd == 1 && s == 1 && Cout == 8 && !skip && Wi % 4 == 0 && (Cin == 4 || Cin == 8) &&
         (long long)B * Di * Hi * (Wi / 4) < (1ll << 31)) {
         const long long NP = (long long)B * Di, n = NP * Hi * (Wi / 4);
         if (Cin == 4) conv0_px4_kernel<4><<<ceil_div(n, 128), 128, 0, st>>>(x, w, bias, y, NP, Hi, Wi, relu);

@@ -273,6 +273,9 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     const bool tma = (flags & MVSTER_ET_TMA_OFF) ? false : (flags & MVSTER_ET_TMA_ON) ? true : ettma::et_tma_default();
     if (plain && window && tma && ettma::try_launch_tma(a, C, G, D, st, &rc)) return rc;  // stages 2-4: TMA-staged source boxes
     if (plain && window && try_launch_win(a, C, G, D, st, &rc)) return rc;  // same arithmetic, taps gathered from global memory
+    MVSTER_REQUIRE(!(flags & MVSTER_ET_INTERLEAVED) || C / G == 8,
+                   "mvster_et_fuse_f32: MVSTER_ET_INTERLEAVED is implemented by the window kernels only ((C,G,D) = (8,4,4), (16,4,4), (32,8,8), "
+                   "no GENERIC / NO_WINDOW / SQDIFF / NO_FUSE_D); got C=%d G=%d D=%d flags=%d", C, G, D, flags);
     if (plain && try_launch_dlane(a, C, G, D, st, &rc)) return rc;   // D = 4 stages: hypotheses across lanes
     if (plain && try_launch_tiled(a, C, G, D, st, &rc)) return rc;   // D = 8 stages: hypotheses unrolled per lane
     return G == 4 ? dispatch_cpg<4>(a, C / G, D, st) : dispatch_cpg<8>(a, C / G, D, st);

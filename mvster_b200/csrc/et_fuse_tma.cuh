@@ -30,7 +30,7 @@ namespace mvster {
 namespace ettma {
 
 constexpr int TW = 32;             // reference tile width (pixels); its height TH depends on the channel count (Cfg)
-constexpr int BW = 48;             // source box per (tile, view): BH rows x BW pixels (x C channels)
+constexpr int BW = 56;             // source box per (tile, view): BH rows x BW pixels (x C channels)
 constexpr int RB = 2;              // source rows per TMA op
 constexpr int MAX_SLOT = 3;        // boxes in flight per CTA (Cfg::NSLOT <= MAX_SLOT)
 constexpr int MAXV = 12;           // tensor maps per launch (more views: chained launches through the partial sums)
@@ -104,7 +104,7 @@ __device__ __forceinline__ Pix8 lds_tap(const unsigned char* smem, unsigned a_lo
 template <int C, int LPP, int TH_>
 struct Cfg {
     static constexpr int TH = TH_;
-    static constexpr int BH = TH + (TH >= 6 ? 11 : 9);    // box rows (footprint of TH rows + the depth-dependent shift)
+    static constexpr int BH = TH >= 12 ? TH + 13 : TH >= 6 ? TH + 11 : TH + 9;  // box rows (footprint of TH rows + the depth-dependent shift), even
     static constexpr int NSLOT = LPP == 4 ? 2 : 3;        // boxes in flight per CTA
     static constexpr int NCW = TH * LPP;                  // consumer warps (a warp covers 32 / LPP pixels of one tile row)
     static constexpr int THREADS = (NCW + 1) * 32;        // + the producer warp
@@ -123,36 +123,50 @@ struct Ctrl {
     int4 box[MAX_SLOT];  // x0, y0, rows loaded (0 = no box: consumers gather from global memory), unused
 };
 
-// Producer: footprint of the tile in source view v from its corners at the extreme hypotheses.  Lanes 0..7 evaluate one
-// (corner, depth) each; returns the box through x0 / y0 / rows (rows = 0 when it does not fit or the geometry is degenerate).
-__device__ __forceinline__ void tile_footprint(const float* __restrict__ pose, int lane, float xa, float xb, float ya, float yb,
-                                               float dmin, float dmax, bool depth_ok, int BH, int& x0, int& y0, int& rows) {
-    const float px = (lane & 1) ? xb : xa, py = (lane & 2) ? yb : ya, d = (lane & 4) ? dmax : dmin;
-    const float rx = fmaf(pose[0], px, fmaf(pose[1], py, pose[2]));
-    const float ry = fmaf(pose[3], px, fmaf(pose[4], py, pose[5]));
-    const float rz = fmaf(pose[6], px, fmaf(pose[7], py, pose[8]));
-    const float X = fmaf(rx, d, pose[9]), Y = fmaf(ry, d, pose[10]), Z = fmaf(rz, d, pose[11]);
-    float u = X / Z, w = Y / Z;
-    // monotone only while the denominator keeps its sign over the tile: require Z > 0 at all eight points
-    bool ok = depth_ok && Z > 0.f && fabsf(u) < 1e6f && fabsf(w) < 1e6f;
-    float umin = floorf(u), umax = umin, wmin = floorf(w), wmax = wmin;
+// Producer: footprint of the tile in source view v.  Lane = tile column; for each of its TH pixels the sampling position at
+// the pixel's smallest and largest hypothesis (the position is monotone in the depth), reduced over the warp.  The arithmetic
+// need not match the consumers' bit for bit - they test their own window against the box - so the rotated pixel is advanced
+// row by row and a 1/64-pixel margin absorbs the difference.  rows = 0: no box (footprint larger than the box, depth <= 0,
+// a point behind the source camera, NaN); the consumers then gather from global memory.
+template <int TH>
+__device__ __forceinline__ void tile_footprint(const float* __restrict__ pose, float x, float y0, const float (&dlo)[TH], const float (&dhi)[TH],
+                                               bool depth_ok, int BH, int& x0, int& y0_out, int& rows) {
+    float rx = fmaf(pose[0], x, fmaf(pose[1], y0, pose[2]));
+    float ry = fmaf(pose[3], x, fmaf(pose[4], y0, pose[5]));
+    float rz = fmaf(pose[6], x, fmaf(pose[7], y0, pose[8]));
+    const float tx = pose[9], ty = pose[10], tz = pose[11];
+    float umin = INFINITY, umax = -INFINITY, wmin = INFINITY, wmax = -INFINITY, zmin = INFINITY;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
+    for (int r = 0; r < TH; ++r) {
+        const float za = fmaf(rz, dlo[r], tz), zb = fmaf(rz, dhi[r], tz);
+        const float ia = rcp_approx(za), ib = rcp_approx(zb);
+        const float ua = fmaf(rx, dlo[r], tx) * ia, ub = fmaf(rx, dhi[r], tx) * ib;
+        const float wa = fmaf(ry, dlo[r], ty) * ia, wb = fmaf(ry, dhi[r], ty) * ib;
+        umin = fminf(umin, fminf(ua, ub)); umax = fmaxf(umax, fmaxf(ua, ub));
+        wmin = fminf(wmin, fminf(wa, wb)); wmax = fmaxf(wmax, fmaxf(wa, wb));
+        zmin = fminf(zmin, fminf(za, zb));
+        rx += pose[1]; ry += pose[4]; rz += pose[7];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
         umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
         umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
         wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
         wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-        ok = __shfl_xor_sync(0xffffffffu, ok ? 1.f : 0.f, o) != 0.f && ok;
+        zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
     }
-    // taps floor(u) .. floor(u) + 1 of every sample: columns umin .. umax + 1
-    const float wcols = umax - umin + 2.f, wrows = wmax - wmin + 2.f;
-    ok = ok && wcols <= (float)BW && wrows <= (float)BH;
-    x0 = ok ? (int)umin : 0;
-    y0 = ok ? (int)wmin : 0;
+    // taps floor(u) .. floor(u) + 1 of every sample (the consumers' third column / row is the +1 of a larger floor)
+    const float m = 1.f / 64.f;
+    const float ulo = floorf(umin - m), uhi = floorf(umax + m), wlo = floorf(wmin - m), whi = floorf(wmax + m);
+    const float wcols = uhi - ulo + 2.f, wrows = whi - wlo + 2.f;
+    const bool ok = depth_ok && zmin > 0.f && fabsf(ulo) < 1e6f && fabsf(uhi) < 1e6f && fabsf(wlo) < 1e6f && fabsf(whi) < 1e6f &&
+                    wcols <= (float)BW && wrows <= (float)BH;  // every comparison is false for NaN
+    x0 = ok ? (int)ulo : 0;
+    y0_out = ok ? (int)wlo : 0;
     rows = ok ? (((int)wrows + RB - 1) / RB) * RB : 0;
 }
 
-template <int C, int G, int D, int LPP, int TH_>
+template <int C, int G, int D, int LPP, int TH_, bool IL>
 __global__ void __launch_bounds__(Cfg<C, LPP, TH_>::THREADS, Cfg<C, LPP, TH_>::MIN_CTAS)
 et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_x, int tiles_y, int ntiles) {
     using K = Cfg<C, LPP, TH_>;
@@ -193,29 +207,29 @@ et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_
             const int ty = t2 / tiles_x, tx = t2 % tiles_x;
             const int x_lo = tx * TW, y_lo = ty * TH;
             const int x_hi = min(x_lo + TW, a.W) - 1, y_hi = min(y_lo + TH, a.H) - 1;
-            // depth range of the tile: every hypothesis of every pixel (the producer does not assume a sorted schedule)
-            float dmin = INFINITY, dmax = -INFINITY;
+            // depth range of every pixel of the lane's column (all D hypotheses: no sorted schedule is assumed)
+            float dlo[TH], dhi[TH];
             bool bad = false;
             const float* hp = a.hypo + (long long)b * D * plane;
-            for (int i = lane; i < D * TH * TW; i += 32) {
-                const int d = i / (TH * TW), r = (i / TW) % TH, cx = i % TW;
-                const int yy = min(y_lo + r, y_hi), xx = min(x_lo + cx, x_hi);
-                const float v = __ldg(hp + (long long)d * plane + yy * a.W + xx);
-                bad = bad || !(v > 0.f) || !(v < 1e30f);
-                dmin = fminf(dmin, v);
-                dmax = fmaxf(dmax, v);
-            }
+            const int xx = min(x_lo + lane, x_hi);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-                dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+            for (int r = 0; r < TH; ++r) {
+                const int yy = min(y_lo + r, y_hi);
+                float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const float v = __ldg(hp + (long long)d * plane + yy * a.W + xx);
+                    bad = bad || !(v > 0.f) || !(v < 1e30f);
+                    lo = fminf(lo, v);
+                    hi = fmaxf(hi, v);
+                }
+                dlo[r] = lo; dhi[r] = hi;
             }
             const bool depth_ok = __all_sync(0xffffffffu, !bad);
             for (int v = 0; v < a.V; ++v) {
                 mbar_wait(&ctrl->empty[slot], phase ^ 1);  // all consumer warps have released the slot's previous box
                 int x0, y0, rows;
-                tile_footprint(a.pose + ((long long)b * a.V + v) * 12, lane, (float)x_lo, (float)x_hi, (float)y_lo, (float)y_hi,
-                               dmin, dmax, depth_ok, K::BH, x0, y0, rows);
+                tile_footprint<TH>(a.pose + ((long long)b * a.V + v) * 12, (float)xx, (float)y_lo, dlo, dhi, depth_ok, K::BH, x0, y0, rows);
                 if (lane == 0) {
                     ctrl->box[slot] = make_int4(x0, y0, rows, 0);
                     if (rows > 0) {
@@ -299,23 +313,30 @@ et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_
         for (int v = 0; v < a.V; ++v) {
             const float4* pp = reinterpret_cast<const float4*>(a.pose + ((long long)b * a.V + v) * 12);
             const float4 q0 = __ldg(pp), q1 = __ldg(pp + 1), q2 = __ldg(pp + 2);  // R (row-major 3x3), t
-            const float rx = fmaf(q0.x, fx, fmaf(q0.y, fy, q0.z));
-            const float ry = fmaf(q0.w, fx, fmaf(q1.x, fy, q1.y));
-            const float rz = fmaf(q1.z, fx, fmaf(q1.w, fy, q2.x));
-            // sampling positions of the D hypotheses, two per packed operation: X = rx d + tx (fused), Z == 0 -> 1e-9,
-            // u = X / Z through one reciprocal + FMA residual (<= 1 ulp)
+            const float rx = fmaf(q0.z, 1.f, fmaf(q0.y, fy, q0.x * fx));
+            const float ry = fmaf(q1.y, 1.f, fmaf(q1.x, fy, q0.w * fx));
+            const float nrz = -fmaf(q2.x, 1.f, fmaf(q1.w, fy, q1.z * fx));
+            const float tx = q2.y, ty = q2.z, ntz = -q2.w;
+            // sampling positions of the D hypotheses, two per packed operation; bit-identical to et_fuse_win_kernel's (and to the
+            // scalar sequence X = rx*d + tx with separately rounded product and sum, Z == 0 -> 1e-9, u = X / Z through one
+            // reciprocal + FMA residual): a fused multiply-add here moves the positions by up to 1e-4 pixel against the
+            // reference and, on white-noise-like features, the cost volume by 3e-4 of its maximum (measured)
+            unsigned long long ix2[D / 2], iy2[D / 2];
             float ix[D], iy[D];
 #pragma unroll
             for (int k = 0; k < D / 2; ++k) {
-                const unsigned long long X2 = fma2(pack2(rx, rx), dep2[k], pack2(q2.y, q2.y));
-                const unsigned long long Y2 = fma2(pack2(ry, ry), dep2[k], pack2(q2.z, q2.z));
-                float2 z = unpack2(fma2(pack2(rz, rz), dep2[k], pack2(q2.w, q2.w)));
-                if (z.x == 0.f) z.x = 1e-9f;
-                if (z.y == 0.f) z.y = 1e-9f;
-                const unsigned long long r2 = pack2(rcp_approx(z.x), rcp_approx(z.y)), Zn2 = pack2(-z.x, -z.y);
+                const float2 dd = unpack2(dep2[k]);
+                const unsigned long long X2 = add2(pack2(__fmul_rn(rx, dd.x), __fmul_rn(rx, dd.y)), pack2(tx, tx));
+                const unsigned long long Y2 = add2(pack2(__fmul_rn(ry, dd.x), __fmul_rn(ry, dd.y)), pack2(ty, ty));
+                float2 zn = unpack2(add2(pack2(__fmul_rn(nrz, dd.x), __fmul_rn(nrz, dd.y)), pack2(ntz, ntz)));  // -Z
+                if (zn.x == 0.f) zn.x = -1e-9f;
+                if (zn.y == 0.f) zn.y = -1e-9f;
+                const float r0 = rcp_approx(-zn.x), r1 = rcp_approx(-zn.y);
+                const unsigned long long Zn2 = pack2(zn.x, zn.y), r2 = pack2(r0, r1);
                 const unsigned long long qx = mul2(X2, r2), qy = mul2(Y2, r2);
-                const float2 px = unpack2(fma2(fma2(qx, Zn2, X2), r2, qx));
-                const float2 py = unpack2(fma2(fma2(qy, Zn2, Y2), r2, qy));
+                ix2[k] = fma2(fma2(qx, Zn2, X2), r2, qx);
+                iy2[k] = fma2(fma2(qy, Zn2, Y2), r2, qy);
+                const float2 px = unpack2(ix2[k]), py = unpack2(iy2[k]);
                 ix[2 * k] = px.x; ix[2 * k + 1] = px.y;
                 iy[2 * k] = py.x; iy[2 * k + 1] = py.y;
             }
@@ -355,20 +376,20 @@ et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_
                 const Pix8 t10 = lds_tap<K::PITCH>(sb, alo[0], ahi[0]), t11 = lds_tap<K::PITCH>(sb, alo[1], ahi[1]);
                 if (needx) {
                     const Pix8 t02 = lds_tap<0>(sb, alo[2], ahi[2]), t12 = lds_tap<K::PITCH>(sb, alo[2], ahi[2]);
-                    tap_groups<CPG, NJ>(t02, ref, T[0][2]);
-                    tap_groups<CPG, NJ>(t12, ref, T[1][2]);
+                    tap_groups<CPG, NJ, IL>(t02, ref, T[0][2]);
+                    tap_groups<CPG, NJ, IL>(t12, ref, T[1][2]);
                 }
-                tap_groups<CPG, NJ>(t00, ref, T[0][0]);
-                tap_groups<CPG, NJ>(t01, ref, T[0][1]);
-                tap_groups<CPG, NJ>(t10, ref, T[1][0]);
-                tap_groups<CPG, NJ>(t11, ref, T[1][1]);
+                tap_groups<CPG, NJ, IL>(t00, ref, T[0][0]);
+                tap_groups<CPG, NJ, IL>(t01, ref, T[0][1]);
+                tap_groups<CPG, NJ, IL>(t10, ref, T[1][0]);
+                tap_groups<CPG, NJ, IL>(t11, ref, T[1][1]);
                 if (needy) {
                     const Pix8 t20 = lds_tap<2 * K::PITCH>(sb, alo[0], ahi[0]), t21 = lds_tap<2 * K::PITCH>(sb, alo[1], ahi[1]);
-                    tap_groups<CPG, NJ>(t20, ref, T[2][0]);
-                    tap_groups<CPG, NJ>(t21, ref, T[2][1]);
+                    tap_groups<CPG, NJ, IL>(t20, ref, T[2][0]);
+                    tap_groups<CPG, NJ, IL>(t21, ref, T[2][1]);
                     if (needx) {
                         const Pix8 t22 = lds_tap<2 * K::PITCH>(sb, alo[2], ahi[2]);
-                        tap_groups<CPG, NJ>(t22, ref, T[2][2]);
+                        tap_groups<CPG, NJ, IL>(t22, ref, T[2][2]);
                     }
                 }
                 __syncwarp();
@@ -382,17 +403,24 @@ et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_
                         dx1[r][j] = sub2(T[r][2][j], T[r][1][j]);
                     }
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const float ux = ix[d] - bxf, uy = iy[d] - byf;  // exact, in [0,2)
-                    const float ax = fminf(ux, 1.f), bx = fmaxf(ux - 1.f, 0.f);
-                    const float ay = fminf(uy, 1.f), by = fmaxf(uy - 1.f, 0.f);
-                    const unsigned long long ax2 = pack2(ax, ax), bx2 = pack2(bx, bx), ay2 = pack2(ay, ay), by2 = pack2(by, by);
+                for (int k = 0; k < D / 2; ++k) {
+                    // offsets from the window origin (exact, in [0,2)) and their split u = a + b, a = min(u, 1), b = u - a
+                    const unsigned long long ux2 = sub2(ix2[k], pack2(bxf, bxf)), uy2 = sub2(iy2[k], pack2(byf, byf));
+                    const float2 ux = unpack2(ux2), uy = unpack2(uy2);
+                    const float axs[2] = {fminf(ux.x, 1.f), fminf(ux.y, 1.f)}, ays[2] = {fminf(uy.x, 1.f), fminf(uy.y, 1.f)};
+                    const float2 bxs = unpack2(sub2(ux2, pack2(axs[0], axs[1]))), bys = unpack2(sub2(uy2, pack2(ays[0], ays[1])));
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        const unsigned long long h0 = fma2(bx2, dx1[0][j], fma2(ax2, dx0[0][j], T[0][0][j]));
-                        const unsigned long long h1 = fma2(bx2, dx1[1][j], fma2(ax2, dx0[1][j], T[1][0][j]));
-                        const unsigned long long h2 = fma2(bx2, dx1[2][j], fma2(ax2, dx0[2][j], T[2][0][j]));
-                        cor2[j][d] = fma2(by2, sub2(h2, h1), fma2(ay2, sub2(h1, h0), h0));
+                    for (int e = 0; e < 2; ++e) {
+                        const int d = 2 * k + e;
+                        const float bx = e ? bxs.y : bxs.x, by = e ? bys.y : bys.x;
+                        const unsigned long long ax2 = pack2(axs[e], axs[e]), bx2 = pack2(bx, bx), ay2 = pack2(ays[e], ays[e]), by2 = pack2(by, by);
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            const unsigned long long h0 = fma2(bx2, dx1[0][j], fma2(ax2, dx0[0][j], T[0][0][j]));
+                            const unsigned long long h1 = fma2(bx2, dx1[1][j], fma2(ax2, dx0[1][j], T[1][0][j]));
+                            const unsigned long long h2 = fma2(bx2, dx1[2][j], fma2(ax2, dx0[2][j], T[2][0][j]));
+                            cor2[j][d] = fma2(by2, sub2(h2, h1), fma2(ay2, sub2(h1, h0), h0));
+                        }
                     }
                 }
             } else {
@@ -427,7 +455,7 @@ et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_
                         wv.p[i] = fma2(t_se.p[i], pack2(w_se, w_se), s);
                     }
                     unsigned long long g2[NJ];
-                    tap_groups<CPG, NJ>(wv, ref, g2);
+                    tap_groups<CPG, NJ, IL>(wv, ref, g2);
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) cor2[j][d] = g2[j];
                 }
@@ -529,15 +557,19 @@ static int launch_et_tma(const EtArgs& a, const Maps& maps, cudaStream_t st) {
     using K = Cfg<C, LPP, TH_>;
     const int tiles_x = ceil_div(a.W, TW), tiles_y = ceil_div(a.H, K::TH);
     const long long ntiles = (long long)tiles_x * tiles_y * a.B;
-    auto k = et_fuse_tma_kernel<C, G, D, LPP, TH_>;
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM) != cudaSuccess) {
+    const bool il = a.flags & MVSTER_ET_INTERLEAVED;
+    if (cudaFuncSetAttribute(et_fuse_tma_kernel<C, G, D, LPP, TH_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(et_fuse_tma_kernel<C, G, D, LPP, TH_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM) != cudaSuccess) {
         cudaGetLastError();
         return -100;
     }
     const int slots = sm_count_here() * K::MIN_CTAS;
     const int grid = (int)(ntiles < slots ? ntiles : slots);
-    et_fuse_tma_kernel<C, G, D, LPP, TH_><<<grid, K::THREADS, K::SMEM, st>>>(a, maps, tiles_x, tiles_y, (int)ntiles);
-    note_et_kernel(TH_ == 15 ? "et_fuse_tma_kernel[15x32 tiles]" : TH_ == 7 ? "et_fuse_tma_kernel[7x32 tiles]" : "et_fuse_tma_kernel[3x32 tiles]", C, G, D, LPP, K::MIN_CTAS);
+    if (il) et_fuse_tma_kernel<C, G, D, LPP, TH_, true><<<grid, K::THREADS, K::SMEM, st>>>(a, maps, tiles_x, tiles_y, (int)ntiles);
+    else et_fuse_tma_kernel<C, G, D, LPP, TH_, false><<<grid, K::THREADS, K::SMEM, st>>>(a, maps, tiles_x, tiles_y, (int)ntiles);
+    note_et_kernel(il ? (TH_ == 15 ? "et_fuse_tma_kernel[15x32 tiles, interleaved]" : TH_ == 7 ? "et_fuse_tma_kernel[7x32 tiles, interleaved]" : "et_fuse_tma_kernel[3x32 tiles, interleaved]")
+                      : (TH_ == 15 ? "et_fuse_tma_kernel[15x32 tiles]" : TH_ == 7 ? "et_fuse_tma_kernel[7x32 tiles]" : "et_fuse_tma_kernel[3x32 tiles]"),
+                   C, G, D, LPP, K::MIN_CTAS);
     return check_launch("et_fuse_tma_kernel");
 }
 

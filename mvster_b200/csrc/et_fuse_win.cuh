@@ -64,9 +64,20 @@ __device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("pref
 
 // Per-group correlations of one 8-channel tap with the lane's (pre-scaled) reference channels,
 // packed two groups per 64-bit pair.  CPG = 2: 4 groups (2 pairs); CPG = 4: 2 groups (1 pair).
-template <int CPG, int NJ>
+// IL (MVSTER_ET_INTERLEAVED): the 8 channels of the block are stored group-interleaved - position p holds channel
+// perm[p], perm = {0,2,1,3,4,6,5,7} for CPG = 2 and {0,4,1,5,2,6,3,7} for CPG = 4 - so that a 64-bit pair holds the SAME
+// channel index of two neighbouring groups and the group sums need no horizontal adds: 4 packed operations per tap
+// instead of 4 packed + 4 scalar + the moves that rebuild the pairs.
+template <int CPG, int NJ, bool IL = false>
 __device__ __forceinline__ void tap_groups(const Pix8& t, const unsigned long long (&ref)[4], unsigned long long (&out)[NJ]) {
-    if constexpr (CPG == 2) {
+    if constexpr (IL && CPG == 2) {
+        static_assert(NJ == 2, "8 channels in groups of 2 = 4 groups");
+        out[0] = fma2(ref[1], t.p[1], mul2(ref[0], t.p[0]));
+        out[1] = fma2(ref[3], t.p[3], mul2(ref[2], t.p[2]));
+    } else if constexpr (IL) {
+        static_assert(CPG == 4 && NJ == 1, "8 channels in groups of 4 = 2 groups");
+        out[0] = fma2(ref[3], t.p[3], fma2(ref[2], t.p[2], fma2(ref[1], t.p[1], mul2(ref[0], t.p[0]))));
+    } else if constexpr (CPG == 2) {
         static_assert(NJ == 2, "8 channels in groups of 2 = 4 groups");
         const float2 m0 = unpack2(mul2(ref[0], t.p[0])), m1 = unpack2(mul2(ref[1], t.p[1]));
         const float2 m2 = unpack2(mul2(ref[2], t.p[2])), m3 = unpack2(mul2(ref[3], t.p[3]));
@@ -103,7 +114,7 @@ __device__ __forceinline__ void win_prefetch(const float4* pose_s, int v, const 
     }
 }
 
-template <int C, int G, int D, int LPP, int MB>
+template <int C, int G, int D, int LPP, int MB, bool IL = false>
 __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
     constexpr int CPL = C / LPP;   // channels per lane
     constexpr int GPL = G / LPP;   // groups per lane
@@ -225,21 +236,21 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
             for (int j = 0; j < NJ; ++j) T[0][2][j] = T[1][2][j] = T[2][0][j] = T[2][1][j] = T[2][2][j] = 0ull;
             if (needx) {
                 const Pix8 t02 = ldg256(p0 + 2 * C), t12 = ldg256(p1 + 2 * C);
-                tap_groups<CPG, NJ>(t02, ref, T[0][2]);
-                tap_groups<CPG, NJ>(t12, ref, T[1][2]);
+                tap_groups<CPG, NJ, IL>(t02, ref, T[0][2]);
+                tap_groups<CPG, NJ, IL>(t12, ref, T[1][2]);
             }
-            tap_groups<CPG, NJ>(t00, ref, T[0][0]);
-            tap_groups<CPG, NJ>(t01, ref, T[0][1]);
-            tap_groups<CPG, NJ>(t10, ref, T[1][0]);
-            tap_groups<CPG, NJ>(t11, ref, T[1][1]);
+            tap_groups<CPG, NJ, IL>(t00, ref, T[0][0]);
+            tap_groups<CPG, NJ, IL>(t01, ref, T[0][1]);
+            tap_groups<CPG, NJ, IL>(t10, ref, T[1][0]);
+            tap_groups<CPG, NJ, IL>(t11, ref, T[1][1]);
             if (needy) {
                 const float* p2 = p1 + row;
                 const Pix8 t20 = ldg256(p2), t21 = ldg256(p2 + C);
-                tap_groups<CPG, NJ>(t20, ref, T[2][0]);
-                tap_groups<CPG, NJ>(t21, ref, T[2][1]);
+                tap_groups<CPG, NJ, IL>(t20, ref, T[2][0]);
+                tap_groups<CPG, NJ, IL>(t21, ref, T[2][1]);
                 if (needx) {
                     const Pix8 t22 = ldg256(p2 + 2 * C);
-                    tap_groups<CPG, NJ>(t22, ref, T[2][2]);
+                    tap_groups<CPG, NJ, IL>(t22, ref, T[2][2]);
                 }
             }
             unsigned long long dx0[3][NJ], dx1[3][NJ];  // column differences
@@ -300,7 +311,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
                     wv.p[i] = fma2(t_se.p[i], pack2(w_se, w_se), s);
                 }
                 unsigned long long g2[NJ];
-                tap_groups<CPG, NJ>(wv, ref, g2);
+                tap_groups<CPG, NJ, IL>(wv, ref, g2);
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) cor2[j][d] = g2[j];
             }
@@ -361,8 +372,9 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
 template <int C, int G, int D, int LPP, int MB>
 static int launch_et_win(const EtArgs& a, cudaStream_t st) {
     dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 4), a.B);
-    et_fuse_win_kernel<C, G, D, LPP, MB><<<grid, 128, 0, st>>>(a);
-    note_et_kernel("et_fuse_win_kernel", C, G, D, LPP, MB);
+    if (a.flags & MVSTER_ET_INTERLEAVED) et_fuse_win_kernel<C, G, D, LPP, MB, true><<<grid, 128, 0, st>>>(a);
+    else et_fuse_win_kernel<C, G, D, LPP, MB, false><<<grid, 128, 0, st>>>(a);
+    note_et_kernel(a.flags & MVSTER_ET_INTERLEAVED ? "et_fuse_win_kernel[interleaved]" : "et_fuse_win_kernel", C, G, D, LPP, MB);
     return check_launch("et_fuse_win_kernel");
 }
 

@@ -479,8 +479,9 @@ extern "C" int mvster_conv_first_f32(const float* img_nchw, const float* w, cons
     MVSTER_REQUIRE(img_nchw && w && bias && y, "mvster_conv_first_f32: null pointer");
     MVSTER_REQUIRE(N > 0 && H > 0 && W > 0, "mvster_conv_first_f32: bad shape");
     const long long n = (long long)N * H * W;
+    // default = the four-pixel kernel (B200, 5 x 512 x 640: 36.9 us vs 51.2 us, same bits - profiles/r02_glue_ab.md); MVSTER_CONV_FIRST=1 = v1
     const char* variant = getenv("MVSTER_CONV_FIRST");
-    if (variant && atoi(variant) == 2 && W % 4 == 0 && n / 4 < (1ll << 31)) {  // four pixels per thread, packed FMAs (opt-in until it has been timed)
+    if ((!variant || atoi(variant) == 2) && W % 4 == 0 && n / 4 < (1ll << 31)) {  // four pixels per thread, packed FMAs
         conv_first4_kernel<<<ceil_div(n / 4, 128), 128, 0, (cudaStream_t)stream>>>(img_nchw, w, bias, y, N, H, W);
         return check_launch("conv_first4_kernel");
     }
@@ -493,8 +494,11 @@ extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, cons
     MVSTER_REQUIRE(top && lateral && w && bias && out, "mvster_fpn_merge_f32: null pointer");
     MVSTER_REQUIRE(N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "mvster_fpn_merge_f32: H,W must be even");
     cudaStream_t st = (cudaStream_t)stream;
-    const char* variant = getenv("MVSTER_FPN_MERGE");
-    if (variant && atoi(variant) == 2 && (long long)N * H * ((W + 3) / 4) * 16 < (1ll << 31)) {  // four pixels per lane (opt-in until it has been timed)
+    // measured on B200 (profiles/r02_glue_ab.md): 16 lateral channels 106.5 (v1) / 65.6 (v2) / 69.6 us (v3); 32 lateral channels
+    // 51.2 / 32.8 / 30.7 us -> default v2, v3 for the 32-channel level; MVSTER_FPN_MERGE=1|2|3 forces one (A/B)
+    const char* env_v = getenv("MVSTER_FPN_MERGE");
+    const int mv = env_v ? atoi(env_v) : (Clat == 32 ? 3 : 2);
+    if (mv == 2 && (long long)N * H * ((W + 3) / 4) * 16 < (1ll << 31)) {  // four pixels per lane
         const long long n4 = (long long)N * H * ((W + 3) / 4) * 16;
         dim3 grid4(ceil_div(n4, 128));
         if (Clat == 8) fpn_merge4_kernel<8><<<grid4, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
@@ -503,7 +507,7 @@ extern "C" int mvster_fpn_merge_f32(const float* top, const float* lateral, cons
         else MVSTER_REQUIRE(false, "mvster_fpn_merge_f32: unsupported lateral channels %d (8,16,32)", Clat);
         return check_launch("fpn_merge4_kernel");
     }
-    if (variant && atoi(variant) == 3 && (long long)N * H * ((W + 3) / 4) * 4 < (1ll << 31)) {  // four lanes per four pixels, packed FMAs (opt-in)
+    if (mv == 3 && (long long)N * H * ((W + 3) / 4) * 4 < (1ll << 31)) {  // four lanes per four pixels, packed FMAs
         const long long n5 = (long long)N * H * ((W + 3) / 4) * 4;
         dim3 grid5(ceil_div(n5, 128));
         if (Clat == 8) fpn_merge5_kernel<8><<<grid5, 128, 0, st>>>(top, lateral, w, bias, out, N, H, W);
@@ -871,8 +875,9 @@ extern "C" int mvster_fpn_out4_gather_f32(const float* U, int u_channels, const 
                    "mvster_fpn_out4_gather_f32: U is [..][>= 72 channels] (9 taps x 8 interleaved) or, with u_channels = 8, planar [9][N][H/2][W/2][8]");
     const long long n = (long long)N * H * W;
     const long long tap_stride = u_channels == 8 ? (long long)N * (H / 2) * (W / 2) * 8 : 8;
+    // measured on B200 (5 x 512 x 640, profiles/r02_glue_ab.md): 198.7 (v1) / 168.0 (v2, same bits) / 262.1 us (v3) -> default v2
     const char* variant = getenv("MVSTER_FPN_GATHER");
-    if (variant && atoi(variant) == 2 && u_channels == 8 && N < 65536) {  // shared-memory tiled variant (opt-in until it has been timed)
+    if ((!variant || atoi(variant) == 2) && u_channels == 8 && N < 65536) {  // shared-memory tiled variant
         auto k = mvster::fpn_out4_gather2_kernel;
         const size_t smem = (size_t)mvster::G2_SMEM_FLOATS * sizeof(float);
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

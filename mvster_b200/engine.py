@@ -139,7 +139,14 @@ class InferenceEngine:
         self.plans = [StagePlan(k, net) for k in range(net.num_stage)]
         self.stage_weights = []
         fpn_sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("feature.")}
-        fpn_packed = fpn_engine.pack_fpn(fpn_sd)
+        # Group-interleaved feature channels (MVSTER_ET_INTERLEAVED): the native pyramid writes stage k's channels in the order the
+        # window kernels want (a 64-bit pair = the same channel index of two neighbouring groups), by permuting the output
+        # channels of out{k} when the weights are packed.  Only for the shipped (C, G, D) classes those kernels are built for.
+        self.interleave = [False] * len(self.plans)
+        if net.group_cor and getattr(net, "fpn_backend", "torch") == "native" and os.environ.get("MVSTER_ET_INTERLEAVE", "1") == "1":
+            self.interleave = [(p.C, p.G, p.D) in ((8, 4, 4), (16, 4, 4), (32, 8, 8)) for p in self.plans]
+        self.perms = [capi.interleave_perm(p.C, p.G) if il else None for p, il in zip(self.plans, self.interleave)]
+        fpn_packed = fpn_engine.pack_fpn(fpn_sd, out_perm={k + 1: perm for k, perm in enumerate(self.perms)})
         self.fp16_safe = {"fpn": packing.fp16_range_ok(v for k, v in fpn_packed.items() if k.endswith(".w")), "reg": True}
         self.fpn_weights = {k: v.to(self.device) for k, v in fpn_packed.items()}
         with torch.cuda.device(self.device):
@@ -159,6 +166,13 @@ class InferenceEngine:
         check_inputs(net, imgs, proj_matrices, depth_values)
         B = imgs[0].shape[0]
         own = list(range(len(imgs))) if shard is None else [0] + shard.views
+        self._native_feats = getattr(net, "fpn_backend", "torch") == "native"  # features in the pyramid's (interleaved) channel order
+        try:
+            return self._forward(net, imgs, proj_matrices, depth_values, shard, B, own)
+        finally:
+            self._native_feats = False
+
+    def _forward(self, net, imgs, proj_matrices, depth_values, shard, B, own) -> Dict:
         with torch.cuda.device(self.device):
             if getattr(net, "fpn_backend", "torch") == "native":
                 # FPN4 inside libmvster_b200 (fpn_engine.py): NCHW images in, NHWC features out
@@ -226,7 +240,7 @@ class InferenceEngine:
     # ------------------------------------------------------------------ the hot path
     def _aggregate(self, p: StagePlan, ref: Tensor, srcs: List[Tensor], proj: Tensor, hypo: Tensor, temp: float,
                    fuse_d: bool, shard, pose: Optional[Tensor] = None) -> Tensor:
-        kw = dict(group_cor=p.group_cor, fuse_d=fuse_d)
+        kw = dict(group_cor=p.group_cor, fuse_d=fuse_d, interleaved=self._interleaved(p.k, ref))
         if shard is None:
             return capi.et_fuse(ref, srcs, capi.pose(proj) if pose is None else pose, hypo, p.G, temp, **kw)
         from . import sharding
@@ -237,6 +251,11 @@ class InferenceEngine:
             capi.et_fuse(ref, srcs, pose, hypo, p.G, temp, cost=acc, wsum=wsum, partial=True, **kw)
 
         return sharding.sharded_aggregate(partial, capi.et_normalize, (B, p.D, H, W, p.G), shard, self.device)
+
+    def _interleaved(self, k: int, ref: Tensor) -> bool:
+        """True when the stage-k features this engine was handed are in the group-interleaved layout (they are whenever they
+        come from the engine's own native pyramid, see refresh_weights; ``run_cascade`` callers pass natural-order features)."""
+        return bool(getattr(self, "_native_feats", False) and k < len(self.interleave) and self.interleave[k])
 
     def _regularise(self, net, p: StagePlan, wts: Dict[str, Tensor], cost: Tensor, hypo: Tensor) -> Dict[str, Tensor]:
         inverse = bool(net.inverse_depth)
@@ -284,8 +303,28 @@ class InferenceEngine:
             out["inverse_min_depth"] = h["inverse_min_depth"]
             out["inverse_max_depth"] = h["inverse_max_depth"]
         if net.mono:
-            out["mono_feat"] = ref.permute(0, 3, 1, 2)  # [B,C,H,W] view, as mvs4net_utils.py:1092
+            if self._interleaved(p.k, ref):  # back to the natural channel order: natural[..., c] = stored[..., inverse[c]]
+                inv = self._inverse_perm(p.k)
+
+                def emit(o=out, r=ref, i=inv):
+                    o["mono_feat"] = r.index_select(3, i).permute(0, 3, 1, 2)
+                if deferred is None:
+                    emit()
+                else:
+                    deferred.append(emit)  # an output only: off the stage-to-stage chain
+            else:
+                out["mono_feat"] = ref.permute(0, 3, 1, 2)  # [B,C,H,W] view, as mvs4net_utils.py:1092
         return out
+
+    def _inverse_perm(self, k: int) -> Tensor:
+        cache = self.__dict__.setdefault("_inv_perm", {})
+        if k not in cache:
+            perm = self.perms[k]
+            inv = [0] * len(perm)
+            for pos, ch in enumerate(perm):
+                inv[ch] = pos
+            cache[k] = torch.tensor(inv, dtype=torch.long, device=self.device)
+        return cache[k]
 
     def run_cascade(self, net, feats: List[List[Tensor]], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
                     attn_temp: Optional[float] = None, shard=None) -> Dict:

@@ -8,7 +8,7 @@ feature tensors the warp kernel consumes.
 from __future__ import annotations
 
 import os
-from typing import Dict, Mapping, Optional
+from typing import Dict, Mapping, Optional, Sequence
 
 import torch
 
@@ -32,9 +32,12 @@ def _plain2d(w: Tensor):
     return w.permute(2, 3, 1, 0).reshape(k * k, w.shape[1], w.shape[0]).float().contiguous()
 
 
-def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Tensor]:
+def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature", out_perm: Optional[Mapping[int, Sequence[int]]] = None) -> Dict[str, Tensor]:
     """All FPN4 weights in kernel layouts (CPU tensors): '<layer>.w' [taps][Cin][Cout], '<layer>.b' [Cout],
-    '<layer>.tc' K-major [hi|lo] slabs for the 3x3 stride-1 layers with Cin >= 16."""
+    '<layer>.tc' K-major [hi|lo] slabs for the 3x3 stride-1 layers with Cin >= 16.
+    ``out_perm[i]`` (i = 1..4): output-channel order of ``out{i}`` - memory position p of the stage-i features holds channel
+    ``out_perm[i][p]`` (the group-interleaved layout of MVSTER_ET_INTERLEAVED, capi.interleave_perm); every packed form of
+    that convolution, the fused last level included, is built from the permuted weights, so the layout costs nothing."""
     out: Dict[str, Tensor] = {}
     p = prefix
     for name in ("conv0.0", "conv0.1", "conv1.0", "conv1.1", "conv1.2", "conv2.0", "conv2.1", "conv2.2", "conv3.0", "conv3.1", "conv3.2"):
@@ -52,6 +55,8 @@ def pack_fpn(sd: Mapping[str, Tensor], prefix: str = "feature") -> Dict[str, Ten
         out[f"inner{i}.b"] = sd[f"{p}.inner{i}.bias"].detach().cpu().float().contiguous()
     for i in (1, 2, 3, 4):
         w = _plain2d(sd[f"{p}.out{i}.weight"])
+        if out_perm and out_perm.get(i) is not None and list(out_perm[i]) != list(range(w.shape[2])):
+            w = w[:, :, list(out_perm[i])].contiguous()
         out[f"out{i}.w"] = w
         if w.shape[0] == 9:
             out[f"out{i}.tc"] = packing.pack_tc2_weights(w, 3)

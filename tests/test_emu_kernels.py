@@ -156,6 +156,13 @@ def test_tma_staged_kernel_on_cpu_matches_oracle(emu, case, monkeypatch):
     assert torch.isfinite(got).all() and (got - want).abs().max().item() <= 2e-4 * scale
     win = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=False))
     assert (got - win).abs().max().item() <= 2e-5 * scale
+    # group-interleaved channel layout (MVSTER_ET_INTERLEAVED): same features with permuted channels, both kernels
+    perm = capi.interleave_perm(C_, G)
+    ref_il, srcs_il = ref[..., perm].contiguous(), [s_[..., perm].contiguous() for s_ in srcs]
+    for tma in (True, False):
+        got_il = from_ndhwc(capi.et_fuse(ref_il, srcs_il, pose, hypo, G, 2.0, tma=tma, interleaved=True))
+        assert "interleaved" in capi.et_last_kernel() or tma
+        assert (got_il - got).abs().max().item() <= 5e-6 * scale, tma
     # view sharding: partial sums of the first views, then accumulate the rest, then normalise
     k = max(1, (nv - 1) // 2)
     wsum = torch.empty(B, D, H, W)
@@ -420,7 +427,7 @@ def test_tiled_gather_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, 
         rc = emu.mvster_fpn_out4_gather_f32(capi._ptr(U), 8, capi._ptr(c0), capi._ptr(wc), capi._ptr(bt), capi._ptr(out), N, H, W, None)
         assert rc == 0
         return out
-    monkeypatch.delenv("MVSTER_FPN_GATHER", raising=False)
+    monkeypatch.setenv("MVSTER_FPN_GATHER", "1")
     want = run()
     monkeypatch.setenv("MVSTER_FPN_GATHER", "2")
     got = run()
@@ -448,7 +455,7 @@ def test_four_pixel_merge_variant_returns_the_same_bits_on_cpu(emu, monkeypatch,
     lat = torch.from_numpy(rng.randn(N, H, W, CL).astype(np.float32))
     w = torch.from_numpy((rng.randn(CL, 64) / 4).astype(np.float32))
     bias = torch.from_numpy(rng.randn(64).astype(np.float32))
-    monkeypatch.delenv("MVSTER_FPN_MERGE", raising=False)
+    monkeypatch.setenv("MVSTER_FPN_MERGE", "1")
     want = fpn_engine._merge(top, lat, w, bias)
     monkeypatch.setenv("MVSTER_FPN_MERGE", "2")
     got = fpn_engine._merge(top, lat, w, bias)
@@ -481,7 +488,7 @@ def test_four_pixel_stem_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, 
                                        C.c_void_p(out.data_ptr()), N, H, W, None)
         assert rc == 0
         return out
-    monkeypatch.delenv("MVSTER_CONV_FIRST", raising=False)
+    monkeypatch.setenv("MVSTER_CONV_FIRST", "1")
     want = run()
     monkeypatch.setenv("MVSTER_CONV_FIRST", "2")
     got = run()
@@ -500,7 +507,7 @@ def test_four_voxel_conv0_variant_returns_the_same_bits_on_cpu(emu, monkeypatch,
     wt = torch.from_numpy((rng.randn(8, G, 1, 3, 3) / 3).astype(np.float32))
     bias = torch.from_numpy(rng.randn(8).astype(np.float32))
     packed = wt[:, :, 0].permute(2, 3, 1, 0).reshape(9, G, 8).contiguous()   # [ky*3+kx][cin][cout]
-    monkeypatch.delenv("MVSTER_CONV0_PX4", raising=False)
+    monkeypatch.setenv("MVSTER_CONV0_PX4", "0")
     want = capi.conv3d_ndhwc(x, packed, bias, 1, relu=relu)
     monkeypatch.setenv("MVSTER_CONV0_PX4", "1")
     got = capi.conv3d_ndhwc(x, packed, bias, 1, relu=relu)
@@ -547,7 +554,7 @@ def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch, na
     monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
     if name.endswith("+variants"):   # the prepared (opt-in) CUDA-core kernel variants switched on
         name = name[:-len("+variants")]
-        for k, v in (("MVSTER_FPN_GATHER", "3"), ("MVSTER_FPN_MERGE", "3"), ("MVSTER_CONV_FIRST", "2"), ("MVSTER_CONV0_PX4", "1")):
+        for k, v in (("MVSTER_FPN_GATHER", "1"), ("MVSTER_FPN_MERGE", "1"), ("MVSTER_CONV_FIRST", "1"), ("MVSTER_CONV0_PX4", "0")):  # the first-generation kernels
             monkeypatch.setenv(k, v)
     z, imgs, proj, dv = load_golden(name)
     m = build_model(GOLDEN_CASES[name], int(z["meta_seed"]))
@@ -576,6 +583,14 @@ def test_engine_forward_on_cpu_matches_the_reference_golden(emu, monkeypatch, na
     assert out["depth"].data_ptr() == out["stage4"]["depth"].data_ptr()
     conf = torch.from_numpy(z["s4_photometric_confidence"])
     assert (out["photometric_confidence"] - conf).abs()[drift_free].max().item() < 1e-3  # max probability of the last stage, after four stages of fp32 noise
+    if GOLDEN_CASES[name].get("mono") and GOLDEN_CASES[name].get("group_cor"):
+        # mono_feat = the reference view's features in the NATURAL channel order although the engine keeps stages 2-4 group-interleaved
+        assert any(eng.interleave), eng.interleave
+        want = oracle.fpn4_features(m.state_dict(), imgs[0])
+        for s_ in range(1, 5):
+            got = out[f"stage{s_}"]["mono_feat"]
+            assert tuple(got.shape) == tuple(want[f"stage{s_}"].shape)
+            assert (got - want[f"stage{s_}"]).abs().max().item() <= 2e-5 * want[f"stage{s_}"].abs().max().item(), s_
 
 
 

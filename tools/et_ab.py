@@ -23,7 +23,10 @@ VARIANTS = [
     ("tiled", dict(MVSTER_ET_WIN="0")),
     ("tma_15x32", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1")),
     ("tma_7x32", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7")),
+    ("tma_15x32_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", IL="1")),
+    ("tma_7x32_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7", IL="1")),
     ("win", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0")),
+    ("win_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0", IL="1")),
     ("win_mb5", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0", MVSTER_ET_WIN_MB="5")),
 ]
 KEYS = ("MVSTER_ET_WIN", "MVSTER_ET_WIN_MB", "MVSTER_ET_PREFETCH", "MVSTER_ET_TMA", "MVSTER_ET_TMA_TH")
@@ -53,19 +56,22 @@ def main():
     for name, env in VARIANTS:
         for key in KEYS:
             os.environ.pop(key, None)
+        env = dict(env)
+        il = env.pop("IL", "0") == "1"  # * = timing only: the features here are in natural order, so the values are not comparable
         os.environ.update(env)
         row = []
         for k, (feats, hypo, pose) in enumerate(stages):
             G = bench.G_K[k]
+            kw = dict(interleaved=il and k > 0)
             cost = torch.empty((B, bench.D_K[k], H >> (3 - k), W >> (3 - k), G), device=dev)
             for _ in range(3):
-                capi.et_fuse(feats[0], feats[1:], pose, hypo, G, 2.0, cost=cost)
+                capi.et_fuse(feats[0], feats[1:], pose, hypo, G, 2.0, cost=cost, **kw)
             ts = []
             for _ in range(args.reps):
                 flush.fill_(1.0)
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s.record()
-                capi.et_fuse(feats[0], feats[1:], pose, hypo, G, 2.0, cost=cost)
+                capi.et_fuse(feats[0], feats[1:], pose, hypo, G, 2.0, cost=cost, **kw)
                 e.record()
                 torch.cuda.synchronize()
                 ts.append(s.elapsed_time(e))

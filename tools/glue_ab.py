@@ -65,11 +65,11 @@ def main():
         _lib.check(lib.mvster_fpn_out4_gather_f32(capi._ptr(U), 8, capi._ptr(c0), capi._ptr(wc), capi._ptr(bt), capi._ptr(out), N, H, W,
                                                   capi._stream()), "gather")
         return out
-    cases.append((f"fpn_out4_gather ({N} x {H} x {W})", "MVSTER_FPN_GATHER", [None, "2", "3"], gather, (U.numel() + c0.numel() + out.numel()) * 4))
+    cases.append((f"fpn_out4_gather ({N} x {H} x {W})", "MVSTER_FPN_GATHER", ["1", "2", "3"], gather, (U.numel() + c0.numel() + out.numel()) * 4))
 
     for (h, w, CL) in ((H // 2, W // 2, 16), (H // 4, W // 4, 32)):
         top, lat, wl, bl = r(N, h // 2, w // 2, 64), r(N, h, w, CL), r(CL, 64) / 4, r(64)
-        cases.append((f"fpn_merge<{CL}> ({N} x {h} x {w})", "MVSTER_FPN_MERGE", [None, "2", "3"],
+        cases.append((f"fpn_merge<{CL}> ({N} x {h} x {w})", "MVSTER_FPN_MERGE", ["1", "2", "3"],
                       (lambda top=top, lat=lat, wl=wl, bl=bl: fpn_engine._merge(top, lat, wl, bl)),
                       (top.numel() + lat.numel() + N * h * w * 64) * 4))
 
@@ -79,11 +79,11 @@ def main():
     def stem():
         _lib.check(lib.mvster_conv_first_f32(capi._ptr(img), capi._ptr(ws), capi._ptr(bs), capi._ptr(o8), N, H, W, capi._stream()), "stem")
         return o8
-    cases.append((f"conv_first ({N} x {H} x {W})", "MVSTER_CONV_FIRST", [None, "2"], stem, (img.numel() + o8.numel()) * 4))
+    cases.append((f"conv_first ({N} x {H} x {W})", "MVSTER_CONV_FIRST", ["1", "2"], stem, (img.numel() + o8.numel()) * 4))
 
     for (D, h, w, G) in ((4, H, W, 4), (4, H // 2, W // 2, 4), (8, H // 4, W // 4, 8), (8, H // 8, W // 8, 8)):
         x, w0, b0 = r(1, D, h, w, G), r(9, G, 8) / 3, r(8)
-        cases.append((f"reg2d conv0 G={G} ({D} x {h} x {w})", "MVSTER_CONV0_PX4", [None, "1"],
+        cases.append((f"reg2d conv0 G={G} ({D} x {h} x {w})", "MVSTER_CONV0_PX4", ["0", "1"],
                       (lambda x=x, w0=w0, b0=b0: capi.conv3d_ndhwc(x, w0, b0, 1)), (x.numel() + D * h * w * 8) * 4))
 
     rows = []
