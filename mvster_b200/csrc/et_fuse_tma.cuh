@@ -31,8 +31,8 @@ namespace ettma {
 
 constexpr int TW = 32;             // reference tile width (pixels); its height TH depends on the channel count (Cfg)
 constexpr int BW = 56;             // source box per (tile, view): BH rows x BW pixels (x C channels)
-constexpr int RB = 2;              // source rows per TMA op
-constexpr int MAX_SLOT = 3;        // boxes in flight per CTA (Cfg::NSLOT <= MAX_SLOT)
+constexpr int RB = 4;              // source rows per TMA op
+constexpr int MAX_SLOT = 4;        // boxes in flight per CTA (Cfg::NSLOT <= MAX_SLOT)
 constexpr int MAXV = 12;           // tensor maps per launch (more views: chained launches through the partial sums)
 
 #ifdef MVSTER_CPU_EMU
@@ -79,7 +79,7 @@ struct SrcMap { CUtensorMap m; };
 __device__ __forceinline__ void mbar_init(Mbar* m, int count) { ptx::mbar_init(ptx::smem_u32(m), count); }
 __device__ __forceinline__ void mbar_arrive(Mbar* m) { ptx::mbar_arrive(ptx::smem_u32(m)); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(Mbar* m, int bytes) { ptx::mbar_expect_tx(ptx::smem_u32(m), bytes); }
-__device__ __forceinline__ void mbar_wait(Mbar* m, int parity) { ptx::mbar_wait(ptx::smem_u32(m), parity); }
+__device__ __forceinline__ void mbar_wait(Mbar* m, int parity) { ptx::mbar_wait_parked(ptx::smem_u32(m), parity, 20000u); }
 __device__ __forceinline__ void tma_rows(unsigned char* slot, unsigned dst_off, const SrcMap* m, Mbar* bar, int x0, int y0, int b) {
     ptx::tma_load_4d(ptx::smem_u32(slot) + dst_off, &m->m, ptx::smem_u32(bar), 0, x0, y0, b);
 }
@@ -104,14 +104,14 @@ __device__ __forceinline__ Pix8 lds_tap(const unsigned char* smem, unsigned a_lo
 template <int C, int LPP, int TH_>
 struct Cfg {
     static constexpr int TH = TH_;
-    static constexpr int BH = TH >= 12 ? TH + 13 : TH >= 6 ? TH + 11 : TH + 9;  // box rows (footprint of TH rows + the depth-dependent shift), even
-    static constexpr int NSLOT = LPP == 4 ? 2 : 3;        // boxes in flight per CTA
+    static constexpr int BH = TH >= 12 ? TH + 13 : TH >= 6 ? TH + 13 : TH + 9;  // box rows (footprint of TH rows + the depth-dependent shift), a multiple of RB
+    static constexpr int NSLOT = LPP == 4 ? 2 : (C == 8 && TH >= 12) ? 4 : 3;  // boxes in flight per CTA
     static constexpr int NCW = TH * LPP;                  // consumer warps (a warp covers 32 / LPP pixels of one tile row)
     static constexpr int THREADS = (NCW + 1) * 32;        // + the producer warp
     static constexpr int PITCH = BW * C * 4;              // bytes per box row
     static constexpr int SLOT_BYTES = BH * PITCH;
     static constexpr int SLOT_STRIDE = (SLOT_BYTES + 1023) / 1024 * 1024;
-    static constexpr int CTRL_BYTES = 256;                // mbarriers + box descriptors
+    static constexpr int CTRL_BYTES = 512;                // mbarriers + box descriptors
     static constexpr int SMEM = NSLOT * SLOT_STRIDE + CTRL_BYTES + 1024;  // + alignment slack
     static constexpr unsigned SWZ_MASK = C / 4 - 1;       // 32 / 64 / 128-byte swizzle for C = 8 / 16 / 32
     static constexpr int MIN_CTAS = THREADS <= 256 ? 2 : 1;
@@ -134,17 +134,17 @@ __device__ __forceinline__ void tile_footprint(const float* __restrict__ pose, f
     float rx = fmaf(pose[0], x, fmaf(pose[1], y0, pose[2]));
     float ry = fmaf(pose[3], x, fmaf(pose[4], y0, pose[5]));
     float rz = fmaf(pose[6], x, fmaf(pose[7], y0, pose[8]));
-    const float tx = pose[9], ty = pose[10], tz = pose[11];
+    const unsigned long long tx2 = pack2(pose[9], pose[9]), ty2 = pack2(pose[10], pose[10]), tz2 = pack2(pose[11], pose[11]);
     float umin = INFINITY, umax = -INFINITY, wmin = INFINITY, wmax = -INFINITY, zmin = INFINITY;
 #pragma unroll
-    for (int r = 0; r < TH; ++r) {
-        const float za = fmaf(rz, dlo[r], tz), zb = fmaf(rz, dhi[r], tz);
-        const float ia = rcp_approx(za), ib = rcp_approx(zb);
-        const float ua = fmaf(rx, dlo[r], tx) * ia, ub = fmaf(rx, dhi[r], tx) * ib;
-        const float wa = fmaf(ry, dlo[r], ty) * ia, wb = fmaf(ry, dhi[r], ty) * ib;
-        umin = fminf(umin, fminf(ua, ub)); umax = fmaxf(umax, fmaxf(ua, ub));
-        wmin = fminf(wmin, fminf(wa, wb)); wmax = fmaxf(wmax, fmaxf(wa, wb));
-        zmin = fminf(zmin, fminf(za, zb));
+    for (int r = 0; r < TH; ++r) {  // both depths of the pixel per packed operation
+        const unsigned long long d2 = pack2(dlo[r], dhi[r]);
+        const float2 z = unpack2(fma2(pack2(rz, rz), d2, tz2));
+        const unsigned long long i2 = pack2(rcp_approx(z.x), rcp_approx(z.y));
+        const float2 u = unpack2(mul2(fma2(pack2(rx, rx), d2, tx2), i2)), w = unpack2(mul2(fma2(pack2(ry, ry), d2, ty2), i2));
+        umin = fminf(umin, fminf(u.x, u.y)); umax = fmaxf(umax, fmaxf(u.x, u.y));
+        wmin = fminf(wmin, fminf(w.x, w.y)); wmax = fmaxf(wmax, fmaxf(w.x, w.y));
+        zmin = fminf(zmin, fminf(z.x, z.y));
         rx += pose[1]; ry += pose[4]; rz += pose[7];
     }
 #pragma unroll
@@ -201,35 +201,42 @@ et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_
 
     if (warp == K::NCW) {
         // ------------------------------------------------------------------ producer warp
+        // Lane = tile column.  Per pixel the farthest / nearest hypothesis (first and last plane: the schedules are monotone in
+        // d; with an unsorted volume the consumers' own in-box test sends the affected warps to the global-gather path).  The
+        // next tile's planes are requested before this tile's boxes are issued, so the producer never waits for DRAM itself.
         int slot = 0, phase = 0;
+        float dlo[TH], dhi[TH], dan[TH], dbn[TH];
+        auto request_range = [&](int tile, float (&da)[TH], float (&db)[TH]) {
+            const int b = tile / (tiles_x * tiles_y), t2 = tile % (tiles_x * tiles_y);
+            const int x_lo = (t2 % tiles_x) * TW, y_lo = (t2 / tiles_x) * TH;
+            const int xx = min(x_lo + lane, a.W - 1);
+            const float* hp = a.hypo + (long long)b * D * plane;
+#pragma unroll
+            for (int r = 0; r < TH; ++r) {
+                const int yy = min(y_lo + r, a.H - 1);
+                da[r] = __ldg(hp + yy * a.W + xx);
+                db[r] = __ldg(hp + (long long)(D - 1) * plane + yy * a.W + xx);
+            }
+        };
+        if ((int)blockIdx.x < ntiles) request_range(blockIdx.x, dan, dbn);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / (tiles_x * tiles_y), t2 = tile % (tiles_x * tiles_y);
             const int ty = t2 / tiles_x, tx = t2 % tiles_x;
             const int x_lo = tx * TW, y_lo = ty * TH;
-            const int x_hi = min(x_lo + TW, a.W) - 1, y_hi = min(y_lo + TH, a.H) - 1;
-            // depth range of every pixel of the lane's column (all D hypotheses: no sorted schedule is assumed)
-            float dlo[TH], dhi[TH];
+            const int xx = min(x_lo + lane, a.W - 1);
             bool bad = false;
-            const float* hp = a.hypo + (long long)b * D * plane;
-            const int xx = min(x_lo + lane, x_hi);
 #pragma unroll
             for (int r = 0; r < TH; ++r) {
-                const int yy = min(y_lo + r, y_hi);
-                float lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const float v = __ldg(hp + (long long)d * plane + yy * a.W + xx);
-                    bad = bad || !(v > 0.f) || !(v < 1e30f);
-                    lo = fminf(lo, v);
-                    hi = fmaxf(hi, v);
-                }
-                dlo[r] = lo; dhi[r] = hi;
+                dlo[r] = fminf(dan[r], dbn[r]);
+                dhi[r] = fmaxf(dan[r], dbn[r]);
+                bad = bad || !(dlo[r] > 0.f) || !(dhi[r] < 1e30f);
             }
             const bool depth_ok = __all_sync(0xffffffffu, !bad);
+            if (tile + (int)gridDim.x < ntiles) request_range(tile + gridDim.x, dan, dbn);  // in flight while this tile's boxes go out
             for (int v = 0; v < a.V; ++v) {
-                mbar_wait(&ctrl->empty[slot], phase ^ 1);  // all consumer warps have released the slot's previous box
                 int x0, y0, rows;
                 tile_footprint<TH>(a.pose + ((long long)b * a.V + v) * 12, (float)xx, (float)y_lo, dlo, dhi, depth_ok, K::BH, x0, y0, rows);
+                mbar_wait(&ctrl->empty[slot], phase ^ 1);  // all consumer warps have released the slot's previous box
                 if (lane == 0) {
                     ctrl->box[slot] = make_int4(x0, y0, rows, 0);
                     if (rows > 0) {
