@@ -717,153 +717,8 @@ __global__ void __launch_bounds__(256) fpn_out4_gather2_kernel(const float* __re
     dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
-// ---- variant 3 (opt-in, MVSTER_FPN_GATHER=3; not timed yet): built for the instruction count ----------------------------
-// Counting SASS shows what bounds variants 1 and 2: ~1750 executed instructions per output pixel (576 + 288 scalar FMAs of
-// arithmetic, one broadcast LDS per FMA group, 64-bit address arithmetic per sample; variant 2 adds a staging loop with four
-// integer divisions per element) next to 45 x 16 L1 wavefronts.  Here
-//   * weights come from shared memory as broadcast 128-bit reads (one wavefront each) shared by the thread's two pixels
-//     (passing them as a __grid_constant__ parameter so that FFMA2 takes them from uniform registers was tried: with ~650
-//     weight pairs live in one unrolled body ptxas shuffles them through UMOV / R2UR and the kernel needs 229 registers);
-//   * the arithmetic is packed two output channels per instruction (fma.rn.f32x2 / mul / add), 64 packed operations per
-//     (pixel, tap) instead of ~150 scalar ones;
-//   * one thread owns the two pixels (y, x), (y+1, x): they share the weights and 2 of the 4 rows of c0;
-//   * the tile's c0 halo and U patches are staged per ROW by whole warps (contiguous 128-bit loads, no divisions), in the
-//     split-halves layout of variant 2 (conflict-free 128-bit reads by consecutive lanes).
-// Same sum as variants 1/2 with the FMAs written out explicitly (so not bit-identical to what nvcc contracts in variant 1;
-// tests/test_emu_kernels.py bounds the difference and checks against F.conv2d).
-
-constexpr int G3_SMEM_FLOATS = 9 * 2 * G2_UPX * 4 + 2 * G2_CPX * 4 + 576 + 72;
-
-__global__ void __launch_bounds__(128) fpn_out4_gather3_kernel(const float* __restrict__ U, long long tap_stride, const float* __restrict__ c0,
-                                                               const float* __restrict__ wc, const float* __restrict__ bt,
-                                                               float* __restrict__ out, int N, int H, int W) {
-    using namespace cf4;
-    extern __shared__ __align__(16) float g3_s[];
-    float* const u_s = g3_s;                          // [9][2][G2_UPX][4]
-    float* const c_s = u_s + 9 * 2 * G2_UPX * 4;      // [2][G2_CPX][4]
-    float* const wc_s = c_s + 2 * G2_CPX * 4;         // [9][8][8] composite weights, then [9][8] lateral bias seen through each tap
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.z;
-    for (int i = tid; i < 576 + 72; i += 128) wc_s[i] = __ldg(i < 576 ? wc + i : bt + (i - 576));
-    const int x0 = blockIdx.x * G2_TW, y0 = blockIdx.y * G2_TH;
-    const int Hc = H / 2, Wc = W / 2;
-    const float sy = Hc > 1 ? __fdiv_rn((float)(Hc - 1), (float)(H - 1)) : 0.f, sx = Wc > 1 ? __fdiv_rn((float)(Wc - 1), (float)(W - 1)) : 0.f;
-    // half-resolution patch covered by the tile's bilinear samples (as in variant 2)
-    const int fy_lo = max(y0 - 1, 0), fy_hi = min(y0 + G2_TH, H - 1), fx_lo = max(x0 - 1, 0), fx_hi = min(x0 + G2_TW, W - 1);
-    const int r_lo = min((int)floorf(__fmul_rn(sy, (float)fy_lo)), Hc - 1), c_lo = min((int)floorf(__fmul_rn(sx, (float)fx_lo)), Wc - 1);
-    int r_hi = min((int)floorf(__fmul_rn(sy, (float)fy_hi)), Hc - 1), c_hi = min((int)floorf(__fmul_rn(sx, (float)fx_hi)), Wc - 1);
-    r_hi += (r_hi < Hc - 1); c_hi += (c_hi < Wc - 1);
-    const int nr = r_hi - r_lo + 1, nc = c_hi - c_lo + 1;  // <= G2_RMAX, G2_CMAX
-    // staging, one warp per row: a patch row of one tap plane is nc * 8 contiguous floats
-    const float* Ub = U + ((long long)b * Hc + r_lo) * Wc * 8 + c_lo * 8;
-    for (int tap = 0; tap < 9; ++tap) {
-        for (int r = warp; r < nr; r += 4) {
-            const float4* src = reinterpret_cast<const float4*>(Ub + tap * tap_stride + (long long)r * Wc * 8);
-            for (int l = lane; l < 2 * nc; l += 32)
-                *reinterpret_cast<float4*>(u_s + ((tap * 2 + (l & 1)) * G2_UPX + r * G2_CMAX + (l >> 1)) * 4) = __ldg(src + l);
-        }
-    }
-    const float* cb = c0 + (long long)b * H * W * 8;
-    for (int r = warp; r < G2_TH + 2; r += 4) {
-        const int yy = y0 - 1 + r;
-        const bool row_ok = (unsigned)yy < (unsigned)H;
-        const float4* src = reinterpret_cast<const float4*>(cb + ((long long)yy * W + (x0 - 1)) * 8);
-        for (int l = lane; l < 2 * (G2_TW + 2); l += 32) {
-            const int xx = x0 - 1 + (l >> 1);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok && (unsigned)xx < (unsigned)W) v = __ldg(src + l);
-            *reinterpret_cast<float4*>(c_s + ((l & 1) * G2_CPX + r * (G2_TW + 2) + (l >> 1)) * 4) = v;
-        }
-    }
-    __syncthreads();
-    const int x = x0 + lane, ya = y0 + 2 * warp;          // this thread: pixels (ya, x) and (ya + 1, x)
-    if (x >= W || ya >= H) return;
-    // align_corners=True source columns of the fine columns x-1..x+1 and source rows of the fine rows ya-1..ya+2 (patch coordinates)
-    int rx0[3], rx1[3], ry0[4], ry1[4];
-    float wx1[3], wy1[4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int xx = min(max(x + k - 1, 0), W - 1);
-        const float fx = __fmul_rn(sx, (float)xx);
-        rx0[k] = min((int)floorf(fx), Wc - 1);
-        rx1[k] = rx0[k] + (rx0[k] < Wc - 1);
-        wx1[k] = fminf(fmaxf(fx - (float)rx0[k], 0.f), 1.f);
-        rx0[k] -= c_lo; rx1[k] -= c_lo;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int yy = min(max(ya + k - 1, 0), H - 1);
-        const float fy = __fmul_rn(sy, (float)yy);
-        ry0[k] = min((int)floorf(fy), Hc - 1);
-        ry1[k] = ry0[k] + (ry0[k] < Hc - 1);
-        wy1[k] = fminf(fmaxf(fy - (float)ry0[k], 0.f), 1.f);
-        ry0[k] = (ry0[k] - r_lo) * G2_CMAX; ry1[k] = (ry1[k] - r_lo) * G2_CMAX;
-    }
-    unsigned long long acc[2][4];
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[p][j] = pack2(0.f, 0.f);
-    // Zero padding of the 3x3 conv without branches (the warp stays convergent, which keeps the weights in uniform registers):
-    // a tap outside the image reads staged zeros of c0, and its bias and bilinear weights are multiplied by a 0/1 mask.
-    float colm[3], rowm[4];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) colm[k] = (unsigned)(x + k - 1) < (unsigned)W ? 1.f : 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) rowm[k] = (unsigned)(ya + k - 1) < (unsigned)H ? 1.f : 0.f;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int tap = ky * 3 + kx;
-            const float lx1 = wx1[kx], lx0 = 1.f - lx1;
-            const unsigned long long lx0v = pack2(lx0, lx0), lx1v = pack2(lx1, lx1);
-#pragma unroll
-            for (int p = 0; p < 2; ++p) {                           // pixel (ya + p, x): H is even, so both rows exist
-                const float m = rowm[p + ky] * colm[kx];
-                const unsigned long long mv = pack2(m, m);
-                // (a) lateral path: composite 3x3 conv on c0 (+ the lateral bias seen through this tap)
-                const int cp = (2 * warp + p + ky) * (G2_TW + 2) + (lane + kx);
-                const float4 cl = *reinterpret_cast<const float4*>(c_s + cp * 4), ch = *reinterpret_cast<const float4*>(c_s + (G2_CPX + cp) * 4);
-                const float cv[8] = {cl.x, cl.y, cl.z, cl.w, ch.x, ch.y, ch.z, ch.w};
-                {
-                    const float4 b0 = *reinterpret_cast<const float4*>(wc_s + 576 + tap * 8), b1 = *reinterpret_cast<const float4*>(wc_s + 580 + tap * 8);
-                    acc[p][0] = fma2(mv, pack2(b0.x, b0.y), acc[p][0]); acc[p][1] = fma2(mv, pack2(b0.z, b0.w), acc[p][1]);
-                    acc[p][2] = fma2(mv, pack2(b1.x, b1.y), acc[p][2]); acc[p][3] = fma2(mv, pack2(b1.z, b1.w), acc[p][3]);
-                }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const unsigned long long vv = pack2(cv[c], cv[c]);
-                    const float4 w0 = *reinterpret_cast<const float4*>(wc_s + tap * 64 + c * 8), w1 = *reinterpret_cast<const float4*>(wc_s + tap * 64 + c * 8 + 4);
-                    acc[p][0] = fma2(vv, pack2(w0.x, w0.y), acc[p][0]); acc[p][1] = fma2(vv, pack2(w0.z, w0.w), acc[p][1]);
-                    acc[p][2] = fma2(vv, pack2(w1.x, w1.y), acc[p][2]); acc[p][3] = fma2(vv, pack2(w1.z, w1.w), acc[p][3]);
-                }
-                // (b) top-down path: bilinear sample of U_tap at the fine position
-                const float ly1 = wy1[p + ky] * m, ly0 = (1.f - wy1[p + ky]) * m;
-                const unsigned long long ly0v = pack2(ly0, ly0), ly1v = pack2(ly1, ly1);
-                const int p00 = ry0[p + ky] + rx0[kx], p01 = ry0[p + ky] + rx1[kx], p10 = ry1[p + ky] + rx0[kx], p11 = ry1[p + ky] + rx1[kx];
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const float* up = u_s + (tap * 2 + half) * G2_UPX * 4;
-                    const float4 a00 = *reinterpret_cast<const float4*>(up + p00 * 4), a01 = *reinterpret_cast<const float4*>(up + p01 * 4);
-                    const float4 a10 = *reinterpret_cast<const float4*>(up + p10 * 4), a11 = *reinterpret_cast<const float4*>(up + p11 * 4);
-                    const unsigned long long top_lo = fma2(lx1v, pack2(a01.x, a01.y), mul2(lx0v, pack2(a00.x, a00.y)));
-                    const unsigned long long bot_lo = fma2(lx1v, pack2(a11.x, a11.y), mul2(lx0v, pack2(a10.x, a10.y)));
-                    const unsigned long long top_hi = fma2(lx1v, pack2(a01.z, a01.w), mul2(lx0v, pack2(a00.z, a00.w)));
-                    const unsigned long long bot_hi = fma2(lx1v, pack2(a11.z, a11.w), mul2(lx0v, pack2(a10.z, a10.w)));
-                    acc[p][half * 2] = add2(acc[p][half * 2], fma2(ly1v, bot_lo, mul2(ly0v, top_lo)));
-                    acc[p][half * 2 + 1] = add2(acc[p][half * 2 + 1], fma2(ly1v, bot_hi, mul2(ly0v, top_hi)));
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        const float2 a0 = unpack2(acc[p][0]), a1 = unpack2(acc[p][1]), a2 = unpack2(acc[p][2]), a3 = unpack2(acc[p][3]);
-        float4* dst = reinterpret_cast<float4*>(out + (((long long)b * H + ya + p) * W + x) * 8);
-        dst[0] = make_float4(a0.x, a0.y, a1.x, a1.y);
-        dst[1] = make_float4(a2.x, a2.y, a3.x, a3.y);
-    }
-}
+// (A third variant - two pixels per thread, packed FMAs, 1111 instructions per pixel - measured 262 us against 168 us for
+// variant 2 and 199 us for variant 1 on B200 and was removed: profiles/r02_glue_ab.md.)
 
 }  // namespace mvster
 
@@ -883,13 +738,6 @@ extern "C" int mvster_fpn_out4_gather_f32(const float* U, int u_channels, const 
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<dim3(mvster::ceil_div(W, mvster::G2_TW), mvster::ceil_div(H, mvster::G2_TH), N), 256, smem, (cudaStream_t)stream>>>(U, tap_stride, c0, w_comp, b_tap, out, N, H, W);
         return mvster::check_launch("fpn_out4_gather2_kernel");
-    }
-    if (variant && atoi(variant) == 3 && u_channels == 8 && N < 65536) {  // two pixels per thread, packed FMAs (opt-in until it has been timed)
-        auto k = mvster::fpn_out4_gather3_kernel;
-        const size_t smem = (size_t)mvster::G3_SMEM_FLOATS * sizeof(float);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<dim3(mvster::ceil_div(W, mvster::G2_TW), mvster::ceil_div(H, mvster::G2_TH), N), 128, smem, (cudaStream_t)stream>>>(U, tap_stride, c0, w_comp, b_tap, out, N, H, W);
-        return mvster::check_launch("fpn_out4_gather3_kernel");
     }
     mvster::fpn_out4_gather_kernel<<<mvster::ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(U, u_channels, tap_stride, c0, w_comp, b_tap, out, N, H, W);
     return mvster::check_launch("fpn_out4_gather_kernel");

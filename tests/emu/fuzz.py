@@ -37,31 +37,29 @@ def setenv(k, v):
 
 def variants(iters, rng):
     lib = _lib.load()
-    worst = {"gather3": 0.0, "merge3": 0.0}
+    worst = {"merge3": 0.0}
     for _ in range(iters):
         N, H, W = int(rng.randint(1, 3)), 2 * int(rng.randint(1, 20)), 2 * int(rng.randint(1, 45))
         U, c0 = t(rng.randn(9, N, H // 2, W // 2, 8)), t(rng.randn(N, H, W, 8))
         wc, bt = t(rng.randn(9, 8, 8) / 8), t(rng.randn(9, 8))
         outs = {}
-        for v in (None, "2", "3"):
+        for v in ("1", "2"):
             setenv("MVSTER_FPN_GATHER", v)
             out = torch.full((N, H, W, 8), float("nan"))
             assert lib.mvster_fpn_out4_gather_f32(capi._ptr(U), 8, capi._ptr(c0), capi._ptr(wc), capi._ptr(bt), capi._ptr(out), N, H, W, None) == 0
             outs[v] = out
         setenv("MVSTER_FPN_GATHER", None)
-        e = ((outs["3"] - outs[None]).abs().max() / outs[None].abs().max()).item()
-        assert torch.equal(outs["2"], outs[None]) and torch.isfinite(outs["3"]).all() and e < 2e-6, ("gather", N, H, W, e)
-        worst["gather3"] = max(worst["gather3"], e)
+        assert torch.isfinite(outs["1"]).all() and torch.equal(outs["2"], outs["1"]), ("gather", N, H, W)
         CL = int(rng.choice([8, 16, 32]))
         top, lat = t(rng.randn(N, H // 2, W // 2, 64)), t(rng.randn(N, H, W, CL))
         w, b = t(rng.randn(CL, 64) / 4), t(rng.randn(64))
         outs = {}
-        for v in (None, "2", "3"):
+        for v in ("1", "2", "3"):
             setenv("MVSTER_FPN_MERGE", v)
             outs[v] = fpn_engine._merge(top, lat, w, b)
         setenv("MVSTER_FPN_MERGE", None)
-        e = ((outs["3"] - outs[None]).abs().max() / outs[None].abs().max()).item()
-        assert torch.equal(outs["2"], outs[None]) and torch.isfinite(outs["3"]).all() and e < 2e-6, ("merge", N, H, W, CL, e)
+        e = ((outs["3"] - outs["1"]).abs().max() / outs["1"].abs().max()).item()
+        assert torch.equal(outs["2"], outs["1"]) and torch.isfinite(outs["3"]).all() and e < 2e-6, ("merge", N, H, W, CL, e)
         worst["merge3"] = max(worst["merge3"], e)
         Hs, Ws = int(rng.randint(1, 12)), int(rng.randint(1, 40))
         img, wt, bs = t(rng.rand(N, 3, Hs, Ws)), t(rng.randn(9, 3, 8) / 3), t(rng.randn(8))
@@ -76,11 +74,11 @@ def variants(iters, rng):
         G, D, Wv = int(rng.choice([4, 8])), int(rng.randint(1, 4)), 2 * int(rng.randint(1, 20))
         x, w0, b0 = t(rng.randn(N, D, Hs, Wv, G)), t(rng.randn(9, G, 8) / 3), t(rng.randn(8))
         outs = {}
-        for v in (None, "1"):
+        for v in ("0", "1"):
             setenv("MVSTER_CONV0_PX4", v)
             outs[v] = capi.conv3d_ndhwc(x, w0, b0, 1)
         setenv("MVSTER_CONV0_PX4", None)
-        assert torch.equal(outs["1"], outs[None]), ("conv0", N, D, Hs, Wv, G)
+        assert torch.equal(outs["1"], outs["0"]), ("conv0", N, D, Hs, Wv, G)
     return worst
 
 

@@ -78,6 +78,14 @@ inline float __shfl_xor_sync(unsigned, float v, int o) {
     w.bar.arrive_and_wait();
     return r;
 }
+inline int __shfl_sync(unsigned, int v, int src) {
+    emu::Warp& w = *emu::ctx.warp;
+    w.vote[emu::ctx.lane] = v;
+    w.bar.arrive_and_wait();
+    const int r = w.vote[src & 31];
+    w.bar.arrive_and_wait();
+    return r;
+}
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }

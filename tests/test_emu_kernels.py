@@ -96,7 +96,7 @@ def et_inputs(B, nv, C, G, D, H, W, step, seed=0):
 
 
 @pytest.mark.parametrize("case", ET_SMALL)
-def test_et_kernels_on_cpu_match_oracle(emu, case, monkeypatch):
+def test_et_kernels_on_cpu_match_oracle(emu, case):
     B, nv, C_, G, D, H, W, step = case
     feats, cams, hypo = et_inputs(*case)
     want = oracle.et_aggregate(feats, cams, hypo, True, G, 2.0)
@@ -106,10 +106,6 @@ def test_et_kernels_on_cpu_match_oracle(emu, case, monkeypatch):
     for kw in variants:
         got = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, **kw))
         assert (got - want).abs().max().item() <= 2e-4 * scale, kw
-    if D == 4 and C_ in (8, 16) and G == 4:  # depth-across-lanes variant (opt-in)
-        monkeypatch.setenv("MVSTER_ET_DLANE", "1")
-        got = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, window=False))
-        assert (got - want).abs().max().item() <= 2e-4 * scale
 
 
 WIN_SMALL = [  # (B, nv, C, G, D, H, W, step_deg, rel_span): hypotheses within one or two source cells -> window path
@@ -171,6 +167,10 @@ def test_tma_staged_kernel_on_cpu_matches_oracle(emu, case, monkeypatch):
         capi.et_fuse(ref, srcs[k:], pose[:, k:].contiguous(), hypo, G, 2.0, cost=cost, wsum=wsum, partial=True, accumulate=True, tma=True)
     capi.et_normalize(cost, wsum)
     assert (from_ndhwc(cost) - want).abs().max().item() <= 2e-4 * scale
+    monkeypatch.setenv("MVSTER_ET_TMA_BOXES", "0")  # source boxes derived by the kernel's producer warp instead of the preceding launch
+    got_b0 = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=True))
+    assert "tma" in capi.et_last_kernel() and (got_b0 - want).abs().max().item() <= 2e-4 * scale
+    monkeypatch.delenv("MVSTER_ET_TMA_BOXES")
     if C_ == 8:
         monkeypatch.setenv("MVSTER_ET_TMA_TH", "7")
         got7 = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=True))
@@ -279,7 +279,8 @@ def test_training_step_with_kernels_on_cpu_matches_pytorch_ops(emu, monkeypatch)
         out = model(imgs, proj, dv)
         loss = MVS4net_loss(out, gt, mask, stage_lw=[1, 1, 1, 1], l1ot_lw=[1, 1], inverse_depth=True, mono=True)[0]
         loss.backward()
-        assert _lib.launch_count() - n0 == (16 if use else 0)       # per stage: pose, forward, normalise, backward
+        n = _lib.launch_count() - n0                                # per stage: pose, [tile boxes,] forward, normalise, backward
+        assert (16 <= n <= 20) if use else n == 0
         losses[use] = loss.item()
         grads[use] = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     assert abs(losses[True] - losses[False]) <= 1e-5 * abs(losses[False])
@@ -311,7 +312,7 @@ def test_more_source_views_than_one_launch_takes_on_cpu(emu):
     want = oracle.et_aggregate(feats, cams, hypo, True, 4, 2.0)
     n0 = _lib.launch_count()
     got = from_ndhwc(capi.et_fuse(nhwc(feats[0]), [nhwc(f) for f in feats[1:]], capi.pose(cams), hypo, 4, 2.0))
-    assert _lib.launch_count() - n0 == 4                                  # pose, two chained launches, normalise
+    assert 4 <= _lib.launch_count() - n0 <= 6                             # pose, two chained launches (+ their tile-box launches), normalise
     assert (got - want).abs().max().item() <= 2e-4 * want.abs().max().item()
     gout = torch.from_numpy(np.random.RandomState(1).randn(1, 4, 4, 4, 8).astype(np.float32))
     f64 = [f.double().requires_grad_(True) for f in feats]
@@ -432,18 +433,14 @@ def test_tiled_gather_variant_returns_the_same_bits_on_cpu(emu, monkeypatch, N, 
     monkeypatch.setenv("MVSTER_FPN_GATHER", "2")
     got = run()
     assert torch.isfinite(want).all() and torch.equal(got, want)
-    # variant 3 (two pixels per thread, packed FMAs, masks instead of branches): the same sum with explicitly fused
-    # multiply-adds, so equal to rounding; and all three against the definition in float64
-    monkeypatch.setenv("MVSTER_FPN_GATHER", "3")
-    got3 = run()
     scale = want.abs().max().item()
-    assert torch.isfinite(got3).all() and (got3 - want).abs().max().item() <= 2e-6 * scale
+    # both against the definition in float64
     up = F.interpolate(U.double().permute(1, 0, 4, 2, 3).reshape(N, 72, H // 2, W // 2), scale_factor=2, mode="bilinear",
                        align_corners=True).reshape(N, 9, 8, H, W)                                   # up2(U_tap) per tap
     lat = torch.einsum("nyxc,tco->ntoyx", c0.double(), wc.double()) + bt.double().reshape(1, 9, 8, 1, 1)
     term = F.pad(up + lat, (1, 1, 1, 1))                                                            # zero padding of the 3x3 conv
     ref = sum(term[:, ky * 3 + kx, :, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)).permute(0, 2, 3, 1)
-    for o in (want, got3):
+    for o in (want, got):
         assert (o.double() - ref).abs().max().item() <= 2e-6 * scale
 
 
@@ -468,7 +465,7 @@ def test_four_pixel_merge_variant_returns_the_same_bits_on_cpu(emu, monkeypatch,
     assert torch.isfinite(got3).all() and (got3 - want).abs().max().item() <= 2e-6 * scale
     ref = F.interpolate(top.double().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1) \
         + lat.double() @ w.double() + bias.double()
-    for o in (want, got3):
+    for o in (want, got):
         assert (o.double() - ref).abs().max().item() <= 2e-6 * scale
 
 

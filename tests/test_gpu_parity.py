@@ -126,7 +126,7 @@ def test_et_fuse_tiled_and_generic_kernels_agree(case):
     n0 = _lib.launch_count()
     tiled = capi.et_fuse(ref, srcs, pose, hy, G, 2.0)
     generic = capi.et_fuse(ref, srcs, pose, hy, G, 2.0, generic=True)
-    assert _lib.launch_count() - n0 == 2
+    assert _lib.launch_count() - n0 in (2, 3)  # the TMA-staged kernel is preceded by its tile-box launch
     err = (tiled - generic).abs().max().item() / generic.abs().max().item()
     record(f"et_tiled_vs_generic_{case}", rel_to_max=err)
     assert err < 2e-4

@@ -53,6 +53,10 @@ def test_tma_kernel_matches_oracle_and_window_kernel(case, monkeypatch):
         capi.et_fuse(ref, srcs[k:], pose[:, k:].contiguous(), hy, G, 2.0, cost=cost, wsum=wsum, partial=True, accumulate=True, tma=True)
     capi.et_normalize(cost, wsum)
     assert (from_ndhwc(cost) - want).abs().max().item() <= 2e-4 * scale
+    monkeypatch.setenv("MVSTER_ET_TMA_BOXES", "0")  # source boxes derived by the kernel's producer warp instead of the preceding launch
+    got_b0 = from_ndhwc(capi.et_fuse(ref, srcs, pose, hy, G, 2.0, tma=True))
+    assert "tma" in capi.et_last_kernel() and (got_b0 - want).abs().max().item() <= 2e-4 * scale
+    monkeypatch.delenv("MVSTER_ET_TMA_BOXES")
     if C_ == 8:
         monkeypatch.setenv("MVSTER_ET_TMA_TH", "7")
         got7 = from_ndhwc(capi.et_fuse(ref, srcs, pose, hy, G, 2.0, tma=True))

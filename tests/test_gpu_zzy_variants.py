@@ -34,7 +34,7 @@ def test_gather_variants(monkeypatch, N, H, W):
     want = run()
     scale = want.abs().max().item()
     assert torch.isfinite(want).all()
-    for variant in ("2", "3"):
+    for variant in ("2",):
         monkeypatch.setenv("MVSTER_FPN_GATHER", variant)
         got = run()
         assert torch.isfinite(got).all() and (got - want).abs().max().item() <= 2e-6 * scale, variant

@@ -22,7 +22,7 @@ def test_backward_kernel_matches_reference_gradients(name):
     cost = train_ops.aggregate(leaves, c["cams"].to(DEV), c["hypo"].to(DEV), c["G"], 2.0)
     assert (cost.detach().cpu() - c["cost"]).abs().max().item() <= 2e-4 * c["cost"].abs().max().item()
     grads = torch.autograd.grad(cost, leaves, c["gout"].to(DEV))
-    assert _lib.launch_count() - n0 == 4                         # pose, forward (partial), normalise, backward
+    assert 4 <= _lib.launch_count() - n0 <= 5                    # pose, [tile boxes,] forward (partial), normalise, backward
     for v in range(c["nv"]):
         scale = c["grads"][v].abs().max().item()
         err = (grads[v].cpu() - c["grads"][v]).abs().max().item()

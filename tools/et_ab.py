@@ -25,11 +25,13 @@ VARIANTS = [
     ("tma_7x32", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7")),
     ("tma_15x32_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", IL="1")),
     ("tma_7x32_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7", IL="1")),
+    ("tma_15x32_interleaved_boxes_in_kernel*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", IL="1", MVSTER_ET_TMA_BOXES="0")),
+    ("tma_7x32_interleaved_boxes_in_kernel*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7", IL="1", MVSTER_ET_TMA_BOXES="0")),
     ("win", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0")),
     ("win_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0", IL="1")),
     ("win_mb5", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0", MVSTER_ET_WIN_MB="5")),
 ]
-KEYS = ("MVSTER_ET_WIN", "MVSTER_ET_WIN_MB", "MVSTER_ET_PREFETCH", "MVSTER_ET_TMA", "MVSTER_ET_TMA_TH")
+KEYS = ("MVSTER_ET_WIN", "MVSTER_ET_WIN_MB", "MVSTER_ET_PREFETCH", "MVSTER_ET_TMA", "MVSTER_ET_TMA_TH", "MVSTER_ET_TMA_DEBUG", "MVSTER_ET_TMA_BOXES")
 
 
 def main():

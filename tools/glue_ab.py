@@ -65,7 +65,7 @@ def main():
         _lib.check(lib.mvster_fpn_out4_gather_f32(capi._ptr(U), 8, capi._ptr(c0), capi._ptr(wc), capi._ptr(bt), capi._ptr(out), N, H, W,
                                                   capi._stream()), "gather")
         return out
-    cases.append((f"fpn_out4_gather ({N} x {H} x {W})", "MVSTER_FPN_GATHER", ["1", "2", "3"], gather, (U.numel() + c0.numel() + out.numel()) * 4))
+    cases.append((f"fpn_out4_gather ({N} x {H} x {W})", "MVSTER_FPN_GATHER", ["1", "2"], gather, (U.numel() + c0.numel() + out.numel()) * 4))
 
     for (h, w, CL) in ((H // 2, W // 2, 16), (H // 4, W // 4, 32)):
         top, lat, wl, bl = r(N, h // 2, w // 2, 64), r(N, h, w, CL), r(CL, 64) / 4, r(64)
