@@ -105,14 +105,7 @@ int mvster_et_fuse_f32(const float* ref, const float* const* src_host, int V, co
                        const float* hypo, float* cost, float* wsum,
                        int B, int C, int G, int D, int H, int W, int Hs, int Ws,
                        float attn_temp, int flags, mvster_stream_t stream);
-/* Same with caller-provided scratch (16-byte aligned, mvster_et_fuse_workspace_bytes bytes; contents undefined afterwards): the
- * TMA-staged kernel then gets the source box of every (reference tile, view) from a small launch that precedes it instead of
- * deriving it in its producer warp.  workspace = NULL behaves like mvster_et_fuse_f32. */
-size_t mvster_et_fuse_workspace_bytes(int B, int V, int H, int W);
-int mvster_et_fuse_ws_f32(const float* ref, const float* const* src_host, int V, const float* pose,
-                          const float* hypo, float* cost, float* wsum,
-                          int B, int C, int G, int D, int H, int W, int Hs, int Ws,
-                          float attn_temp, int flags, void* workspace, size_t workspace_bytes, mvster_stream_t stream);
+
 
 /* cost[b,d,y,x,g] = acc / (1e-8 + wsum[b,d,y,x]) in place: the division of
  * mvs4net_utils.py:1060 applied after the partials were all-reduced. */

@@ -31,8 +31,6 @@ SIGNATURES = {
     "mvster_reg3d_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_pose_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mvster_et_fuse_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
-    "mvster_et_fuse_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
-    "mvster_et_fuse_ws_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, C.c_size_t, _p]),
     "mvster_et_normalize_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "mvster_et_last_kernel": (C.c_char_p, []),
     "mvster_et_fuse_bwd_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _p, _p, C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),

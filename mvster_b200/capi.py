@@ -139,11 +139,9 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
             wsum = torch.empty((B, D, H, W), device=ref.device, dtype=torch.float32)
         pose_c = _chk(pose[:, v0:v0 + len(chunk)].contiguous(), "pose", (B, len(chunk), 12))
         arr = (C.c_void_p * len(chunk))(*[s.data_ptr() for s in chunk])
-        ws_bytes = int(lib.mvster_et_fuse_workspace_bytes(B, len(chunk), H, W))
-        ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.int32, device=ref.device)  # source boxes of the TMA-staged kernel
-        _lib.check(lib.mvster_et_fuse_ws_f32(_ptr(ref), arr, len(chunk), _ptr(pose_c), _ptr(hypo), _ptr(cost), _ptr(wsum),
-                                             B, Cc, G, D, H, W, Hs, Ws, float(attn_temp), flags, _ptr(ws), ws_bytes, _stream()),
-                   "mvster_et_fuse_ws_f32")
+        _lib.check(lib.mvster_et_fuse_f32(_ptr(ref), arr, len(chunk), _ptr(pose_c), _ptr(hypo), _ptr(cost), _ptr(wsum),
+                                          B, Cc, G, D, H, W, Hs, Ws, float(attn_temp), flags, _stream()),
+                   "mvster_et_fuse_f32")
     if V > MAX_VIEWS and not partial:
         et_normalize(cost, wsum)
     return cost

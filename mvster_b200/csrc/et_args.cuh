@@ -14,7 +14,6 @@ struct EtArgs {
     float attn_temp, sqrt_c;
     int flags;
     int prefetch;  // window kernels: L2 prefetch of every view's window rows before the view loop
-    const int4* boxes;  // TMA kernel: [tiles][V] source boxes (x0, y0, rows, 0) from et_tile_boxes_kernel, or nullptr
 };
 
 }  // namespace mvster

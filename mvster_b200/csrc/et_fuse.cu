@@ -238,23 +238,10 @@ static int dispatch_cpg(const EtArgs& a, int cpg, int D, cudaStream_t st) {
 
 using namespace mvster;
 
-extern "C" size_t mvster_et_fuse_workspace_bytes(int B, int V, int H, int W) {
-    if (B <= 0 || V <= 0 || H <= 0 || W <= 0) return 0;
-    // one 16-byte box per (tile, view) for the smallest tile the TMA-staged kernels use (3 x 32 pixels)
-    return (size_t)B * ((H + 2) / 3) * ((W + 31) / 32) * V * 16;
-}
-
 extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host, int V, const float* pose,
                                   const float* hypo, float* cost, float* wsum,
                                   int B, int C, int G, int D, int H, int W, int Hs, int Ws,
                                   float attn_temp, int flags, mvster_stream_t stream) {
-    return mvster_et_fuse_ws_f32(ref, src_host, V, pose, hypo, cost, wsum, B, C, G, D, H, W, Hs, Ws, attn_temp, flags, nullptr, 0, stream);
-}
-
-extern "C" int mvster_et_fuse_ws_f32(const float* ref, const float* const* src_host, int V, const float* pose,
-                                     const float* hypo, float* cost, float* wsum,
-                                     int B, int C, int G, int D, int H, int W, int Hs, int Ws,
-                                     float attn_temp, int flags, void* workspace, size_t workspace_bytes, mvster_stream_t stream) {
     MVSTER_REQUIRE(ref && src_host && pose && hypo && cost, "mvster_et_fuse_f32: null pointer");
     MVSTER_REQUIRE(V >= 1 && V <= MVSTER_MAX_VIEWS, "mvster_et_fuse_f32: V=%d outside 1..%d", V, MVSTER_MAX_VIEWS);
     MVSTER_REQUIRE(B > 0 && H > 0 && W > 0 && Hs > 0 && Ws > 0, "mvster_et_fuse_f32: bad shape");
@@ -278,11 +265,6 @@ extern "C" int mvster_et_fuse_ws_f32(const float* ref, const float* const* src_h
     a.sqrt_c = (float)sqrt((double)C);  // math.sqrt(C) -> fp32 scalar
     a.flags = flags;
     { const char* pf = getenv("MVSTER_ET_PREFETCH"); a.prefetch = pf ? atoi(pf) : 1; }
-    { const char* dbg = getenv("MVSTER_ET_TMA_DEBUG"); if (dbg && atoi(dbg)) a.prefetch |= 256; }
-    // scratch for the per-tile source boxes of the TMA-staged kernel (16-byte aligned, >= mvster_et_fuse_workspace_bytes)
-    a.boxes = (workspace && !((uintptr_t)workspace & 15) && workspace_bytes >= mvster_et_fuse_workspace_bytes(B, V, H, W))
-                  ? reinterpret_cast<const int4*>(workspace) : nullptr;
-    { const char* nb = getenv("MVSTER_ET_TMA_BOXES"); if (nb && !atoi(nb)) a.boxes = nullptr; }  // A/B: 0 = footprints inside the kernel
     cudaStream_t st = (cudaStream_t)stream;
     int rc = MVSTER_OK;
     const bool plain = !(flags & (MVSTER_ET_GENERIC | MVSTER_ET_SQDIFF | MVSTER_ET_NO_FUSE_D));

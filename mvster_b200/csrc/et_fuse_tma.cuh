@@ -99,80 +99,6 @@ __device__ __forceinline__ Pix8 lds_tap(const unsigned char* smem, unsigned a_lo
     return t;
 }
 
-// Source boxes of every (tile, view), computed AHEAD of the main kernel (one small launch): the footprint needs the sampling
-// positions of all TH x 32 pixels of a tile at their extreme hypotheses - done by the main kernel's single producer warp that
-// is ~450 dependent instructions per view, as long as a consumer warp needs for the view itself, and the ring runs dry
-// (measured: 20 polls per consumer wait, profiles/r02_et_fuse_tma_ncu.md).  Here one CTA per tile does it with 128 threads and
-// the producer is left with one 16-byte load and the TMA issue per (tile, view).
-// boxes[tile * V + v] = (x0, y0, rows, 0); rows = 0: no box (the consumers gather that view from global memory).
-template <int TH, int D>
-__global__ void __launch_bounds__(128) et_tile_boxes_kernel(const EtArgs a, int4* __restrict__ boxes, int tiles_x, int tiles_y, int BH) {
-    constexpr int PPT = (TH * TW + 127) / 128;  // pixels per thread
-    __shared__ float red[4][6];
-    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = tile / (tiles_x * tiles_y), t2 = tile % (tiles_x * tiles_y);
-    const int x_lo = (t2 % tiles_x) * TW, y_lo = (t2 / tiles_x) * TH;
-    const int plane = a.H * a.W;
-    const float* hp = a.hypo + (long long)b * D * plane;
-    float px[PPT], py[PPT], dlo[PPT], dhi[PPT];
-    bool bad = false;
-#pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-        const int p = min(tid + i * 128, TH * TW - 1);  // the last threads repeat the tile's last pixel
-        const int xx = min(x_lo + p % TW, a.W - 1), yy = min(y_lo + p / TW, a.H - 1);
-        const float d0 = __ldg(hp + yy * a.W + xx), d1 = __ldg(hp + (long long)(D - 1) * plane + yy * a.W + xx);
-        px[i] = (float)xx; py[i] = (float)yy;
-        dlo[i] = fminf(d0, d1); dhi[i] = fmaxf(d0, d1);
-        bad = bad || !(dlo[i] > 0.f) || !(dhi[i] < 1e30f);
-    }
-    for (int v = 0; v < a.V; ++v) {
-        const float* pose = a.pose + ((long long)b * a.V + v) * 12;
-        float umin = INFINITY, umax = -INFINITY, wmin = INFINITY, wmax = -INFINITY, zmin = INFINITY;
-#pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-            const float rx = fmaf(pose[0], px[i], fmaf(pose[1], py[i], pose[2]));
-            const float ry = fmaf(pose[3], px[i], fmaf(pose[4], py[i], pose[5]));
-            const float rz = fmaf(pose[6], px[i], fmaf(pose[7], py[i], pose[8]));
-            const float za = fmaf(rz, dlo[i], pose[11]), zb = fmaf(rz, dhi[i], pose[11]);
-            const float ia = rcp_approx(za), ib = rcp_approx(zb);
-            const float ua = fmaf(rx, dlo[i], pose[9]) * ia, ub = fmaf(rx, dhi[i], pose[9]) * ib;
-            const float wa = fmaf(ry, dlo[i], pose[10]) * ia, wb = fmaf(ry, dhi[i], pose[10]) * ib;
-            umin = fminf(umin, fminf(ua, ub)); umax = fmaxf(umax, fmaxf(ua, ub));
-            wmin = fminf(wmin, fminf(wa, wb)); wmax = fmaxf(wmax, fmaxf(wa, wb));
-            zmin = fminf(zmin, fminf(za, zb));
-        }
-        float okf = bad ? 0.f : 1.f;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-            umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-            wmin = fminf(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
-            wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-            zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
-            okf = fminf(okf, __shfl_xor_sync(0xffffffffu, okf, o));
-        }
-        if (lane == 0) {
-            red[warp][0] = umin; red[warp][1] = umax; red[warp][2] = wmin; red[warp][3] = wmax; red[warp][4] = zmin; red[warp][5] = okf;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < 4; ++w) {
-                umin = fminf(umin, red[w][0]); umax = fmaxf(umax, red[w][1]);
-                wmin = fminf(wmin, red[w][2]); wmax = fmaxf(wmax, red[w][3]);
-                zmin = fminf(zmin, red[w][4]); okf = fminf(okf, red[w][5]);
-            }
-            // taps floor(u) .. floor(u) + 1 of every sample; 1/64 pixel of slack against the consumers' own rounding
-            const float m = 1.f / 64.f;
-            const float ulo = floorf(umin - m), uhi = floorf(umax + m), wlo = floorf(wmin - m), whi = floorf(wmax + m);
-            const float wcols = uhi - ulo + 2.f, wrows = whi - wlo + 2.f;
-            const bool ok = okf > 0.f && zmin > 0.f && fabsf(ulo) < 1e6f && fabsf(uhi) < 1e6f && fabsf(wlo) < 1e6f && fabsf(whi) < 1e6f &&
-                            wcols <= (float)BW && wrows <= (float)BH;  // every comparison is false for NaN
-            boxes[(long long)tile * a.V + v] = ok ? make_int4((int)ulo, (int)wlo, (((int)wrows + RB - 1) / RB) * RB, 0) : make_int4(0, 0, 0, 0);
-        }
-        __syncthreads();
-    }
-}
-
 // TH reference tile rows.  Warps per CTA = TH * LPP consumers + 1 producer; the register file is split over 4 scheduler
 // partitions, so 8 warps (x 2 CTAs per SM) or 13..16 warps (x 1) leave 128 registers per thread, 9 or 17 warps only 96.
 template <int C, int LPP, int TH_>
@@ -292,34 +218,6 @@ et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_
                 db[r] = __ldg(hp + (long long)(D - 1) * plane + yy * a.W + xx);
             }
         };
-        if (a.boxes) {
-            // boxes precomputed by et_tile_boxes_kernel: lane v holds the tile's box for view v, the next tile's row is requested
-            // before this tile's boxes are issued
-            int4 nxt = make_int4(0, 0, 0, 0);
-            if ((int)blockIdx.x < ntiles && lane < a.V) nxt = __ldg(a.boxes + (long long)blockIdx.x * a.V + lane);
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int b = tile / (tiles_x * tiles_y);
-                const int4 cur = nxt;
-                if (tile + (int)gridDim.x < ntiles && lane < a.V) nxt = __ldg(a.boxes + (long long)(tile + gridDim.x) * a.V + lane);
-                for (int v = 0; v < a.V; ++v) {
-                    const int x0 = __shfl_sync(0xffffffffu, cur.x, v), y0 = __shfl_sync(0xffffffffu, cur.y, v), rows = __shfl_sync(0xffffffffu, cur.z, v);
-                    mbar_wait(&ctrl->empty[slot], phase ^ 1);  // all consumer warps have released the slot's previous box
-                    if (lane == 0) {
-                        ctrl->box[slot] = make_int4(x0, y0, rows, 0);
-                        if (rows > 0) {
-                            mbar_arrive_expect_tx(&ctrl->full[slot], rows * K::PITCH);
-                            for (int r = 0; r < rows; r += RB)
-                                tma_rows(smem + slot * K::SLOT_STRIDE, r * K::PITCH, &maps.m[v], &ctrl->full[slot], x0, y0 + r, b);
-                        } else {
-                            mbar_arrive(&ctrl->full[slot]);
-                        }
-                    }
-                    __syncwarp();
-                    if (++slot == NSLOT) { slot = 0; phase ^= 1; }
-                }
-            }
-            return;
-        }
         if ((int)blockIdx.x < ntiles) request_range(blockIdx.x, dan, dbn);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / (tiles_x * tiles_y), t2 = tile % (tiles_x * tiles_y);
@@ -337,11 +235,7 @@ et_fuse_tma_kernel(const EtArgs a, const __grid_constant__ Maps maps, int tiles_
             if (tile + (int)gridDim.x < ntiles) request_range(tile + gridDim.x, dan, dbn);  // in flight while this tile's boxes go out
             for (int v = 0; v < a.V; ++v) {
                 int x0, y0, rows;
-                if (a.prefetch & 256) {  // MVSTER_ET_TMA_DEBUG=1 (timing experiments only, WRONG results): a fixed box around the tile
-                    x0 = x_lo - 12; y0 = y_lo - 6; rows = K::BH;
-                } else {
-                    tile_footprint<TH>(a.pose + ((long long)b * a.V + v) * 12, (float)xx, (float)y_lo, dlo, dhi, depth_ok, K::BH, x0, y0, rows);
-                }
+                tile_footprint<TH>(a.pose + ((long long)b * a.V + v) * 12, (float)xx, (float)y_lo, dlo, dhi, depth_ok, K::BH, x0, y0, rows);
                 mbar_wait(&ctrl->empty[slot], phase ^ 1);  // all consumer warps have released the slot's previous box
                 if (lane == 0) {
                     ctrl->box[slot] = make_int4(x0, y0, rows, 0);
@@ -676,11 +570,6 @@ static int launch_et_tma(const EtArgs& a, const Maps& maps, cudaStream_t st) {
         cudaGetLastError();
         return -100;
     }
-    if (a.boxes) {
-        et_tile_boxes_kernel<K::TH, D><<<(int)ntiles, 128, 0, st>>>(a, const_cast<int4*>(a.boxes), tiles_x, tiles_y, K::BH);
-        const int rc = check_launch("et_tile_boxes_kernel");
-        if (rc != MVSTER_OK) return rc;
-    }
     const int slots = sm_count_here() * K::MIN_CTAS;
     const int grid = (int)(ntiles < slots ? ntiles : slots);
     if (il) et_fuse_tma_kernel<C, G, D, LPP, TH_, true><<<grid, K::THREADS, K::SMEM, st>>>(a, maps, tiles_x, tiles_y, (int)ntiles);
@@ -708,8 +597,9 @@ static bool try_launch_tma(const EtArgs& a, int C, int G, int D, cudaStream_t st
     for (int v = 0; v < a.V; ++v)
         if (!make_map(&maps.m[v], a.src[v], a.B, a.Hs, a.Ws, C)) return false;
     int r = -100;
+    // measured on B200 (cfg2 stage 4, profiles/r02_et_fuse_tma_ncu.md): 7 x 32 tiles, two CTAs per SM 45.0 us; 15 x 32 tiles, one CTA 46.6 us
     const char* the = getenv("MVSTER_ET_TMA_TH");
-    const int th8 = the ? atoi(the) : 15;  // A/B: 7 = 7 x 32 tiles, 2 CTAs per SM
+    const int th8 = the ? atoi(the) : 7;  // A/B: 15 = 15 x 32 tiles, one CTA per SM
     if (C == 8) r = th8 == 7 ? launch_et_tma<8, 4, 4, 1, 7>(a, maps, st) : launch_et_tma<8, 4, 4, 1, 15>(a, maps, st);
     else if (C == 16) r = launch_et_tma<16, 4, 4, 2, 7>(a, maps, st);
     else r = launch_et_tma<32, 8, 8, 4, 3>(a, maps, st);

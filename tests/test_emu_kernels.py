@@ -167,15 +167,11 @@ def test_tma_staged_kernel_on_cpu_matches_oracle(emu, case, monkeypatch):
         capi.et_fuse(ref, srcs[k:], pose[:, k:].contiguous(), hypo, G, 2.0, cost=cost, wsum=wsum, partial=True, accumulate=True, tma=True)
     capi.et_normalize(cost, wsum)
     assert (from_ndhwc(cost) - want).abs().max().item() <= 2e-4 * scale
-    monkeypatch.setenv("MVSTER_ET_TMA_BOXES", "0")  # source boxes derived by the kernel's producer warp instead of the preceding launch
-    got_b0 = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=True))
-    assert "tma" in capi.et_last_kernel() and (got_b0 - want).abs().max().item() <= 2e-4 * scale
-    monkeypatch.delenv("MVSTER_ET_TMA_BOXES")
     if C_ == 8:
-        monkeypatch.setenv("MVSTER_ET_TMA_TH", "7")
-        got7 = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=True))
-        assert "7x32" in capi.et_last_kernel()
-        assert (got7 - want).abs().max().item() <= 2e-4 * scale
+        monkeypatch.setenv("MVSTER_ET_TMA_TH", "15")
+        got15 = from_ndhwc(capi.et_fuse(ref, srcs, pose, hypo, G, 2.0, tma=True))
+        assert "15x32" in capi.et_last_kernel()
+        assert (got15 - want).abs().max().item() <= 2e-4 * scale
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])

@@ -21,12 +21,10 @@ from mvster_b200 import capi, synth  # noqa: E402
 
 VARIANTS = [
     ("tiled", dict(MVSTER_ET_WIN="0")),
-    ("tma_15x32", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1")),
+    ("tma_15x32", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="15")),
     ("tma_7x32", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7")),
-    ("tma_15x32_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", IL="1")),
+    ("tma_15x32_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="15", IL="1")),
     ("tma_7x32_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7", IL="1")),
-    ("tma_15x32_interleaved_boxes_in_kernel*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", IL="1", MVSTER_ET_TMA_BOXES="0")),
-    ("tma_7x32_interleaved_boxes_in_kernel*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="1", MVSTER_ET_TMA_TH="7", IL="1", MVSTER_ET_TMA_BOXES="0")),
     ("win", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0")),
     ("win_interleaved*", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0", IL="1")),
     ("win_mb5", dict(MVSTER_ET_WIN="1", MVSTER_ET_TMA="0", MVSTER_ET_WIN_MB="5")),

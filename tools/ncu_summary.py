@@ -34,7 +34,37 @@ KEYS = [
 ]
 
 
+def traffic(rep, pattern, key, out):
+    """--traffic REPORT KERNEL_REGEX KEY OUT.json: DRAM bytes per launch (mean over the matching launches) of an `ncu --set full`
+    capture, stored under KEY (the kernel name bench.py prints, capi.et_last_kernel()) - bench.py reads roofline.traffic from it."""
+    import json
+    import os
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    pat = re.compile(pattern)
+    sel = [r for r in data if pat.search(r[idx["Kernel Name"]])]
+    if not sel:
+        raise SystemExit(f"no launch matches {pattern!r}")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def mean(metric):
+        u = scale[units[idx[metric]]]
+        return sum(float(r[idx[metric]].replace(",", "")) for r in sel) / len(sel) * u
+    rec = {"dram_bytes_read": mean("dram__bytes_read.sum"), "dram_bytes_write": mean("dram__bytes_write.sum"), "launches": len(sel),
+           "duration_us_under_ncu": sum(float(r[idx["gpu__time_duration.sum"]].replace(",", "")) for r in sel) / len(sel)
+                                    * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[idx["gpu__time_duration.sum"]].replace("second", "s").replace("usecond", "us"), 1.0),
+           "capture": os.path.basename(rep), "kernel_regex": pattern}
+    cur = json.load(open(out)) if os.path.exists(out) else {}
+    cur[key] = rec
+    json.dump(cur, open(out, "w"), indent=1, sort_keys=True)
+    print(json.dumps({key: rec}, indent=1))
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(*sys.argv[2:6])
     rep = sys.argv[1]
     pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
