@@ -665,7 +665,7 @@ def main():
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(config_dict(world, P), engine={
                 "fpn_backend": model.fpn_backend, "fpn_precision": model.fpn_precision, "reg_precision": model.reg_precision,
-                "tc_kernel_gen": model.tc_kernel_gen, "cuda_graph": bool(model.use_cuda_graph) and P == 1,
+                "cuda_graph": bool(model.use_cuda_graph) and P == 1,
                 "overlap_stages": bool(getattr(model, "overlap_stages", False)) and P == 1}),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e,
                     "mode": "serving loop: step i+1's pinned-host -> device copy on a copy stream (double-buffered inputs) under step i's "

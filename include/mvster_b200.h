@@ -143,16 +143,6 @@ int mvster_conv3d_ndhwc_f32(const float* x, const float* w, const float* bias, c
                             int kd, int stride_d, int stride_hw, int transposed, int relu,
                             mvster_stream_t stream);
 
-/* The same layer on the tcgen05 tensor cores (TMA-fed implicit GEMM, accumulators in TMEM) for
- * stride-1 (kd,3,3) convolutions with Cin, Cout in {16,32,64} (reg2d conv2/conv4/conv6 = 69% of its FLOPs).
- * w_packed: [hi | lo] halves, each [kd*9][Cin/KC][Cout][KC] fp32 with KC = min(Cin,32)
- * (K-major weight slabs; lo half only when npass == 3), see mvster_b200/packing.py:pack_tc_weights.
- * npass = 3: error-compensated 3xTF32 (fp32-faithful, ~2^-21 relative); npass = 1: plain TF32. */
-int mvster_conv3d_tc_supported(int Cin, int Cout, int kd, int stride_hw, int transposed);
-int mvster_conv3d_tc_f32(const float* x, const float* w_packed, const float* bias, const float* skip, float* y,
-                         int B, int D, int H, int W, int Cin, int Cout, int kd, int relu, int npass,
-                         mvster_stream_t stream);
-
 /* Generation 2 of the tensor-core layer: each 16x8-pixel tile (+halo) is staged once per depth plane and
  * the in-plane taps are addressed through the UMMA descriptor (no per-tap reload).  Cout may also be 8
  * (padded to N = 16).  w_packed: [hi | lo] x [kd*9][Cin/16][max(Cout,16)][16], packing.pack_tc2_weights. */
@@ -212,10 +202,10 @@ int mvster_reg2d_layer_info(int G, int layer, int64_t* info_host);
 int mvster_reg2d_f32(const float* blob, const float* cost, float* feat8, float* workspace,
                      int B, int G, int D, int H, int W, mvster_stream_t stream);
 
-/* Same network with conv2/conv4/conv6 on the tensor cores.  kernel_gen = 1: mvster_conv3d_tc_f32, tc_blob =
- * pack_tc_weights(conv2) | (conv4) | (conv6); kernel_gen = 2: mvster_conv3d_tc2_f32, tc_blob = pack_tc2_weights(...)
- * of the same layers.  Both in the npass = 3 [hi|lo] layout (mvster_reg2d_tc_blob_floats() floats); biases are
- * read from `blob`. */
+/* Same network with conv2/conv4/conv6 on the tensor cores in TF32 arithmetic (mvster_conv3d_tc2_f32; npass = 3: 3xTF32,
+ * 1: plain TF32): tc_blob = pack_tc2_weights(conv2) | (conv4) | (conv6) in the npass = 3 [hi|lo] layout
+ * (mvster_reg2d_tc_blob_floats() floats); biases are read from `blob`.  kernel_gen must be 2 (the first-generation per-tap
+ * kernel was removed in round 2). */
 size_t mvster_reg2d_tc_blob_floats(void);
 int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* cost, float* feat8, float* workspace,
                         int B, int G, int D, int H, int W, int npass, int kernel_gen, mvster_stream_t stream);

@@ -35,8 +35,6 @@ SIGNATURES = {
     "mvster_et_last_kernel": (C.c_char_p, []),
     "mvster_et_fuse_bwd_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _p, _p, C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
     "mvster_conv3d_ndhwc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "mvster_conv3d_tc_supported": (_i, [_i, _i, _i, _i, _i]),
-    "mvster_conv3d_tc_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_reg2d_blob_floats": (C.c_size_t, [_i]),
     "mvster_reg2d_workspace_floats": (C.c_size_t, [_i, _i, _i, _i]),
     "mvster_reg2d_layer_info": (_i, [_i, _i, C.POINTER(C.c_int64)]),

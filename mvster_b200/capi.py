@@ -225,25 +225,6 @@ def conv3d_ndhwc(x: Tensor, w: Tensor, bias: Optional[Tensor], kd: int, stride_d
     return y
 
 
-def conv3d_tc(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, relu: bool = True,
-              skip: Optional[Tensor] = None, npass: int = 3) -> Tensor:
-    """tcgen05 implicit-GEMM conv: x [B,D,H,W,Cin], w_packed from packing.pack_tc_weights -> [B,D,H,W,cout]."""
-    _chk(x, "x")
-    _chk(w_packed, "w_packed")
-    B, D, H, W, Cin = x.shape
-    y = torch.empty((B, D, H, W, cout), device=x.device, dtype=torch.float32)
-    if bias is not None:
-        _chk(bias, "bias", (cout,))
-    if skip is not None:
-        _chk(skip, "skip", tuple(y.shape))
-    want = kd * 9 * Cin * cout * (2 if npass == 3 else 1)
-    if w_packed.numel() != want:
-        raise ValueError(f"w_packed has {w_packed.numel()} floats, expected {want}")
-    _lib.check(_lib.load().mvster_conv3d_tc_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
-                                                kd, int(relu), npass, _stream()), "mvster_conv3d_tc_f32")
-    return y
-
-
 def conv3d_tc2(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, relu: bool = True,
                skip: Optional[Tensor] = None, npass: int = 3) -> Tensor:
     """Generation-2 tcgen05 conv (tile staged once per plane): w_packed from packing.pack_tc2_weights."""
@@ -387,10 +368,10 @@ def reg2d_workspace_floats(B: int, D: int, H: int, W: int) -> int:
 
 
 def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: Optional[Tensor] = None,
-          tc_blob: Optional[Tensor] = None, npass: int = 3, kernel_gen: int = 1, split: int = 3) -> Tensor:
+          tc_blob: Optional[Tensor] = None, npass: int = 3, kernel_gen: int = 2, split: int = 3) -> Tensor:
     """cost [B,D,H,W,G] -> feat8 [B,D,H,W,8] (everything of reg2d except the 1x1x1 prob layer).
-    With ``tc_blob`` the three 3x3x3 layers run on the tensor cores (npass 3 = 3xTF32, 1 = TF32;
-    kernel_gen 1 = per-tap TMA kernel with packing.pack_tc_weights slabs, 2 = staged-tile kernel with pack_tc2_weights slabs)."""
+    With ``tc_blob``: kernel_gen 3 = conv1..conv11 on the persistent tcgen05 kernel (pack_reg2d 'tc3_blob' / 'tc3h_blob' with
+    split 3 / 2); kernel_gen 2 = the three 3x3x3 layers on the staged-tile TF32 kernel (pack_tc2_weights slabs; npass 3 = 3xTF32, 1 = TF32)."""
     _chk(cost, "cost")
     _chk(blob, "blob")
     B, D, H, W, G = cost.shape

@@ -294,6 +294,7 @@ extern "C" int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, cons
                                    int B, int G, int D, int H, int W, int npass, int kernel_gen, mvster_stream_t stream) {
     MVSTER_REQUIRE(tc_blob, "mvster_reg2d_tc_f32: tc_blob is null");
     MVSTER_REQUIRE(npass == 1 || npass == 3, "mvster_reg2d_tc_f32: npass must be 1 or 3");
+    MVSTER_REQUIRE(kernel_gen == 2, "mvster_reg2d_tc_f32: kernel_gen must be 2 (the first-generation TF32 kernel was removed)");
     return reg2d_run(blob, tc_blob, npass, kernel_gen, cost, feat8, ws, B, G, D, H, W, stream);
 }
 
@@ -369,8 +370,8 @@ static int reg2d_run(const float* blob, const float* tc_blob, int npass, int gen
             // conv2 / conv4 / conv6 (3x3x3, 69 % of the FLOPs) on the tcgen05 tensor cores; their [hi|lo]
             // K-major slabs sit back to back in tc_blob (2*27*Cin*Cout floats each).
             const size_t off = i == 2 ? 0 : (i == 4 ? (size_t)2 * 27 * 16 * 16 : (size_t)2 * 27 * (16 * 16 + 32 * 32));
-            rc = (gen == 2 ? mvster_conv3d_tc2_f32 : mvster_conv3d_tc_f32)(in[i], tc_blob + off, blob + info[6], skip[i], out[i], B, D,
-                                                                            H / div[i], W / div[i], L[i].cin, L[i].cout, 3, 1, npass, stream);
+            rc = mvster_conv3d_tc2_f32(in[i], tc_blob + off, blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i], L[i].cin, L[i].cout,
+                                       3, 1, npass, stream);
         } else {
             rc = run_conv(in[i], blob + info[5], blob + info[6], skip[i], out[i], B, D, H / div[i], W / div[i],
                           L[i].cin, L[i].cout, L[i].kd, 1, L[i].s, L[i].transposed, 1, st);

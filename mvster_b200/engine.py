@@ -204,7 +204,7 @@ class InferenceEngine:
         (test_mvs4.py:196) capture and replay from their own host threads."""
         key = (tuple(tuple(t.shape) for t in imgs), tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
                tuple(depth_values.shape), self.weights_version, self._precision(net, "reg"),
-               getattr(net, "tc_kernel_gen", 1), getattr(net, "fpn_backend", "torch"), self._precision(net, "fpn"),
+               getattr(net, "fpn_backend", "torch"), self._precision(net, "fpn"),
                getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"),
                None if shard is None else (shard.first_view, shard.count, shard.parts, id(shard.group)))
         entry = self._graphs.get(key)
@@ -270,9 +270,7 @@ class InferenceEngine:
         elif prec == "2xfp16":  # same kernel, two fp16 terms per operand (22-bit operands, 2/3 of the MMAs; |x| < 65504)
             feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc3h_blob"], kernel_gen=3, split=2)
         else:                   # 3x3x3 layers on tcgen05: "3xtf32" (fp32-faithful) or "tf32"
-            gen = int(getattr(net, "tc_kernel_gen", 1))
-            feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc2_blob" if gen == 2 else "tc_blob"],
-                               npass=3 if prec == "3xtf32" else 1, kernel_gen=gen)
+            feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc2_blob"], npass=3 if prec == "3xtf32" else 1, kernel_gen=2)
         return capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=inverse)
 
     def _run_stage(self, net, p: StagePlan, wts: Dict[str, Tensor], feats_k: List[Tensor], proj_matrices: Dict[str, Tensor],

@@ -260,10 +260,9 @@ class MVS4net(nn.Module):
         #            per layer <= 2.1e-6 of max against an fp64 convolution, tests/test_gpu_tc_conv.py) - the default; valid while
         #            the layer inputs stay below 65504 in magnitude (they are BN-normalised activations; larger values saturate)
         #   "3xbf16" same kernel, three bf16 terms per operand (24-bit operands, full fp32 range; <= 5e-6 of max), 1.5x the MMAs
-        #   "3xtf32" the 3x3x3 layers on the generation-1/2 kernels, error-compensated TF32 (<= 1.6e-5 of max)
+        #   "3xtf32" the 3x3x3 layers on the staged-tile TF32 kernel (conv_tc2.cu), error-compensated TF32 (<= 1.6e-5 of max)
         #   "tf32"   ... single TF32 pass (reduced precision, opt-in)
         self.reg_precision = os.environ.get("MVSTER_REG_PRECISION", "2xfp16")
-        self.tc_kernel_gen = int(os.environ.get("MVSTER_TC_GEN", "2"))  # TF32 modes: 1 = per-tap TMA kernel, 2 = staged-tile kernel
         # feature pyramid at inference: "native" (libmvster_b200 kernels, fpn_engine.py; fpn_precision as above, "3xbf16" puts
         # every layer after the 3-channel stem on the tensor cores) or "torch" (the module's own convs through cuDNN, channels-last)
         self.fpn_backend = os.environ.get("MVSTER_FPN", "native")

@@ -37,22 +37,6 @@ def fold_deconv3d(w: Tensor, scale: Tensor, shift: Tensor) -> Tuple[Tensor, Tens
 TF32_MASK = -8192  # 0xFFFFE000 as int32: keep sign, exponent and the top 10 mantissa bits
 
 
-def pack_tc_weights(w: Tensor, npass: int = 3) -> Tensor:
-    """[taps][Cin][Cout] fp32 -> the K-major slabs the tcgen05 conv kernel streams by TMA:
-    [hi | lo] x [taps][Cin/KC][Cout][KC], KC = min(Cin, 32).  hi = w truncated to TF32, lo = TF32(w - hi)
-    (exact split: hi + lo reproduces w to 2^-21 relative); npass == 1 keeps w unsplit."""
-    taps, cin, cout = w.shape
-    kc = 32 if cin >= 32 else 16
-    if cin % kc:
-        raise ValueError(f"Cin={cin} is not a multiple of {kc}")
-    slabs = w.float().reshape(taps, cin // kc, kc, cout).permute(0, 1, 3, 2).contiguous()
-    if npass == 1:
-        return slabs.reshape(-1)
-    hi = (slabs.view(torch.int32) & TF32_MASK).view(torch.float32)
-    lo = ((slabs - hi).view(torch.int32) & TF32_MASK).view(torch.float32)
-    return torch.cat([hi.reshape(-1), lo.reshape(-1)])
-
-
 def pack_tc2_weights(w: Tensor, npass: int = 3) -> Tensor:
     """[taps][Cin][Cout] fp32 -> slabs for the staged-tile tcgen05 kernel (conv_tc2.cu):
     [hi | lo] x [taps][Cin/16][N][16] with N = max(Cout, 16) (zero rows pad Cout = 8 to the minimum UMMA N)."""
@@ -219,11 +203,10 @@ def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, 
             raise ValueError(f"{p}: packed shape {tuple(w.shape)} != layer table {(L['taps'], L['cin'], L['cout'])}")
         blob[L["w_off"]:L["w_off"] + w.numel()] = w.reshape(-1)
         blob[L["b_off"]:L["b_off"] + b.numel()] = b
-    tc, tc2 = [], []
+    tc2 = []
     for name, L in zip(REG2D_ORDER, layer_table):
         if L["kd"] == 3:  # conv2 / conv4 / conv6: K-major [hi|lo] slabs for the tcgen05 paths
             w = blob[L["w_off"]:L["w_off"] + L["taps"] * L["cin"] * L["cout"]].reshape(L["taps"], L["cin"], L["cout"])
-            tc.append(pack_tc_weights(w, 3))
             tc2.append(pack_tc2_weights(w, 3))
     tc3 = {3: [], 2: []}  # three bf16 terms ('tc3_blob') and two fp16 terms ('tc3h_blob', MVSTER_TC3_FP16X2)
     for name, L in zip(REG2D_ORDER, layer_table):
@@ -236,7 +219,7 @@ def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, 
                 lst.append(pack_tc3_deconv_weights(w, -1, split))
             else:                       # conv7 (64 -> 32): output rows of parity 0, then parity 1
                 lst += [pack_tc3_deconv_weights(w, 0, split), pack_tc3_deconv_weights(w, 1, split)]
-    return {"blob": blob, "tc_blob": torch.cat(tc), "tc2_blob": torch.cat(tc2), "tc3_blob": torch.cat(tc3[3]),
+    return {"blob": blob, "tc2_blob": torch.cat(tc2), "tc3_blob": torch.cat(tc3[3]),
             "tc3h_blob": torch.cat(tc3[2]),
             "prob_w": sd[prefix + ".prob.weight"].detach().cpu().reshape(-1).float().contiguous(),
             "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}

@@ -13,7 +13,7 @@ sys.path.insert(0, str(HERE))
 import build_emu  # noqa: E402
 
 HOST_ONLY = {"mvster_conv_tc3_plan", "mvster_conv_tc3_packed_bytes", "mvster_conv_tc3_supported", "mvster_deconv_tc3_packed_bytes",
-             "mvster_deconv_tc3_supported", "mvster_conv3d_tc_supported", "mvster_conv3d_tc2_supported"}
+             "mvster_deconv_tc3_supported", "mvster_conv3d_tc2_supported"}
 
 
 class EmuWithHostLogic:

@@ -40,7 +40,7 @@ def reg2d_main(gen):
     packed = packing.pack_reg2d(sd, "reg.0" if G == 8 else "reg.3", capi.reg2d_layer_table(G))
     rng = np.random.RandomState(G + H)
     cost = torch.from_numpy((rng.randn(B, D, H, W, G) * 0.05).astype(np.float32)).to(dev)
-    blob, tcb = packed["blob"].to(dev), packed["tc2_blob" if gen == 2 else "tc_blob"].to(dev)
+    blob, tcb = packed["blob"].to(dev), packed["tc2_blob"].to(dev)
     want = capi.reg2d(blob, cost)
     got = capi.reg2d(blob, cost, tc_blob=tcb, npass=npass, kernel_gen=gen)
     torch.cuda.synchronize()
@@ -127,8 +127,9 @@ def main():
     if mode == "d3":
         return d3_main()
     if mode.startswith("reg2d"):
-        return reg2d_main(2 if mode.endswith("v2") else 1)
-    gen = 2 if mode == "v2" else 1
+        return reg2d_main(2)
+    if mode != "v2":
+        raise SystemExit(f"unknown mode {mode!r} (v2, v3, d3, reg2dv2)")
     cin, cout, kd, B, D, H, W, npass = map(int, sys.argv[2:10])
     use_skip, relu = "skip" in sys.argv, "norelu" not in sys.argv
     dev = torch.device("cuda", 0)
@@ -138,12 +139,8 @@ def main():
     bias = torch.from_numpy(rng.randn(cout).astype(np.float32) * 0.1).to(dev)
     skip = torch.from_numpy(rng.randn(B, D, H, W, cout).astype(np.float32)).to(dev) if use_skip else None
     want = capi.conv3d_ndhwc(x, w, bias, kd, 1, 1, False, relu, skip=skip)
-    if gen == 2:
-        wp = packing.pack_tc2_weights(w.cpu(), npass).to(dev)
-        run = lambda: capi.conv3d_tc2(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
-    else:
-        wp = packing.pack_tc_weights(w.cpu(), npass).to(dev)
-        run = lambda: capi.conv3d_tc(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
+    wp = packing.pack_tc2_weights(w.cpu(), npass).to(dev)
+    run = lambda: capi.conv3d_tc2(x, wp, bias, cout, kd, relu, skip=skip, npass=npass)
     got = run()
     torch.cuda.synchronize()
     err, scale = (got - want).abs().max().item(), want.abs().max().item()

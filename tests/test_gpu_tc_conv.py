@@ -13,12 +13,6 @@ from util import REPO
 pytestmark = pytest.mark.gpu
 
 CASES = [  # generation cin cout kd B D H W npass [flags]
-    "v1 32 32 3 1 4 16 32 3",
-    "v1 16 16 3 1 8 24 40 3 skip",      # 64-byte swizzle path, ragged right/bottom tiles
-    "v1 64 64 3 1 8 8 10 3",            # two K chunks per tap, image smaller than one tile
-    "v1 32 32 1 2 4 16 16 3 norelu",    # (1,3,3) kernel, batch 2
-    "v1 32 64 3 1 4 32 48 1",           # plain TF32
-    "v1 64 64 3 1 4 64 80 3 skip",      # reg2d conv6 at cfg2 stage 4
     "v2 32 32 3 1 4 16 32 3",
     "v2 16 16 3 1 8 24 40 3 skip",      # ragged right/bottom tiles (16x8 tiles on 24x40)
     "v2 64 64 3 1 8 8 10 3",            # four 16-channel chunks, image smaller than one tile, depth padding
@@ -71,8 +65,7 @@ CASES = [  # generation cin cout kd B D H W npass [flags]
     "d3 32 16 2 2 16 16 h16",
     "d3 64 32 1 4 8 10 skip h16",
     "d3 16 8 1 4 256 320 skip h16",
-    "reg2d 8 1 8 64 80 3",              # whole reg2d U-Net, stage-1 shape of cfg2, 3xTF32, generation 1
-    "reg2dv2 8 1 8 64 80 3",            # ... generation 2
+    "reg2dv2 8 1 8 64 80 3",            # whole reg2d U-Net, stage-1 shape of cfg2, 3xTF32
     "reg2dv2 4 1 4 512 640 3",          # stage-4 shape of cfg2 (1.31 M voxels)
     "reg2dv2 4 1 4 128 160 1",          # plain TF32
 ]

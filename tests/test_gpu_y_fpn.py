@@ -58,7 +58,7 @@ def test_forward_with_native_fpn_against_reference_golden(precision):
     z, imgs, proj, dv = load_golden(name)
     m = build_model(GOLDEN_CASES[name], int(z["meta_seed"])).to(DEV)
     m.fpn_backend, m.fpn_precision = "native", precision
-    m.reg_precision, m.tc_kernel_gen = precision, 2
+    m.reg_precision = precision
     with torch.no_grad():
         out = m([t.to(DEV) for t in imgs], {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV))
     ok = torch.ones_like(torch.from_numpy(z["s1_depth"]), dtype=torch.bool)
