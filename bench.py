@@ -252,7 +252,8 @@ def et_traffic_record(kernel_key: str):
 
 
 def _timed_ranks(fn, steps, flush, dist, dev, warmup=3):
-    """Summed step time in ms over ``steps`` calls (CUDA events per step, L2 flushed between steps), max over ranks."""
+    """Median step time in ms over ``steps`` calls (CUDA events per step, L2 flushed between steps), max over ranks.  The
+    median, because these informational legs are short and a single host hiccup (allocator, NCCL watchdog) would skew a mean."""
     for _ in range(warmup):
         fn()
     dist.barrier()
@@ -265,9 +266,9 @@ def _timed_ranks(fn, steps, flush, dist, dev, warmup=3):
         e.record()
     dist.barrier()
     torch.cuda.synchronize()
-    total = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], dtype=torch.float64, device=dev)
+    total = torch.tensor([statistics.median(s.elapsed_time(e) for s, e in evs)], dtype=torch.float64, device=dev)
     dist.all_reduce(total, op=dist.ReduceOp.MAX)
-    return float(total.item()) / steps
+    return float(total.item())
 
 
 def multi_gpu_legs(args, rank, world, dev, flush):
@@ -523,7 +524,11 @@ def main():
     l0 = _lib.launch_count()
     if args.profile_range:
         torch.cuda.profiler.start()
+    import gc
+    gc.collect()
+    gc.disable()  # no collector pause between the launches of the timed steps
     ms_total = timed(step_resident, args.steps)
+    gc.enable()
     step_stats = {"min_ms": min(per_step), "median_ms": statistics.median(per_step),
                   "p95_ms": sorted(per_step)[min(len(per_step) - 1, int(0.95 * len(per_step)))], "max_ms": max(per_step)}
     if args.profile_range:

@@ -172,6 +172,11 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
  * other's cap.  The SM count is that of the calling thread's current device.  Used by the host to run the small
  * early cascade stages on a second stream next to the feature pyramid's large layers. */
 void mvster_set_sm_budget(int n);
+/* Range check of the two-fp16-term arithmetic (MVSTER_TC3_FP16X2): while a device word is registered, every such launch of the
+ * CALLING THREAD sets it to 1 if one of the layer's input values does not fit the fp16 terms (|x| >= 65504 or non-finite; the
+ * conversion saturates there).  NULL switches the check off again (then it costs nothing).  The host (engine.py) keeps it on for
+ * the warm-up forwards of a new weight set / input signature and falls back to three bf16 terms (full fp32 range) if it fires. */
+void mvster_tc3_set_overflow_flag(unsigned* device_flag);
 int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw);
 int mvster_conv_tc3_plan(int Cin, int kd, int k, int stride_hw, int* slabs, int max_slabs);
 size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int stride_hw);

@@ -72,6 +72,9 @@ struct Args {
     // stay; otherwise they stream through a ring of NB slabs per group of tiles (large Cin * taps * Cout)
     int resident, nslab;
     int cin_merged;  // > 0: x_map is the 3-D map with (channels x pixels) merged; value = channels per pixel
+    // two-fp16-term arithmetic only: if non-null, the converters track max |x| of the layer's input and set *overflow when a value
+    // does not fit the fp16 terms (|x| >= 65504 or non-finite) - mvster_tc3_set_overflow_flag; null = no tracking, no cost
+    unsigned* overflow;
 };
 
 // plain / planar-block / depth-to-space output addressing of a launch; false if an offset would not fit 32 bits
@@ -330,6 +333,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
         // team's conversion (with all 8 warps on one tile-stage the role cost ~1100 cycles per tile-stage whatever the tap count).
         const int team = (threadIdx.x - 96) / CTEAM, tid = (threadIdx.x - 96) % CTEAM;
         uint32_t u = 0;
+        float amax = 0.f;  // NaN-propagating running max of |input| (fp16 arithmetic with a.overflow only)
         for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
             MVSTER_TC3_GROUP_HEAD
             for (int s = 0; s < a.nstage; ++s) {
@@ -369,6 +373,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                                 *reinterpret_cast<uint2*>(dst + A_SPLIT) = t2;
                                 *reinterpret_cast<uint2*>(dst + 2 * A_SPLIT) = t3;
                             } else {
+                                if (a.overflow) {
+                                    float m4;
+                                    asm("{\n\t.reg .f32 t, u;\n\tmax.NaN.f32 t, %1, %2;\n\tmax.NaN.f32 u, %3, %4;\n\tmax.NaN.f32 %0, t, u;\n\t}"
+                                        : "=f"(m4) : "f"(fabsf(v[k].x)), "f"(fabsf(v[k].y)), "f"(fabsf(v[k].z)), "f"(fabsf(v[k].w)));
+                                    asm("max.NaN.f32 %0, %0, %1;" : "+f"(amax) : "f"(m4));
+                                }
                                 uint2 t1, t2;
                                 split2h(v[k].x, v[k].y, t1.x, t2.x);
                                 split2h(v[k].z, v[k].w, t1.y, t2.y);
@@ -382,6 +392,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     mbar_arrive(F_EMPTY(fs));
                 }
             }
+        }
+        if constexpr (NS == 2) {
+            if (a.overflow && !(amax < 65504.f)) atomicOr(a.overflow, 1u);  // also true for NaN
         }
     } else {
         // ------------------------------------------------------------------ epilogue
@@ -548,6 +561,9 @@ static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[6]
 // Thread-local: under nn.DataParallel (test_mvs4.py:196) every replica drives its own device from its own host thread, and a
 // cap set by one replica must not leak into another replica's launches (or into a CUDA-graph capture running beside it).
 static thread_local int g_sm_budget = 0;
+// Device word that the two-fp16-term launches of the calling thread OR a 1 into when a layer input does not fit the fp16 terms
+// (mvster_tc3_set_overflow_flag; nullptr = off).  Thread-local for the same reason as the SM cap.
+static thread_local unsigned* g_overflow_flag = nullptr;
 
 // SM count of the CURRENT device (replicas may sit on different devices; cached per device id).
 static int current_sm_count() {
@@ -603,6 +619,7 @@ static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long to
 using namespace mvster;
 
 extern "C" void mvster_set_sm_budget(int n) { tc3::g_sm_budget = n > 0 ? n : 0; }
+extern "C" void mvster_tc3_set_overflow_flag(unsigned* device_flag) { tc3::g_overflow_flag = device_flag; }
 
 extern "C" int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw) {
     return tc3::supported(Cin, Cout, kd, k, stride_hw);
@@ -670,6 +687,7 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     a.tiles_x = ceil_div(a.Wo, TW);
     a.tiles_per_plane = a.tiles_x * ceil_div(a.Ho, TH);
     { const char* dbg = getenv("MVSTER_TC3_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
+    a.overflow = tc3::g_overflow_flag;
     a.zero_a = Cin < 8;  // Cin = 4: each 16-byte row holds 4 real channels, the other 4 must read as zero (Cin = 8 fills the one plane it reads)
     const bool blocks = block > 0 && block < Cout;
     if (blocks) a.cout = block;
@@ -765,6 +783,7 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
     a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
     a.zero_a = 0;
     { const char* dbg = getenv("MVSTER_TC3_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
+    a.overflow = tc3::g_overflow_flag;
     MVSTER_REQUIRE(set_output_mode(a, deconv_ncls(rows), rows == 1 ? 1 : 0, true, 0), "mvster_deconv_tc3_f32: output row pitch does not fit 32 bits");
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
     cudaStream_t st = (cudaStream_t)stream;

@@ -117,6 +117,10 @@ class InferenceEngine:
         self._side = None  # second stream for the early cascade stages (_forward_overlapped)
         self.fp16_safe = {"fpn": True, "reg": True}  # folded weights inside the two-fp16-term range (refresh_weights)
         self._warned_fp16 = False
+        # activation range of the two-fp16-term arithmetic: checked on the device during the first forward after the weights
+        # changed (and on every eager forward with MVSTER_RANGE_CHECK=always); a hit switches this engine to three bf16 terms
+        self._range_checked = False
+        self._overflow_flag: Optional[Tensor] = None
 
     def _precision(self, net, which: str) -> str:
         """Arithmetic of the convolutions of ``which`` ("fpn" | "reg"): the module's setting, except that "2xfp16" becomes "3xbf16"
@@ -135,6 +139,7 @@ class InferenceEngine:
     def refresh_weights(self, net) -> None:
         check_supported(net)
         self._graphs.clear()  # captured graphs reference the previous packed weights
+        self._range_checked = False
         sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("reg.")}
         self.plans = [StagePlan(k, net) for k in range(net.num_stage)]
         self.stage_weights = []
@@ -168,9 +173,44 @@ class InferenceEngine:
         own = list(range(len(imgs))) if shard is None else [0] + shard.views
         self._native_feats = getattr(net, "fpn_backend", "torch") == "native"  # features in the pyramid's (interleaved) channel order
         try:
+            if self._needs_range_check(net):
+                return self._range_checked_forward(net, imgs, proj_matrices, depth_values, shard, B, own)
             return self._forward(net, imgs, proj_matrices, depth_values, shard, B, own)
         finally:
             self._native_feats = False
+
+    def _needs_range_check(self, net) -> bool:
+        if self.device.type != "cuda" or torch.cuda.is_current_stream_capturing():
+            return False
+        if "2xfp16" not in (self._precision(net, "fpn"), self._precision(net, "reg")):
+            return False
+        return (not self._range_checked) or os.environ.get("MVSTER_RANGE_CHECK", "once") == "always"
+
+    def _range_checked_forward(self, net, imgs, proj_matrices, depth_values, shard, B, own) -> Dict:
+        """One forward with the converters of every two-fp16-term convolution reporting inputs that do not fit the fp16 terms
+        (|x| >= 65504 or non-finite: `cvt.rn.satfinite` would clamp them silently).  If any does, the engine switches to three
+        bf16 terms - same kernel, full fp32 range - warns once and repeats the forward.  Costs one device-to-host read."""
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            if self._overflow_flag is None:
+                self._overflow_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._overflow_flag.zero_()
+            lib.mvster_tc3_set_overflow_flag(self._overflow_flag.data_ptr())
+            try:
+                out = self._forward(net, imgs, proj_matrices, depth_values, shard, B, own)
+            finally:
+                lib.mvster_tc3_set_overflow_flag(None)
+            hit = int(self._overflow_flag.item()) != 0
+        self._range_checked = True
+        if hit:
+            import warnings
+            warnings.warn("mvster_b200: an activation exceeds the range of the two-fp16-term convolution arithmetic (|x| >= 65504 or "
+                          "non-finite); this engine now uses three bf16 terms (full fp32 range) instead")
+            self.fp16_safe = {"fpn": False, "reg": False}
+            self._warned_fp16 = True
+            self._graphs.clear()
+            out = self._forward(net, imgs, proj_matrices, depth_values, shard, B, own)
+        return out
 
     def _forward(self, net, imgs, proj_matrices, depth_values, shard, B, own) -> Dict:
         with torch.cuda.device(self.device):
@@ -180,8 +220,8 @@ class InferenceEngine:
                 prec = self._precision(net, "fpn")
                 npass = {"fp32": 0, "3xtf32": 3, "tf32": 1, "3xbf16": 3, "2xfp16": 2}[prec]
                 gen = 3 if prec in ("3xbf16", "2xfp16") else 2
-                if shard is None and net.num_stage == 4 and getattr(net, "overlap_stages", True):
-                    return self._forward_overlapped(net, x, B, len(own), proj_matrices, depth_values, npass, gen)
+                if net.num_stage == 4 and getattr(net, "overlap_stages", True) and (shard is None or shard.count > 0):
+                    return self._forward_overlapped(net, x, B, len(own), proj_matrices, depth_values, npass, gen, shard)
                 pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen)
                 nhwc = [pyramid[f"stage{k + 1}"] for k in range(net.num_stage)]
             else:
@@ -220,7 +260,9 @@ class InferenceEngine:
                         self.forward(net, s_imgs, s_proj, s_dv, shard=shard)
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                # an explicit capture stream on THIS device: torch.cuda.graph's default one is created once, on whichever device was
+                # current then, and capturing it from another device's replica fails ("operation not permitted when stream is capturing")
+                with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=self.device), capture_error_mode="thread_local"):
                     out = self.forward(net, s_imgs, s_proj, s_dv, shard=shard)
             entry = self._graphs[key] = (graph, s_imgs, s_proj, s_dv, out)
             if len(self._graphs) > 4:  # keep the cache small: each graph pins its own workspace
@@ -246,8 +288,9 @@ class InferenceEngine:
         from . import sharding
         B, H, W, _ = ref.shape
 
-        def partial(acc, wsum):
-            pose = capi.pose(proj, first_view=shard.first_view, n_views=shard.count)
+        def partial(acc, wsum, pose=pose):
+            if pose is None:
+                pose = capi.pose(proj, first_view=shard.first_view, n_views=shard.count)
             capi.et_fuse(ref, srcs, pose, hypo, p.G, temp, cost=acc, wsum=wsum, partial=True, **kw)
 
         return sharding.sharded_aggregate(partial, capi.et_normalize, (B, p.D, H, W, p.G), shard, self.device)
@@ -340,7 +383,7 @@ class InferenceEngine:
 
     # ------------------------------------------------------------------ two-stream forward
     def _forward_overlapped(self, net, x: Tensor, B: int, n_own: int, proj_matrices: Dict[str, Tensor], depth_values: Tensor,
-                            npass: int, gen: int) -> Dict:
+                            npass: int, gen: int, shard=None) -> Dict:
         """The early cascade stages work on 1/64, 1/16 and 1/4 of the last stage's voxels: ~45 short, latency-bound launches
         (0.7 ms of 2.1 ms at cfg2) that leave most SMs idle, and stage k only needs pyramid level k.  So they run on a second,
         high-priority stream next to the pyramid's remaining large layers: level events fork the side stream, the persistent
@@ -368,7 +411,8 @@ class InferenceEngine:
         deferred: List = []
         try:
             # relative poses depend on the inputs only: computed up front, off the stage-to-stage chain
-            poses = [capi.pose(proj_matrices[f"stage{k + 1}"].to(device=self.device, dtype=torch.float32).contiguous()) for k in range(4)]
+            pose_kw = {} if shard is None else dict(first_view=shard.first_view, n_views=shard.count)  # a view shard: its own source views only
+            poses = [capi.pose(proj_matrices[f"stage{k + 1}"].to(device=self.device, dtype=torch.float32).contiguous(), **pose_kw) for k in range(4)]
             pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen, on_level=on_level)
             feats = [[pyramid[f"stage{k + 1}"][i * B:(i + 1) * B] for i in range(n_own)] for k in range(4)]
             lib.mvster_set_sm_budget(side_sms)
@@ -376,13 +420,13 @@ class InferenceEngine:
             with torch.cuda.stream(side):
                 for p, wts in zip(self.plans[:3], self.stage_weights[:3]):
                     side.wait_event(events[p.k])
-                    prev = self._run_stage(net, p, wts, feats[p.k], proj_matrices, dv, prev, temp, pose=poses[p.k], deferred=deferred)
+                    prev = self._run_stage(net, p, wts, feats[p.k], proj_matrices, dv, prev, temp, shard=shard, pose=poses[p.k], deferred=deferred)
                     outputs[f"stage{p.k + 1}"] = prev
                 done = torch.cuda.Event()
                 done.record(side)
             lib.mvster_set_sm_budget(0)
             main.wait_event(done)
-            prev = self._run_stage(net, self.plans[3], self.stage_weights[3], feats[3], proj_matrices, dv, prev, temp, pose=poses[3])
+            prev = self._run_stage(net, self.plans[3], self.stage_weights[3], feats[3], proj_matrices, dv, prev, temp, shard=shard, pose=poses[3])
             for fn in deferred:  # confidence maps of stages 1-3 (outputs only)
                 fn()
             outputs["stage4"] = prev

@@ -74,3 +74,39 @@ def test_forward_with_native_fpn_against_reference_golden(precision):
                attn_err_s1=float((st["attn_weight"].cpu() - ref_attn).abs().max()) if s == 1 else -1.0)
         assert bad < 5e-3, f"stage {s}: {bad:.3%} of tie-free, drift-free pixels differ"
         ok = ok & agree
+
+
+def test_fp16_term_arithmetic_detects_out_of_range_activations_and_falls_back():
+    """the default `2xfp16` arithmetic saturates layer inputs at +-65504.  The converters report such inputs
+    during the first forward of a weight set; the engine must then warn, switch to three bf16 terms (full fp32 range) and return
+    what the exact-fp32 engine returns - not a silently clamped result."""
+    import warnings
+    from util import SHIPPED, build_model, top2_gap
+    from mvster_b200 import synth
+    imgs, proj, dv = synth.make_inputs(1, 3, 128, 192, seed=11)
+    imgs = [t * 3.0e5 for t in imgs]  # pyramid activations far above the fp16 range
+    args = ([t.to(DEV) for t in imgs], {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV))
+    m = build_model(SHIPPED, 4).to(DEV)
+    m.use_cuda_graph = False
+    with torch.no_grad(), warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        got = m(*args)
+    assert any("two-fp16-term" in str(w.message) for w in caught), [str(w.message) for w in caught]
+    eng = m._engines[DEV.index]
+    assert eng._precision(m, "fpn") == "3xbf16" and eng._precision(m, "reg") == "3xbf16"
+    ref_m = build_model(SHIPPED, 4).to(DEV)
+    ref_m.use_cuda_graph, ref_m.reg_precision, ref_m.fpn_precision = False, "fp32", "fp32"
+    with torch.no_grad():
+        want = ref_m(*args)
+    stable = top2_gap(want["stage1"]["attn_weight"]) > 1e-3
+    bad = ((got["stage1"]["depth"] != want["stage1"]["depth"]) & stable).float().mean().item()
+    assert torch.isfinite(got["depth"]).all() and bad < 1e-3, bad
+    # in-range inputs: no warning, the fast arithmetic stays
+    m2 = build_model(SHIPPED, 4).to(DEV)
+    m2.use_cuda_graph = False
+    imgs2, proj2, dv2 = synth.make_inputs(1, 3, 128, 192, seed=11)
+    with torch.no_grad(), warnings.catch_warnings(record=True) as caught2:
+        warnings.simplefilter("always")
+        m2([t.to(DEV) for t in imgs2], {k: v.to(DEV) for k, v in proj2.items()}, dv2.to(DEV))
+    assert not any("two-fp16-term" in str(w.message) for w in caught2)
+    assert m2._engines[DEV.index]._precision(m2, "reg") == "2xfp16"
