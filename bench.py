@@ -266,7 +266,9 @@ def _timed_ranks(fn, steps, flush, dist, dev, warmup=3):
         e.record()
     dist.barrier()
     torch.cuda.synchronize()
-    total = torch.tensor([statistics.median(s.elapsed_time(e) for s, e in evs)], dtype=torch.float64, device=dev)
+    ts = [s.elapsed_time(e) for s, e in evs]
+    _timed_ranks.last = [round(t, 4) for t in ts]  # this rank's step times, for the record
+    total = torch.tensor([statistics.median(ts)], dtype=torch.float64, device=dev)
     dist.all_reduce(total, op=dist.ReduceOp.MAX)
     return float(total.item())
 
@@ -298,11 +300,13 @@ def multi_gpu_legs(args, rank, world, dev, flush):
             return model(imgs, proj, dv)
 
     ms_full = _timed_ranks(fwd, steps, flush, dist, dev)     # P = 1: every rank runs the whole 10-view frame alone
+    full_steps = list(_timed_ranks.last)
     full = fwd()
     full_depth, full_attn1 = full["depth"].clone(), full["stage1"]["attn_weight"].clone()
     shard = sharding.make_view_shard(NV - 1, P)
     model.set_view_shard(shard)
     ms_shard = _timed_ranks(fwd, steps, flush, dist, dev)
+    shard_steps = list(_timed_ranks.last)
     part = fwd()
     torch.cuda.synchronize()
     same = torch.tensor([(part["depth"] == full_depth).float().mean().item(),
@@ -321,6 +325,7 @@ def multi_gpu_legs(args, rank, world, dev, flush):
         "workload": f"cfg4: 9 source views, 512x640, fp32; {P} view ranks per frame x {frames} frame replica(s)",
         "view_parallel": P, "frames": frames, "value": frames / (ms_shard * 1e-3), "unit": UNIT, "ms_per_step": ms_shard,
         "unsharded_ms_per_step": ms_full, "strong_scaling_vs_P1": ms_full / ms_shard,
+        "rank0_step_ms": {"unsharded": full_steps, "sharded": shard_steps},
         "views_per_rank": [c for _, c in sharding.partition_views(NV - 1, P)],
         "allreduce_us_per_stage": ar_us, "allreduce_bytes": ar_bytes,
         "depth_equal_unsharded": float(same[0].item()), "stage1_attn_abs_vs_unsharded": -float(same[1].item()),

@@ -82,6 +82,18 @@ def check_inputs(net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], 
         raise ValueError(f"depth_values must be [B={B}, >= 2], got {tuple(depth_values.shape)}")
 
 
+def module_state(net) -> Dict[str, Tensor]:
+    """``state_dict()`` that also works on an nn.DataParallel replica: `replicate` keeps a replica's parameters as plain tensor
+    attributes (listed in ``_former_parameters``), so its own ``state_dict()`` only holds the buffers."""
+    out = {k: v.detach() for k, v in net.state_dict().items()}
+    for prefix, mod in net.named_modules():
+        former = getattr(mod, "_former_parameters", None)
+        if former:
+            for k, v in former.items():
+                out[(prefix + "." if prefix else "") + k] = v.detach()
+    return out
+
+
 def _copy_outputs(out: Dict) -> Dict:
     """Fresh tensors for every distinct tensor of an output dict (one multi-tensor copy); entries that alias each other in
     ``out`` (the top-level keys and ``stage4``'s, MVS4Net.py:104-105) alias each other in the result."""
@@ -140,10 +152,11 @@ class InferenceEngine:
         check_supported(net)
         self._graphs.clear()  # captured graphs reference the previous packed weights
         self._range_checked = False
-        sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("reg.")}
+        state = module_state(net)
+        sd = {k: v for k, v in state.items() if k.startswith("reg.")}
         self.plans = [StagePlan(k, net) for k in range(net.num_stage)]
         self.stage_weights = []
-        fpn_sd = {k: v.detach() for k, v in net.state_dict().items() if k.startswith("feature.")}
+        fpn_sd = {k: v for k, v in state.items() if k.startswith("feature.")}
         # Group-interleaved feature channels (MVSTER_ET_INTERLEAVED): the native pyramid writes stage k's channels in the order the
         # window kernels want (a 64-bit pair = the same channel index of two neighbouring groups), by permuting the output
         # channels of out{k} when the weights are packed.  Only for the shipped (C, G, D) classes those kernels are built for.

@@ -53,6 +53,9 @@ def main():
         assert all(r["final_depth_identical_frac"] > 0.98 for r in gathered), gathered
         assert sum(len(r["views"]) for r in gathered) == n_views - 1
         print("view-sharded forward == unsharded forward: OK")
+    m._engines.clear()  # captured CUDA graphs hold NCCL kernels: release them before the communicator goes away
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
 
 
