@@ -535,7 +535,8 @@ def main():
     ms_total = timed(step_resident, args.steps)
     gc.enable()
     step_stats = {"min_ms": min(per_step), "median_ms": statistics.median(per_step),
-                  "p95_ms": sorted(per_step)[min(len(per_step) - 1, int(0.95 * len(per_step)))], "max_ms": max(per_step)}
+                  "p95_ms": sorted(per_step)[min(len(per_step) - 1, int(0.95 * len(per_step)))], "max_ms": max(per_step),
+                  "steps_ms": [round(t, 3) for t in per_step]}
     if args.profile_range:
         torch.cuda.profiler.stop()
     launches = launches_per_step * args.steps if (model.use_cuda_graph and P == 1) else _lib.launch_count() - l0

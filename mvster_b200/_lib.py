@@ -7,9 +7,11 @@ stream is torch's current CUDA stream.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmvster_b200.so"
+# MVSTER_LIB_PATH: an alternative build of the same library (A/B of compile-time switches); default = the in-tree build
+LIB_PATH = Path(os.environ.get("MVSTER_LIB_PATH") or Path(__file__).resolve().parent / "lib" / "libmvster_b200.so")
 
 _p = C.c_void_p
 _i = C.c_int

@@ -178,11 +178,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // Programmatic dependent launch (launch_ns sets the stream-serialisation attribute): the NEXT convolution of the stream may
-    // become resident and run its prologue - barrier init, TMEM allocation, the (static) weight slabs - while this one is still
-    // computing; everything that touches data of the previous launch sits behind griddepcontrol.wait below.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
     if (threadIdx.x == 0) {
         for (int s = 0; s < NF; ++s) { mbar_init(F_FULL(s), 1); mbar_init(F_EMPTY(s), CTEAM); }
         for (int s = 0; s < C::NA; ++s) { mbar_init(A_FULL(s), CTEAM); mbar_init(A_EMPTY(s), 1); }
@@ -212,7 +207,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
         // Its own warp: sharing one issue thread with the weight stream (a ring of ~1 stage of taps) tied the activation
         // prefetch distance to the MMA progress and left the converters waiting for data half of the time.
         if (elect_one()) {
-            asm volatile("griddepcontrol.wait;" ::: "memory");  // the activations are the previous launch's output
             uint32_t fu = 0;
             for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
                 MVSTER_TC3_GROUP_HEAD
@@ -406,7 +400,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
         // ------------------------------------------------------------------ epilogue
         const int q = warp & 3, r = q * 32 + lane;  // TMEM lane quarter, accumulator row = pixel in the tile
         uint32_t gc = 0;
-        asm volatile("griddepcontrol.wait;" ::: "memory");  // skip tensor reads and output writes: after the previous launch
         for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x, ++gc) {
             MVSTER_TC3_GROUP_HEAD
             (void)z;
@@ -607,24 +600,10 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
     a.resident = !force_stream && a.nslab > 0 && C::SMEM_FIXED + a.nslab * C::B_BYTES <= C::SMEM_MAX;
     const int smem = C::SMEM_FIXED + (a.resident ? a.nslab : NB) * C::B_BYTES;
     const int grid = a.total_groups < sms ? a.total_groups : sms;
-    // MVSTER_TC3_PDL=0 launches without the programmatic-dependency attribute (A/B; the kernel's griddepcontrol instructions are
-    // then no-ops)
-    static const bool pdl = !(getenv("MVSTER_TC3_PDL") && atoi(getenv("MVSTER_TC3_PDL")) == 0);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, k, xm, plan, a) != cudaSuccess) {
-        set_error("conv_tc3_kernel: %s", cudaGetErrorString(cudaGetLastError()));
-        return MVSTER_ERR_CUDA;
-    }
+    // (Programmatic dependent launch between consecutive convolutions - griddepcontrol.launch_dependents at the top, .wait before
+    // the first activation load and the epilogue - was measured and removed: -60 us (3.4 %) per step with one stream, but with
+    // the two-stream forward the replayed graph stalled for 7-100 ms every few steps; profiles/r02_pdl.md.)
+    k<<<grid, THREADS, smem, st>>>(xm, plan, a);
     return check_launch("conv_tc3_kernel");
 }
 
