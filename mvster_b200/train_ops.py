@@ -28,8 +28,10 @@ def _on(device):
 
 
 def enabled_by_default() -> bool:
-    """MVSTER_TRAIN_ET=1 routes the training-mode aggregation of CUDA tensors through the kernels (default: PyTorch ops)."""
-    return os.environ.get("MVSTER_TRAIN_ET", "0") == "1"
+    """The training-mode aggregation of fp32 CUDA features runs through the fused kernel and its hand-written backward unless
+    MVSTER_TRAIN_ET=0 (then: PyTorch ops).  Measured on B200 at the cfg2 stage shapes (profiles/r02_et_backward.md): forward +
+    backward 0.29-0.53 ms against 2.9-3.6 ms, 4.2-6.7 x less memory held between the passes, gradients within 1.6e-4 of max."""
+    return os.environ.get("MVSTER_TRAIN_ET", "1") == "1"
 
 
 def usable(features: Sequence[Tensor], G: int = 0, D: int = 0) -> bool:

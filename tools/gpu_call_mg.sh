@@ -11,9 +11,10 @@ python - <<PY
 import json
 try:
     j=json.loads(open('gpurun_out/mg${N}_bench.json').read().strip().splitlines()[-1])
-    print('value', j['value'], 'ms', j['ms_per_step']); print(json.dumps(j.get('view_sharded'), indent=1)); print(json.dumps(j.get('cfg5')))
+    print('value', j['value'], 'ms', j['ms_per_step'], j['step_stats']); print(json.dumps(j.get('view_sharded'))); print(json.dumps(j.get('cfg5')))
 except Exception as e: print('no bench line', e)
 PY
+[ "$N" -gt 2 ] && exit 0
 MVSTER_SHARD_GRAPH=0 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/mg${N}_bench_nograph.json 2> gpurun_out/mg${N}_bench_nograph.err; echo "bench (eager shard) rc=$?"
 python - <<PY
 import json
