@@ -256,6 +256,7 @@ def _timed_ranks(fn, steps, flush, dist, dev, warmup=3):
     median, because these informational legs are short and a single host hiccup (allocator, NCCL watchdog) would skew a mean."""
     for _ in range(warmup):
         fn()
+    torch.cuda.synchronize()  # drain first: the barrier's NCCL kernel must not spin next to queued steps (see main().barrier)
     dist.barrier()
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -264,6 +265,7 @@ def _timed_ranks(fn, steps, flush, dist, dev, warmup=3):
         s.record()
         fn()
         e.record()
+    torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     ts = [s.elapsed_time(e) for s, e in evs]
@@ -445,9 +447,14 @@ def main():
         return out
 
     def barrier():
+        """Rendezvous of the ranks around a timed region.  The device is drained BEFORE the NCCL barrier: ProcessGroupNCCL runs the
+        barrier's all-reduce on its own stream, where it would spin on a few SMs next to the still queued steps - and a persistent
+        convolution kernel that finds 140 of 148 SMs free needs two waves (measured at 8 ranks: steps at 2.5-8.6 ms instead of 1.58
+        once the host had enqueued everything and reached the barrier)."""
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
     def timed_e2e_pipelined(steps):
         """K end-to-end steps as a serving loop runs them: the pinned-host -> device copy of step i+1's inputs is enqueued on a
