@@ -446,15 +446,26 @@ def main():
             conf_host.copy_(out["photometric_confidence"], non_blocking=True)
         return out
 
+    def drain():
+        """Wait for the device.  MVSTER_BENCH_SYNC=sleep polls an event with short sleeps instead of spinning in
+        cudaStreamSynchronize (A/B of host-side interference at 8 ranks per node)."""
+        if os.environ.get("MVSTER_BENCH_SYNC", "spin") == "sleep":
+            ev = torch.cuda.Event()
+            ev.record()
+            while not ev.query():
+                time.sleep(0.0002)
+        else:
+            torch.cuda.synchronize()
+
     def barrier():
         """Rendezvous of the ranks around a timed region.  The device is drained BEFORE the NCCL barrier: ProcessGroupNCCL runs the
         barrier's all-reduce on its own stream, where it would spin on a few SMs next to the still queued steps - and a persistent
         convolution kernel that finds 140 of 148 SMs free needs two waves (measured at 8 ranks: steps at 2.5-8.6 ms instead of 1.58
         once the host had enqueued everything and reached the barrier)."""
-        torch.cuda.synchronize()
+        drain()
         if world > 1:
             dist.barrier()
-            torch.cuda.synchronize()
+            drain()
 
     def timed_e2e_pipelined(steps):
         """K end-to-end steps as a serving loop runs them: the pinned-host -> device copy of step i+1's inputs is enqueued on a
