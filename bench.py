@@ -549,9 +549,7 @@ def main():
         torch.cuda.profiler.start()
     import gc
     gc.collect()
-    gc.disable()  # no collector pause between the launches of the timed steps
     ms_total = timed(step_resident, args.steps)
-    gc.enable()
     step_stats = {"min_ms": min(per_step), "median_ms": statistics.median(per_step),
                   "p95_ms": sorted(per_step)[min(len(per_step) - 1, int(0.95 * len(per_step)))], "max_ms": max(per_step),
                   "steps_ms": [round(t, 3) for t in per_step]}

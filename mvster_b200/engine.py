@@ -94,26 +94,28 @@ def module_state(net) -> Dict[str, Tensor]:
     return out
 
 
+def _dup(v, memo: Dict[int, Tensor], srcs: List[Tensor], dsts: List[Tensor]):
+    if isinstance(v, dict):
+        return {k: _dup(x, memo, srcs, dsts) for k, x in v.items()}
+    if not torch.is_tensor(v):
+        return v
+    got = memo.get(id(v))
+    if got is None:
+        got = memo[id(v)] = torch.empty_like(v)  # preserve_format: the permuted mono_feat view keeps its strides
+        srcs.append(v)
+        dsts.append(got)
+    return got
+
+
 def _copy_outputs(out: Dict) -> Dict:
     """Fresh tensors for every distinct tensor of an output dict (one multi-tensor copy); entries that alias each other in
-    ``out`` (the top-level keys and ``stage4``'s, MVS4Net.py:104-105) alias each other in the result."""
-    memo: Dict[int, Tensor] = {}
+    ``out`` (the top-level keys and ``stage4``'s, MVS4Net.py:104-105) alias each other in the result.  (A module-level helper, not
+    a recursive closure: a closure that refers to itself is cyclic garbage that keeps its lists - and with them every copied
+    tensor, ~45 MB per call at cfg2 - alive until the cycle collector runs; with the collector off the caching allocator then
+    falls back to cudaMalloc after a dozen calls and each step stalls for milliseconds - measured at 8 ranks, profiles/r02_multi_gpu.md.)"""
     srcs: List[Tensor] = []
     dsts: List[Tensor] = []
-
-    def dup(v):
-        if isinstance(v, dict):
-            return {k: dup(x) for k, x in v.items()}
-        if not torch.is_tensor(v):
-            return v
-        got = memo.get(id(v))
-        if got is None:
-            got = memo[id(v)] = torch.empty_like(v)  # preserve_format: the permuted mono_feat view keeps its strides
-            srcs.append(v)
-            dsts.append(got)
-        return got
-
-    res = dup(out)
+    res = _dup(out, {}, srcs, dsts)
     if srcs:
         torch._foreach_copy_(dsts, srcs)
     return res

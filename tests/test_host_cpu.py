@@ -259,3 +259,25 @@ def test_engine_input_contract_is_checked_before_any_launch():
     for a, b, c, msg in bad:
         with pytest.raises(ValueError, match=msg.replace("[", r"\[").replace("]", r"\]")):
             engine.check_inputs(m, a, b, c)
+
+
+def test_graph_output_copies_leave_no_cyclic_garbage():
+    """engine._copy_outputs runs once per forward on ~45 MB of outputs: its copies must die with the caller's reference (no
+    reference cycle that waits for the cycle collector) and keep the aliasing between the top-level and the stage-4 entries."""
+    import gc
+    import weakref
+    from mvster_b200.engine import _copy_outputs
+    gc.collect()
+    gc.disable()
+    try:
+        t = torch.zeros(1000)
+        st = {"depth": t, "mono_feat": torch.ones(3, 4).t()}
+        out = {"stage4": st, "depth": t}
+        r = _copy_outputs(out)
+        assert r["depth"] is r["stage4"]["depth"] and r["depth"] is not t
+        assert r["stage4"]["mono_feat"].stride() == st["mono_feat"].stride() and torch.equal(r["stage4"]["mono_feat"], st["mono_feat"])
+        w = weakref.ref(r["depth"])
+        del r
+        assert w() is None
+    finally:
+        gc.enable()
