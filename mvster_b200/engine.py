@@ -333,7 +333,7 @@ class InferenceEngine:
 
     def _run_stage(self, net, p: StagePlan, wts: Dict[str, Tensor], feats_k: List[Tensor], proj_matrices: Dict[str, Tensor],
                    dv: Tensor, prev: Optional[Dict], temp: float, shard=None, pose: Optional[Tensor] = None,
-                   deferred: Optional[List] = None) -> Dict:
+                   deferred: Optional[List] = None, mono_feat: Optional[Tensor] = None) -> Dict:
         """One cascade stage (MVS4Net.py:78-105 loop body + stagenet.forward) on the current stream.  ``pose``: relative poses
         computed earlier (they only depend on the inputs); ``deferred``: if given, the confidence up-sampling - which no later
         stage reads - is appended to it as a closure instead of being launched here, to keep it off the stage-to-stage chain."""
@@ -358,19 +358,16 @@ class InferenceEngine:
         if inverse:
             out["inverse_min_depth"] = h["inverse_min_depth"]
             out["inverse_max_depth"] = h["inverse_max_depth"]
-        if net.mono:
-            if self._interleaved(p.k, ref):  # back to the natural channel order: natural[..., c] = stored[..., inverse[c]]
-                inv = self._inverse_perm(p.k)
-
-                def emit(o=out, r=ref, i=inv):
-                    o["mono_feat"] = r.index_select(3, i).permute(0, 3, 1, 2)
-                if deferred is None:
-                    emit()
-                else:
-                    deferred.append(emit)  # an output only: off the stage-to-stage chain
-            else:
-                out["mono_feat"] = ref.permute(0, 3, 1, 2)  # [B,C,H,W] view, as mvs4net_utils.py:1092
+        if net.mono:  # [B,C,H,W] view of the reference features, as mvs4net_utils.py:1092
+            out["mono_feat"] = mono_feat if mono_feat is not None else self._mono_feat(p.k, ref)
         return out
+
+    def _mono_feat(self, k: int, ref: Tensor) -> Tensor:
+        """The reference view's stage-k features as [B,C,H,W] in the NATURAL channel order (an output only).  Where the engine keeps
+        them group-interleaved this is one gather: natural[..., c] = stored[..., inverse[c]]."""
+        if self._interleaved(k, ref):
+            return ref.index_select(3, self._inverse_perm(k)).permute(0, 3, 1, 2)
+        return ref.permute(0, 3, 1, 2)
 
     def _inverse_perm(self, k: int) -> Tensor:
         cache = self.__dict__.setdefault("_inv_perm", {})
@@ -430,20 +427,28 @@ class InferenceEngine:
             poses = [capi.pose(proj_matrices[f"stage{k + 1}"].to(device=self.device, dtype=torch.float32).contiguous(), **pose_kw) for k in range(4)]
             pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen, on_level=on_level)
             feats = [[pyramid[f"stage{k + 1}"][i * B:(i + 1) * B] for i in range(n_own)] for k in range(4)]
+            # outputs that only depend on the pyramid go out here, on the main stream, in the gap between the pyramid's last launch
+            # and the join with the side stream (at the end of the forward they were 37 us of serialised tail)
+            mono = [self._mono_feat(k, feats[k][0]) if net.mono else None for k in range(4)]
             lib.mvster_set_sm_budget(side_sms)
             prev = None
             with torch.cuda.stream(side):
                 for p, wts in zip(self.plans[:3], self.stage_weights[:3]):
                     side.wait_event(events[p.k])
-                    prev = self._run_stage(net, p, wts, feats[p.k], proj_matrices, dv, prev, temp, shard=shard, pose=poses[p.k], deferred=deferred)
+                    prev = self._run_stage(net, p, wts, feats[p.k], proj_matrices, dv, prev, temp, shard=shard, pose=poses[p.k], deferred=deferred,
+                                           mono_feat=mono[p.k])
                     outputs[f"stage{p.k + 1}"] = prev
                 done = torch.cuda.Event()
                 done.record(side)
+                for fn in deferred:  # confidence maps of stages 1-3 (outputs only): on the side stream, next to stage 4
+                    fn()
+                tail = torch.cuda.Event()
+                tail.record(side)
             lib.mvster_set_sm_budget(0)
             main.wait_event(done)
-            prev = self._run_stage(net, self.plans[3], self.stage_weights[3], feats[3], proj_matrices, dv, prev, temp, shard=shard, pose=poses[3])
-            for fn in deferred:  # confidence maps of stages 1-3 (outputs only)
-                fn()
+            prev = self._run_stage(net, self.plans[3], self.stage_weights[3], feats[3], proj_matrices, dv, prev, temp, shard=shard, pose=poses[3],
+                                   mono_feat=mono[3])
+            main.wait_event(tail)  # join: everything the forward returns is ordered before the caller's stream continues
             outputs["stage4"] = prev
             outputs.update(prev)
         finally:
