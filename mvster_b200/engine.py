@@ -261,7 +261,8 @@ class InferenceEngine:
                tuple(depth_values.shape), self.weights_version, self._precision(net, "reg"),
                getattr(net, "fpn_backend", "torch"), self._precision(net, "fpn"),
                getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"),
-               None if shard is None else (shard.first_view, shard.count, shard.parts, id(shard.group)))
+               None if shard is None else (shard.first_view, shard.count, shard.parts, id(shard.group)),
+               int(getattr(net, "graph_slot", 0)))
         entry = self._graphs.get(key)
         if entry is None:
             with _CAPTURE_LOCK, torch.cuda.device(self.device):
