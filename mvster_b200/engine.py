@@ -423,9 +423,15 @@ class InferenceEngine:
         outputs: Dict = {}
         deferred: List = []
         try:
-            # relative poses depend on the inputs only: computed up front, off the stage-to-stage chain
+            # relative poses depend on the inputs only: computed up front, off the stage-to-stage chain - and off the main stream,
+            # whose first launch is the pyramid's stem (the four one-warp pose launches were 18 us in front of it)
             pose_kw = {} if shard is None else dict(first_view=shard.first_view, n_views=shard.count)  # a view shard: its own source views only
-            poses = [capi.pose(proj_matrices[f"stage{k + 1}"].to(device=self.device, dtype=torch.float32).contiguous(), **pose_kw) for k in range(4)]
+            projs = [proj_matrices[f"stage{k + 1}"].to(device=self.device, dtype=torch.float32).contiguous() for k in range(4)]
+            fork = torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(fork)  # the inputs were produced on (or before) the main stream
+                poses = [capi.pose(pr, **pose_kw) for pr in projs]
             pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen, on_level=on_level)
             feats = [[pyramid[f"stage{k + 1}"][i * B:(i + 1) * B] for i in range(n_own)] for k in range(4)]
             # outputs that only depend on the pyramid go out here, on the main stream, in the gap between the pyramid's last launch
