@@ -274,9 +274,9 @@ class MVS4net(nn.Module):
         # buffers, valid until the next call with the same signature).
         self.use_cuda_graph = os.environ.get("MVSTER_CUDA_GRAPH", "1") == "1"
         self.graph_static_outputs = os.environ.get("MVSTER_GRAPH_STATIC_OUTPUTS", "0") == "1"
-        # several frames in flight: each value of graph_slot owns its own captured graph (static inputs, workspace, outputs), so a
-        # serving loop can replay slot 0 and slot 1 on two streams and let frame i+1's feature pyramid fill the SMs that frame i's
-        # latency-bound cascade stages leave idle (bench.py: e2e with frames_in_flight = 2)
+        # several frames in flight (experimental): each value of graph_slot owns its own captured graph (static inputs, workspace,
+        # outputs), so a serving loop can replay slot 0 and slot 1 on two streams.  Measured with bench.py's MVSTER_BENCH_INFLIGHT=2:
+        # +15-19 % in some runs, 2-4x slower in others (both graphs' persistent kernels size their grids for the whole GPU)
         self.graph_slot = 0
         self._view_shard = None  # sharding.ViewShard: this rank's slice of the source views (multi-GPU inference)
 
