@@ -232,6 +232,89 @@ def extra_legs(model, dev, flush, steps=5):
     return out
 
 
+def bf16_storage_leg(model, dev, flush, ref_fp32=None, inputs_cfg2=None, steps=5):
+    """BASELINE configs[2]: the bf16-storage configuration (model.storage = "bf16": bf16 features and cost volume in HBM, one-term
+    bf16 tcgen05 convolutions in the regulariser, fp32 geometry / softmax / accumulation; the reference has no bf16 path, so
+    PARITY IS UNPINNED - the yardstick is this repository's oracle.cascade_forward(storage_dtype=bfloat16,
+    storage_fpn_internal=False)) at the reference's full test-time size, 5 views 1152x1600 (general_eval4.py:92-109 crops DTU's
+    1200x1600 to a multiple of 64), with the warp/ET kernel's own roofline (bf16 bytes) and, at cfg2's size, the comparison with
+    the bf16 oracle."""
+    from mvster_b200 import capi, fpn_engine, synth
+    peak, peak_src = measured_peaks()
+    nv, H, W = 5, 1152, 1600
+    res = {"workload": f"cfg3: {nv} views, {H}x{W}, 4-stage cascade, bf16 storage (features, cost volume, regulariser operands), one frame",
+           "parity_pin": "unpinned (the reference has no bf16 path; oracle definition: oracle/mvster_oracle.py storage)"}
+    prev = getattr(model, "storage", "fp32")
+    eng = model._engines.get(dev.index)
+    try:
+        for storage in ("bf16", "fp32"):
+            model.storage = storage
+            imgs, proj, dv = synth.make_inputs(1, nv, H, W, seed=0)
+            imgs, proj, dv = [t.to(dev) for t in imgs], {k: v.to(dev) for k, v in proj.items()}, dv.to(dev)
+
+            def fwd():
+                with torch.no_grad():
+                    return model(imgs, proj, dv)
+            ms, best = _time_forward(fwd, steps, flush)
+            res["ms_per_step" if storage == "bf16" else "fp32_ms_per_step"] = ms
+            if storage == "bf16":
+                res.update(min_ms=best, value=1.0 / (ms * 1e-3), unit=UNIT)
+                out = fwd()
+                # the stage launches of the warp/ET kernel alone, on the engine's own (interleaved, bf16) features
+                prec = eng._precision(model, "fpn")
+                npass = {"fp32": 0, "3xtf32": 3, "tf32": 1, "3xbf16": 3, "2xfp16": 2}[prec]
+                with torch.no_grad():
+                    pyr = fpn_engine.run_fpn(eng.fpn_weights, torch.cat(imgs, 0).contiguous(), npass, gen=3 if prec in ("3xbf16", "2xfp16") else 2)
+                per_stage = []
+                for k in range(4):
+                    f = capi.cast_bf16(pyr[f"stage{k + 1}"])
+                    feats = [f[v:v + 1] for v in range(nv)]
+                    hypo, pose = out[f"stage{k + 1}"]["hypo_depth"], capi.pose(proj[f"stage{k + 1}"])
+                    ts = []
+                    for i in range(13):
+                        flush.fill_(1.0)
+                        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        s.record()
+                        capi.et_fuse_bf16(feats[0], feats[1:], pose, hypo, G_K[k], 2.0, interleaved=bool(eng.interleave[k]))
+                        e.record()
+                        torch.cuda.synchronize()
+                        if i >= 3:
+                            ts.append(s.elapsed_time(e))
+                    h, w = H >> (3 - k), W >> (3 - k)
+                    nbytes = nv * C_K[k] * h * w * 2 + D_K[k] * h * w * 4 + G_K[k] * D_K[k] * h * w * 2  # bf16 features + fp32 hypotheses + bf16 cost
+                    t = statistics.mean(ts)
+                    per_stage.append({"stage": k + 1, "us": t * 1e3, "bytes": nbytes, "gbs": nbytes / (t * 1e-3) / 1e9, "kernel": capi.et_last_kernel()})
+                tot_b, tot_t = sum(p["bytes"] for p in per_stage), sum(p["us"] for p in per_stage) * 1e-6
+                res["roofline"] = {"kernel": per_stage[3]["kernel"] + f" (stage 4 launch, {H * W} pixels, {nv - 1} source views)", "bound": "hbm",
+                                   "achieved": per_stage[3]["gbs"], "peak": peak, "unit": "GB/s", "frac": per_stage[3]["gbs"] / peak,
+                                   "peak_source": peak_src, "algorithmic_bytes": per_stage[3]["bytes"], "traffic": None,
+                                   "all_stages": {"achieved": tot_b / tot_t / 1e9, "frac": tot_b / tot_t / 1e9 / peak, "bytes": tot_b, "us": tot_t * 1e6},
+                                   "per_stage": per_stage}
+                del pyr, out
+            del imgs, proj, dv
+            eng._graphs.clear()
+            torch.cuda.empty_cache()
+        if ref_fp32 is not None and inputs_cfg2 is not None:  # comparison with the bf16 oracle at cfg2's size (the oracle as CHECKER)
+            from oracle import mvster_oracle as oracle
+            from oracle.compare import cascade_parity
+            imgs_h, proj_h, dv_h, sd, cfg = inputs_cfg2
+            model.storage = "bf16"
+            with torch.no_grad():
+                ours = model([t.to(dev) for t in imgs_h], {k: v.to(dev) for k, v in proj_h.items()}, dv_h.to(dev))
+            want = oracle.cascade_forward(sd, cfg, imgs_h, proj_h, dv_h, storage_dtype=torch.bfloat16, storage_fpn_internal=False)
+            rep = cascade_parity(ours, want, tie_gap=0.1, max_bad=2e-2, max_attn1=0.1)
+            dist_ours = [(ours[f"stage{s}"]["attn_weight"].cpu() - want[f"stage{s}"]["attn_weight"]).abs().mean().item() for s in range(1, 5)]
+            dist_fp32 = [(ref_fp32[f"stage{s}"]["attn_weight"] - want[f"stage{s}"]["attn_weight"]).abs().mean().item() for s in range(1, 5)]
+            rep["mean_attn_distance_to_bf16_oracle"] = {"ours": dist_ours, "fp32_network": dist_fp32}
+            rep["ok"] = bool(rep["ok"] and all(a <= 0.9 * b for a, b in zip(dist_ours, dist_fp32)))
+            rep["criterion"] += "; per stage mean |attn - attn_bf16_oracle| below 0.9x the fp32 network's distance to the same oracle"
+            res["parity"] = rep
+            eng._graphs.clear()
+    finally:
+        model.storage = prev
+    return res
+
+
 def et_traffic_record(kernel_key: str):
     """DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) of the stage-4 warp/ET launch, read from the
     committed summary of an `ncu --set full` capture (profiles/et_traffic.json, written by tools/ncu_summary.py --traffic);
@@ -679,7 +762,7 @@ def main():
                            "; every M128 x K16 MMA is bound by its 4 KB A-operand fetch from shared memory, not by the multipliers, and the"
                            " layer by the activation ring's latency (profiles/r01_conv_tc3_h16_ncu.md)", "traffic": None}
 
-    cpu_base, parity = None, None
+    cpu_base, parity, bf16_inputs, ref_out = None, None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import mvster_oracle as oracle
         from oracle.compare import cascade_parity
@@ -696,6 +779,7 @@ def main():
                     "sample": f"{args.cpu_baseline_steps} full forwards of the same frame after 1 warm-up (oracle port, torch CPU fp32)"}
         # the oracle as CHECKER: the frame the timed loop produced (same inputs, same weights) against the oracle's
         parity = cascade_parity(step_resident(), ref_out)
+        bf16_inputs = (imgs_h, proj_h, dv_h, sd, cfg)
 
     eager, extra = None, None
     if rank == 0 and world == 1 and not args.quick:
@@ -705,6 +789,10 @@ def main():
         ms, best = _time_forward(step_resident, 10, flush)
         model.use_cuda_graph = graphed
         extra["no_cuda_graph"] = {"ms_per_step": ms, "min_ms": best, "value": B / (ms * 1e-3)}
+        try:  # informational: a failure here must not take the headline down with it
+            extra["bf16_storage"] = bf16_storage_leg(model, dev, flush, ref_out, bf16_inputs)
+        except Exception as exc:  # noqa: BLE001
+            extra["bf16_storage"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
 
     multi = None
     if world > 1 and not args.quick and P == 1:

@@ -107,6 +107,16 @@ int mvster_et_fuse_f32(const float* ref, const float* const* src_host, int V, co
                        float attn_temp, int flags, mvster_stream_t stream);
 
 
+/* bf16-storage form of the same fused kernel (BASELINE configs[2]): ref / src hold bf16 features, cost [B][D][H][W][G] is
+ * written as bf16 (one rounding, on the way out); geometry, correlations, softmax and the weighted sums are the fp32
+ * arithmetic of mvster_et_fuse_f32.  Halves the kernel's HBM traffic.  (C,G,D) in {(64,8,8),(32,8,8),(16,4,4),(8,4,4)};
+ * flags: MVSTER_ET_WINDOW / NO_WINDOW / INTERLEAVED only (no partial sums: view sharding stays fp32). */
+int mvster_et_fuse_bf16(const void* ref, const void* const* src_host, int V, const float* pose,
+                        const float* hypo, void* cost, int B, int C, int G, int D, int H, int W, int Hs, int Ws,
+                        float attn_temp, int flags, mvster_stream_t stream);
+/* fp32 -> bf16, round to nearest even (the feature pyramid's outputs on their way into mvster_et_fuse_bf16); 16-byte aligned. */
+int mvster_cast_bf16(const float* in, void* out, long long n, mvster_stream_t stream);
+
 /* cost[b,d,y,x,g] = acc / (1e-8 + wsum[b,d,y,x]) in place: the division of
  * mvs4net_utils.py:1060 applied after the partials were all-reduced. */
 int mvster_et_normalize_f32(float* cost, const float* wsum, int B, int G, int D, int H, int W,
@@ -166,6 +176,13 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
  * the activations are split the same way and the layer costs two MMAs per 16 channels instead of three; same fp32-class
  * accuracy (22-bit operands) for |x|, |w| < 65504. */
 #define MVSTER_TC3_FP16X2 256
+/* Third arithmetic, the bf16-storage configuration (BASELINE configs[2]; the reference itself has no bf16 path, its pixel grid is
+ * hard-coded fp32, mvs4net_utils.py:28-29): OR MVSTER_TC3_BF16X1 into `relu` when w_packed holds ONE bf16 term per weight, rows
+ * [w1 | unused | unused] (packing.pack_tc3_weights(split=1)).  The layer's fp32 input is rounded to bf16 (nearest even - what a
+ * bf16 store applies) on its way into the MMA, products are exact, accumulation fp32: one MMA per 16 channels.  The _scaled
+ * entry points multiply the accumulator by a per-output-channel fp32 factor before the bias (the BatchNorm scale, which
+ * therefore stays out of the bf16 weights): y = [relu](scale * conv(bf16(x), w) + bias) [+ skip].  scale may be NULL. */
+#define MVSTER_TC3_BF16X1 512
 /* The generation-3 kernel is persistent (one CTA per SM for the whole launch): the grid size is how much of the GPU a launch
  * claims.  mvster_set_sm_budget(n) caps the grid of the mvster_*_tc3_* launches that follow FROM THE CALLING THREAD (thread-local
  * like the error string; 0 = all SMs, the default): replicas driven by different host threads (nn.DataParallel) do not see each
@@ -183,6 +200,9 @@ size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int stride
 int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
                         int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
                         mvster_stream_t stream);
+int mvster_conv_tc3_scaled_f32(const float* x, const void* w_packed, const float* scale, const float* bias, const float* skip,
+                               float* y, int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
+                               mvster_stream_t stream);
 
 /* Transposed convolution on the same kernel: kernel (1,3,3), stride (1,2,2), padding 1, output padding 1 (Deconv3d after BN
  * folding: the ConvTranspose3d + BN + ReLU sequences of reg2d, mvs4net_utils.py:885-898) computed as a 2x2 stride-1 convolution on the input grid whose N columns are the
@@ -194,6 +214,8 @@ int mvster_deconv_tc3_supported(int Cin, int Cout, int rows);
 size_t mvster_deconv_tc3_packed_bytes(int Cin, int Cout, int rows);
 int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
                           int B, int D, int H, int W, int Cin, int Cout, int rows, int relu, mvster_stream_t stream);
+int mvster_deconv_tc3_scaled_f32(const float* x, const void* w_packed, const float* scale, const float* bias, const float* skip,
+                                 float* y, int B, int D, int H, int W, int Cin, int Cout, int rows, int relu, mvster_stream_t stream);
 
 /* reg2d U-Net (mvs4net_utils.py:870-912) up to, not including, the 1x1x1 `prob`
  * layer: cost [B][D][H][W][G] -> feat8 [B][D][H][W][8].  `blob` holds the folded
@@ -226,6 +248,17 @@ int mvster_reg2d_tc3_ex_f32(const float* blob, const void* tc3_blob, const float
                             mvster_stream_t stream);
 int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* workspace,
                          int B, int G, int D, int H, int W, mvster_stream_t stream);
+
+/* bf16-storage reg2d (BASELINE configs[2]): cost_bf16 [B][D][H][W][G] as bf16 (what mvster_et_fuse_bf16 writes) -> feat8 fp32.
+ * Every convolution computes conv(bf16(x), bf16(w)) with fp32 accumulation, then the BatchNorm scale and shift in fp32, ReLU and
+ * the skip sum in fp32 - i.e. conv -> BN -> ReLU of mvs4net_utils.py:116-123 with bf16 rounding at the convolution's operands
+ * only.  `blob_q`: the layout of mvster_reg2d_layer_info with the UNFOLDED weights rounded to bf16 (stored as fp32) and the
+ * BatchNorm shift in the bias slots; `scales`: the BatchNorm factors of conv0..conv11 back to back (sum of Cout = 288 floats);
+ * `tc3_blob`: the slab streams of conv0..conv11 in the order of mvster_reg2d_tc3_ex_f32 packed with split = 1.  conv0 runs on
+ * the CUDA cores (bf16 loads, fp32 FMA), conv1..conv11 on the tcgen05 kernel with MVSTER_TC3_BF16X1. */
+#define MVSTER_REG2D_SCALE_FLOATS 288
+int mvster_reg2d_bf16(const float* blob_q, const void* tc3_blob, const float* scales, const void* cost_bf16, float* feat8,
+                      float* workspace, int B, int G, int D, int H, int W, mvster_stream_t stream);
 
 /* reg3d U-Net (mvs4net_utils.py:914-965; optional `--reg_mode reg3d`): 3x3x3 kernels, stride 2 along D too,
  * down_size in {1,2,3} (MVS4Net.py:48), prob = 3x3x3 conv 8->1 without bias.  cost [B][D][H][W][G] ->
@@ -283,6 +316,14 @@ int mvster_head_f32(const float* logits, const float* feat8, const float* prob_w
                     const float* hypo, float* attn, float* depth, float* conf,
                     float* inv_min, float* inv_max, float* soft_depth,
                     int B, int D, int H, int W, float split_itv, mvster_stream_t stream);
+
+/* Same with flags: MVSTER_HEAD_BF16_INPUT rounds feat8 to bf16 on the way into the `prob` layer (bf16-storage configuration;
+ * prob_w then holds bf16 values). */
+#define MVSTER_HEAD_BF16_INPUT 1
+int mvster_head_ex_f32(const float* logits, const float* feat8, const float* prob_w, const float* prob_b,
+                       const float* hypo, float* attn, float* depth, float* conf,
+                       float* inv_min, float* inv_max, float* soft_depth,
+                       int B, int D, int H, int W, float split_itv, int flags, mvster_stream_t stream);
 
 /* F.interpolate(mode='bilinear', align_corners=True) on [B][H][W] -> [B][H*f][W*f]
  * (confidence up-sampling of mvs4net_utils.py:1076-1077). */

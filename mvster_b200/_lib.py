@@ -33,6 +33,8 @@ SIGNATURES = {
     "mvster_reg3d_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_pose_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mvster_et_fuse_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "mvster_et_fuse_bf16": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "mvster_cast_bf16": (_i, [_p, _p, C.c_longlong, _p]),
     "mvster_et_normalize_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "mvster_et_last_kernel": (C.c_char_p, []),
     "mvster_et_fuse_bwd_f32": (_i, [_p, C.POINTER(_p), _i, _p, _p, _p, _p, _p, _p, C.POINTER(_p), _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
@@ -57,6 +59,9 @@ SIGNATURES = {
     "mvster_conv_tc3_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), _i]),
     "mvster_conv_tc3_packed_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "mvster_conv_tc3_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_conv_tc3_scaled_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_deconv_tc3_scaled_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_reg2d_bf16": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "mvster_pointwise_tc3_blocks_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.c_longlong, _p]),
     "mvster_pointwise_tc3_blocks_ex_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.c_longlong, _i, _p]),
     "mvster_conv2d_nhwc_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
@@ -66,6 +71,7 @@ SIGNATURES = {
     "mvster_fpn_out4_gather_f32": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p]),
     "mvster_geo_consistency_f32": (_i, [_p, _p, C.POINTER(C.c_double), _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p]),
     "mvster_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
+    "mvster_head_ex_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "mvster_upsample_bilinear_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "mvster_nchw_to_nhwc_f32": (_i, [_p, _p, _i, _i, _i, _i, _p]),
 }

@@ -34,11 +34,11 @@ def _ptr(t: Optional[Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def _chk(t: Tensor, name: str, shape: Optional[Sequence[int]] = None) -> Tensor:
+def _chk(t: Tensor, name: str, shape: Optional[Sequence[int]] = None, dtype: torch.dtype = torch.float32) -> Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise _lib.MvsterLibraryError(f"{name}: a CUDA tensor is required (the hot path has no CPU fallback)")
-    if t.dtype != torch.float32:
-        raise TypeError(f"{name}: float32 required, got {t.dtype}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: {dtype} required, got {t.dtype}")
     if not t.is_contiguous():
         raise ValueError(f"{name}: must be contiguous, got strides {t.stride()} for shape {tuple(t.shape)}")
     if shape is not None and tuple(t.shape) != tuple(shape):
@@ -144,6 +144,42 @@ def et_fuse(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: 
                    "mvster_et_fuse_f32")
     if V > MAX_VIEWS and not partial:
         et_normalize(cost, wsum)
+    return cost
+
+
+def cast_bf16(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """fp32 -> bf16 (round to nearest even) on the library's own kernel: the feature pyramid's outputs as the bf16-storage
+    configuration stores them."""
+    _chk(x, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out is None else _chk(out, "out", tuple(x.shape), torch.bfloat16)
+    _lib.check(_lib.load().mvster_cast_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "mvster_cast_bf16")
+    return out
+
+
+def et_fuse_bf16(ref: Tensor, srcs: Sequence[Tensor], pose: Tensor, hypo: Tensor, G: int, attn_temp: float,
+                 window: Optional[bool] = None, interleaved: bool = False) -> Tensor:
+    """bf16-storage form of ``et_fuse``: ref [B,H,W,C] and srcs V x [B,Hs,Ws,C] in torch.bfloat16 -> cost [B,D,H,W,G] in
+    torch.bfloat16; fp32 arithmetic in between (mvster_et_fuse_bf16)."""
+    B, H, W, Cc = ref.shape
+    _chk(ref, "ref", dtype=torch.bfloat16)
+    V = len(srcs)
+    if V > MAX_VIEWS:
+        raise ValueError(f"et_fuse_bf16: at most {MAX_VIEWS} source views per call (no partial sums with bf16 storage), got {V}")
+    D = hypo.shape[1]
+    _chk(hypo, "hypo", (B, D, H, W))
+    Hs, Ws = srcs[0].shape[1:3]
+    for i, s in enumerate(srcs):
+        _chk(s, f"src[{i}]", (B, Hs, Ws, Cc), torch.bfloat16)
+    _chk(pose, "pose", (B, V, 12))
+    cost = torch.empty((B, D, H, W, G), device=ref.device, dtype=torch.bfloat16)
+    flags = 0
+    if window is not None:
+        flags |= ET_WINDOW if window else ET_NO_WINDOW
+    if interleaved:
+        flags |= ET_INTERLEAVED
+    arr = (C.c_void_p * V)(*[s.data_ptr() for s in srcs])
+    _lib.check(_lib.load().mvster_et_fuse_bf16(_ptr(ref), arr, V, _ptr(pose), _ptr(hypo), _ptr(cost), B, Cc, G, D, H, W, Hs, Ws,
+                                               float(attn_temp), flags, _stream()), "mvster_et_fuse_bf16")
     return cost
 
 
@@ -258,12 +294,22 @@ def conv_tc3_plan(cin: int, kd: int, k: int, stride: int) -> List[tuple]:
 
 
 TC3_FP16X2 = 256  # MVSTER_TC3_FP16X2: the packed weights hold two fp16 terms (packing.pack_tc3_weights(split=2))
+TC3_BF16X1 = 512  # MVSTER_TC3_BF16X1: one bf16 term (split=1): the bf16-storage arithmetic
+REG2D_SCALE_FLOATS = 288
+
+
+def _tc3_flags(relu: bool, split: int) -> int:
+    if split not in (1, 2, 3):
+        raise ValueError(f"split must be 1 (one bf16 term), 2 (two fp16 terms) or 3 (three bf16 terms), got {split}")
+    return int(relu) | {1: TC3_BF16X1, 2: TC3_FP16X2, 3: 0}[split]
 
 
 def conv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, k: int, stride: int = 1, relu: bool = True,
-             skip: Optional[Tensor] = None, out: Optional[Tensor] = None, split: int = 3) -> Tensor:
+             skip: Optional[Tensor] = None, out: Optional[Tensor] = None, split: int = 3, scale: Optional[Tensor] = None) -> Tensor:
     """Generation-3 tcgen05 conv (persistent): x [B,D,H,W,Cin] -> [B,D,Ho,Wo,cout]; w_packed from
-    packing.pack_tc3_weights(split=split) (a float32-typed byte blob); split 3 = three bf16 terms per operand, 2 = two fp16."""
+    packing.pack_tc3_weights(split=split) (a float32-typed byte blob); split 3 = three bf16 terms per operand, 2 = two fp16,
+    1 = one bf16 term (the input is rounded to bf16: bf16-storage arithmetic).  ``scale`` [cout]: per-channel factor applied
+    to the accumulator before the bias."""
     _chk(x, "x")
     _chk(w_packed, "w_packed")
     B, D, H, W, Cin = x.shape
@@ -277,8 +323,10 @@ def conv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd:
     want = lib.mvster_conv_tc3_packed_bytes(Cin, cout, kd, k, stride)
     if want == 0 or w_packed.numel() * 4 != want:
         raise ValueError(f"conv_tc3: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
-    _lib.check(lib.mvster_conv_tc3_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
-                                       kd, k, stride, int(relu) | (TC3_FP16X2 if split == 2 else 0), _stream()), "mvster_conv_tc3_f32")
+    if scale is not None:
+        _chk(scale, "scale", (cout,))
+    _lib.check(lib.mvster_conv_tc3_scaled_f32(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
+                                              kd, k, stride, _tc3_flags(relu, split), _stream()), "mvster_conv_tc3_f32")
     return y
 
 
@@ -327,7 +375,7 @@ def reg3d(blob: Tensor, cost: Tensor, down_size: int) -> Tensor:
 
 
 def deconv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, rows: int = -1, relu: bool = True,
-               skip: Optional[Tensor] = None, out: Optional[Tensor] = None, split: int = 3) -> Tensor:
+               skip: Optional[Tensor] = None, out: Optional[Tensor] = None, split: int = 3, scale: Optional[Tensor] = None) -> Tensor:
     """Transposed conv (1,3,3) / stride (1,2,2) on the generation-3 tcgen05 kernel: x [B,D,H,W,Cin] -> [B,D,2H,2W,cout].
     rows = -1 writes every output pixel; rows = 0 / 1 only the output rows of that parity (pass ``out`` to the second call)."""
     _chk(x, "x")
@@ -342,8 +390,10 @@ def deconv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, r
     want = lib.mvster_deconv_tc3_packed_bytes(Cin, cout, rows)
     if want == 0 or w_packed.numel() * 4 != want:
         raise ValueError(f"deconv_tc3: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
-    _lib.check(lib.mvster_deconv_tc3_f32(_ptr(x), _ptr(w_packed), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout, rows,
-                                         int(relu) | (TC3_FP16X2 if split == 2 else 0), _stream()), "mvster_deconv_tc3_f32")
+    if scale is not None:
+        _chk(scale, "scale", (cout,))
+    _lib.check(lib.mvster_deconv_tc3_scaled_f32(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout, rows,
+                                                _tc3_flags(relu, split), _stream()), "mvster_deconv_tc3_f32")
     return y
 
 
@@ -398,9 +448,29 @@ def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: O
     return out
 
 
+def reg2d_bf16(blob_q: Tensor, tc3_blob: Tensor, scales: Tensor, cost: Tensor, workspace: Optional[Tensor] = None,
+               out: Optional[Tensor] = None) -> Tensor:
+    """bf16-storage reg2d (mvster_reg2d_bf16): cost [B,D,H,W,G] torch.bfloat16 -> feat8 [B,D,H,W,8] fp32; the three weight
+    tensors come from packing.pack_reg2d_bf16."""
+    _chk(cost, "cost", dtype=torch.bfloat16)
+    B, D, H, W, G = cost.shape
+    _chk(blob_q, "blob_q", (reg2d_blob_floats(G),))
+    _chk(tc3_blob, "tc3_blob", (int(_lib.load().mvster_reg2d_tc3_blob_bytes(G)) // 4,))
+    _chk(scales, "scales", (REG2D_SCALE_FLOATS,))
+    need = reg2d_workspace_floats(B, D, H, W)
+    if workspace is None:
+        workspace = torch.empty(need, device=cost.device, dtype=torch.float32)
+    if workspace.numel() < need:
+        raise ValueError(f"workspace too small: {workspace.numel()} < {need} floats")
+    out = torch.empty((B, D, H, W, 8), device=cost.device, dtype=torch.float32) if out is None else _chk(out, "feat8", (B, D, H, W, 8))
+    _lib.check(_lib.load().mvster_reg2d_bf16(_ptr(blob_q), _ptr(tc3_blob), _ptr(scales), _ptr(cost), _ptr(out), _ptr(workspace),
+                                             B, G, D, H, W, _stream()), "mvster_reg2d_bf16")
+    return out
+
+
 def head(hypo: Tensor, split_itv: float, logits: Optional[Tensor] = None, feat8: Optional[Tensor] = None,
          prob_w: Optional[Tensor] = None, prob_b: Optional[Tensor] = None, inverse: bool = True,
-         want_soft: bool = False) -> dict:
+         want_soft: bool = False, bf16_input: bool = False) -> dict:
     _chk(hypo, "hypo")
     B, D, H, W = hypo.shape
     if logits is not None:
@@ -417,10 +487,10 @@ def head(hypo: Tensor, split_itv: float, logits: Optional[Tensor] = None, feat8:
         out["inverse_max_depth"] = new(B, H, W)
     if want_soft:
         out["soft_depth"] = new(B, H, W)
-    _lib.check(_lib.load().mvster_head_f32(_ptr(logits), _ptr(feat8), _ptr(prob_w), _ptr(prob_b), _ptr(hypo),
-                                           _ptr(out["attn_weight"]), _ptr(out["depth"]), _ptr(out["conf_low"]),
-                                           _ptr(out.get("inverse_min_depth")), _ptr(out.get("inverse_max_depth")),
-                                           _ptr(out.get("soft_depth")), B, D, H, W, float(split_itv), _stream()),
+    _lib.check(_lib.load().mvster_head_ex_f32(_ptr(logits), _ptr(feat8), _ptr(prob_w), _ptr(prob_b), _ptr(hypo),
+                                              _ptr(out["attn_weight"]), _ptr(out["depth"]), _ptr(out["conf_low"]),
+                                              _ptr(out.get("inverse_min_depth")), _ptr(out.get("inverse_max_depth")),
+                                              _ptr(out.get("soft_depth")), B, D, H, W, float(split_itv), 1 if bf16_input else 0, _stream()),
                "mvster_head_f32")
     return out
 

@@ -120,14 +120,17 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 #endif
 }  // namespace px4
 
-template <int CIN>
+// BF (bf16 storage, mvster_reg2d_bf16): x holds bf16 voxels (the bf16 cost volume), `scale` the per-channel BatchNorm factor that
+// stays out of the bf16-valued weights: y = relu(scale * conv(x, w) + bias), accumulators start at zero.
+template <int CIN, bool BF = false>
 __global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y,
-                                                        long long NP, int H, int W, int relu) {   // NP = B * D planes
+                                                        long long NP, int H, int W, int relu, const float* __restrict__ scale = nullptr) {   // NP = B * D planes
     using namespace px4;
-    __shared__ __align__(16) float w_s[9 * CIN * 8 + 8];
+    __shared__ __align__(16) float w_s[9 * CIN * 8 + 16];
     for (int i = threadIdx.x; i < 9 * CIN * 8; i += blockDim.x) w_s[i] = __ldg(w + i);
     if (threadIdx.x < 8) w_s[9 * CIN * 8 + threadIdx.x] = bias ? __ldg(bias + threadIdx.x) : 0.f;
+    if (BF && threadIdx.x >= 8 && threadIdx.x < 16) w_s[9 * CIN * 8 + threadIdx.x] = scale ? __ldg(scale + threadIdx.x - 8) : 1.f;
     __syncthreads();
     const unsigned W4 = (unsigned)W >> 2;
     const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;                 // quads: < 2^31 (checked on the host)
@@ -136,7 +139,10 @@ __global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict_
     const int x0 = (int)(q - r * W4) * 4, yy = (int)(r % (unsigned)H);
     const long long pl = r / (unsigned)H;
     unsigned long long acc[4][4];                                             // [voxel][output-channel pair]
-    {
+    if constexpr (BF) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = pack2(0.f, 0.f);
+    } else {
         const float4 b0 = *reinterpret_cast<const float4*>(w_s + 9 * CIN * 8), b1 = *reinterpret_cast<const float4*>(w_s + 9 * CIN * 8 + 4);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -149,13 +155,27 @@ __global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict_
     for (int ky = 0; ky < 3; ++ky) {
         const int iy = yy + ky - 1;
         if ((unsigned)iy >= (unsigned)H) continue;
-        const float4* row = reinterpret_cast<const float4*>(x + ((pl * H + iy) * W + x0) * CIN);
         float4 t[6][CIN / 4];                                                 // voxels x0-1 .. x0+4
+        if constexpr (BF) {  // 4 bf16 channels = 8 bytes; bf16 -> fp32 is a shift / mask
+            const uint2* row = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + ((pl * H + iy) * W + x0) * CIN);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const bool ok = (i > 0 || x0 > 0) && (i < 5 || x0 + 4 < W);
+            for (int i = 0; i < 6; ++i) {
+                const bool ok = (i > 0 || x0 > 0) && (i < 5 || x0 + 4 < W);
 #pragma unroll
-            for (int c4 = 0; c4 < CIN / 4; ++c4) t[i][c4] = ok ? __ldg(row + (i - 1) * (CIN / 4) + c4) : zero;
+                for (int c4 = 0; c4 < CIN / 4; ++c4) {
+                    const uint2 u = ok ? __ldg(row + (i - 1) * (CIN / 4) + c4) : make_uint2(0u, 0u);
+                    t[i][c4] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                                           __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+                }
+            }
+        } else {
+            const float4* row = reinterpret_cast<const float4*>(x + ((pl * H + iy) * W + x0) * CIN);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const bool ok = (i > 0 || x0 > 0) && (i < 5 || x0 + 4 < W);
+#pragma unroll
+                for (int c4 = 0; c4 < CIN / 4; ++c4) t[i][c4] = ok ? __ldg(row + (i - 1) * (CIN / 4) + c4) : zero;
+            }
         }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
@@ -183,6 +203,11 @@ __global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict_
     for (int p = 0; p < 4; ++p) {
         const float2 a0 = unpack2(acc[p][0]), a1 = unpack2(acc[p][1]), a2 = unpack2(acc[p][2]), a3 = unpack2(acc[p][3]);
         float4 r0 = make_float4(a0.x, a0.y, a1.x, a1.y), r1 = make_float4(a2.x, a2.y, a3.x, a3.y);
+        if constexpr (BF) {
+            const float* bs = w_s + 9 * CIN * 8;  // [8] bias, [8] scale
+            r0.x = fmaf(r0.x, bs[8], bs[0]); r0.y = fmaf(r0.y, bs[9], bs[1]); r0.z = fmaf(r0.z, bs[10], bs[2]); r0.w = fmaf(r0.w, bs[11], bs[3]);
+            r1.x = fmaf(r1.x, bs[12], bs[4]); r1.y = fmaf(r1.y, bs[13], bs[5]); r1.z = fmaf(r1.z, bs[14], bs[6]); r1.w = fmaf(r1.w, bs[15], bs[7]);
+        }
         if (relu) {
             r0.x = fmaxf(r0.x, 0.f); r0.y = fmaxf(r0.y, 0.f); r0.z = fmaxf(r0.z, 0.f); r0.w = fmaxf(r0.w, 0.f);
             r1.x = fmaxf(r1.x, 0.f); r1.y = fmaxf(r1.y, 0.f); r1.z = fmaxf(r1.z, 0.f); r1.w = fmaxf(r1.w, 0.f);
@@ -236,6 +261,16 @@ int conv_px2(const float* x, const float* w, const float* bias, const float* ski
         case 64: return dispatch_px2<64>(a, st);
     }
     return -100;
+}
+
+// conv0 of the bf16-storage regulariser: x = the bf16 cost volume [NP][H][W][Cin], w [9][Cin][8] (bf16-valued fp32), y fp32
+int conv0_bf16(const void* x, const float* w, const float* scale, const float* bias, float* y, long long NP, int H, int W, int Cin,
+               cudaStream_t st) {
+    if (W % 4 || (Cin != 4 && Cin != 8) || NP * H * (W / 4) >= (1ll << 31)) return -100;
+    const long long n = NP * H * (W / 4);
+    if (Cin == 4) conv0_px4_kernel<4, true><<<ceil_div(n, 128), 128, 0, st>>>((const float*)x, w, bias, y, NP, H, W, 1, scale);
+    else conv0_px4_kernel<8, true><<<ceil_div(n, 128), 128, 0, st>>>((const float*)x, w, bias, y, NP, H, W, 1, scale);
+    return check_launch("conv0_px4_kernel[bf16]");
 }
 
 }  // namespace mvster

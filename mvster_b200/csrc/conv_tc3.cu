@@ -24,10 +24,16 @@
 //     fp32-class accuracy with 2/3 of the MMAs, operand conversions and operand bytes; valid for |x| < 65504 (fp16 range; larger
 //     inputs saturate), which is why the 3 x bf16 arithmetic stays available.
 //
+//   * Third arithmetic (NS = 1, MVSTER_TC3_BF16X1): ONE bf16 term per operand - the bf16-storage configuration (BASELINE
+//     configs[2]): the converters round the fp32 activations to bf16 (round to nearest even, the rounding a bf16 store applies),
+//     the weights are bf16 values, one MMA per tap and 16 channels, products exact, fp32 accumulation; an optional per-channel
+//     fp32 scale (the BatchNorm factor, kept out of the bf16 weights) is applied to the accumulator before the bias.
+//
 // warp 0 = activation producer (TMA), warp 1 = TMEM owner + MMA issuer, warp 2 = weight producer, warps 3-10 = fp32 -> 3 x bf16
 // (or 2 x fp16) converters, warps 11-14 = epilogue.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "conv_tc3_plan.h"
 #include <stdlib.h>
 #include <type_traits>
 
@@ -35,33 +41,17 @@ namespace mvster {
 namespace tc3 {
 using namespace ptx;
 
-constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2, HPIX = HW_ * HH_;
-constexpr int QBYTES = HPIX * 16;            // bytes per channel quad of a halo tile (2880)
 constexpr int F_BYTES = 4 * QBYTES;          // fp32 staging of one tile-stage: [180 pixels][<= 16 channels], ONE TMA box
-constexpr int PLANE = QBYTES;                // bf16 operand plane = [180 pixels][8 channels]; 2880 = 64 (mod 128): the two
-                                             // octet planes a converter half-warp writes fall into disjoint banks
 constexpr int A_SPLIT = 2 * PLANE;           // one 16-bit term of one tile-stage: 2 channel octets
 constexpr int NCONV = 256;                 // converter threads (8 warps: one warp per SM sub-partition was latency-bound)
 constexpr int CTEAM = NCONV / 2;           // ... in two teams that take alternate tile-stages
 constexpr int THREADS = 96 + NCONV + 128;
-constexpr int MAX_STAGES = 16, MAX_TAPS = 9;
 constexpr int NF = 4, NB = 10;
 
-struct Stage {
-    short c0, nq, ox, oy, dz, ntap, slab0, pad;
-};
-struct Plan {
-    Stage st[MAX_STAGES];
-    // Per MMA slot of a stage, the low descriptor word to add to the tile's base: start shift = halo row * 10 + halo column of the
-    // tap (16-byte units, bits 0-13) | LBO (bits 16-29).  LBO = distance between the two 8-channel K halves of the MMA: the next
-    // channel-octet plane for Cin >= 16; for Cin <= 8 the second K half is a SECOND TAP of the same plane (LBO = its shift minus
-    // the first tap's), so a 3x3 conv on 8 channels needs 5 MMA slots instead of 9.
-    uint32_t a_desc[MAX_STAGES][MAX_TAPS];
-};
-__host__ inline uint32_t tap_desc(int off, int lbo) { return (uint32_t)off | ((uint32_t)lbo << 16); }
 struct Args {
     const uint8_t* w;
     const float* bias; const float* skip; float* y;
+    const float* scale;  // per output channel, applied to the accumulator before the bias (nullptr = 1)
     int D, Ho, Wo, cout, relu, sx, nstage, T, tiles_x, tiles_per_plane, groups_per_plane, total_groups, zero_a;
     // epilogue addressing (see there): ncls column blocks of Cout channels; up = 2 for the depth-to-space scatter of a transposed conv
     int ncls, py0, up, lg_cout, cls_a, cls_b;
@@ -130,7 +120,14 @@ __device__ __forceinline__ void split2h(float x, float y, uint32_t& t1, uint32_t
 template <int NC, int NS>
 __device__ __forceinline__ void mma_tile(uint32_t lo, uint64_t bd, uint32_t d, uint32_t accumulate) {
     constexpr uint32_t A_HI32 = (uint32_t)((HW_ * 16) >> 4) | (1u << 14);
-    if constexpr (NS == 3) {
+    if constexpr (NS == 1) {
+        asm volatile(
+            "{\n\t.reg .pred pa;\n\t.reg .b64 a1;\n\t"
+            "setp.ne.b32 pa, %3, 0;\n\t"
+            "mov.b64 a1, {%1, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, %2, %5, pa;\n\t}"  // bf16(a) x bf16(w)
+            ::"r"(d), "r"(lo), "l"(bd), "r"(accumulate), "n"(A_HI32), "n"(idesc_bf16_m128(NC)) : "memory");
+    } else if constexpr (NS == 3) {
         asm volatile(
             "{\n\t.reg .pred pa, pt;\n\t.reg .b32 l2, l3;\n\t.reg .b64 a1, a2, a3;\n\t"
             "setp.ne.b32 pa, %3, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
@@ -365,7 +362,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         if (i < items) {
                             const int p = i >> qsh, q = i & (nq - 1);
                             uint8_t* dst = A + (q >> 1) * PLANE + p * 16 + (q & 1) * 8;
-                            if constexpr (NS == 3) {
+                            if constexpr (NS == 1) {
+                                *reinterpret_cast<uint2*>(dst) = make_uint2(bf16x2_rn(v[k].x, v[k].y), bf16x2_rn(v[k].z, v[k].w));
+                            } else if constexpr (NS == 3) {
                                 uint2 t1, t2, t3;
                                 split3(v[k].x, v[k].y, t1.x, t2.x, t3.x);
                                 split3(v[k].z, v[k].w, t1.y, t2.y, t3.y);
@@ -438,7 +437,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     for (int c0 = cb; c0 < cb + RC; c0 += 16) {
                         uint32_t v1[16], v2[16], v3[16];
                         tmem_ld16(col + c0, v1);
-                        tmem_ld16(col + NC + c0, v2);
+                        if constexpr (NS >= 2) tmem_ld16(col + NC + c0, v2);
                         if constexpr (NS == 3) tmem_ld16(col + 2 * NC + c0, v3);
                         tmem_ld_wait();
                         if (ok && c0 < ncol) {
@@ -451,7 +450,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     if constexpr (NS == 3) o[e] = (__uint_as_float(v3[j + e]) + __uint_as_float(v2[j + e])) + __uint_as_float(v1[j + e]);
-                                    else o[e] = fmaf(__uint_as_float(v2[j + e]), 1.f / 2048.f, __uint_as_float(v1[j + e]));
+                                    else if constexpr (NS == 2) o[e] = fmaf(__uint_as_float(v2[j + e]), 1.f / 2048.f, __uint_as_float(v1[j + e]));
+                                    else o[e] = __uint_as_float(v1[j + e]);
+                                    if (a.scale) o[e] *= __ldg(a.scale + ch + e);
                                     if (a.bias) o[e] += __ldg(a.bias + ch + e);
                                     if (a.relu) o[e] = fmaxf(o[e], 0.f);
                                 }
@@ -491,68 +492,6 @@ static EncodeTiledFn encode_fn() {
             fn = (EncodeTiledFn)p;
     }
     return fn;
-}
-
-static bool supported(int Cin, int Cout, int kd, int k, int s) {
-    const bool cin_ok = Cin == 4 || Cin == 8 || Cin == 16 || Cin == 32 || Cin == 64;
-    const bool cout_ok = Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64 || (Cout == 72 && k == 1 && kd == 1);  // 72: N padded to 80
-    const bool shape_ok =(s == 1 && (k == 1 || k == 3) && (kd == 1 || kd == 3)) || (s == 2 && (k == 3 || k == 5) && kd == 1);
-    return cin_ok && cout_ok && shape_ok && kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16) <= MAX_STAGES;
-}
-
-// Stage/tap enumeration shared by the launcher and by the host-side weight packer (mvster_conv_tc3_plan).
-// Stride 2: input row 2y + ky - pad = 2 (y + m) + py with parity class py in {0,1}; class (py, px) is staged as its own halo
-// tile (TMA element strides 2, origin 2*y0 - 2 + py) and tap ky lands on halo row m + 1.
-// slabs[i] = {kz, ky, kx, first input channel, ky2, kx2}: the weights of MMA slot i; (ky2, kx2) = the tap in the second K half
-// when two taps of an <= 8-channel layer share one MMA, else (-1, -1).
-static int build_plan(int Cin, int kd, int k, int s, Plan* plan, int (*slabs)[6]) {
-    int ns = 0, nslab = 0;
-    const int kch = (Cin + 15) / 16, pz = kd / 2, pad = k / 2, npar = s == 2 ? 2 : 1;
-    const bool pair = Cin <= 8;
-    for (int kz = 0; kz < kd; ++kz)
-        for (int py = 0; py < npar; ++py)
-            for (int px = 0; px < npar; ++px)
-                for (int kc = 0; kc < kch; ++kc, ++ns) {
-                    Stage S;
-                    S.c0 = (short)(kc * 16);
-                    S.nq = (short)((Cin - kc * 16) / 4 < 4 ? (Cin - kc * 16) / 4 : 4);
-                    S.dz = (short)(kz - pz);
-                    S.ox = (short)(s == 2 ? -2 + px : -1);
-                    S.oy = (short)(s == 2 ? -2 + py : -1);
-                    S.slab0 = (short)nslab;
-                    S.pad = 0;
-                    int nt = 0, toff[25], tky[25], tkx[25];  // the stage's taps, halo offsets ascending
-                    for (int ky = 0; ky < k; ++ky)
-                        for (int kx = 0; kx < k; ++kx) {
-                            int hy, hx;
-                            if (s == 1) {
-                                hy = ky - pad + 1; hx = kx - pad + 1;
-                            } else {
-                                const int oy = ky - pad, ox = kx - pad, cy = ((oy % 2) + 2) % 2, cx = ((ox % 2) + 2) % 2;
-                                if (cy != py || cx != px) continue;
-                                hy = (oy - cy) / 2 + 1; hx = (ox - cx) / 2 + 1;
-                            }
-                            toff[nt] = hy * HW_ + hx; tky[nt] = ky; tkx[nt] = kx;
-                            ++nt;
-                        }
-                    int nslot = 0;
-                    for (int t = 0; t < nt; ++nslot, ++nslab) {
-                        // paired layers with an odd tap count: the FIRST slot is the single one, so that its second K half
-                        // (LBO = 1: the next pixel, against zero weights) still reads converted data and never past the tile
-                        const bool two = pair && !(t == 0 && (nt & 1));
-                        // LBO: next channel-octet plane, or (paired) the second tap relative to the first
-                        const int lbo = pair ? (two ? toff[t + 1] - toff[t] : 1) : (PLANE >> 4);
-                        if (plan) plan->a_desc[ns][nslot] = tap_desc(toff[t], lbo);
-                        if (slabs) {
-                            slabs[nslab][0] = kz; slabs[nslab][1] = tky[t]; slabs[nslab][2] = tkx[t]; slabs[nslab][3] = kc * 16;
-                            slabs[nslab][4] = two ? tky[t + 1] : -1; slabs[nslab][5] = two ? tkx[t + 1] : -1;
-                        }
-                        t += two ? 2 : 1;
-                    }
-                    S.ntap = (short)nslot;
-                    if (plan) plan->st[ns] = S;
-                }
-    return nslab;
 }
 
 // Persistent CTAs keep their SM for the whole launch, so the grid size is also how much of the GPU a launch claims.
@@ -607,8 +546,13 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
     return check_launch("conv_tc3_kernel");
 }
 
+// terms = operand terms of the arithmetic: 3 (bf16 x 3, the default), 2 (MVSTER_TC3_FP16X2), 1 (MVSTER_TC3_BF16X1)
+static int arith_terms(int relu_arg) { return (relu_arg & MVSTER_TC3_BF16X1) ? 1 : (relu_arg & MVSTER_TC3_FP16X2) ? 2 : 3; }
+
 template <int NC>
-static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st, bool fp16x2) {
+static int launch(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st, int terms) {
+    if (terms == 1) return launch_ns<NC, 1>(xm, plan, a, total_tiles, sms, st);  // (the merged-dimension map is not instantiated for it)
+    const bool fp16x2 = terms == 2;
     if constexpr (NC <= 32) {  // merged-dimension activation map: only small-Cin layers qualify (conv_tc3_run decides)
         if (a.cin_merged > 0)
             return fp16x2 ? launch_ns<NC, 2, true>(xm, plan, a, total_tiles, sms, st) : launch_ns<NC, 3, true>(xm, plan, a, total_tiles, sms, st);
@@ -646,7 +590,7 @@ extern "C" size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k,
 
 // block == 0: y [B][D][Ho][Wo][Cout].  block > 0 (divides Cout): output channels [j*block, (j+1)*block) go to a separate
 // tensor [B][D][Ho][Wo][block] at y + j*block_stride (floats).
-static int conv_tc3_run(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
+static int conv_tc3_run(const float* x, const void* w_packed, const float* scale, const float* bias, const float* skip, float* y,
                         int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
                         int block, long long block_stride, mvster_stream_t stream) {
     using namespace mvster::tc3;
@@ -661,7 +605,8 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     const int s = stride_hw;
     CUtensorMap xm;
     static const bool want_merge = getenv("MVSTER_TC3_MERGE") && atoi(getenv("MVSTER_TC3_MERGE")) != 0;
-    const bool merged = want_merge && s == 1 && Cin <= 16 && Cout <= 32 && (long long)W * Cin < (1ll << 31);
+    const int terms = arith_terms(relu);
+    const bool merged = want_merge && terms != 1 && s == 1 && Cin <= 16 && Cout <= 32 && (long long)W * Cin < (1ll << 31);
     if (merged) {  // [B*D][H][W*C]: a box row = the halo row's HW_ pixels x Cin channels as ONE contiguous run
         cuuint64_t dims[3] = {(cuuint64_t)W * Cin, (cuuint64_t)H, (cuuint64_t)B * D};
         cuuint64_t strides[2] = {(cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
@@ -683,8 +628,7 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     Args a;
     a.nslab = nslab;
     a.cin_merged = merged ? Cin : 0;
-    a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
-    const bool fp16x2 = relu & MVSTER_TC3_FP16X2;
+    a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y; a.scale = scale;
     a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = relu & 1; a.sx = s;
     a.nstage = kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16);
     a.tiles_x = ceil_div(a.Wo, TW);
@@ -700,23 +644,29 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* bias,
     cudaStream_t st = (cudaStream_t)stream;
     MVSTER_REQUIRE(Cout <= 64 || blocks, "mvster_conv_tc3_f32: Cout = %d only as separate channel blocks", Cout);
     const int NC = Cout < 16 ? 16 : (Cout > 64 ? 80 : Cout);
-    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st, fp16x2);
-    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st, fp16x2);
-    if (NC == 80) return launch<80>(xm, plan, a, total_tiles, sms, st, fp16x2);
-    return launch<64>(xm, plan, a, total_tiles, sms, st, fp16x2);
+    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st, terms);
+    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st, terms);
+    if (NC == 80) return launch<80>(xm, plan, a, total_tiles, sms, st, terms);
+    return launch<64>(xm, plan, a, total_tiles, sms, st, terms);
 }
 
 extern "C" int mvster_conv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
                                    int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
                                    mvster_stream_t stream) {
-    return conv_tc3_run(x, w_packed, bias, skip, y, B, D, H, W, Cin, Cout, kd, k, stride_hw, relu, 0, 0, stream);
+    return conv_tc3_run(x, w_packed, nullptr, bias, skip, y, B, D, H, W, Cin, Cout, kd, k, stride_hw, relu, 0, 0, stream);
+}
+
+extern "C" int mvster_conv_tc3_scaled_f32(const float* x, const void* w_packed, const float* scale, const float* bias, const float* skip,
+                                          float* y, int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
+                                          mvster_stream_t stream) {
+    return conv_tc3_run(x, w_packed, scale, bias, skip, y, B, D, H, W, Cin, Cout, kd, k, stride_hw, relu, 0, 0, stream);
 }
 
 extern "C" int mvster_pointwise_tc3_blocks_ex_f32(const float* x, const void* w_packed, float* y, int N, int H, int W, int Cin, int Cout,
                                                   int block, long long block_stride_floats, int flags, mvster_stream_t stream) {
     MVSTER_REQUIRE(block >= 4 && block % 4 == 0 && Cout % block == 0 && (Cout == block || block_stride_floats % 4 == 0),
                    "mvster_pointwise_tc3_blocks_f32: bad block %d for Cout %d", block, Cout);
-    return conv_tc3_run(x, w_packed, nullptr, nullptr, y, N, 1, H, W, Cin, Cout, 1, 1, 1, flags & MVSTER_TC3_FP16X2, block,
+    return conv_tc3_run(x, w_packed, nullptr, nullptr, nullptr, y, N, 1, H, W, Cin, Cout, 1, 1, 1, flags & MVSTER_TC3_FP16X2, block,
                         block_stride_floats, stream);
 }
 
@@ -734,8 +684,8 @@ extern "C" int mvster_pointwise_tc3_blocks_f32(const float* x, const void* w_pac
 // followed by a depth-to-space scatter in the epilogue.  rows = -1: all four classes in one launch (4*Cout <= 64 columns);
 // rows = 0 / 1: only the output rows of parity py (2*Cout columns; two launches cover the layer when 4*Cout > 64).
 // Slab order: [16-channel chunk][tap (dy,dx) row-major over the taps the launch needs]; rows = 0 needs only dy = 0.
-static int deconv_ncls(int rows) { return rows < 0 ? 4 : 2; }
-static int deconv_ntap(int rows) { return rows == 0 ? 2 : 4; }
+using mvster::tc3::deconv_ncls;
+using mvster::tc3::deconv_ntap;
 
 extern "C" int mvster_deconv_tc3_supported(int Cin, int Cout, int rows) {
     const int n = deconv_ncls(rows) * Cout;
@@ -750,6 +700,12 @@ extern "C" size_t mvster_deconv_tc3_packed_bytes(int Cin, int Cout, int rows) {
 
 extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
                                      int B, int D, int H, int W, int Cin, int Cout, int rows, int relu, mvster_stream_t stream) {
+    return mvster_deconv_tc3_scaled_f32(x, w_packed, nullptr, bias, skip, y, B, D, H, W, Cin, Cout, rows, relu, stream);
+}
+
+extern "C" int mvster_deconv_tc3_scaled_f32(const float* x, const void* w_packed, const float* scale, const float* bias, const float* skip,
+                                            float* y, int B, int D, int H, int W, int Cin, int Cout, int rows, int relu,
+                                            mvster_stream_t stream) {
     using namespace mvster::tc3;
     MVSTER_REQUIRE(x && w_packed && y, "mvster_deconv_tc3_f32: null pointer");
     MVSTER_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "mvster_deconv_tc3_f32: bad shape");
@@ -777,8 +733,8 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
         for (int t = 0; t < ntap; ++t) plan.a_desc[kc][t] = tap_desc((t / 2 + 1) * HW_ + (t % 2 + 1), PLANE >> 4);  // halo (1 + dy, 1 + dx)
     }
     Args a;
-    a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y;
-    const bool fp16x2 = relu & MVSTER_TC3_FP16X2;
+    a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y; a.scale = scale;
+    const int terms = arith_terms(relu);
     a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = relu & 1; a.sx = 1; a.nstage = kch;
     a.nslab = kch * ntap;
     a.cin_merged = 0;
@@ -791,7 +747,7 @@ extern "C" int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const
     const long long total_tiles = (long long)a.tiles_per_plane * B * D;
     cudaStream_t st = (cudaStream_t)stream;
     const int NC = a.ncls * Cout;
-    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st, fp16x2);
-    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st, fp16x2);
-    return launch<64>(xm, plan, a, total_tiles, sms, st, fp16x2);
+    if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st, terms);
+    if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st, terms);
+    return launch<64>(xm, plan, a, total_tiles, sms, st, terms);
 }

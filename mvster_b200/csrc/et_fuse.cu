@@ -279,6 +279,39 @@ extern "C" int mvster_et_fuse_f32(const float* ref, const float* const* src_host
     return G == 4 ? dispatch_cpg<4>(a, C / G, D, st) : dispatch_cpg<8>(a, C / G, D, st);
 }
 
+// bf16 storage (BASELINE configs[2]): features and cost volume are bf16 in HBM, everything in between is the fp32 arithmetic
+// of the kernels above (geometry, correlations, softmax, weighted sums); the cost is rounded once, on the way out.
+extern "C" int mvster_et_fuse_bf16(const void* ref, const void* const* src_host, int V, const float* pose,
+                                   const float* hypo, void* cost, int B, int C, int G, int D, int H, int W, int Hs, int Ws,
+                                   float attn_temp, int flags, mvster_stream_t stream) {
+    MVSTER_REQUIRE(ref && src_host && pose && hypo && cost, "mvster_et_fuse_bf16: null pointer");
+    MVSTER_REQUIRE(V >= 1 && V <= MVSTER_MAX_VIEWS, "mvster_et_fuse_bf16: V=%d outside 1..%d", V, MVSTER_MAX_VIEWS);
+    MVSTER_REQUIRE(B > 0 && H > 0 && W > 0 && Hs > 0 && Ws > 0, "mvster_et_fuse_bf16: bad shape");
+    MVSTER_REQUIRE(!(flags & ~(MVSTER_ET_WINDOW | MVSTER_ET_NO_WINDOW | MVSTER_ET_INTERLEAVED)),
+                   "mvster_et_fuse_bf16: only MVSTER_ET_WINDOW / NO_WINDOW / INTERLEAVED are supported with bf16 storage (flags=%d)", flags);
+    MVSTER_REQUIRE(attn_temp != 0.f, "mvster_et_fuse_bf16: attn_temp == 0");
+    MVSTER_REQUIRE(((uintptr_t)ref & 15) == 0 && ((uintptr_t)cost & 7) == 0, "mvster_et_fuse_bf16: ref must be 16-byte, cost 8-byte aligned");
+    EtArgs a;
+    a.ref = reinterpret_cast<const float*>(ref);
+    for (int v = 0; v < MVSTER_MAX_VIEWS; ++v) a.src[v] = v < V ? reinterpret_cast<const float*>(src_host[v]) : nullptr;
+    for (int v = 0; v < V; ++v) MVSTER_REQUIRE(a.src[v] && ((uintptr_t)a.src[v] & 15) == 0, "mvster_et_fuse_bf16: src[%d] is null or not 16-byte aligned", v);
+    a.pose = pose; a.hypo = hypo; a.cost = reinterpret_cast<float*>(cost); a.wsum = nullptr;
+    a.B = B; a.V = V; a.H = H; a.W = W; a.Hs = Hs; a.Ws = Ws;
+    a.attn_temp = attn_temp;
+    a.sqrt_c = (float)sqrt((double)C);
+    a.flags = flags;
+    { const char* pf = getenv("MVSTER_ET_PREFETCH"); a.prefetch = pf ? atoi(pf) : 1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = MVSTER_OK;
+    const bool window = (flags & MVSTER_ET_NO_WINDOW) ? false : (flags & MVSTER_ET_WINDOW) ? true : et_window_default();
+    if (window && try_launch_win_bf16(a, C, G, D, st, &rc)) return rc;
+    MVSTER_REQUIRE(!(flags & MVSTER_ET_INTERLEAVED) || C / G == 8,
+                   "mvster_et_fuse_bf16: MVSTER_ET_INTERLEAVED needs a window specialisation ((C,G,D) = (8,4,4), (16,4,4), (32,8,8)); got C=%d G=%d D=%d", C, G, D);
+    if (try_launch_tiled_bf16(a, C, G, D, st, &rc)) return rc;
+    set_error("mvster_et_fuse_bf16: unsupported (C,G,D) = (%d,%d,%d): bf16 storage covers (64,8,8), (32,8,8), (16,4,4), (8,4,4)", C, G, D);
+    return MVSTER_ERR_ARG;
+}
+
 extern "C" const char* mvster_et_last_kernel(void) { return g_et_kernel; }
 
 extern "C" int mvster_et_normalize_f32(float* cost, const float* wsum, int B, int G, int D, int H, int W,

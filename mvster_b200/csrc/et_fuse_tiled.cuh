@@ -63,6 +63,44 @@ __device__ __forceinline__ Pix8 ldg256(const float* p) {
     return r;
 }
 
+// bf16 storage (mvster_et_fuse_bf16): a lane's 8-channel tap is 16 bytes = one 128-bit load; bf16 -> fp32 is a shift / mask of
+// the packed words, so the arithmetic below is unchanged (fp32 geometry, correlations and softmax).
+typedef uint16_t bf16_t;
+__device__ __forceinline__ Pix8 ldg256(const bf16_t* p) {
+    Pix8 r;
+#ifdef MVSTER_CPU_EMU
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t lo = (uint32_t)p[2 * i] << 16, hi = (uint32_t)p[2 * i + 1] << 16;
+        float fl, fh;
+        memcpy(&fl, &lo, 4); memcpy(&fh, &hi, 4);
+        r.p[i] = emu::pack(fl, fh);
+    }
+#else
+    uint32_t w[4];
+    asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.p[i] = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+#endif
+    return r;
+}
+// fp32 -> bf16, round to nearest even (NaN stays NaN): the rounding of torch's .to(torch.bfloat16)
+__device__ __forceinline__ uint32_t f2bf(float x) {
+#ifdef MVSTER_CPU_EMU
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (u >> 16) | 0x40u;
+    return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+#else
+    uint16_t r;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ uint32_t f2bf2(float lo, float hi) { return f2bf(lo) | (f2bf(hi) << 16); }
+// feature / cost element types of a kernel instantiation
+template <bool BF> struct EtTypes { typedef float feat; typedef float cost; };
+template <> struct EtTypes<true> { typedef bf16_t feat; typedef bf16_t cost; };
+
 __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP
 #ifdef MVSTER_CPU_EMU
     return 1.f / x;
@@ -88,8 +126,9 @@ __device__ __forceinline__ float div_corrected(float a, float b, float r) {
     return fmaf(fmaf(-q, b, a), r, q);
 }
 
-template <int C, int G, int D, int LPP, int MB>
+template <int C, int G, int D, int LPP, int MB, bool BF = false>
 __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) {
+    typedef typename EtTypes<BF>::feat FT;  // BF: bf16 features in, bf16 cost volume out (no PARTIAL / ACCUMULATE: checked on the host)
     constexpr int CPL = C / LPP;   // channels per lane
     constexpr int GPL = G / LPP;   // groups per lane
     constexpr int CPG = C / G;     // channels per group
@@ -108,7 +147,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) 
 
     unsigned long long ref[NP];
     {
-        const Pix8 t = ldg256(a.ref + ((long long)b * plane + pix) * C + sub * CPL);
+        const Pix8 t = ldg256(reinterpret_cast<const FT*>(a.ref) + ((long long)b * plane + pix) * C + sub * CPL);
 #pragma unroll
         for (int i = 0; i < NP; ++i) ref[i] = t.p[i];
     }
@@ -116,7 +155,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) 
     const float* hp = a.hypo + (long long)b * D * plane + pix;
 #pragma unroll
     for (int d = 0; d < D; ++d) dep[d] = __ldg(hp + (long long)d * plane);
-    if (a.flags & MVSTER_ET_ACCUMULATE) {
+    if (!BF && (a.flags & MVSTER_ET_ACCUMULATE)) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const long long o = ((long long)b * D + d) * plane + pix;
@@ -150,7 +189,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) 
         const float ry = fmaf(__ldg(P + 5), 1.f, fmaf(__ldg(P + 4), fy, __ldg(P + 3) * fx));
         const float rz = fmaf(__ldg(P + 8), 1.f, fmaf(__ldg(P + 7), fy, __ldg(P + 6) * fx));
         const float tx = __ldg(P + 9), ty = __ldg(P + 10), tz = __ldg(P + 11);
-        const float* S = a.src[v];  // warp-uniform base; batch/lane offsets live in the 32-bit tap offsets
+        const FT* S = reinterpret_cast<const FT*>(a.src[v]);  // warp-uniform base; batch/lane offsets live in the 32-bit tap offsets
 
         float cor[GPL][D];
 #pragma unroll
@@ -243,7 +282,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) 
     }
 
     if (!live) return;
-    const bool partial = a.flags & MVSTER_ET_PARTIAL;
+    const bool partial = !BF && (a.flags & MVSTER_ET_PARTIAL);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const long long o = ((long long)b * D + d) * plane + pix;
@@ -251,6 +290,19 @@ __global__ void __launch_bounds__(128, MB) et_fuse_tiled_kernel(const EtArgs a) 
         float out[GPL];
 #pragma unroll
         for (int g = 0; g < GPL; ++g) out[g] = partial ? acc[g][d] : acc[g][d] * r;
+        if constexpr (BF) {  // bf16 cost volume: the lane's GPL groups as 16-bit values (GPL even, or 1 with LPP = 8)
+            bf16_t* dstb = reinterpret_cast<bf16_t*>(a.cost) + o * G + sub * GPL;
+            if constexpr (GPL % 4 == 0) {
+#pragma unroll
+                for (int g = 0; g < GPL; g += 4) *reinterpret_cast<uint2*>(dstb + g) = make_uint2(f2bf2(out[g], out[g + 1]), f2bf2(out[g + 2], out[g + 3]));
+            } else if constexpr (GPL == 2) {
+                *reinterpret_cast<uint32_t*>(dstb) = f2bf2(out[0], out[1]);
+            } else {
+#pragma unroll
+                for (int g = 0; g < GPL; ++g) dstb[g] = (bf16_t)f2bf(out[g]);
+            }
+            continue;
+        }
         float* dst = a.cost + o * G + sub * GPL;
         if constexpr (GPL % 4 == 0) {
 #pragma unroll
@@ -271,6 +323,14 @@ static int launch_et_tiled(const EtArgs& a, cudaStream_t st) {
     et_fuse_tiled_kernel<C, G, D, LPP, MB><<<grid, 128, 0, st>>>(a);
     note_et_kernel("et_fuse_tiled_kernel", C, G, D, LPP, MB);
     return check_launch("et_fuse_tiled_kernel");
+}
+
+template <int C, int G, int D, int LPP, int MB>
+static int launch_et_tiled_bf16(const EtArgs& a, cudaStream_t st) {
+    dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 4), a.B);
+    et_fuse_tiled_kernel<C, G, D, LPP, MB, true><<<grid, 128, 0, st>>>(a);
+    note_et_kernel("et_fuse_tiled_kernel[bf16]", C, G, D, LPP, MB);
+    return check_launch("et_fuse_tiled_kernel[bf16]");
 }
 
 // Resident CTAs per SM the D = 4 kernels are compiled for (register cap 65536 / (128 * MB)): 4 -> 128 regs,
@@ -295,6 +355,16 @@ static bool try_launch_tiled(const EtArgs& a, int C, int G, int D, cudaStream_t 
     }
     if (C == 32 && G == 8 && D == 8) { *rc = launch_et_tiled<32, 8, 8, 4, 4>(a, st); return true; }
     if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled<64, 8, 8, 8, 4>(a, st); return true; }
+    return false;
+}
+
+// bf16 storage: same specialisations (natural channel order only: the tiled kernel has no interleaved form)
+static bool try_launch_tiled_bf16(const EtArgs& a, int C, int G, int D, cudaStream_t st, int* rc) {
+    if ((long long)a.B * a.Hs * a.Ws * C >= (1ll << 31) || a.B > 65535) return false;
+    if (C == 8 && G == 4 && D == 4) { *rc = launch_et_tiled_bf16<8, 4, 4, 1, 5>(a, st); return true; }
+    if (C == 16 && G == 4 && D == 4) { *rc = launch_et_tiled_bf16<16, 4, 4, 2, 5>(a, st); return true; }
+    if (C == 32 && G == 8 && D == 8) { *rc = launch_et_tiled_bf16<32, 8, 8, 4, 4>(a, st); return true; }
+    if (C == 64 && G == 8 && D == 8) { *rc = launch_et_tiled_bf16<64, 8, 8, 8, 4>(a, st); return true; }
     return false;
 }
 

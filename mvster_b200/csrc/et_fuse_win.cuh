@@ -35,8 +35,8 @@ __device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigne
 }
 __device__ __forceinline__ float min_nan(float a, float b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
 __device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
-__device__ __forceinline__ void prefetch_l2(const float*) {}
-__device__ __forceinline__ void prefetch_l1(const float*) {}
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+__device__ __forceinline__ void prefetch_l1(const void*) {}
 #else
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
     unsigned long long d;
@@ -58,8 +58,8 @@ __device__ __forceinline__ float max_nan(float a, float b) {
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
     return d;
 }
-__device__ __forceinline__ void prefetch_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
 // Per-group correlations of one 8-channel tap with the lane's (pre-scaled) reference channels,
@@ -93,8 +93,8 @@ __device__ __forceinline__ void tap_groups(const Pix8& t, const unsigned long lo
 
 // Request the two window rows a lane will sample in source view v (position of the first hypothesis; the others lie
 // within a pixel or two) without holding registers: level 2 = CCTL.PF2 (towards L2), level 1 = CCTL.PF1 (towards L1).
-template <int C, int LEVEL>
-__device__ __forceinline__ void win_prefetch(const float4* pose_s, int v, const float* src, float fx, float fy, float d0,
+template <int C, int LEVEL, typename FT>
+__device__ __forceinline__ void win_prefetch(const float4* pose_s, int v, const FT* src, float fx, float fy, float d0,
                                              float max_x, float max_y, int lane_base, int row) {
     const float4 q0 = pose_s[v * 3], q1 = pose_s[v * 3 + 1], q2 = pose_s[v * 3 + 2];
     const float X = fmaf(fmaf(q0.z, 1.f, fmaf(q0.y, fy, q0.x * fx)), d0, q2.y);
@@ -103,7 +103,7 @@ __device__ __forceinline__ void win_prefetch(const float4* pose_s, int v, const 
     const float r = rcp_approx(Z);
     const float px = X * r, py = Y * r;
     if (px >= 0.f && px < max_x && py >= 0.f && py < max_y) {
-        const float* p = src + (lane_base + (int)py * row + (int)px * C);
+        const FT* p = src + (lane_base + (int)py * row + (int)px * C);
         if constexpr (LEVEL == 2) {
             prefetch_l2(p);
             prefetch_l2(p + row);
@@ -114,8 +114,9 @@ __device__ __forceinline__ void win_prefetch(const float4* pose_s, int v, const 
     }
 }
 
-template <int C, int G, int D, int LPP, int MB, bool IL = false>
+template <int C, int G, int D, int LPP, int MB, bool IL = false, bool BF = false>
 __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
+    typedef typename EtTypes<BF>::feat FT;  // BF: bf16 features in, bf16 cost volume out (no PARTIAL / ACCUMULATE: checked on the host)
     constexpr int CPL = C / LPP;   // channels per lane
     constexpr int GPL = G / LPP;   // groups per lane
     constexpr int CPG = C / G;     // channels per group
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
 
     unsigned long long ref[4];
     {
-        const Pix8 t = ldg256(a.ref + ((long long)b * plane + pix) * C + sub * CPL);
+        const Pix8 t = ldg256(reinterpret_cast<const FT*>(a.ref) + ((long long)b * plane + pix) * C + sub * CPL);
         // fold the 1/CPG of .mean(2) into the reference features (power of two: exact)
 #pragma unroll
         for (int i = 0; i < 4; ++i) ref[i] = mul2(t.p[i], pack2(1.f / CPG, 1.f / CPG));
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
         for (int k = 0; k < D / 2; ++k)
             dep2[k] = pack2(__ldg(hp + (long long)(2 * k) * plane), __ldg(hp + (long long)(2 * k + 1) * plane));
     }
-    if (a.flags & MVSTER_ET_ACCUMULATE) {
+    if (!BF && (a.flags & MVSTER_ET_ACCUMULATE)) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const long long o = ((long long)b * D + d) * plane + pix;
@@ -181,17 +182,17 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
     const int lane_base = b * a.Hs * row + sub * CPL;  // < 2^31 (checked on the host)
     const float dfirst = unpack2(dep2[0]).x;
     if (a.prefetch & 1)  // every view's window rows towards L2 before the loop
-        for (int v = 0; v < a.V; ++v) win_prefetch<C, 2>(pose_s, v, a.src[v], fx, fy, dfirst, max_x, max_y, lane_base, row);
+        for (int v = 0; v < a.V; ++v) win_prefetch<C, 2>(pose_s, v, reinterpret_cast<const FT*>(a.src[v]), fx, fy, dfirst, max_x, max_y, lane_base, row);
 
     for (int v = 0; v < a.V; ++v) {
         if ((a.prefetch & 2) && v + 1 < a.V)  // the next view's rows towards L1 while this view is processed
-            win_prefetch<C, 1>(pose_s, v + 1, a.src[v + 1], fx, fy, dfirst, max_x, max_y, lane_base, row);
+            win_prefetch<C, 1>(pose_s, v + 1, reinterpret_cast<const FT*>(a.src[v + 1]), fx, fy, dfirst, max_x, max_y, lane_base, row);
         const float4 q0 = pose_s[v * 3], q1 = pose_s[v * 3 + 1], q2 = pose_s[v * 3 + 2];  // R (row-major 3x3), t
         const float rx = fmaf(q0.z, 1.f, fmaf(q0.y, fy, q0.x * fx));
         const float ry = fmaf(q1.y, 1.f, fmaf(q1.x, fy, q0.w * fx));
         const float nrz = -fmaf(q2.x, 1.f, fmaf(q1.w, fy, q1.z * fx));
         const float tx = q2.y, ty = q2.z, ntz = -q2.w;
-        const float* S = a.src[v];  // warp-uniform base; batch/lane offsets live in the 32-bit tap offsets
+        const FT* S = reinterpret_cast<const FT*>(a.src[v]);  // warp-uniform base; batch/lane offsets live in the 32-bit tap offsets
 
         // sampling positions of the D hypotheses, two per packed operation; bit-identical to the scalar
         // sequence X = rx*d + tx (separate mul, add), Z == 0 -> 1e-9, ix = X / Z (reciprocal + FMA residual)
@@ -228,8 +229,8 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
         unsigned long long cor2[NJ][D];
         if (__all_sync(0xffffffffu, fits)) {
             const bool needx = mxf > bxf, needy = myf > byf;
-            const float* p0 = S + (lane_base + (int)byf * row + (int)bxf * C);
-            const float* p1 = p0 + row;
+            const FT* p0 = S + (lane_base + (int)byf * row + (int)bxf * C);
+            const FT* p1 = p0 + row;
             const Pix8 t00 = ldg256(p0), t01 = ldg256(p0 + C), t10 = ldg256(p1), t11 = ldg256(p1 + C);
             unsigned long long T[3][3][NJ];
 #pragma unroll
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
             tap_groups<CPG, NJ, IL>(t10, ref, T[1][0]);
             tap_groups<CPG, NJ, IL>(t11, ref, T[1][1]);
             if (needy) {
-                const float* p2 = p1 + row;
+                const FT* p2 = p1 + row;
                 const Pix8 t20 = ldg256(p2), t21 = ldg256(p2 + C);
                 tap_groups<CPG, NJ, IL>(t20, ref, T[2][0]);
                 tap_groups<CPG, NJ, IL>(t21, ref, T[2][1]);
@@ -347,11 +348,22 @@ __global__ void __launch_bounds__(128, MB) et_fuse_win_kernel(const EtArgs a) {
     }
 
     if (!live) return;
-    const bool partial = a.flags & MVSTER_ET_PARTIAL;
+    const bool partial = !BF && (a.flags & MVSTER_ET_PARTIAL);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const long long o = ((long long)b * D + d) * plane + pix;
         const float r = partial ? 1.f : __frcp_rn(ws[d]);
+        if constexpr (BF) {  // bf16 cost volume: the lane's GPL = 2 NJ groups as 16-bit values
+            bf16_t* dstb = reinterpret_cast<bf16_t*>(a.cost) + o * G + sub * GPL;
+            const float2 u0 = unpack2(acc2[0][d]);
+            if constexpr (NJ == 2) {
+                const float2 u1 = unpack2(acc2[1][d]);
+                *reinterpret_cast<uint2*>(dstb) = make_uint2(f2bf2(u0.x * r, u0.y * r), f2bf2(u1.x * r, u1.y * r));
+            } else {
+                *reinterpret_cast<uint32_t*>(dstb) = f2bf2(u0.x * r, u0.y * r);
+            }
+            continue;
+        }
         float* dst = a.cost + o * G + sub * GPL;
         if constexpr (NJ == 2) {
             const float2 u0 = unpack2(acc2[0][d]), u1 = unpack2(acc2[1][d]);
@@ -376,6 +388,15 @@ static int launch_et_win(const EtArgs& a, cudaStream_t st) {
     else et_fuse_win_kernel<C, G, D, LPP, MB, false><<<grid, 128, 0, st>>>(a);
     note_et_kernel(a.flags & MVSTER_ET_INTERLEAVED ? "et_fuse_win_kernel[interleaved]" : "et_fuse_win_kernel", C, G, D, LPP, MB);
     return check_launch("et_fuse_win_kernel");
+}
+
+template <int C, int G, int D, int LPP, int MB>
+static int launch_et_win_bf16(const EtArgs& a, cudaStream_t st) {
+    dim3 grid(ceil_div(a.W, 32 / LPP), ceil_div(a.H, 4), a.B);
+    if (a.flags & MVSTER_ET_INTERLEAVED) et_fuse_win_kernel<C, G, D, LPP, MB, true, true><<<grid, 128, 0, st>>>(a);
+    else et_fuse_win_kernel<C, G, D, LPP, MB, false, true><<<grid, 128, 0, st>>>(a);
+    note_et_kernel(a.flags & MVSTER_ET_INTERLEAVED ? "et_fuse_win_kernel[bf16, interleaved]" : "et_fuse_win_kernel[bf16]", C, G, D, LPP, MB);
+    return check_launch("et_fuse_win_kernel[bf16]");
 }
 
 // MVSTER_ET_WIN=0/1 overrides the built-in default (A/B measurements); the MVSTER_ET_WINDOW /
@@ -403,6 +424,16 @@ static bool try_launch_win(const EtArgs& a, int C, int G, int D, cudaStream_t st
         *rc = mb == 2 ? launch_et_win<32, 8, 8, 4, 2>(a, st) : mb == 4 ? launch_et_win<32, 8, 8, 4, 4>(a, st) : launch_et_win<32, 8, 8, 4, 3>(a, st);
         return true;
     }
+    return false;
+}
+
+// bf16 storage: the same three window specialisations (pose staged the same way)
+static bool try_launch_win_bf16(const EtArgs& a, int C, int G, int D, cudaStream_t st, int* rc) {
+    if ((long long)a.B * a.Hs * a.Ws * C >= (1ll << 31) || a.B > 65535) return false;
+    if (a.V * 3 > 128 || ((uintptr_t)a.pose & 15)) return false;
+    if (C == 8 && G == 4 && D == 4) { *rc = launch_et_win_bf16<8, 4, 4, 1, 4>(a, st); return true; }
+    if (C == 16 && G == 4 && D == 4) { *rc = launch_et_win_bf16<16, 4, 4, 2, 5>(a, st); return true; }
+    if (C == 32 && G == 8 && D == 8) { *rc = launch_et_win_bf16<32, 8, 8, 4, 3>(a, st); return true; }
     return false;
 }
 

@@ -69,7 +69,14 @@ struct HeadArgs {
     float* attn; float* depth; float* conf; float* inv_min; float* inv_max; float* soft;
     int B, H, W;
     float split_itv;
+    int round_bf16;  // bf16 storage: the `prob` layer reads feat8 rounded to bf16 (its weights arrive bf16-valued)
 };
+
+// fp32 -> nearest-even bf16 value, as fp32 (finite inputs)
+__device__ __forceinline__ float bf16_value(float x) {
+    const unsigned u = __float_as_uint(x);
+    return __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u);
+}
 
 template <int D>
 __global__ void head_kernel(const HeadArgs a) {
@@ -90,7 +97,11 @@ __global__ void head_kernel(const HeadArgs a) {
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             const float4* f = reinterpret_cast<const float4*>(a.feat8 + (((long long)b * D + d) * plane + p) * 8);
-            const float4 f0 = __ldg(f), f1 = __ldg(f + 1);
+            float4 f0 = __ldg(f), f1 = __ldg(f + 1);
+            if (a.round_bf16) {
+                f0.x = bf16_value(f0.x); f0.y = bf16_value(f0.y); f0.z = bf16_value(f0.z); f0.w = bf16_value(f0.w);
+                f1.x = bf16_value(f1.x); f1.y = bf16_value(f1.y); f1.z = bf16_value(f1.z); f1.w = bf16_value(f1.w);
+            }
             float s = f0.x * w[0];
             s = fmaf(f0.y, w[1], s); s = fmaf(f0.z, w[2], s); s = fmaf(f0.w, w[3], s);
             s = fmaf(f1.x, w[4], s); s = fmaf(f1.y, w[5], s); s = fmaf(f1.z, w[6], s); s = fmaf(f1.w, w[7], s);
@@ -165,6 +176,25 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
     }
 }
 
+// fp32 -> bf16 (round to nearest even), 8 elements per thread: what a bf16 store of the feature pyramid's outputs applies
+__global__ void cast_bf16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n8, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    auto rn = [](float x) -> unsigned {
+        const unsigned u = __float_as_uint(x);
+        if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (u >> 16) | 0x40u;  // NaN stays NaN
+        return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+    };
+    if (i < n8) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+        uint4 o;
+        o.x = rn(a.x) | (rn(a.y) << 16); o.y = rn(a.z) | (rn(a.w) << 16);
+        o.z = rn(b.x) | (rn(b.y) << 16); o.w = rn(b.z) | (rn(b.w) << 16);
+        reinterpret_cast<uint4*>(out)[i] = o;
+    } else if (i == n8) {  // tail (n % 8 elements)
+        for (long long j = 8 * n8; j < n; ++j) out[j] = (uint16_t)rn(in[j]);
+    }
+}
+
 }  // namespace mvster
 
 using namespace mvster;
@@ -194,10 +224,18 @@ extern "C" int mvster_head_f32(const float* logits, const float* feat8, const fl
                                const float* hypo, float* attn, float* depth, float* conf,
                                float* inv_min, float* inv_max, float* soft_depth,
                                int B, int D, int H, int W, float split_itv, mvster_stream_t stream) {
+    return mvster_head_ex_f32(logits, feat8, prob_w, prob_b, hypo, attn, depth, conf, inv_min, inv_max, soft_depth, B, D, H, W, split_itv, 0, stream);
+}
+
+extern "C" int mvster_head_ex_f32(const float* logits, const float* feat8, const float* prob_w, const float* prob_b,
+                                  const float* hypo, float* attn, float* depth, float* conf,
+                                  float* inv_min, float* inv_max, float* soft_depth,
+                                  int B, int D, int H, int W, float split_itv, int flags, mvster_stream_t stream) {
     MVSTER_REQUIRE(hypo, "mvster_head_f32: hypo is null");
     MVSTER_REQUIRE(logits || (feat8 && prob_w && prob_b), "mvster_head_f32: need logits or (feat8, prob_w, prob_b)");
     MVSTER_REQUIRE(B > 0 && H > 0 && W > 0, "mvster_head_f32: bad shape");
-    HeadArgs a{logits, feat8, prob_w, prob_b, hypo, attn, depth, conf, inv_min, inv_max, soft_depth, B, H, W, split_itv};
+    HeadArgs a{logits, feat8, prob_w, prob_b, hypo, attn, depth, conf, inv_min, inv_max, soft_depth, B, H, W, split_itv,
+               (flags & MVSTER_HEAD_BF16_INPUT) ? 1 : 0};
     const long long n = (long long)B * H * W;
     cudaStream_t st = (cudaStream_t)stream;
     if (D == 4) head_kernel<4><<<ceil_div(n, 128), 128, 0, st>>>(a);
@@ -362,4 +400,12 @@ extern "C" int mvster_hypo_schedule_linear_f32(const float* depth, const float* 
     else if (D == 8) mvster::hypo_schedule_linear_kernel<8><<<mvster::ceil_div(n, 256), 256, 0, st>>>(depth, depth_values, n_dv, ratio, hypo, B, H, W);
     else MVSTER_REQUIRE(false, "mvster_hypo_schedule_linear_f32: unsupported D=%d (4 or 8)", D);
     return mvster::check_launch("hypo_schedule_linear_kernel");
+}
+
+extern "C" int mvster_cast_bf16(const float* in, void* out, long long n, mvster_stream_t stream) {
+    MVSTER_REQUIRE(in && out && n > 0, "mvster_cast_bf16: bad arguments");
+    MVSTER_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "mvster_cast_bf16: pointers must be 16-byte aligned");
+    const long long n8 = n / 8;
+    cast_bf16_kernel<<<ceil_div(n8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(in, reinterpret_cast<uint16_t*>(out), n8, n);
+    return check_launch("cast_bf16_kernel");
 }

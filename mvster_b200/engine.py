@@ -62,6 +62,36 @@ def check_supported(net) -> None:
         raise NotImplementedError("the CUDA inference path does not cover: " + ", ".join(bad))
 
 
+BF16_ET_CLASSES = ((64, 8, 8), (32, 8, 8), (16, 4, 4), (8, 4, 4))  # (C, G, D) the bf16 warp / ET kernels are instantiated for
+
+
+def bf16_storage(net) -> bool:
+    st = getattr(net, "storage", "fp32")
+    if st not in ("fp32", "bf16"):
+        raise ValueError(f"storage must be 'fp32' or 'bf16', got {st!r}")
+    return st == "bf16"
+
+
+def check_bf16_supported(net, shard) -> None:
+    bad = []
+    if net.reg_net != "reg2d":
+        bad.append(f"reg_net={net.reg_net!r} (reg2d)")
+    if not net.group_cor:
+        bad.append("group_cor=False")
+    if not net.stagenet.attn_fuse_d:
+        bad.append("attn_fuse_d=False")
+    if getattr(net, "fpn_backend", "native") != "native":
+        bad.append("fpn_backend != 'native'")
+    if shard is not None:
+        bad.append("view sharding (partial sums are fp32)")
+    for k in range(min(net.num_stage, 4)):
+        cls = (net.feature.out_channels[k], net.group_cor_dim[k], net.stage_splits[k])
+        if net.group_cor and cls not in BF16_ET_CLASSES:
+            bad.append(f"stage {k + 1} (C, G, D) = {cls}")
+    if bad:
+        raise NotImplementedError("storage='bf16' does not cover: " + ", ".join(bad))
+
+
 def check_inputs(net, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor) -> None:
     """Shape contract of ``MVS4net.forward`` (MVS4Net.py:60-77), checked before anything is launched; the reference
     fails on the same inputs with ATen shape errors deep inside the U-Nets."""
@@ -135,6 +165,8 @@ class InferenceEngine:
         # changed (and on every eager forward with MVSTER_RANGE_CHECK=always); a hit switches this engine to three bf16 terms
         self._range_checked = False
         self._overflow_flag: Optional[Tensor] = None
+        self._reg_state: Dict[str, Tensor] = {}    # CPU view of the regulariser's state: packed for storage='bf16' on first use
+        self._bf16_weights: Dict[int, Dict[str, Tensor]] = {}
 
     def _precision(self, net, which: str) -> str:
         """Arithmetic of the convolutions of ``which`` ("fpn" | "reg"): the module's setting, except that "2xfp16" becomes "3xbf16"
@@ -156,6 +188,7 @@ class InferenceEngine:
         self._range_checked = False
         state = module_state(net)
         sd = {k: v for k, v in state.items() if k.startswith("reg.")}
+        self._reg_state, self._bf16_weights = sd, {}
         self.plans = [StagePlan(k, net) for k in range(net.num_stage)]
         self.stage_weights = []
         fpn_sd = {k: v for k, v in state.items() if k.startswith("feature.")}
@@ -186,6 +219,8 @@ class InferenceEngine:
         check_inputs(net, imgs, proj_matrices, depth_values)
         B = imgs[0].shape[0]
         own = list(range(len(imgs))) if shard is None else [0] + shard.views
+        if bf16_storage(net):
+            check_bf16_supported(net, shard)
         self._native_feats = getattr(net, "fpn_backend", "torch") == "native"  # features in the pyramid's (interleaved) channel order
         try:
             if self._needs_range_check(net):
@@ -239,6 +274,8 @@ class InferenceEngine:
                     return self._forward_overlapped(net, x, B, len(own), proj_matrices, depth_values, npass, gen, shard)
                 pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen)
                 nhwc = [pyramid[f"stage{k + 1}"] for k in range(net.num_stage)]
+                if bf16_storage(net):  # the pyramid's outputs as they are stored: bf16
+                    nhwc = [capi.cast_bf16(t) for t in nhwc]
             else:
                 x = torch.cat([imgs[v] for v in own], 0).contiguous(memory_format=torch.channels_last)
                 pyramid = net.feature(x)  # {stage: [len(own)*B, C, h, w]}, channels-last strides
@@ -260,7 +297,7 @@ class InferenceEngine:
         key = (tuple(tuple(t.shape) for t in imgs), tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
                tuple(depth_values.shape), self.weights_version, self._precision(net, "reg"),
                getattr(net, "fpn_backend", "torch"), self._precision(net, "fpn"),
-               getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"),
+               getattr(net, "storage", "fp32"), getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"),
                None if shard is None else (shard.first_view, shard.count, shard.parts, id(shard.group)),
                int(getattr(net, "graph_slot", 0)))
         entry = self._graphs.get(key)
@@ -298,6 +335,8 @@ class InferenceEngine:
     # ------------------------------------------------------------------ the hot path
     def _aggregate(self, p: StagePlan, ref: Tensor, srcs: List[Tensor], proj: Tensor, hypo: Tensor, temp: float,
                    fuse_d: bool, shard, pose: Optional[Tensor] = None) -> Tensor:
+        if ref.dtype == torch.bfloat16:  # storage='bf16': bf16 features in, bf16 cost volume out
+            return capi.et_fuse_bf16(ref, srcs, capi.pose(proj) if pose is None else pose, hypo, p.G, temp, interleaved=self._interleaved(p.k, ref))
         kw = dict(group_cor=p.group_cor, fuse_d=fuse_d, interleaved=self._interleaved(p.k, ref))
         if shard is None:
             return capi.et_fuse(ref, srcs, capi.pose(proj) if pose is None else pose, hypo, p.G, temp, **kw)
@@ -318,6 +357,10 @@ class InferenceEngine:
 
     def _regularise(self, net, p: StagePlan, wts: Dict[str, Tensor], cost: Tensor, hypo: Tensor) -> Dict[str, Tensor]:
         inverse = bool(net.inverse_depth)
+        if cost.dtype == torch.bfloat16:  # storage='bf16': one-term bf16 operands, BatchNorm scale in fp32 (mvster_reg2d_bf16)
+            q = self._bf16_stage_weights(p)
+            feat8 = capi.reg2d_bf16(q["blob_q"], q["tc3_blob"], q["scales"], cost)
+            return capi.head(hypo, p.split_itv, feat8=feat8, prob_w=q["prob_w"], prob_b=q["prob_b"], inverse=inverse, bf16_input=True)
         if net.reg_net == "reg3d":
             logits = capi.reg3d(wts["blob"], cost, p.down)
             return capi.head(hypo, p.split_itv, logits=logits, inverse=inverse)
@@ -331,6 +374,13 @@ class InferenceEngine:
         else:                   # 3x3x3 layers on tcgen05: "3xtf32" (fp32-faithful) or "tf32"
             feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc2_blob"], npass=3 if prec == "3xtf32" else 1, kernel_gen=2)
         return capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=inverse)
+
+    def _bf16_stage_weights(self, p: StagePlan) -> Dict[str, Tensor]:
+        got = self._bf16_weights.get(p.k)
+        if got is None:
+            packed = packing.pack_reg2d_bf16(self._reg_state, f"reg.{p.k}", capi.reg2d_layer_table(p.G))
+            got = self._bf16_weights[p.k] = {k: v.to(self.device) for k, v in packed.items()}
+        return got
 
     def _run_stage(self, net, p: StagePlan, wts: Dict[str, Tensor], feats_k: List[Tensor], proj_matrices: Dict[str, Tensor],
                    dv: Tensor, prev: Optional[Dict], temp: float, shard=None, pose: Optional[Tensor] = None,
@@ -366,6 +416,8 @@ class InferenceEngine:
     def _mono_feat(self, k: int, ref: Tensor) -> Tensor:
         """The reference view's stage-k features as [B,C,H,W] in the NATURAL channel order (an output only).  Where the engine keeps
         them group-interleaved this is one gather: natural[..., c] = stored[..., inverse[c]]."""
+        if ref.dtype != torch.float32:  # storage='bf16': the stored (rounded) features, returned as fp32 like every other output
+            ref = ref.float()
         if self._interleaved(k, ref):
             return ref.index_select(3, self._inverse_perm(k)).permute(0, 3, 1, 2)
         return ref.permute(0, 3, 1, 2)
@@ -413,7 +465,12 @@ class InferenceEngine:
         reserve, side_sms = int(os.environ.get("MVSTER_MAIN_RESERVE", "48")), int(os.environ.get("MVSTER_SIDE_SMS", "0"))
         events = [torch.cuda.Event() for _ in range(4)]
 
+        stored: List[Optional[Tensor]] = [None] * 4
+        as_bf16 = bf16_storage(net)
+
         def on_level(k, t):
+            if as_bf16:  # storage='bf16': the level as it is stored, cast on the main stream before the cascade stage may start
+                stored[k] = capi.cast_bf16(t)
             events[k].record(main)
             if k == 0 and reserve > 0:
                 lib.mvster_set_sm_budget(self._sm_count - reserve)
@@ -433,7 +490,8 @@ class InferenceEngine:
                 side.wait_event(fork)  # the inputs were produced on (or before) the main stream
                 poses = [capi.pose(pr, **pose_kw) for pr in projs]
             pyramid = fpn_engine.run_fpn(self.fpn_weights, x, npass, gen=gen, on_level=on_level)
-            feats = [[pyramid[f"stage{k + 1}"][i * B:(i + 1) * B] for i in range(n_own)] for k in range(4)]
+            levels = stored if as_bf16 else [pyramid[f"stage{k + 1}"] for k in range(4)]
+            feats = [[levels[k][i * B:(i + 1) * B] for i in range(n_own)] for k in range(4)]
             # outputs that only depend on the pyramid go out here, on the main stream, in the gap between the pyramid's last launch
             # and the join with the side stream (at the end of the forward they were 37 us of serialised tail)
             mono = [self._mono_feat(k, feats[k][0]) if net.mono else None for k in range(4)]

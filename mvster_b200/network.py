@@ -263,6 +263,12 @@ class MVS4net(nn.Module):
         #   "3xtf32" the 3x3x3 layers on the staged-tile TF32 kernel (conv_tc2.cu), error-compensated TF32 (<= 1.6e-5 of max)
         #   "tf32"   ... single TF32 pass (reduced precision, opt-in)
         self.reg_precision = os.environ.get("MVSTER_REG_PRECISION", "2xfp16")
+        # storage type of the hot path's tensors at inference: "fp32" (the reference's), or "bf16" (BASELINE configs[2]; the
+        # reference has no such path): the pyramid's output features and the cost volume are bf16 in HBM and the regulariser /
+        # head convolutions take bf16 operands (one-term tcgen05 arithmetic, BatchNorm scale in fp32); geometry, correlations,
+        # softmax and accumulation stay fp32; the feature pyramid itself computes with fpn_precision.  reg2d + group correlation
+        # + attn_fuse_d only (the shipped configuration); no view sharding.
+        self.storage = os.environ.get("MVSTER_STORAGE", "fp32")
         # feature pyramid at inference: "native" (libmvster_b200 kernels, fpn_engine.py; fpn_precision as above, "3xbf16" puts
         # every layer after the 3-channel stem on the tensor cores) or "torch" (the module's own convs through cuDNN, channels-last)
         self.fpn_backend = os.environ.get("MVSTER_FPN", "native")

@@ -91,7 +91,9 @@ def _split_terms(wt: Tensor, split: int):
         return [t.view(torch.int16) for t in bf16_split3(wt)]
     if split == 2:
         return [t.view(torch.int16) for t in fp16_split2(wt)]  # third row block of the slab stays zero (unused)
-    raise ValueError(f"split must be 2 (fp16 terms) or 3 (bf16 terms), got {split}")
+    if split == 1:
+        return [wt.to(torch.bfloat16).view(torch.int16)]       # bf16-storage arithmetic: one term, rows 2 and 3 unused
+    raise ValueError(f"split must be 1 (one bf16 term), 2 (fp16 terms) or 3 (bf16 terms), got {split}")
 
 
 def pack_tc3_weights(w: Tensor, kd: int, k: int, stride: int = 1, split: int = 3) -> Tensor:
@@ -222,4 +224,40 @@ def pack_reg2d(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, 
     return {"blob": blob, "tc2_blob": torch.cat(tc2), "tc3_blob": torch.cat(tc3[3]),
             "tc3h_blob": torch.cat(tc3[2]),
             "prob_w": sd[prefix + ".prob.weight"].detach().cpu().reshape(-1).float().contiguous(),
+            "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}
+
+
+def bf16_round(t: Tensor) -> Tensor:
+    """fp32 values rounded to the nearest bf16 (ties to even), kept as fp32: what a bf16 store holds."""
+    return t.float().to(torch.bfloat16).float()
+
+
+def pack_reg2d_bf16(sd: Mapping[str, Tensor], prefix: str, layer_table) -> Dict[str, Tensor]:
+    """bf16-storage arithmetic of one reg2d (mvster_reg2d_bf16): the convolution weights are rounded to bf16 UNFOLDED - the
+    BatchNorm factor stays an fp32 per-channel scale applied to the accumulator, the shift goes to the bias slot - so that a
+    layer computes BN(conv(bf16(x), bf16(w))) as the bf16 configuration is defined (oracle.storage).
+    Returns {'blob_q', 'scales' [288], 'tc3_blob' (split = 1), 'prob_w' (bf16 values), 'prob_b'} on the CPU."""
+    total = layer_table[-1]["b_off"] + layer_table[-1]["cout"]
+    blob = torch.zeros(total, dtype=torch.float32)
+    scales, tc3 = [], []
+    one = lambda n: torch.ones(n, dtype=torch.float64)
+    for name, L in zip(REG2D_ORDER, layer_table):
+        p = f"{prefix}.{name}"
+        if L["transposed"]:
+            s, t = bn_scale_shift(sd, p + ".1")
+            w, _ = fold_deconv3d(bf16_round(sd[p + ".0.weight"].detach().cpu()), one(L["cout"]), t.cpu())
+        else:
+            s, t = bn_scale_shift(sd, p + ".bn")
+            w, _ = fold_conv3d(bf16_round(sd[p + ".conv.weight"].detach().cpu()), one(L["cout"]), t.cpu())
+        blob[L["w_off"]:L["w_off"] + w.numel()] = w.reshape(-1)
+        blob[L["b_off"]:L["b_off"] + L["cout"]] = t.float()
+        scales.append(s.float().cpu())
+        if not L["transposed"]:
+            tc3.append(pack_tc3_weights(w, L["kd"], 3, L["stride"], 1))
+        elif 4 * L["cout"] <= 64:
+            tc3.append(pack_tc3_deconv_weights(w, -1, 1))
+        else:
+            tc3 += [pack_tc3_deconv_weights(w, 0, 1), pack_tc3_deconv_weights(w, 1, 1)]
+    return {"blob_q": blob, "scales": torch.cat(scales).contiguous(), "tc3_blob": torch.cat(tc3),
+            "prob_w": bf16_round(sd[prefix + ".prob.weight"].detach().cpu().reshape(-1)).contiguous(),
             "prob_b": sd[prefix + ".prob.bias"].detach().cpu().reshape(-1).float().contiguous()}

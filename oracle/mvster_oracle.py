@@ -40,23 +40,29 @@ BN_EPS = 1e-5  # torch.nn.BatchNorm{2,3}d default, used by every BN in the refer
 # defined as the fp32 reference with bf16 ROUNDING at the points where a bf16 build stores data: the FPN outputs, the cost
 # volume, and every convolution's operands (activations and weights; accumulation, BN, geometry and softmax stay fp32).
 # PARITY UNPINNED for this configuration: there is no reference output to pin it to; the fp32 path it is built on is pinned.
+# ``fpn_internal=False`` is the variant the CUDA path implements (mvster_b200 storage="bf16"): the rounding applies to what the
+# named hot path stores and reads - the pyramid's OUTPUT features, the cost volume, the regulariser's and the head's convolution
+# operands - while the feature pyramid itself (outside the named path) computes in fp32.
 # --------------------------------------------------------------------------
 _STORAGE = None
+_STORAGE_FPN_INTERNAL = True
 
 
 class storage:
     """``with storage(torch.bfloat16): ...`` - emulate that storage type in every function below (None = exact fp32)."""
 
-    def __init__(self, dtype):
+    def __init__(self, dtype, fpn_internal: bool = True):
         self.dtype = dtype
+        self.fpn_internal = fpn_internal
 
     def __enter__(self):
-        global _STORAGE
-        self.prev, _STORAGE = _STORAGE, self.dtype
+        global _STORAGE, _STORAGE_FPN_INTERNAL
+        self.prev, _STORAGE = (_STORAGE, _STORAGE_FPN_INTERNAL), self.dtype
+        _STORAGE_FPN_INTERNAL = self.fpn_internal
 
     def __exit__(self, *exc):
-        global _STORAGE
-        _STORAGE = self.prev
+        global _STORAGE, _STORAGE_FPN_INTERNAL
+        _STORAGE, _STORAGE_FPN_INTERNAL = self.prev
 
 
 def _q(x: Tensor) -> Tensor:
@@ -98,6 +104,12 @@ def _cbr2(x: Tensor, sd: State, p: str, stride: int, pad: int, relu: bool = True
 def fpn4_features(sd: State, img: Tensor, p: str = "feature") -> Dict[str, Tensor]:
     """mvs4net_utils.py:472-502.  img [B,3,H,W] -> stage1..4 features with
     64/32/16/8 channels at H/8 .. H."""
+    if _STORAGE is not None and not _STORAGE_FPN_INTERNAL:  # fp32 pyramid, reduced-precision storage of its outputs only
+        dtype = _STORAGE
+        with storage(None):
+            full = fpn4_features(sd, img, p)
+        with storage(dtype, False):
+            return {k: _q(v) for k, v in full.items()}
     c0 = _cbr2(_cbr2(img, sd, p + ".conv0.0", 1, 1), sd, p + ".conv0.1", 1, 1)
     c1 = _cbr2(c0, sd, p + ".conv1.0", 2, 2)
     c1 = _cbr2(_cbr2(c1, sd, p + ".conv1.1", 1, 1), sd, p + ".conv1.2", 1, 1)
@@ -349,10 +361,12 @@ def stage_forward(sd: State, cfg: dict, k: int, feats: List[Tensor], cams: Tenso
 
 
 def cascade_forward(sd: State, cfg: dict, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor],
-                    depth_values: Tensor, features: Optional[List[Dict[str, Tensor]]] = None, storage_dtype=None) -> Dict:
+                    depth_values: Tensor, features: Optional[List[Dict[str, Tensor]]] = None, storage_dtype=None,
+                    storage_fpn_internal: bool = True) -> Dict:
     """MVS4net.forward in eval mode, MVS4Net.py:60-111.  ``storage_dtype=torch.bfloat16`` evaluates the bf16-storage
-    configuration (see ``storage`` above); None is the reference's fp32."""
-    with torch.no_grad(), storage(storage_dtype):
+    configuration (see ``storage`` above; ``storage_fpn_internal=False``: the variant the CUDA path implements); None is the
+    reference's fp32."""
+    with torch.no_grad(), storage(storage_dtype, storage_fpn_internal):
         if features is None:
             features = [fpn4_features(sd, im) for im in imgs]
         outputs: Dict = {}

@@ -42,8 +42,8 @@ def load():
     return EmuWithHostLogic(lib, real)
 
 
-def cpu_chk(t, name, shape=None):
-    assert isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.is_contiguous() and not t.is_cuda, name
+def cpu_chk(t, name, shape=None, dtype=torch.float32):
+    assert isinstance(t, torch.Tensor) and t.dtype == dtype and t.is_contiguous() and not t.is_cuda, name
     assert shape is None or tuple(t.shape) == tuple(shape), (name, tuple(t.shape), tuple(shape))
     return t
 

@@ -4,8 +4,8 @@ trap or a barrier deadlock in a tensor-core kernel cannot take the rest of the s
 
     python tests/tc_conv_check.py {v1|v2} CIN COUT KD B D H W NPASS [skip] [norelu]
     python tests/tc_conv_check.py {reg2d|reg2dv2} G B D H W NPASS
-    python tests/tc_conv_check.py v3 CIN COUT KD K STRIDE B D H W [skip] [norelu] [h16]     (h16: two-fp16-term arithmetic)
-    python tests/tc_conv_check.py d3 CIN COUT B D H W [skip] [h16]
+    python tests/tc_conv_check.py v3 CIN COUT KD K STRIDE B D H W [skip] [norelu] [h16 | b16]   (h16: two-fp16-term arithmetic;
+    python tests/tc_conv_check.py d3 CIN COUT B D H W [skip] [h16 | b16]                         b16: one bf16 term + per-channel scale)
 """
 import json
 import sys
@@ -53,6 +53,10 @@ def reg2d_main(gen):
                       "finite": bool(torch.isfinite(got).all()), "us_tc": t_tc, "us_simt": t_simt}))
 
 
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
 def v3_main():
     """generation 3 (persistent, 3 x bf16): v3 CIN COUT KD K STRIDE B D H W [skip] [norelu]; truth = fp64 torch conv."""
     import torch.nn.functional as F
@@ -65,16 +69,24 @@ def v3_main():
     bias = torch.from_numpy(rng.randn(cout).astype(np.float32) * 0.1).to(dev)
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     skip = torch.from_numpy(rng.randn(B, D, Ho, Wo, cout).astype(np.float32)).to(dev) if use_skip else None
+    b16 = "b16" in sys.argv  # bf16-storage arithmetic: y = relu(scale * conv(bf16(x), bf16(w)) + bias) + skip, truth in fp64
+    ch_scale = torch.from_numpy(rng.uniform(0.5, 2.0, cout).astype(np.float32)).to(dev) if b16 else None
+    if b16:
+        w = bf16_round(w)
     w5 = w.to(dev).double().reshape(kd, k, k, cin, cout).permute(4, 3, 0, 1, 2)
-    want = F.conv3d(x.double().permute(0, 4, 1, 2, 3), w5, bias.double(), stride=(1, stride, stride), padding=(kd // 2, k // 2, k // 2))
+    xin = bf16_round(x) if b16 else x
+    want = F.conv3d(xin.double().permute(0, 4, 1, 2, 3), w5, None, stride=(1, stride, stride), padding=(kd // 2, k // 2, k // 2))
     want = want.permute(0, 2, 3, 4, 1)
+    if b16:
+        want = want * ch_scale.double()
+    want = want + bias.double()
     if relu:
         want = want.clamp_min(0)
     if skip is not None:
         want = want + skip.double()
-    split = 2 if "h16" in sys.argv else 3  # h16: two fp16 terms per operand (MVSTER_TC3_FP16X2)
+    split = 1 if b16 else 2 if "h16" in sys.argv else 3  # h16: two fp16 terms per operand (MVSTER_TC3_FP16X2)
     wp = packing.pack_tc3_weights(w, kd, k, stride, split).to(dev)
-    run = lambda: capi.conv_tc3(x, wp, bias, cout, kd, k, stride, relu, skip=skip, split=split)
+    run = lambda: capi.conv_tc3(x, wp, bias, cout, kd, k, stride, relu, skip=skip, split=split, scale=ch_scale)
     got = run()
     torch.cuda.synchronize()
     err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()
@@ -95,22 +107,30 @@ def d3_main():
     w = torch.from_numpy((rng.randn(9, cin, cout) / np.sqrt(2.25 * cin)).astype(np.float32))
     bias = torch.from_numpy(rng.randn(cout).astype(np.float32) * 0.1).to(dev)
     skip = torch.from_numpy(rng.randn(B, D, 2 * H, 2 * W, cout).astype(np.float32)).to(dev) if use_skip else None
+    b16 = "b16" in sys.argv
+    ch_scale = torch.from_numpy(rng.uniform(0.5, 2.0, cout).astype(np.float32)).to(dev) if b16 else None
+    if b16:
+        w = bf16_round(w)
     wt = w.to(dev).double().reshape(1, 3, 3, cin, cout).permute(3, 4, 0, 1, 2)  # [Cin][Cout][1][3][3]
-    want = F.conv_transpose3d(x.double().permute(0, 4, 1, 2, 3), wt, bias.double(), stride=(1, 2, 2), padding=(0, 1, 1), output_padding=(0, 1, 1))
-    want = want.permute(0, 2, 3, 4, 1).clamp_min(0)
+    xin = bf16_round(x) if b16 else x
+    want = F.conv_transpose3d(xin.double().permute(0, 4, 1, 2, 3), wt, None, stride=(1, 2, 2), padding=(0, 1, 1), output_padding=(0, 1, 1))
+    want = want.permute(0, 2, 3, 4, 1)
+    if b16:
+        want = want * ch_scale.double()
+    want = (want + bias.double()).clamp_min(0)
     if skip is not None:
         want = want + skip.double()
-    split = 2 if "h16" in sys.argv else 3
+    split = 1 if b16 else 2 if "h16" in sys.argv else 3
     if 4 * cout <= 64:
         wp = packing.pack_tc3_deconv_weights(w, -1, split).to(dev)
-        run = lambda: capi.deconv_tc3(x, wp, bias, cout, -1, True, skip=skip, split=split)
+        run = lambda: capi.deconv_tc3(x, wp, bias, cout, -1, True, skip=skip, split=split, scale=ch_scale)
     else:
         wp0, wp1 = packing.pack_tc3_deconv_weights(w, 0, split).to(dev), packing.pack_tc3_deconv_weights(w, 1, split).to(dev)
         buf = torch.full((B, D, 2 * H, 2 * W, cout), float("nan"), device=dev)
 
         def run():
-            capi.deconv_tc3(x, wp0, bias, cout, 0, True, skip=skip, out=buf, split=split)
-            return capi.deconv_tc3(x, wp1, bias, cout, 1, True, skip=skip, out=buf, split=split)
+            capi.deconv_tc3(x, wp0, bias, cout, 0, True, skip=skip, out=buf, split=split, scale=ch_scale)
+            return capi.deconv_tc3(x, wp1, bias, cout, 1, True, skip=skip, out=buf, split=split, scale=ch_scale)
     got = run()
     torch.cuda.synchronize()
     err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()
