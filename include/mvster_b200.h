@@ -183,6 +183,9 @@ int mvster_conv3d_tc2_f32(const float* x, const float* w_packed, const float* bi
  * entry points multiply the accumulator by a per-output-channel fp32 factor before the bias (the BatchNorm scale, which
  * therefore stays out of the bf16 weights): y = [relu](scale * conv(bf16(x), w) + bias) [+ skip].  scale may be NULL. */
 #define MVSTER_TC3_BF16X1 512
+/* with MVSTER_TC3_BF16X1: round the stored output (after ReLU and the skip sum) to bf16 values - the layer's output as a bf16
+ * build stores it, kept in its fp32 container */
+#define MVSTER_TC3_ROUND_OUT 2048
 /* The generation-3 kernel is persistent (one CTA per SM for the whole launch): the grid size is how much of the GPU a launch
  * claims.  mvster_set_sm_budget(n) caps the grid of the mvster_*_tc3_* launches that follow FROM THE CALLING THREAD (thread-local
  * like the error string; 0 = all SMs, the default): replicas driven by different host threads (nn.DataParallel) do not see each
@@ -249,6 +252,18 @@ int mvster_reg2d_tc3_ex_f32(const float* blob, const void* tc3_blob, const float
 int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* workspace,
                          int B, int G, int D, int H, int W, mvster_stream_t stream);
 
+/* Packed operands (bf16 storage): the same two layers with activations that LIVE in HBM as bf16 in the operand's own order,
+ * octet-planar [B*D][C/8][H][W][8 channels] ("PB16"; for C = 8 this is plain NHWC bf16): a TMA box lands a stage's halo tile
+ * directly in the MMA operand ring - no fp32 staging, no conversion pass, half the activation bytes.  x and skip (may be NULL;
+ * shape of the output) are PB16; y is PB16 with MVSTER_TC3_OUT_PB16 in `flags` (rounded to bf16 after ReLU and the skip sum),
+ * else fp32 NDHWC.  flags bit 0 = ReLU.  w_packed: one bf16 term (packing.pack_tc3_weights(split=1) /
+ * pack_tc3_deconv_weights(split=1)); scale as in the _scaled entry points.  Cin in {8,16,32,64}, Cout in {8,16,32,64}. */
+#define MVSTER_TC3_OUT_PB16 1024
+int mvster_conv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
+                         int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int flags, mvster_stream_t stream);
+int mvster_deconv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
+                           int B, int D, int H, int W, int Cin, int Cout, int rows, int flags, mvster_stream_t stream);
+
 /* bf16-storage reg2d (BASELINE configs[2]): cost_bf16 [B][D][H][W][G] as bf16 (what mvster_et_fuse_bf16 writes) -> feat8 fp32.
  * Every convolution computes conv(bf16(x), bf16(w)) with fp32 accumulation, then the BatchNorm scale and shift in fp32, ReLU and
  * the skip sum in fp32 - i.e. conv -> BN -> ReLU of mvs4net_utils.py:116-123 with bf16 rounding at the convolution's operands
@@ -257,8 +272,12 @@ int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* c
  * `tc3_blob`: the slab streams of conv0..conv11 in the order of mvster_reg2d_tc3_ex_f32 packed with split = 1.  conv0 runs on
  * the CUDA cores (bf16 loads, fp32 FMA), conv1..conv11 on the tcgen05 kernel with MVSTER_TC3_BF16X1. */
 #define MVSTER_REG2D_SCALE_FLOATS 288
+/* flags: MVSTER_REG2D_BF16_PACKED keeps the activations between the layers as packed bf16 operands (mvster_conv_tc3_pb16 /
+ * mvster_deconv_tc3_pb16: no conversion pass, half the bytes); 0 keeps them as bf16-rounded values in fp32 containers
+ * (mvster_conv_tc3_scaled_f32 with MVSTER_TC3_BF16X1 | MVSTER_TC3_ROUND_OUT).  Same arithmetic either way. */
+#define MVSTER_REG2D_BF16_PACKED 1
 int mvster_reg2d_bf16(const float* blob_q, const void* tc3_blob, const float* scales, const void* cost_bf16, float* feat8,
-                      float* workspace, int B, int G, int D, int H, int W, mvster_stream_t stream);
+                      float* workspace, int B, int G, int D, int H, int W, int flags, mvster_stream_t stream);
 
 /* reg3d U-Net (mvs4net_utils.py:914-965; optional `--reg_mode reg3d`): 3x3x3 kernels, stride 2 along D too,
  * down_size in {1,2,3} (MVS4Net.py:48), prob = 3x3x3 conv 8->1 without bias.  cost [B][D][H][W][G] ->

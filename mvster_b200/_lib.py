@@ -61,7 +61,9 @@ SIGNATURES = {
     "mvster_conv_tc3_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_conv_tc3_scaled_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_deconv_tc3_scaled_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "mvster_reg2d_bf16": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "mvster_reg2d_bf16": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_conv_tc3_pb16": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "mvster_deconv_tc3_pb16": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_pointwise_tc3_blocks_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.c_longlong, _p]),
     "mvster_pointwise_tc3_blocks_ex_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, C.c_longlong, _i, _p]),
     "mvster_conv2d_nhwc_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -298,10 +298,10 @@ TC3_BF16X1 = 512  # MVSTER_TC3_BF16X1: one bf16 term (split=1): the bf16-storage
 REG2D_SCALE_FLOATS = 288
 
 
-def _tc3_flags(relu: bool, split: int) -> int:
+def _tc3_flags(relu: bool, split: int, round_out: bool = False) -> int:
     if split not in (1, 2, 3):
         raise ValueError(f"split must be 1 (one bf16 term), 2 (two fp16 terms) or 3 (three bf16 terms), got {split}")
-    return int(relu) | {1: TC3_BF16X1, 2: TC3_FP16X2, 3: 0}[split]
+    return int(relu) | {1: TC3_BF16X1, 2: TC3_FP16X2, 3: 0}[split] | (2048 if round_out and split == 1 else 0)
 
 
 def conv_tc3(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, k: int, stride: int = 1, relu: bool = True,
@@ -448,10 +448,80 @@ def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: O
     return out
 
 
+TC3_OUT_PB16 = 1024   # MVSTER_TC3_OUT_PB16
+TC3_ROUND_OUT = 2048  # MVSTER_TC3_ROUND_OUT
+
+
+def to_pb16(x: Tensor) -> Tensor:
+    """[P..., H, W, C] fp32 / bf16 (channels last) -> the packed-operand layout of the bf16 tensor-core layers: octet-planar
+    bf16 [P..., C/8, H, W, 8] (round to nearest even).  Host-side helper for tests and tools: inside the path the producing
+    kernels write this layout themselves."""
+    *lead, H, W, Cc = x.shape
+    return x.to(torch.bfloat16).reshape(*lead, H, W, Cc // 8, 8).movedim(-2, -4).contiguous()
+
+
+def from_pb16(x: Tensor) -> Tensor:
+    """Inverse of ``to_pb16``: [P..., C/8, H, W, 8] bf16 -> [P..., H, W, C] fp32."""
+    *lead, n8, H, W, _ = x.shape
+    return x.float().movedim(-4, -2).reshape(*lead, H, W, n8 * 8).contiguous()
+
+
+def conv_tc3_pb16(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, k: int, stride: int = 1, relu: bool = True,
+                  skip: Optional[Tensor] = None, scale: Optional[Tensor] = None, out_pb16: bool = True) -> Tensor:
+    """Packed-operand tcgen05 conv (mvster_conv_tc3_pb16): x [B,D,Cin/8,H,W,8] bf16 -> [B,D,cout/8,Ho,Wo,8] bf16 (out_pb16) or
+    [B,D,Ho,Wo,cout] fp32; skip in the packed layout of the output; w_packed = packing.pack_tc3_weights(split=1)."""
+    _chk(x, "x", dtype=torch.bfloat16)
+    _chk(w_packed, "w_packed")
+    B, D, n8, H, W, _ = x.shape
+    Cin = 8 * n8
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out_pb16:
+        y = torch.empty((B, D, cout // 8, Ho, Wo, 8), device=x.device, dtype=torch.bfloat16)
+    else:
+        y = torch.empty((B, D, Ho, Wo, cout), device=x.device, dtype=torch.float32)
+    if skip is not None:
+        _chk(skip, "skip", (B, D, cout // 8, Ho, Wo, 8), torch.bfloat16)
+    for t, n in ((bias, "bias"), (scale, "scale")):
+        if t is not None:
+            _chk(t, n, (cout,))
+    lib = _lib.load()
+    want = lib.mvster_conv_tc3_packed_bytes(Cin, cout, kd, k, stride)
+    if want == 0 or w_packed.numel() * 4 != want:
+        raise ValueError(f"conv_tc3_pb16: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
+    _lib.check(lib.mvster_conv_tc3_pb16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
+                                        kd, k, stride, int(relu) | (TC3_OUT_PB16 if out_pb16 else 0), _stream()), "mvster_conv_tc3_pb16")
+    return y
+
+
+def deconv_tc3_pb16(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, rows: int = -1, relu: bool = True,
+                    skip: Optional[Tensor] = None, scale: Optional[Tensor] = None, out_pb16: bool = True, out: Optional[Tensor] = None) -> Tensor:
+    """Packed-operand transposed conv (mvster_deconv_tc3_pb16): x [B,D,Cin/8,H,W,8] bf16 -> [B,D,cout/8,2H,2W,8] bf16 or
+    [B,D,2H,2W,cout] fp32; rows as in ``deconv_tc3`` (pass ``out`` to the second call)."""
+    _chk(x, "x", dtype=torch.bfloat16)
+    _chk(w_packed, "w_packed")
+    B, D, n8, H, W, _ = x.shape
+    Cin = 8 * n8
+    shape, dt = ((B, D, cout // 8, 2 * H, 2 * W, 8), torch.bfloat16) if out_pb16 else ((B, D, 2 * H, 2 * W, cout), torch.float32)
+    y = torch.empty(shape, device=x.device, dtype=dt) if out is None else _chk(out, "out", shape, dt)
+    if skip is not None:
+        _chk(skip, "skip", (B, D, cout // 8, 2 * H, 2 * W, 8), torch.bfloat16)
+    for t, n in ((bias, "bias"), (scale, "scale")):
+        if t is not None:
+            _chk(t, n, (cout,))
+    lib = _lib.load()
+    want = lib.mvster_deconv_tc3_packed_bytes(Cin, cout, rows)
+    if want == 0 or w_packed.numel() * 4 != want:
+        raise ValueError(f"deconv_tc3_pb16: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
+    _lib.check(lib.mvster_deconv_tc3_pb16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout, rows,
+                                          int(relu) | (TC3_OUT_PB16 if out_pb16 else 0), _stream()), "mvster_deconv_tc3_pb16")
+    return y
+
+
 def reg2d_bf16(blob_q: Tensor, tc3_blob: Tensor, scales: Tensor, cost: Tensor, workspace: Optional[Tensor] = None,
-               out: Optional[Tensor] = None) -> Tensor:
+               out: Optional[Tensor] = None, packed: bool = True) -> Tensor:
     """bf16-storage reg2d (mvster_reg2d_bf16): cost [B,D,H,W,G] torch.bfloat16 -> feat8 [B,D,H,W,8] fp32; the three weight
-    tensors come from packing.pack_reg2d_bf16."""
+    tensors come from packing.pack_reg2d_bf16.  ``packed``: activations between the layers as packed bf16 operands
+    (mvster_conv_tc3_pb16) instead of bf16-rounded values in fp32 containers - same arithmetic."""
     _chk(cost, "cost", dtype=torch.bfloat16)
     B, D, H, W, G = cost.shape
     _chk(blob_q, "blob_q", (reg2d_blob_floats(G),))
@@ -464,7 +534,7 @@ def reg2d_bf16(blob_q: Tensor, tc3_blob: Tensor, scales: Tensor, cost: Tensor, w
         raise ValueError(f"workspace too small: {workspace.numel()} < {need} floats")
     out = torch.empty((B, D, H, W, 8), device=cost.device, dtype=torch.float32) if out is None else _chk(out, "feat8", (B, D, H, W, 8))
     _lib.check(_lib.load().mvster_reg2d_bf16(_ptr(blob_q), _ptr(tc3_blob), _ptr(scales), _ptr(cost), _ptr(out), _ptr(workspace),
-                                             B, G, D, H, W, _stream()), "mvster_reg2d_bf16")
+                                             B, G, D, H, W, 1 if packed else 0, _stream()), "mvster_reg2d_bf16")
     return out
 
 

@@ -36,7 +36,7 @@ int conv_px2(const float* x, const float* w, const float* bias, const float* ski
              int B, int Di, int Hi, int Wi, int Cin, int Cout, int kd, int k, int sd, int s, int relu, cudaStream_t st);
 
 // conv_simt_px2.cu: conv0 (G -> 8, 3x3) of the bf16-storage regulariser; -100 = shape not covered
-int conv0_bf16(const void* x, const float* w, const float* scale, const float* bias, float* y, long long NP, int H, int W, int Cin,
+int conv0_bf16(const void* x, const float* w, const float* scale, const float* bias, void* y, int out_bf16, long long NP, int H, int W, int Cin,
                cudaStream_t st);
 
 }  // namespace mvster

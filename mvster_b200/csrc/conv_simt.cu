@@ -331,7 +331,7 @@ extern "C" int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, con
 }
 
 extern "C" int mvster_reg2d_bf16(const float* blob_q, const void* tc3_blob, const float* scales, const void* cost_bf16, float* feat8,
-                                 float* ws, int B, int G, int D, int H, int W, mvster_stream_t stream) {
+                                 float* ws, int B, int G, int D, int H, int W, int flags, mvster_stream_t stream) {
     MVSTER_REQUIRE(blob_q && tc3_blob && scales && cost_bf16 && feat8 && ws, "mvster_reg2d_bf16: null pointer");
     MVSTER_REQUIRE(G == 4 || G == 8, "mvster_reg2d_bf16: unsupported G=%d (4 or 8)", G);
     MVSTER_REQUIRE(H % 8 == 0 && W % 8 == 0, "mvster_reg2d_bf16: H,W must be multiples of 8 (got %dx%d)", H, W);
@@ -339,6 +339,7 @@ extern "C" int mvster_reg2d_bf16(const float* blob_q, const void* tc3_blob, cons
     Layer L[MVSTER_REG2D_LAYERS];
     reg2d_layers(G, L);
     const size_t N = (size_t)B * D * H * W;
+    // same workspace map as the fp32 network (offsets in floats); packed bf16 activations use the first half of each slot
     float* c0 = ws;           float* c1 = c0 + 8 * N;  float* c2 = c1 + 4 * N;  float* c3 = c2 + 4 * N;
     float* c4 = c3 + 2 * N;   float* c5 = c4 + 2 * N;  float* c6 = c5 + N;      float* u7 = c6 + N;
     float* u9 = u7 + 2 * N;
@@ -346,26 +347,41 @@ extern "C" int mvster_reg2d_bf16(const float* blob_q, const void* tc3_blob, cons
     float* out[MVSTER_REG2D_LAYERS] = {c0, c1, c2, c3, c4, c5, c6, u7, u9, feat8};
     const float* skip[MVSTER_REG2D_LAYERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c4, c2, c0};
     const int div[MVSTER_REG2D_LAYERS] = {1, 1, 2, 2, 4, 4, 8, 8, 4, 2};  // input resolution divisor
-    const int relu1 = 1 | MVSTER_TC3_BF16X1;
+    const bool packed = flags & MVSTER_REG2D_BF16_PACKED;
     const float* sc = scales;
     for (int i = 0; i < MVSTER_REG2D_LAYERS; sc += L[i].cout, ++i) {
         int64_t info[8];
         mvster_reg2d_layer_info(G, i, info);
         const uint8_t* wl = (const uint8_t*)tc3_blob + tc3_layer_offset(L, i);
+        const float* bias = blob_q + info[6];
+        const bool last = i == MVSTER_REG2D_LAYERS - 1;  // conv11: its sum with conv0 stays fp32 (the head's `prob` rounds its own operand)
+        const int h = H / div[i], w = W / div[i];
         int rc;
         if (i == 0) {  // G -> 8 at full resolution: CUDA cores (K and N would be mostly padding on the tensor core)
-            rc = conv0_bf16(cost_bf16, blob_q + info[5], sc, blob_q + info[6], c0, (long long)B * D, H, W, G, st);
+            rc = conv0_bf16(cost_bf16, blob_q + info[5], sc, bias, c0, packed ? 1 : 0, (long long)B * D, H, W, G, st);
             MVSTER_REQUIRE(rc != -100, "mvster_reg2d_bf16: conv0 shape not covered (W %% 4, G in {4,8})");
-        } else if (!L[i].transposed) {
-            rc = mvster_conv_tc3_scaled_f32(in[i], wl, sc, blob_q + info[6], skip[i], out[i], B, D, H / div[i], W / div[i], L[i].cin,
-                                            L[i].cout, L[i].kd, 3, L[i].s, relu1, stream);
+        } else if (packed) {
+            const int pf = 1 | (last ? 0 : MVSTER_TC3_OUT_PB16);
+            if (!L[i].transposed) {
+                rc = mvster_conv_tc3_pb16(in[i], wl, sc, bias, skip[i], out[i], B, D, h, w, L[i].cin, L[i].cout, L[i].kd, 3, L[i].s, pf, stream);
+            } else {
+                const int rows = tc3_deconv_rows(L[i]);
+                rc = mvster_deconv_tc3_pb16(in[i], wl, sc, bias, skip[i], out[i], B, D, h, w, L[i].cin, L[i].cout, rows, pf, stream);
+                if (rc == MVSTER_OK && rows == 0)
+                    rc = mvster_deconv_tc3_pb16(in[i], wl + mvster_deconv_tc3_packed_bytes(L[i].cin, L[i].cout, 0), sc, bias, skip[i], out[i],
+                                                B, D, h, w, L[i].cin, L[i].cout, 1, pf, stream);
+            }
         } else {
-            const int rows = tc3_deconv_rows(L[i]);
-            rc = mvster_deconv_tc3_scaled_f32(in[i], wl, sc, blob_q + info[6], skip[i], out[i], B, D, H / div[i], W / div[i], L[i].cin,
-                                              L[i].cout, rows, relu1, stream);
-            if (rc == MVSTER_OK && rows == 0)
-                rc = mvster_deconv_tc3_scaled_f32(in[i], wl + mvster_deconv_tc3_packed_bytes(L[i].cin, L[i].cout, 0), sc, blob_q + info[6],
-                                                  skip[i], out[i], B, D, H / div[i], W / div[i], L[i].cin, L[i].cout, 1, relu1, stream);
+            const int rf = 1 | MVSTER_TC3_BF16X1 | (last ? 0 : MVSTER_TC3_ROUND_OUT);
+            if (!L[i].transposed) {
+                rc = mvster_conv_tc3_scaled_f32(in[i], wl, sc, bias, skip[i], out[i], B, D, h, w, L[i].cin, L[i].cout, L[i].kd, 3, L[i].s, rf, stream);
+            } else {
+                const int rows = tc3_deconv_rows(L[i]);
+                rc = mvster_deconv_tc3_scaled_f32(in[i], wl, sc, bias, skip[i], out[i], B, D, h, w, L[i].cin, L[i].cout, rows, rf, stream);
+                if (rc == MVSTER_OK && rows == 0)
+                    rc = mvster_deconv_tc3_scaled_f32(in[i], wl + mvster_deconv_tc3_packed_bytes(L[i].cin, L[i].cout, 0), sc, bias, skip[i], out[i],
+                                                      B, D, h, w, L[i].cin, L[i].cout, 1, rf, stream);
+            }
         }
         if (rc != MVSTER_OK) return rc;
     }

@@ -122,10 +122,13 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 
 // BF (bf16 storage, mvster_reg2d_bf16): x holds bf16 voxels (the bf16 cost volume), `scale` the per-channel BatchNorm factor that
 // stays out of the bf16-valued weights: y = relu(scale * conv(x, w) + bias), accumulators start at zero.
+// BF output: out_bf16 = 1 writes y as bf16 NHWC (8 channels = 16 bytes per voxel: the packed-operand layout for C = 8), 0 writes
+// fp32 holding the bf16-rounded values (a bf16 build stores this layer's output either way).
 template <int CIN, bool BF = false>
 __global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y,
-                                                        long long NP, int H, int W, int relu, const float* __restrict__ scale = nullptr) {   // NP = B * D planes
+                                                        long long NP, int H, int W, int relu, const float* __restrict__ scale = nullptr,
+                                                        int out_bf16 = 0) {   // NP = B * D planes
     using namespace px4;
     __shared__ __align__(16) float w_s[9 * CIN * 8 + 16];
     for (int i = threadIdx.x; i < 9 * CIN * 8; i += blockDim.x) w_s[i] = __ldg(w + i);
@@ -212,6 +215,20 @@ __global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict_
             r0.x = fmaxf(r0.x, 0.f); r0.y = fmaxf(r0.y, 0.f); r0.z = fmaxf(r0.z, 0.f); r0.w = fmaxf(r0.w, 0.f);
             r1.x = fmaxf(r1.x, 0.f); r1.y = fmaxf(r1.y, 0.f); r1.z = fmaxf(r1.z, 0.f); r1.w = fmaxf(r1.w, 0.f);
         }
+        if constexpr (BF) {
+            auto rn = [](float v) -> unsigned {  // fp32 -> bf16 bits, round to nearest even (finite values)
+                const unsigned u = __float_as_uint(v);
+                return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+            };
+            const unsigned b0 = rn(r0.x) | (rn(r0.y) << 16), b1 = rn(r0.z) | (rn(r0.w) << 16);
+            const unsigned b2 = rn(r1.x) | (rn(r1.y) << 16), b3 = rn(r1.z) | (rn(r1.w) << 16);
+            if (out_bf16) {
+                reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(y) + ((pl * H + yy) * W + x0) * 8)[p] = make_uint4(b0, b1, b2, b3);
+                continue;
+            }
+            r0 = make_float4(__uint_as_float(b0 << 16), __uint_as_float(b0 & 0xFFFF0000u), __uint_as_float(b1 << 16), __uint_as_float(b1 & 0xFFFF0000u));
+            r1 = make_float4(__uint_as_float(b2 << 16), __uint_as_float(b2 & 0xFFFF0000u), __uint_as_float(b3 << 16), __uint_as_float(b3 & 0xFFFF0000u));
+        }
         dst[2 * p] = r0;
         dst[2 * p + 1] = r1;
     }
@@ -263,13 +280,14 @@ int conv_px2(const float* x, const float* w, const float* bias, const float* ski
     return -100;
 }
 
-// conv0 of the bf16-storage regulariser: x = the bf16 cost volume [NP][H][W][Cin], w [9][Cin][8] (bf16-valued fp32), y fp32
-int conv0_bf16(const void* x, const float* w, const float* scale, const float* bias, float* y, long long NP, int H, int W, int Cin,
+// conv0 of the bf16-storage regulariser: x = the bf16 cost volume [NP][H][W][Cin], w [9][Cin][8] (bf16-valued fp32); y = the
+// rounded output as bf16 NHWC (out_bf16) or as fp32
+int conv0_bf16(const void* x, const float* w, const float* scale, const float* bias, void* y, int out_bf16, long long NP, int H, int W, int Cin,
                cudaStream_t st) {
     if (W % 4 || (Cin != 4 && Cin != 8) || NP * H * (W / 4) >= (1ll << 31)) return -100;
     const long long n = NP * H * (W / 4);
-    if (Cin == 4) conv0_px4_kernel<4, true><<<ceil_div(n, 128), 128, 0, st>>>((const float*)x, w, bias, y, NP, H, W, 1, scale);
-    else conv0_px4_kernel<8, true><<<ceil_div(n, 128), 128, 0, st>>>((const float*)x, w, bias, y, NP, H, W, 1, scale);
+    if (Cin == 4) conv0_px4_kernel<4, true><<<ceil_div(n, 128), 128, 0, st>>>((const float*)x, w, bias, (float*)y, NP, H, W, 1, scale, out_bf16);
+    else conv0_px4_kernel<8, true><<<ceil_div(n, 128), 128, 0, st>>>((const float*)x, w, bias, (float*)y, NP, H, W, 1, scale, out_bf16);
     return check_launch("conv0_px4_kernel[bf16]");
 }
 

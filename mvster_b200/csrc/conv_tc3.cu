@@ -29,6 +29,13 @@
 //     the weights are bf16 values, one MMA per tap and 16 channels, products exact, fp32 accumulation; an optional per-channel
 //     fp32 scale (the BatchNorm factor, kept out of the bf16 weights) is applied to the accumulator before the bias.
 //
+//   * Packed operands (PB, mvster_conv_tc3_pb16 / mvster_deconv_tc3_pb16; bf16 storage only): the activations live in HBM as bf16
+//     in the operand's own order - octet-planar [plane][C/8][H][W][8 channels] - so a TMA box lands the halo tile of a stage
+//     directly in the operand ring (16 slots) in the un-swizzled K-major layout the MMA descriptors address: no fp32 staging
+//     ring, no converter warps (224 threads), half the activation bytes; the epilogue writes the same layout (8 channels of a
+//     pixel = one 16-byte store, 8 pixels of a tile row = 128 contiguous bytes) and reads the skip tensor from it.
+//     tools/tma_microbench.cu: TMA stages such boxes as fast as the fp32 ones (0.40 us per box and SM, 6 in flight).
+//
 // warp 0 = activation producer (TMA), warp 1 = TMEM owner + MMA issuer, warp 2 = weight producer, warps 3-10 = fp32 -> 3 x bf16
 // (or 2 x fp16) converters, warps 11-14 = epilogue.
 #include "common.cuh"
@@ -46,12 +53,17 @@ constexpr int A_SPLIT = 2 * PLANE;           // one 16-bit term of one tile-stag
 constexpr int NCONV = 256;                 // converter threads (8 warps: one warp per SM sub-partition was latency-bound)
 constexpr int CTEAM = NCONV / 2;           // ... in two teams that take alternate tile-stages
 constexpr int THREADS = 96 + NCONV + 128;
-constexpr int NF = 4, NB = 10;
+constexpr int NB = 10;
+#ifndef MVSTER_TC3_NF_SMALL
+#define MVSTER_TC3_NF_SMALL 4   // fp32 staging boxes in flight for the N <= 32 layers (A/B builds: tools/tma_microbench.cu, profiles/r02_tma_microbench.md)
+#endif
 
 struct Args {
     const uint8_t* w;
     const float* bias; const float* skip; float* y;
     const float* scale;  // per output channel, applied to the accumulator before the bias (nullptr = 1)
+    int round_out;       // one-term arithmetic with fp32 activations: round the stored output to bf16 values (MVSTER_TC3_ROUND_OUT)
+    int out_pb16;        // packed-operand kernels: y is octet-planar bf16 [plane][Cout/8][Hout][Wout][8] (else fp32 NDHWC); skip always is
     int D, Ho, Wo, cout, relu, sx, nstage, T, tiles_x, tiles_per_plane, groups_per_plane, total_groups, zero_a;
     // epilogue addressing (see there): ncls column blocks of Cout channels; up = 2 for the depth-to-space scatter of a transposed conv
     int ncls, py0, up, lg_cout, cls_a, cls_b;
@@ -80,13 +92,17 @@ static bool set_output_mode(Args& a, int ncls, int py0, bool d2s, long long bloc
     return true;
 }
 
-template <int NC, int NS>
+template <int NC, int NS, bool PB = false>
 struct Cfg {
+    static_assert(!PB || NS == 1, "packed operands: one bf16 term");
     static constexpr int TMAX = NC > 64 ? 1 : 64 / NC;      // tiles accumulated side by side: 3*NC*TMAX <= 240 TMEM columns per set
-    static constexpr int NA = NC >= 64 ? 6 : 8;             // 16-bit operand ring (tile-stages)
+    static constexpr int NF = PB ? 0 : (NC <= 32 ? MVSTER_TC3_NF_SMALL : 4);  // fp32 staging ring (TMA boxes in flight); none with packed operands
+    static constexpr int NA = PB ? 16 : (NC >= 64 ? 6 : 8); // 16-bit operand ring (tile-stages)
     static constexpr int A_BYTES = NS * A_SPLIT;            // a1 | a2 | a3   (NS = 2: a1 | a2)
     static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 x 16 bit]
-    static constexpr int SMEM_FIXED = 1024 + NF * F_BYTES + NA * A_BYTES + 512;  // alignment slack, rings, barriers; + weight slabs
+    static constexpr int BAR_BYTES = 1024;                  // mbarriers + TMEM slot
+    static constexpr int NTHREADS = PB ? 96 + 128 : THREADS;
+    static constexpr int SMEM_FIXED = 1024 + NF * F_BYTES + NA * A_BYTES + BAR_BYTES;  // alignment slack, rings, barriers; + weight slabs
     static constexpr int SMEM_MAX = 232448;                                         // 227 KB opt-in limit per CTA on sm_100
 };
 
@@ -154,15 +170,17 @@ __device__ __forceinline__ void mma_tile(uint32_t lo, uint64_t bd, uint32_t d, u
 // MG (opt-in, MVSTER_TC3_MERGE=1; not timed yet): the activation tensor map has channels and pixels MERGED into one dimension
 // (stride-1 layers whose stage covers all channels, Cin <= 16), so a halo-tile row is one contiguous run for the TMA unit instead
 // of HW_ pixel-sized pieces; the bytes land in shared memory in the same order.
-template <int NC, int NS, bool MG = false>
+template <int NC, int NS, bool MG = false, bool PB = false>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ Plan plan, const Args a) {
-    using C = Cfg<NC, NS>;
+    using C = Cfg<NC, NS, PB>;
     constexpr int A_BYTES = C::A_BYTES;
+    constexpr int NF = C::NF;
+    constexpr int EPI0 = PB ? 3 : 3 + NCONV / 32;  // first epilogue warp (packed operands: no converter warps)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t f_base = base, a_base = f_base + NF * F_BYTES, bar_base = a_base + C::NA * A_BYTES, b_base = bar_base + 512;
+    const uint32_t f_base = base, a_base = f_base + NF * F_BYTES, bar_base = a_base + C::NA * A_BYTES, b_base = bar_base + C::BAR_BYTES;
     auto F_FULL = [&](uint32_t s) { return bar_base + 8u * s; };
     auto F_EMPTY = [&](uint32_t s) { return bar_base + 8u * (NF + s); };
     auto A_FULL = [&](uint32_t s) { return bar_base + 8u * (2 * NF + s); };
@@ -177,7 +195,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NF; ++s) { mbar_init(F_FULL(s), 1); mbar_init(F_EMPTY(s), CTEAM); }
-        for (int s = 0; s < C::NA; ++s) { mbar_init(A_FULL(s), CTEAM); mbar_init(A_EMPTY(s), 1); }
+        for (int s = 0; s < C::NA; ++s) { mbar_init(A_FULL(s), PB ? 1 : CTEAM); mbar_init(A_EMPTY(s), 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(B_FULL(s), 1); mbar_init(B_EMPTY(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(ACC_FULL(s), 1); mbar_init(ACC_EMPTY(s), 128); }
         fence_barrier_init();
@@ -185,7 +203,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     if (a.zero_a) {  // Cin < 16: the converters never write the upper channel planes, the MMAs read them as zeros
         uint4* p = reinterpret_cast<uint4*>(smem_raw + (a_base - raw));
-        for (int i = threadIdx.x; i < C::NA * A_BYTES / 16; i += THREADS) p[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < C::NA * A_BYTES / 16; i += blockDim.x) p[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
     }
     tc_fence_before();
@@ -203,7 +221,31 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
         // ------------------------------------------------------------------ activation producer (TMA halo tiles)
         // Its own warp: sharing one issue thread with the weight stream (a ring of ~1 stage of taps) tied the activation
         // prefetch distance to the MMA progress and left the converters waiting for data half of the time.
-        if (elect_one()) {
+        if constexpr (PB) {
+            // packed operands: the box IS the operand tile - [<= 2 channel octets][18 rows][10 pixels][8 x bf16] - straight into the ring
+            if (elect_one()) {
+                uint32_t au = 0;
+                for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
+                    MVSTER_TC3_GROUP_HEAD
+                    for (int s = 0; s < a.nstage; ++s) {
+                        if (MVSTER_TC3_STAGE_SKIP(s)) continue;
+                        const Stage st = plan.st[s];
+                        const int noct = st.nq >> 1, oct0 = st.c0 >> 3;  // nq = 2 / 4 channel quads = 1 / 2 octets
+                        for (int t = 0; t < Tg; ++t, ++au) {
+                            const uint32_t as = au % C::NA;
+                            mbar_wait(A_EMPTY(as), ((au / C::NA) & 1) ^ 1);
+                            mbar_expect_tx(A_FULL(as), noct * PLANE);
+                            const int ti = tile0 + t, y0 = (ti / a.tiles_x) * TH, x0 = (ti % a.tiles_x) * TW;
+                            const uint32_t dst = a_base + as * A_BYTES;
+                            if (a.sx == 1)  // 4-D map, pixels x channels-of-an-octet merged: a halo row is one 160-byte run
+                                tma_load_4d(dst, &x_map, A_FULL(as), (x0 + st.ox) * 8, y0 + st.oy, oct0, plane + st.dz);
+                            else            // 5-D map with element strides 2 along x and y: one parity class of the input
+                                tma_load_5d(dst, &x_map, A_FULL(as), 0, a.sx * x0 + st.ox, a.sx * y0 + st.oy, oct0, plane + st.dz);
+                        }
+                    }
+                }
+            }
+        } else if (elect_one()) {
             uint32_t fu = 0;
             for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x) {
                 MVSTER_TC3_GROUP_HEAD
@@ -324,7 +366,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
             if (a.resident) run_role(std::true_type{});
             else run_role(std::false_type{});
         }
-    } else if (warp < 3 + NCONV / 32) {
+    } else if (warp < EPI0) {
         // ------------------------------------------------------------------ converters: fp32 halo tile -> a1 | a2 | a3 (bf16)
         // Two teams of CTEAM threads take alternate tile-stages, so one team's barrier waits and proxy fence overlap the other
         // team's conversion (with all 8 warps on one tile-stage the role cost ~1100 cycles per tile-stage whatever the tap count).
@@ -338,8 +380,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                 const int nq = plan.st[s].nq, items = HPIX * nq, qsh = nq >> 1;  // nq in {1,2,4}: pixel = item >> qsh
                 for (int t = 0; t < Tg; ++t, ++u) {
                     if ((int)(u & 1) != team) continue;
-                    const uint32_t fs = u % NF, as = u % C::NA;
-                    mbar_wait(F_FULL(fs), (u / NF) & 1);
+                    constexpr int NFD = NF ? NF : 1;  // (this role does not exist with packed operands: NF = 0)
+                    const uint32_t fs = u % NFD, as = u % C::NA;
+                    mbar_wait(F_FULL(fs), (u / NFD) & 1);
                     mbar_wait(A_EMPTY(as), ((u / C::NA) & 1) ^ 1);
                     const uint8_t* F = smem_raw + (f_base + fs * F_BYTES - raw);
                     uint8_t* A = smem_raw + (a_base + as * A_BYTES - raw);
@@ -422,6 +465,53 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     ch = c & (a.cout - 1);
                     return (cls >> 1) * a.cls_a + (cls & 1) * a.cls_b + ch;
                 };
+                if constexpr (PB) {
+                    // Packed operands: the skip tensor and (out_pb16) the output are octet-planar bf16 [plane][Cout/8][Hout][Wout][8]; 8
+                    // accumulator columns = one channel octet of one output pixel = one 16-byte access.  Column c = class * Cout +
+                    // channel as above; class (py, px) of a transposed layer is output pixel (2 yy + py0 + py, 2 xx + px).
+                    const int Hout = a.up * a.Ho, Wout = a.up * a.Wo, noct_out = a.cout >> 3;
+                    const uint4* const skip_pb = reinterpret_cast<const uint4*>(a.skip);
+                    uint4* const y_pb = reinterpret_cast<uint4*>(a.y);
+#pragma unroll
+                    for (int c0 = 0; c0 < NC; c0 += 16) {
+                        uint32_t v1[16];
+                        tmem_ld16(col + c0, v1);
+                        tmem_ld_wait();
+                        if (ok && c0 < ncol) {
+#pragma unroll
+                            for (int h8 = 0; h8 < 16; h8 += 8) {
+                                const int c = c0 + h8;
+                                if (c >= ncol) break;
+                                const int cls = c >> a.lg_cout, ch = c & (a.cout - 1);
+                                const int Y = a.up * yy + a.py0 + (a.up == 2 ? (cls >> 1) : 0), X = a.up * xx + (a.up == 2 ? (cls & 1) : 0);
+                                const long long pix_o = ((long long)(plane * noct_out + (ch >> 3)) * Hout + Y) * Wout + X;  // 16-byte units
+                                float o[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    o[e] = __uint_as_float(v1[h8 + e]);
+                                    if (a.scale) o[e] *= __ldg(a.scale + ch + e);
+                                    if (a.bias) o[e] += __ldg(a.bias + ch + e);
+                                    if (a.relu) o[e] = fmaxf(o[e], 0.f);
+                                }
+                                if (a.skip) {
+                                    const uint4 s4 = __ldg(skip_pb + pix_o);
+                                    o[0] += __uint_as_float(s4.x << 16); o[1] += __uint_as_float(s4.x & 0xFFFF0000u);
+                                    o[2] += __uint_as_float(s4.y << 16); o[3] += __uint_as_float(s4.y & 0xFFFF0000u);
+                                    o[4] += __uint_as_float(s4.z << 16); o[5] += __uint_as_float(s4.z & 0xFFFF0000u);
+                                    o[6] += __uint_as_float(s4.w << 16); o[7] += __uint_as_float(s4.w & 0xFFFF0000u);
+                                }
+                                if (a.out_pb16) {
+                                    y_pb[pix_o] = make_uint4(bf16x2_rn(o[0], o[1]), bf16x2_rn(o[2], o[3]), bf16x2_rn(o[4], o[5]), bf16x2_rn(o[6], o[7]));
+                                } else {  // fp32 NDHWC (the regulariser's last layer, read by the head)
+                                    float* dstf = a.y + (((long long)plane * Hout + Y) * Wout + X) * a.cout + ch;
+                                    *reinterpret_cast<float4*>(dstf) = make_float4(o[0], o[1], o[2], o[3]);
+                                    *reinterpret_cast<float4*>(dstf + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                                }
+                            }
+                        }
+                    }
+                    continue;
+                }
                 constexpr int RC = NC % 32 ? 16 : 32;  // columns per round: their skip values are fetched up front, all in flight
 #pragma unroll
                 for (int cb = 0; cb < NC; cb += RC) {
@@ -459,6 +549,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                                 if (a.skip) {
                                     const float4 s4 = sk[(c0 - cb + j) / 4];
                                     o[0] += s4.x; o[1] += s4.y; o[2] += s4.z; o[3] += s4.w;
+                                }
+                                if constexpr (NS == 1) {
+                                    if (a.round_out) {  // what a bf16 store of this layer's output keeps
+                                        const uint32_t p0 = bf16x2_rn(o[0], o[1]), p1 = bf16x2_rn(o[2], o[3]);
+                                        o[0] = __uint_as_float(p0 << 16); o[1] = __uint_as_float(p0 & 0xFFFF0000u);
+                                        o[2] = __uint_as_float(p1 << 16); o[3] = __uint_as_float(p1 & 0xFFFF0000u);
+                                    }
                                 }
                                 *reinterpret_cast<float4*>(yb + o_off) = make_float4(o[0], o[1], o[2], o[3]);
                             }
@@ -518,9 +615,9 @@ static int current_sm_count() {
     return n;
 }
 
-template <int NC, int NS, bool MG = false>
+template <int NC, int NS, bool MG = false, bool PB = false>
 static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long total_tiles, int sms, cudaStream_t st) {
-    using C = Cfg<NC, NS>;
+    using C = Cfg<NC, NS, PB>;
     if (g_sm_budget > 0 && g_sm_budget < sms) sms = g_sm_budget;
     int T = C::TMAX;
     while (T > 1 && total_tiles < (long long)T * 2 * sms) T >>= 1;  // keep every SM busy before widening the groups
@@ -528,7 +625,7 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
     a.T = T;
     a.groups_per_plane = ceil_div(a.tiles_per_plane, T);
     a.total_groups = (int)(total_tiles / a.tiles_per_plane) * a.groups_per_plane;
-    auto k = conv_tc3_kernel<NC, NS, MG>;
+    auto k = conv_tc3_kernel<NC, NS, MG, PB>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_MAX) != cudaSuccess) {
         set_error("conv_tc3_kernel: cannot reserve %d bytes of shared memory", C::SMEM_MAX);
         cudaGetLastError();
@@ -542,7 +639,7 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
     // (Programmatic dependent launch between consecutive convolutions - griddepcontrol.launch_dependents at the top, .wait before
     // the first activation load and the epilogue - was measured and removed: -60 us (3.4 %) per step with one stream, but with
     // the two-stream forward the replayed graph stalled for 7-100 ms every few steps; profiles/r02_pdl.md.)
-    k<<<grid, THREADS, smem, st>>>(xm, plan, a);
+    k<<<grid, C::NTHREADS, smem, st>>>(xm, plan, a);
     return check_launch("conv_tc3_kernel");
 }
 
@@ -629,6 +726,7 @@ static int conv_tc3_run(const float* x, const void* w_packed, const float* scale
     a.nslab = nslab;
     a.cin_merged = merged ? Cin : 0;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y; a.scale = scale;
+    a.round_out = (terms == 1 && (relu & MVSTER_TC3_ROUND_OUT)) ? 1 : 0; a.out_pb16 = 0;
     a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = relu & 1; a.sx = s;
     a.nstage = kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16);
     a.tiles_x = ceil_div(a.Wo, TW);
@@ -735,6 +833,7 @@ extern "C" int mvster_deconv_tc3_scaled_f32(const float* x, const void* w_packed
     Args a;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = skip; a.y = y; a.scale = scale;
     const int terms = arith_terms(relu);
+    a.round_out = (terms == 1 && (relu & MVSTER_TC3_ROUND_OUT)) ? 1 : 0; a.out_pb16 = 0;
     a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = relu & 1; a.sx = 1; a.nstage = kch;
     a.nslab = kch * ntap;
     a.cin_merged = 0;
@@ -750,4 +849,108 @@ extern "C" int mvster_deconv_tc3_scaled_f32(const float* x, const void* w_packed
     if (NC == 16) return launch<16>(xm, plan, a, total_tiles, sms, st, terms);
     if (NC == 32) return launch<32>(xm, plan, a, total_tiles, sms, st, terms);
     return launch<64>(xm, plan, a, total_tiles, sms, st, terms);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Packed operands (bf16 storage): x, skip and (MVSTER_TC3_OUT_PB16) y are octet-planar bf16, [B*D][C/8][H][W][8 channels].
+static int encode_pb16_map(CUtensorMap* xm, const void* x, int P, int H, int W, int Cin, int s, const char* who) {
+    using namespace mvster::tc3;
+    EncodeTiledFn enc = encode_fn();
+    MVSTER_REQUIRE(enc, "%s: cuTensorMapEncodeTiled is unavailable in this driver", who);
+    const cuuint32_t noct = Cin >= 16 ? 2 : 1;  // channel octets per stage
+    CUresult r;
+    if (s == 1) {  // {W*8 elements, H, C/8, P}: pixels and the 8 channels of an octet are one contiguous run
+        cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)P};
+        cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 2 * Cin};
+        cuuint32_t box[4] = {(cuuint32_t)(HW_ * 8), (cuuint32_t)HH_, noct, 1}, es[4] = {1, 1, 1, 1};
+        r = enc(xm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {       // {8, W, H, C/8, P} with element strides s along x and y: one parity class of a stride-2 layer per box
+        cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)P};
+        cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 2 * Cin};
+        cuuint32_t box[5] = {8, (cuuint32_t)(HW_ * s), (cuuint32_t)(HH_ * s), noct, 1}, es[5] = {1, (cuuint32_t)s, (cuuint32_t)s, 1, 1};
+        r = enc(xm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    MVSTER_REQUIRE(r == CUDA_SUCCESS, "%s: packed activation tensor map rejected (CUresult %d)", who, (int)r);
+    return MVSTER_OK;
+}
+
+template <int NC>
+static int launch_pb(const CUtensorMap& xm, const mvster::tc3::Plan& plan, mvster::tc3::Args& a, long long total_tiles, int sms, cudaStream_t st) {
+    return mvster::tc3::launch_ns<NC, 1, false, true>(xm, plan, a, total_tiles, sms, st);
+}
+
+extern "C" int mvster_conv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
+                                    int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int flags,
+                                    mvster_stream_t stream) {
+    using namespace mvster::tc3;
+    MVSTER_REQUIRE(x && w_packed && y, "mvster_conv_tc3_pb16: null pointer");
+    MVSTER_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "mvster_conv_tc3_pb16: bad shape");
+    MVSTER_REQUIRE(supported(Cin, Cout, kd, k, stride_hw) && Cin >= 8 && Cout <= 64, "mvster_conv_tc3_pb16: unsupported layer Cin=%d Cout=%d kd=%d k=%d stride=%d",
+                   Cin, Cout, kd, k, stride_hw);
+    MVSTER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)skip & 15) == 0,
+                   "mvster_conv_tc3_pb16: pointers must be 16-byte aligned");
+    const int s = stride_hw;
+    CUtensorMap xm;
+    int rc = encode_pb16_map(&xm, x, B * D, H, W, Cin, s, "mvster_conv_tc3_pb16");
+    if (rc != MVSTER_OK) return rc;
+    Plan plan;
+    memset(&plan, 0, sizeof(plan));
+    Args a;
+    memset(&a, 0, sizeof(a));
+    a.nslab = build_plan(Cin, kd, k, s, &plan, nullptr);
+    a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = (const float*)skip; a.y = (float*)y; a.scale = scale;
+    a.out_pb16 = (flags & MVSTER_TC3_OUT_PB16) ? 1 : 0;
+    a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = flags & 1; a.sx = s;
+    a.nstage = kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16);
+    a.tiles_x = ceil_div(a.Wo, TW);
+    a.tiles_per_plane = a.tiles_x * ceil_div(a.Ho, TH);
+    MVSTER_REQUIRE(set_output_mode(a, 1, 0, false, 0), "mvster_conv_tc3_pb16: Cout must be a power of two");
+    const long long total_tiles = (long long)a.tiles_per_plane * B * D;
+    const int sms = current_sm_count();
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NC = Cout < 16 ? 16 : Cout;
+    if (NC == 16) return launch_pb<16>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 32) return launch_pb<32>(xm, plan, a, total_tiles, sms, st);
+    return launch_pb<64>(xm, plan, a, total_tiles, sms, st);
+}
+
+extern "C" int mvster_deconv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
+                                      int B, int D, int H, int W, int Cin, int Cout, int rows, int flags, mvster_stream_t stream) {
+    using namespace mvster::tc3;
+    MVSTER_REQUIRE(x && w_packed && y, "mvster_deconv_tc3_pb16: null pointer");
+    MVSTER_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "mvster_deconv_tc3_pb16: bad shape");
+    MVSTER_REQUIRE(mvster_deconv_tc3_supported(Cin, Cout, rows), "mvster_deconv_tc3_pb16: unsupported layer Cin=%d Cout=%d rows=%d", Cin, Cout, rows);
+    MVSTER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)skip & 15) == 0,
+                   "mvster_deconv_tc3_pb16: pointers must be 16-byte aligned");
+    CUtensorMap xm;
+    int rc = encode_pb16_map(&xm, x, B * D, H, W, Cin, 1, "mvster_deconv_tc3_pb16");
+    if (rc != MVSTER_OK) return rc;
+    Plan plan;
+    memset(&plan, 0, sizeof(plan));
+    const int kch = Cin / 16, ntap = deconv_ntap(rows);
+    for (int kc = 0; kc < kch; ++kc) {
+        Stage S;
+        S.c0 = (short)(kc * 16); S.nq = 4; S.ox = -1; S.oy = -1; S.dz = 0; S.ntap = (short)ntap; S.slab0 = (short)(kc * ntap); S.pad = 0;
+        plan.st[kc] = S;
+        for (int t = 0; t < ntap; ++t) plan.a_desc[kc][t] = tap_desc((t / 2 + 1) * HW_ + (t % 2 + 1), PLANE >> 4);  // halo (1 + dy, 1 + dx)
+    }
+    Args a;
+    memset(&a, 0, sizeof(a));
+    a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = (const float*)skip; a.y = (float*)y; a.scale = scale;
+    a.out_pb16 = (flags & MVSTER_TC3_OUT_PB16) ? 1 : 0;
+    a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = flags & 1; a.sx = 1; a.nstage = kch;
+    a.nslab = kch * ntap;
+    a.tiles_x = ceil_div(W, TW);
+    a.tiles_per_plane = a.tiles_x * ceil_div(H, TH);
+    MVSTER_REQUIRE(set_output_mode(a, deconv_ncls(rows), rows == 1 ? 1 : 0, true, 0), "mvster_deconv_tc3_pb16: output row pitch does not fit 32 bits");
+    const long long total_tiles = (long long)a.tiles_per_plane * B * D;
+    const int sms = current_sm_count();
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NC = a.ncls * Cout;
+    if (NC == 16) return launch_pb<16>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 32) return launch_pb<32>(xm, plan, a, total_tiles, sms, st);
+    return launch_pb<64>(xm, plan, a, total_tiles, sms, st);
 }

@@ -359,7 +359,8 @@ class InferenceEngine:
         inverse = bool(net.inverse_depth)
         if cost.dtype == torch.bfloat16:  # storage='bf16': one-term bf16 operands, BatchNorm scale in fp32 (mvster_reg2d_bf16)
             q = self._bf16_stage_weights(p)
-            feat8 = capi.reg2d_bf16(q["blob_q"], q["tc3_blob"], q["scales"], cost)
+            # MVSTER_BF16_PACKED=0: activations as bf16-rounded values in fp32 containers (converter path) instead of packed operands
+            feat8 = capi.reg2d_bf16(q["blob_q"], q["tc3_blob"], q["scales"], cost, packed=os.environ.get("MVSTER_BF16_PACKED", "1") == "1")
             return capi.head(hypo, p.split_itv, feat8=feat8, prob_w=q["prob_w"], prob_b=q["prob_b"], inverse=inverse, bf16_input=True)
         if net.reg_net == "reg3d":
             logits = capi.reg3d(wts["blob"], cost, p.down)

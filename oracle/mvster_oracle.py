@@ -38,7 +38,8 @@ BN_EPS = 1e-5  # torch.nn.BatchNorm{2,3}d default, used by every BN in the refer
 # reduced-precision STORAGE (BASELINE cfg3 "bf16"): the reference has no bf16 path - its pixel grid is hard-coded fp32
 # (mvs4net_utils.py:28-29) and torch.autocast destroys the geometry - so the bf16 configuration is
 # defined as the fp32 reference with bf16 ROUNDING at the points where a bf16 build stores data: the FPN outputs, the cost
-# volume, and every convolution's operands (activations and weights; accumulation, BN, geometry and softmax stay fp32).
+# volume, every convolution's operands (activations and weights) and the regulariser's stored layer outputs (skip sums included);
+# accumulation, BN, geometry and softmax stay fp32.
 # PARITY UNPINNED for this configuration: there is no reference output to pin it to; the fp32 path it is built on is pinned.
 # ``fpn_internal=False`` is the variant the CUDA path implements (mvster_b200 storage="bf16"): the rounding applies to what the
 # named hot path stores and reads - the pyramid's OUTPUT features, the cost volume, the regulariser's and the head's convolution
@@ -276,12 +277,14 @@ def et_normalize(acc: Tensor, wsum: Tensor) -> Tensor:
 def reg2d_logits(sd: State, p: str, cost: Tensor) -> Tensor:
     """mvs4net_utils.py:870-912.  cost [B,G,D,H,W] -> logits [B,D,H,W]."""
     s2, p2 = (1, 2, 2), (0, 1, 1)
-    c0 = _cbr3(cost, sd, p + ".conv0", (1, 1, 1), p2)
-    c2 = _cbr3(_cbr3(c0, sd, p + ".conv1", s2, p2), sd, p + ".conv2")
-    c4 = _cbr3(_cbr3(c2, sd, p + ".conv3", s2, p2), sd, p + ".conv4")
-    x = _cbr3(_cbr3(c4, sd, p + ".conv5", s2, p2), sd, p + ".conv6")
-    x = c4 + _up3(x, sd, p + ".conv7", s2, p2, p2)
-    x = c2 + _up3(x, sd, p + ".conv9", s2, p2, p2)
+    # _q(...) marks what a reduced-precision build STORES (identity in fp32): every layer's output, skip sums included; the last
+    # sum feeds the `prob` layer, which rounds its operand itself
+    c0 = _q(_cbr3(cost, sd, p + ".conv0", (1, 1, 1), p2))
+    c2 = _q(_cbr3(_q(_cbr3(c0, sd, p + ".conv1", s2, p2)), sd, p + ".conv2"))
+    c4 = _q(_cbr3(_q(_cbr3(c2, sd, p + ".conv3", s2, p2)), sd, p + ".conv4"))
+    x = _q(_cbr3(_q(_cbr3(c4, sd, p + ".conv5", s2, p2)), sd, p + ".conv6"))
+    x = _q(c4 + _up3(x, sd, p + ".conv7", s2, p2, p2))
+    x = _q(c2 + _up3(x, sd, p + ".conv9", s2, p2, p2))
     x = c0 + _up3(x, sd, p + ".conv11", s2, p2, p2)
     return F.conv3d(_q(x), _q(sd[p + ".prob.weight"]), sd[p + ".prob.bias"]).squeeze(1)
 

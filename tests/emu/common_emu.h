@@ -27,6 +27,6 @@ inline int check_launch(const char*) { count_launch(); return MVSTER_OK; }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 int conv_px2(const float* x, const float* w, const float* bias, const float* skip, float* y,
              int B, int Di, int Hi, int Wi, int Cin, int Cout, int kd, int k, int sd, int s, int relu, cudaStream_t st);
-int conv0_bf16(const void* x, const float* w, const float* scale, const float* bias, float* y, long long NP, int H, int W, int Cin,
+int conv0_bf16(const void* x, const float* w, const float* scale, const float* bias, void* y, int out_bf16, long long NP, int H, int W, int Cin,
                cudaStream_t st);
 }  // namespace mvster

@@ -17,6 +17,8 @@
 typedef void* mvster_stream_t;
 #define MVSTER_TC3_FP16X2 256
 #define MVSTER_TC3_BF16X1 512
+#define MVSTER_TC3_OUT_PB16 1024
+#define MVSTER_TC3_ROUND_OUT 2048
 
 namespace {
 
@@ -67,6 +69,7 @@ float finish(double acc, int ch, const float* scale, const float* bias, const fl
     if (bias) o += bias[ch];
     if (relu & 1) o = o > 0.f ? o : 0.f;
     if (skip) o += skip[off];
+    if ((relu & MVSTER_TC3_BF16X1) && (relu & MVSTER_TC3_ROUND_OUT)) o = round_bf16(o);
     return o;
 }
 
@@ -168,6 +171,29 @@ int deconv_run(const float* x, const void* w_packed, const float* scale, const f
     return 0;
 }
 
+// octet-planar bf16 [P][C/8][H][W][8]  <->  fp32 [P][H][W][C]
+std::vector<float> unpack_pb16(const void* x, long long P, int H, int W, int C) {
+    const uint16_t* p = static_cast<const uint16_t*>(x);
+    std::vector<float> out((size_t)P * H * W * C);
+    for (long long pl = 0; pl < P; ++pl)
+        for (int o = 0; o < C / 8; ++o)
+            for (long long px = 0; px < (long long)H * W; ++px)
+                for (int e = 0; e < 8; ++e) out[((size_t)pl * H * W + px) * C + o * 8 + e] = bf16_to_float(p[(((size_t)pl * (C / 8) + o) * H * W + px) * 8 + e]);
+    return out;
+}
+void pack_pb16(const std::vector<float>& v, void* y, long long P, int H, int W, int C) {
+    uint16_t* p = static_cast<uint16_t*>(y);
+    for (long long pl = 0; pl < P; ++pl)
+        for (int o = 0; o < C / 8; ++o)
+            for (long long px = 0; px < (long long)H * W; ++px)
+                for (int e = 0; e < 8; ++e) {
+                    const float f = round_bf16(v[((size_t)pl * H * W + px) * C + o * 8 + e]);
+                    uint32_t u;
+                    std::memcpy(&u, &f, 4);
+                    p[(((size_t)pl * (C / 8) + o) * H * W + px) * 8 + e] = (uint16_t)(u >> 16);
+                }
+}
+
 }  // namespace
 
 extern "C" {
@@ -202,6 +228,39 @@ int mvster_deconv_tc3_scaled_f32(const float* x, const void* w_packed, const flo
 int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const float* bias, const float* skip, float* y,
                           int B, int D, int H, int W, int Cin, int Cout, int rows, int relu, mvster_stream_t st) {
     return mvster_deconv_tc3_scaled_f32(x, w_packed, nullptr, bias, skip, y, B, D, H, W, Cin, Cout, rows, relu, st);
+}
+// packed operands: unpack -> the same direct evaluation (one bf16 term) -> pack (or fp32 out)
+int mvster_conv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
+                         int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int s, int flags, mvster_stream_t) {
+    if (!x || !y || Cin < 8) return -1;
+    const int Ho = (H - 1) / s + 1, Wo = (W - 1) / s + 1;
+    const long long P = (long long)B * D;
+    const std::vector<float> xf = unpack_pb16(x, P, H, W, Cin);
+    std::vector<float> sf, yf((size_t)P * Ho * Wo * Cout);
+    if (skip) sf = unpack_pb16(skip, P, Ho, Wo, Cout);
+    const int rc = conv_run(xf.data(), w_packed, scale, bias, skip ? sf.data() : nullptr, yf.data(), B, D, H, W, Cin, Cout, kd, k, s,
+                            (flags & 1) | MVSTER_TC3_BF16X1, 0, 0);
+    if (rc) return rc;
+    if (flags & MVSTER_TC3_OUT_PB16) pack_pb16(yf, y, P, Ho, Wo, Cout);
+    else std::memcpy(y, yf.data(), yf.size() * 4);
+    return 0;
+}
+int mvster_deconv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
+                           int B, int D, int H, int W, int Cin, int Cout, int rows, int flags, mvster_stream_t) {
+    if (!x || !y) return -1;
+    const long long P = (long long)B * D;
+    const std::vector<float> xf = unpack_pb16(x, P, H, W, Cin);
+    std::vector<float> sf, yf;
+    // a rows = 0 / 1 launch writes only its own output rows: start from what the output buffer already holds
+    if (flags & MVSTER_TC3_OUT_PB16) yf = unpack_pb16(y, P, 2 * H, 2 * W, Cout);
+    else yf.assign(static_cast<const float*>(y), static_cast<const float*>(y) + (size_t)P * 4 * H * W * Cout);
+    if (skip) sf = unpack_pb16(skip, P, 2 * H, 2 * W, Cout);
+    const int rc = deconv_run(xf.data(), w_packed, scale, bias, skip ? sf.data() : nullptr, yf.data(), B, D, H, W, Cin, Cout, rows,
+                              (flags & 1) | MVSTER_TC3_BF16X1);
+    if (rc) return rc;
+    if (flags & MVSTER_TC3_OUT_PB16) pack_pb16(yf, y, P, 2 * H, 2 * W, Cout);
+    else std::memcpy(y, yf.data(), yf.size() * 4);
+    return 0;
 }
 size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int s) {
     if (!mvster::tc3::supported(Cin, Cout, kd, k, s)) return 0;

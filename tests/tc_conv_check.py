@@ -6,6 +6,7 @@ trap or a barrier deadlock in a tensor-core kernel cannot take the rest of the s
     python tests/tc_conv_check.py {reg2d|reg2dv2} G B D H W NPASS
     python tests/tc_conv_check.py v3 CIN COUT KD K STRIDE B D H W [skip] [norelu] [h16 | b16]   (h16: two-fp16-term arithmetic;
     python tests/tc_conv_check.py d3 CIN COUT B D H W [skip] [h16 | b16]                         b16: one bf16 term + per-channel scale)
+    ... b16 p16 / b16 p16f: packed bf16 operands (mvster_conv_tc3_pb16: x and skip octet-planar bf16), output packed bf16 / fp32
 """
 import json
 import sys
@@ -86,14 +87,27 @@ def v3_main():
         want = want + skip.double()
     split = 1 if b16 else 2 if "h16" in sys.argv else 3  # h16: two fp16 terms per operand (MVSTER_TC3_FP16X2)
     wp = packing.pack_tc3_weights(w, kd, k, stride, split).to(dev)
-    run = lambda: capi.conv_tc3(x, wp, bias, cout, kd, k, stride, relu, skip=skip, split=split, scale=ch_scale)
+    packed, packed_out = "p16" in sys.argv or "p16f" in sys.argv, "p16" in sys.argv
+    extra = {}
+    if packed:  # packed operands: the skip tensor is bf16 too
+        assert b16
+        if skip is not None:
+            want = want - skip.double() + bf16_round(skip).double()
+        xp, sp = capi.to_pb16(x), None if skip is None else capi.to_pb16(skip)
+        raw = lambda: capi.conv_tc3_pb16(xp, wp, bias, cout, kd, k, stride, relu, skip=sp, scale=ch_scale, out_pb16=packed_out)
+        run = (lambda: capi.from_pb16(raw())) if packed_out else raw
+    else:
+        run = lambda: capi.conv_tc3(x, wp, bias, cout, kd, k, stride, relu, skip=skip, split=split, scale=ch_scale)
     got = run()
     torch.cuda.synchronize()
+    if packed_out:  # the stored output is rounded to bf16: equal to the rounded truth except where fp32 noise flips a rounding
+        extra["flip_frac"] = (got.double() != bf16_round(want.float()).double()).double().mean().item()
+        want = bf16_round(want.float()).double()
     err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()
-    t_tc = timeit(run, 20)
+    t_tc = timeit(raw if packed else run, 20)
     flops = 2.0 * B * D * Ho * Wo * kd * k * k * cin * cout
     print(json.dumps({"case": sys.argv[1:], "abs_err": err, "scale": scale, "rel": err / scale, "finite": bool(torch.isfinite(got).all()),
-                      "us_tc": t_tc, "tflops_tc": flops / (t_tc * 1e-6) / 1e12}))
+                      "us_tc": t_tc, "tflops_tc": flops / (t_tc * 1e-6) / 1e12, **extra}))
 
 
 def d3_main():
@@ -121,7 +135,23 @@ def d3_main():
     if skip is not None:
         want = want + skip.double()
     split = 1 if b16 else 2 if "h16" in sys.argv else 3
-    if 4 * cout <= 64:
+    packed, packed_out = "p16" in sys.argv or "p16f" in sys.argv, "p16" in sys.argv
+    extra = {}
+    if packed:
+        assert b16
+        if skip is not None:
+            want = want - skip.double() + bf16_round(skip).double()
+        xp, sp = capi.to_pb16(x), None if skip is None else capi.to_pb16(skip)
+        shape, dt = ((B, D, cout // 8, 2 * H, 2 * W, 8), torch.bfloat16) if packed_out else ((B, D, 2 * H, 2 * W, cout), torch.float32)
+        buf = torch.full(shape, float("nan"), device=dev, dtype=dt)
+        wps = [packing.pack_tc3_deconv_weights(w, r_, 1).to(dev) for r_ in ((-1,) if 4 * cout <= 64 else (0, 1))]
+
+        def raw():
+            for r_, wp_ in zip((-1,) if 4 * cout <= 64 else (0, 1), wps):
+                capi.deconv_tc3_pb16(xp, wp_, bias, cout, r_, True, skip=sp, scale=ch_scale, out_pb16=packed_out, out=buf)
+            return buf
+        run = (lambda: capi.from_pb16(raw())) if packed_out else raw
+    elif 4 * cout <= 64:
         wp = packing.pack_tc3_deconv_weights(w, -1, split).to(dev)
         run = lambda: capi.deconv_tc3(x, wp, bias, cout, -1, True, skip=skip, split=split, scale=ch_scale)
     else:
@@ -133,11 +163,14 @@ def d3_main():
             return capi.deconv_tc3(x, wp1, bias, cout, 1, True, skip=skip, out=buf, split=split, scale=ch_scale)
     got = run()
     torch.cuda.synchronize()
+    if packed_out:
+        extra["flip_frac"] = (got.double() != bf16_round(want.float()).double()).double().mean().item()
+        want = bf16_round(want.float()).double()
     err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()
-    t_tc = timeit(run, 20)
+    t_tc = timeit(raw if packed else run, 20)
     t_simt = timeit(lambda: capi.conv3d_ndhwc(x, w.to(dev), bias, 1, 1, 2, True, True, skip=skip), 20)
     print(json.dumps({"case": sys.argv[1:], "abs_err": err, "scale": scale, "rel": err / scale, "finite": bool(torch.isfinite(got).all()),
-                      "us_tc": t_tc, "us_simt": t_simt, "tflops_tc": 2.0 * B * D * H * W * 9 * cin * cout / (t_tc * 1e-6) / 1e12}))
+                      "us_tc": t_tc, "us_simt": t_simt, "tflops_tc": 2.0 * B * D * H * W * 9 * cin * cout / (t_tc * 1e-6) / 1e12, **extra}))
 
 
 def main():

@@ -16,7 +16,7 @@ from util import REPO, SHIPPED, build_model, narrow_et_inputs, oracle, oracle_cf
 from mvster_b200 import capi, packing, synth
 
 pytestmark = pytest.mark.gpu
-BF16_ULP = 2.0 ** -8
+BF16_ULP = 2.0 ** -7  # largest relative spacing of bf16 values (8 significand bits): a flipped rounding moves a value by at most this much
 
 
 def q(t):
@@ -37,6 +37,19 @@ TC_CASES = [  # tests/tc_conv_check.py cases with b16: y = relu(scale * conv(bf1
     "d3 16 8 1 2 24 40 skip b16",             # conv11 class
     "d3 32 16 2 2 16 16 b16",                 # conv9 class
     "d3 64 32 1 4 8 10 skip b16",             # conv7 class: two launches
+    # packed operands (mvster_conv_tc3_pb16 / mvster_deconv_tc3_pb16: x and skip octet-planar bf16, TMA straight into the operand
+    # ring).  p16f = fp32 output: the sharp check of the load / MMA path; p16 = packed bf16 output (rounded once)
+    "v3 16 16 3 3 1 1 8 24 40 skip b16 p16f",  # depth taps, ragged tiles, 4-D merged map
+    "v3 8 16 1 3 2 1 4 64 80 b16 p16f",        # conv1: stride 2 (5-D map with element strides), one octet, two taps per MMA
+    "v3 16 32 1 3 2 1 4 30 44 b16 p16f",       # conv3, odd output size
+    "v3 32 64 1 3 2 2 2 32 32 b16 p16f",       # conv5: two stages per parity class
+    "v3 64 64 3 3 1 1 4 64 80 b16 p16f",       # conv6
+    "v3 32 32 3 3 1 2 4 16 16 norelu b16 p16", # packed output, batch 2
+    "v3 16 16 3 3 1 1 4 256 320 b16 p16",      # conv2 at cfg2 stage 4
+    "v3 8 16 1 3 2 1 4 512 640 b16 p16",       # conv1 at cfg2 stage 4
+    "d3 16 8 1 2 24 40 skip b16 p16f",         # conv11: packed skip (8 channels = NHWC bf16), fp32 out
+    "d3 32 16 2 2 16 16 skip b16 p16",         # conv9
+    "d3 64 32 1 4 8 10 skip b16 p16",          # conv7: two launches into one packed output
 ]
 
 
@@ -47,6 +60,9 @@ def test_one_term_bf16_tc_conv_matches_fp64_conv_of_rounded_operands(case):
     res = json.loads(p.stdout.strip().splitlines()[-1])
     with open(REPO / "gpurun_out" / "tc_conv_report.jsonl", "a") as f:
         f.write(json.dumps(res) + "\n")
+    if case.split()[-1] == "p16":  # packed bf16 output: the rounded truth, except where fp32 summation noise flips a rounding
+        assert res["finite"] and res["rel"] <= BF16_ULP and res["flip_frac"] < 2e-3, res
+        return
     # products of bf16 values are exact in fp32: what remains is the tensor core's fp32 accumulation of K <= 1728 terms
     assert res["finite"] and res["rel"] < 1e-5, res
 
@@ -91,6 +107,21 @@ def test_bf16_et_kernels_match_oracle(case):
         b = capi.et_fuse_bf16(il[0], il[1:], capi.pose(cams.cuda()), hypo.cuda(), G, 2.0, window=True, interleaved=True)
         assert "interleaved" in capi.et_last_kernel()
         assert (b.float().permute(0, 4, 1, 2, 3).cpu() - got).abs().max().item() <= BF16_ULP * scale
+
+
+@pytest.mark.parametrize("k,D,H,W", [(0, 8, 8, 8), (3, 4, 16, 8), (2, 4, 24, 16), (3, 4, 64, 80), (1, 8, 40, 56)])
+def test_packed_and_container_bf16_reg2d_are_the_same_arithmetic(k, D, H, W):
+    """mvster_reg2d_bf16 with packed bf16 operands between the layers (no conversion pass) against the same network with the
+    bf16-rounded activations kept in fp32 containers: same MMAs, same epilogue arithmetic, same roundings - bit-identical."""
+    sd = build_model(SHIPPED, 5).state_dict()
+    G = SHIPPED["group_cor_dim"][k]
+    rng = np.random.RandomState(100 + k)
+    cost = torch.from_numpy((rng.randn(2, D, H, W, G) * 0.1).astype(np.float32)).cuda().to(torch.bfloat16)
+    packed = {n: t.cuda() for n, t in packing.pack_reg2d_bf16(sd, f"reg.{k}", capi.reg2d_layer_table(G)).items()}
+    a = capi.reg2d_bf16(packed["blob_q"], packed["tc3_blob"], packed["scales"], cost, packed=True)
+    b = capi.reg2d_bf16(packed["blob_q"], packed["tc3_blob"], packed["scales"], cost, packed=False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all() and torch.equal(a, b), (a - b).abs().max().item()
 
 
 @pytest.mark.parametrize("k,D,H,W", [(0, 8, 8, 8), (3, 4, 16, 8), (2, 4, 24, 16), (3, 4, 64, 80)])
