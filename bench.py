@@ -738,21 +738,29 @@ def main():
         xin = torch.randn(*vox, 16, device=dev)
         wp = packing.pack_tc3_weights(torch.randn(27, 16, 16) / 20.0, 3, 3, 1, split).to(dev)
         bias = torch.zeros(16, device=dev)
-        yout = torch.empty(*vox, 16, device=dev)
+        # the form the engine runs by default: two fp16 terms with PACKED operands (activations stored as the (a1, a2) planes the
+        # producing layer's epilogue wrote; MVSTER_REG_PACKED=0 or three bf16 terms: fp32 activations + converter warps)
+        packed_tc = split == 2 and os.environ.get("MVSTER_REG_PACKED", "1") == "1"
+        if packed_tc:
+            xp = capi.to_ph16(xin)
+            layer = lambda: capi.conv_tc3_pb16(xp, wp, bias, 16, 3, 3, 1, True)
+        else:
+            yout = torch.empty(*vox, 16, device=dev)
+            layer = lambda: capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout, split=split)
         for _ in range(3):
-            capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout, split=split)
+            layer()
         ts = []
         for _ in range(20):
             flush.fill_(1.0)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            capi.conv_tc3(xin, wp, bias, 16, 3, 3, 1, True, out=yout, split=split)
+            layer()
             e.record()
             torch.cuda.synchronize()
             ts.append(s.elapsed_time(e))
         t = statistics.mean(ts)
         flops = 2.0 * vox[0] * vox[1] * vox[2] * vox[3] * 27 * 16 * 16
-        roof_tc = {"kernel": "conv_tc3_kernel<16,%d> (reg2d conv2 at stage 4: 16 -> 16 channels, 3x3x3, %d voxels)" % (split, vox[0] * vox[1] * vox[2] * vox[3]),
+        roof_tc = {"kernel": "conv_tc3_kernel<16,%d%s> (reg2d conv2 at stage 4: 16 -> 16 channels, 3x3x3, %d voxels)" % (split, ", packed operands" if packed_tc else "", vox[0] * vox[1] * vox[2] * vox[3]),
                    "bound": "tensor", "achieved": flops / (t * 1e-3) / 1e12, "peak": tf_peak[0], "unit": "TFLOP/s",
                    "frac": flops / (t * 1e-3) / 1e12 / tf_peak[0], "peak_source": tf_peak[1], "us": t * 1e3,
                    "algorithmic_flops": flops,
@@ -806,6 +814,7 @@ def main():
             "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(config_dict(world, P), engine={
                 "fpn_backend": model.fpn_backend, "fpn_precision": model.fpn_precision, "reg_precision": model.reg_precision,
+                "reg_packed_operands": os.environ.get("MVSTER_REG_PACKED", "1") == "1" and model.reg_precision == "2xfp16",
                 "cuda_graph": bool(model.use_cuda_graph) and P == 1,
                 "overlap_stages": bool(getattr(model, "overlap_stages", False)) and P == 1}),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_step_e2e,

@@ -197,6 +197,7 @@ void mvster_set_sm_budget(int n);
  * conversion saturates there).  NULL switches the check off again (then it costs nothing).  The host (engine.py) keeps it on for
  * the warm-up forwards of a new weight set / input signature and falls back to three bf16 terms (full fp32 range) if it fires. */
 void mvster_tc3_set_overflow_flag(unsigned* device_flag);
+unsigned* mvster_tc3_overflow_flag(void);   /* the calling thread's registered word (NULL = none) */
 int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw);
 int mvster_conv_tc3_plan(int Cin, int kd, int k, int stride_hw, int* slabs, int max_slabs);
 size_t mvster_conv_tc3_packed_bytes(int Cin, int Cout, int kd, int k, int stride_hw);
@@ -246,18 +247,23 @@ int mvster_reg2d_tc_f32(const float* blob, const float* tc_blob, const float* co
  * (mvster_reg2d_tc3_blob_bytes(G) bytes, 16-byte aligned; conv0's slabs are present but unused); biases and the CUDA-core
  * layers' weights are read from `blob`. */
 size_t mvster_reg2d_tc3_blob_bytes(int G);
+/* flags: 0 or MVSTER_TC3_FP16X2 (tc3_blob packed with split=2); with it, MVSTER_REG2D_PACKED keeps the activations between the
+ * layers as packed fp16 pairs (mvster_conv_tc3_pb16 with MVSTER_TC3_FP16X2: conv0 and every epilogue write the operand terms of
+ * the next layer; no conversion pass) - same products, the skip sums see their addend to 22 bits (G in {4,8}, else ignored). */
+#define MVSTER_REG2D_PACKED 4096
 int mvster_reg2d_tc3_ex_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* workspace,
-                            int B, int G, int D, int H, int W, int flags /* 0 or MVSTER_TC3_FP16X2 (tc3_blob packed with split=2) */,
-                            mvster_stream_t stream);
+                            int B, int G, int D, int H, int W, int flags, mvster_stream_t stream);
 int mvster_reg2d_tc3_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* workspace,
                          int B, int G, int D, int H, int W, mvster_stream_t stream);
 
-/* Packed operands (bf16 storage): the same two layers with activations that LIVE in HBM as bf16 in the operand's own order,
- * octet-planar [B*D][C/8][H][W][8 channels] ("PB16"; for C = 8 this is plain NHWC bf16): a TMA box lands a stage's halo tile
- * directly in the MMA operand ring - no fp32 staging, no conversion pass, half the activation bytes.  x and skip (may be NULL;
- * shape of the output) are PB16; y is PB16 with MVSTER_TC3_OUT_PB16 in `flags` (rounded to bf16 after ReLU and the skip sum),
- * else fp32 NDHWC.  flags bit 0 = ReLU.  w_packed: one bf16 term (packing.pack_tc3_weights(split=1) /
- * pack_tc3_deconv_weights(split=1)); scale as in the _scaled entry points.  Cin in {8,16,32,64}, Cout in {8,16,32,64}. */
+/* Packed operands: the same two layers with activations that LIVE in HBM as the 16-bit operand terms of the arithmetic, in the
+ * operand's own order: octet-planar [B*D][C/8][NT][H][W][8 channels].  NT = 1 (default): bf16 ("PB16", the bf16-storage
+ * configuration; for C = 8 this is plain NHWC bf16).  NT = 2 (MVSTER_TC3_FP16X2 in `flags`): the fp16 pair (a1, a2) with
+ * a = a1 + 2^-11 a2 of the two-fp16-term arithmetic - 32 bits per element like fp32, split once by the PRODUCING layer instead of
+ * by every consumer (w_packed then holds two fp16 terms, split = 2).  A TMA box lands a stage's halo tile directly in the MMA
+ * operand ring: no fp32 staging, no conversion pass (and half the activation bytes with bf16).  x and skip (may be NULL; shape of
+ * the output) are packed; y is packed with MVSTER_TC3_OUT_PB16 in `flags` (rounded / split after ReLU and the skip sum), else fp32
+ * NDHWC.  flags bit 0 = ReLU.  scale as in the _scaled entry points.  Cin in {8,16,32,64}, Cout in {8,16,32,64}. */
 #define MVSTER_TC3_OUT_PB16 1024
 int mvster_conv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
                          int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int flags, mvster_stream_t stream);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "mvster_deconv_tc3_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_set_sm_budget": (None, [_i]),
     "mvster_tc3_set_overflow_flag": (None, [_p]),
+    "mvster_tc3_overflow_flag": (_p, []),
     "mvster_conv_tc3_supported": (_i, [_i, _i, _i, _i, _i]),
     "mvster_conv_tc3_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i), _i]),
     "mvster_conv_tc3_packed_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),

@@ -417,8 +417,11 @@ def reg2d_workspace_floats(B: int, D: int, H: int, W: int) -> int:
     return int(_lib.load().mvster_reg2d_workspace_floats(B, D, H, W))
 
 
+REG2D_PACKED = 4096  # MVSTER_REG2D_PACKED
+
+
 def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: Optional[Tensor] = None,
-          tc_blob: Optional[Tensor] = None, npass: int = 3, kernel_gen: int = 2, split: int = 3) -> Tensor:
+          tc_blob: Optional[Tensor] = None, npass: int = 3, kernel_gen: int = 2, split: int = 3, packed: bool = False) -> Tensor:
     """cost [B,D,H,W,G] -> feat8 [B,D,H,W,8] (everything of reg2d except the 1x1x1 prob layer).
     With ``tc_blob``: kernel_gen 3 = conv1..conv11 on the persistent tcgen05 kernel (pack_reg2d 'tc3_blob' / 'tc3h_blob' with
     split 3 / 2); kernel_gen 2 = the three 3x3x3 layers on the staged-tile TF32 kernel (pack_tc2_weights slabs; npass 3 = 3xTF32, 1 = TF32)."""
@@ -436,7 +439,8 @@ def reg2d(blob: Tensor, cost: Tensor, workspace: Optional[Tensor] = None, out: O
     if tc_blob is not None and kernel_gen == 3:  # conv0..conv6 on the persistent 3 x bf16 kernel (packing.pack_reg2d 'tc3_blob')
         _chk(tc_blob, "tc3_blob", (int(_lib.load().mvster_reg2d_tc3_blob_bytes(G)) // 4,))
         _lib.check(_lib.load().mvster_reg2d_tc3_ex_f32(_ptr(blob), _ptr(tc_blob), _ptr(cost), _ptr(out), _ptr(workspace), B, G, D, H, W,
-                                                       TC3_FP16X2 if split == 2 else 0, _stream()), "mvster_reg2d_tc3_f32")
+                                                       (TC3_FP16X2 | (REG2D_PACKED if packed else 0)) if split == 2 else 0, _stream()),
+                   "mvster_reg2d_tc3_f32")
         return out
     if tc_blob is not None:
         _chk(tc_blob, "tc_blob", (int(_lib.load().mvster_reg2d_tc_blob_floats()),))
@@ -466,21 +470,54 @@ def from_pb16(x: Tensor) -> Tensor:
     return x.float().movedim(-4, -2).reshape(*lead, H, W, n8 * 8).contiguous()
 
 
+def to_ph16(x: Tensor) -> Tensor:
+    """[P..., H, W, C] fp32 -> the packed fp16-pair layout of the two-term tensor-core layers: [P..., C/8, 2, H, W, 8] fp16 with
+    x == a1 + 2^-11 a2 to 22 bits (a1 = fp16(x), a2 = fp16(2^11 (x - a1)); |x| < 65504).  Host-side helper for tests and tools."""
+    from . import packing
+    *lead, H, W, Cc = x.shape
+    a1, a2 = packing.fp16_split2(x.float())
+    t = torch.stack([a1, a2], dim=-1)                                     # [..., H, W, C, 2]
+    return t.reshape(*lead, H, W, Cc // 8, 8, 2).permute(*range(len(lead)), -3, -1, -5, -4, -2).contiguous()
+
+
+def from_ph16(x: Tensor) -> Tensor:
+    """Inverse of ``to_ph16``: [P..., C/8, 2, H, W, 8] fp16 -> [P..., H, W, C] fp32 (a1 + 2^-11 a2, exact)."""
+    *lead, n8, two, H, W, _ = x.shape
+    v = x[..., 0, :, :, :].float() + x[..., 1, :, :, :].float() / 2048.0   # [..., C/8, H, W, 8]
+    return v.movedim(-4, -2).reshape(*lead, H, W, n8 * 8).contiguous()
+
+
+def _packed_shape(x: Tensor):
+    """(B, D, Cin, H, W, term planes, dtype) of a packed activation tensor: [B,D,C/8,H,W,8] bf16 or [B,D,C/8,2,H,W,8] fp16."""
+    if x.dtype == torch.bfloat16 and x.dim() == 6:
+        B, D, n8, H, W, _ = x.shape
+        return B, D, 8 * n8, H, W, 1
+    if x.dtype == torch.float16 and x.dim() == 7 and x.shape[3] == 2:
+        B, D, n8, _, H, W, _ = x.shape
+        return B, D, 8 * n8, H, W, 2
+    raise TypeError(f"packed activations must be [B,D,C/8,H,W,8] bfloat16 or [B,D,C/8,2,H,W,8] float16, got {tuple(x.shape)} {x.dtype}")
+
+
+def _packed_out(B, D, cout, Ho, Wo, NT):
+    return ((B, D, cout // 8, Ho, Wo, 8), torch.bfloat16) if NT == 1 else ((B, D, cout // 8, 2, Ho, Wo, 8), torch.float16)
+
+
 def conv_tc3_pb16(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, kd: int, k: int, stride: int = 1, relu: bool = True,
                   skip: Optional[Tensor] = None, scale: Optional[Tensor] = None, out_pb16: bool = True) -> Tensor:
-    """Packed-operand tcgen05 conv (mvster_conv_tc3_pb16): x [B,D,Cin/8,H,W,8] bf16 -> [B,D,cout/8,Ho,Wo,8] bf16 (out_pb16) or
-    [B,D,Ho,Wo,cout] fp32; skip in the packed layout of the output; w_packed = packing.pack_tc3_weights(split=1)."""
-    _chk(x, "x", dtype=torch.bfloat16)
+    """Packed-operand tcgen05 conv (mvster_conv_tc3_pb16): x [B,D,Cin/8,H,W,8] bf16 (one bf16 term; w_packed split = 1) or
+    [B,D,Cin/8,2,H,W,8] fp16 (the fp16 pair; split = 2) -> the same packing of the output (out_pb16) or [B,D,Ho,Wo,cout] fp32;
+    skip in the packed layout of the output."""
+    _chk(x, "x", dtype=x.dtype)
     _chk(w_packed, "w_packed")
-    B, D, n8, H, W, _ = x.shape
-    Cin = 8 * n8
+    B, D, Cin, H, W, NT = _packed_shape(x)
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    pshape, pdt = _packed_out(B, D, cout, Ho, Wo, NT)
     if out_pb16:
-        y = torch.empty((B, D, cout // 8, Ho, Wo, 8), device=x.device, dtype=torch.bfloat16)
+        y = torch.empty(pshape, device=x.device, dtype=pdt)
     else:
         y = torch.empty((B, D, Ho, Wo, cout), device=x.device, dtype=torch.float32)
     if skip is not None:
-        _chk(skip, "skip", (B, D, cout // 8, Ho, Wo, 8), torch.bfloat16)
+        _chk(skip, "skip", pshape, pdt)
     for t, n in ((bias, "bias"), (scale, "scale")):
         if t is not None:
             _chk(t, n, (cout,))
@@ -489,22 +526,23 @@ def conv_tc3_pb16(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int
     if want == 0 or w_packed.numel() * 4 != want:
         raise ValueError(f"conv_tc3_pb16: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
     _lib.check(lib.mvster_conv_tc3_pb16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout,
-                                        kd, k, stride, int(relu) | (TC3_OUT_PB16 if out_pb16 else 0), _stream()), "mvster_conv_tc3_pb16")
+                                        kd, k, stride, int(relu) | (TC3_OUT_PB16 if out_pb16 else 0) | (TC3_FP16X2 if NT == 2 else 0), _stream()),
+               "mvster_conv_tc3_pb16")
     return y
 
 
 def deconv_tc3_pb16(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: int, rows: int = -1, relu: bool = True,
                     skip: Optional[Tensor] = None, scale: Optional[Tensor] = None, out_pb16: bool = True, out: Optional[Tensor] = None) -> Tensor:
-    """Packed-operand transposed conv (mvster_deconv_tc3_pb16): x [B,D,Cin/8,H,W,8] bf16 -> [B,D,cout/8,2H,2W,8] bf16 or
-    [B,D,2H,2W,cout] fp32; rows as in ``deconv_tc3`` (pass ``out`` to the second call)."""
-    _chk(x, "x", dtype=torch.bfloat16)
+    """Packed-operand transposed conv (mvster_deconv_tc3_pb16): x packed as in ``conv_tc3_pb16`` -> the same packing at
+    (2H, 2W) or [B,D,2H,2W,cout] fp32; rows as in ``deconv_tc3`` (pass ``out`` to the second call)."""
+    _chk(x, "x", dtype=x.dtype)
     _chk(w_packed, "w_packed")
-    B, D, n8, H, W, _ = x.shape
-    Cin = 8 * n8
-    shape, dt = ((B, D, cout // 8, 2 * H, 2 * W, 8), torch.bfloat16) if out_pb16 else ((B, D, 2 * H, 2 * W, cout), torch.float32)
+    B, D, Cin, H, W, NT = _packed_shape(x)
+    pshape, pdt = _packed_out(B, D, cout, 2 * H, 2 * W, NT)
+    shape, dt = (pshape, pdt) if out_pb16 else ((B, D, 2 * H, 2 * W, cout), torch.float32)
     y = torch.empty(shape, device=x.device, dtype=dt) if out is None else _chk(out, "out", shape, dt)
     if skip is not None:
-        _chk(skip, "skip", (B, D, cout // 8, 2 * H, 2 * W, 8), torch.bfloat16)
+        _chk(skip, "skip", pshape, pdt)
     for t, n in ((bias, "bias"), (scale, "scale")):
         if t is not None:
             _chk(t, n, (cout,))
@@ -513,7 +551,8 @@ def deconv_tc3_pb16(x: Tensor, w_packed: Tensor, bias: Optional[Tensor], cout: i
     if want == 0 or w_packed.numel() * 4 != want:
         raise ValueError(f"deconv_tc3_pb16: w_packed holds {w_packed.numel() * 4} bytes, layer needs {want} (0 = unsupported layer)")
     _lib.check(lib.mvster_deconv_tc3_pb16(_ptr(x), _ptr(w_packed), _ptr(scale), _ptr(bias), _ptr(skip), _ptr(y), B, D, H, W, Cin, cout, rows,
-                                          int(relu) | (TC3_OUT_PB16 if out_pb16 else 0), _stream()), "mvster_deconv_tc3_pb16")
+                                          int(relu) | (TC3_OUT_PB16 if out_pb16 else 0) | (TC3_FP16X2 if NT == 2 else 0), _stream()),
+               "mvster_deconv_tc3_pb16")
     return y
 
 

@@ -39,4 +39,6 @@ int conv_px2(const float* x, const float* w, const float* bias, const float* ski
 int conv0_bf16(const void* x, const float* w, const float* scale, const float* bias, void* y, int out_bf16, long long NP, int H, int W, int Cin,
                cudaStream_t st);
 
+int conv0_packed_h16(const float* x, const float* w, const float* bias, void* y, unsigned* overflow, long long NP, int H, int W, int Cin,
+                     cudaStream_t st);
 }  // namespace mvster

@@ -318,9 +318,53 @@ extern "C" size_t mvster_reg2d_tc3_blob_bytes(int G) {
     return tc3_layer_offset(L, MVSTER_REG2D_LAYERS);
 }
 
+// Two-fp16-term regulariser with PACKED activations between the layers: conv0 (CUDA cores, fp32 cost volume in) and every
+// tensor-core epilogue store the fp16 pair (a1, a2) of their output in the operand layout of the next layer; the last layer
+// (conv11 + conv0) writes fp32 for the head.  Same blobs as the unpacked form (folded weights, 'tc3h_blob').
+static int reg2d_packed_h16(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* ws,
+                            int B, int G, int D, int H, int W, mvster_stream_t stream) {
+    MVSTER_REQUIRE(blob && cost && feat8 && ws, "mvster_reg2d_tc3_f32: null pointer");
+    MVSTER_REQUIRE(H % 8 == 0 && W % 8 == 0, "mvster_reg2d_f32: H,W must be multiples of 8 (got %dx%d)", H, W);
+    Layer L[MVSTER_REG2D_LAYERS];
+    reg2d_layers(G, L);
+    const size_t N = (size_t)B * D * H * W;
+    float* c0 = ws;           float* c1 = c0 + 8 * N;  float* c2 = c1 + 4 * N;  float* c3 = c2 + 4 * N;   // 32 bits per element, as fp32
+    float* c4 = c3 + 2 * N;   float* c5 = c4 + 2 * N;  float* c6 = c5 + N;      float* u7 = c6 + N;
+    float* u9 = u7 + 2 * N;
+    const float* in[MVSTER_REG2D_LAYERS] = {cost, c0, c1, c2, c3, c4, c5, c6, u7, u9};
+    float* out[MVSTER_REG2D_LAYERS] = {c0, c1, c2, c3, c4, c5, c6, u7, u9, feat8};
+    const float* skip[MVSTER_REG2D_LAYERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c4, c2, c0};
+    const int div[MVSTER_REG2D_LAYERS] = {1, 1, 2, 2, 4, 4, 8, 8, 4, 2};
+    for (int i = 0; i < MVSTER_REG2D_LAYERS; ++i) {
+        int64_t info[8];
+        mvster_reg2d_layer_info(G, i, info);
+        const uint8_t* wl = (const uint8_t*)tc3_blob + tc3_layer_offset(L, i);
+        const float* bias = blob + info[6];
+        const int h = H / div[i], w = W / div[i];
+        const int pf = 1 | MVSTER_TC3_FP16X2 | (i == MVSTER_REG2D_LAYERS - 1 ? 0 : MVSTER_TC3_OUT_PB16);
+        int rc;
+        if (i == 0) {
+            rc = conv0_packed_h16(cost, blob + info[5], bias, c0, mvster_tc3_overflow_flag(), (long long)B * D, H, W, G, (cudaStream_t)stream);
+            MVSTER_REQUIRE(rc != -100, "mvster_reg2d_tc3_f32: conv0 shape not covered by the packed form");
+        } else if (!L[i].transposed) {
+            rc = mvster_conv_tc3_pb16(in[i], wl, nullptr, bias, skip[i], out[i], B, D, h, w, L[i].cin, L[i].cout, L[i].kd, 3, L[i].s, pf, stream);
+        } else {
+            const int rows = tc3_deconv_rows(L[i]);
+            rc = mvster_deconv_tc3_pb16(in[i], wl, nullptr, bias, skip[i], out[i], B, D, h, w, L[i].cin, L[i].cout, rows, pf, stream);
+            if (rc == MVSTER_OK && rows == 0)
+                rc = mvster_deconv_tc3_pb16(in[i], wl + mvster_deconv_tc3_packed_bytes(L[i].cin, L[i].cout, 0), nullptr, bias, skip[i], out[i],
+                                            B, D, h, w, L[i].cin, L[i].cout, 1, pf, stream);
+        }
+        if (rc != MVSTER_OK) return rc;
+    }
+    return MVSTER_OK;
+}
+
 extern "C" int mvster_reg2d_tc3_ex_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* ws,
                                        int B, int G, int D, int H, int W, int flags, mvster_stream_t stream) {
     MVSTER_REQUIRE(tc3_blob, "mvster_reg2d_tc3_f32: tc3_blob is null");
+    if ((flags & MVSTER_TC3_FP16X2) && (flags & MVSTER_REG2D_PACKED) && (G == 4 || G == 8))
+        return reg2d_packed_h16(blob, tc3_blob, cost, feat8, ws, B, G, D, H, W, stream);
     // npass carries the arithmetic of the generation-3 layers: 3 = three bf16 terms, 2 = two fp16 terms
     return reg2d_run(blob, (const float*)tc3_blob, (flags & MVSTER_TC3_FP16X2) ? 2 : 3, 3, cost, feat8, ws, B, G, D, H, W, stream);
 }

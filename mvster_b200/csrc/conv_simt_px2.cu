@@ -120,6 +120,47 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 #endif
 }  // namespace px4
 
+// two fp32 -> the packed fp16 pairs (t1, t2) with v == t1 + 2^-11 t2 to 22 bits: the operand terms of the two-fp16-term tensor-core
+// arithmetic (conv_tc3.cu split2h: same instructions, same bits)
+#ifdef MVSTER_CPU_EMU
+static inline unsigned emu_f2h(float f) {  // fp32 -> fp16 bits, round to nearest even, saturating to +-65504 (cvt.rn.satfinite.f16.f32)
+    unsigned u;
+    memcpy(&u, &f, 4);
+    const unsigned sign = (u >> 16) & 0x8000u;
+    u &= 0x7FFFFFFFu;
+    if (u > 0x7F800000u) return sign | 0x7FFFu;                 // NaN
+    if (u >= 0x477FF000u) return sign | 0x7BFFu;                // >= 65520 rounds past the largest finite value: saturate
+    if (u < 0x33000001u) return sign;                           // below half of the smallest subnormal
+    const int e = (int)(u >> 23) - 127;
+    unsigned m = (u & 0x7FFFFFu) | 0x800000u;
+    int shift = e >= -14 ? 13 : 13 + (-14 - e);                 // subnormal results shift further
+    const unsigned half = 1u << (shift - 1), rest = m & ((1u << shift) - 1);
+    m >>= shift;
+    if (rest > half || (rest == half && (m & 1u))) ++m;
+    const unsigned base = e >= -14 ? ((unsigned)(e + 15) << 10) - 0x400u : 0u;  // m carries the implicit bit for normals
+    return sign | (base + m);
+}
+static inline float emu_h2f(unsigned h) {
+    const int s = (h >> 15) & 1, e = (h >> 10) & 31, m = h & 1023;
+    float v = e == 0 ? ldexpf((float)m, -24) : e == 31 ? (m ? NAN : INFINITY) : ldexpf((float)(m | 1024), e - 25);
+    return s ? -v : v;
+}
+__device__ __forceinline__ void split2h_pair(float x, float y, unsigned& t1, unsigned& t2) {
+    const unsigned hx = emu_f2h(x), hy = emu_f2h(y);
+    t1 = hx | (hy << 16);
+    const float rx = (x - emu_h2f(hx)) * 2048.f, ry = (y - emu_h2f(hy)) * 2048.f;
+    t2 = emu_f2h(rx) | (emu_f2h(ry) << 16);
+}
+#else
+__device__ __forceinline__ void split2h_pair(float x, float y, unsigned& t1, unsigned& t2) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(t1) : "f"(y), "f"(x));
+    float bx, by;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(bx), "=f"(by) : "r"(t1));
+    const float rx = (x - bx) * 2048.f, ry = (y - by) * 2048.f;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(t2) : "f"(ry), "f"(rx));
+}
+#endif
+
 // BF (bf16 storage, mvster_reg2d_bf16): x holds bf16 voxels (the bf16 cost volume), `scale` the per-channel BatchNorm factor that
 // stays out of the bf16-valued weights: y = relu(scale * conv(x, w) + bias), accumulators start at zero.
 // BF output: out_bf16 = 1 writes y as bf16 NHWC (8 channels = 16 bytes per voxel: the packed-operand layout for C = 8), 0 writes
@@ -128,7 +169,9 @@ template <int CIN, bool BF = false>
 __global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ y,
                                                         long long NP, int H, int W, int relu, const float* __restrict__ scale = nullptr,
-                                                        int out_bf16 = 0) {   // NP = B * D planes
+                                                        int out_bf16 = 0, unsigned* overflow = nullptr) {   // NP = B * D planes
+    // !BF with out_bf16 = 2: y as the packed fp16 pair [NP][1 octet][a1 | a2][H][W][8] - the operand layout of the packed two-term
+    // tensor-core layers (mvster_conv_tc3_pb16 with MVSTER_TC3_FP16X2); `overflow` as in mvster_tc3_set_overflow_flag
     using namespace px4;
     __shared__ __align__(16) float w_s[9 * CIN * 8 + 16];
     for (int i = threadIdx.x; i < 9 * CIN * 8; i += blockDim.x) w_s[i] = __ldg(w + i);
@@ -229,6 +272,21 @@ __global__ void __launch_bounds__(128) conv0_px4_kernel(const float* __restrict_
             r0 = make_float4(__uint_as_float(b0 << 16), __uint_as_float(b0 & 0xFFFF0000u), __uint_as_float(b1 << 16), __uint_as_float(b1 & 0xFFFF0000u));
             r1 = make_float4(__uint_as_float(b2 << 16), __uint_as_float(b2 & 0xFFFF0000u), __uint_as_float(b3 << 16), __uint_as_float(b3 & 0xFFFF0000u));
         }
+        if (!BF && out_bf16 == 2) {
+            uint4 t1, t2;
+            split2h_pair(r0.x, r0.y, t1.x, t2.x); split2h_pair(r0.z, r0.w, t1.y, t2.y);
+            split2h_pair(r1.x, r1.y, t1.z, t2.z); split2h_pair(r1.z, r1.w, t1.w, t2.w);
+            uint4* yp = reinterpret_cast<uint4*>(y) + ((pl * 2) * H + yy) * W + x0 + p;
+            yp[0] = t1;
+            yp[(long long)H * W] = t2;
+            if (overflow) {
+                const float m = fmaxf(fmaxf(fmaxf(fabsf(r0.x), fabsf(r0.y)), fmaxf(fabsf(r0.z), fabsf(r0.w))),
+                                      fmaxf(fmaxf(fabsf(r1.x), fabsf(r1.y)), fmaxf(fabsf(r1.z), fabsf(r1.w))));
+                const bool nan = r0.x != r0.x || r0.y != r0.y || r0.z != r0.z || r0.w != r0.w || r1.x != r1.x || r1.y != r1.y || r1.z != r1.z || r1.w != r1.w;
+                if (nan || !(m < 65504.f)) atomicOr(overflow, 1u);
+            }
+            continue;
+        }
         dst[2 * p] = r0;
         dst[2 * p + 1] = r1;
     }
@@ -289,6 +347,16 @@ int conv0_bf16(const void* x, const float* w, const float* scale, const float* b
     if (Cin == 4) conv0_px4_kernel<4, true><<<ceil_div(n, 128), 128, 0, st>>>((const float*)x, w, bias, (float*)y, NP, H, W, 1, scale, out_bf16);
     else conv0_px4_kernel<8, true><<<ceil_div(n, 128), 128, 0, st>>>((const float*)x, w, bias, (float*)y, NP, H, W, 1, scale, out_bf16);
     return check_launch("conv0_px4_kernel[bf16]");
+}
+
+// conv0 of the fp32 regulariser writing its output as the packed fp16 pair (x fp32 cost volume, folded weights): -100 = not covered
+int conv0_packed_h16(const float* x, const float* w, const float* bias, void* y, unsigned* overflow, long long NP, int H, int W, int Cin,
+                     cudaStream_t st) {
+    if (W % 4 || (Cin != 4 && Cin != 8) || NP * H * (W / 4) >= (1ll << 31)) return -100;
+    const long long n = NP * H * (W / 4);
+    if (Cin == 4) conv0_px4_kernel<4><<<ceil_div(n, 128), 128, 0, st>>>(x, w, bias, (float*)y, NP, H, W, 1, nullptr, 2, overflow);
+    else conv0_px4_kernel<8><<<ceil_div(n, 128), 128, 0, st>>>(x, w, bias, (float*)y, NP, H, W, 1, nullptr, 2, overflow);
+    return check_launch("conv0_px4_kernel[packed fp16 pair]");
 }
 
 }  // namespace mvster

@@ -29,11 +29,13 @@
 //     the weights are bf16 values, one MMA per tap and 16 channels, products exact, fp32 accumulation; an optional per-channel
 //     fp32 scale (the BatchNorm factor, kept out of the bf16 weights) is applied to the accumulator before the bias.
 //
-//   * Packed operands (PB, mvster_conv_tc3_pb16 / mvster_deconv_tc3_pb16; bf16 storage only): the activations live in HBM as bf16
-//     in the operand's own order - octet-planar [plane][C/8][H][W][8 channels] - so a TMA box lands the halo tile of a stage
-//     directly in the operand ring (16 slots) in the un-swizzled K-major layout the MMA descriptors address: no fp32 staging
-//     ring, no converter warps (224 threads), half the activation bytes; the epilogue writes the same layout (8 channels of a
-//     pixel = one 16-byte store, 8 pixels of a tile row = 128 contiguous bytes) and reads the skip tensor from it.
+//   * Packed operands (PB, mvster_conv_tc3_pb16 / mvster_deconv_tc3_pb16): the activations live in HBM as 16-bit operand terms
+//     in the operand's own order - octet-planar [plane][C/8][NS terms][H][W][8 channels]; NS = 1: bf16 (bf16 storage), NS = 2:
+//     the fp16 pair (a1, a2) of the two-term arithmetic, 32 bits per element like fp32, split ONCE by the producing layer's
+//     epilogue instead of by every consumer - so a TMA box lands the halo tile of a stage directly in the operand ring in the
+//     un-swizzled K-major layout the MMA descriptors address: no fp32 staging ring, no converter warps (224 threads); the
+//     epilogue writes the same layout (8 channels of a pixel = one 16-byte store per term, 8 pixels of a tile row = 128
+//     contiguous bytes) and reads the skip tensor from it.
 //     tools/tma_microbench.cu: TMA stages such boxes as fast as the fp32 ones (0.40 us per box and SM, 6 in flight).
 //
 // warp 0 = activation producer (TMA), warp 1 = TMEM owner + MMA issuer, warp 2 = weight producer, warps 3-10 = fp32 -> 3 x bf16
@@ -63,7 +65,7 @@ struct Args {
     const float* bias; const float* skip; float* y;
     const float* scale;  // per output channel, applied to the accumulator before the bias (nullptr = 1)
     int round_out;       // one-term arithmetic with fp32 activations: round the stored output to bf16 values (MVSTER_TC3_ROUND_OUT)
-    int out_pb16;        // packed-operand kernels: y is octet-planar bf16 [plane][Cout/8][Hout][Wout][8] (else fp32 NDHWC); skip always is
+    int out_pb16;        // packed-operand kernels: y is packed like the input, [plane][Cout/8][NS][Hout][Wout][8] (else fp32 NDHWC); skip always is
     int D, Ho, Wo, cout, relu, sx, nstage, T, tiles_x, tiles_per_plane, groups_per_plane, total_groups, zero_a;
     // epilogue addressing (see there): ncls column blocks of Cout channels; up = 2 for the depth-to-space scatter of a transposed conv
     int ncls, py0, up, lg_cout, cls_a, cls_b;
@@ -94,10 +96,10 @@ static bool set_output_mode(Args& a, int ncls, int py0, bool d2s, long long bloc
 
 template <int NC, int NS, bool PB = false>
 struct Cfg {
-    static_assert(!PB || NS == 1, "packed operands: one bf16 term");
+    static_assert(!PB || NS <= 2, "packed operands: one bf16 term or the fp16 pair");
     static constexpr int TMAX = NC > 64 ? 1 : 64 / NC;      // tiles accumulated side by side: 3*NC*TMAX <= 240 TMEM columns per set
     static constexpr int NF = PB ? 0 : (NC <= 32 ? MVSTER_TC3_NF_SMALL : 4);  // fp32 staging ring (TMA boxes in flight); none with packed operands
-    static constexpr int NA = PB ? 16 : (NC >= 64 ? 6 : 8); // 16-bit operand ring (tile-stages)
+    static constexpr int NA = PB ? (NS == 1 ? 16 : 10) : (NC >= 64 ? 6 : 8); // 16-bit operand ring (tile-stages)
     static constexpr int A_BYTES = NS * A_SPLIT;            // a1 | a2 | a3   (NS = 2: a1 | a2)
     static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 x 16 bit]
     static constexpr int BAR_BYTES = 1024;                  // mbarriers + TMEM slot
@@ -133,8 +135,10 @@ __device__ __forceinline__ void split2h(float x, float y, uint32_t& t1, uint32_t
 // blocks by a constant column offset, and every other operand is an immediate - so the issuing thread spends one add and the
 // register -> uniform-register moves of (lo, d) per tile instead of re-materialising every operand per MMA (the issue thread,
 // not the tensor pipe, bounded the N <= 32 layers: ncu source page, profiles/r01_conv_tc3_h16_ncu.md).
-template <int NC, int NS>
+template <int NC, int NS, bool PB = false>
 __device__ __forceinline__ void mma_tile(uint32_t lo, uint64_t bd, uint32_t d, uint32_t accumulate) {
+    // distance of the second operand term from the first: converter layout [a1: octets][a2: octets]; packed layout [octet][a1 | a2]
+    constexpr int TERM2 = (PB ? PLANE : A_SPLIT) >> 4;
     constexpr uint32_t A_HI32 = (uint32_t)((HW_ * 16) >> 4) | (1u << 14);
     if constexpr (NS == 1) {
         asm volatile(
@@ -162,7 +166,7 @@ __device__ __forceinline__ void mma_tile(uint32_t lo, uint64_t bd, uint32_t d, u
             "mov.b64 a1, {%1, %6};\n\tmov.b64 a2, {l2, %6};\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, %2, %7, pa;\n\t"   // a1 x [w1|w2]: block 0 = a1 w1, block 1 = a1 w2
             "tcgen05.mma.cta_group::1.kind::f16 [d2], a2, %2, %8, pt;\n\t}"  // a2 x [w1] onto block 1
-            ::"r"(d), "r"(lo), "l"(bd), "r"(accumulate), "n"(A_SPLIT >> 4), "n"(NC), "n"(A_HI32),
+            ::"r"(d), "r"(lo), "l"(bd), "r"(accumulate), "n"(TERM2), "n"(NC), "n"(A_HI32),
               "n"(idesc_f16_m128(2 * NC)), "n"(idesc_f16_m128(NC)) : "memory");
     }
 }
@@ -230,7 +234,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     for (int s = 0; s < a.nstage; ++s) {
                         if (MVSTER_TC3_STAGE_SKIP(s)) continue;
                         const Stage st = plan.st[s];
-                        const int noct = st.nq >> 1, oct0 = st.c0 >> 3;  // nq = 2 / 4 channel quads = 1 / 2 octets
+                        const int noct = (st.nq >> 1) * NS, oct0 = (st.c0 >> 3) * NS;  // nq = 2 / 4 channel quads = 1 / 2 octets of NS term planes
                         for (int t = 0; t < Tg; ++t, ++au) {
                             const uint32_t as = au % C::NA;
                             mbar_wait(A_EMPTY(as), ((au / C::NA) & 1) ^ 1);
@@ -349,7 +353,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         // every tile slot of the group is issued, also past Tg (a ragged last group of a plane): alo[] then repeats
                         // tile 0's operands and the MMAs land in accumulator columns the epilogue never reads - straight-line code
 #pragma unroll
-                        for (int t = 0; t < C::TMAX; ++t) mma_tile<NC, NS>(alo[t] + shift, bd, d0 + (uint32_t)(t * 3 * NC), accumulate);
+                        for (int t = 0; t < C::TMAX; ++t) mma_tile<NC, NS, PB>(alo[t] + shift, bd, d0 + (uint32_t)(t * 3 * NC), accumulate);
                         if constexpr (!RES) {
                             umma_commit(B_EMPTY(b_slot));
                             if (++b_slot == NB) { b_slot = 0; b_par ^= 1; }
@@ -442,6 +446,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
         // ------------------------------------------------------------------ epilogue
         const int q = warp & 3, r = q * 32 + lane;  // TMEM lane quarter, accumulator row = pixel in the tile
         uint32_t gc = 0;
+        [[maybe_unused]] bool bad = false;  // packed fp16-pair output: a stored value outside the fp16 terms' range
         for (int g = blockIdx.x; g < a.total_groups; g += gridDim.x, ++gc) {
             MVSTER_TC3_GROUP_HEAD
             (void)z;
@@ -466,16 +471,19 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                     return (cls >> 1) * a.cls_a + (cls & 1) * a.cls_b + ch;
                 };
                 if constexpr (PB) {
-                    // Packed operands: the skip tensor and (out_pb16) the output are octet-planar bf16 [plane][Cout/8][Hout][Wout][8]; 8
-                    // accumulator columns = one channel octet of one output pixel = one 16-byte access.  Column c = class * Cout +
-                    // channel as above; class (py, px) of a transposed layer is output pixel (2 yy + py0 + py, 2 xx + px).
+                    // Packed operands: the skip tensor and (out_pb16) the output are octet-planar 16-bit terms,
+                    // [plane][Cout/8][NS][Hout][Wout][8]: 8 accumulator columns = one channel octet of one output pixel = one 16-byte
+                    // access per term.  Column c = class * Cout + channel as above; class (py, px) of a transposed layer is output
+                    // pixel (2 yy + py0 + py, 2 xx + px).
                     const int Hout = a.up * a.Ho, Wout = a.up * a.Wo, noct_out = a.cout >> 3;
+                    const long long term_stride = (long long)Hout * Wout;  // 16-byte units between the a1 and the a2 plane of an octet
                     const uint4* const skip_pb = reinterpret_cast<const uint4*>(a.skip);
                     uint4* const y_pb = reinterpret_cast<uint4*>(a.y);
 #pragma unroll
                     for (int c0 = 0; c0 < NC; c0 += 16) {
-                        uint32_t v1[16];
+                        uint32_t v1[16], v2[16];
                         tmem_ld16(col + c0, v1);
+                        if constexpr (NS == 2) tmem_ld16(col + NC + c0, v2);
                         tmem_ld_wait();
                         if (ok && c0 < ncol) {
 #pragma unroll
@@ -484,24 +492,50 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                                 if (c >= ncol) break;
                                 const int cls = c >> a.lg_cout, ch = c & (a.cout - 1);
                                 const int Y = a.up * yy + a.py0 + (a.up == 2 ? (cls >> 1) : 0), X = a.up * xx + (a.up == 2 ? (cls & 1) : 0);
-                                const long long pix_o = ((long long)(plane * noct_out + (ch >> 3)) * Hout + Y) * Wout + X;  // 16-byte units
+                                const long long pix_o = ((long long)(plane * noct_out + (ch >> 3)) * NS * Hout + Y) * Wout + X;  // 16-byte units
                                 float o[8];
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
-                                    o[e] = __uint_as_float(v1[h8 + e]);
+                                    if constexpr (NS == 2) o[e] = fmaf(__uint_as_float(v2[h8 + e]), 1.f / 2048.f, __uint_as_float(v1[h8 + e]));
+                                    else o[e] = __uint_as_float(v1[h8 + e]);
                                     if (a.scale) o[e] *= __ldg(a.scale + ch + e);
                                     if (a.bias) o[e] += __ldg(a.bias + ch + e);
                                     if (a.relu) o[e] = fmaxf(o[e], 0.f);
                                 }
                                 if (a.skip) {
                                     const uint4 s4 = __ldg(skip_pb + pix_o);
-                                    o[0] += __uint_as_float(s4.x << 16); o[1] += __uint_as_float(s4.x & 0xFFFF0000u);
-                                    o[2] += __uint_as_float(s4.y << 16); o[3] += __uint_as_float(s4.y & 0xFFFF0000u);
-                                    o[4] += __uint_as_float(s4.z << 16); o[5] += __uint_as_float(s4.z & 0xFFFF0000u);
-                                    o[6] += __uint_as_float(s4.w << 16); o[7] += __uint_as_float(s4.w & 0xFFFF0000u);
+                                    if constexpr (NS == 2) {  // skip = a1 + 2^-11 a2 (exact in fp32)
+                                        const uint4 r4 = __ldg(skip_pb + pix_o + term_stride);
+                                        const uint32_t w1[4] = {s4.x, s4.y, s4.z, s4.w}, w2[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            float a1x, a1y, a2x, a2y;
+                                            asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(a1x), "=f"(a1y) : "r"(w1[e]));
+                                            asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(a2x), "=f"(a2y) : "r"(w2[e]));
+                                            o[2 * e] += fmaf(a2x, 1.f / 2048.f, a1x);
+                                            o[2 * e + 1] += fmaf(a2y, 1.f / 2048.f, a1y);
+                                        }
+                                    } else {
+                                        o[0] += __uint_as_float(s4.x << 16); o[1] += __uint_as_float(s4.x & 0xFFFF0000u);
+                                        o[2] += __uint_as_float(s4.y << 16); o[3] += __uint_as_float(s4.y & 0xFFFF0000u);
+                                        o[4] += __uint_as_float(s4.z << 16); o[5] += __uint_as_float(s4.z & 0xFFFF0000u);
+                                        o[6] += __uint_as_float(s4.w << 16); o[7] += __uint_as_float(s4.w & 0xFFFF0000u);
+                                    }
                                 }
                                 if (a.out_pb16) {
-                                    y_pb[pix_o] = make_uint4(bf16x2_rn(o[0], o[1]), bf16x2_rn(o[2], o[3]), bf16x2_rn(o[4], o[5]), bf16x2_rn(o[6], o[7]));
+                                    if constexpr (NS == 2) {  // the next layer's operand terms, split here once: a = a1 + 2^-11 a2
+                                        if (a.overflow) {     // range check of the fp16 terms (mvster_tc3_set_overflow_flag), on what this layer stores
+#pragma unroll
+                                            for (int e = 0; e < 8; ++e) bad |= !(fabsf(o[e]) < 65504.f);  // also true for NaN
+                                        }
+                                        uint4 t1, t2;
+                                        split2h(o[0], o[1], t1.x, t2.x); split2h(o[2], o[3], t1.y, t2.y);
+                                        split2h(o[4], o[5], t1.z, t2.z); split2h(o[6], o[7], t1.w, t2.w);
+                                        y_pb[pix_o] = t1;
+                                        y_pb[pix_o + term_stride] = t2;
+                                    } else {
+                                        y_pb[pix_o] = make_uint4(bf16x2_rn(o[0], o[1]), bf16x2_rn(o[2], o[3]), bf16x2_rn(o[4], o[5]), bf16x2_rn(o[6], o[7]));
+                                    }
                                 } else {  // fp32 NDHWC (the regulariser's last layer, read by the head)
                                     float* dstf = a.y + (((long long)plane * Hout + Y) * Wout + X) * a.cout + ch;
                                     *reinterpret_cast<float4*>(dstf) = make_float4(o[0], o[1], o[2], o[3]);
@@ -565,6 +599,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
             }
             tc_fence_before();
             mbar_arrive(ACC_EMPTY(set));
+        }
+        if constexpr (PB && NS == 2) {
+            if (a.overflow && bad) atomicOr(a.overflow, 1u);
         }
     }
 #undef MVSTER_TC3_GROUP_HEAD
@@ -664,6 +701,7 @@ using namespace mvster;
 
 extern "C" void mvster_set_sm_budget(int n) { tc3::g_sm_budget = n > 0 ? n : 0; }
 extern "C" void mvster_tc3_set_overflow_flag(unsigned* device_flag) { tc3::g_overflow_flag = device_flag; }
+extern "C" unsigned* mvster_tc3_overflow_flag(void) { return tc3::g_overflow_flag; }
 
 extern "C" int mvster_conv_tc3_supported(int Cin, int Cout, int kd, int k, int stride_hw) {
     return tc3::supported(Cin, Cout, kd, k, stride_hw);
@@ -853,24 +891,26 @@ extern "C" int mvster_deconv_tc3_scaled_f32(const float* x, const void* w_packed
 
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Packed operands (bf16 storage): x, skip and (MVSTER_TC3_OUT_PB16) y are octet-planar bf16, [B*D][C/8][H][W][8 channels].
-static int encode_pb16_map(CUtensorMap* xm, const void* x, int P, int H, int W, int Cin, int s, const char* who) {
+// Packed operands: x, skip and (MVSTER_TC3_OUT_PB16) y are octet-planar 16-bit terms, [B*D][C/8][NT][H][W][8 channels]; NT = 1:
+// bf16, NT = 2 (MVSTER_TC3_FP16X2): the fp16 pair.  The (octet, term) planes of a stage are consecutive: one box dimension.
+static int encode_pb16_map(CUtensorMap* xm, const void* x, int P, int H, int W, int Cin, int s, int NT, const char* who) {
     using namespace mvster::tc3;
     EncodeTiledFn enc = encode_fn();
     MVSTER_REQUIRE(enc, "%s: cuTensorMapEncodeTiled is unavailable in this driver", who);
-    const cuuint32_t noct = Cin >= 16 ? 2 : 1;  // channel octets per stage
+    const cuuint32_t noct = (Cin >= 16 ? 2 : 1) * NT;  // (octet, term) planes per stage
+    const CUtensorMapDataType dt = NT == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUresult r;
     if (s == 1) {  // {W*8 elements, H, C/8, P}: pixels and the 8 channels of an octet are one contiguous run
-        cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)P};
-        cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 2 * Cin};
+        cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(Cin / 8 * NT), (cuuint64_t)P};
+        cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 2 * Cin * NT};
         cuuint32_t box[4] = {(cuuint32_t)(HW_ * 8), (cuuint32_t)HH_, noct, 1}, es[4] = {1, 1, 1, 1};
-        r = enc(xm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        r = enc(xm, dt, 4, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {       // {8, W, H, C/8, P} with element strides s along x and y: one parity class of a stride-2 layer per box
-        cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)P};
-        cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 2 * Cin};
+        cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8 * NT), (cuuint64_t)P};
+        cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 2 * Cin * NT};
         cuuint32_t box[5] = {8, (cuuint32_t)(HW_ * s), (cuuint32_t)(HH_ * s), noct, 1}, es[5] = {1, (cuuint32_t)s, (cuuint32_t)s, 1, 1};
-        r = enc(xm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        r = enc(xm, dt, 5, (void*)x, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     MVSTER_REQUIRE(r == CUDA_SUCCESS, "%s: packed activation tensor map rejected (CUresult %d)", who, (int)r);
@@ -878,8 +918,18 @@ static int encode_pb16_map(CUtensorMap* xm, const void* x, int P, int H, int W, 
 }
 
 template <int NC>
-static int launch_pb(const CUtensorMap& xm, const mvster::tc3::Plan& plan, mvster::tc3::Args& a, long long total_tiles, int sms, cudaStream_t st) {
+static int launch_pb(const CUtensorMap& xm, const mvster::tc3::Plan& plan, mvster::tc3::Args& a, long long total_tiles, int sms, cudaStream_t st, int NT) {
+    if (NT == 2) return mvster::tc3::launch_ns<NC, 2, false, true>(xm, plan, a, total_tiles, sms, st);
     return mvster::tc3::launch_ns<NC, 1, false, true>(xm, plan, a, total_tiles, sms, st);
+}
+
+// fp16-pair operands: the two channel octets of an MMA's K halves are 2 planes apart ([octet][a1 | a2]); the paired-tap layers
+// (Cin <= 8: second K half = a second tap of the same plane) keep their tap distance
+static void widen_octet_lbo(mvster::tc3::Plan& plan, int nstage) {
+    using namespace mvster::tc3;
+    for (int s = 0; s < nstage; ++s)
+        for (int t = 0; t < plan.st[s].ntap; ++t)
+            if ((plan.a_desc[s][t] >> 16) == (uint32_t)(PLANE >> 4)) plan.a_desc[s][t] = tap_desc(plan.a_desc[s][t] & 0xFFFFu, 2 * PLANE >> 4);
 }
 
 extern "C" int mvster_conv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
@@ -892,15 +942,17 @@ extern "C" int mvster_conv_tc3_pb16(const void* x, const void* w_packed, const f
                    Cin, Cout, kd, k, stride_hw);
     MVSTER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)skip & 15) == 0,
                    "mvster_conv_tc3_pb16: pointers must be 16-byte aligned");
-    const int s = stride_hw;
+    const int s = stride_hw, NT = (flags & MVSTER_TC3_FP16X2) ? 2 : 1;
     CUtensorMap xm;
-    int rc = encode_pb16_map(&xm, x, B * D, H, W, Cin, s, "mvster_conv_tc3_pb16");
+    int rc = encode_pb16_map(&xm, x, B * D, H, W, Cin, s, NT, "mvster_conv_tc3_pb16");
     if (rc != MVSTER_OK) return rc;
     Plan plan;
     memset(&plan, 0, sizeof(plan));
     Args a;
     memset(&a, 0, sizeof(a));
     a.nslab = build_plan(Cin, kd, k, s, &plan, nullptr);
+    if (NT == 2 && Cin >= 16) widen_octet_lbo(plan, kd * (s == 2 ? 4 : 1) * ((Cin + 15) / 16));
+    a.overflow = NT == 2 ? tc3::g_overflow_flag : nullptr;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = (const float*)skip; a.y = (float*)y; a.scale = scale;
     a.out_pb16 = (flags & MVSTER_TC3_OUT_PB16) ? 1 : 0;
     a.D = D; a.Ho = (H - 1) / s + 1; a.Wo = (W - 1) / s + 1; a.cout = Cout; a.relu = flags & 1; a.sx = s;
@@ -912,9 +964,9 @@ extern "C" int mvster_conv_tc3_pb16(const void* x, const void* w_packed, const f
     const int sms = current_sm_count();
     cudaStream_t st = (cudaStream_t)stream;
     const int NC = Cout < 16 ? 16 : Cout;
-    if (NC == 16) return launch_pb<16>(xm, plan, a, total_tiles, sms, st);
-    if (NC == 32) return launch_pb<32>(xm, plan, a, total_tiles, sms, st);
-    return launch_pb<64>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 16) return launch_pb<16>(xm, plan, a, total_tiles, sms, st, NT);
+    if (NC == 32) return launch_pb<32>(xm, plan, a, total_tiles, sms, st, NT);
+    return launch_pb<64>(xm, plan, a, total_tiles, sms, st, NT);
 }
 
 extern "C" int mvster_deconv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
@@ -925,8 +977,9 @@ extern "C" int mvster_deconv_tc3_pb16(const void* x, const void* w_packed, const
     MVSTER_REQUIRE(mvster_deconv_tc3_supported(Cin, Cout, rows), "mvster_deconv_tc3_pb16: unsupported layer Cin=%d Cout=%d rows=%d", Cin, Cout, rows);
     MVSTER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)skip & 15) == 0,
                    "mvster_deconv_tc3_pb16: pointers must be 16-byte aligned");
+    const int NT = (flags & MVSTER_TC3_FP16X2) ? 2 : 1;
     CUtensorMap xm;
-    int rc = encode_pb16_map(&xm, x, B * D, H, W, Cin, 1, "mvster_deconv_tc3_pb16");
+    int rc = encode_pb16_map(&xm, x, B * D, H, W, Cin, 1, NT, "mvster_deconv_tc3_pb16");
     if (rc != MVSTER_OK) return rc;
     Plan plan;
     memset(&plan, 0, sizeof(plan));
@@ -935,10 +988,11 @@ extern "C" int mvster_deconv_tc3_pb16(const void* x, const void* w_packed, const
         Stage S;
         S.c0 = (short)(kc * 16); S.nq = 4; S.ox = -1; S.oy = -1; S.dz = 0; S.ntap = (short)ntap; S.slab0 = (short)(kc * ntap); S.pad = 0;
         plan.st[kc] = S;
-        for (int t = 0; t < ntap; ++t) plan.a_desc[kc][t] = tap_desc((t / 2 + 1) * HW_ + (t % 2 + 1), PLANE >> 4);  // halo (1 + dy, 1 + dx)
+        for (int t = 0; t < ntap; ++t) plan.a_desc[kc][t] = tap_desc((t / 2 + 1) * HW_ + (t % 2 + 1), NT * PLANE >> 4);  // halo (1 + dy, 1 + dx)
     }
     Args a;
     memset(&a, 0, sizeof(a));
+    a.overflow = NT == 2 ? tc3::g_overflow_flag : nullptr;
     a.w = (const uint8_t*)w_packed; a.bias = bias; a.skip = (const float*)skip; a.y = (float*)y; a.scale = scale;
     a.out_pb16 = (flags & MVSTER_TC3_OUT_PB16) ? 1 : 0;
     a.D = D; a.Ho = H; a.Wo = W; a.cout = Cout; a.relu = flags & 1; a.sx = 1; a.nstage = kch;
@@ -950,7 +1004,7 @@ extern "C" int mvster_deconv_tc3_pb16(const void* x, const void* w_packed, const
     const int sms = current_sm_count();
     cudaStream_t st = (cudaStream_t)stream;
     const int NC = a.ncls * Cout;
-    if (NC == 16) return launch_pb<16>(xm, plan, a, total_tiles, sms, st);
-    if (NC == 32) return launch_pb<32>(xm, plan, a, total_tiles, sms, st);
-    return launch_pb<64>(xm, plan, a, total_tiles, sms, st);
+    if (NC == 16) return launch_pb<16>(xm, plan, a, total_tiles, sms, st, NT);
+    if (NC == 32) return launch_pb<32>(xm, plan, a, total_tiles, sms, st, NT);
+    return launch_pb<64>(xm, plan, a, total_tiles, sms, st, NT);
 }

@@ -297,7 +297,8 @@ class InferenceEngine:
         key = (tuple(tuple(t.shape) for t in imgs), tuple(sorted((k, tuple(v.shape)) for k, v in proj_matrices.items())),
                tuple(depth_values.shape), self.weights_version, self._precision(net, "reg"),
                getattr(net, "fpn_backend", "torch"), self._precision(net, "fpn"),
-               getattr(net, "storage", "fp32"), getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"),
+               getattr(net, "storage", "fp32"), os.environ.get("MVSTER_REG_PACKED", "1"), os.environ.get("MVSTER_BF16_PACKED", "1"),
+               getattr(net, "overlap_stages", True), os.environ.get("MVSTER_SIDE_SMS", "0"), os.environ.get("MVSTER_MAIN_RESERVE", "48"),
                None if shard is None else (shard.first_view, shard.count, shard.parts, id(shard.group)),
                int(getattr(net, "graph_slot", 0)))
         entry = self._graphs.get(key)
@@ -371,7 +372,10 @@ class InferenceEngine:
         elif prec == "3xbf16":  # conv0..conv6 on the persistent tcgen05 kernel, three bf16 terms per operand (fp32-faithful)
             feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc3_blob"], kernel_gen=3)
         elif prec == "2xfp16":  # same kernel, two fp16 terms per operand (22-bit operands, 2/3 of the MMAs; |x| < 65504)
-            feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc3h_blob"], kernel_gen=3, split=2)
+            # MVSTER_REG_PACKED=0: fp32 activations between the layers, split into their fp16 terms by every consuming layer's
+            # converter warps (the round-1 form) instead of once by the producing epilogue
+            feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc3h_blob"], kernel_gen=3, split=2,
+                               packed=os.environ.get("MVSTER_REG_PACKED", "1") == "1")
         else:                   # 3x3x3 layers on tcgen05: "3xtf32" (fp32-faithful) or "tf32"
             feat8 = capi.reg2d(wts["blob"], cost, tc_blob=wts["tc2_blob"], npass=3 if prec == "3xtf32" else 1, kernel_gen=2)
         return capi.head(hypo, p.split_itv, feat8=feat8, prob_w=wts["prob_w"], prob_b=wts["prob_b"], inverse=inverse)

@@ -171,26 +171,58 @@ int deconv_run(const float* x, const void* w_packed, const float* scale, const f
     return 0;
 }
 
-// octet-planar bf16 [P][C/8][H][W][8]  <->  fp32 [P][H][W][C]
-std::vector<float> unpack_pb16(const void* x, long long P, int H, int W, int C) {
+unsigned f2h_sat(float f) {  // fp32 -> fp16 bits, round to nearest even, saturating (cvt.rn.satfinite.f16.f32)
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    const unsigned sign = (u >> 16) & 0x8000u;
+    u &= 0x7FFFFFFFu;
+    if (u > 0x7F800000u) return sign | 0x7FFFu;
+    if (u >= 0x477FF000u) return sign | 0x7BFFu;
+    if (u < 0x33000001u) return sign;
+    const int e = (int)(u >> 23) - 127;
+    unsigned m = (u & 0x7FFFFFu) | 0x800000u;
+    const int shift = e >= -14 ? 13 : 13 + (-14 - e);
+    const unsigned half = 1u << (shift - 1), rest = m & ((1u << shift) - 1);
+    m >>= shift;
+    if (rest > half || (rest == half && (m & 1u))) ++m;
+    const unsigned base = e >= -14 ? ((unsigned)(e + 15) << 10) - 0x400u : 0u;
+    return sign | (base + m);
+}
+
+// octet-planar 16-bit terms [P][C/8][NT][H][W][8]  <->  fp32 [P][H][W][C]; NT = 1: bf16, NT = 2: fp16 pair a1 + 2^-11 a2
+std::vector<float> unpack_pb16(const void* x, long long P, int H, int W, int C, int NT = 1) {
     const uint16_t* p = static_cast<const uint16_t*>(x);
     std::vector<float> out((size_t)P * H * W * C);
-    for (long long pl = 0; pl < P; ++pl)
-        for (int o = 0; o < C / 8; ++o)
-            for (long long px = 0; px < (long long)H * W; ++px)
-                for (int e = 0; e < 8; ++e) out[((size_t)pl * H * W + px) * C + o * 8 + e] = bf16_to_float(p[(((size_t)pl * (C / 8) + o) * H * W + px) * 8 + e]);
-    return out;
-}
-void pack_pb16(const std::vector<float>& v, void* y, long long P, int H, int W, int C) {
-    uint16_t* p = static_cast<uint16_t*>(y);
+    const size_t plane = (size_t)H * W * 8;
     for (long long pl = 0; pl < P; ++pl)
         for (int o = 0; o < C / 8; ++o)
             for (long long px = 0; px < (long long)H * W; ++px)
                 for (int e = 0; e < 8; ++e) {
-                    const float f = round_bf16(v[((size_t)pl * H * W + px) * C + o * 8 + e]);
-                    uint32_t u;
-                    std::memcpy(&u, &f, 4);
-                    p[(((size_t)pl * (C / 8) + o) * H * W + px) * 8 + e] = (uint16_t)(u >> 16);
+                    const size_t i = ((size_t)pl * (C / 8) + o) * NT * plane + (size_t)px * 8 + e;
+                    out[((size_t)pl * H * W + px) * C + o * 8 + e] =
+                        NT == 2 ? half_to_float(p[i]) + half_to_float(p[i + plane]) * (1.f / 2048.f) : bf16_to_float(p[i]);
+                }
+    return out;
+}
+void pack_pb16(const std::vector<float>& v, void* y, long long P, int H, int W, int C, int NT = 1) {
+    uint16_t* p = static_cast<uint16_t*>(y);
+    const size_t plane = (size_t)H * W * 8;
+    for (long long pl = 0; pl < P; ++pl)
+        for (int o = 0; o < C / 8; ++o)
+            for (long long px = 0; px < (long long)H * W; ++px)
+                for (int e = 0; e < 8; ++e) {
+                    const float val = v[((size_t)pl * H * W + px) * C + o * 8 + e];
+                    const size_t i = ((size_t)pl * (C / 8) + o) * NT * plane + (size_t)px * 8 + e;
+                    if (NT == 2) {
+                        const unsigned h1 = f2h_sat(val);
+                        p[i] = (uint16_t)h1;
+                        p[i + plane] = (uint16_t)f2h_sat((val - half_to_float((uint16_t)h1)) * 2048.f);
+                    } else {
+                        const float f = round_bf16(val);
+                        uint32_t u;
+                        std::memcpy(&u, &f, 4);
+                        p[i] = (uint16_t)(u >> 16);
+                    }
                 }
 }
 
@@ -202,6 +234,7 @@ int mvster_conv3d_tc2_f32(...) { return -2; }
 int mvster_pointwise_tc2_f32(...) { return -2; }
 void mvster_set_sm_budget(int) {}
 void mvster_tc3_set_overflow_flag(unsigned*) {}
+unsigned* mvster_tc3_overflow_flag(void) { return nullptr; }
 
 int mvster_conv_tc3_scaled_f32(const float* x, const void* w_packed, const float* scale, const float* bias, const float* skip,
                                float* y, int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,
@@ -233,15 +266,15 @@ int mvster_deconv_tc3_f32(const float* x, const void* w_packed, const float* bia
 int mvster_conv_tc3_pb16(const void* x, const void* w_packed, const float* scale, const float* bias, const void* skip, void* y,
                          int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int s, int flags, mvster_stream_t) {
     if (!x || !y || Cin < 8) return -1;
-    const int Ho = (H - 1) / s + 1, Wo = (W - 1) / s + 1;
+    const int Ho = (H - 1) / s + 1, Wo = (W - 1) / s + 1, NT = (flags & MVSTER_TC3_FP16X2) ? 2 : 1;
     const long long P = (long long)B * D;
-    const std::vector<float> xf = unpack_pb16(x, P, H, W, Cin);
+    const std::vector<float> xf = unpack_pb16(x, P, H, W, Cin, NT);
     std::vector<float> sf, yf((size_t)P * Ho * Wo * Cout);
-    if (skip) sf = unpack_pb16(skip, P, Ho, Wo, Cout);
+    if (skip) sf = unpack_pb16(skip, P, Ho, Wo, Cout, NT);
     const int rc = conv_run(xf.data(), w_packed, scale, bias, skip ? sf.data() : nullptr, yf.data(), B, D, H, W, Cin, Cout, kd, k, s,
-                            (flags & 1) | MVSTER_TC3_BF16X1, 0, 0);
+                            (flags & 1) | (NT == 2 ? MVSTER_TC3_FP16X2 : MVSTER_TC3_BF16X1), 0, 0);
     if (rc) return rc;
-    if (flags & MVSTER_TC3_OUT_PB16) pack_pb16(yf, y, P, Ho, Wo, Cout);
+    if (flags & MVSTER_TC3_OUT_PB16) pack_pb16(yf, y, P, Ho, Wo, Cout, NT);
     else std::memcpy(y, yf.data(), yf.size() * 4);
     return 0;
 }
@@ -249,16 +282,17 @@ int mvster_deconv_tc3_pb16(const void* x, const void* w_packed, const float* sca
                            int B, int D, int H, int W, int Cin, int Cout, int rows, int flags, mvster_stream_t) {
     if (!x || !y) return -1;
     const long long P = (long long)B * D;
-    const std::vector<float> xf = unpack_pb16(x, P, H, W, Cin);
+    const int NT = (flags & MVSTER_TC3_FP16X2) ? 2 : 1;
+    const std::vector<float> xf = unpack_pb16(x, P, H, W, Cin, NT);
     std::vector<float> sf, yf;
     // a rows = 0 / 1 launch writes only its own output rows: start from what the output buffer already holds
-    if (flags & MVSTER_TC3_OUT_PB16) yf = unpack_pb16(y, P, 2 * H, 2 * W, Cout);
+    if (flags & MVSTER_TC3_OUT_PB16) yf = unpack_pb16(y, P, 2 * H, 2 * W, Cout, NT);
     else yf.assign(static_cast<const float*>(y), static_cast<const float*>(y) + (size_t)P * 4 * H * W * Cout);
-    if (skip) sf = unpack_pb16(skip, P, 2 * H, 2 * W, Cout);
+    if (skip) sf = unpack_pb16(skip, P, 2 * H, 2 * W, Cout, NT);
     const int rc = deconv_run(xf.data(), w_packed, scale, bias, skip ? sf.data() : nullptr, yf.data(), B, D, H, W, Cin, Cout, rows,
-                              (flags & 1) | MVSTER_TC3_BF16X1);
+                              (flags & 1) | (NT == 2 ? MVSTER_TC3_FP16X2 : MVSTER_TC3_BF16X1));
     if (rc) return rc;
-    if (flags & MVSTER_TC3_OUT_PB16) pack_pb16(yf, y, P, 2 * H, 2 * W, Cout);
+    if (flags & MVSTER_TC3_OUT_PB16) pack_pb16(yf, y, P, 2 * H, 2 * W, Cout, NT);
     else std::memcpy(y, yf.data(), yf.size() * 4);
     return 0;
 }

@@ -113,6 +113,7 @@ inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c);
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 inline float __expf(float a) { return std::exp(a); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return std::atomic_ref<unsigned>(*p).fetch_or(v, std::memory_order_relaxed); }
 inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 
 namespace emu {

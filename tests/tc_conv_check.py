@@ -7,6 +7,7 @@ trap or a barrier deadlock in a tensor-core kernel cannot take the rest of the s
     python tests/tc_conv_check.py v3 CIN COUT KD K STRIDE B D H W [skip] [norelu] [h16 | b16]   (h16: two-fp16-term arithmetic;
     python tests/tc_conv_check.py d3 CIN COUT B D H W [skip] [h16 | b16]                         b16: one bf16 term + per-channel scale)
     ... b16 p16 / b16 p16f: packed bf16 operands (mvster_conv_tc3_pb16: x and skip octet-planar bf16), output packed bf16 / fp32
+    ... h16 p16 / h16 p16f: packed fp16-pair operands (x and skip as (a1, a2) planes), output packed / fp32
 """
 import json
 import sys
@@ -89,18 +90,19 @@ def v3_main():
     wp = packing.pack_tc3_weights(w, kd, k, stride, split).to(dev)
     packed, packed_out = "p16" in sys.argv or "p16f" in sys.argv, "p16" in sys.argv
     extra = {}
-    if packed:  # packed operands: the skip tensor is bf16 too
-        assert b16
-        if skip is not None:
+    if packed:  # packed operands: the skip tensor is packed too (bf16: rounded; fp16 pair: 22 bits)
+        assert b16 or split == 2
+        pack, unpack = (capi.to_pb16, capi.from_pb16) if b16 else (capi.to_ph16, capi.from_ph16)
+        if skip is not None and b16:
             want = want - skip.double() + bf16_round(skip).double()
-        xp, sp = capi.to_pb16(x), None if skip is None else capi.to_pb16(skip)
+        xp, sp = pack(x), None if skip is None else pack(skip)
         raw = lambda: capi.conv_tc3_pb16(xp, wp, bias, cout, kd, k, stride, relu, skip=sp, scale=ch_scale, out_pb16=packed_out)
-        run = (lambda: capi.from_pb16(raw())) if packed_out else raw
+        run = (lambda: unpack(raw())) if packed_out else raw
     else:
         run = lambda: capi.conv_tc3(x, wp, bias, cout, kd, k, stride, relu, skip=skip, split=split, scale=ch_scale)
     got = run()
     torch.cuda.synchronize()
-    if packed_out:  # the stored output is rounded to bf16: equal to the rounded truth except where fp32 noise flips a rounding
+    if packed_out and b16:  # the stored output is rounded to bf16: equal to the rounded truth except where fp32 noise flips a rounding
         extra["flip_frac"] = (got.double() != bf16_round(want.float()).double()).double().mean().item()
         want = bf16_round(want.float()).double()
     err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()
@@ -138,19 +140,21 @@ def d3_main():
     packed, packed_out = "p16" in sys.argv or "p16f" in sys.argv, "p16" in sys.argv
     extra = {}
     if packed:
-        assert b16
-        if skip is not None:
+        assert b16 or split == 2
+        pack, unpack = (capi.to_pb16, capi.from_pb16) if b16 else (capi.to_ph16, capi.from_ph16)
+        if skip is not None and b16:
             want = want - skip.double() + bf16_round(skip).double()
-        xp, sp = capi.to_pb16(x), None if skip is None else capi.to_pb16(skip)
-        shape, dt = ((B, D, cout // 8, 2 * H, 2 * W, 8), torch.bfloat16) if packed_out else ((B, D, 2 * H, 2 * W, cout), torch.float32)
+        xp, sp = pack(x), None if skip is None else pack(skip)
+        pshape, pdt = capi._packed_out(B, D, cout, 2 * H, 2 * W, 1 if b16 else 2)
+        shape, dt = (pshape, pdt) if packed_out else ((B, D, 2 * H, 2 * W, cout), torch.float32)
         buf = torch.full(shape, float("nan"), device=dev, dtype=dt)
-        wps = [packing.pack_tc3_deconv_weights(w, r_, 1).to(dev) for r_ in ((-1,) if 4 * cout <= 64 else (0, 1))]
+        wps = [packing.pack_tc3_deconv_weights(w, r_, split).to(dev) for r_ in ((-1,) if 4 * cout <= 64 else (0, 1))]
 
         def raw():
             for r_, wp_ in zip((-1,) if 4 * cout <= 64 else (0, 1), wps):
                 capi.deconv_tc3_pb16(xp, wp_, bias, cout, r_, True, skip=sp, scale=ch_scale, out_pb16=packed_out, out=buf)
             return buf
-        run = (lambda: capi.from_pb16(raw())) if packed_out else raw
+        run = (lambda: unpack(raw())) if packed_out else raw
     elif 4 * cout <= 64:
         wp = packing.pack_tc3_deconv_weights(w, -1, split).to(dev)
         run = lambda: capi.deconv_tc3(x, wp, bias, cout, -1, True, skip=skip, split=split, scale=ch_scale)
@@ -163,7 +167,7 @@ def d3_main():
             return capi.deconv_tc3(x, wp1, bias, cout, 1, True, skip=skip, out=buf, split=split, scale=ch_scale)
     got = run()
     torch.cuda.synchronize()
-    if packed_out:
+    if packed_out and b16:
         extra["flip_frac"] = (got.double() != bf16_round(want.float()).double()).double().mean().item()
         want = bf16_round(want.float()).double()
     err, scale = (got.double() - want).abs().max().item(), want.abs().max().item()

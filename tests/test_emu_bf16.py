@@ -120,12 +120,33 @@ def test_packed_and_container_bf16_reg2d_agree_on_cpu(emu):
     assert torch.isfinite(a).all() and torch.equal(a, b)
 
 
+def test_packed_fp16_pair_reg2d_on_cpu(emu):
+    """mvster_reg2d_tc3_ex_f32 with MVSTER_REG2D_PACKED (conv0 kernel writing the fp16 pair as compiled source, every later layer
+    through the decoded slab streams on packed (a1, a2) planes) against the unpacked form and the oracle."""
+    k, D, H, W = 3, 4, 16, 24
+    sd, G, cost, hypo = reg2d_case(k, D, H, W, 31)
+    cost = cost * 3 + torch.randn_like(cost) * 0.01  # not bf16-valued
+    with torch.no_grad():
+        want = oracle.depth_head(oracle.reg2d_logits(sd, f"reg.{k}", cost), hypo, k, 0.5, True)
+    packed = packing.pack_reg2d(sd, f"reg.{k}", capi.reg2d_layer_table(G))
+    cl = cost.permute(0, 2, 3, 4, 1).contiguous()
+    a = capi.reg2d(packed["blob"], cl, tc_blob=packed["tc3h_blob"], kernel_gen=3, split=2, packed=True)
+    b = capi.reg2d(packed["blob"], cl, tc_blob=packed["tc3h_blob"], kernel_gen=3, split=2, packed=False)
+    assert torch.isfinite(a).all() and (a - b).abs().max().item() <= 2e-6 * b.abs().max().item()
+    h = capi.head(hypo, 0.5, feat8=a, prob_w=packed["prob_w"], prob_b=packed["prob_b"])
+    assert (h["attn_weight"] - want["attn_weight"]).abs().max().item() < 2e-5
+
+
 def test_pb16_layout_helpers_round_trip():
     x = torch.randn(2, 3, 5, 7, 16)
     p = capi.to_pb16(x)
     assert p.shape == (2, 3, 2, 5, 7, 8) and p.dtype == torch.bfloat16
     assert torch.equal(capi.from_pb16(p), x.to(torch.bfloat16).float())
     assert torch.equal(p[1, 2, 1, 4, 6], x[1, 2, 4, 6, 8:].to(torch.bfloat16))
+    h = capi.to_ph16(x * 50)
+    assert h.shape == (2, 3, 2, 2, 5, 7, 8) and h.dtype == torch.float16
+    assert torch.equal(h[1, 2, 1, 0, 4, 6], (x * 50)[1, 2, 4, 6, 8:].half())
+    assert (capi.from_ph16(h) - x * 50).abs().max().item() <= 2.0 ** -21 * (x * 50).abs().max().item()
 
 
 @pytest.mark.parametrize("split", [2, 3])

@@ -65,6 +65,20 @@ CASES = [  # generation cin cout kd B D H W npass [flags]
     "d3 32 16 2 2 16 16 h16",
     "d3 64 32 1 4 8 10 skip h16",
     "d3 16 8 1 4 256 320 skip h16",
+    # packed fp16-pair operands (mvster_conv_tc3_pb16 with MVSTER_TC3_FP16X2: x and skip as (a1, a2) planes in the operand's own
+    # order, TMA straight into the operand ring, no converter warps); p16f = fp32 output, p16 = packed output (split by the epilogue)
+    "v3 16 16 3 3 1 1 8 24 40 skip h16 p16f",   # depth taps, ragged tiles, 4-D merged map
+    "v3 8 16 1 3 2 1 4 64 80 h16 p16f",         # conv1: stride 2 (5-D map with element strides), one octet, two taps per MMA
+    "v3 16 32 1 3 2 1 4 30 44 h16 p16",         # conv3, odd output size
+    "v3 32 64 1 3 2 2 2 32 32 h16 p16",         # conv5
+    "v3 32 32 3 3 1 2 4 16 16 norelu h16 p16",  # two channel chunks, batch 2
+    "v3 64 64 3 3 1 1 4 64 80 skip h16 p16",    # conv6
+    "v3 16 16 3 3 1 1 4 256 320 h16 p16",       # conv2 at cfg2 stage 4
+    "v3 32 32 3 3 1 1 4 128 160 skip h16 p16",  # conv4 (streamed weights)
+    "d3 16 8 1 2 24 40 skip h16 p16f",          # conv11: packed skip, fp32 out
+    "d3 32 16 2 2 16 16 skip h16 p16",          # conv9
+    "d3 64 32 1 4 8 10 skip h16 p16",           # conv7: two launches into one packed output
+    "d3 16 8 1 4 256 320 skip h16 p16f",        # conv11 at cfg2 stage 4
     "reg2dv2 8 1 8 64 80 3",            # whole reg2d U-Net, stage-1 shape of cfg2, 3xTF32
     "reg2dv2 4 1 4 512 640 3",          # stage-4 shape of cfg2 (1.31 M voxels)
     "reg2dv2 4 1 4 128 160 1",          # plain TF32

@@ -124,6 +124,26 @@ def test_packed_and_container_bf16_reg2d_are_the_same_arithmetic(k, D, H, W):
     assert torch.isfinite(a).all() and torch.equal(a, b), (a - b).abs().max().item()
 
 
+@pytest.mark.parametrize("k,D,H,W", [(0, 8, 8, 8), (3, 4, 16, 8), (2, 4, 24, 16), (3, 4, 64, 80), (1, 8, 40, 56), (3, 4, 256, 320)])
+def test_packed_fp16_pair_reg2d_equals_the_unpacked_form(k, D, H, W):
+    """The fp32-faithful default regulariser (two fp16 terms per operand) with PACKED activations between the layers - the producing
+    epilogue stores the next layer's operand terms (a1, a2) - against the form whose consumers split fp32 activations themselves:
+    same products; only the skip sums see their addend to 22 instead of 24 bits."""
+    sd = build_model(SHIPPED, 5).state_dict()
+    G = SHIPPED["group_cor_dim"][k]
+    rng = np.random.RandomState(200 + k)
+    cost = torch.from_numpy((rng.randn(1, D, H, W, G) * 0.3).astype(np.float32)).cuda()
+    packed = {n: t.cuda() for n, t in packing.pack_reg2d(sd, f"reg.{k}", capi.reg2d_layer_table(G)).items()}
+    a = capi.reg2d(packed["blob"], cost, tc_blob=packed["tc3h_blob"], kernel_gen=3, split=2, packed=True)
+    b = capi.reg2d(packed["blob"], cost, tc_blob=packed["tc3h_blob"], kernel_gen=3, split=2, packed=False)
+    exact = capi.reg2d(packed["blob"], cost)  # every layer in exact fp32 on the CUDA cores
+    torch.cuda.synchronize()
+    scale = exact.abs().max().item()
+    assert torch.isfinite(a).all()
+    assert (a - b).abs().max().item() <= 2e-6 * scale, (a - b).abs().max().item() / scale
+    assert (a - exact).abs().max().item() <= 2e-5 * scale, (a - exact).abs().max().item() / scale
+
+
 @pytest.mark.parametrize("k,D,H,W", [(0, 8, 8, 8), (3, 4, 16, 8), (2, 4, 24, 16), (3, 4, 64, 80)])
 def test_bf16_reg2d_and_head_match_oracle(k, D, H, W):
     sd = build_model(SHIPPED, 5).state_dict()
