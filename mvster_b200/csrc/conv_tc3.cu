@@ -99,7 +99,15 @@ struct Cfg {
     static_assert(!PB || NS <= 2, "packed operands: one bf16 term or the fp16 pair");
     static constexpr int TMAX = NC > 64 ? 1 : 64 / NC;      // tiles accumulated side by side: 3*NC*TMAX <= 240 TMEM columns per set
     static constexpr int NF = PB ? 0 : (NC <= 32 ? MVSTER_TC3_NF_SMALL : 4);  // fp32 staging ring (TMA boxes in flight); none with packed operands
-    static constexpr int NA = PB ? (NS == 1 ? 16 : 10) : (NC >= 64 ? 6 : 8); // 16-bit operand ring (tile-stages)
+    // 16-bit operand ring (tile-stages).  Packed operands: the ring is what TMA has in flight, and a box takes ~2.3 us to land
+    // (tools/tma_microbench.cu) while a group's MMAs hold up to TMAX slots - MVSTER_TC3_DEEP_RING=1 (A/B builds) deepens it where
+    // the layer's weights still fit next to it
+#ifndef MVSTER_TC3_DEEP_RING
+#define MVSTER_TC3_DEEP_RING 0
+#endif
+    static constexpr int NA_PB = NS == 1 ? (MVSTER_TC3_DEEP_RING && NC <= 32 ? 24 : 16)
+                                         : (MVSTER_TC3_DEEP_RING ? (NC == 16 ? 16 : NC == 32 ? 12 : 10) : 10);
+    static constexpr int NA = PB ? NA_PB : (NC >= 64 ? 6 : 8);
     static constexpr int A_BYTES = NS * A_SPLIT;            // a1 | a2 | a3   (NS = 2: a1 | a2)
     static constexpr int B_BYTES = 96 * NC;                 // one (stage, tap) weight slab: [2 K-halves][3*NC rows][8 x 16 bit]
     static constexpr int BAR_BYTES = 1024;                  // mbarriers + TMEM slot
@@ -671,8 +679,12 @@ static int launch_ns(const CUtensorMap& xm, const Plan& plan, Args& a, long long
     // weights resident in shared memory when the whole layer fits next to the rings (MVSTER_TC3_STREAM=1 forces the ring)
     static const bool force_stream = getenv("MVSTER_TC3_STREAM") && atoi(getenv("MVSTER_TC3_STREAM")) != 0;
     a.resident = !force_stream && a.nslab > 0 && C::SMEM_FIXED + a.nslab * C::B_BYTES <= C::SMEM_MAX;
-    const int smem = C::SMEM_FIXED + (a.resident ? a.nslab : NB) * C::B_BYTES;
     const int grid = a.total_groups < sms ? a.total_groups : sms;
+    // MVSTER_TC3_STREAM_SMALL=1 (A/B): a launch whose CTAs each process ONE group reuses no slab, and the resident form makes its
+    // first MMA wait for the whole layer's weights (up to 110 KB per CTA); streamed, the first MMA starts after the first slab
+    static const bool stream_small = getenv("MVSTER_TC3_STREAM_SMALL") && atoi(getenv("MVSTER_TC3_STREAM_SMALL")) != 0;
+    if (stream_small && a.total_groups <= sms) a.resident = 0;
+    const int smem = C::SMEM_FIXED + (a.resident ? a.nslab : NB) * C::B_BYTES;
     // (Programmatic dependent launch between consecutive convolutions - griddepcontrol.launch_dependents at the top, .wait before
     // the first activation load and the epilogue - was measured and removed: -60 us (3.4 %) per step with one stream, but with
     // the two-stream forward the replayed graph stalled for 7-100 ms every few steps; profiles/r02_pdl.md.)
