@@ -797,6 +797,21 @@ def main():
         ms, best = _time_forward(step_resident, 10, flush)
         model.use_cuda_graph = graphed
         extra["no_cuda_graph"] = {"ms_per_step": ms, "min_ms": best, "value": B / (ms * 1e-3)}
+        try:  # throughput with two frames per forward (batch 2 in ONE graph): the latency-bound early stages do twice the work per launch
+            i2, p2, d2 = synth.make_inputs(2, NV, H, W, seed=0)
+            i2, p2, d2 = [t.to(dev) for t in i2], {k: v.to(dev) for k, v in p2.items()}, d2.to(dev)
+
+            def fwd2():
+                with torch.no_grad():
+                    return model(i2, p2, d2)
+            ms2, best2 = _time_forward(fwd2, 10, flush)
+            extra["batch2"] = {"ms_per_step": ms2, "min_ms": best2, "value": 2.0 / (ms2 * 1e-3), "unit": UNIT,
+                               "note": "informational: two frames per forward; the headline stays one frame per forward (the reference's test_mvs4.py batch size)"}
+            del i2, p2, d2
+            model._engines[dev.index]._graphs.clear()
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001
+            extra["batch2"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
         try:  # informational: a failure here must not take the headline down with it
             extra["bf16_storage"] = bf16_storage_leg(model, dev, flush, ref_out, bf16_inputs)
         except Exception as exc:  # noqa: BLE001
