@@ -363,7 +363,9 @@ static int reg2d_packed_h16(const float* blob, const void* tc3_blob, const float
 extern "C" int mvster_reg2d_tc3_ex_f32(const float* blob, const void* tc3_blob, const float* cost, float* feat8, float* ws,
                                        int B, int G, int D, int H, int W, int flags, mvster_stream_t stream) {
     MVSTER_REQUIRE(tc3_blob, "mvster_reg2d_tc3_f32: tc3_blob is null");
-    if ((flags & MVSTER_TC3_FP16X2) && (flags & MVSTER_REG2D_PACKED) && (G == 4 || G == 8))
+    // packed form: needs the four-voxel conv0 kernel (G in {4, 8}, 32-bit quad index); anything else takes the unpacked chain
+    if ((flags & MVSTER_TC3_FP16X2) && (flags & MVSTER_REG2D_PACKED) && (G == 4 || G == 8) && W % 4 == 0 &&
+        (long long)B * D * H * (W / 4) < (1ll << 31))
         return reg2d_packed_h16(blob, tc3_blob, cost, feat8, ws, B, G, D, H, W, stream);
     // npass carries the arithmetic of the generation-3 layers: 3 = three bf16 terms, 2 = two fp16 terms
     return reg2d_run(blob, (const float*)tc3_blob, (flags & MVSTER_TC3_FP16X2) ? 2 : 3, 3, cost, feat8, ws, B, G, D, H, W, stream);
