@@ -7,7 +7,9 @@ with the AddressSanitizer build so that any out-of-bounds access at an odd shape
 Part 1: every default-off kernel variant (gather 2 / 3, merge 2 / 3, four-pixel stem, four-voxel conv0) against the default
 kernel at random sizes (ragged and tiny ones included).  Part 2: the warp + ET forward (library's choice of kernel) and the
 backward kernel against the oracle / autograd through the oracle at random channel configurations, view counts, baselines
-and hypothesis ranges."""
+and hypothesis ranges.  Part 3 (round 2): the bf16-storage kernels - cast, bf16 warp + ET (tiled / window, natural and
+interleaved channels) against the oracle on bf16-valued features - at random shapes (the regulariser's conv0 kernel with its
+bf16 / packed fp16-pair stores has no entry point of its own: tests/test_emu_bf16.py drives it through the reg2d entry points)."""
 import os
 import sys
 from pathlib import Path
@@ -107,8 +109,37 @@ def warp_et(iters, rng):
     return worst_f, worst_b
 
 
+def bf16_storage(iters, rng):
+    q = lambda x: x.to(torch.bfloat16).float()
+    worst_eq = 1.0
+    cfgs = [(64, 8, 8), (32, 8, 8), (16, 4, 4), (8, 4, 4)]
+    for it in range(iters):
+        n = int(rng.randint(1, 300))
+        x = t(rng.randn(n) * 10 ** rng.uniform(-3, 3, n))
+        assert torch.equal(capi.cast_bf16(x).view(torch.int16), x.to(torch.bfloat16).view(torch.int16)), ("cast", n)
+        C_, G, D = cfgs[it % len(cfgs)]
+        B, nv, H, W = int(rng.randint(1, 3)), int(rng.randint(2, 5)), int(rng.randint(2, 9)), int(rng.randint(2, 40))
+        step = float(rng.choice([0.3, 1.0, 5.0]))
+        feats = [q(t(rng.randn(B, C_, H, W))) for _ in range(nv)]
+        cams = synth.stage_projections(synth.arc_cameras(nv, H, W, step), B, num_stage=1)["stage1"]
+        base = t(np.exp(rng.uniform(np.log(300.0), np.log(2e3), (B, 1, H, W))))
+        hypo = (base * torch.linspace(1.0, float(rng.choice([0.999, 0.97, 0.5])), D).reshape(1, D, 1, 1)).contiguous()
+        want = q(oracle.et_aggregate(feats, cams, hypo, True, G, 2.0))
+        nh = [f.permute(0, 2, 3, 1).contiguous() for f in feats]
+        for window, il in ((None, False), (False, False), (True, C_ // G in (2, 4))):
+            perm = capi.interleave_perm(C_, G) if il else list(range(C_))
+            fb = [f[..., perm].contiguous().to(torch.bfloat16) for f in nh]
+            got = capi.et_fuse_bf16(fb[0], fb[1:], capi.pose(cams), hypo, G, 2.0, window=window, interleaved=il).float().permute(0, 4, 1, 2, 3)
+            scale = max(want.abs().max().item(), 1e-6)
+            assert torch.isfinite(got).all() and (got - want).abs().max().item() <= (2.0 ** -7 + 1e-3) * scale, (C_, G, D, B, nv, H, W, step, window, il)
+            worst_eq = min(worst_eq, (got == want).float().mean().item())
+    return worst_eq
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = np.random.RandomState(2024)
     print("variants vs default kernels, worst deviation / max:", variants(n, rng))
     print("warp + ET forward / backward vs oracle, worst deviation / max:", warp_et(n, rng))
+    print("bf16 storage: cast bit-exact, warp + ET within one bf16 spacing of the rounded oracle; smallest fraction of exactly equal values:",
+          bf16_storage(n, rng))
