@@ -233,8 +233,9 @@ int mvster_conv3d_tc_f32(...) { return -2; }
 int mvster_conv3d_tc2_f32(...) { return -2; }
 int mvster_pointwise_tc2_f32(...) { return -2; }
 void mvster_set_sm_budget(int) {}
-void mvster_tc3_set_overflow_flag(unsigned*) {}
-unsigned* mvster_tc3_overflow_flag(void) { return nullptr; }
+static thread_local unsigned* g_flag = nullptr;
+void mvster_tc3_set_overflow_flag(unsigned* p) { g_flag = p; }
+unsigned* mvster_tc3_overflow_flag(void) { return g_flag; }
 
 int mvster_conv_tc3_scaled_f32(const float* x, const void* w_packed, const float* scale, const float* bias, const float* skip,
                                float* y, int B, int D, int H, int W, int Cin, int Cout, int kd, int k, int stride_hw, int relu,

@@ -137,6 +137,24 @@ def test_packed_fp16_pair_reg2d_on_cpu(emu):
     assert (h["attn_weight"] - want["attn_weight"]).abs().max().item() < 2e-5
 
 
+def test_packed_conv0_reports_values_outside_the_fp16_terms_on_cpu(emu):
+    """The range check of the two-fp16-term arithmetic moves with the split: in the packed form conv0 (and, on the GPU, every
+    epilogue) checks what it STORES.  Here: the conv0 kernel as compiled source, flag word registered like the engine does."""
+    import ctypes as C
+    sd, G, cost, hypo = reg2d_case(3, 4, 8, 16, 41)
+    packed = packing.pack_reg2d(sd, "reg.3", capi.reg2d_layer_table(G))
+    flag = torch.zeros(1, dtype=torch.int32)
+    lib = emu
+    for scale, want in ((1.0, 0), (1.0e7, 1)):
+        flag.zero_()
+        lib.mvster_tc3_set_overflow_flag(C.c_void_p(flag.data_ptr()))
+        try:
+            capi.reg2d(packed["blob"], (cost * scale).permute(0, 2, 3, 4, 1).contiguous(), tc_blob=packed["tc3h_blob"], kernel_gen=3, split=2, packed=True)
+        finally:
+            lib.mvster_tc3_set_overflow_flag(None)
+        assert int(flag.item()) == want, (scale, int(flag.item()))
+
+
 def test_pb16_layout_helpers_round_trip():
     x = torch.randn(2, 3, 5, 7, 16)
     p = capi.to_pb16(x)

@@ -144,6 +144,39 @@ def test_packed_fp16_pair_reg2d_equals_the_unpacked_form(k, D, H, W):
     assert (a - exact).abs().max().item() <= 2e-5 * scale, (a - exact).abs().max().item() / scale
 
 
+def test_packed_fp16_pair_layers_report_values_outside_the_fp16_terms():
+    """The range check of the two-fp16-term arithmetic (mvster_tc3_set_overflow_flag) in the packed form: the producer of a packed
+    tensor checks what it stores - conv0 (CUDA cores) and every tensor-core epilogue."""
+    from mvster_b200 import _lib
+    lib = _lib.load()
+    sd = build_model(SHIPPED, 5).state_dict()
+    packed = {n: t.cuda() for n, t in packing.pack_reg2d(sd, "reg.3", capi.reg2d_layer_table(4)).items()}
+    rng = np.random.RandomState(7)
+    cost = torch.from_numpy((rng.randn(1, 4, 32, 48, 4) * 0.3).astype(np.float32)).cuda()
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def run(fn):
+        flag.zero_()
+        lib.mvster_tc3_set_overflow_flag(flag.data_ptr())
+        try:
+            fn()
+            torch.cuda.synchronize()
+        finally:
+            lib.mvster_tc3_set_overflow_flag(None)
+        return int(flag.item())
+
+    reg = lambda c: capi.reg2d(packed["blob"], c, tc_blob=packed["tc3h_blob"], kernel_gen=3, split=2, packed=True)
+    assert run(lambda: reg(cost)) == 0
+    assert run(lambda: reg(cost * 1.0e7)) == 1            # conv0's output leaves the range
+    # one tensor-core layer alone: in-range input, weights that push the stored output beyond 65504
+    x = capi.to_ph16(torch.full((1, 2, 16, 16, 16), 100.0, device="cuda"))
+    w_big = packing.pack_tc3_weights(torch.full((9, 16, 16), 10.0), 1, 3, 1, 2).cuda()   # 144 * 100 * 10 = 144 000
+    w_ok = packing.pack_tc3_weights(torch.full((9, 16, 16), 0.01), 1, 3, 1, 2).cuda()
+    assert run(lambda: capi.conv_tc3_pb16(x, w_ok, None, 16, 1, 3, 1, True)) == 0
+    assert run(lambda: capi.conv_tc3_pb16(x, w_big, None, 16, 1, 3, 1, True)) == 1
+    assert run(lambda: capi.conv_tc3_pb16(x, w_big, None, 16, 1, 3, 1, True, out_pb16=False)) == 0  # fp32 output: nothing is split
+
+
 @pytest.mark.parametrize("k,D,H,W", [(0, 8, 8, 8), (3, 4, 16, 8), (2, 4, 24, 16), (3, 4, 64, 80)])
 def test_bf16_reg2d_and_head_match_oracle(k, D, H, W):
     sd = build_model(SHIPPED, 5).state_dict()
