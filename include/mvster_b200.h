@@ -359,6 +359,17 @@ int mvster_upsample_bilinear_f32(const float* in, float* out, int B, int H, int 
 int mvster_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W,
                             mvster_stream_t stream);
 
+/* ---- training loss ----------------------------------------------------------- */
+/* models/mvs4net_utils.py:1096-1142 `sinkhorn` (the optimal-transport term of MVS4net_loss, MVS4Net.py:149), forward and backward
+ * fused: one thread per pixel runs the `iters` log-domain Sinkhorn iterations on its own D x D (continuous != 0: D x (D+1)) ground
+ * cost, writes the pixel's transport cost sum_ij T_ij cost_ij into loss_px [B][H][W] (0 where mask == 0) and, if grad_attn is not
+ * NULL, d loss_px / d attn into grad_attn [B][D][H][W] by reverse-mode differentiation of its iteration history (0 where
+ * mask == 0).  The loss of the reference is the mean of loss_px over the masked pixels.  gt_depth [B][H][W], hypo / attn
+ * [B][D][H][W], mask [B][H][W] as bytes (torch.bool).  D in {4, 8}; 0 <= iters <= 32. */
+int mvster_sinkhorn_f32(const float* gt_depth, const float* hypo, const float* attn, const unsigned char* mask,
+                        float* loss_px, float* grad_attn, int B, int D, int H, int W, int iters, float eps, int continuous,
+                        mvster_stream_t stream);
+
 /* ---- geometric-consistency filter (after the forward) ---------------------- */
 /* test_mvs4.py:271-328 (reproject_with_depth + check_geometric_consistency) for one (reference, source) pair, and the
  * accumulation of filter_depth :362-378.  depth_ref [H][W], depth_src [Hs][Ws] (device, fp32).  mats: HOST array of 60 doubles =

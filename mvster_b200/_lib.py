@@ -72,6 +72,7 @@ SIGNATURES = {
     "mvster_fpn_merge_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "mvster_pointwise_tc2_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "mvster_fpn_out4_gather_f32": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "mvster_sinkhorn_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
     "mvster_geo_consistency_f32": (_i, [_p, _p, C.POINTER(C.c_double), _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p]),
     "mvster_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _p]),
     "mvster_head_ex_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),

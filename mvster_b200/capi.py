@@ -613,3 +613,19 @@ def upsample_bilinear(x: Tensor, factor: int) -> Tensor:
     _lib.check(_lib.load().mvster_upsample_bilinear_f32(_ptr(x), _ptr(out), B, H, W, factor, _stream()),
                "mvster_upsample_bilinear_f32")
     return out
+
+
+def sinkhorn(gt_depth: Tensor, hypo: Tensor, attn: Tensor, mask: Tensor, iters: int, eps: float, continuous: bool, want_grad: bool = True):
+    """mvster_sinkhorn_f32: per-pixel transport cost [B,H,W] (0 outside the mask) and, with ``want_grad``, its gradient w.r.t.
+    ``attn`` [B,D,H,W].  mask: torch.bool [B,H,W]."""
+    B, D, H, W = attn.shape
+    _chk(attn, "attn")
+    _chk(hypo, "hypo", (B, D, H, W))
+    _chk(gt_depth, "gt_depth", (B, H, W))
+    _chk(mask, "mask", (B, H, W), torch.bool)
+    loss_px = torch.empty((B, H, W), device=attn.device, dtype=torch.float32)
+    grad = torch.empty((B, D, H, W), device=attn.device, dtype=torch.float32) if want_grad else None
+    _lib.check(_lib.load().mvster_sinkhorn_f32(_ptr(gt_depth), _ptr(hypo), _ptr(attn), _ptr(mask), _ptr(loss_px), _ptr(grad), B, D, H, W,
+                                               int(iters), float(eps), int(bool(continuous)), _stream()), "mvster_sinkhorn_f32")
+    return loss_px, grad
+

@@ -1,6 +1,7 @@
-"""Training losses with the reference's signatures (models/MVS4Net.py:113-206) - plain PyTorch,
-not accelerated (training-only; they read ``depth``, ``hypo_depth``, ``attn_weight`` and
-``mono_depth`` from the per-stage output dicts)."""
+"""Training losses with the reference's signatures (models/MVS4Net.py:113-206) - plain PyTorch
+(training-only; they read ``depth``, ``hypo_depth``, ``attn_weight`` and ``mono_depth`` from the per-stage output
+dicts).  The optimal-transport term can run on the fused kernel of csrc/sinkhorn.cu (MVSTER_TRAIN_SINKHORN=1,
+mvster_b200/train_ops.py)."""
 from __future__ import annotations
 
 import torch
@@ -69,8 +70,12 @@ def _stage_terms(inputs, depth_gt_ms, mask_ms, kw):
             itv = (hypo[:, 2] - hypo[:, 1]).abs()
             miss = ((hypo - gt.unsqueeze(1)).abs() <= itv.unsqueeze(1)).sum(1) == 0
         oor.append(miss[mask].float().mean())
-        ot = sinkhorn(gt, hypo, attn, mask, iters=kw.get("ot_iter", 3), eps=kw.get("ot_eps", 1),
-                      continuous=kw.get("ot_continous", False))[1]
+        ot_args = dict(iters=kw.get("ot_iter", 3), eps=kw.get("ot_eps", 1), continuous=kw.get("ot_continous", False))
+        from . import train_ops  # the fused forward + backward kernel (opt-in, MVSTER_TRAIN_SINKHORN=1); else PyTorch ops
+        if train_ops.sinkhorn_enabled() and train_ops.sinkhorn_usable(attn, ot_args["iters"]):
+            ot = train_ops.sinkhorn_loss(gt, hypo, attn, mask, **ot_args)
+        else:
+            ot = sinkhorn(gt, hypo, attn, mask, **ot_args)[1]
         l1s.append(l1)
         ots.append(ot)
         total = total + lw[idx] * (l1w * l1 + otw * ot)

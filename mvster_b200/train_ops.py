@@ -84,3 +84,40 @@ def aggregate(features: Sequence[Tensor], cams: Tensor, hypo: Tensor, G: int, at
     nhwc = [f.permute(0, 2, 3, 1).contiguous() for f in features]
     cost = EtFuse.apply(pose, hypo, int(G), float(attn_temp), *nhwc)
     return cost.permute(0, 4, 1, 2, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# optimal-transport loss (mvs4net_utils.py:1096-1142), forward and backward in one launch (csrc/sinkhorn.cu)
+def sinkhorn_enabled() -> bool:
+    """MVSTER_TRAIN_SINKHORN=1 routes the OT term of MVS4net_loss / Blend_loss through the fused kernel (default 0: PyTorch ops - the
+    kernel is checked against gradients taken through the unmodified reference, tests/golden/sinkhorn.npz, but has not been timed
+    on a GPU yet)."""
+    return os.environ.get("MVSTER_TRAIN_SINKHORN", "0") == "1"
+
+
+def sinkhorn_usable(attn: Tensor, iters: int) -> bool:
+    return attn.is_cuda and attn.dtype == torch.float32 and attn.shape[1] in (4, 8) and 0 <= int(iters) <= 32
+
+
+class SinkhornLoss(torch.autograd.Function):
+    """Masked mean of the per-pixel transport cost; the gradient w.r.t. ``attn`` comes from the same launch."""
+
+    @staticmethod
+    def forward(ctx, attn: Tensor, gt: Tensor, hypo: Tensor, mask: Tensor, iters: int, eps: float, continuous: bool) -> Tensor:
+        with _on(attn.device):
+            loss_px, grad = capi.sinkhorn(gt.detach().contiguous().float(), hypo.detach().contiguous().float(), attn.detach().contiguous(),
+                                          mask.contiguous(), iters, eps, continuous, want_grad=attn.requires_grad)
+        count = mask.sum()
+        ctx.save_for_backward(grad, count)
+        return loss_px.sum() / count  # loss_px is 0 outside the mask; an empty mask gives NaN like the reference's mean of nothing
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        grad, count = ctx.saved_tensors
+        return (None if grad is None else grad * (g / count), None, None, None, None, None, None)
+
+
+def sinkhorn_loss(gt: Tensor, hypo: Tensor, attn: Tensor, mask: Tensor, iters: int, eps: float = 1.0, continuous: bool = False) -> Tensor:
+    """Differentiable drop-in for ``losses.sinkhorn(...)[1]``."""
+    return SinkhornLoss.apply(attn, gt, hypo, mask, int(iters), float(eps), bool(continuous))
+

@@ -11,7 +11,7 @@ CSRC = REPO / "mvster_b200" / "csrc"
 sys.path.insert(0, str(HERE))
 from transform import build_tree  # noqa: E402
 
-SOURCES = ["common.cu", "hypo_head.cu", "fusion.cu", "et_fuse.cu", "et_fuse_bwd.cu", "conv_simt.cu", "conv_simt_px2.cu", "fpn.cu"]
+SOURCES = ["common.cu", "hypo_head.cu", "fusion.cu", "et_fuse.cu", "et_fuse_bwd.cu", "conv_simt.cu", "conv_simt_px2.cu", "fpn.cu", "sinkhorn.cu"]
 HEADERS = ["et_args.cuh", "et_fuse_tiled.cuh", "et_fuse_win.cuh", "et_fuse_tma.cuh", "conv_tc3_plan.h"]
 FLAGS = ["-std=c++20", "-O1", "-ffp-contract=off", "-pthread", "-fPIC", "-w", "-x", "c++"]
 
