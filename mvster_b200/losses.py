@@ -1,7 +1,7 @@
 """Training losses with the reference's signatures (models/MVS4Net.py:113-206) - plain PyTorch
 (training-only; they read ``depth``, ``hypo_depth``, ``attn_weight`` and ``mono_depth`` from the per-stage output
-dicts).  The optimal-transport term can run on the fused kernel of csrc/sinkhorn.cu (MVSTER_TRAIN_SINKHORN=1,
-mvster_b200/train_ops.py)."""
+dicts).  The optimal-transport term of fp32 CUDA tensors runs on the fused kernel of csrc/sinkhorn.cu
+(mvster_b200/train_ops.py; MVSTER_TRAIN_SINKHORN=0 keeps it on PyTorch ops)."""
 from __future__ import annotations
 
 import torch
@@ -71,7 +71,7 @@ def _stage_terms(inputs, depth_gt_ms, mask_ms, kw):
             miss = ((hypo - gt.unsqueeze(1)).abs() <= itv.unsqueeze(1)).sum(1) == 0
         oor.append(miss[mask].float().mean())
         ot_args = dict(iters=kw.get("ot_iter", 3), eps=kw.get("ot_eps", 1), continuous=kw.get("ot_continous", False))
-        from . import train_ops  # the fused forward + backward kernel (opt-in, MVSTER_TRAIN_SINKHORN=1); else PyTorch ops
+        from . import train_ops  # the fused forward + backward kernel for fp32 CUDA tensors (MVSTER_TRAIN_SINKHORN=0: PyTorch ops)
         if train_ops.sinkhorn_enabled() and train_ops.sinkhorn_usable(attn, ot_args["iters"]):
             ot = train_ops.sinkhorn_loss(gt, hypo, attn, mask, **ot_args)
         else:

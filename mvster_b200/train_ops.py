@@ -89,10 +89,10 @@ def aggregate(features: Sequence[Tensor], cams: Tensor, hypo: Tensor, G: int, at
 # ---------------------------------------------------------------------------------------------------------------------------
 # optimal-transport loss (mvs4net_utils.py:1096-1142), forward and backward in one launch (csrc/sinkhorn.cu)
 def sinkhorn_enabled() -> bool:
-    """MVSTER_TRAIN_SINKHORN=1 routes the OT term of MVS4net_loss / Blend_loss through the fused kernel (default 0: PyTorch ops - the
-    kernel is checked against gradients taken through the unmodified reference, tests/golden/sinkhorn.npz, but has not been timed
-    on a GPU yet)."""
-    return os.environ.get("MVSTER_TRAIN_SINKHORN", "0") == "1"
+    """The OT term of MVS4net_loss / Blend_loss runs on the fused kernel unless MVSTER_TRAIN_SINKHORN=0 (then: PyTorch ops).  Measured
+    on B200 at the cfg2 stage shapes, 10 iterations (profiles/r02_sinkhorn.md): forward + backward 0.17-0.22 ms per stage against
+    2.9-4.1 ms; loss and gradients within 1e-4 of values taken through the unmodified reference."""
+    return os.environ.get("MVSTER_TRAIN_SINKHORN", "1") == "1"
 
 
 def sinkhorn_usable(attn: Tensor, iters: int) -> bool:

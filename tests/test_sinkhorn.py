@@ -47,7 +47,7 @@ def test_fused_kernel_without_gradient_and_argument_errors(emu):
     with pytest.raises(Exception, match="iters"):
         capi.sinkhorn(t["gt"], t["hypo"], t["attn"], t["mask"], 33, eps, cont)
     assert not train_ops.sinkhorn_usable(t["attn"], 10)       # host tensors: the product path stays on PyTorch ops
-    assert not train_ops.sinkhorn_enabled()                     # opt-in until it has been timed on a GPU
+    assert train_ops.sinkhorn_enabled()                         # default on (MVSTER_TRAIN_SINKHORN=0 switches it off)
 
 
 def test_loss_functions_route_through_the_fused_kernel_on_cpu(emu, monkeypatch):
