@@ -56,6 +56,9 @@ constexpr int NCONV = 256;                 // converter threads (8 warps: one wa
 constexpr int CTEAM = NCONV / 2;           // ... in two teams that take alternate tile-stages
 constexpr int THREADS = 96 + NCONV + 128;
 constexpr int NB = 10;
+#ifndef MVSTER_TC3_SKIP_DUMMY
+#define MVSTER_TC3_SKIP_DUMMY 0  // 1 (A/B builds, not yet run on a GPU): skip the MMA slots of tiles a shrunk group does not have
+#endif
 #ifndef MVSTER_TC3_NF_SMALL
 #define MVSTER_TC3_NF_SMALL 4   // fp32 staging boxes in flight for the N <= 32 layers (A/B builds: tools/tma_microbench.cu, profiles/r02_tma_microbench.md)
 #endif
@@ -361,7 +364,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant
                         // every tile slot of the group is issued, also past Tg (a ragged last group of a plane): alo[] then repeats
                         // tile 0's operands and the MMAs land in accumulator columns the epilogue never reads - straight-line code
 #pragma unroll
-                        for (int t = 0; t < C::TMAX; ++t) mma_tile<NC, NS, PB>(alo[t] + shift, bd, d0 + (uint32_t)(t * 3 * NC), accumulate);
+                        for (int t = 0; t < C::TMAX; ++t) {
+#if MVSTER_TC3_SKIP_DUMMY  // A/B build: do not issue the slots of tiles the group does not have (profiles/r02_packed_operands.md)
+                            if (t >= Tg) continue;
+#endif
+                            mma_tile<NC, NS, PB>(alo[t] + shift, bd, d0 + (uint32_t)(t * 3 * NC), accumulate);
+                        }
                         if constexpr (!RES) {
                             umma_commit(B_EMPTY(b_slot));
                             if (++b_slot == NB) { b_slot = 0; b_par ^= 1; }
